@@ -1,0 +1,163 @@
+/*
+ * pamg.h -- C ABI of libpamg_cuda.so: the B200 (sm_100a) implementation of the P1 DG
+ * transport/diffusion smoother / residual / multigrid hot path of P-A_multigrids.
+ *
+ * The reference (serial Fortran 90) has no operator / plugin / FFI boundary: smoother,
+ * get_residual, restrictor, prolongator and update_overlaps are procedures contained in or called
+ * from Semi_implicit_iterative (transport_tri_semi.F90:319-379, :407-889).  This header IS the
+ * boundary a Fortran host binds through ISO_C_BINDING (see INTEGRATION.md and
+ * p-a_multigrids_b200/host/pamg_iface.F90).  Conventions:
+ *   - plain pointers and sizes only; every entry returns int: 0 ok, <0 error
+ *     (mirrors ierr / errorflag out-arguments, Msh2Tri.F90:137, matrices.F90:1631);
+ *   - field layout at the boundary is the reference's column-major T(nloc=3, C, U), i.e. flat
+ *     0-based index ((un-1)*C + (str-1))*3 + (iloc-1)  ==  glob_no_semi-1 (matrices.F90:1496-1500);
+ *   - levels are 1-based like ilevel; level l has split s = n_split-l+1 and C = 4**s children
+ *     per parent (transport_tri_semi.F90:180,324);
+ *   - element / parent ids inside Neig are 1-based, 0 = domain boundary (Structures.F90:151);
+ *   - the library owns all device memory; fields stay resident in HBM between calls;
+ *   - one host thread per handle; there is NO CPU fallback: every compute entry needs a CUDA device.
+ */
+#ifndef PAMG_H
+#define PAMG_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAMG_OK 0
+#define PAMG_ERR_ARG (-1)
+#define PAMG_ERR_CUDA (-2)
+#define PAMG_ERR_STATE (-3)
+#define PAMG_ERR_IO (-4)
+#define PAMG_ERR_SINGULAR (-5) /* FINDInv errorflag = -1, matrices.F90:1665-1688 */
+#define PAMG_ERR_UNSUPPORTED (-6)
+
+/* Everything the reference hard-codes or passes as literal arguments (main.F90:46-47,
+ * transport_tri_semi.F90:117-140).  Switches select LITERAL (HEAD) or INTENDED behaviour where the
+ * reference is work in progress; nothing is "fixed" silently. */
+typedef struct pamg_params {
+  int32_t n_split;        /* transport_tri_semi.F90:118 */
+  int32_t multi_levels;   /* main.F90:46; must be <= n_split (:120-123) */
+  int32_t n_smooth;       /* main.F90:47 */
+  int32_t n_multigrid;    /* main.F90:46 */
+  int32_t n_coarse_smooth;/* 15 smoother calls on the coarsest level (:351) */
+  int32_t solver;         /* 1 Jacobi, 2 Richardson, 3 Gauss-Seidel (two-colour ordering on the GPU) */
+  int32_t face_terms;     /* 0: face loop body commented out as at HEAD (:619-688); 1: face block on */
+  int32_t literal_source; /* 1: get_RHS sums M*src while overwriting src (:456); 0: plain M*src */
+  int32_t transfer;       /* 0: restrictor/prolongator as written (splitting.F90:10-91); 1: P1 interpolation + transpose */
+  int32_t residual_sign;  /* +1: r = A x - b (:869);  -1: r = b - A x */
+  int32_t halo_rule;      /* 0: Dir/Nside reversal table (splitting.F90:1256-1391); 1: geometric pairing */
+  int32_t coarse_bc_zero; /* 1: homogeneous Dirichlet data on levels > 1; 0: sin(x+y) on every level (HEAD) */
+  double theta;           /* :117 (only theta = 1 is implemented, like the reference's literal) */
+  double dt;              /* :133  dt = CFL*dx */
+  double k;               /* :136 */
+  double omega;           /* :140 */
+  double u_x, u_y;        /* :208-212 uniform velocity */
+  double source_coef;     /* source = source_coef*sin(x+y); HEAD: -2k (:593) */
+} pamg_params;
+
+typedef struct pamg_handle pamg_handle;
+typedef struct pamg_mesh pamg_mesh;
+
+/* field ids: tracer(ilevel)%tnew/told/RHS/residuale (Structures.F90:185-188) and tnew_nonlin */
+enum { PAMG_TNEW = 0, PAMG_TOLD = 1, PAMG_RHS = 2, PAMG_RES = 3, PAMG_TNONLIN = 5 };
+
+const char* pamg_version(void);
+int pamg_device_count(int* n);               /* PAMG_ERR_CUDA when no CUDA driver/device is present */
+void pamg_default_params(pamg_params* p, int literal_head);
+
+/* ---- host mesh pipeline (replaces ReadMSH + CheckNeig all-pairs search + getNeigDataMesh,
+ *      Msh2Tri.F90:132-334,454-548,780-963, with an O(N) edge hash) ------------------------------ */
+int pamg_mesh_read_msh(const char* path, pamg_mesh** out);
+/* G right super-triangles (G/2 unit squares in a strip), each split kp times with the reference's own
+ * get_splitting numbering (Msh2Tri.F90:69-107) into 4**kp parents: SURVEY 8(d) synthetic input */
+int pamg_mesh_synthetic(int kp, int G, pamg_mesh** out);
+int pamg_mesh_from_arrays(int U, const double* X /* [U][3][2] */, const int32_t* region, pamg_mesh** out);
+int pamg_mesh_size(const pamg_mesh* m, int* U);
+/* any output pointer may be NULL.  X [U][3][2]; neig/fneig/dir [U][3]; region [U] */
+int pamg_mesh_get(const pamg_mesh* m, double* X, int32_t* neig, int32_t* fneig, int32_t* dir, int32_t* region);
+void pamg_mesh_free(pamg_mesh* m);
+
+/* ---- handle ------------------------------------------------------------------------------------ */
+int pamg_create(const pamg_params* p, int device, pamg_handle** out);
+void pamg_destroy(pamg_handle* h);
+const char* pamg_last_error(const pamg_handle* h);
+/* Mesh%X, Neig, fNeig, Dir (Structures.F90:143-170).  Builds per-parent geometry for every level
+ * (semi_tri_det_nlx_multigrid / semi_det_snlx_multigrid / get_d_center) and allocates the fields. */
+int pamg_set_parents(pamg_handle* h, int U, const double* X, const int32_t* neig, const int32_t* fneig,
+                     const int32_t* dir);
+/* distributed run (one process per GPU): the mesh is cut into nparts contiguous blocks of parents,
+ * part i owning [part_first[i], part_first[i+1]); this handle owns block my_part.  Faces cut by the
+ * partition exchange their halo strips over NCCL inside pamg_update_overlaps / pamg_smooth. */
+int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, const int32_t* neig,
+                               const int32_t* fneig, const int32_t* dir, int nparts, const int32_t* part_first,
+                               int my_part);
+int pamg_ndof(const pamg_handle* h, int level, int64_t* ndof);
+
+int pamg_upload_field(pamg_handle* h, int field, int level, const double* host);
+int pamg_download_field(pamg_handle* h, int field, int level, double* host);
+int pamg_fill_field(pamg_handle* h, int field, int level, double value);
+int pamg_copy_field(pamg_handle* h, int level, int dst_field, int src_field);
+int pamg_download_overlap(pamg_handle* h, int level, int old, double* host /* [U][3][2**s][3] */);
+int pamg_device_ptr(pamg_handle* h, int field, int level, void** dptr); /* for zero-copy interop */
+
+/* ---- the hot path ------------------------------------------------------------------------------ */
+/* update_overlaps (splitting.F90:1210-1397): halo strips from TNEW/TOLD of the level */
+int pamg_update_overlaps(pamg_handle* h, int level);
+/* level-1 RHS = (1/dt) M told + M src (get_RHS, transport_tri_semi.F90:452-464, theta = 1) */
+int pamg_build_rhs(pamg_handle* h);
+/* smoother (:543-722): nsweeps sweeps on TNONLIN; each sweep does TNEW <- TNONLIN (:550), halo (:555),
+ * then one Jacobi / Richardson / two-colour GS update of every child */
+int pamg_smooth(pamg_handle* h, int level, int solver, int nsweeps);
+/* get_residual (:725-873) on TNEW with the current halo strips; norms of RES by warp-shuffle reduction */
+int pamg_residual(pamg_handle* h, int level, double* l2, double* linf);
+int pamg_convergence(pamg_handle* h, int level, double* conv);   /* get_convergence (:876-889), signed max */
+int pamg_restrict(pamg_handle* h, int fine_level);               /* restrictor, splitting.F90:10-32 */
+int pamg_prolong(pamg_handle* h, int fine_level);                /* prolongator, splitting.F90:38-91 */
+/* V-cycles of the INTENDED composition until ||r||2/||r0||2 <= tol; hist gets max_cycles+1 norms */
+int pamg_vcycle_solve(pamg_handle* h, int solver, int nu1, int nu2, int ncoarse, int max_cycles, double tol,
+                      int* cycles, double* hist);
+/* one itime of the HEAD loop (:316-379), every quirk included */
+int pamg_literal_timestep(pamg_handle* h, int solver, int n_multigrid, int n_smooth);
+/* whole reference-facing time step with HOST buffers: upload tnew, told=tnew, solve, download tnew */
+int pamg_timestep_host(pamg_handle* h, const double* tnew_in, double* tnew_out, int max_cycles, double tol,
+                       int* cycles, double* relres);
+
+/* ---- distributed halo (update_overlaps across GPUs; Generic.F90:387-401 sketches the block partition) -- */
+/* host-only: where every halo strip lives and how cut faces are ordered per peer (no CUDA needed).
+ * arrays are [U_local*3]; peers is [npeers][4] = part, nfaces, strip_begin, send_begin;
+ * counts = npeers, nstrips, nsend, U_local, first */
+int pamg_halo_plan(int U_global, const double* X, const int32_t* neig, const int32_t* fneig, const int32_t* dir,
+                   int halo_rule, int nparts, const int32_t* part_first, int my_part, int32_t* strip_of,
+                   int32_t* dst_strip, int32_t* rev, int32_t* hmap, int32_t* peers, int32_t* counts);
+int pamg_comm_unique_id(char* id128);                        /* rank 0: ncclGetUniqueId */
+int pamg_comm_init(pamg_handle* h, const char* id128, int nranks, int rank);
+int pamg_halo_peer_count(const pamg_handle* h, int* npeers);
+int pamg_halo_peer_info(const pamg_handle* h, int idx, int* peer_part, int* nfaces);
+
+/* ---- unstructured explicit DG step (unstr_explicit, transport_tri_unstr.F90:588-795) ------------ */
+int pamg_set_unstructured(pamg_handle* h, int E, const double* X, const int32_t* neig, const int32_t* fneig);
+int pamg_unstr_upload(pamg_handle* h, const double* tnew /* (3,E) */);
+int pamg_unstr_download(pamg_handle* h, double* tnew);
+/* ntime x nits nonlinear iterations; njac_its Jacobi iterations on M x = M told + dt rhs, or the exact
+ * register-resident local inverse when use_exact_minv != 0 (transport_rect.F90:277-291) */
+int pamg_explicit_step(pamg_handle* h, double dt, double u_x, double u_y, double t_bc, int ntime, int nits,
+                       int njac_its, int use_exact_minv, int use_dir);
+
+/* ---- batched element-local inverse (FINDInv, matrix_inversion.F90:50-148) ----------------------- */
+/* M, x, rhs on the HOST; n in {3,4,6}; M row-major [batch][n][n].  x = M^-1 rhs (Minv optional out).
+ * status[b] = 0 or -1 (singular) like errorflag. */
+int pamg_apply_local_minv(pamg_handle* h, int n, int batch, const double* M, const double* rhs, double* x,
+                          double* Minv, int32_t* status);
+
+/* ---- timing helpers (CUDA events on the handle's stream) ---------------------------------------- */
+int pamg_sync(pamg_handle* h);
+int pamg_event_record(pamg_handle* h, int slot);       /* slot 0..15 */
+int pamg_event_elapsed_ms(pamg_handle* h, int slot_a, int slot_b, float* ms);
+int pamg_launch_count(const pamg_handle* h, int64_t* n); /* kernels launched by this handle so far */
+int pamg_flush_l2(pamg_handle* h);                     /* writes a 256 MiB scratch buffer */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

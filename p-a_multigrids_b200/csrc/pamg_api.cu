@@ -1,0 +1,828 @@
+// pamg_api.cu -- handle, device memory and the C ABI of libpamg_cuda.so (see include/pamg.h).
+// Host orchestration mirrors the contained procedures of Semi_implicit_iterative
+// (transport_tri_semi.F90:407-889) and its V-cycle loop (:319-379).  No CPU fallback: every compute
+// entry fails with PAMG_ERR_CUDA when no device is present.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pamg_internal.h"
+#include "pamg_kernels.cuh"
+#include "pamg_unstr.cuh"
+
+using namespace pamg;
+
+// ------------------------------------------------------------------ NCCL, bound lazily with dlopen
+// (libnccl.so.2; the few entry points used for the halo exchange and the norm all-reduce)
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclFloat64 = 8, ncclSum = 0, ncclMax = 2, ncclSuccess = 0 };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  bool load() {
+    if (lib) return true;
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return false;
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart");
+    GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
+    Send = (decltype(Send))dlsym(lib, "ncclSend");
+    Recv = (decltype(Recv))dlsym(lib, "ncclRecv");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    return GetUniqueId && CommInitRank && CommDestroy && GroupStart && GroupEnd && Send && Recv && AllReduce;
+  }
+};
+NcclApi g_nccl;
+}  // namespace
+
+// ------------------------------------------------------------------ handle
+struct LevelDev {
+  int s = 0, S = 0;
+  long long C = 0, nelem = 0, ndof = 0;
+  double* T[2] = {nullptr, nullptr};  // T[cur] = TNONLIN (the iterate); T[cur^1] = TNEW unless aliased
+  int cur = 0;
+  bool tnew_alias = true;             // TNEW == TNONLIN logically (no separate copy materialised)
+  double *told = nullptr, *rhs = nullptr, *res = nullptr;
+  double *ovl = nullptr, *ovl_old = nullptr;  // (nstrips + nsend) * 3S doubles
+  double* pc = nullptr;               // [U][NPC]
+  bool rhs_valid = false;             // level 1: RHS matches TOLD
+};
+
+struct pamg_handle {
+  pamg_params p;
+  int device = 0, nsm = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[16] = {};
+  long long launches = 0;
+  std::string err;
+  HaloPlan plan;
+  int U = 0;  // local parents
+  double* xg = nullptr;
+  int32_t *strip_of = nullptr, *dst_strip = nullptr, *rev = nullptr, *hmap = nullptr;
+  std::vector<LevelDev> lev;
+  double* partial = nullptr; int npartial = 0;
+  double* out3 = nullptr;         // device
+  double* out3_host = nullptr;    // pinned
+  double* scratch = nullptr; size_t scratch_bytes = 0;  // L2 flush
+  double* stage = nullptr; size_t stage_bytes = 0;      // pinned staging for host-buffer entry points
+  // distributed
+  ncclComm_t comm = nullptr; int nranks = 1, rank = 0;
+  // unstructured
+  UnstrDev un;
+};
+
+namespace {
+
+int fail(pamg_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+#define CK(call)                                                                                 \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      return fail(h, PAMG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+  } while (0)
+
+inline int grid_for(const pamg_handle* h, long long n) {
+  long long need = (n + TPB - 1) / TPB;
+  long long cap = (long long)h->nsm * 8;  // 8 resident CTAs of 256 threads per SM
+  return (int)std::max(1ll, std::min(need, cap));
+}
+
+bool valid_level(const pamg_handle* h, int level) { return h && level >= 1 && level <= (int)h->lev.size(); }
+
+double* tnew_ptr(LevelDev& L) { return L.tnew_alias ? L.T[L.cur] : L.T[L.cur ^ 1]; }
+
+// make TNEW a real, separate copy of what it logically holds
+int materialise_tnew(pamg_handle* h, LevelDev& L) {
+  if (!L.tnew_alias) return PAMG_OK;
+  CK(cudaMemcpyAsync(L.T[L.cur ^ 1], L.T[L.cur], L.ndof * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  L.tnew_alias = false;
+  return PAMG_OK;
+}
+
+double* field_ptr(pamg_handle* h, int field, int level, bool for_write, int* rc) {
+  *rc = PAMG_OK;
+  LevelDev& L = h->lev[level - 1];
+  switch (field) {
+    case PAMG_TNEW:
+      if (for_write) { *rc = materialise_tnew(h, L); return L.T[L.cur ^ 1]; }
+      return tnew_ptr(L);
+    case PAMG_TNONLIN:
+      if (for_write) *rc = materialise_tnew(h, L);
+      return L.T[L.cur];
+    case PAMG_TOLD: if (for_write) L.rhs_valid = false; return L.told;
+    case PAMG_RHS: if (for_write) L.rhs_valid = true; return L.rhs;
+    case PAMG_RES: return L.res;
+  }
+  *rc = PAMG_ERR_ARG;
+  return nullptr;
+}
+
+// ---- per-parent geometry in closed form (tri_det_nlx ShapFun.F90:1414-1454; det_snlx_all :1554-1590;
+//      level scaling :1678-1683,1751-1780; get_d_center Msh2Tri.F90:358-383; add_diffusion_surf
+//      matrices.F90:84-110).  One row of NPC coefficients per parent per level.
+void parent_coefficients(const pamg_params& p, const double* Xall, const int32_t* neig, int g /*global parent*/,
+                         int s, double* pc) {
+  const double* X = Xall + (size_t)g * 6;
+  const double x1 = X[0], y1 = X[1], x2 = X[2], y2 = X[3], x3 = X[4], y3 = X[5];
+  const double A = x1 - x3, B = y1 - y3, Cc = x2 - x3, D = y2 - y3;
+  const double detj = A * D - B * Cc;
+  const double area = 0.5 * std::fabs(detj);
+  const double g1[2] = {D / detj, -Cc / detj}, g2[2] = {-B / detj, A / detj};
+  const double g3[2] = {-(g1[0] + g2[0]), -(g1[1] + g2[1])};
+  const double* G[3] = {g1, g2, g3};
+  const double two_s = std::ldexp(1.0, s), four_s = std::ldexp(1.0, 2 * s);
+  pc[PC_CM] = area / (12.0 * four_s * p.dt);
+  auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1]; };
+  pc[PC_K11] = p.k * area * dot(g1, g1); pc[PC_K12] = p.k * area * dot(g1, g2); pc[PC_K13] = p.k * area * dot(g1, g3);
+  pc[PC_K22] = p.k * area * dot(g2, g2); pc[PC_K23] = p.k * area * dot(g2, g3); pc[PC_K33] = p.k * area * dot(g3, g3);
+  const double uu[2] = {p.u_x, p.u_y};
+  for (int i = 0; i < 3; ++i) pc[PC_ADV + i] = area * dot(G[i], uu) / (3.0 * two_s);
+  const double cx = (x1 + x2 + x3) / 3.0, cy = (y1 + y2 + y3) / 3.0;
+  // child faces: f1 = nodes (1,3) on side 1, f2 = (3,2) on side 3, f3 = (2,1) on side 2
+  const int fa[3] = {0, 2, 1}, fb[3] = {2, 1, 0}, mface[3] = {0, 2, 1};
+  const double V1[2] = {A, B}, V2[2] = {Cc, D};
+  const double ci[3][2] = {{1.0 / 3, -2.0 / 3}, {-2.0 / 3, 1.0 / 3}, {1.0 / 3, 1.0 / 3}};  // centroid offsets of child 2's neighbours
+  for (int f = 0; f < 3; ++f) {
+    const double ax = X[2 * fa[f]], ay = X[2 * fa[f] + 1], bx = X[2 * fb[f]], by = X[2 * fb[f] + 1];
+    const double ex = bx - ax, ey = by - ay, L = std::sqrt(ex * ex + ey * ey);
+    double nx = ey / L, ny = -ex / L;
+    const double mx = 0.5 * (ax + bx), my = 0.5 * (ay + by);
+    if (nx * (mx - cx) + ny * (my - cy) < 0) { nx = -nx; ny = -ny; }
+    const double lhalf = 0.5 * L;
+    pc[PC_FL + f] = (uu[0] * nx + uu[1] * ny) * lhalf / (3.0 * two_s);
+    const double dix = ci[f][0] * V1[0] + ci[f][1] * V2[0], diy = ci[f][0] * V1[1] + ci[f][1] * V2[1];
+    const double dcI = std::sqrt(dix * dix + diy * diy);
+    pc[PC_PENI + f] = p.k * lhalf / (3.0 * dcI);
+    const int q = neig[(size_t)g * 3 + mface[f]];
+    double dcX;
+    if (q != 0) {
+      const double* Y = Xall + (size_t)(q - 1) * 6;
+      const double qx = (Y[0] + Y[2] + Y[4]) / 3.0, qy = (Y[1] + Y[3] + Y[5]) / 3.0;
+      dcX = std::sqrt((cx - qx) * (cx - qx) + (cy - qy) * (cy - qy));
+    } else {
+      dcX = std::sqrt((cx - mx) * (cx - mx) + (cy - my) * (cy - my));
+    }
+    pc[PC_PENX + f] = p.k * lhalf / (3.0 * dcX);
+  }
+  pc[19] = 0.0;
+}
+
+int launch_halo(pamg_handle* h, int level);
+
+// exchange of the cut-face strips (one process per GPU): the send slots follow the local strips in the
+// strip space; the receive range of a peer is a contiguous range of my own strips (pamg_plan.cpp)
+int exchange_halo(pamg_handle* h, LevelDev& L) {
+  if (h->plan.peers.empty()) return PAMG_OK;
+  if (!h->comm) return fail(h, PAMG_ERR_STATE, "partitioned mesh but pamg_comm_init was not called");
+  const size_t S3 = (size_t)3 * L.S;
+  g_nccl.GroupStart();
+  for (const auto& pr : h->plan.peers) {
+    const size_t n = (size_t)pr.nfaces * S3;
+    g_nccl.Send(L.ovl + ((size_t)h->plan.nstrips + pr.send_begin) * S3, n, ncclFloat64, pr.part, h->comm, h->stream);
+    g_nccl.Recv(L.ovl + (size_t)pr.strip_begin * S3, n, ncclFloat64, pr.part, h->comm, h->stream);
+  }
+  if (g_nccl.GroupEnd() != ncclSuccess) return fail(h, PAMG_ERR_CUDA, "ncclGroupEnd failed in halo exchange");
+  return PAMG_OK;
+}
+
+int launch_halo(pamg_handle* h, int level) {
+  LevelDev& L = h->lev[level - 1];
+  HaloArgs a;
+  a.tnew = tnew_ptr(L); a.told = L.told; a.ovl = L.ovl; a.ovl_old = L.ovl_old; a.xg = h->xg;
+  a.dst_strip = h->dst_strip; a.rev = h->rev; a.strip_of = h->strip_of;
+  a.bc_scale = (h->p.coarse_bc_zero && level > 1) ? 0.0 : 1.0;
+  a.U = h->U; a.s = L.s; a.with_old = 1;
+  const long long n = (long long)h->U * 3 * L.S;
+  k_halo<<<grid_for(h, n), TPB, 0, h->stream>>>(a);
+  h->launches++;
+  CK(cudaGetLastError());
+  return exchange_halo(h, L);
+}
+
+int launch_build_rhs(pamg_handle* h) {
+  LevelDev& L = h->lev[0];
+  RhsArgs a;
+  a.told = L.told; a.rhs = L.rhs; a.pc = L.pc; a.xg = h->xg; a.dt = h->p.dt; a.source_coef = h->p.source_coef;
+  a.nelem = L.nelem; a.s = L.s; a.literal_source = h->p.literal_source;
+  k_build_rhs<<<grid_for(h, L.nelem), TPB, 0, h->stream>>>(a);
+  h->launches++;
+  CK(cudaGetLastError());
+  L.rhs_valid = true;
+  return PAMG_OK;
+}
+
+template <int MODE>
+int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout, int colour, int grid) {
+  ElemArgs a;
+  a.Tin = Tin; a.Tout = Tout; a.rhs = L.rhs; a.ovl = L.ovl; a.pc = L.pc; a.strip_of = h->strip_of; a.hmap = h->hmap;
+  a.partial = h->partial; a.omega = h->p.omega; a.rsign = (double)h->p.residual_sign; a.nelem = L.nelem; a.s = L.s;
+  a.colour = colour;
+  if (h->p.face_terms) k_element<MODE, true><<<grid, TPB, 0, h->stream>>>(a);
+  else k_element<MODE, false><<<grid, TPB, 0, h->stream>>>(a);
+  h->launches++;
+  CK(cudaGetLastError());
+  return PAMG_OK;
+}
+
+int do_smooth(pamg_handle* h, int level, int solver, int nsweeps) {
+  LevelDev& L = h->lev[level - 1];
+  if (level == 1 && !L.rhs_valid) { int rc = launch_build_rhs(h); if (rc) return rc; }
+  const int grid = grid_for(h, L.nelem);
+  for (int sw = 0; sw < nsweeps; ++sw) {
+    // tnew <- tnew_nonlin (:550) is the buffer swap below for Jacobi; halo from it (:555)
+    L.tnew_alias = true;
+    int rc = launch_halo(h, level);
+    if (rc) return rc;
+    if (solver == 1 || solver == 2) {
+      rc = (solver == 1) ? launch_element<MODE_JACOBI>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid)
+                         : launch_element<MODE_RICH>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid);
+      if (rc) return rc;
+      L.cur ^= 1;
+      L.tnew_alias = false;  // the old buffer now holds the start-of-sweep field = tracer%tnew
+    } else if (solver == 3 || solver == 4) {
+      // two-colour ordering of the reference's Gauss-Seidel sweep: all down children, then all up children;
+      // values across parent faces stay lagged through the halo strips exactly as at :647-655.
+      if (sw == nsweeps - 1) { rc = materialise_tnew(h, L); if (rc) return rc; }  // keep tracer%tnew observable
+      rc = launch_element<MODE_GS>(h, L, L.T[L.cur], L.T[L.cur], 0, grid);
+      if (rc) return rc;
+      rc = launch_element<MODE_GS>(h, L, L.T[L.cur], L.T[L.cur], 1, grid);
+      if (rc) return rc;
+    } else {
+      return fail(h, PAMG_ERR_ARG, "solver must be 1 (Jacobi), 2 (Richardson) or 3 (Gauss-Seidel)");
+    }
+  }
+  return PAMG_OK;
+}
+
+int do_residual(pamg_handle* h, int level, double* l2, double* linf, double* smax) {
+  LevelDev& L = h->lev[level - 1];
+  if (level == 1 && !L.rhs_valid) { int rc = launch_build_rhs(h); if (rc) return rc; }
+  const int grid = grid_for(h, L.nelem);
+  if (grid > h->npartial) return fail(h, PAMG_ERR_STATE, "partial buffer too small");
+  int rc = launch_element<MODE_RESID>(h, L, tnew_ptr(L), L.res, 0, grid);
+  if (rc) return rc;
+  if (l2 || linf || smax) {
+    k_reduce_partials<<<1, 1024, 0, h->stream>>>(h->partial, grid, h->out3);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (h->comm && h->nranks > 1) {
+      // global norms: sum of squares, max |r|, max r
+      g_nccl.GroupStart();
+      g_nccl.AllReduce(h->out3, h->out3, 1, ncclFloat64, ncclSum, h->comm, h->stream);
+      g_nccl.AllReduce(h->out3 + 1, h->out3 + 1, 2, ncclFloat64, ncclMax, h->comm, h->stream);
+      if (g_nccl.GroupEnd() != ncclSuccess) return fail(h, PAMG_ERR_CUDA, "ncclAllReduce failed");
+    }
+    CK(cudaMemcpyAsync(h->out3_host, h->out3, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (l2) *l2 = std::sqrt(h->out3_host[0]);
+    if (linf) *linf = h->out3_host[1];
+    if (smax) *smax = h->out3_host[2];
+  }
+  return PAMG_OK;
+}
+
+int do_restrict(pamg_handle* h, int fine_level) {
+  if (fine_level >= (int)h->lev.size()) return PAMG_OK;  // splitting.F90:18
+  LevelDev& F = h->lev[fine_level - 1];
+  LevelDev& Cc = h->lev[fine_level];
+  XferArgs a;
+  a.src = F.res; a.dst = Cc.rhs; a.ncoarse = Cc.nelem; a.sc = Cc.s; a.mode = h->p.transfer;
+  k_restrict<<<grid_for(h, Cc.nelem), TPB, 0, h->stream>>>(a);
+  h->launches++;
+  CK(cudaGetLastError());
+  Cc.rhs_valid = true;
+  return PAMG_OK;
+}
+
+int do_prolong(pamg_handle* h, int fine_level) {
+  if (fine_level >= (int)h->lev.size()) return fail(h, PAMG_ERR_ARG, "no coarser level to prolong from");
+  LevelDev& F = h->lev[fine_level - 1];
+  LevelDev& Cc = h->lev[fine_level];
+  XferArgs a;
+  a.ncoarse = Cc.nelem; a.sc = Cc.s; a.mode = h->p.transfer;
+  if (h->p.transfer == 0) {
+    // as written: tracer(ilevel)%tnew += f(tracer(ilevel+1)%tnew), splitting.F90:59-88
+    int rc = materialise_tnew(h, F);
+    if (rc) return rc;
+    a.src = tnew_ptr(Cc); a.dst = F.T[F.cur ^ 1];
+    k_prolong_literal<<<grid_for(h, Cc.nelem), TPB, 0, h->stream>>>(a);
+  } else {
+    int rc = materialise_tnew(h, F);  // the correction goes to the iterate only
+    if (rc) return rc;
+    a.src = Cc.T[Cc.cur]; a.dst = F.T[F.cur];
+    k_prolong_p1<<<grid_for(h, F.nelem), TPB, 0, h->stream>>>(a);
+  }
+  h->launches++;
+  CK(cudaGetLastError());
+  return PAMG_OK;
+}
+
+int do_fill(pamg_handle* h, double* p, long long n, double v) {
+  if (v == 0.0) { CK(cudaMemsetAsync(p, 0, n * sizeof(double), h->stream)); return PAMG_OK; }
+  k_fill<<<grid_for(h, n), TPB, 0, h->stream>>>(p, n, v);
+  h->launches++;
+  CK(cudaGetLastError());
+  return PAMG_OK;
+}
+
+int vcycle_rec(pamg_handle* h, int level, int solver, int nu1, int nu2, int ncoarse) {
+  const int Lmax = (int)h->lev.size();
+  int rc;
+  if (level == Lmax) return do_smooth(h, level, solver, ncoarse);
+  if ((rc = do_smooth(h, level, solver, nu1))) return rc;
+  LevelDev& L = h->lev[level - 1];
+  L.tnew_alias = true;                                   // tnew = tnew_nonlin
+  if ((rc = launch_halo(h, level))) return rc;
+  if ((rc = do_residual(h, level, nullptr, nullptr, nullptr))) return rc;
+  if ((rc = do_restrict(h, level))) return rc;
+  LevelDev& Cc = h->lev[level];
+  if ((rc = do_fill(h, Cc.T[Cc.cur], Cc.ndof, 0.0))) return rc;
+  Cc.tnew_alias = true;
+  if ((rc = vcycle_rec(h, level + 1, solver, nu1, nu2, ncoarse))) return rc;
+  if ((rc = do_prolong(h, level))) return rc;
+  return do_smooth(h, level, solver, nu2);
+}
+
+void free_levels(pamg_handle* h) {
+  for (auto& L : h->lev) {
+    cudaFree(L.T[0]); cudaFree(L.T[1]); cudaFree(L.told); cudaFree(L.rhs); cudaFree(L.res);
+    cudaFree(L.ovl); cudaFree(L.ovl_old); cudaFree(L.pc);
+  }
+  h->lev.clear();
+  cudaFree(h->xg); cudaFree(h->strip_of); cudaFree(h->dst_strip); cudaFree(h->rev); cudaFree(h->hmap);
+  cudaFree(h->partial);
+  h->xg = nullptr; h->strip_of = h->dst_strip = h->rev = h->hmap = nullptr; h->partial = nullptr;
+}
+
+int ensure_stage(pamg_handle* h, size_t bytes) {
+  if (h->stage_bytes >= bytes) return PAMG_OK;
+  if (h->stage) cudaFreeHost(h->stage);
+  h->stage = nullptr; h->stage_bytes = 0;
+  CK(cudaMallocHost(&h->stage, bytes));
+  h->stage_bytes = bytes;
+  return PAMG_OK;
+}
+
+}  // namespace
+
+// ================================================================== C ABI
+extern "C" {
+
+const char* pamg_version(void) { return "pamg-b200 0.1 (sm_100a)"; }
+
+int pamg_device_count(int* n) {
+  if (!n) return PAMG_ERR_ARG;
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess || c < 1) { *n = 0; return PAMG_ERR_CUDA; }
+  *n = c;
+  return PAMG_OK;
+}
+
+void pamg_default_params(pamg_params* p, int literal_head) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->n_split = 1; p->multi_levels = 1; p->n_smooth = 4; p->n_multigrid = 2; p->n_coarse_smooth = 15; p->solver = 3;
+  p->theta = 1.0; p->k = 1.0; p->omega = 0.8; p->u_x = 0.0; p->u_y = 0.0;
+  if (literal_head) {  // main.F90:46-47, transport_tri_semi.F90:117-140 as checked in
+    p->dt = 1.25e-5; p->face_terms = 0; p->literal_source = 1; p->transfer = 0; p->residual_sign = 1;
+    p->halo_rule = 0; p->coarse_bc_zero = 0; p->source_coef = -2.0;
+  } else {
+    p->dt = 1e-3; p->face_terms = 1; p->literal_source = 0; p->transfer = 1; p->residual_sign = -1;
+    p->halo_rule = 1; p->coarse_bc_zero = 1; p->source_coef = 2.0;
+  }
+}
+
+int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
+  if (!p || !out) return PAMG_ERR_ARG;
+  *out = nullptr;
+  if (p->n_split < 1 || p->n_split > 13 || p->multi_levels < 1 || p->multi_levels > p->n_split) return PAMG_ERR_ARG;  // :120-123
+  if (p->theta != 1.0) return PAMG_ERR_UNSUPPORTED;
+  if (!(p->dt > 0.0)) return PAMG_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return PAMG_ERR_CUDA;  // no CPU fallback
+  if (device < 0 || device >= ndev) return PAMG_ERR_ARG;
+  pamg_handle* h = new pamg_handle();
+  h->p = *p; h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete h; return PAMG_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->nsm = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return PAMG_ERR_CUDA; }
+  for (auto& e : h->ev) cudaEventCreate(&e);
+  cudaMalloc(&h->out3, 3 * sizeof(double));
+  cudaMallocHost(&h->out3_host, 3 * sizeof(double));
+  *out = h;
+  return PAMG_OK;
+}
+
+void pamg_destroy(pamg_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm) g_nccl.CommDestroy(h->comm);
+  free_levels(h);
+  unstr_free(h->un);
+  cudaFree(h->out3); cudaFreeHost(h->out3_host); cudaFree(h->scratch);
+  if (h->stage) cudaFreeHost(h->stage);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* pamg_last_error(const pamg_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, const int32_t* neig,
+                               const int32_t* fneig, const int32_t* dir, int nparts, const int32_t* part_first,
+                               int my_part) {
+  if (!h) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  int rc = build_halo_plan(U_global, X, neig, fneig, dir, h->p.halo_rule, nparts, part_first, my_part, h->plan);
+  if (rc) return fail(h, rc, "inconsistent parent arrays (X / Neig / fNeig)");
+  free_levels(h);
+  const int U = h->plan.U_local, first = h->plan.first;
+  if (U < 1) return fail(h, PAMG_ERR_ARG, "empty partition");
+  h->U = U;
+  std::vector<double> xg((size_t)U * 6);
+  for (int u = 0; u < U; ++u) {
+    const double* P = X + (size_t)(first + u) * 6;
+    double* o = &xg[(size_t)u * 6];
+    o[0] = P[4]; o[1] = P[5]; o[2] = P[0] - P[4]; o[3] = P[1] - P[5]; o[4] = P[2] - P[4]; o[5] = P[3] - P[5];
+  }
+  CK(cudaMalloc(&h->xg, xg.size() * sizeof(double)));
+  CK(cudaMemcpy(h->xg, xg.data(), xg.size() * sizeof(double), cudaMemcpyHostToDevice));
+  const size_t n3 = (size_t)U * 3 * sizeof(int32_t);
+  CK(cudaMalloc(&h->strip_of, n3)); CK(cudaMalloc(&h->dst_strip, n3)); CK(cudaMalloc(&h->rev, n3)); CK(cudaMalloc(&h->hmap, n3));
+  CK(cudaMemcpy(h->strip_of, h->plan.strip_of.data(), n3, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->dst_strip, h->plan.dst_strip.data(), n3, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->rev, h->plan.rev.data(), n3, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->hmap, h->plan.hmap.data(), n3, cudaMemcpyHostToDevice));
+  h->lev.resize(h->p.multi_levels);
+  std::vector<double> pc((size_t)U * NPC);
+  for (int il = 0; il < h->p.multi_levels; ++il) {
+    LevelDev& L = h->lev[il];
+    L.s = h->p.n_split - il; L.S = 1 << L.s; L.C = 1ll << (2 * L.s);
+    L.nelem = L.C * U; L.ndof = 3 * L.nelem;
+    const size_t fb = (size_t)L.ndof * sizeof(double);
+    CK(cudaMalloc(&L.T[0], fb)); CK(cudaMalloc(&L.T[1], fb)); CK(cudaMalloc(&L.told, fb));
+    CK(cudaMalloc(&L.rhs, fb)); CK(cudaMalloc(&L.res, fb));
+    CK(cudaMemsetAsync(L.T[0], 0, fb, h->stream)); CK(cudaMemsetAsync(L.T[1], 0, fb, h->stream));
+    CK(cudaMemsetAsync(L.told, 0, fb, h->stream)); CK(cudaMemsetAsync(L.rhs, 0, fb, h->stream));
+    CK(cudaMemsetAsync(L.res, 0, fb, h->stream));
+    const size_t ob = (size_t)(h->plan.nstrips + h->plan.nsend) * 3 * L.S * sizeof(double);
+    CK(cudaMalloc(&L.ovl, ob)); CK(cudaMalloc(&L.ovl_old, ob));
+    CK(cudaMemsetAsync(L.ovl, 0, ob, h->stream)); CK(cudaMemsetAsync(L.ovl_old, 0, ob, h->stream));  // :207
+    for (int u = 0; u < U; ++u) parent_coefficients(h->p, X, neig, first + u, L.s, &pc[(size_t)u * NPC]);
+    CK(cudaMalloc(&L.pc, pc.size() * sizeof(double)));
+    CK(cudaMemcpy(L.pc, pc.data(), pc.size() * sizeof(double), cudaMemcpyHostToDevice));
+    L.cur = 0; L.tnew_alias = true; L.rhs_valid = (il != 0);
+  }
+  h->npartial = h->nsm * 8;
+  CK(cudaMalloc(&h->partial, (size_t)h->npartial * 3 * sizeof(double)));
+  CK(cudaStreamSynchronize(h->stream));
+  return PAMG_OK;
+}
+
+int pamg_set_parents(pamg_handle* h, int U, const double* X, const int32_t* neig, const int32_t* fneig,
+                     const int32_t* dir) {
+  return pamg_set_parents_partition(h, U, X, neig, fneig, dir, 1, nullptr, 0);
+}
+
+int pamg_ndof(const pamg_handle* h, int level, int64_t* ndof) {
+  if (!valid_level(h, level) || !ndof) return PAMG_ERR_ARG;
+  *ndof = h->lev[level - 1].ndof;
+  return PAMG_OK;
+}
+
+int pamg_upload_field(pamg_handle* h, int field, int level, const double* host) {
+  if (!valid_level(h, level) || !host) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  int rc;
+  double* d = field_ptr(h, field, level, true, &rc);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(d, host, h->lev[level - 1].ndof * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PAMG_OK;
+}
+
+int pamg_download_field(pamg_handle* h, int field, int level, double* host) {
+  if (!valid_level(h, level) || !host) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  int rc;
+  double* d = field_ptr(h, field, level, false, &rc);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(host, d, h->lev[level - 1].ndof * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PAMG_OK;
+}
+
+int pamg_fill_field(pamg_handle* h, int field, int level, double value) {
+  if (!valid_level(h, level)) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  int rc;
+  double* d = field_ptr(h, field, level, true, &rc);
+  if (rc) return rc;
+  return do_fill(h, d, h->lev[level - 1].ndof, value);
+}
+
+int pamg_copy_field(pamg_handle* h, int level, int dst_field, int src_field) {
+  if (!valid_level(h, level)) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  LevelDev& L = h->lev[level - 1];
+  if (dst_field == src_field) return PAMG_OK;
+  if (dst_field == PAMG_TNEW && src_field == PAMG_TNONLIN) { L.tnew_alias = true; return PAMG_OK; }      // :550
+  if (dst_field == PAMG_TNONLIN && src_field == PAMG_TNEW) {                                             // :327
+    if (!L.tnew_alias) { L.cur ^= 1; L.tnew_alias = true; }
+    return PAMG_OK;
+  }
+  int rc;
+  const double* s = field_ptr(h, src_field, level, false, &rc);
+  if (rc) return rc;
+  double* d = field_ptr(h, dst_field, level, true, &rc);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(d, s, L.ndof * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  return PAMG_OK;
+}
+
+int pamg_download_overlap(pamg_handle* h, int level, int old, double* host) {
+  if (!valid_level(h, level) || !host) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  LevelDev& L = h->lev[level - 1];
+  const size_t S3 = (size_t)3 * L.S;
+  std::vector<double> tmp((size_t)h->plan.nstrips * S3);
+  CK(cudaMemcpyAsync(tmp.data(), old ? L.ovl_old : L.ovl, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int lf = 0; lf < h->U * 3; ++lf)
+    std::memcpy(host + (size_t)lf * S3, &tmp[(size_t)h->plan.strip_of[lf] * S3], S3 * sizeof(double));
+  return PAMG_OK;
+}
+
+int pamg_device_ptr(pamg_handle* h, int field, int level, void** dptr) {
+  if (!valid_level(h, level) || !dptr) return PAMG_ERR_ARG;
+  int rc;
+  *dptr = field_ptr(h, field, level, false, &rc);
+  return rc;
+}
+
+int pamg_update_overlaps(pamg_handle* h, int level) {
+  if (!valid_level(h, level)) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  return launch_halo(h, level);
+}
+
+int pamg_build_rhs(pamg_handle* h) {
+  if (!valid_level(h, 1)) return PAMG_ERR_STATE;
+  CK(cudaSetDevice(h->device));
+  return launch_build_rhs(h);
+}
+
+int pamg_smooth(pamg_handle* h, int level, int solver, int nsweeps) {
+  if (!valid_level(h, level) || nsweeps < 0) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  return do_smooth(h, level, solver, nsweeps);
+}
+
+int pamg_residual(pamg_handle* h, int level, double* l2, double* linf) {
+  if (!valid_level(h, level)) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  return do_residual(h, level, l2, linf, nullptr);
+}
+
+int pamg_convergence(pamg_handle* h, int level, double* conv) {
+  if (!valid_level(h, level) || !conv) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  double l2, li;
+  return do_residual(h, level, &l2, &li, conv);
+}
+
+int pamg_restrict(pamg_handle* h, int fine_level) {
+  if (!valid_level(h, fine_level)) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  return do_restrict(h, fine_level);
+}
+
+int pamg_prolong(pamg_handle* h, int fine_level) {
+  if (!valid_level(h, fine_level)) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  return do_prolong(h, fine_level);
+}
+
+int pamg_vcycle_solve(pamg_handle* h, int solver, int nu1, int nu2, int ncoarse, int max_cycles, double tol,
+                      int* cycles, double* hist) {
+  if (!valid_level(h, 1) || max_cycles < 0) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  LevelDev& L = h->lev[0];
+  int rc;
+  L.tnew_alias = true;
+  if ((rc = launch_halo(h, 1))) return rc;
+  double r0 = 0, r = 0;
+  if ((rc = do_residual(h, 1, &r0, nullptr, nullptr))) return rc;
+  if (hist) hist[0] = r0;
+  if (cycles) *cycles = 0;
+  if (r0 == 0.0) return PAMG_OK;
+  for (int c = 1; c <= max_cycles; ++c) {
+    if ((rc = vcycle_rec(h, 1, solver, nu1, nu2, ncoarse))) return rc;
+    L.tnew_alias = true;
+    if ((rc = launch_halo(h, 1))) return rc;
+    if ((rc = do_residual(h, 1, &r, nullptr, nullptr))) return rc;
+    if (hist) hist[c] = r;
+    if (cycles) *cycles = c;
+    if (r / r0 <= tol) return PAMG_OK;
+  }
+  if (cycles) *cycles = max_cycles + 1;
+  return PAMG_OK;
+}
+
+int pamg_literal_timestep(pamg_handle* h, int solver, int n_multigrid, int n_smooth) {
+  if (!valid_level(h, 1)) return PAMG_ERR_STATE;
+  CK(cudaSetDevice(h->device));
+  const int ML = (int)h->lev.size();
+  int rc;
+  if ((rc = pamg_copy_field(h, 1, PAMG_TOLD, PAMG_TNEW))) return rc;      // :316
+  if ((rc = pamg_copy_field(h, 1, PAMG_TNONLIN, PAMG_TNEW))) return rc;   // :317
+  for (int mg = 0; mg < n_multigrid; ++mg) {
+    for (int il = 1; il <= ML; ++il) {
+      if ((rc = pamg_copy_field(h, il, PAMG_TNONLIN, PAMG_TNEW))) return rc;   // :327
+      if ((rc = do_smooth(h, il, solver, n_smooth))) return rc;                // :331
+      if ((rc = do_restrict(h, il))) return rc;                                // :336
+      if ((rc = do_residual(h, il, nullptr, nullptr, nullptr))) return rc;     // :338
+    }
+    if ((rc = pamg_copy_field(h, ML, PAMG_TNONLIN, PAMG_TNEW))) return rc;     // :348
+    for (int i = 0; i < h->p.n_coarse_smooth; ++i)
+      if ((rc = do_smooth(h, ML, solver, n_smooth))) return rc;                // :351-352
+    for (int il = ML - 1; il >= 1; --il) {
+      if ((rc = pamg_copy_field(h, il, PAMG_TNONLIN, PAMG_TNEW))) return rc;   // :367
+      if ((rc = do_prolong(h, il))) return rc;                                 // :370
+      if ((rc = do_smooth(h, il, solver, n_smooth))) return rc;                // :376
+    }
+  }
+  return PAMG_OK;
+}
+
+int pamg_timestep_host(pamg_handle* h, const double* tnew_in, double* tnew_out, int max_cycles, double tol,
+                       int* cycles, double* relres) {
+  if (!valid_level(h, 1) || !tnew_in || !tnew_out) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  LevelDev& L = h->lev[0];
+  const size_t bytes = (size_t)L.ndof * sizeof(double);
+  // told = tnew ; tnew_nonlin = tnew (transport_tri_semi.F90:316-317)
+  CK(cudaMemcpyAsync(L.T[L.cur], tnew_in, bytes, cudaMemcpyHostToDevice, h->stream));
+  L.tnew_alias = true;
+  CK(cudaMemcpyAsync(L.told, L.T[L.cur], bytes, cudaMemcpyDeviceToDevice, h->stream));
+  L.rhs_valid = false;
+  std::vector<double> hist((size_t)max_cycles + 2, 0.0);
+  int cyc = 0;
+  int rc = pamg_vcycle_solve(h, h->p.solver, h->p.n_smooth, h->p.n_smooth, h->p.n_coarse_smooth, max_cycles, tol, &cyc,
+                             hist.data());
+  if (rc) return rc;
+  if (cycles) *cycles = cyc;
+  if (relres) *relres = hist[0] > 0 ? hist[std::min(cyc, max_cycles)] / hist[0] : 0.0;
+  CK(cudaMemcpyAsync(tnew_out, L.T[L.cur], bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PAMG_OK;
+}
+
+// ---- distributed ------------------------------------------------------------------------------
+int pamg_comm_unique_id(char* id128) {
+  if (!id128) return PAMG_ERR_ARG;
+  if (!g_nccl.load()) return PAMG_ERR_STATE;
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return PAMG_ERR_CUDA;
+  std::memcpy(id128, id.internal, 128);
+  return PAMG_OK;
+}
+
+int pamg_comm_init(pamg_handle* h, const char* id128, int nranks, int rank) {
+  if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return PAMG_ERR_ARG;
+  if (!g_nccl.load()) return fail(h, PAMG_ERR_STATE, "libnccl.so.2 could not be loaded");
+  CK(cudaSetDevice(h->device));
+  ncclUniqueId id;
+  std::memcpy(id.internal, id128, 128);
+  if (g_nccl.CommInitRank(&h->comm, nranks, id, rank) != ncclSuccess) return fail(h, PAMG_ERR_CUDA, "ncclCommInitRank failed");
+  h->nranks = nranks; h->rank = rank;
+  return PAMG_OK;
+}
+
+int pamg_halo_peer_count(const pamg_handle* h, int* npeers) {
+  if (!h || !npeers) return PAMG_ERR_ARG;
+  *npeers = (int)h->plan.peers.size();
+  return PAMG_OK;
+}
+
+int pamg_halo_peer_info(const pamg_handle* h, int idx, int* peer_part, int* nfaces) {
+  if (!h || idx < 0 || idx >= (int)h->plan.peers.size()) return PAMG_ERR_ARG;
+  if (peer_part) *peer_part = h->plan.peers[idx].part;
+  if (nfaces) *nfaces = h->plan.peers[idx].nfaces;
+  return PAMG_OK;
+}
+
+// ---- unstructured explicit step ------------------------------------------------------------------
+int pamg_set_unstructured(pamg_handle* h, int E, const double* X, const int32_t* neig, const int32_t* fneig) {
+  if (!h || E < 1 || !X || !neig || !fneig) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  std::string e;
+  int rc = unstr_setup(h->un, E, X, neig, fneig, h->stream, e);
+  if (rc) return fail(h, rc, e);
+  return PAMG_OK;
+}
+
+int pamg_unstr_upload(pamg_handle* h, const double* tnew) {
+  if (!h || !tnew || h->un.E < 1) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h->un.T[h->un.cur], tnew, (size_t)h->un.E * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PAMG_OK;
+}
+
+int pamg_unstr_download(pamg_handle* h, double* tnew) {
+  if (!h || !tnew || h->un.E < 1) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(tnew, h->un.T[h->un.cur], (size_t)h->un.E * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PAMG_OK;
+}
+
+int pamg_explicit_step(pamg_handle* h, double dt, double u_x, double u_y, double t_bc, int ntime, int nits,
+                       int njac_its, int use_exact_minv, int use_dir) {
+  if (!h || h->un.E < 1 || ntime < 0 || nits < 1 || njac_its < 0) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  std::string e;
+  long long nl = 0;
+  int rc = unstr_step(h->un, dt, u_x, u_y, t_bc, ntime, nits, njac_its, use_exact_minv, use_dir, h->nsm, h->stream, nl, e);
+  h->launches += nl;
+  if (rc) return fail(h, rc, e);
+  return PAMG_OK;
+}
+
+int pamg_apply_local_minv(pamg_handle* h, int n, int batch, const double* M, const double* rhs, double* x,
+                          double* Minv, int32_t* status) {
+  if (!h || batch < 1 || !M || !(n == 3 || n == 4 || n == 6)) return PAMG_ERR_ARG;
+  if (!rhs != !x) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  std::string e;
+  long long nl = 0;
+  int rc = local_minv(n, batch, M, rhs, x, Minv, status, h->nsm, h->stream, nl, e);
+  h->launches += nl;
+  if (rc) return fail(h, rc, e);
+  return PAMG_OK;
+}
+
+// ---- timing helpers --------------------------------------------------------------------------------
+int pamg_sync(pamg_handle* h) {
+  if (!h) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  return PAMG_OK;
+}
+
+int pamg_event_record(pamg_handle* h, int slot) {
+  if (!h || slot < 0 || slot >= 16) return PAMG_ERR_ARG;
+  CK(cudaEventRecord(h->ev[slot], h->stream));
+  return PAMG_OK;
+}
+
+int pamg_event_elapsed_ms(pamg_handle* h, int a, int b, float* ms) {
+  if (!h || !ms || a < 0 || a >= 16 || b < 0 || b >= 16) return PAMG_ERR_ARG;
+  CK(cudaEventSynchronize(h->ev[b]));
+  CK(cudaEventElapsedTime(ms, h->ev[a], h->ev[b]));
+  return PAMG_OK;
+}
+
+int pamg_launch_count(const pamg_handle* h, int64_t* n) {
+  if (!h || !n) return PAMG_ERR_ARG;
+  *n = h->launches;
+  return PAMG_OK;
+}
+
+int pamg_flush_l2(pamg_handle* h) {
+  if (!h) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  if (!h->scratch) {
+    h->scratch_bytes = (size_t)256 << 20;
+    CK(cudaMalloc(&h->scratch, h->scratch_bytes));
+  }
+  k_fill<<<grid_for(h, (long long)(h->scratch_bytes / 8)), TPB, 0, h->stream>>>(h->scratch, (long long)(h->scratch_bytes / 8), 1.0);
+  CK(cudaGetLastError());
+  return PAMG_OK;
+}
+
+}  // extern "C"

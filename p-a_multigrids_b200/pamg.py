@@ -1,0 +1,391 @@
+"""Python host mirror of the reference's operator interface, bound to libpamg_cuda.so through ctypes.
+
+The reference has no plugin API; its hot path is the set of procedures contained in
+Semi_implicit_iterative (transport_tri_semi.F90:407-889) plus update_overlaps / restrictor /
+prolongator (splitting.F90) and the element loop of unstr_explicit (transport_tri_unstr.F90:600-791).
+This module exposes those procedures under their reference names and argument meaning, all running on
+the GPU.  There is no CPU fallback: constructing a solver without a CUDA device raises PamgError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpamg_cuda.so")
+
+OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_IO, ERR_SINGULAR, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+TNEW, TOLD, RHS, RES, TNONLIN = 0, 1, 2, 3, 5
+JACOBI, RICHARDSON, GAUSS_SEIDEL = 1, 2, 3
+
+_f64 = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_i32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+class PamgError(RuntimeError):
+    def __init__(self, code, msg=""):
+        super().__init__(f"pamg error {code}: {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    """pamg_params (include/pamg.h): everything the reference hard-codes (main.F90:46-47,
+    transport_tri_semi.F90:117-140) plus the LITERAL/INTENDED switches of SURVEY appendix B."""
+    _fields_ = [
+        ("n_split", C.c_int32), ("multi_levels", C.c_int32), ("n_smooth", C.c_int32), ("n_multigrid", C.c_int32),
+        ("n_coarse_smooth", C.c_int32), ("solver", C.c_int32), ("face_terms", C.c_int32),
+        ("literal_source", C.c_int32), ("transfer", C.c_int32), ("residual_sign", C.c_int32),
+        ("halo_rule", C.c_int32), ("coarse_bc_zero", C.c_int32),
+        ("theta", C.c_double), ("dt", C.c_double), ("k", C.c_double), ("omega", C.c_double),
+        ("u_x", C.c_double), ("u_y", C.c_double), ("source_coef", C.c_double),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Loads the in-tree CUDA library; fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PamgError(ERR_STATE, f"{LIB_PATH} is missing: run `python __graft_entry__.py build` "
+                                   "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, ci, cd = C.c_void_p, C.c_int, C.c_double
+    pvp = C.POINTER(C.c_void_p)
+    pint = C.POINTER(C.c_int)
+    pdbl = C.POINTER(C.c_double)
+    sig = {
+        "pamg_version": (C.c_char_p, []),
+        "pamg_device_count": (ci, [pint]),
+        "pamg_default_params": (None, [C.POINTER(Params), ci]),
+        "pamg_mesh_read_msh": (ci, [C.c_char_p, pvp]),
+        "pamg_mesh_synthetic": (ci, [ci, ci, pvp]),
+        "pamg_mesh_from_arrays": (ci, [ci, _f64, vp, pvp]),
+        "pamg_mesh_size": (ci, [vp, pint]),
+        "pamg_mesh_get": (ci, [vp, vp, vp, vp, vp, vp]),
+        "pamg_mesh_free": (None, [vp]),
+        "pamg_create": (ci, [C.POINTER(Params), ci, pvp]),
+        "pamg_destroy": (None, [vp]),
+        "pamg_last_error": (C.c_char_p, [vp]),
+        "pamg_set_parents": (ci, [vp, ci, _f64, _i32, _i32, _i32]),
+        "pamg_set_parents_partition": (ci, [vp, ci, _f64, _i32, _i32, _i32, ci, _i32, ci]),
+        "pamg_ndof": (ci, [vp, ci, C.POINTER(C.c_int64)]),
+        "pamg_upload_field": (ci, [vp, ci, ci, vp]),
+        "pamg_download_field": (ci, [vp, ci, ci, vp]),
+        "pamg_fill_field": (ci, [vp, ci, ci, cd]),
+        "pamg_copy_field": (ci, [vp, ci, ci, ci]),
+        "pamg_download_overlap": (ci, [vp, ci, ci, _f64]),
+        "pamg_device_ptr": (ci, [vp, ci, ci, pvp]),
+        "pamg_update_overlaps": (ci, [vp, ci]),
+        "pamg_build_rhs": (ci, [vp]),
+        "pamg_smooth": (ci, [vp, ci, ci, ci]),
+        "pamg_residual": (ci, [vp, ci, pdbl, pdbl]),
+        "pamg_convergence": (ci, [vp, ci, pdbl]),
+        "pamg_restrict": (ci, [vp, ci]),
+        "pamg_prolong": (ci, [vp, ci]),
+        "pamg_vcycle_solve": (ci, [vp, ci, ci, ci, ci, ci, cd, pint, _f64]),
+        "pamg_literal_timestep": (ci, [vp, ci, ci, ci]),
+        "pamg_timestep_host": (ci, [vp, vp, vp, ci, cd, pint, pdbl]),
+        "pamg_halo_plan": (ci, [ci, _f64, _i32, _i32, _i32, ci, ci, _i32, ci, _i32, _i32, _i32, _i32, _i32, _i32]),
+        "pamg_comm_unique_id": (ci, [C.c_char_p]),
+        "pamg_comm_init": (ci, [vp, C.c_char_p, ci, ci]),
+        "pamg_halo_peer_count": (ci, [vp, pint]),
+        "pamg_halo_peer_info": (ci, [vp, ci, pint, pint]),
+        "pamg_set_unstructured": (ci, [vp, ci, _f64, _i32, _i32]),
+        "pamg_unstr_upload": (ci, [vp, _f64]),
+        "pamg_unstr_download": (ci, [vp, _f64]),
+        "pamg_explicit_step": (ci, [vp, cd, cd, cd, cd, ci, ci, ci, ci, ci]),
+        "pamg_apply_local_minv": (ci, [vp, ci, ci, _f64, vp, vp, vp, vp]),
+        "pamg_sync": (ci, [vp]),
+        "pamg_event_record": (ci, [vp, ci]),
+        "pamg_event_elapsed_ms": (ci, [vp, ci, ci, C.POINTER(C.c_float)]),
+        "pamg_launch_count": (ci, [vp, C.POINTER(C.c_int64)]),
+        "pamg_flush_l2": (ci, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    L._signatures = sig
+    _lib = L
+    return L
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = lib().pamg_device_count(C.byref(n))
+    return n.value if rc == OK else 0
+
+
+def default_params(literal_head=False, **kw):
+    p = Params()
+    lib().pamg_default_params(C.byref(p), 1 if literal_head else 0)
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    if "k" in kw and "source_coef" not in kw:
+        p.source_coef = (-2.0 if literal_head else 2.0) * p.k
+    return p
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+# ------------------------------------------------------------------------------ mesh (host)
+class Mesh:
+    """Parent triangles with the reference's Mesh%X / Neig / fNeig / Dir / region_id
+    (Structures.F90:143-170) built by the O(N) host pipeline."""
+
+    def __init__(self, handle):
+        self._h = handle
+        L = lib()
+        n = C.c_int(0)
+        L.pamg_mesh_size(handle, C.byref(n))
+        self.U = n.value
+        self.X = np.zeros((self.U, 3, 2))
+        self.neig = np.zeros((self.U, 3), np.int32)
+        self.fneig = np.zeros((self.U, 3), np.int32)
+        self.dir = np.zeros((self.U, 3), np.int32)
+        self.region = np.zeros(self.U, np.int32)
+        L.pamg_mesh_get(handle, _ptr(self.X), _ptr(self.neig), _ptr(self.fneig), _ptr(self.dir), _ptr(self.region))
+        L.pamg_mesh_free(handle)
+        self._h = None
+
+    @classmethod
+    def read_msh(cls, path):
+        """ReadMSH (Msh2Tri.F90:132) + getNeigDataMesh (:454)."""
+        h = C.c_void_p()
+        rc = lib().pamg_mesh_read_msh(os.fsencode(path), C.byref(h))
+        if rc != OK:
+            raise PamgError(rc, f"cannot read gmsh 2.2 ASCII mesh {path}")
+        return cls(h)
+
+    @classmethod
+    def synthetic(cls, kp, G=1):
+        h = C.c_void_p()
+        rc = lib().pamg_mesh_synthetic(kp, G, C.byref(h))
+        if rc != OK:
+            raise PamgError(rc, "pamg_mesh_synthetic")
+        return cls(h)
+
+    @classmethod
+    def from_arrays(cls, X, region=None):
+        X = np.ascontiguousarray(X, np.float64)
+        reg = None if region is None else np.ascontiguousarray(region, np.int32)
+        h = C.c_void_p()
+        rc = lib().pamg_mesh_from_arrays(X.shape[0], X, _ptr(reg), C.byref(h))
+        if rc != OK:
+            raise PamgError(rc, "pamg_mesh_from_arrays")
+        return cls(h)
+
+
+def halo_plan(mesh, halo_rule=1, nparts=1, part_first=None, my_part=0):
+    """Host-only description of where every halo strip lives (pamg_plan.cpp)."""
+    U = mesh.U
+    pf = np.ascontiguousarray(part_first if part_first is not None else [0, U], np.int32)
+    ul = int(pf[my_part + 1] - pf[my_part])
+    out = {k: np.zeros(ul * 3, np.int32) for k in ("strip_of", "dst_strip", "rev", "hmap")}
+    peers = np.zeros(max(nparts, 1) * 4, np.int32)
+    counts = np.zeros(5, np.int32)
+    rc = lib().pamg_halo_plan(U, mesh.X, mesh.neig, mesh.fneig, mesh.dir, halo_rule, nparts, pf, my_part,
+                              out["strip_of"], out["dst_strip"], out["rev"], out["hmap"], peers, counts)
+    if rc != OK:
+        raise PamgError(rc, "pamg_halo_plan")
+    out["peers"] = peers.reshape(-1, 4)[: counts[0]].copy()
+    out["nstrips"], out["nsend"], out["U_local"], out["first"] = (int(c) for c in counts[1:5])
+    return out
+
+
+# ------------------------------------------------------------------------------ solver handle
+class SemiImplicitIterative:
+    """GPU implementation of Semi_implicit_iterative's contained procedures
+    (transport_tri_semi.F90:14-891).  Method names follow the reference."""
+
+    def __init__(self, params, mesh, device=0, nparts=1, part_first=None, my_part=0):
+        self.L = lib()
+        self.params = params
+        self.mesh = mesh
+        h = C.c_void_p()
+        rc = self.L.pamg_create(C.byref(params), device, C.byref(h))
+        if rc != OK:
+            raise PamgError(rc, "pamg_create failed (no CUDA device? there is no CPU fallback)")
+        self.h = h
+        if nparts == 1:
+            self._ck(self.L.pamg_set_parents(h, mesh.U, mesh.X, mesh.neig, mesh.fneig, mesh.dir))
+            self.U = mesh.U
+        else:
+            pf = np.ascontiguousarray(part_first, np.int32)
+            self._ck(self.L.pamg_set_parents_partition(h, mesh.U, mesh.X, mesh.neig, mesh.fneig, mesh.dir,
+                                                       nparts, pf, my_part))
+            self.U = int(pf[my_part + 1] - pf[my_part])
+
+    def _ck(self, rc):
+        if rc != OK:
+            raise PamgError(rc, (self.L.pamg_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pamg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- fields -------------------------------------------------------------------------------
+    def split(self, level):
+        return self.params.n_split - level + 1
+
+    def shape(self, level=1):
+        return (self.U, 4 ** self.split(level), 3)
+
+    def ndof(self, level=1):
+        n = C.c_int64()
+        self._ck(self.L.pamg_ndof(self.h, level, C.byref(n)))
+        return n.value
+
+    def upload(self, field, level, array):
+        a = np.ascontiguousarray(array, np.float64)
+        assert a.size == self.ndof(level)
+        self._ck(self.L.pamg_upload_field(self.h, field, level, _ptr(a)))
+
+    def download(self, field, level=1):
+        out = np.empty(self.shape(level))
+        self._ck(self.L.pamg_download_field(self.h, field, level, _ptr(out)))
+        return out
+
+    def fill(self, field, level, value):
+        self._ck(self.L.pamg_fill_field(self.h, field, level, float(value)))
+
+    def copy(self, level, dst, src):
+        self._ck(self.L.pamg_copy_field(self.h, level, dst, src))
+
+    def overlap(self, level=1, old=False):
+        S = 2 ** self.split(level)
+        out = np.zeros((self.U, 3, S, 3))
+        self._ck(self.L.pamg_download_overlap(self.h, level, 1 if old else 0, out))
+        return out
+
+    # -- the contained procedures ---------------------------------------------------------------
+    def update_overlaps(self, level=1):
+        """update_overlaps (splitting.F90:1210)."""
+        self._ck(self.L.pamg_update_overlaps(self.h, level))
+
+    def get_RHS(self):
+        """get_RHS (transport_tri_semi.F90:452) for every level-1 child."""
+        self._ck(self.L.pamg_build_rhs(self.h))
+
+    def smoother(self, level=1, solver=None, n_smooth=None):
+        """smoother (:543): n_smooth sweeps of solver 1 Jacobi / 2 Richardson / 3 Gauss-Seidel."""
+        self._ck(self.L.pamg_smooth(self.h, level, solver or self.params.solver,
+                                    self.params.n_smooth if n_smooth is None else n_smooth))
+
+    def get_residual(self, level=1):
+        """get_residual (:725); returns (||r||_2, ||r||_inf)."""
+        l2, li = C.c_double(), C.c_double()
+        self._ck(self.L.pamg_residual(self.h, level, C.byref(l2), C.byref(li)))
+        return l2.value, li.value
+
+    def get_convergence(self, level=1):
+        """get_convergence (:876): signed max of the residual, floor 0."""
+        c = C.c_double()
+        self._ck(self.L.pamg_convergence(self.h, level, C.byref(c)))
+        return c.value
+
+    def restrictor(self, fine_level):
+        """restrictor (splitting.F90:10)."""
+        self._ck(self.L.pamg_restrict(self.h, fine_level))
+
+    def prolongator(self, fine_level):
+        """prolongator (splitting.F90:38)."""
+        self._ck(self.L.pamg_prolong(self.h, fine_level))
+
+    def vcycle_solve(self, solver=None, nu1=None, nu2=None, ncoarse=None, max_cycles=50, tol=1e-8):
+        p = self.params
+        hist = np.zeros(max_cycles + 2)
+        cyc = C.c_int(0)
+        self._ck(self.L.pamg_vcycle_solve(self.h, solver or p.solver, p.n_smooth if nu1 is None else nu1,
+                                          p.n_smooth if nu2 is None else nu2,
+                                          p.n_coarse_smooth if ncoarse is None else ncoarse, max_cycles, tol,
+                                          C.byref(cyc), hist))
+        return cyc.value, hist[: min(cyc.value, max_cycles) + 1]
+
+    def literal_timestep(self, solver=None, n_multigrid=None, n_smooth=None):
+        """One itime of the loop at transport_tri_semi.F90:316-379 exactly as checked in."""
+        p = self.params
+        self._ck(self.L.pamg_literal_timestep(self.h, solver or p.solver, n_multigrid or p.n_multigrid,
+                                              n_smooth or p.n_smooth))
+
+    def timestep_host(self, tnew_in, tnew_out, max_cycles=50, tol=1e-8):
+        """Reference-facing time step with HOST buffers (upload, told=tnew, V-cycles, download)."""
+        cyc, rel = C.c_int(0), C.c_double(0)
+        self._ck(self.L.pamg_timestep_host(self.h, _ptr(tnew_in), _ptr(tnew_out), max_cycles, tol,
+                                           C.byref(cyc), C.byref(rel)))
+        return cyc.value, rel.value
+
+    # -- distributed -----------------------------------------------------------------------------
+    def comm_init(self, unique_id, nranks, rank):
+        self._ck(self.L.pamg_comm_init(self.h, unique_id, nranks, rank))
+
+    # -- timing ------------------------------------------------------------------------------------
+    def sync(self):
+        self._ck(self.L.pamg_sync(self.h))
+
+    def event_record(self, slot):
+        self._ck(self.L.pamg_event_record(self.h, slot))
+
+    def elapsed_ms(self, a, b):
+        ms = C.c_float()
+        self._ck(self.L.pamg_event_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_int64()
+        self._ck(self.L.pamg_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def flush_l2(self):
+        self._ck(self.L.pamg_flush_l2(self.h))
+
+    # -- unstructured explicit (unstr_explicit, transport_tri_unstr.F90:413) ------------------------
+    def set_unstructured(self, mesh):
+        self._ck(self.L.pamg_set_unstructured(self.h, mesh.U, mesh.X, mesh.neig, mesh.fneig))
+        self._E = mesh.U
+
+    def unstr_explicit(self, tnew, dt, u_x, u_y, ntime=2, nits=2, njac_its=10, t_bc=0.0, exact_minv=False,
+                       use_dir=False):
+        t = np.ascontiguousarray(tnew, np.float64)
+        self._ck(self.L.pamg_unstr_upload(self.h, t))
+        self._ck(self.L.pamg_explicit_step(self.h, dt, u_x, u_y, t_bc, ntime, nits, njac_its, int(exact_minv),
+                                           int(use_dir)))
+        out = np.empty_like(t)
+        self._ck(self.L.pamg_unstr_download(self.h, out))
+        return out
+
+    def findinv(self, M, rhs=None):
+        """Batched FINDInv (matrices.F90:1618): returns (Minv, x, status)."""
+        M = np.ascontiguousarray(M, np.float64)
+        batch, n = M.shape[0], M.shape[1]
+        Minv = np.zeros_like(M)
+        status = np.zeros(batch, np.int32)
+        r = None if rhs is None else np.ascontiguousarray(rhs, np.float64)
+        x = None if rhs is None else np.zeros_like(r)
+        rc = self.L.pamg_apply_local_minv(self.h, n, batch, M, _ptr(r), _ptr(x), _ptr(Minv), _ptr(status))
+        if rc not in (OK, ERR_SINGULAR):
+            self._ck(rc)
+        return Minv, x, status
+
+
+def get_unique_id():
+    buf = C.create_string_buffer(128)
+    rc = lib().pamg_comm_unique_id(buf)
+    if rc != OK:
+        raise PamgError(rc, "pamg_comm_unique_id (libnccl.so.2 missing?)")
+    return buf.raw

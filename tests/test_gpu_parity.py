@@ -1,0 +1,274 @@
+"""GPU parity tests proper: every kernel of the hot path, called through the C ABI (ctypes), against the
+CPU oracle on identical seeded inputs.  Tolerance for floating point: relative L2 <= 1e-12 per Jacobi
+sweep and per residual evaluation (BASELINE.json north_star); copies are bit-exact."""
+import numpy as np
+import pytest
+
+import oracle_api as orc
+from helpers import rel_l2, rng_field, write_msh
+from pamg_pkg import pamg
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def make_pair(mesh, n, levels, intended, u=(0.0, 0.0), dt=None, halo_rule=None, **kw):
+    if intended:
+        op = orc.intended_params(n, levels, dt=dt or 1e-3, u=u)
+    else:
+        op = orc.literal_params(n, levels, dt=dt or 1.25e-5, u=u)
+    if halo_rule is not None:
+        op.halo_rule = halo_rule
+    for k, v in kw.items():
+        setattr(op, k, v)
+    gp = pamg.default_params(literal_head=not intended, n_split=n, multi_levels=levels)
+    for f in ("face_terms", "literal_source", "transfer", "residual_sign", "halo_rule", "coarse_bc_zero",
+              "theta", "dt", "k", "omega", "u_x", "u_y", "source_coef"):
+        setattr(gp, f, getattr(op, f))
+    o = orc.Semi(op, mesh.X, mesh.neig, mesh.fneig, mesh.dir)
+    g = pamg.SemiImplicitIterative(gp, mesh)
+    return o, g
+
+
+def seed_fields(o, g, level=1, seed=20221, with_rhs=False):
+    shape = g.shape(level)
+    T = rng_field(shape, seed)
+    Told = rng_field(shape, seed + 1)
+    o.field(orc.TNONLIN, level)[:] = T
+    o.field(orc.TNEW, level)[:] = T
+    o.field(orc.TOLD, level)[:] = Told
+    g.upload(pamg.TNONLIN, level, T)
+    g.copy(level, pamg.TNEW, pamg.TNONLIN)
+    g.upload(pamg.TOLD, level, Told)
+    if with_rhs:
+        R = rng_field(shape, seed + 2)
+        o.field(orc.RHS, level)[:] = R
+        g.upload(pamg.RHS, level, R)
+    return T, Told
+
+
+@pytest.fixture(scope="module")
+def meshes(tmp_path_factory):
+    d = tmp_path_factory.mktemp("msh")
+    out = {}
+    for name in ("test_sn2", "split0", "split1", "900_ele", "untitled8192", "irregular"):
+        out[name] = pamg.Mesh.read_msh(write_msh(name, str(d / (name + ".msh"))))
+    out["syn"] = pamg.Mesh.synthetic(1, 2)
+    return out
+
+
+@pytest.mark.parametrize("name,n", [("test_sn2", 1), ("test_sn2", 3), ("split0", 5), ("irregular", 2), ("syn", 4)])
+@pytest.mark.parametrize("rule", [0, 1])
+def test_update_overlaps(meshes, name, n, rule):
+    o, g = make_pair(meshes[name], n, 1, True, halo_rule=rule)
+    seed_fields(o, g)
+    o.update_overlaps(1)
+    g.update_overlaps(1)
+    ref, got = o.overlap(1), g.overlap(1)
+    interior = meshes[name].neig != 0
+    assert np.array_equal(got[interior], ref[interior])          # copies: bit exact
+    assert np.allclose(got[~interior], ref[~interior], rtol=0, atol=4e-16)   # sin(x+y) Dirichlet data
+    assert np.array_equal(g.overlap(1, old=True)[interior], o.overlap(1, old=True)[interior])
+
+
+@pytest.mark.parametrize("literal_source", [0, 1])
+def test_build_rhs(meshes, literal_source):
+    o, g = make_pair(meshes["test_sn2"], 3, 1, True, literal_source=literal_source)
+    seed_fields(o, g)
+    o.build_rhs()
+    g.get_RHS()
+    assert rel_l2(g.download(pamg.RHS), o.field(orc.RHS)) <= TOL
+
+
+SWEEP_CASES = [
+    # mesh, n_split, intended, velocity
+    ("test_sn2", 1, False, (0.0, 0.0)),       # HEAD default (main.F90:46, mesh at transport_tri_semi.F90:99)
+    ("test_sn2", 3, True, (0.0, 0.0)),
+    ("test_sn2", 3, True, (0.9, 0.3)),
+    ("split0", 1, True, (0.9, 0.3)),
+    ("split0", 4, True, (0.9, 0.3)),
+    ("split0", 6, True, (0.0, 0.0)),
+    ("split1", 3, False, (0.1, 0.1)),
+    ("900_ele", 2, True, (0.1, 0.1)),          # config c1
+    ("900_ele", 1, False, (0.0, 0.0)),
+    ("irregular", 3, True, (-0.4, 0.7)),
+    ("syn", 5, True, (0.9, 0.3)),
+]
+
+
+@pytest.mark.parametrize("name,n,intended,u", SWEEP_CASES)
+def test_jacobi_sweep_and_residual(meshes, name, n, intended, u):
+    o, g = make_pair(meshes[name], n, 1, intended, u=u)
+    seed_fields(o, g)
+    for sweep in range(3):                      # parity per sweep
+        o.smooth(1, 1, 1)
+        g.smoother(1, pamg.JACOBI, 1)
+        assert rel_l2(g.download(pamg.TNONLIN), o.field(orc.TNONLIN)) <= TOL, sweep
+        assert rel_l2(g.download(pamg.TNEW), o.field(orc.TNEW)) <= TOL
+    # residual evaluation on the swept field
+    o.field(orc.TNEW)[:] = o.field(orc.TNONLIN)
+    g.copy(1, pamg.TNEW, pamg.TNONLIN)
+    o.update_overlaps(1); g.update_overlaps(1)
+    l2o, lio = o.residual(1)
+    l2g, lig = g.get_residual(1)
+    assert rel_l2(g.download(pamg.RES), o.field(orc.RES)) <= TOL
+    assert abs(l2g - l2o) <= 1e-12 * l2o and abs(lig - lio) <= 1e-12 * lio
+    assert abs(g.get_convergence(1) - o.convergence(1)) <= 1e-12 * max(1.0, abs(lio))
+
+
+@pytest.mark.parametrize("name,n,u", [("test_sn2", 3, (0.9, 0.3)), ("split0", 5, (0.0, 0.0)), ("900_ele", 2, (0.1, 0.1)),
+                                      ("syn", 4, (0.9, 0.3))])
+def test_two_colour_gauss_seidel_sweep(meshes, name, n, u):
+    o, g = make_pair(meshes[name], n, 1, True, u=u)
+    seed_fields(o, g)
+    for sweep in range(3):
+        o.smooth(1, 4, 1)                       # oracle runs the same colouring: down children, then up
+        g.smoother(1, pamg.GAUSS_SEIDEL, 1)
+        assert rel_l2(g.download(pamg.TNONLIN), o.field(orc.TNONLIN)) <= TOL, sweep
+        assert rel_l2(g.download(pamg.TNEW), o.field(orc.TNEW)) <= TOL   # start-of-sweep copy (:550)
+
+
+def test_literal_head_gs_equals_reference_order(meshes):
+    """At HEAD the face block is commented out, so the lexicographic sweep of the reference and the
+    two-colour GPU sweep must agree to rounding."""
+    o, g = make_pair(meshes["test_sn2"], 2, 1, False)
+    seed_fields(o, g)
+    o.smooth(1, 3, 4)
+    g.smoother(1, pamg.GAUSS_SEIDEL, 4)
+    assert rel_l2(g.download(pamg.TNONLIN), o.field(orc.TNONLIN)) <= TOL
+
+
+def test_richardson_sweep(meshes):
+    o, g = make_pair(meshes["split0"], 3, 1, True, u=(0.9, 0.3), omega=1e-6)
+    seed_fields(o, g)
+    o.smooth(1, 2, 2)
+    g.smoother(1, pamg.RICHARDSON, 2)
+    assert rel_l2(g.download(pamg.TNONLIN), o.field(orc.TNONLIN)) <= TOL
+
+
+@pytest.mark.parametrize("transfer", [0, 1])
+@pytest.mark.parametrize("name,n", [("test_sn2", 3), ("split0", 5)])
+def test_restrict_and_prolong(meshes, name, n, transfer):
+    o, g = make_pair(meshes[name], n, n, True, transfer=transfer)
+    for lvl in range(1, n):
+        shape_f, shape_c = g.shape(lvl), g.shape(lvl + 1)
+        R = rng_field(shape_f, 7 + lvl)
+        o.field(orc.RES, lvl)[:] = R
+        g.upload(pamg.RES, lvl, R)
+        o.restrict(lvl); g.restrictor(lvl)
+        assert rel_l2(g.download(pamg.RHS, lvl + 1), o.field(orc.RHS, lvl + 1)) <= TOL
+        Tf, Tc = rng_field(shape_f, 70 + lvl), rng_field(shape_c, 700 + lvl)
+        for fld_o, fld_g in ((orc.TNONLIN, pamg.TNONLIN), (orc.TNEW, pamg.TNEW)):
+            o.field(fld_o, lvl)[:] = Tf; o.field(fld_o, lvl + 1)[:] = Tc
+        g.upload(pamg.TNONLIN, lvl, Tf); g.copy(lvl, pamg.TNEW, pamg.TNONLIN)
+        g.upload(pamg.TNONLIN, lvl + 1, Tc); g.copy(lvl + 1, pamg.TNEW, pamg.TNONLIN)
+        o.prolong(lvl); g.prolongator(lvl)
+        fld = (orc.TNEW, pamg.TNEW) if transfer == 0 else (orc.TNONLIN, pamg.TNONLIN)
+        assert rel_l2(g.download(fld[1], lvl), o.field(fld[0], lvl)) <= TOL
+
+
+@pytest.mark.parametrize("name,n,solver,u", [("split0", 4, 1, (0.0, 0.0)), ("split0", 5, 3, (0.0, 0.0)),
+                                             ("test_sn2", 4, 3, (0.3, 0.1)), ("900_ele", 2, 1, (0.1, 0.1))])
+def test_vcycle_to_1e8_matches_oracle(meshes, name, n, solver, u):
+    o, g = make_pair(meshes[name], n, n, True, u=u)
+    it_o, hist_o = o.vcycle_solve(solver=4 if solver == 3 else 1, nu1=4, nu2=4, ncoarse=15, max_cycles=40, tol=1e-8)
+    it_g, hist_g = g.vcycle_solve(solver=solver, nu1=4, nu2=4, ncoarse=15, max_cycles=40, tol=1e-8)
+    assert it_g <= 40 and abs(it_g - it_o) <= 1
+    assert hist_g[-1] / hist_g[0] <= 1e-8
+    m = min(len(hist_o), len(hist_g))
+    assert np.allclose(hist_g[:m], hist_o[:m], rtol=1e-6)
+    if it_g == it_o:
+        sol_o, sol_g = o.field(orc.TNONLIN), g.download(pamg.TNONLIN)
+        assert np.max(np.abs(sol_g - sol_o)) <= 1e-10 * max(1.0, np.max(np.abs(sol_o)))
+
+
+def test_literal_head_timestep_mode9(meshes):
+    """mode = 9 exactly as checked in: test_sn2.msh, n_split 1, multi_levels 1, GS, n_smooth 4, n_multigrid 2,
+    IC T = 1 where region_id == 4 (main.F90:46-47, transport_tri_semi.F90:99,118,249-251)."""
+    mesh = meshes["test_sn2"]
+    o, g = make_pair(mesh, 1, 1, False)
+    ic = np.zeros(g.shape(1))
+    ic[mesh.region == 4] = 1.0
+    o.field(orc.TNEW)[:] = ic
+    g.upload(pamg.TNEW, 1, ic)
+    for step in range(2):                       # ntime = 2 (:135)
+        o.literal_timestep(solver=3, n_multigrid=2, n_smooth=4)
+        g.literal_timestep(solver=3, n_multigrid=2, n_smooth=4)
+        assert rel_l2(g.download(pamg.TNEW), o.field(orc.TNEW)) <= TOL
+        assert rel_l2(g.download(pamg.TNONLIN), o.field(orc.TNONLIN)) <= TOL
+        assert rel_l2(g.download(pamg.RES), o.field(orc.RES)) <= 1e-10
+
+
+def test_literal_multilevel_timestep(meshes):
+    o, g = make_pair(meshes["split0"], 3, 3, False, u=(0.1, 0.1))
+    ic = rng_field(g.shape(1), 5)
+    o.field(orc.TNEW)[:] = ic
+    g.upload(pamg.TNEW, 1, ic)
+    o.literal_timestep(solver=1, n_multigrid=2, n_smooth=4)
+    g.literal_timestep(solver=1, n_multigrid=2, n_smooth=4)
+    for lvl in (1, 2, 3):
+        assert rel_l2(g.download(pamg.TNEW, lvl), o.field(orc.TNEW, lvl)) <= 1e-11, lvl
+
+
+@pytest.mark.parametrize("exact,use_dir", [(0, 0), (1, 0), (0, 1)])
+def test_unstr_explicit_config2(meshes, exact, use_dir):
+    """unstr_explicit with the literal arguments of main.F90:28 on untitled8192.msh (IC tag 12)."""
+    mesh = meshes["untitled8192"]
+    g = pamg.SemiImplicitIterative(pamg.default_params(), pamg.Mesh.synthetic(0, 1))
+    g.set_unstructured(mesh)
+    T0 = np.zeros((mesh.U, 3))
+    T0[mesh.region == 12] = 1.0
+    dt = 0.07 * 1e-3
+    ref = T0.copy()
+    orc.lib().orc_unstr_explicit(mesh.U, mesh.X, mesh.neig, mesh.fneig, mesh.dir, 0.9, 0.0, dt, 2, 2, 10, exact,
+                                 use_dir, 0.0, ref)
+    got = g.unstr_explicit(T0, dt, 0.9, 0.0, ntime=2, nits=2, njac_its=10, exact_minv=bool(exact), use_dir=bool(use_dir))
+    assert rel_l2(got, ref) <= TOL
+    assert np.max(np.abs(got - ref)) <= 1e-13
+
+
+def test_unstr_explicit_random_field_long(meshes):
+    mesh = meshes["split1"]
+    g = pamg.SemiImplicitIterative(pamg.default_params(), pamg.Mesh.synthetic(0, 1))
+    g.set_unstructured(mesh)
+    T0 = rng_field((mesh.U, 3), 3)
+    ref = T0.copy()
+    orc.lib().orc_unstr_explicit(mesh.U, mesh.X, mesh.neig, mesh.fneig, mesh.dir, 0.4, -0.7, 1e-3, 5, 2, 10, 0, 1, 0.25, ref)
+    got = g.unstr_explicit(T0, 1e-3, 0.4, -0.7, ntime=5, nits=2, njac_its=10, t_bc=0.25, use_dir=True)
+    assert rel_l2(got, ref) <= TOL
+
+
+@pytest.mark.parametrize("n", [3, 4, 6])
+def test_batched_local_inverse(n):
+    g = pamg.SemiImplicitIterative(pamg.default_params(), pamg.Mesh.synthetic(0, 1))
+    rng = np.random.default_rng(n)
+    B = 1000
+    M = rng.random((B, n, n)) + n * np.eye(n)
+    M[5] = 0.0                                   # singular block -> errorflag -1, inverse = 0
+    if n == 3:
+        A = 0.37
+        M[6] = A / 12 * (np.ones((3, 3)) + np.eye(3))   # P1 mass matrix: inverse (12/A)(I - J/4)
+    M[7, 0, 0] = 0.0                             # zero leading pivot: repaired by adding row 2
+    rhs = rng.random((B, n))
+    Minv, x, status = g.findinv(M, rhs)
+    for b in range(B):
+        ref = np.zeros(n * n)
+        flag = orc.lib().orc_findinv(np.ascontiguousarray(M[b].ravel()), ref, n)
+        assert status[b] == flag
+        assert np.allclose(Minv[b].ravel(), ref, rtol=1e-12, atol=1e-13)
+        if flag == 0:
+            assert np.allclose(x[b], ref.reshape(n, n) @ rhs[b], rtol=1e-12, atol=1e-13)
+    assert status[5] == -1 and np.all(Minv[5] == 0)
+    if n == 3:
+        assert np.allclose(Minv[6], 12 / 0.37 * (np.eye(3) - 0.25 * np.ones((3, 3))), rtol=1e-12)
+
+
+def test_errors_are_reported_not_swallowed(meshes):
+    p = pamg.default_params(n_split=2, multi_levels=3)
+    with pytest.raises(pamg.PamgError):
+        pamg.SemiImplicitIterative(p, meshes["test_sn2"])       # multi_levels > n_split (:120-123)
+    g = pamg.SemiImplicitIterative(pamg.default_params(n_split=2, multi_levels=1), meshes["test_sn2"])
+    with pytest.raises(pamg.PamgError):
+        g.smoother(2, 1, 1)                                      # no such level
+    with pytest.raises(pamg.PamgError):
+        g.smoother(1, 9, 1)                                      # unknown solver (select case default)
