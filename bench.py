@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- DG DOF-updates/s of the smoother sweep (and V-cycle time to 1e-8) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    torchrun --nproc-per-node N ... bench.py --gpus N --steps K --warmup W      (N > 1)
+
+Workload (BASELINE.json configs[4], SURVEY 8(d) "c5"): synthetic semi-structured triangle mesh,
+kp = 4 (256 parents per GPU), n_split = 8 -> 16 777 216 P1 DG elements = 50.3 M DOFs PER GPU (weak
+scaling: N GPUs hold N super-triangles coupled through ordinary parent faces; halo over NCCL).
+One step = one call of the reference's `smoother` (transport_tri_semi.F90:543-722) on level 1:
+n_smooth = 4 Jacobi sweeps, each preceded by update_overlaps.  Fields (403 MB each) are far larger than
+the 126 MB L2, so no flush is needed between timed iterations.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+KP, NSPLIT, NSMOOTH = 4, 8, 4
+BYTES_PER_DOF_JACOBI = 24.0      # read T, read b, write T' 
+METRIC = "DG DOF-updates/s per smoother sweep"
+UNIT = "DOF-updates/s"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm)); out["sm_max_mhz"] = float(max(mx)); out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def oracle_api():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_api as orc       # CPU oracle: only used for the cpu_baseline / --impl reference legs
+    return orc
+
+
+def cpu_smoother_rate(orc, pkg, kp, threads, sweeps):
+    """DOF-updates/s of the oracle's smoother (Jacobi, face block on) on 4**kp parents x 4**8 children."""
+    mesh = pkg.Mesh.synthetic(kp, 1)
+    p = orc.intended_params(NSPLIT, 1, dt=1e-3, u=(0.9, 0.3))
+    s = orc.Semi(p, mesh.X, mesh.neig, mesh.fneig, mesh.dir)
+    rng = np.random.Generator(np.random.MT19937(20221))
+    s.field(orc.TNONLIN)[:] = rng.random(s.field(orc.TNONLIN).shape)
+    s.field(orc.TOLD)[:] = rng.random(s.field(orc.TOLD).shape)
+    orc.lib().orc_semi_set_threads(threads)
+    t0 = time.perf_counter()
+    s.smooth(1, 1, sweeps)
+    dt = time.perf_counter() - t0
+    ndof = s.field(orc.TNEW).size
+    del s
+    return ndof * sweeps / dt, ndof, dt
+
+
+def run_reference(args, rank):
+    """Reference arm: the reference's own CPU algorithm (C++ restatement; the Fortran cannot be compiled
+    here) on the host cores, all threads, same metric / config."""
+    if rank != 0:
+        return
+    pkg = importlib.import_module("p-a_multigrids_b200")
+    orc = oracle_api()
+    cores = os.cpu_count() or 1
+    # calibrate on 16 parents, then pick the sample so that the whole run stays within ~2 minutes
+    rate, _, _ = cpu_smoother_rate(orc, pkg, 2, cores, 1)
+    total = args.steps + args.warmup
+    kp = KP
+    while kp > 1 and (3 * 4 ** (kp + NSPLIT) * NSMOOTH * total) / rate > 120.0:
+        kp -= 1
+    mesh = pkg.Mesh.synthetic(kp, 1)
+    p = orc.intended_params(NSPLIT, 1, dt=1e-3, u=(0.9, 0.3))
+    s = orc.Semi(p, mesh.X, mesh.neig, mesh.fneig, mesh.dir)
+    rng = np.random.Generator(np.random.MT19937(20221))
+    s.field(orc.TNONLIN)[:] = rng.random(s.field(orc.TNONLIN).shape)
+    s.field(orc.TOLD)[:] = rng.random(s.field(orc.TOLD).shape)
+    orc.lib().orc_semi_set_threads(cores)
+    for _ in range(args.warmup):
+        s.smooth(1, 1, NSMOOTH)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        s.smooth(1, 1, NSMOOTH)
+    dt = time.perf_counter() - t0
+    ndof = s.field(orc.TNEW).size
+    value = ndof * NSMOOTH * args.steps / dt
+    sample = f"{4 ** kp} of 256 parents x 4^8 children ({ndof} DOFs), {NSMOOTH} Jacobi sweeps per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference Fortran cannot be compiled in this image (no Fortran compiler); this is the fp64 C++ "
+                "restatement of its algorithm (oracle/), OpenMP over parents",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    return {"workload": f"c5: synthetic semi-structured triangles, kp={KP} (256 parents) x n_split={NSPLIT} = 16777216 "
+                        f"elements (50.3M DOFs) per GPU; smoother = {NSMOOTH} Jacobi sweeps + update_overlaps on level 1",
+            "elements_per_gpu": 4 ** (KP + NSPLIT), "n_split": NSPLIT, "parents_per_gpu": 4 ** KP,
+            "n_smooth": NSMOOTH, "face_terms": 1, "velocity": [0.9, 0.3], "dt": 1e-3, "k": 1.0, "omega": 0.8,
+            "parallelism": f"parent-partition x{n}, NCCL halo", "l2_policy": "inputs larger than L2 (403 MB per field)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="pamg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vcycle", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    args.warmup = max(args.warmup, 3)
+    pkg = importlib.import_module("p-a_multigrids_b200")
+    if pkg.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group(backend="gloo")   # control plane only; the data path is NCCL inside libpamg_cuda
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def allmax(v):
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- set-up: mesh, partition, handle ------------------------------------------------------------
+    mesh = pkg.Mesh.synthetic(KP, world)
+    per = 4 ** KP
+    params = pkg.default_params(n_split=NSPLIT, multi_levels=NSPLIT, n_smooth=NSMOOTH, solver=pkg.JACOBI,
+                                u_x=0.9, u_y=0.3, dt=1e-3)
+    part_first = np.arange(world + 1, dtype=np.int32) * per
+    g = pkg.SemiImplicitIterative(params, mesh, device=local, nparts=world, part_first=part_first, my_part=rank)
+    if world > 1:
+        ids = [pkg.get_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        g.comm_init(ids[0], world, rank)
+    ndof = g.ndof(1)
+    rng = np.random.Generator(np.random.MT19937(20221 + rank))
+    pin_in = pkg.PinnedBuffer(ndof)
+    pin_out = pkg.PinnedBuffer(ndof)
+    pin_in.array[:] = rng.random(ndof)
+    g.upload(pkg.TOLD, 1, rng.random(ndof))
+    g.upload_ptr(pkg.TNONLIN, 1, pin_in.ptr)
+    g.copy(1, pkg.TNEW, pkg.TNONLIN)
+
+    def step():
+        g.smoother(1, pkg.JACOBI, NSMOOTH)
+
+    # ---- device-resident timing ----------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    g.sync(); barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    g.profile(True)
+    l0 = g.launch_count()
+    g.sync(); barrier()
+    g.event_record(0)
+    for _ in range(args.steps):
+        step()
+    g.event_record(1)
+    g.sync(); barrier()
+    ms = allmax(g.elapsed_ms(0, 1))
+    launches = g.launch_count() - l0
+    kern_ms, kern_n = g.profile_read()
+    g.profile(False)
+    value = world * ndof * NSMOOTH * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the C ABI with HOST buffers ---------------------------------------------------
+    # every step: pinned host -> device copy of the field, the smoother call, device -> host read of the result
+    def e2e_step():
+        g.upload_ptr(pkg.TNONLIN, 1, pin_in.ptr)
+        g.copy(1, pkg.TNEW, pkg.TNONLIN)
+        step()
+        g.download_ptr(pkg.TNONLIN, 1, pin_out.ptr)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_step()
+    g.sync(); barrier()
+    t0 = time.perf_counter()
+    g.event_record(2)
+    for _ in range(e2e_steps):
+        e2e_step()
+    g.event_record(3)
+    g.sync(); barrier()
+    e2e_ms = allmax(g.elapsed_ms(2, 3))
+    e2e_wall = allmax((time.perf_counter() - t0) * 1e3)
+    e2e_ms = max(e2e_ms, e2e_wall)      # blocking host copies: take the slower of device and host clocks
+    e2e_value = world * ndof * NSMOOTH * e2e_steps / (e2e_ms * 1e-3)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- V-cycle time to 1e-8 (second half of the BASELINE metric) ----------------------------------------
+    vc = None
+    if not args.no_vcycle:
+        gs = {}
+        for name, solver in (("jacobi", pkg.JACOBI), ("gauss_seidel", pkg.GAUSS_SEIDEL)):
+            g.fill(pkg.TNONLIN, 1, 0.0)
+            g.copy(1, pkg.TNEW, pkg.TNONLIN)
+            g.fill(pkg.TOLD, 1, 0.0)
+            g.sync(); barrier()
+            l1 = g.launch_count()
+            g.event_record(4)
+            cyc, hist = g.vcycle_solve(solver=solver, nu1=NSMOOTH, nu2=NSMOOTH, ncoarse=15, max_cycles=60, tol=1e-8)
+            g.event_record(5)
+            g.sync(); barrier()
+            gs[name] = {"cycles": cyc, "ms": allmax(g.elapsed_ms(4, 5)), "relres": float(hist[-1] / hist[0]),
+                        "launches": g.launch_count() - l1}
+        vc = gs
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        kern_avg_ms = kern_ms / max(kern_n, 1)
+        achieved = BYTES_PER_DOF_JACOBI * ndof / (kern_avg_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * ndof, "d2h_bytes_per_step": 8 * ndof,
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "k_element<JACOBI,face>", "kernel_avg_ms": kern_avg_ms,
+                         "kernel_launches_timed": kern_n, "algorithmic_bytes_per_launch": BYTES_PER_DOF_JACOBI * ndof,
+                         "peak_source": peak_src,
+                         "whole_step_frac": (BYTES_PER_DOF_JACOBI * ndof * NSMOOTH * args.steps / (ms * 1e-3) / 1e9) / peak},
+            "clocks": clocks,
+            "vcycle_to_1e-8": vc,
+        }
+        if not args.no_cpu_baseline:
+            orc = oracle_api()
+            cores = os.cpu_count() or 1
+            v1, nd1, t1 = cpu_smoother_rate(orc, pkg, 4, 1, 2)       # all 256 parents, 1 thread (serial like the reference)
+            vall, nd2, t2 = cpu_smoother_rate(orc, pkg, 4, cores, 2)  # all 256 parents, all cores
+            line["cpu_baseline"] = {
+                "value": v1, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"256 parents x 4^8 children ({nd1} DOFs), 2 Jacobi sweeps incl. update_overlaps, {t1:.1f} s",
+                "all_cores": {"value": vall, "cores": cores,
+                              "sample": f"full 256 parents ({nd2} DOFs), 2 sweeps, {t2:.1f} s, OpenMP over parents"}}
+        print(json.dumps(line), flush=True)
+    pin_in.free(); pin_out.free()
+    g.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

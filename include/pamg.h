@@ -156,6 +156,13 @@ int pamg_event_record(pamg_handle* h, int slot);       /* slot 0..15 */
 int pamg_event_elapsed_ms(pamg_handle* h, int slot_a, int slot_b, float* ms);
 int pamg_launch_count(const pamg_handle* h, int64_t* n); /* kernels launched by this handle so far */
 int pamg_flush_l2(pamg_handle* h);                     /* writes a 256 MiB scratch buffer */
+/* per-kernel device time of the element kernels (Jacobi / GS / residual): CUDA events recorded on the
+ * launching stream around each launch while profiling is on (at most 1024 launches are kept) */
+int pamg_profile(pamg_handle* h, int on);
+int pamg_profile_read(pamg_handle* h, double* total_ms, int* launches);
+/* pinned host memory for the HOST-buffer entry points */
+int pamg_host_alloc(void** p, int64_t bytes);
+int pamg_host_free(void* p);
 
 #ifdef __cplusplus
 }

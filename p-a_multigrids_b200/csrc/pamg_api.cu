@@ -82,6 +82,10 @@ struct pamg_handle {
   double* out3_host = nullptr;    // pinned
   double* scratch = nullptr; size_t scratch_bytes = 0;  // L2 flush
   double* stage = nullptr; size_t stage_bytes = 0;      // pinned staging for host-buffer entry points
+  // per-kernel timing (element kernels only)
+  bool profiling = false;
+  std::vector<cudaEvent_t> pev;  // pairs
+  int pev_used = 0;
   // distributed
   ncclComm_t comm = nullptr; int nranks = 1, rank = 0;
   // unstructured
@@ -237,8 +241,11 @@ int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout,
   a.Tin = Tin; a.Tout = Tout; a.rhs = L.rhs; a.ovl = L.ovl; a.pc = L.pc; a.strip_of = h->strip_of; a.hmap = h->hmap;
   a.partial = h->partial; a.omega = h->p.omega; a.rsign = (double)h->p.residual_sign; a.nelem = L.nelem; a.s = L.s;
   a.colour = colour;
+  const bool prof = h->profiling && h->pev_used + 2 <= (int)h->pev.size();
+  if (prof) CK(cudaEventRecord(h->pev[h->pev_used], h->stream));
   if (h->p.face_terms) k_element<MODE, true><<<grid, TPB, 0, h->stream>>>(a);
   else k_element<MODE, false><<<grid, TPB, 0, h->stream>>>(a);
+  if (prof) { CK(cudaEventRecord(h->pev[h->pev_used + 1], h->stream)); h->pev_used += 2; }
   h->launches++;
   CK(cudaGetLastError());
   return PAMG_OK;
@@ -445,6 +452,7 @@ void pamg_destroy(pamg_handle* h) {
   cudaFree(h->out3); cudaFreeHost(h->out3_host); cudaFree(h->scratch);
   if (h->stage) cudaFreeHost(h->stage);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : h->pev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -812,6 +820,40 @@ int pamg_launch_count(const pamg_handle* h, int64_t* n) {
   *n = h->launches;
   return PAMG_OK;
 }
+
+int pamg_profile(pamg_handle* h, int on) {
+  if (!h) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  if (on && h->pev.empty()) {
+    h->pev.resize(2048);
+    for (auto& e : h->pev) CK(cudaEventCreate(&e));
+  }
+  h->profiling = on != 0;
+  h->pev_used = 0;
+  return PAMG_OK;
+}
+
+int pamg_profile_read(pamg_handle* h, double* total_ms, int* launches) {
+  if (!h || !total_ms || !launches) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  double tot = 0.0;
+  for (int i = 0; i + 1 < h->pev_used; i += 2) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->pev[i], h->pev[i + 1]));
+    tot += ms;
+  }
+  *total_ms = tot;
+  *launches = h->pev_used / 2;
+  return PAMG_OK;
+}
+
+int pamg_host_alloc(void** p, int64_t bytes) {
+  if (!p || bytes <= 0) return PAMG_ERR_ARG;
+  return cudaMallocHost(p, (size_t)bytes) == cudaSuccess ? PAMG_OK : PAMG_ERR_CUDA;
+}
+
+int pamg_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? PAMG_OK : PAMG_ERR_CUDA; }
 
 int pamg_flush_l2(pamg_handle* h) {
   if (!h) return PAMG_ERR_ARG;

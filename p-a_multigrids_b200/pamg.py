@@ -104,6 +104,10 @@ def lib():
         "pamg_event_elapsed_ms": (ci, [vp, ci, ci, C.POINTER(C.c_float)]),
         "pamg_launch_count": (ci, [vp, C.POINTER(C.c_int64)]),
         "pamg_flush_l2": (ci, [vp]),
+        "pamg_profile": (ci, [vp, ci]),
+        "pamg_profile_read": (ci, [vp, pdbl, pint]),
+        "pamg_host_alloc": (ci, [pvp, C.c_int64]),
+        "pamg_host_free": (ci, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -354,6 +358,20 @@ class SemiImplicitIterative:
     def flush_l2(self):
         self._ck(self.L.pamg_flush_l2(self.h))
 
+    def profile(self, on=True):
+        self._ck(self.L.pamg_profile(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        ms, n = C.c_double(), C.c_int()
+        self._ck(self.L.pamg_profile_read(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def upload_ptr(self, field, level, host_ptr):
+        self._ck(self.L.pamg_upload_field(self.h, field, level, host_ptr))
+
+    def download_ptr(self, field, level, host_ptr):
+        self._ck(self.L.pamg_download_field(self.h, field, level, host_ptr))
+
     # -- unstructured explicit (unstr_explicit, transport_tri_unstr.F90:413) ------------------------
     def set_unstructured(self, mesh):
         self._ck(self.L.pamg_set_unstructured(self.h, mesh.U, mesh.X, mesh.neig, mesh.fneig))
@@ -381,6 +399,24 @@ class SemiImplicitIterative:
         if rc not in (OK, ERR_SINGULAR):
             self._ck(rc)
         return Minv, x, status
+
+
+class PinnedBuffer:
+    """cudaMallocHost buffer exposed as a numpy array (for the HOST-buffer entry points)."""
+
+    def __init__(self, n_doubles):
+        p = C.c_void_p()
+        rc = lib().pamg_host_alloc(C.byref(p), int(n_doubles) * 8)
+        if rc != OK:
+            raise PamgError(rc, "pamg_host_alloc")
+        self.ptr = p
+        self.array = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(int(n_doubles),))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().pamg_host_free(self.ptr)
+            self.ptr = None
 
 
 def get_unique_id():

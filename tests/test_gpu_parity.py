@@ -196,7 +196,9 @@ def test_literal_head_timestep_mode9(meshes):
         g.literal_timestep(solver=3, n_multigrid=2, n_smooth=4)
         assert rel_l2(g.download(pamg.TNEW), o.field(orc.TNEW)) <= TOL
         assert rel_l2(g.download(pamg.TNONLIN), o.field(orc.TNONLIN)) <= TOL
-        assert rel_l2(g.download(pamg.RES), o.field(orc.RES)) <= 1e-10
+        # the field has converged: r = A x - b is pure cancellation, so compare against the size of b
+        scale = np.max(np.abs(o.field(orc.RHS)))
+        assert np.max(np.abs(g.download(pamg.RES) - o.field(orc.RES))) <= 1e-13 * scale
 
 
 def test_literal_multilevel_timestep(meshes):
