@@ -206,6 +206,8 @@ def main():
     per = 4 ** KP
     params = pkg.default_params(n_split=NSPLIT, multi_levels=NSPLIT, n_smooth=NSMOOTH, solver=pkg.JACOBI,
                                 u_x=0.9, u_y=0.3, dt=1e-3)
+    if os.environ.get("PAMG_BENCH_FACE") == "0":      # experiment only: volume terms only (HEAD's operator)
+        params.face_terms = 0
     part_first = np.arange(world + 1, dtype=np.int32) * per
     g = pkg.SemiImplicitIterative(params, mesh, device=local, nparts=world, part_first=part_first, my_part=rank)
     if world > 1:

@@ -14,6 +14,7 @@
 
 #include "pamg_internal.h"
 #include "pamg_kernels.cuh"
+#include "pamg_stream.cuh"
 #include "pamg_unstr.cuh"
 
 using namespace pamg;
@@ -62,6 +63,7 @@ struct LevelDev {
   double *told = nullptr, *rhs = nullptr, *res = nullptr;
   double *ovl = nullptr, *ovl_old = nullptr;  // (nstrips + nsend) * 3S doubles
   double* pc = nullptr;               // [U][NPC]
+  int2* items = nullptr; int nitems = 0;  // work list of the row-streaming kernel (levels with s >= STREAM_MIN_S)
   bool rhs_valid = false;             // level 1: RHS matches TOLD
 };
 
@@ -77,11 +79,13 @@ struct pamg_handle {
   double* xg = nullptr;
   int32_t *strip_of = nullptr, *dst_strip = nullptr, *rev = nullptr, *hmap = nullptr;
   std::vector<LevelDev> lev;
-  double* partial = nullptr; int npartial = 0;
+  double* partial = nullptr; int npartial = 0; int last_partials = 0;
   double* out3 = nullptr;         // device
   double* out3_host = nullptr;    // pinned
   double* scratch = nullptr; size_t scratch_bytes = 0;  // L2 flush
   double* stage = nullptr; size_t stage_bytes = 0;      // pinned staging for host-buffer entry points
+  int kernel_mode = 1;  // 1 pipelined 1-D TMA tiles (default), 2 row-streaming, 0 direct loads; PAMG_KERNEL=direct|tma1d|stream
+  int* counters = nullptr;
   // per-kernel timing (element kernels only)
   bool profiling = false;
   std::vector<cudaEvent_t> pev;  // pairs
@@ -243,8 +247,33 @@ int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout,
   a.colour = colour;
   const bool prof = h->profiling && h->pev_used + 2 <= (int)h->pev.size();
   if (prof) CK(cudaEventRecord(h->pev[h->pev_used], h->stream));
-  if (h->p.face_terms) k_element<MODE, true><<<grid, TPB, 0, h->stream>>>(a);
-  else k_element<MODE, false><<<grid, TPB, 0, h->stream>>>(a);
+  if (MODE != MODE_GS && h->kernel_mode == 2 && L.nitems > 0) {
+    // row-streaming kernel: TMA-prefetched ring of row segments, all neighbours from shared memory
+    StreamArgs sa;
+    sa.e = a; sa.items = L.items; sa.nitems = L.nitems; sa.counters = h->counters;
+    const int sgrid = std::min(L.nitems, std::min(grid, h->nsm * 5));
+    if (h->p.face_terms) k_stream<MODE, true><<<sgrid, SW, 0, h->stream>>>(sa);
+    else k_stream<MODE, false><<<sgrid, SW, 0, h->stream>>>(sa);
+    if (MODE == MODE_RESID) h->last_partials = sgrid;
+  } else if (MODE != MODE_GS && h->kernel_mode >= 1 && L.C >= TPB) {
+    // 1-D TMA tiles: contiguous 6 KB spans through shared memory (pamg_kernels.cuh)
+    // contiguous tile ranges per CTA: exactly one wave of resident CTAs (occupancy from the runtime)
+    auto kern = h->p.face_terms ? k_element_tma<MODE, true> : k_element_tma<MODE, false>;
+    static int resident_by_face[2] = {0, 0};   // per instantiation
+    int& resident = resident_by_face[h->p.face_terms ? 1 : 0];
+    if (resident == 0) {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_BYTES));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, TPB, TMA_SMEM_BYTES));
+      if (resident < 1) resident = 1;
+    }
+    const int tgrid = (int)std::max(1ll, std::min((L.nelem + TPB - 1) / TPB, (long long)h->nsm * resident));
+    kern<<<tgrid, TPB, TMA_SMEM_BYTES, h->stream>>>(a);
+    if (MODE == MODE_RESID) h->last_partials = tgrid;
+  } else {
+    if (MODE == MODE_RESID) h->last_partials = grid;
+    if (h->p.face_terms) k_element<MODE, true><<<grid, TPB, 0, h->stream>>>(a);
+    else k_element<MODE, false><<<grid, TPB, 0, h->stream>>>(a);
+  }
   if (prof) { CK(cudaEventRecord(h->pev[h->pev_used + 1], h->stream)); h->pev_used += 2; }
   h->launches++;
   CK(cudaGetLastError());
@@ -289,7 +318,7 @@ int do_residual(pamg_handle* h, int level, double* l2, double* linf, double* sma
   int rc = launch_element<MODE_RESID>(h, L, tnew_ptr(L), L.res, 0, grid);
   if (rc) return rc;
   if (l2 || linf || smax) {
-    k_reduce_partials<<<1, 1024, 0, h->stream>>>(h->partial, grid, h->out3);
+    k_reduce_partials<<<1, 1024, 0, h->stream>>>(h->partial, h->last_partials, h->out3);
     h->launches++;
     CK(cudaGetLastError());
     if (h->comm && h->nranks > 1) {
@@ -373,11 +402,11 @@ int vcycle_rec(pamg_handle* h, int level, int solver, int nu1, int nu2, int ncoa
 void free_levels(pamg_handle* h) {
   for (auto& L : h->lev) {
     cudaFree(L.T[0]); cudaFree(L.T[1]); cudaFree(L.told); cudaFree(L.rhs); cudaFree(L.res);
-    cudaFree(L.ovl); cudaFree(L.ovl_old); cudaFree(L.pc);
+    cudaFree(L.ovl); cudaFree(L.ovl_old); cudaFree(L.pc); cudaFree(L.items);
   }
   h->lev.clear();
   cudaFree(h->xg); cudaFree(h->strip_of); cudaFree(h->dst_strip); cudaFree(h->rev); cudaFree(h->hmap);
-  cudaFree(h->partial);
+  cudaFree(h->partial); cudaFree(h->counters); h->counters = nullptr;
   h->xg = nullptr; h->strip_of = h->dst_strip = h->rev = h->hmap = nullptr; h->partial = nullptr;
 }
 
@@ -431,6 +460,12 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
   if (device < 0 || device >= ndev) return PAMG_ERR_ARG;
   pamg_handle* h = new pamg_handle();
   h->p = *p; h->device = device;
+  {
+    const char* e = getenv("PAMG_KERNEL");
+    if (e && !strcmp(e, "direct")) h->kernel_mode = 0;
+    else if (e && !strcmp(e, "tma1d")) h->kernel_mode = 1;
+    else if (e && !strcmp(e, "stream")) h->kernel_mode = 2;
+  }
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return PAMG_ERR_CUDA; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->nsm = prop.multiProcessorCount;
@@ -503,7 +538,32 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
     CK(cudaMalloc(&L.pc, pc.size() * sizeof(double)));
     CK(cudaMemcpy(L.pc, pc.data(), pc.size() * sizeof(double), cudaMemcpyHostToDevice));
     L.cur = 0; L.tnew_alias = true; L.rhs_valid = (il != 0);
+    // work list of the row-streaming kernel: (parent, row chunk, column strip) cut out of the triangle of
+    // children in (r, x = ipos + r - 1) coordinates; largest items first (dynamic scheduling)
+    if (L.s >= STREAM_MIN_S) {
+      const int b = 2 << L.s;
+      struct It { int u, r0, x0, n; };
+      std::vector<It> its;
+      for (int u = 0; u < U; ++u)
+        for (int r0 = 1; r0 <= L.S; r0 += SR)
+          for (int x0 = 1; x0 <= b - 1; x0 += SW) {
+            const int x1 = x0 + SW - 1;
+            const int rend = std::min(std::min(r0 + SR - 1, L.S), std::min(x1, b - x0));
+            if (rend < r0) continue;
+            int n = 0;
+            for (int r = r0; r <= rend; ++r) n += std::min(x1, b - r) - std::max(x0, r) + 1;
+            its.push_back(It{u, r0, x0, n});
+          }
+      std::stable_sort(its.begin(), its.end(), [](const It& p, const It& q) { return p.n > q.n; });
+      std::vector<int2> packed(its.size());
+      for (size_t i = 0; i < its.size(); ++i) packed[i] = make_int2(its[i].u, (its[i].r0 << 16) | its[i].x0);
+      L.nitems = (int)packed.size();
+      CK(cudaMalloc(&L.items, packed.size() * sizeof(int2)));
+      CK(cudaMemcpy(L.items, packed.data(), packed.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    }
   }
+  CK(cudaMalloc(&h->counters, 2 * sizeof(int)));
+  CK(cudaMemset(h->counters, 0, 2 * sizeof(int)));
   h->npartial = h->nsm * 8;
   CK(cudaMalloc(&h->partial, (size_t)h->npartial * 3 * sizeof(double)));
   CK(cudaStreamSynchronize(h->stream));

@@ -52,6 +52,113 @@ __device__ __forceinline__ void child_from_flat(int t, int s, int& r, int& ipos,
   ele = 1 + (r - 1) * (b + 1 - r) + ipos - 1;
 }
 
+// neighbour values at the nodes coincident with my face nodes (a,b) of child faces
+//   f1:(1,3)  f2:(3,2)  f3:(2,1)      (transport_tri_semi.F90:142-147), and the penalty coefficient of each face
+struct FaceIn { double n1a, n1b, n2a, n2b, n3a, n3b, pen1, pen2, pen3; };
+
+// One child: A x (get_A_x, transport_tri_semi.F90:412-448, theta = 1), the diagonal (get_diagonal :481-486)
+// and the update of the chosen solver.  Shared by the direct and the TMA-tiled kernels.
+template <int MODE, bool FACE>
+__device__ __forceinline__ void elem_apply(const double* __restrict__ pc, bool up, double T1, double T2, double T3,
+                                           const FaceIn& fi, double b1, double b2, double b3, double omega,
+                                           double rsign, double& o1, double& o2, double& o3) {
+  const double sg = up ? 1.0 : -1.0;
+  // ---- volume terms: (1/dt) M T - S T + K T
+  const double cm = __ldg(pc + PC_CM);
+  const double sumT = T1 + T2 + T3;
+  const double k11 = __ldg(pc + PC_K11), k12 = __ldg(pc + PC_K12), k13 = __ldg(pc + PC_K13);
+  const double k22 = __ldg(pc + PC_K22), k23 = __ldg(pc + PC_K23), k33 = __ldg(pc + PC_K33);
+  const double adv = sg * sumT;
+  const double mass1 = cm * (T1 + sumT), mass2 = cm * (T2 + sumT), mass3 = cm * (T3 + sumT);
+  const double st1 = __ldg(pc + PC_ADV + 0) * adv, st2 = __ldg(pc + PC_ADV + 1) * adv, st3 = __ldg(pc + PC_ADV + 2) * adv;
+  double ax1 = mass1 - st1 + (k11 * T1 + k12 * T2 + k13 * T3);
+  double ax2 = mass2 - st2 + (k12 * T1 + k22 * T2 + k23 * T3);
+  double ax3 = mass3 - st3 + (k13 * T1 + k23 * T2 + k33 * T3);
+  // ml/dt + K_ii (+ penalty diagonal below); ml = A/3 = 4 * A/12
+  double d1 = 4.0 * cm + k11, d2 = 4.0 * cm + k22, d3 = 4.0 * cm + k33;
+  double fx1 = 0.0, fx2 = 0.0, fx3 = 0.0;  // upwind flux, kept apart for Richardson (:516)
+  if (FACE) {
+    // penalty diffusion (k/dx) int sn_i (T - T2)  (matrices.F90:113-115, get_diff_surf_stencl :468-477):
+    // face mass (L/6)[[2,1],[1,2]] folded into pen = k (L/2) / (3 dx)
+    {
+      const double da = T1 - fi.n1a, db = T3 - fi.n1b;   // face 1: a = node 1, b = node 3
+      ax1 += fi.pen1 * (2.0 * da + db); ax3 += fi.pen1 * (da + 2.0 * db);
+      d1 += 2.0 * fi.pen1; d3 += 2.0 * fi.pen1;
+    }
+    {
+      const double da = T3 - fi.n2a, db = T2 - fi.n2b;   // face 2: a = node 3, b = node 2
+      ax3 += fi.pen2 * (2.0 * da + db); ax2 += fi.pen2 * (da + 2.0 * db);
+      d3 += 2.0 * fi.pen2; d2 += 2.0 * fi.pen2;
+    }
+    {
+      const double da = T2 - fi.n3a, db = T1 - fi.n3b;   // face 3: a = node 2, b = node 1
+      ax2 += fi.pen3 * (2.0 * da + db); ax1 += fi.pen3 * (da + 2.0 * db);
+      d2 += 2.0 * fi.pen3; d1 += 2.0 * fi.pen3;
+    }
+    // upwind flux: income = 1 when n.u < 0 (transport_tri_unstr.F90:729-738)
+    {
+      const double fl = sg * __ldg(pc + PC_FL + 0);
+      const bool in = fl < 0.0;
+      const double wa = in ? fi.n1a : T1, wb = in ? fi.n1b : T3;
+      fx1 += fl * (2.0 * wa + wb); fx3 += fl * (wa + 2.0 * wb);
+    }
+    {
+      const double fl = sg * __ldg(pc + PC_FL + 1);
+      const bool in = fl < 0.0;
+      const double wa = in ? fi.n2a : T3, wb = in ? fi.n2b : T2;
+      fx3 += fl * (2.0 * wa + wb); fx2 += fl * (wa + 2.0 * wb);
+    }
+    {
+      const double fl = sg * __ldg(pc + PC_FL + 2);
+      const bool in = fl < 0.0;
+      const double wa = in ? fi.n3a : T2, wb = in ? fi.n3b : T1;
+      fx2 += fl * (2.0 * wa + wb); fx1 += fl * (wa + 2.0 * wb);
+    }
+    ax1 += fx1; ax2 += fx2; ax3 += fx3;
+  }
+  if (MODE == MODE_RESID) {
+    o1 = rsign * (ax1 - b1); o2 = rsign * (ax2 - b2); o3 = rsign * (ax3 - b3);  // :869
+  } else if (MODE == MODE_RICH) {
+    // solve_Richardson (:511-518): omega * (b - (mass - stiff + flux))
+    o1 = T1 + omega * (b1 - (mass1 - st1 + fx1));
+    o2 = T2 + omega * (b2 - (mass2 - st2 + fx2));
+    o3 = T3 + omega * (b3 - (mass3 - st3 + fx3));
+  } else {
+    // solve_Jacobi (:491-497) / solve_Gauss_Seidel (:501-507)
+    o1 = T1 + omega / d1 * (b1 - ax1);
+    o2 = T2 + omega / d2 * (b2 - ax2);
+    o3 = T3 + omega / d3 * (b3 - ax3);
+  }
+}
+
+// halo strip entry of an up child on a parent face: mf = gmsh side (0..2), slot0 = 0-based strip position
+__device__ __forceinline__ void halo_pair(const ElemArgs& a, int u, int mf, int slot0, int S, double& va, double& vb) {
+  const int hm = __ldg(a.hmap + u * 3 + mf);
+  const double* e = a.ovl + ((size_t)__ldg(a.strip_of + u * 3 + mf) * S + slot0) * 3;
+  va = __ldg(e + (hm & 3)); vb = __ldg(e + (hm >> 2));
+}
+
+// deterministic two-stage norm reduction: warp shuffle, then one partial per CTA
+__device__ __forceinline__ void block_partial(double acc_sum, double acc_abs, double acc_max, double* partial) {
+  for (int o = 16; o > 0; o >>= 1) {
+    acc_sum += __shfl_xor_sync(0xffffffffu, acc_sum, o);
+    acc_abs = fmax(acc_abs, __shfl_xor_sync(0xffffffffu, acc_abs, o));
+    acc_max = fmax(acc_max, __shfl_xor_sync(0xffffffffu, acc_max, o));
+  }
+  __shared__ double sh[3][TPB / 32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh[0][w] = acc_sum; sh[1][w] = acc_abs; sh[2][w] = acc_max; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int i = 0; i < TPB / 32; ++i) { s0 += sh[0][i]; s1 = fmax(s1, sh[1][i]); s2 = fmax(s2, sh[2][i]); }
+    partial[(size_t)blockIdx.x * 3 + 0] = s0;
+    partial[(size_t)blockIdx.x * 3 + 1] = s1;
+    partial[(size_t)blockIdx.x * 3 + 2] = s2;
+  }
+}
+
+// ---- direct kernel: thread per child, 8-byte loads through L1 (used for the in-place coloured GS pass)
 template <int MODE, bool FACE>
 __global__ void __launch_bounds__(TPB) k_element(ElemArgs a) {
   const int s = a.s;
@@ -75,145 +182,332 @@ __global__ void __launch_bounds__(TPB) k_element(ElemArgs a) {
     auto ldT = [&](long long i) -> double { return MODE == MODE_GS ? a.Tin[i] : __ldg(a.Tin + i); };
     const double T1 = ldT(base), T2 = ldT(base + 1), T3 = ldT(base + 2);
     const double* __restrict__ pc = a.pc + (size_t)u * NPC;
-    const double sg = up ? 1.0 : -1.0;
-
-    // ---- volume terms: (1/dt) M T - S T + K T   (get_A_x, transport_tri_semi.F90:412-448, theta = 1)
-    const double cm = __ldg(pc + PC_CM);
-    const double sumT = T1 + T2 + T3;
-    const double k11 = __ldg(pc + PC_K11), k12 = __ldg(pc + PC_K12), k13 = __ldg(pc + PC_K13);
-    const double k22 = __ldg(pc + PC_K22), k23 = __ldg(pc + PC_K23), k33 = __ldg(pc + PC_K33);
-    const double adv = sg * sumT;
-    double mass1 = cm * (T1 + sumT), mass2 = cm * (T2 + sumT), mass3 = cm * (T3 + sumT);
-    double st1 = __ldg(pc + PC_ADV + 0) * adv, st2 = __ldg(pc + PC_ADV + 1) * adv, st3 = __ldg(pc + PC_ADV + 2) * adv;
-    double ax1 = mass1 - st1 + (k11 * T1 + k12 * T2 + k13 * T3);
-    double ax2 = mass2 - st2 + (k12 * T1 + k22 * T2 + k23 * T3);
-    double ax3 = mass3 - st3 + (k13 * T1 + k23 * T2 + k33 * T3);
-    // get_diagonal (:481-486): ml/dt + K_ii (+ penalty diagonal below); ml = A/3 = 4 * A/12
-    double d1 = 4.0 * cm + k11, d2 = 4.0 * cm + k22, d3 = 4.0 * cm + k33;
-    double fx1 = 0.0, fx2 = 0.0, fx3 = 0.0;  // upwind flux, kept apart for Richardson (:516)
-
+    FaceIn fi;
     if (FACE) {
-      // neighbour values at the nodes coincident with my face nodes (a,b) of child faces
-      //   f1:(1,3)  f2:(3,2)  f3:(2,1)      (transport_tri_semi.F90:142-147)
-      double n1a, n1b, n2a, n2b, n3a, n3b;
-      double pen1, pen2, pen3;
       if (!up) {
         // down child: f1 -> child above, f2 -> ele+1, f3 -> ele-1 (splitting.F90:766); never on a parent face
         const long long o1 = (pbase + (ele + b - 2 * r) - 1) * 3;
         const long long o2 = base + 3, o3 = base - 3;
-        n1a = ldT(o1 + 2); n1b = ldT(o1 + 0);   // my node 1 <-> its node 3, my node 3 <-> its node 1
-        n2a = ldT(o2 + 1); n2b = ldT(o2 + 2);   // my 3 <-> its 2, my 2 <-> its 3
-        n3a = ldT(o3 + 0); n3b = ldT(o3 + 1);   // my 2 <-> its 1, my 1 <-> its 2
-        pen1 = __ldg(pc + PC_PENI + 0); pen2 = __ldg(pc + PC_PENI + 1); pen3 = __ldg(pc + PC_PENI + 2);
+        fi.n1a = ldT(o1 + 2); fi.n1b = ldT(o1 + 0);   // my node 1 <-> its node 3, my node 3 <-> its node 1
+        fi.n2a = ldT(o2 + 1); fi.n2b = ldT(o2 + 2);   // my 3 <-> its 2, my 2 <-> its 3
+        fi.n3a = ldT(o3 + 0); fi.n3b = ldT(o3 + 1);   // my 2 <-> its 1, my 1 <-> its 2
+        fi.pen1 = __ldg(pc + PC_PENI + 0); fi.pen2 = __ldg(pc + PC_PENI + 1); fi.pen3 = __ldg(pc + PC_PENI + 2);
       } else {
-        const size_t S3 = (size_t)3 * S;
         if (r > 1) {
           const long long o1 = (pbase + (ele - b - 2 + 2 * r) - 1) * 3;
-          n1a = ldT(o1 + 2); n1b = ldT(o1 + 0);
-          pen1 = __ldg(pc + PC_PENI + 0);
+          fi.n1a = ldT(o1 + 2); fi.n1b = ldT(o1 + 0);
+          fi.pen1 = __ldg(pc + PC_PENI + 0);
         } else {  // parent face 1, slot ipos/2+1 (:629-631)
-          const int hm = __ldg(a.hmap + u * 3 + 0);
-          const double* e = a.ovl + (size_t)__ldg(a.strip_of + u * 3 + 0) * S3 + (size_t)(ipos >> 1) * 3;
-          n1a = __ldg(e + (hm & 3)); n1b = __ldg(e + (hm >> 2));
-          pen1 = __ldg(pc + PC_PENX + 0);
+          halo_pair(a, u, 0, ipos >> 1, S, fi.n1a, fi.n1b);
+          fi.pen1 = __ldg(pc + PC_PENX + 0);
         }
         if (ipos > 1) {
-          n2a = ldT(base - 3 + 1); n2b = ldT(base - 3 + 2);
-          pen2 = __ldg(pc + PC_PENI + 1);
+          fi.n2a = ldT(base - 3 + 1); fi.n2b = ldT(base - 3 + 2);
+          fi.pen2 = __ldg(pc + PC_PENI + 1);
         } else {  // parent face 3, slot irow (:632-634)
-          const int hm = __ldg(a.hmap + u * 3 + 2);
-          const double* e = a.ovl + (size_t)__ldg(a.strip_of + u * 3 + 2) * S3 + (size_t)(r - 1) * 3;
-          n2a = __ldg(e + (hm & 3)); n2b = __ldg(e + (hm >> 2));
-          pen2 = __ldg(pc + PC_PENX + 1);
+          halo_pair(a, u, 2, r - 1, S, fi.n2a, fi.n2b);
+          fi.pen2 = __ldg(pc + PC_PENX + 1);
         }
         if (ipos < len) {
-          n3a = ldT(base + 3 + 0); n3b = ldT(base + 3 + 1);
-          pen3 = __ldg(pc + PC_PENI + 2);
+          fi.n3a = ldT(base + 3 + 0); fi.n3b = ldT(base + 3 + 1);
+          fi.pen3 = __ldg(pc + PC_PENI + 2);
         } else {  // parent face 2, slot irow (:635-637)
-          const int hm = __ldg(a.hmap + u * 3 + 1);
-          const double* e = a.ovl + (size_t)__ldg(a.strip_of + u * 3 + 1) * S3 + (size_t)(r - 1) * 3;
-          n3a = __ldg(e + (hm & 3)); n3b = __ldg(e + (hm >> 2));
-          pen3 = __ldg(pc + PC_PENX + 2);
+          halo_pair(a, u, 1, r - 1, S, fi.n3a, fi.n3b);
+          fi.pen3 = __ldg(pc + PC_PENX + 2);
         }
       }
-      // penalty diffusion (k/dx) int sn_i (T - T2)  (matrices.F90:113-115, get_diff_surf_stencl :468-477):
-      // face mass (L/6)[[2,1],[1,2]] folded into pen = k (L/2) / (3 dx)
-      {
-        const double da = T1 - n1a, db = T3 - n1b;   // face 1: a = node 1, b = node 3
-        ax1 += pen1 * (2.0 * da + db); ax3 += pen1 * (da + 2.0 * db);
-        d1 += 2.0 * pen1; d3 += 2.0 * pen1;
-      }
-      {
-        const double da = T3 - n2a, db = T2 - n2b;   // face 2: a = node 3, b = node 2
-        ax3 += pen2 * (2.0 * da + db); ax2 += pen2 * (da + 2.0 * db);
-        d3 += 2.0 * pen2; d2 += 2.0 * pen2;
-      }
-      {
-        const double da = T2 - n3a, db = T1 - n3b;   // face 3: a = node 2, b = node 1
-        ax2 += pen3 * (2.0 * da + db); ax1 += pen3 * (da + 2.0 * db);
-        d2 += 2.0 * pen3; d1 += 2.0 * pen3;
-      }
-      // upwind flux: income = 1 when n.u < 0 (transport_tri_unstr.F90:729-738)
-      {
-        const double fl = sg * __ldg(pc + PC_FL + 0);
-        const bool in = fl < 0.0;
-        const double wa = in ? n1a : T1, wb = in ? n1b : T3;
-        fx1 += fl * (2.0 * wa + wb); fx3 += fl * (wa + 2.0 * wb);
-      }
-      {
-        const double fl = sg * __ldg(pc + PC_FL + 1);
-        const bool in = fl < 0.0;
-        const double wa = in ? n2a : T3, wb = in ? n2b : T2;
-        fx3 += fl * (2.0 * wa + wb); fx2 += fl * (wa + 2.0 * wb);
-      }
-      {
-        const double fl = sg * __ldg(pc + PC_FL + 2);
-        const bool in = fl < 0.0;
-        const double wa = in ? n3a : T2, wb = in ? n3b : T1;
-        fx2 += fl * (2.0 * wa + wb); fx1 += fl * (wa + 2.0 * wb);
-      }
-      ax1 += fx1; ax2 += fx2; ax3 += fx3;
     }
-
     const double b1 = __ldg(a.rhs + base), b2 = __ldg(a.rhs + base + 1), b3 = __ldg(a.rhs + base + 2);
+    double o1, o2, o3;
+    elem_apply<MODE, FACE>(pc, up, T1, T2, T3, fi, b1, b2, b3, a.omega, a.rsign, o1, o2, o3);
+    a.Tout[base] = o1; a.Tout[base + 1] = o2; a.Tout[base + 2] = o3;
     if (MODE == MODE_RESID) {
-      const double r1 = a.rsign * (ax1 - b1), r2 = a.rsign * (ax2 - b2), r3 = a.rsign * (ax3 - b3);  // :869
-      a.Tout[base] = r1; a.Tout[base + 1] = r2; a.Tout[base + 2] = r3;
-      acc_sum += r1 * r1 + r2 * r2 + r3 * r3;
-      acc_abs = fmax(acc_abs, fmax(fabs(r1), fmax(fabs(r2), fabs(r3))));
-      acc_max = fmax(acc_max, fmax(r1, fmax(r2, r3)));
-    } else if (MODE == MODE_RICH) {
-      // solve_Richardson (:511-518): omega * (b - (mass - stiff + flux))
-      a.Tout[base] = T1 + a.omega * (b1 - (mass1 - st1 + fx1));
-      a.Tout[base + 1] = T2 + a.omega * (b2 - (mass2 - st2 + fx2));
-      a.Tout[base + 2] = T3 + a.omega * (b3 - (mass3 - st3 + fx3));
-    } else {
-      // solve_Jacobi (:491-497) / solve_Gauss_Seidel (:501-507)
-      a.Tout[base] = T1 + a.omega / d1 * (b1 - ax1);
-      a.Tout[base + 1] = T2 + a.omega / d2 * (b2 - ax2);
-      a.Tout[base + 2] = T3 + a.omega / d3 * (b3 - ax3);
+      acc_sum += o1 * o1 + o2 * o2 + o3 * o3;
+      acc_abs = fmax(acc_abs, fmax(fabs(o1), fmax(fabs(o2), fabs(o3))));
+      acc_max = fmax(acc_max, fmax(o1, fmax(o2, o3)));
     }
   }
+  if (MODE == MODE_RESID) block_partial(acc_sum, acc_abs, acc_max, a.partial);
+}
 
-  if (MODE == MODE_RESID) {
-    // warp-shuffle reduction, then one partial per CTA (deterministic two-stage reduction)
-    for (int o = 16; o > 0; o >>= 1) {
-      acc_sum += __shfl_xor_sync(0xffffffffu, acc_sum, o);
-      acc_abs = fmax(acc_abs, __shfl_xor_sync(0xffffffffu, acc_abs, o));
-      acc_max = fmax(acc_max, __shfl_xor_sync(0xffffffffu, acc_max, o));
+// ------------------------------------------------------------------------------------------------
+// TMA-tiled kernel (Jacobi / Richardson / residual): the CTA owns TPB children that are CONTIGUOUS IN
+// MEMORY, i.e. one 6144-byte span of T, of b and of the output.  One elected thread moves the spans with
+// 1-D bulk copies (cp.async.bulk -> UBLKCP) that complete on an mbarrier; every thread then works out of
+// shared memory (stride-3 doubles is bank-conflict free) and the result leaves through a bulk store.
+// This removes the 24-byte-stride LDG/STG traffic that saturated the L1 wavefront pipe in the direct kernel
+// (profiles/r1a_jacobi_simple_ncu_full.txt).  Left/right neighbours come from the tile (+1 child of halo on
+// each side); only the vertical neighbour (other row) is a global load.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE_%=;\n"
+      "bra LAB_WAIT_%=;\n"
+      "LAB_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// memory-order child index k (0-based) -> row, position.  Row r starts at m(b-m), m = r-1; the float sqrt
+// guess is off by at most one, fixed with two predicated corrections (no loops, no divergence).
+__device__ __forceinline__ void child_from_ele0(int k, int s, int& r, int& ipos, int& len) {
+  const int b = 2 << s, S = 1 << s;
+  int m = (int)(((float)b - sqrtf((float)(b * b - 4 * k))) * 0.5f);
+  m = max(0, min(m, S - 1));
+  m -= (m * (b - m) > k);
+  m += (m + 1 < S) && ((m + 1) * (b - m - 1) <= k);
+  m -= (m * (b - m) > k);
+  r = m + 1;
+  ipos = k - m * (b - m) + 1;
+  len = b + 1 - 2 * r;
+}
+
+constexpr int TMA_T_DOUBLES = 3 * TPB + 8;   // tile + one child of halo on each side, padded to 16-byte spans
+constexpr int NSTAGE = 3;                    // tiles in flight per CTA
+constexpr size_t TMA_SMEM_BYTES = sizeof(double) * (NSTAGE * (TMA_T_DOUBLES + 3 * TPB) + 2 * 3 * TPB) + 16 * NSTAGE + 64;
+
+// per-parent coefficients held in registers while a CTA walks through the tiles of one parent
+struct ParentRegs {
+  double cm, k11, k12, k13, k22, k23, k33, adv1, adv2, adv3, fl1, fl2, fl3, pi1, pi2, pi3;
+  double w1, w2, w3;   // omega / D for children whose three faces are all inside the parent
+  double px1, px2, px3;   // penalty coefficients of faces on the parent boundary
+};
+__device__ __forceinline__ void load_parent(const double* __restrict__ pc, double omega, bool face, ParentRegs& P) {
+  P.cm = __ldg(pc + PC_CM);
+  P.k11 = __ldg(pc + PC_K11); P.k12 = __ldg(pc + PC_K12); P.k13 = __ldg(pc + PC_K13);
+  P.k22 = __ldg(pc + PC_K22); P.k23 = __ldg(pc + PC_K23); P.k33 = __ldg(pc + PC_K33);
+  P.adv1 = __ldg(pc + PC_ADV); P.adv2 = __ldg(pc + PC_ADV + 1); P.adv3 = __ldg(pc + PC_ADV + 2);
+  P.fl1 = __ldg(pc + PC_FL); P.fl2 = __ldg(pc + PC_FL + 1); P.fl3 = __ldg(pc + PC_FL + 2);
+  P.pi1 = __ldg(pc + PC_PENI); P.pi2 = __ldg(pc + PC_PENI + 1); P.pi3 = __ldg(pc + PC_PENI + 2);
+  // get_diagonal (:481-486): node 1 sits on faces 1,3; node 2 on faces 2,3; node 3 on faces 1,2
+  const double f = face ? 2.0 : 0.0;   // the penalty diagonal exists only with the face block on
+  P.w1 = omega / (4.0 * P.cm + P.k11 + f * (P.pi1 + P.pi3));
+  P.w2 = omega / (4.0 * P.cm + P.k22 + f * (P.pi2 + P.pi3));
+  P.w3 = omega / (4.0 * P.cm + P.k33 + f * (P.pi1 + P.pi2));
+  P.px1 = __ldg(pc + PC_PENX); P.px2 = __ldg(pc + PC_PENX + 1); P.px3 = __ldg(pc + PC_PENX + 2);
+}
+
+// Same arithmetic as elem_apply, coefficients from registers; `interior` children (no face on the parent
+// boundary) use the precomputed omega / D.
+template <int MODE, bool FACE>
+__device__ __forceinline__ void elem_apply_regs(const ParentRegs& P, bool up, bool interior, double T1, double T2,
+                                                double T3, const FaceIn& fi, double b1, double b2, double b3,
+                                                double omega, double rsign, double& o1, double& o2, double& o3) {
+  const double sg = up ? 1.0 : -1.0;
+  const double sumT = T1 + T2 + T3;
+  const double adv = sg * sumT;
+  const double mass1 = P.cm * (T1 + sumT), mass2 = P.cm * (T2 + sumT), mass3 = P.cm * (T3 + sumT);
+  const double st1 = P.adv1 * adv, st2 = P.adv2 * adv, st3 = P.adv3 * adv;
+  double ax1 = mass1 - st1 + (P.k11 * T1 + P.k12 * T2 + P.k13 * T3);
+  double ax2 = mass2 - st2 + (P.k12 * T1 + P.k22 * T2 + P.k23 * T3);
+  double ax3 = mass3 - st3 + (P.k13 * T1 + P.k23 * T2 + P.k33 * T3);
+  double fx1 = 0.0, fx2 = 0.0, fx3 = 0.0;
+  if (FACE) {
+    {
+      const double da = T1 - fi.n1a, db = T3 - fi.n1b;
+      ax1 += fi.pen1 * (2.0 * da + db); ax3 += fi.pen1 * (da + 2.0 * db);
     }
-    __shared__ double sh[3][TPB / 32];
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (l == 0) { sh[0][w] = acc_sum; sh[1][w] = acc_abs; sh[2][w] = acc_max; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double s0 = 0, s1 = 0, s2 = 0;
-      for (int i = 0; i < TPB / 32; ++i) { s0 += sh[0][i]; s1 = fmax(s1, sh[1][i]); s2 = fmax(s2, sh[2][i]); }
-      a.partial[(size_t)blockIdx.x * 3 + 0] = s0;
-      a.partial[(size_t)blockIdx.x * 3 + 1] = s1;
-      a.partial[(size_t)blockIdx.x * 3 + 2] = s2;
+    {
+      const double da = T3 - fi.n2a, db = T2 - fi.n2b;
+      ax3 += fi.pen2 * (2.0 * da + db); ax2 += fi.pen2 * (da + 2.0 * db);
     }
+    {
+      const double da = T2 - fi.n3a, db = T1 - fi.n3b;
+      ax2 += fi.pen3 * (2.0 * da + db); ax1 += fi.pen3 * (da + 2.0 * db);
+    }
+    {
+      const double fl = sg * P.fl1;
+      const bool in = fl < 0.0;
+      const double wa = in ? fi.n1a : T1, wb = in ? fi.n1b : T3;
+      fx1 += fl * (2.0 * wa + wb); fx3 += fl * (wa + 2.0 * wb);
+    }
+    {
+      const double fl = sg * P.fl2;
+      const bool in = fl < 0.0;
+      const double wa = in ? fi.n2a : T3, wb = in ? fi.n2b : T2;
+      fx3 += fl * (2.0 * wa + wb); fx2 += fl * (wa + 2.0 * wb);
+    }
+    {
+      const double fl = sg * P.fl3;
+      const bool in = fl < 0.0;
+      const double wa = in ? fi.n3a : T2, wb = in ? fi.n3b : T1;
+      fx2 += fl * (2.0 * wa + wb); fx1 += fl * (wa + 2.0 * wb);
+    }
+    ax1 += fx1; ax2 += fx2; ax3 += fx3;
   }
+  if (MODE == MODE_RESID) {
+    o1 = rsign * (ax1 - b1); o2 = rsign * (ax2 - b2); o3 = rsign * (ax3 - b3);
+  } else if (MODE == MODE_RICH) {
+    o1 = T1 + omega * (b1 - (mass1 - st1 + fx1));
+    o2 = T2 + omega * (b2 - (mass2 - st2 + fx2));
+    o3 = T3 + omega * (b3 - (mass3 - st3 + fx3));
+  } else {
+    double w1 = P.w1, w2 = P.w2, w3 = P.w3;
+    if (!interior) {
+      double d1 = 4.0 * P.cm + P.k11, d2 = 4.0 * P.cm + P.k22, d3 = 4.0 * P.cm + P.k33;
+      if (FACE) { d1 += 2.0 * (fi.pen1 + fi.pen3); d2 += 2.0 * (fi.pen2 + fi.pen3); d3 += 2.0 * (fi.pen1 + fi.pen2); }
+      w1 = omega / d1; w2 = omega / d2; w3 = omega / d3;
+    }
+    o1 = T1 + w1 * (b1 - ax1);
+    o2 = T2 + w2 * (b2 - ax2);
+    o3 = T3 + w3 * (b3 - ax3);
+  }
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Pipelined 1-D TMA tile kernel.  Every CTA owns a CONTIGUOUS range of tiles (so it stays inside one parent
+// for hundreds of tiles and the vertical neighbours it needs were touched by itself a moment ago); NSTAGE
+// tiles are in flight through a ring of shared-memory stages, each filled by two bulk copies that complete
+// on the stage's mbarrier.  The vertical neighbour values of the NEXT tile are fetched one iteration ahead,
+// the per-parent coefficients live in shared memory, and results leave through one 6 KB bulk store per tile.
+// (A warp-decoupled variant with full/empty mbarriers and per-warp stores measured slower: profiles/README.)
+template <int MODE, bool FACE>
+__global__ void __launch_bounds__(TPB) k_element_tma(ElemArgs a) {
+  extern __shared__ __align__(128) unsigned char dsm[];   // TMA_SMEM_BYTES, carved below
+  double (*sT)[TMA_T_DOUBLES] = reinterpret_cast<double (*)[TMA_T_DOUBLES]>(dsm);
+  double (*sB)[3 * TPB] = reinterpret_cast<double (*)[3 * TPB]>(dsm + sizeof(double) * NSTAGE * TMA_T_DOUBLES);
+  double (*sO)[3 * TPB] = reinterpret_cast<double (*)[3 * TPB]>(dsm + sizeof(double) * NSTAGE * (TMA_T_DOUBLES + 3 * TPB));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(dsm + sizeof(double) * (NSTAGE * (TMA_T_DOUBLES + 3 * TPB) + 2 * 3 * TPB));
+  __shared__ ParentRegs P;
+  const int s = a.s, twos = 2 * s, b = 2 << s, S = 1 << s;
+  const long long Cmask = (1ll << twos) - 1;
+  const long long ndof = a.nelem * 3;
+  const int tid = threadIdx.x;
+  double acc_sum = 0.0, acc_abs = 0.0, acc_max = 0.0;
+  if (tid == 0) {
+    for (int i = 0; i < NSTAGE; ++i) mbar_init(&bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long ntiles = (a.nelem + TPB - 1) / TPB;
+  const long long per = (ntiles + gridDim.x - 1) / gridDim.x;
+  const long long tbeg = (long long)blockIdx.x * per, tend = min(ntiles, tbeg + per);
+
+  auto issue = [&](long long tile) {   // tid 0 only
+    const int st = (int)((tile - tbeg) % NSTAGE);
+    const long long g0 = tile * TPB;
+    const int count = (int)min((long long)TPB, a.nelem - g0);
+    const long long dlo = (g0 == 0) ? 0 : g0 * 3 - 4;          // even offsets => 16-byte aligned spans
+    const long long dhi = min(ndof, (g0 + count) * 3 + 4);
+    const uint32_t bt = (uint32_t)((dhi - dlo) * 8), bb = (uint32_t)(count * 24);
+    mbar_expect_tx(&bar[st], bt + bb);
+    tma_load_1d(sT[st], a.Tin + dlo, bt, &bar[st]);
+    tma_load_1d(sB[st], a.rhs + g0 * 3, bb, &bar[st]);
+  };
+  if (tid == 0)
+    for (long long t = tbeg; t < min(tend, tbeg + NSTAGE - 1); ++t) issue(t);
+
+  // per-thread state of the tile being prepared (indices, vertical neighbour values)
+  struct Prep { int u, r, ipos, len; bool active, up; double va, vb; };
+  auto prepare = [&](long long tile, Prep& p) {
+    const long long g = tile * TPB + tid;
+    p.active = (tile < tend) && (g < a.nelem);
+    p.u = 0; p.r = 1; p.ipos = 1; p.len = 1; p.up = true; p.va = 0.0; p.vb = 0.0;
+    if (!p.active) return;
+    p.u = (int)(g >> twos);
+    const int k = (int)(g & Cmask);
+    child_from_ele0(k, s, p.r, p.ipos, p.len);
+    p.up = p.ipos & 1;
+    if (FACE) {
+      // vertical neighbour: child above for a down child, child below for an up child (splitting.F90:749-769);
+      // up children of row 1 sit on parent face 1 and read the halo strip instead
+      const int nb = p.up ? (k - b - 2 + 2 * p.r) : (k + b - 2 * p.r);       // 0-based child index
+      if (p.up && p.r == 1) {
+        halo_pair(a, p.u, 0, p.ipos >> 1, S, p.va, p.vb);
+      } else {
+        const unsigned o1 = ((unsigned)(g - k) + (unsigned)nb) * 3u;         // offsets in doubles fit 32 bits
+        p.va = __ldg(a.Tin + o1 + 2); p.vb = __ldg(a.Tin + o1);
+      }
+    }
+  };
+  Prep cur, nxt;
+  prepare(tbeg, cur);
+  int u_loaded = -1;
+  int obuf = 0;
+  for (long long tile = tbeg; tile < tend; ++tile) {
+    const int it = (int)(tile - tbeg);
+    const int st = it % NSTAGE;
+    if (tid == 0 && tile + NSTAGE - 1 < tend) issue(tile + NSTAGE - 1);   // its stage was drained last iteration
+    prepare(tile + 1, nxt);
+    const long long g0 = tile * TPB;
+    const int off0 = (g0 == 0) ? 0 : 4;
+    {
+      const int u_tile = (int)(g0 >> twos);          // uniform over the CTA (a tile never spans two parents)
+      if (u_tile != u_loaded) {
+        __syncthreads();
+        if (tid == 0) load_parent(a.pc + (size_t)u_tile * NPC, a.omega, FACE, P);
+        __syncthreads();
+        u_loaded = u_tile;
+      }
+    }
+    mbar_wait(&bar[st], (uint32_t)((it / NSTAGE) & 1));
+    double* so = sO[obuf];
+    if (cur.active) {
+      const double* t = sT[st] + off0 + tid * 3;
+      const double T1 = t[0], T2 = t[1], T3 = t[2];
+      FaceIn fi;
+      bool interior = true;
+      if (FACE) {
+        fi.n1a = cur.va; fi.n1b = cur.vb;
+        fi.pen1 = P.pi1; fi.pen2 = P.pi2; fi.pen3 = P.pi3;
+        // face 2 looks left for an up child and right for a down child, face 3 the other way (splitting.F90:749-769)
+        const int d = cur.up ? -3 : 3;
+        fi.n2a = t[d + 1]; fi.n2b = t[d + 2];
+        fi.n3a = t[-d]; fi.n3b = t[-d + 1];
+        if (cur.up && (cur.r == 1 || cur.ipos == 1 || cur.ipos == cur.len)) {   // child on a parent face (rare)
+          interior = false;
+          if (cur.r == 1) fi.pen1 = P.px1;
+          if (cur.ipos == 1) { halo_pair(a, cur.u, 2, cur.r - 1, S, fi.n2a, fi.n2b); fi.pen2 = P.px2; }
+          if (cur.ipos == cur.len) { halo_pair(a, cur.u, 1, cur.r - 1, S, fi.n3a, fi.n3b); fi.pen3 = P.px3; }
+        }
+      }
+      const double* bb = sB[st] + tid * 3;
+      double o1, o2, o3;
+      elem_apply_regs<MODE, FACE>(P, cur.up, interior, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.omega, a.rsign, o1, o2, o3);
+      so[tid * 3] = o1; so[tid * 3 + 1] = o2; so[tid * 3 + 2] = o3;
+      if (MODE == MODE_RESID) {
+        acc_sum += o1 * o1 + o2 * o2 + o3 * o3;
+        acc_abs = fmax(acc_abs, fmax(fabs(o1), fmax(fabs(o2), fabs(o3))));
+        acc_max = fmax(acc_max, fmax(o1, fmax(o2, o3)));
+      }
+    }
+    if (tid == 0) tma_store_wait_read();   // the previous tile's store has drained the other staging buffer
+    fence_async_smem();
+    __syncthreads();                       // sO complete; stage `st` fully consumed
+    if (tid == 0) {
+      const int count = (int)min((long long)TPB, a.nelem - g0);
+      tma_store_1d(a.Tout + g0 * 3, so, (uint32_t)(count * 24));
+      tma_store_commit();
+    }
+    obuf ^= 1;
+    cur = nxt;
+  }
+  if (tid == 0) tma_store_wait_all();
+  if (MODE == MODE_RESID) block_partial(acc_sum, acc_abs, acc_max, a.partial);
 }
 
 // second stage of the norm reduction: one CTA

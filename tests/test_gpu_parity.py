@@ -93,6 +93,11 @@ SWEEP_CASES = [
     ("900_ele", 1, False, (0.0, 0.0)),
     ("irregular", 3, True, (-0.4, 0.7)),
     ("syn", 5, True, (0.9, 0.3)),
+    # levels with s >= 6 run the TMA row-streaming kernel (pamg_stream.cuh)
+    ("test_sn2", 6, True, (0.9, 0.3)),
+    ("split0", 7, True, (-0.5, 0.8)),
+    ("split0", 6, False, (0.1, 0.1)),
+    ("syn", 8, True, (0.9, 0.3)),
 ]
 
 
@@ -168,7 +173,8 @@ def test_restrict_and_prolong(meshes, name, n, transfer):
 
 
 @pytest.mark.parametrize("name,n,solver,u", [("split0", 4, 1, (0.0, 0.0)), ("split0", 5, 3, (0.0, 0.0)),
-                                             ("test_sn2", 4, 3, (0.3, 0.1)), ("900_ele", 2, 1, (0.1, 0.1))])
+                                             ("test_sn2", 4, 3, (0.3, 0.1)), ("900_ele", 2, 1, (0.1, 0.1)),
+                                             ("split0", 7, 1, (0.3, 0.1)), ("test_sn2", 6, 3, (0.0, 0.0))])
 def test_vcycle_to_1e8_matches_oracle(meshes, name, n, solver, u):
     o, g = make_pair(meshes[name], n, n, True, u=u)
     it_o, hist_o = o.vcycle_solve(solver=4 if solver == 3 else 1, nu1=4, nu2=4, ncoarse=15, max_cycles=40, tol=1e-8)
