@@ -192,7 +192,38 @@ void parent_coefficients(const pamg_params& p, const double* Xall, const int32_t
     }
     pc[PC_PENX + f] = p.k * lhalf / (3.0 * dcX);
   }
-  pc[19] = 0.0;
+  // omega / D of children with all three faces inside the parent (get_diagonal :481-486): node 1 sits on
+  // faces 1,3; node 2 on faces 2,3; node 3 on faces 1,2.  The penalty diagonal exists only with the face block.
+  const double f2 = p.face_terms ? 2.0 : 0.0;
+  pc[PC_W + 0] = p.omega / (4.0 * pc[PC_CM] + pc[PC_K11] + f2 * (pc[PC_PENI + 0] + pc[PC_PENI + 2]));
+  pc[PC_W + 1] = p.omega / (4.0 * pc[PC_CM] + pc[PC_K22] + f2 * (pc[PC_PENI + 1] + pc[PC_PENI + 2]));
+  pc[PC_W + 2] = p.omega / (4.0 * pc[PC_CM] + pc[PC_K33] + f2 * (pc[PC_PENI + 0] + pc[PC_PENI + 1]));
+  pc[22] = 0.0; pc[23] = 0.0;
+  // folded operator of interior children, one set per orientation (struct Folded in pamg_kernels.cuh)
+  for (int o = 0; o < 2; ++o) {
+    const double sg = o == 0 ? 1.0 : -1.0;
+    double* F = pc + PC_FOLD + 16 * o;
+    double A[3][3];
+    const double K[3][3] = {{pc[PC_K11], pc[PC_K12], pc[PC_K13]}, {pc[PC_K12], pc[PC_K22], pc[PC_K23]},
+                            {pc[PC_K13], pc[PC_K23], pc[PC_K33]}};
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        A[i][j] = pc[PC_CM] * ((i == j ? 1.0 : 0.0) + 1.0) - sg * pc[PC_ADV + i] + K[i][j];
+    const int fa2[3] = {0, 2, 1}, fb2[3] = {2, 1, 0};   // face nodes (a,b): f1 (1,3), f2 (3,2), f3 (2,1)
+    double c[3];
+    for (int f = 0; f < 3; ++f) {
+      const double pen = p.face_terms ? pc[PC_PENI + f] : 0.0;
+      const double fl = p.face_terms ? sg * pc[PC_FL + f] : 0.0;
+      const bool in = fl < 0.0;
+      const double own = pen + (in ? 0.0 : fl);
+      c[f] = -pen + (in ? fl : 0.0);
+      const int ia = fa2[f], ib = fb2[f];
+      A[ia][ia] += 2.0 * own; A[ia][ib] += own; A[ib][ia] += own; A[ib][ib] += 2.0 * own;
+    }
+    F[0] = A[0][0]; F[1] = A[0][1]; F[2] = A[0][2]; F[3] = A[1][0]; F[4] = A[1][1]; F[5] = A[1][2];
+    F[6] = A[2][0]; F[7] = A[2][1]; F[8] = A[2][2]; F[9] = c[0]; F[10] = c[1]; F[11] = c[2];
+    F[12] = pc[PC_W + 0]; F[13] = pc[PC_W + 1]; F[14] = pc[PC_W + 2]; F[15] = 0.0;
+  }
 }
 
 int launch_halo(pamg_handle* h, int level);
@@ -245,6 +276,7 @@ int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout,
   a.Tin = Tin; a.Tout = Tout; a.rhs = L.rhs; a.ovl = L.ovl; a.pc = L.pc; a.strip_of = h->strip_of; a.hmap = h->hmap;
   a.partial = h->partial; a.omega = h->p.omega; a.rsign = (double)h->p.residual_sign; a.nelem = L.nelem; a.s = L.s;
   a.colour = colour;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("PAMG_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
   const bool prof = h->profiling && h->pev_used + 2 <= (int)h->pev.size();
   if (prof) CK(cudaEventRecord(h->pev[h->pev_used], h->stream));
   if (MODE != MODE_GS && h->kernel_mode == 2 && L.nitems > 0) {
@@ -255,7 +287,7 @@ int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout,
     if (h->p.face_terms) k_stream<MODE, true><<<sgrid, SW, 0, h->stream>>>(sa);
     else k_stream<MODE, false><<<sgrid, SW, 0, h->stream>>>(sa);
     if (MODE == MODE_RESID) h->last_partials = sgrid;
-  } else if (MODE != MODE_GS && h->kernel_mode >= 1 && L.C >= TPB) {
+  } else if (MODE != MODE_GS && (h->kernel_mode == 1 || h->kernel_mode == 2) && L.C >= TPB) {
     // 1-D TMA tiles: contiguous 6 KB spans through shared memory (pamg_kernels.cuh)
     // contiguous tile ranges per CTA: exactly one wave of resident CTAs (occupancy from the runtime)
     auto kern = h->p.face_terms ? k_element_tma<MODE, true> : k_element_tma<MODE, false>;
@@ -269,6 +301,11 @@ int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout,
     const int tgrid = (int)std::max(1ll, std::min((L.nelem + TPB - 1) / TPB, (long long)h->nsm * resident));
     kern<<<tgrid, TPB, TMA_SMEM_BYTES, h->stream>>>(a);
     if (MODE == MODE_RESID) h->last_partials = tgrid;
+  } else if (h->kernel_mode != 0) {
+    // branch-free direct kernel (all loads of a child in flight at once); also the coloured GS pass
+    if (MODE == MODE_RESID) h->last_partials = grid;
+    if (h->p.face_terms) k_element_direct2<MODE, true><<<grid, TPB, 0, h->stream>>>(a);
+    else k_element_direct2<MODE, false><<<grid, TPB, 0, h->stream>>>(a);
   } else {
     if (MODE == MODE_RESID) h->last_partials = grid;
     if (h->p.face_terms) k_element<MODE, true><<<grid, TPB, 0, h->stream>>>(a);
@@ -465,6 +502,7 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
     if (e && !strcmp(e, "direct")) h->kernel_mode = 0;
     else if (e && !strcmp(e, "tma1d")) h->kernel_mode = 1;
     else if (e && !strcmp(e, "stream")) h->kernel_mode = 2;
+    else if (e && !strcmp(e, "direct2")) h->kernel_mode = 3;
   }
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return PAMG_ERR_CUDA; }
   cudaDeviceProp prop;

@@ -16,9 +16,10 @@
 
 namespace pamg {
 
-constexpr int NPC = 20;  // doubles per parent per level
+constexpr int NPC = 56;  // doubles per parent per level: ParentRegs (22, padded to 24) + Folded up (16) + Folded down (16)
+constexpr int PC_FOLD = 24;
 // per-parent per-level coefficient slots
-enum { PC_CM = 0, PC_K11 = 1, PC_K12, PC_K13, PC_K22, PC_K23, PC_K33, PC_ADV = 7, PC_FL = 10, PC_PENI = 13, PC_PENX = 16 };
+enum { PC_CM = 0, PC_K11 = 1, PC_K12, PC_K13, PC_K22, PC_K23, PC_K33, PC_ADV = 7, PC_FL = 10, PC_PENI = 13, PC_W = 16, PC_PENX = 19 };
 
 constexpr int TPB = 256;
 
@@ -38,6 +39,7 @@ struct ElemArgs {
   long long nelem;        // U * C
   int s;                  // split of this level
   int colour;             // GS: 0 = down children, 1 = up children
+  int dbg;                // experiments only (PAMG_DBG): 1 = skip the vertical-neighbour loads of the tile kernel
 };
 
 // flat child index t in [0, 4^s) -> row r (1-based), position ipos (1-based), element id ele (1-based)
@@ -293,19 +295,37 @@ struct ParentRegs {
   double w1, w2, w3;   // omega / D for children whose three faces are all inside the parent
   double px1, px2, px3;   // penalty coefficients of faces on the parent boundary
 };
-__device__ __forceinline__ void load_parent(const double* __restrict__ pc, double omega, bool face, ParentRegs& P) {
-  P.cm = __ldg(pc + PC_CM);
-  P.k11 = __ldg(pc + PC_K11); P.k12 = __ldg(pc + PC_K12); P.k13 = __ldg(pc + PC_K13);
-  P.k22 = __ldg(pc + PC_K22); P.k23 = __ldg(pc + PC_K23); P.k33 = __ldg(pc + PC_K33);
-  P.adv1 = __ldg(pc + PC_ADV); P.adv2 = __ldg(pc + PC_ADV + 1); P.adv3 = __ldg(pc + PC_ADV + 2);
-  P.fl1 = __ldg(pc + PC_FL); P.fl2 = __ldg(pc + PC_FL + 1); P.fl3 = __ldg(pc + PC_FL + 2);
-  P.pi1 = __ldg(pc + PC_PENI); P.pi2 = __ldg(pc + PC_PENI + 1); P.pi3 = __ldg(pc + PC_PENI + 2);
-  // get_diagonal (:481-486): node 1 sits on faces 1,3; node 2 on faces 2,3; node 3 on faces 1,2
-  const double f = face ? 2.0 : 0.0;   // the penalty diagonal exists only with the face block on
-  P.w1 = omega / (4.0 * P.cm + P.k11 + f * (P.pi1 + P.pi3));
-  P.w2 = omega / (4.0 * P.cm + P.k22 + f * (P.pi2 + P.pi3));
-  P.w3 = omega / (4.0 * P.cm + P.k33 + f * (P.pi1 + P.pi2));
-  P.px1 = __ldg(pc + PC_PENX); P.px2 = __ldg(pc + PC_PENX + 1); P.px3 = __ldg(pc + PC_PENX + 2);
+static_assert(sizeof(ParentRegs) == 22 * sizeof(double), "ParentRegs must mirror the pc table");
+__device__ __forceinline__ void load_parent(const double* __restrict__ pc, ParentRegs& P) {
+  double* d = reinterpret_cast<double*>(&P);
+#pragma unroll
+  for (int i = 0; i < 22; ++i) d[i] = __ldg(pc + i);
+}
+
+// Folded operator of a child whose three faces are inside the parent, one set per orientation (up / down).
+// Everything elem_apply adds up term by term is linear in (T, neighbour values), so for such children
+//   (A x)_i = sum_j a_ij T_j + sum_f c_f [[2,1],[1,2]] (n_fa, n_fb)
+// with a_ij = mass + advection + diffusion + penalty + outflow flux and c_f = -pen_f (+ inflow flux).
+// The host folds the coefficients once per parent and level (fold_coefficients in pamg_api.cu); the kernels
+// spend 27 fp64 operations per child instead of ~70 and need no upwind selects.
+struct Folded { double a11, a12, a13, a21, a22, a23, a31, a32, a33, c1, c2, c3, w1, w2, w3, pad; };
+static_assert(sizeof(Folded) == 16 * sizeof(double), "Folded layout");
+
+template <int MODE>
+__device__ __forceinline__ void elem_apply_folded(const Folded& F, double T1, double T2, double T3, const FaceIn& fi,
+                                                  double b1, double b2, double b3, double rsign, double& o1,
+                                                  double& o2, double& o3) {
+  double ax1 = F.a11 * T1 + F.a12 * T2 + F.a13 * T3;
+  double ax2 = F.a21 * T1 + F.a22 * T2 + F.a23 * T3;
+  double ax3 = F.a31 * T1 + F.a32 * T2 + F.a33 * T3;
+  ax1 += F.c1 * (2.0 * fi.n1a + fi.n1b); ax3 += F.c1 * (fi.n1a + 2.0 * fi.n1b);   // face 1: nodes (1,3)
+  ax3 += F.c2 * (2.0 * fi.n2a + fi.n2b); ax2 += F.c2 * (fi.n2a + 2.0 * fi.n2b);   // face 2: nodes (3,2)
+  ax2 += F.c3 * (2.0 * fi.n3a + fi.n3b); ax1 += F.c3 * (fi.n3a + 2.0 * fi.n3b);   // face 3: nodes (2,1)
+  if (MODE == MODE_RESID) {
+    o1 = rsign * (ax1 - b1); o2 = rsign * (ax2 - b2); o3 = rsign * (ax3 - b3);
+  } else {
+    o1 = T1 + F.w1 * (b1 - ax1); o2 = T2 + F.w2 * (b2 - ax2); o3 = T3 + F.w3 * (b3 - ax3);
+  }
 }
 
 // Same arithmetic as elem_apply, coefficients from registers; `interior` children (no face on the parent
@@ -392,7 +412,8 @@ __global__ void __launch_bounds__(TPB) k_element_tma(ElemArgs a) {
   double (*sB)[3 * TPB] = reinterpret_cast<double (*)[3 * TPB]>(dsm + sizeof(double) * NSTAGE * TMA_T_DOUBLES);
   double (*sO)[3 * TPB] = reinterpret_cast<double (*)[3 * TPB]>(dsm + sizeof(double) * NSTAGE * (TMA_T_DOUBLES + 3 * TPB));
   uint64_t* bar = reinterpret_cast<uint64_t*>(dsm + sizeof(double) * (NSTAGE * (TMA_T_DOUBLES + 3 * TPB) + 2 * 3 * TPB));
-  __shared__ ParentRegs P;
+  __shared__ __align__(16) double sPC[NPC];
+  const ParentRegs& P = *reinterpret_cast<const ParentRegs*>(sPC);
   const int s = a.s, twos = 2 * s, b = 2 << s, S = 1 << s;
   const long long Cmask = (1ll << twos) - 1;
   const long long ndof = a.nelem * 3;
@@ -438,7 +459,7 @@ __global__ void __launch_bounds__(TPB) k_element_tma(ElemArgs a) {
       const int nb = p.up ? (k - b - 2 + 2 * p.r) : (k + b - 2 * p.r);       // 0-based child index
       if (p.up && p.r == 1) {
         halo_pair(a, p.u, 0, p.ipos >> 1, S, p.va, p.vb);
-      } else {
+      } else if (a.dbg != 1) {
         const unsigned o1 = ((unsigned)(g - k) + (unsigned)nb) * 3u;         // offsets in doubles fit 32 bits
         p.va = __ldg(a.Tin + o1 + 2); p.vb = __ldg(a.Tin + o1);
       }
@@ -459,7 +480,7 @@ __global__ void __launch_bounds__(TPB) k_element_tma(ElemArgs a) {
       const int u_tile = (int)(g0 >> twos);          // uniform over the CTA (a tile never spans two parents)
       if (u_tile != u_loaded) {
         __syncthreads();
-        if (tid == 0) load_parent(a.pc + (size_t)u_tile * NPC, a.omega, FACE, P);
+        if (tid < NPC) sPC[tid] = __ldg(a.pc + (size_t)u_tile * NPC + tid);
         __syncthreads();
         u_loaded = u_tile;
       }
@@ -487,7 +508,12 @@ __global__ void __launch_bounds__(TPB) k_element_tma(ElemArgs a) {
       }
       const double* bb = sB[st] + tid * 3;
       double o1, o2, o3;
-      elem_apply_regs<MODE, FACE>(P, cur.up, interior, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.omega, a.rsign, o1, o2, o3);
+      if (FACE && MODE != MODE_RICH && interior) {
+        const Folded& F = *reinterpret_cast<const Folded*>(sPC + PC_FOLD + (cur.up ? 0 : 16));
+        elem_apply_folded<MODE>(F, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
+      } else {
+        elem_apply_regs<MODE, FACE>(P, cur.up, interior, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.omega, a.rsign, o1, o2, o3);
+      }
       so[tid * 3] = o1; so[tid * 3 + 1] = o2; so[tid * 3 + 2] = o3;
       if (MODE == MODE_RESID) {
         acc_sum += o1 * o1 + o2 * o2 + o3 * o3;
@@ -507,6 +533,68 @@ __global__ void __launch_bounds__(TPB) k_element_tma(ElemArgs a) {
     cur = nxt;
   }
   if (tid == 0) tma_store_wait_all();
+  if (MODE == MODE_RESID) block_partial(acc_sum, acc_abs, acc_max, a.partial);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Branch-free direct kernel: thread per child, every load of the child (own values, rhs, the three
+// neighbours) is issued before the first use so that one memory latency is exposed per child instead of a
+// chain of two or three; children on a parent face patch their neighbour values from the halo strips in a
+// rare branch.  Coefficients come straight from the per-parent table (L1-resident).  Used for the coloured
+// Gauss-Seidel pass (in place) and selectable for the other modes (PAMG_KERNEL=direct2).
+template <int MODE, bool FACE>
+__global__ void __launch_bounds__(TPB) k_element_direct2(ElemArgs a) {
+  const int s = a.s, twos = 2 * s, b = 2 << s, S = 1 << s;
+  const unsigned Cmask = (1u << twos) - 1u;
+  double acc_sum = 0.0, acc_abs = 0.0, acc_max = 0.0;
+  const unsigned nelem = (unsigned)a.nelem;
+  for (unsigned gid = blockIdx.x * TPB + threadIdx.x; gid < nelem; gid += gridDim.x * TPB) {
+    const int u = (int)(gid >> twos);
+    int r, ipos, ele, len;
+    child_from_flat((int)(gid & Cmask), s, r, ipos, ele, len);
+    const bool up = ipos & 1;
+    if (MODE == MODE_GS && (int)up != a.colour) continue;
+    const unsigned pbase = (unsigned)u << twos;
+    const unsigned e0 = pbase + (unsigned)(ele - 1);
+    // neighbour children; a missing neighbour (parent face) falls back to the child itself (valid address)
+    const int nb1 = up ? (r > 1 ? ele - b - 2 + 2 * r : ele) : ele + b - 2 * r;
+    const int nb2 = up ? (ipos > 1 ? ele - 1 : ele) : ele + 1;
+    const int nb3 = up ? (ipos < len ? ele + 1 : ele) : ele - 1;
+    const unsigned base = e0 * 3u;
+    auto ldT = [&](unsigned i) -> double { return MODE == MODE_GS ? a.Tin[i] : __ldg(a.Tin + i); };
+    const double T1 = ldT(base), T2 = ldT(base + 1), T3 = ldT(base + 2);
+    const double b1 = __ldg(a.rhs + base), b2 = __ldg(a.rhs + base + 1), b3 = __ldg(a.rhs + base + 2);
+    FaceIn fi;
+    const ParentRegs& P = *reinterpret_cast<const ParentRegs*>(a.pc + (size_t)u * NPC);
+    bool interior = true;
+    if (FACE) {
+      const unsigned o1 = (pbase + (unsigned)(nb1 - 1)) * 3u, o2 = (pbase + (unsigned)(nb2 - 1)) * 3u,
+                     o3 = (pbase + (unsigned)(nb3 - 1)) * 3u;
+      fi.n1a = ldT(o1 + 2); fi.n1b = ldT(o1);        // my node 1 <-> its node 3, my node 3 <-> its node 1
+      fi.n2a = ldT(o2 + 1); fi.n2b = ldT(o2 + 2);    // my 3 <-> its 2, my 2 <-> its 3
+      fi.n3a = ldT(o3); fi.n3b = ldT(o3 + 1);        // my 2 <-> its 1, my 1 <-> its 2
+      fi.pen1 = P.pi1; fi.pen2 = P.pi2; fi.pen3 = P.pi3;
+      if (up && (r == 1 || ipos == 1 || ipos == len)) {   // child on a parent face (rare): halo strips
+        interior = false;
+        if (r == 1) { halo_pair(a, u, 0, ipos >> 1, S, fi.n1a, fi.n1b); fi.pen1 = P.px1; }
+        if (ipos == 1) { halo_pair(a, u, 2, r - 1, S, fi.n2a, fi.n2b); fi.pen2 = P.px2; }
+        if (ipos == len) { halo_pair(a, u, 1, r - 1, S, fi.n3a, fi.n3b); fi.pen3 = P.px3; }
+      }
+    }
+    double o1v, o2v, o3v;
+    if (FACE && MODE != MODE_RICH && interior) {
+      const Folded& F = *reinterpret_cast<const Folded*>(a.pc + (size_t)u * NPC + PC_FOLD + (up ? 0 : 16));
+      elem_apply_folded<MODE>(F, T1, T2, T3, fi, b1, b2, b3, a.rsign, o1v, o2v, o3v);
+    } else {
+      elem_apply_regs<MODE, FACE>(P, up, interior, T1, T2, T3, fi, b1, b2, b3, a.omega, a.rsign, o1v, o2v, o3v);
+    }
+    a.Tout[base] = o1v; a.Tout[base + 1] = o2v; a.Tout[base + 2] = o3v;
+    if (MODE == MODE_RESID) {
+      acc_sum += o1v * o1v + o2v * o2v + o3v * o3v;
+      acc_abs = fmax(acc_abs, fmax(fabs(o1v), fmax(fabs(o2v), fabs(o3v))));
+      acc_max = fmax(acc_max, fmax(o1v, fmax(o2v, o3v)));
+    }
+  }
   if (MODE == MODE_RESID) block_partial(acc_sum, acc_abs, acc_max, a.partial);
 }
 
