@@ -268,10 +268,30 @@ def main():
     e2e_value = world * ndof * NSMOOTH * e2e_steps / (e2e_ms * 1e-3)
     clocks = sampler.stop() if sampler else None
 
+    # ---- other kernels of the path: coloured GS sweep (32 B/DOF) and residual + norms (24 B/DOF) -----------
+    extra = {}
+    for name, fn, bpd in (("gauss_seidel_sweep", lambda: g.smoother(1, pkg.GAUSS_SEIDEL, 1), 32.0),
+                          ("residual_with_norms", lambda: g.get_residual(1), 24.0)):
+        for _ in range(3):
+            fn()
+        g.sync(); barrier()
+        g.event_record(6)
+        reps = 10
+        for _ in range(reps):
+            fn()
+        g.event_record(7)
+        g.sync(); barrier()
+        t_ms = allmax(g.elapsed_ms(6, 7)) / reps
+        extra[name] = {"ms": t_ms, "dof_updates_per_s": world * ndof / (t_ms * 1e-3),
+                       "algorithmic_GBps_per_gpu": bpd * ndof / (t_ms * 1e-3) / 1e9, "bytes_per_dof": bpd}
+
     # ---- V-cycle time to 1e-8 (second half of the BASELINE metric) ----------------------------------------
     vc = None
     if not args.no_vcycle:
         gs = {}
+        # untimed warm-up cycle: first use of the coarse-level kernels and (N > 1) of the NCCL channels
+        g.fill(pkg.TNONLIN, 1, 0.0); g.copy(1, pkg.TNEW, pkg.TNONLIN); g.fill(pkg.TOLD, 1, 0.0)
+        g.vcycle_solve(solver=pkg.GAUSS_SEIDEL, nu1=NSMOOTH, nu2=NSMOOTH, ncoarse=15, max_cycles=1, tol=1e-8)
         for name, solver in (("jacobi", pkg.JACOBI), ("gauss_seidel", pkg.GAUSS_SEIDEL)):
             g.fill(pkg.TNONLIN, 1, 0.0)
             g.copy(1, pkg.TNEW, pkg.TNONLIN)
@@ -304,7 +324,15 @@ def main():
                          "whole_step_frac": (BYTES_PER_DOF_JACOBI * ndof * NSMOOTH * args.steps / (ms * 1e-3) / 1e9) / peak},
             "clocks": clocks,
             "vcycle_to_1e-8": vc,
+            "other_kernels": extra,
         }
+        try:   # DRAM bytes of the dominant kernel from the committed ncu --set full capture (per launch)
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tr = json.load(f)
+            line["roofline"]["traffic"] = tr.get("k_element_tma_jacobi_face_dram_bytes_per_launch")
+            line["roofline"]["traffic_source"] = tr.get("source")
+        except Exception:
+            pass
         if not args.no_cpu_baseline:
             orc = oracle_api()
             cores = os.cpu_count() or 1

@@ -48,6 +48,9 @@ typedef struct pamg_params {
   int32_t residual_sign;  /* +1: r = A x - b (:869);  -1: r = b - A x */
   int32_t halo_rule;      /* 0: Dir/Nside reversal table (splitting.F90:1256-1391); 1: geometric pairing */
   int32_t coarse_bc_zero; /* 1: homogeneous Dirichlet data on levels > 1; 0: sin(x+y) on every level (HEAD) */
+  int32_t keep_tnew_gs;   /* 1: the in-place GS sweep keeps tracer%tnew = start-of-last-sweep field (:550) by a device copy;
+                             0: TNEW aliases the iterate after a GS smoother call (saves 16 B/DOF per call) */
+  int32_t reserved;       /* keeps the doubles 8-byte aligned */
   double theta;           /* :117 (only theta = 1 is implemented, like the reference's literal) */
   double dt;              /* :133  dt = CFL*dx */
   double k;               /* :136 */

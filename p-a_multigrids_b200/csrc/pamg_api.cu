@@ -335,7 +335,7 @@ int do_smooth(pamg_handle* h, int level, int solver, int nsweeps) {
     } else if (solver == 3 || solver == 4) {
       // two-colour ordering of the reference's Gauss-Seidel sweep: all down children, then all up children;
       // values across parent faces stay lagged through the halo strips exactly as at :647-655.
-      if (sw == nsweeps - 1) { rc = materialise_tnew(h, L); if (rc) return rc; }  // keep tracer%tnew observable
+      if (sw == nsweeps - 1 && h->p.keep_tnew_gs) { rc = materialise_tnew(h, L); if (rc) return rc; }  // keep tracer%tnew observable
       rc = launch_element<MODE_GS>(h, L, L.T[L.cur], L.T[L.cur], 0, grid);
       if (rc) return rc;
       rc = launch_element<MODE_GS>(h, L, L.T[L.cur], L.T[L.cur], 1, grid);
@@ -479,10 +479,10 @@ void pamg_default_params(pamg_params* p, int literal_head) {
   p->theta = 1.0; p->k = 1.0; p->omega = 0.8; p->u_x = 0.0; p->u_y = 0.0;
   if (literal_head) {  // main.F90:46-47, transport_tri_semi.F90:117-140 as checked in
     p->dt = 1.25e-5; p->face_terms = 0; p->literal_source = 1; p->transfer = 0; p->residual_sign = 1;
-    p->halo_rule = 0; p->coarse_bc_zero = 0; p->source_coef = -2.0;
+    p->halo_rule = 0; p->coarse_bc_zero = 0; p->source_coef = -2.0; p->keep_tnew_gs = 1;
   } else {
     p->dt = 1e-3; p->face_terms = 1; p->literal_source = 0; p->transfer = 1; p->residual_sign = -1;
-    p->halo_rule = 1; p->coarse_bc_zero = 1; p->source_coef = 2.0;
+    p->halo_rule = 1; p->coarse_bc_zero = 1; p->source_coef = 2.0; p->keep_tnew_gs = 0;
   }
 }
 

@@ -1,0 +1,171 @@
+! pamg_iface.F90 -- ISO_C_BINDING interfaces to libpamg_cuda.so (include/pamg.h) for the reference's own
+! Fortran driver (main.F90 / transport_tri_semi.F90).  NOT COMPILED OR TESTED IN THIS REPOSITORY: the build
+! image has no Fortran compiler.  The identical call sequence is exercised from C++ (host/pamg_host.cpp)
+! and Python (pamg.py).  See INTEGRATION.md for where each call replaces a contained procedure of
+! Semi_implicit_iterative.
+!
+! Layout notes: tracer(ilevel)%tnew(nloc, totele_str, totele_unst) is passed as is (column-major, contiguous);
+! meshList(:)%X / Neig / fNeig / Dir are gathered once into X(2,3,U), neig(3,U), fneig(3,U), dir(3,U)
+! (Dir: .true. -> 1).  All routines return 0 on success, < 0 on error (like ierr / errorflag).
+module pamg_iface
+  use, intrinsic :: iso_c_binding
+  implicit none
+
+  integer(c_int), parameter :: PAMG_TNEW = 0, PAMG_TOLD = 1, PAMG_RHS = 2, PAMG_RES = 3, PAMG_TNONLIN = 5
+
+  type, bind(c) :: pamg_params
+    integer(c_int32_t) :: n_split, multi_levels, n_smooth, n_multigrid, n_coarse_smooth, solver
+    integer(c_int32_t) :: face_terms, literal_source, transfer, residual_sign, halo_rule, coarse_bc_zero
+    integer(c_int32_t) :: keep_tnew_gs, reserved
+    real(c_double) :: theta, dt, k, omega, u_x, u_y, source_coef
+  end type pamg_params
+
+  interface
+    subroutine pamg_default_params(p, literal_head) bind(c, name="pamg_default_params")
+      import :: pamg_params, c_int
+      type(pamg_params), intent(out) :: p
+      integer(c_int), value :: literal_head
+    end subroutine
+
+    integer(c_int) function pamg_create(p, device, handle) bind(c, name="pamg_create")
+      import :: pamg_params, c_int, c_ptr
+      type(pamg_params), intent(in) :: p
+      integer(c_int), value :: device
+      type(c_ptr), intent(out) :: handle
+    end function
+
+    subroutine pamg_destroy(handle) bind(c, name="pamg_destroy")
+      import :: c_ptr
+      type(c_ptr), value :: handle
+    end subroutine
+
+    integer(c_int) function pamg_set_parents(handle, U, X, neig, fneig, dir) bind(c, name="pamg_set_parents")
+      import :: c_int, c_ptr, c_double, c_int32_t
+      type(c_ptr), value :: handle
+      integer(c_int), value :: U
+      real(c_double), intent(in) :: X(2, 3, *)
+      integer(c_int32_t), intent(in) :: neig(3, *), fneig(3, *), dir(3, *)
+    end function
+
+    integer(c_int) function pamg_upload_field(handle, field, level, host) bind(c, name="pamg_upload_field")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      integer(c_int), value :: field, level
+      real(c_double), intent(in) :: host(*)
+    end function
+
+    integer(c_int) function pamg_download_field(handle, field, level, host) bind(c, name="pamg_download_field")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      integer(c_int), value :: field, level
+      real(c_double), intent(out) :: host(*)
+    end function
+
+    integer(c_int) function pamg_copy_field(handle, level, dst_field, src_field) bind(c, name="pamg_copy_field")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int), value :: level, dst_field, src_field
+    end function
+
+    ! update_overlaps (splitting.F90:1210)
+    integer(c_int) function pamg_update_overlaps(handle, level) bind(c, name="pamg_update_overlaps")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int), value :: level
+    end function
+
+    ! smoother (transport_tri_semi.F90:543)
+    integer(c_int) function pamg_smooth(handle, level, solver, nsweeps) bind(c, name="pamg_smooth")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int), value :: level, solver, nsweeps
+    end function
+
+    ! get_residual (:725) + norms
+    integer(c_int) function pamg_residual(handle, level, l2, linf) bind(c, name="pamg_residual")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      integer(c_int), value :: level
+      real(c_double), intent(out) :: l2, linf
+    end function
+
+    ! get_convergence (:876)
+    integer(c_int) function pamg_convergence(handle, level, conv) bind(c, name="pamg_convergence")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      integer(c_int), value :: level
+      real(c_double), intent(out) :: conv
+    end function
+
+    ! restrictor / prolongator (splitting.F90:10,38)
+    integer(c_int) function pamg_restrict(handle, fine_level) bind(c, name="pamg_restrict")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int), value :: fine_level
+    end function
+
+    integer(c_int) function pamg_prolong(handle, fine_level) bind(c, name="pamg_prolong")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int), value :: fine_level
+    end function
+
+    integer(c_int) function pamg_vcycle_solve(handle, solver, nu1, nu2, ncoarse, max_cycles, tol, cycles, hist) &
+        bind(c, name="pamg_vcycle_solve")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      integer(c_int), value :: solver, nu1, nu2, ncoarse, max_cycles
+      real(c_double), value :: tol
+      integer(c_int), intent(out) :: cycles
+      real(c_double), intent(out) :: hist(*)
+    end function
+
+    ! one itime of the loop at transport_tri_semi.F90:316-379
+    integer(c_int) function pamg_literal_timestep(handle, solver, n_multigrid, n_smooth) &
+        bind(c, name="pamg_literal_timestep")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int), value :: solver, n_multigrid, n_smooth
+    end function
+
+    ! unstr_explicit (transport_tri_unstr.F90:413)
+    integer(c_int) function pamg_set_unstructured(handle, E, X, neig, fneig) bind(c, name="pamg_set_unstructured")
+      import :: c_int, c_ptr, c_double, c_int32_t
+      type(c_ptr), value :: handle
+      integer(c_int), value :: E
+      real(c_double), intent(in) :: X(2, 3, *)
+      integer(c_int32_t), intent(in) :: neig(3, *), fneig(3, *)
+    end function
+
+    integer(c_int) function pamg_unstr_upload(handle, tnew) bind(c, name="pamg_unstr_upload")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), intent(in) :: tnew(3, *)
+    end function
+
+    integer(c_int) function pamg_unstr_download(handle, tnew) bind(c, name="pamg_unstr_download")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), intent(out) :: tnew(3, *)
+    end function
+
+    integer(c_int) function pamg_explicit_step(handle, dt, u_x, u_y, t_bc, ntime, nits, njac_its, use_exact_minv, &
+                                               use_dir) bind(c, name="pamg_explicit_step")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), value :: dt, u_x, u_y, t_bc
+      integer(c_int), value :: ntime, nits, njac_its, use_exact_minv, use_dir
+    end function
+
+    ! FINDInv (matrices.F90:1618), batched
+    integer(c_int) function pamg_apply_local_minv(handle, n, batch, M, rhs, x, Minv, status) &
+        bind(c, name="pamg_apply_local_minv")
+      import :: c_int, c_ptr, c_double, c_int32_t
+      type(c_ptr), value :: handle
+      integer(c_int), value :: n, batch
+      real(c_double), intent(in) :: M(*)      ! note: row-major [batch][n][n]; pass transpose(matrix) per block
+      type(c_ptr), value :: rhs, x, Minv, status
+    end function
+  end interface
+
+end module pamg_iface

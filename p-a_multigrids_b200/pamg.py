@@ -35,7 +35,7 @@ class Params(C.Structure):
         ("n_split", C.c_int32), ("multi_levels", C.c_int32), ("n_smooth", C.c_int32), ("n_multigrid", C.c_int32),
         ("n_coarse_smooth", C.c_int32), ("solver", C.c_int32), ("face_terms", C.c_int32),
         ("literal_source", C.c_int32), ("transfer", C.c_int32), ("residual_sign", C.c_int32),
-        ("halo_rule", C.c_int32), ("coarse_bc_zero", C.c_int32),
+        ("halo_rule", C.c_int32), ("coarse_bc_zero", C.c_int32), ("keep_tnew_gs", C.c_int32), ("reserved", C.c_int32),
         ("theta", C.c_double), ("dt", C.c_double), ("k", C.c_double), ("omega", C.c_double),
         ("u_x", C.c_double), ("u_y", C.c_double), ("source_coef", C.c_double),
     ]

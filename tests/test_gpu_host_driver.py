@@ -1,0 +1,64 @@
+"""The C++ host driver (pamg_host, mirror of main.F90 modes 4 and 9) against the oracle."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_api as orc
+from helpers import ROOT, write_msh
+from pamg_pkg import pamg
+
+pytestmark = pytest.mark.gpu
+HOST = os.path.join(ROOT, "p-a_multigrids_b200", "lib", "pamg_host")
+
+
+def run_host(*args):
+    r = subprocess.run([HOST, *map(str, args)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+def test_mode9_as_checked_in(tmp_path):
+    """main.F90:46-47 on test_sn2.msh: n_split 1, 1 level, GS, 4 sweeps, 2 cycles, 2 steps, IC region 4."""
+    path = write_msh("test_sn2", str(tmp_path / "test_sn2.msh"))
+    out = run_host("--mode", 9, "--mesh", path)
+    m = re.search(r"tnew: sum ([-+0-9.e]+) min ([-+0-9.e]+) max ([-+0-9.e]+)", out)
+    assert m, out
+    mesh = pamg.Mesh.read_msh(path)
+    o = orc.Semi(orc.literal_params(1, 1), mesh.X, mesh.neig, mesh.fneig, mesh.dir)
+    ic = np.zeros(o.field(orc.TNEW).shape)
+    ic[mesh.region == 4] = 1.0
+    o.field(orc.TNEW)[:] = ic
+    for _ in range(2):
+        o.literal_timestep(solver=3, n_multigrid=2, n_smooth=4)
+    ref = o.field(orc.TNEW)
+    assert abs(float(m.group(1)) - ref.sum()) <= 1e-9 * max(1.0, abs(ref.sum()))
+    assert abs(float(m.group(2)) - ref.min()) <= 1e-6 and abs(float(m.group(3)) - ref.max()) <= 1e-6
+    assert "totele_unst, totele_str, totele 12 4 48" in out
+
+
+def test_mode9_intended_vcycles(tmp_path):
+    path = write_msh("split0", str(tmp_path / "split0.msh"))
+    out = run_host("--mode", 9, "--mesh", path, "--intended", "--n_split", 5, "--multi_levels", 5, "--ntime", 1,
+                   "--solver", 3, "--region", 99)
+    m = re.search(r"V-cycles (\d+)\s+\|\|r\|\|/\|\|r0\|\| ([0-9.e+-]+)", out)
+    assert m, out
+    mesh = pamg.Mesh.read_msh(path)
+    o = orc.Semi(orc.intended_params(5, 5), mesh.X, mesh.neig, mesh.fneig, mesh.dir)
+    it, _ = o.vcycle_solve(solver=4, max_cycles=50, tol=1e-8)
+    assert abs(int(m.group(1)) - it) <= 1 and float(m.group(2)) <= 1e-8
+
+
+def test_mode4_unstr_explicit(tmp_path):
+    path = write_msh("untitled8192", str(tmp_path / "u.msh"))
+    out = run_host("--mode", 4, "--mesh", path)
+    m = re.search(r"tnew: sum ([-+0-9.e]+) min ([-+0-9.e]+) max ([-+0-9.e]+)", out)
+    assert m, out
+    mesh = pamg.Mesh.read_msh(path)
+    T = np.zeros((mesh.U, 3))
+    T[mesh.region == 12] = 1.0
+    orc.lib().orc_unstr_explicit(mesh.U, mesh.X, mesh.neig, mesh.fneig, mesh.dir, 0.9, 0.0, 0.07e-3, 2, 2, 10, 0, 0, 0.0, T)
+    assert abs(float(m.group(1)) - T.sum()) <= 1e-9 * abs(T.sum())
+    assert "totele = 8192" in out

@@ -1,0 +1,24 @@
+"""Two-rank run on two GPUs (NCCL halo exchange inside libpamg_cuda) against the single-GPU result.
+Skipped when the box has fewer than 2 GPUs."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from pamg_pkg import pamg
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.parametrize("world", [2])
+def test_partitioned_smoother_and_vcycle_match_single_gpu(world):
+    if pamg.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    port = 29700 + (os.getpid() % 200)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "multi_gpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "MULTI_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -19,9 +19,10 @@ def make_pair(mesh, n, levels, intended, u=(0.0, 0.0), dt=None, halo_rule=None, 
         op = orc.literal_params(n, levels, dt=dt or 1.25e-5, u=u)
     if halo_rule is not None:
         op.halo_rule = halo_rule
+    gkw = {k: kw.pop(k) for k in list(kw) if k in ("keep_tnew_gs",)}
     for k, v in kw.items():
         setattr(op, k, v)
-    gp = pamg.default_params(literal_head=not intended, n_split=n, multi_levels=levels)
+    gp = pamg.default_params(literal_head=not intended, n_split=n, multi_levels=levels, **gkw)
     for f in ("face_terms", "literal_source", "transfer", "residual_sign", "halo_rule", "coarse_bc_zero",
               "theta", "dt", "k", "omega", "u_x", "u_y", "source_coef"):
         setattr(gp, f, getattr(op, f))
@@ -124,7 +125,7 @@ def test_jacobi_sweep_and_residual(meshes, name, n, intended, u):
 @pytest.mark.parametrize("name,n,u", [("test_sn2", 3, (0.9, 0.3)), ("split0", 5, (0.0, 0.0)), ("900_ele", 2, (0.1, 0.1)),
                                       ("syn", 4, (0.9, 0.3))])
 def test_two_colour_gauss_seidel_sweep(meshes, name, n, u):
-    o, g = make_pair(meshes[name], n, 1, True, u=u)
+    o, g = make_pair(meshes[name], n, 1, True, u=u, keep_tnew_gs=1)
     seed_fields(o, g)
     for sweep in range(3):
         o.smooth(1, 4, 1)                       # oracle runs the same colouring: down children, then up
