@@ -224,6 +224,17 @@ void parent_coefficients(const pamg_params& p, const double* Xall, const int32_t
     F[6] = A[2][0]; F[7] = A[2][1]; F[8] = A[2][2]; F[9] = c[0]; F[10] = c[1]; F[11] = c[2];
     F[12] = pc[PC_W + 0]; F[13] = pc[PC_W + 1]; F[14] = pc[PC_W + 2]; F[15] = 0.0;
   }
+  // children with faces on the parent boundary: penalty change per face and omega / D per face mask
+  for (int f = 0; f < 3; ++f) pc[PC_DPEN + f] = p.face_terms ? pc[PC_PENX + f] - pc[PC_PENI + f] : 0.0;
+  pc[PC_DPEN + 3] = 0.0;
+  for (int mask = 0; mask < 8; ++mask) {
+    double pen[3];
+    for (int f = 0; f < 3; ++f) pen[f] = p.face_terms ? ((mask >> f) & 1 ? pc[PC_PENX + f] : pc[PC_PENI + f]) : 0.0;
+    pc[PC_WB + mask * 3 + 0] = p.omega / (4.0 * pc[PC_CM] + pc[PC_K11] + 2.0 * (pen[0] + pen[2]));
+    pc[PC_WB + mask * 3 + 1] = p.omega / (4.0 * pc[PC_CM] + pc[PC_K22] + 2.0 * (pen[1] + pen[2]));
+    pc[PC_WB + mask * 3 + 2] = p.omega / (4.0 * pc[PC_CM] + pc[PC_K33] + 2.0 * (pen[0] + pen[1]));
+  }
+  for (int i = PC_WB + 24; i < NPC; ++i) pc[i] = 0.0;
 }
 
 int launch_halo(pamg_handle* h, int level);

@@ -16,8 +16,11 @@
 
 namespace pamg {
 
-constexpr int NPC = 56;  // doubles per parent per level: ParentRegs (22, padded to 24) + Folded up (16) + Folded down (16)
+constexpr int NPC = 88;  // doubles per parent per level: ParentRegs (22, padded to 24) + Folded up (16) + Folded down (16)
+                         // + boundary corrections: dpen (3, padded to 4) + omega/D for the 8 face masks (24) + pad (4)
 constexpr int PC_FOLD = 24;
+constexpr int PC_DPEN = 56;   // penX_f - penI_f : what changes when child face f lies on the parent boundary
+constexpr int PC_WB = 60;     // [mask][3] omega / D with mask bit f set when face f+1 is on the parent boundary
 // per-parent per-level coefficient slots
 enum { PC_CM = 0, PC_K11 = 1, PC_K12, PC_K13, PC_K22, PC_K23, PC_K33, PC_ADV = 7, PC_FL = 10, PC_PENI = 13, PC_W = 16, PC_PENX = 19 };
 
@@ -138,6 +141,11 @@ __device__ __forceinline__ void halo_pair(const ElemArgs& a, int u, int mf, int 
   const int hm = __ldg(a.hmap + u * 3 + mf);
   const double* e = a.ovl + ((size_t)__ldg(a.strip_of + u * 3 + mf) * S + slot0) * 3;
   va = __ldg(e + (hm & 3)); vb = __ldg(e + (hm >> 2));
+}
+
+// same with the strip index and node map already at hand (kept in shared memory by the tile kernel)
+__device__ __forceinline__ const double* halo_entry(const ElemArgs& a, int strip, int slot0, int S) {
+  return a.ovl + ((size_t)strip * S + slot0) * 3;
 }
 
 // deterministic two-stage norm reduction: warp shuffle, then one partial per CTA
@@ -311,20 +319,32 @@ __device__ __forceinline__ void load_parent(const double* __restrict__ pc, Paren
 struct Folded { double a11, a12, a13, a21, a22, a23, a31, a32, a33, c1, c2, c3, w1, w2, w3, pad; };
 static_assert(sizeof(Folded) == 16 * sizeof(double), "Folded layout");
 
+// `mask` has bit f-1 set when child face f lies on the parent boundary (only up children, rare); `ext` points
+// at the PC_DPEN / PC_WB part of the parent's table.  The correction is the penalty formula with
+// dpen = penX - penI (the neighbour values already come from the halo strip), and omega / D is tabulated
+// per mask, so a boundary child costs a handful of extra FMAs instead of the generic path with 3 divisions.
 template <int MODE>
-__device__ __forceinline__ void elem_apply_folded(const Folded& F, double T1, double T2, double T3, const FaceIn& fi,
-                                                  double b1, double b2, double b3, double rsign, double& o1,
-                                                  double& o2, double& o3) {
+__device__ __forceinline__ void elem_apply_folded(const Folded& F, const double* ext, int mask, double T1, double T2,
+                                                  double T3, const FaceIn& fi, double b1, double b2, double b3,
+                                                  double rsign, double& o1, double& o2, double& o3) {
   double ax1 = F.a11 * T1 + F.a12 * T2 + F.a13 * T3;
   double ax2 = F.a21 * T1 + F.a22 * T2 + F.a23 * T3;
   double ax3 = F.a31 * T1 + F.a32 * T2 + F.a33 * T3;
   ax1 += F.c1 * (2.0 * fi.n1a + fi.n1b); ax3 += F.c1 * (fi.n1a + 2.0 * fi.n1b);   // face 1: nodes (1,3)
   ax3 += F.c2 * (2.0 * fi.n2a + fi.n2b); ax2 += F.c2 * (fi.n2a + 2.0 * fi.n2b);   // face 2: nodes (3,2)
   ax2 += F.c3 * (2.0 * fi.n3a + fi.n3b); ax1 += F.c3 * (fi.n3a + 2.0 * fi.n3b);   // face 3: nodes (2,1)
+  double w1 = F.w1, w2 = F.w2, w3 = F.w3;
+  if (mask) {
+    if (mask & 1) { const double dp = ext[0], da = T1 - fi.n1a, db = T3 - fi.n1b; ax1 += dp * (2.0 * da + db); ax3 += dp * (da + 2.0 * db); }
+    if (mask & 2) { const double dp = ext[1], da = T3 - fi.n2a, db = T2 - fi.n2b; ax3 += dp * (2.0 * da + db); ax2 += dp * (da + 2.0 * db); }
+    if (mask & 4) { const double dp = ext[2], da = T2 - fi.n3a, db = T1 - fi.n3b; ax2 += dp * (2.0 * da + db); ax1 += dp * (da + 2.0 * db); }
+    const double* wb = ext + 4 + mask * 3;
+    w1 = wb[0]; w2 = wb[1]; w3 = wb[2];
+  }
   if (MODE == MODE_RESID) {
     o1 = rsign * (ax1 - b1); o2 = rsign * (ax2 - b2); o3 = rsign * (ax3 - b3);
   } else {
-    o1 = T1 + F.w1 * (b1 - ax1); o2 = T2 + F.w2 * (b2 - ax2); o3 = T3 + F.w3 * (b3 - ax3);
+    o1 = T1 + w1 * (b1 - ax1); o2 = T2 + w2 * (b2 - ax2); o3 = T3 + w3 * (b3 - ax3);
   }
 }
 
@@ -406,13 +426,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // the per-parent coefficients live in shared memory, and results leave through one 6 KB bulk store per tile.
 // (A warp-decoupled variant with full/empty mbarriers and per-warp stores measured slower: profiles/README.)
 template <int MODE, bool FACE>
-__global__ void __launch_bounds__(TPB) k_element_tma(ElemArgs a) {
+__global__ void __launch_bounds__(TPB, 3) k_element_tma(ElemArgs a) {
   extern __shared__ __align__(128) unsigned char dsm[];   // TMA_SMEM_BYTES, carved below
   double (*sT)[TMA_T_DOUBLES] = reinterpret_cast<double (*)[TMA_T_DOUBLES]>(dsm);
   double (*sB)[3 * TPB] = reinterpret_cast<double (*)[3 * TPB]>(dsm + sizeof(double) * NSTAGE * TMA_T_DOUBLES);
   double (*sO)[3 * TPB] = reinterpret_cast<double (*)[3 * TPB]>(dsm + sizeof(double) * NSTAGE * (TMA_T_DOUBLES + 3 * TPB));
   uint64_t* bar = reinterpret_cast<uint64_t*>(dsm + sizeof(double) * (NSTAGE * (TMA_T_DOUBLES + 3 * TPB) + 2 * 3 * TPB));
   __shared__ __align__(16) double sPC[NPC];
+  __shared__ int sStrip[3], sHmap[3];   // strip index / node map of the three faces of the current parent
   const ParentRegs& P = *reinterpret_cast<const ParentRegs*>(sPC);
   const int s = a.s, twos = 2 * s, b = 2 << s, S = 1 << s;
   const long long Cmask = (1ll << twos) - 1;
@@ -463,6 +484,17 @@ __global__ void __launch_bounds__(TPB) k_element_tma(ElemArgs a) {
         const unsigned o1 = ((unsigned)(g - k) + (unsigned)nb) * 3u;         // offsets in doubles fit 32 bits
         p.va = __ldg(a.Tin + o1 + 2); p.vb = __ldg(a.Tin + o1);
       }
+      // children at a row end read a halo strip entry one tile later: pull it into L1 now, so that the
+      // single lane that needs it does not hold up its warp (and the CTA barrier) for a chain of L2 misses
+      if (p.up && (p.ipos == 1 || p.ipos == p.len)) {
+        const int mf = (p.ipos == 1) ? 2 : 1;
+        const double* e = halo_entry(a, __ldg(a.strip_of + p.u * 3 + mf), p.r - 1, S);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(e));
+        if (p.ipos == 1 && p.len == 1) {
+          const double* e2 = halo_entry(a, __ldg(a.strip_of + p.u * 3 + 1), p.r - 1, S);
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(e2));
+        }
+      }
     }
   };
   Prep cur, nxt;
@@ -481,6 +513,8 @@ __global__ void __launch_bounds__(TPB) k_element_tma(ElemArgs a) {
       if (u_tile != u_loaded) {
         __syncthreads();
         if (tid < NPC) sPC[tid] = __ldg(a.pc + (size_t)u_tile * NPC + tid);
+        else if (tid < NPC + 3) sStrip[tid - NPC] = __ldg(a.strip_of + u_tile * 3 + (tid - NPC));
+        else if (tid < NPC + 6) sHmap[tid - NPC - 3] = __ldg(a.hmap + u_tile * 3 + (tid - NPC - 3));
         __syncthreads();
         u_loaded = u_tile;
       }
@@ -492,6 +526,7 @@ __global__ void __launch_bounds__(TPB) k_element_tma(ElemArgs a) {
       const double T1 = t[0], T2 = t[1], T3 = t[2];
       FaceIn fi;
       bool interior = true;
+      int bmask = 0;
       if (FACE) {
         fi.n1a = cur.va; fi.n1b = cur.vb;
         fi.pen1 = P.pi1; fi.pen2 = P.pi2; fi.pen3 = P.pi3;
@@ -501,16 +536,24 @@ __global__ void __launch_bounds__(TPB) k_element_tma(ElemArgs a) {
         fi.n3a = t[-d]; fi.n3b = t[-d + 1];
         if (cur.up && (cur.r == 1 || cur.ipos == 1 || cur.ipos == cur.len)) {   // child on a parent face (rare)
           interior = false;
-          if (cur.r == 1) fi.pen1 = P.px1;
-          if (cur.ipos == 1) { halo_pair(a, cur.u, 2, cur.r - 1, S, fi.n2a, fi.n2b); fi.pen2 = P.px2; }
-          if (cur.ipos == cur.len) { halo_pair(a, cur.u, 1, cur.r - 1, S, fi.n3a, fi.n3b); fi.pen3 = P.px3; }
+          if (cur.r == 1) { fi.pen1 = P.px1; bmask |= 1; }
+          if (cur.ipos == 1) {
+            const double* e = halo_entry(a, sStrip[2], cur.r - 1, S);
+            const int hm = sHmap[2];
+            fi.n2a = __ldg(e + (hm & 3)); fi.n2b = __ldg(e + (hm >> 2)); fi.pen2 = P.px2; bmask |= 2;
+          }
+          if (cur.ipos == cur.len) {
+            const double* e = halo_entry(a, sStrip[1], cur.r - 1, S);
+            const int hm = sHmap[1];
+            fi.n3a = __ldg(e + (hm & 3)); fi.n3b = __ldg(e + (hm >> 2)); fi.pen3 = P.px3; bmask |= 4;
+          }
         }
       }
       const double* bb = sB[st] + tid * 3;
       double o1, o2, o3;
-      if (FACE && MODE != MODE_RICH && interior) {
+      if (FACE && MODE != MODE_RICH) {
         const Folded& F = *reinterpret_cast<const Folded*>(sPC + PC_FOLD + (cur.up ? 0 : 16));
-        elem_apply_folded<MODE>(F, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
+        elem_apply_folded<MODE>(F, sPC + PC_DPEN, bmask, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
       } else {
         elem_apply_regs<MODE, FACE>(P, cur.up, interior, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.omega, a.rsign, o1, o2, o3);
       }
@@ -567,6 +610,7 @@ __global__ void __launch_bounds__(TPB) k_element_direct2(ElemArgs a) {
     FaceIn fi;
     const ParentRegs& P = *reinterpret_cast<const ParentRegs*>(a.pc + (size_t)u * NPC);
     bool interior = true;
+    int bmask = 0;
     if (FACE) {
       const unsigned o1 = (pbase + (unsigned)(nb1 - 1)) * 3u, o2 = (pbase + (unsigned)(nb2 - 1)) * 3u,
                      o3 = (pbase + (unsigned)(nb3 - 1)) * 3u;
@@ -576,15 +620,16 @@ __global__ void __launch_bounds__(TPB) k_element_direct2(ElemArgs a) {
       fi.pen1 = P.pi1; fi.pen2 = P.pi2; fi.pen3 = P.pi3;
       if (up && (r == 1 || ipos == 1 || ipos == len)) {   // child on a parent face (rare): halo strips
         interior = false;
-        if (r == 1) { halo_pair(a, u, 0, ipos >> 1, S, fi.n1a, fi.n1b); fi.pen1 = P.px1; }
-        if (ipos == 1) { halo_pair(a, u, 2, r - 1, S, fi.n2a, fi.n2b); fi.pen2 = P.px2; }
-        if (ipos == len) { halo_pair(a, u, 1, r - 1, S, fi.n3a, fi.n3b); fi.pen3 = P.px3; }
+        if (r == 1) { halo_pair(a, u, 0, ipos >> 1, S, fi.n1a, fi.n1b); fi.pen1 = P.px1; bmask |= 1; }
+        if (ipos == 1) { halo_pair(a, u, 2, r - 1, S, fi.n2a, fi.n2b); fi.pen2 = P.px2; bmask |= 2; }
+        if (ipos == len) { halo_pair(a, u, 1, r - 1, S, fi.n3a, fi.n3b); fi.pen3 = P.px3; bmask |= 4; }
       }
     }
     double o1v, o2v, o3v;
-    if (FACE && MODE != MODE_RICH && interior) {
-      const Folded& F = *reinterpret_cast<const Folded*>(a.pc + (size_t)u * NPC + PC_FOLD + (up ? 0 : 16));
-      elem_apply_folded<MODE>(F, T1, T2, T3, fi, b1, b2, b3, a.rsign, o1v, o2v, o3v);
+    if (FACE && MODE != MODE_RICH) {
+      const double* pcu = a.pc + (size_t)u * NPC;
+      const Folded& F = *reinterpret_cast<const Folded*>(pcu + PC_FOLD + (up ? 0 : 16));
+      elem_apply_folded<MODE>(F, pcu + PC_DPEN, bmask, T1, T2, T3, fi, b1, b2, b3, a.rsign, o1v, o2v, o3v);
     } else {
       elem_apply_regs<MODE, FACE>(P, up, interior, T1, T2, T3, fi, b1, b2, b3, a.omega, a.rsign, o1v, o2v, o3v);
     }
