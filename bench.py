@@ -289,21 +289,20 @@ def main():
     vc = None
     if not args.no_vcycle:
         gs = {}
-        # untimed warm-up cycle: first use of the coarse-level kernels and (N > 1) of the NCCL channels
-        g.fill(pkg.TNONLIN, 1, 0.0); g.copy(1, pkg.TNEW, pkg.TNONLIN); g.fill(pkg.TOLD, 1, 0.0)
-        g.vcycle_solve(solver=pkg.GAUSS_SEIDEL, nu1=NSMOOTH, nu2=NSMOOTH, ncoarse=15, max_cycles=1, tol=1e-8)
         for name, solver in (("jacobi", pkg.JACOBI), ("gauss_seidel", pkg.GAUSS_SEIDEL)):
-            g.fill(pkg.TNONLIN, 1, 0.0)
-            g.copy(1, pkg.TNEW, pkg.TNONLIN)
-            g.fill(pkg.TOLD, 1, 0.0)
-            g.sync(); barrier()
-            l1 = g.launch_count()
-            g.event_record(4)
-            cyc, hist = g.vcycle_solve(solver=solver, nu1=NSMOOTH, nu2=NSMOOTH, ncoarse=15, max_cycles=60, tol=1e-8)
-            g.event_record(5)
-            g.sync(); barrier()
-            gs[name] = {"cycles": cyc, "ms": allmax(g.elapsed_ms(4, 5)), "relres": float(hist[-1] / hist[0]),
-                        "launches": g.launch_count() - l1}
+            for timed in (False, True):   # first solve untimed: kernel attributes, CUDA-graph capture, NCCL channels
+                g.fill(pkg.TNONLIN, 1, 0.0)
+                g.copy(1, pkg.TNEW, pkg.TNONLIN)
+                g.fill(pkg.TOLD, 1, 0.0)
+                g.sync(); barrier()
+                l1 = g.launch_count()
+                g.event_record(4)
+                cyc, hist = g.vcycle_solve(solver=solver, nu1=NSMOOTH, nu2=NSMOOTH, ncoarse=15, max_cycles=60, tol=1e-8)
+                g.event_record(5)
+                g.sync(); barrier()
+                if timed:
+                    gs[name] = {"cycles": cyc, "ms": allmax(g.elapsed_ms(4, 5)), "relres": float(hist[-1] / hist[0]),
+                                "launches": g.launch_count() - l1}
         vc = gs
 
     if rank == 0:

@@ -86,6 +86,11 @@ struct pamg_handle {
   double* stage = nullptr; size_t stage_bytes = 0;      // pinned staging for host-buffer entry points
   int kernel_mode = 1;  // 1 pipelined 1-D TMA tiles (default), 2 row-streaming, 0 direct loads; PAMG_KERNEL=direct|tma1d|stream
   int* counters = nullptr;
+  bool capturing = false;   // stream capture in progress: no synchronisation, no per-launch error polling
+  bool use_graph = true;    // replay the V-cycle as a CUDA graph from the second cycle on (PAMG_GRAPH=0 disables)
+  struct VcGraph { long long key; cudaGraphExec_t exec; long long launches; };
+  std::vector<VcGraph> vc_graphs;   // a few cached V-cycle graphs (solver / sweep counts / buffer parity)
+  bool gs_tma = true;   // coloured GS pass through the TMA tile kernel (PAMG_GS=direct selects the direct kernel)
   // per-kernel timing (element kernels only)
   bool profiling = false;
   std::vector<cudaEvent_t> pev;  // pairs
@@ -298,7 +303,7 @@ int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout,
     if (h->p.face_terms) k_stream<MODE, true><<<sgrid, SW, 0, h->stream>>>(sa);
     else k_stream<MODE, false><<<sgrid, SW, 0, h->stream>>>(sa);
     if (MODE == MODE_RESID) h->last_partials = sgrid;
-  } else if (MODE != MODE_GS && (h->kernel_mode == 1 || h->kernel_mode == 2) && L.C >= TPB) {
+  } else if ((MODE != MODE_GS || h->gs_tma) && (h->kernel_mode == 1 || h->kernel_mode == 2) && L.C >= TPB) {
     // 1-D TMA tiles: contiguous 6 KB spans through shared memory (pamg_kernels.cuh)
     // contiguous tile ranges per CTA: exactly one wave of resident CTAs (occupancy from the runtime)
     auto kern = h->p.face_terms ? k_element_tma<MODE, true> : k_element_tma<MODE, false>;
@@ -377,6 +382,7 @@ int do_residual(pamg_handle* h, int level, double* l2, double* linf, double* sma
       if (g_nccl.GroupEnd() != ncclSuccess) return fail(h, PAMG_ERR_CUDA, "ncclAllReduce failed");
     }
     CK(cudaMemcpyAsync(h->out3_host, h->out3, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (h->capturing) return PAMG_OK;      // the caller synchronises after the graph launch
     CK(cudaStreamSynchronize(h->stream));
     if (l2) *l2 = std::sqrt(h->out3_host[0]);
     if (linf) *linf = h->out3_host[1];
@@ -398,7 +404,7 @@ int do_restrict(pamg_handle* h, int fine_level) {
   return PAMG_OK;
 }
 
-int do_prolong(pamg_handle* h, int fine_level) {
+int do_prolong(pamg_handle* h, int fine_level, bool keep_tnew = true) {
   if (fine_level >= (int)h->lev.size()) return fail(h, PAMG_ERR_ARG, "no coarser level to prolong from");
   LevelDev& F = h->lev[fine_level - 1];
   LevelDev& Cc = h->lev[fine_level];
@@ -411,8 +417,12 @@ int do_prolong(pamg_handle* h, int fine_level) {
     a.src = tnew_ptr(Cc); a.dst = F.T[F.cur ^ 1];
     k_prolong_literal<<<grid_for(h, Cc.nelem), TPB, 0, h->stream>>>(a);
   } else {
-    int rc = materialise_tnew(h, F);  // the correction goes to the iterate only
-    if (rc) return rc;
+    if (keep_tnew) {                  // the correction goes to the iterate only: keep tracer%tnew as it was
+      int rc = materialise_tnew(h, F);
+      if (rc) return rc;
+    } else {
+      F.tnew_alias = true;            // inside the V-cycle nothing reads the pre-correction field
+    }
     a.src = Cc.T[Cc.cur]; a.dst = F.T[F.cur];
     k_prolong_p1<<<grid_for(h, F.nelem), TPB, 0, h->stream>>>(a);
   }
@@ -429,12 +439,26 @@ int do_fill(pamg_handle* h, double* p, long long n, double v) {
   return PAMG_OK;
 }
 
+// Jacobi / Richardson sweeps ping-pong between the two T buffers; a cycle that ends on the other buffer would not
+// be replayable as a CUDA graph (pointers are baked in), so the iterate is moved back when the sweep count is odd.
+int normalise_parity(pamg_handle* h, LevelDev& L, int cur0) {
+  if (L.cur == cur0) return PAMG_OK;
+  CK(cudaMemcpyAsync(L.T[L.cur ^ 1], L.T[L.cur], L.ndof * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  L.cur ^= 1;
+  L.tnew_alias = true;
+  return PAMG_OK;
+}
+
 int vcycle_rec(pamg_handle* h, int level, int solver, int nu1, int nu2, int ncoarse) {
   const int Lmax = (int)h->lev.size();
   int rc;
-  if (level == Lmax) return do_smooth(h, level, solver, ncoarse);
-  if ((rc = do_smooth(h, level, solver, nu1))) return rc;
   LevelDev& L = h->lev[level - 1];
+  const int cur0 = L.cur;
+  if (level == Lmax) {
+    if ((rc = do_smooth(h, level, solver, ncoarse))) return rc;
+    return normalise_parity(h, L, cur0);
+  }
+  if ((rc = do_smooth(h, level, solver, nu1))) return rc;
   L.tnew_alias = true;                                   // tnew = tnew_nonlin
   if ((rc = launch_halo(h, level))) return rc;
   if ((rc = do_residual(h, level, nullptr, nullptr, nullptr))) return rc;
@@ -443,11 +467,29 @@ int vcycle_rec(pamg_handle* h, int level, int solver, int nu1, int nu2, int ncoa
   if ((rc = do_fill(h, Cc.T[Cc.cur], Cc.ndof, 0.0))) return rc;
   Cc.tnew_alias = true;
   if ((rc = vcycle_rec(h, level + 1, solver, nu1, nu2, ncoarse))) return rc;
-  if ((rc = do_prolong(h, level))) return rc;
-  return do_smooth(h, level, solver, nu2);
+  if ((rc = do_prolong(h, level, false))) return rc;
+  if ((rc = do_smooth(h, level, solver, nu2))) return rc;
+  return normalise_parity(h, L, cur0);
+}
+
+// one V-cycle followed by the residual norms of level 1 (the copy to pinned memory is queued, not awaited)
+int vcycle_body(pamg_handle* h, int solver, int nu1, int nu2, int ncoarse) {
+  int rc;
+  if ((rc = vcycle_rec(h, 1, solver, nu1, nu2, ncoarse))) return rc;
+  LevelDev& L = h->lev[0];
+  L.tnew_alias = true;
+  if ((rc = launch_halo(h, 1))) return rc;
+  double dummy;
+  const bool cap = h->capturing;
+  h->capturing = true;    // do_residual: queue the read-back only
+  rc = do_residual(h, 1, &dummy, nullptr, nullptr);
+  h->capturing = cap;
+  return rc;
 }
 
 void free_levels(pamg_handle* h) {
+  for (auto& g : h->vc_graphs) cudaGraphExecDestroy(g.exec);
+  h->vc_graphs.clear();
   for (auto& L : h->lev) {
     cudaFree(L.T[0]); cudaFree(L.T[1]); cudaFree(L.told); cudaFree(L.rhs); cudaFree(L.res);
     cudaFree(L.ovl); cudaFree(L.ovl_old); cudaFree(L.pc); cudaFree(L.items);
@@ -514,6 +556,10 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
     else if (e && !strcmp(e, "tma1d")) h->kernel_mode = 1;
     else if (e && !strcmp(e, "stream")) h->kernel_mode = 2;
     else if (e && !strcmp(e, "direct2")) h->kernel_mode = 3;
+    const char* gr = getenv("PAMG_GRAPH");
+    if (gr && gr[0] == '0') h->use_graph = false;
+    const char* g = getenv("PAMG_GS");
+    if (g && !strcmp(g, "direct")) h->gs_tma = false;
   }
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return PAMG_ERR_CUDA; }
   cudaDeviceProp prop;
@@ -756,11 +802,42 @@ int pamg_vcycle_solve(pamg_handle* h, int solver, int nu1, int nu2, int ncoarse,
   if (hist) hist[0] = r0;
   if (cycles) *cycles = 0;
   if (r0 == 0.0) return PAMG_OK;
+  // cycle 1 runs eagerly (it also sets the kernels' attributes); from cycle 2 on the identical launch sequence
+  // (~170 launches, most of them on launch-bound coarse levels) is replayed as one CUDA graph
+  const long long key0 = ((((long long)solver * 64 + nu1) * 64 + nu2) * 64 + ncoarse);
+  const bool graph_ok = h->use_graph && !h->comm && !h->profiling;
   for (int c = 1; c <= max_cycles; ++c) {
-    if ((rc = vcycle_rec(h, 1, solver, nu1, nu2, ncoarse))) return rc;
-    L.tnew_alias = true;
-    if ((rc = launch_halo(h, 1))) return rc;
-    if ((rc = do_residual(h, 1, &r, nullptr, nullptr))) return rc;
+    if (c >= 2 && graph_ok) {
+      long long key = key0;                      // the graph bakes in which of the two T buffers holds the iterate
+      for (auto& Lv : h->lev) key = key * 2 + Lv.cur;
+      pamg_handle::VcGraph* vg = nullptr;
+      for (auto& g : h->vc_graphs) if (g.key == key) vg = &g;
+      if (!vg) {
+        if (h->vc_graphs.size() >= 8) { cudaGraphExecDestroy(h->vc_graphs.front().exec); h->vc_graphs.erase(h->vc_graphs.begin()); }
+        cudaGraph_t graph = nullptr;
+        const long long l0 = h->launches;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        h->capturing = true;
+        rc = vcycle_body(h, solver, nu1, nu2, ncoarse);
+        h->capturing = false;
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return fail(h, PAMG_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+        pamg_handle::VcGraph ng{key, nullptr, h->launches - l0};
+        h->launches = l0;
+        ce = cudaGraphInstantiate(&ng.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return fail(h, PAMG_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+        h->vc_graphs.push_back(ng);
+        vg = &h->vc_graphs.back();
+      }
+      CK(cudaGraphLaunch(vg->exec, h->stream));
+      h->launches += vg->launches;
+    } else {
+      if ((rc = vcycle_body(h, solver, nu1, nu2, ncoarse))) return rc;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    r = std::sqrt(h->out3_host[0]);
     if (hist) hist[c] = r;
     if (cycles) *cycles = c;
     if (r / r0 <= tol) return PAMG_OK;

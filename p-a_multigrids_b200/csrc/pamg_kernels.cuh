@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(TPB, 3) k_element_tma(ElemArgs a) {
     const int k = (int)(g & Cmask);
     child_from_ele0(k, s, p.r, p.ipos, p.len);
     p.up = p.ipos & 1;
-    if (FACE) {
+    if (FACE && !(MODE == MODE_GS && (int)p.up != a.colour)) {
       // vertical neighbour: child above for a down child, child below for an up child (splitting.F90:749-769);
       // up children of row 1 sit on parent face 1 and read the halo strip instead
       const int nb = p.up ? (k - b - 2 + 2 * p.r) : (k + b - 2 * p.r);       // 0-based child index
@@ -551,7 +551,9 @@ __global__ void __launch_bounds__(TPB, 3) k_element_tma(ElemArgs a) {
       }
       const double* bb = sB[st] + tid * 3;
       double o1, o2, o3;
-      if (FACE && MODE != MODE_RICH) {
+      if (MODE == MODE_GS && (int)cur.up != a.colour) {
+        o1 = T1; o2 = T2; o3 = T3;      // other colour: written back unchanged (in-place pass)
+      } else if (FACE && MODE != MODE_RICH) {
         const Folded& F = *reinterpret_cast<const Folded*>(sPC + PC_FOLD + (cur.up ? 0 : 16));
         elem_apply_folded<MODE>(F, sPC + PC_DPEN, bmask, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
       } else {
