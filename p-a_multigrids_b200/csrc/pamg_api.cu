@@ -61,7 +61,10 @@ struct LevelDev {
   int cur = 0;
   bool tnew_alias = true;             // TNEW == TNONLIN logically (no separate copy materialised)
   double *told = nullptr, *rhs = nullptr, *res = nullptr;
-  double *ovl = nullptr, *ovl_old = nullptr;  // (nstrips + nsend) * 3S doubles
+  double* ovlb[2] = {nullptr, nullptr};       // halo strips, double-buffered: (nstrips + nsend) * 3S doubles each
+  int ovl_cur = 0;                            // ovlb[ovl_cur] holds the strips of the current iterate when strips_valid
+  bool strips_valid = false;
+  double* ovl_old = nullptr;                  // told strips (update_overlaps as written only)
   double* pc = nullptr;               // [U][NPC]
   int2* items = nullptr; int nitems = 0;  // work list of the row-streaming kernel (levels with s >= STREAM_MIN_S)
   bool rhs_valid = false;             // level 1: RHS matches TOLD
@@ -90,6 +93,8 @@ struct pamg_handle {
   bool use_graph = true;    // replay the V-cycle as a CUDA graph from the second cycle on (PAMG_GRAPH=0 disables)
   struct VcGraph { long long key; cudaGraphExec_t exec; long long launches; };
   std::vector<VcGraph> vc_graphs;   // a few cached V-cycle graphs (solver / sweep counts / buffer parity)
+  bool fused_halo = false;  // PAMG_FUSED_HALO=1: sweeps write the next sweep's strips themselves (measured slower: the extra work
+                            // of the few children on parent faces delays the per-tile barrier; profiles/README.md)
   bool gs_tma = true;   // coloured GS pass through the TMA tile kernel (PAMG_GS=direct selects the direct kernel)
   // per-kernel timing (element kernels only)
   bool profiling = false;
@@ -137,10 +142,10 @@ double* field_ptr(pamg_handle* h, int field, int level, bool for_write, int* rc)
   LevelDev& L = h->lev[level - 1];
   switch (field) {
     case PAMG_TNEW:
-      if (for_write) { *rc = materialise_tnew(h, L); return L.T[L.cur ^ 1]; }
+      if (for_write) { *rc = materialise_tnew(h, L); L.strips_valid = false; return L.T[L.cur ^ 1]; }
       return tnew_ptr(L);
     case PAMG_TNONLIN:
-      if (for_write) *rc = materialise_tnew(h, L);
+      if (for_write) { *rc = materialise_tnew(h, L); L.strips_valid = false; }
       return L.T[L.cur];
     case PAMG_TOLD: if (for_write) L.rhs_valid = false; return L.told;
     case PAMG_RHS: if (for_write) L.rhs_valid = true; return L.rhs;
@@ -242,36 +247,49 @@ void parent_coefficients(const pamg_params& p, const double* Xall, const int32_t
   for (int i = PC_WB + 24; i < NPC; ++i) pc[i] = 0.0;
 }
 
-int launch_halo(pamg_handle* h, int level);
+int launch_halo(pamg_handle* h, int level, int what = 0);
 
 // exchange of the cut-face strips (one process per GPU): the send slots follow the local strips in the
 // strip space; the receive range of a peer is a contiguous range of my own strips (pamg_plan.cpp)
-int exchange_halo(pamg_handle* h, LevelDev& L) {
+int exchange_halo(pamg_handle* h, LevelDev& L, double* ovl) {
   if (h->plan.peers.empty()) return PAMG_OK;
   if (!h->comm) return fail(h, PAMG_ERR_STATE, "partitioned mesh but pamg_comm_init was not called");
   const size_t S3 = (size_t)3 * L.S;
   g_nccl.GroupStart();
   for (const auto& pr : h->plan.peers) {
     const size_t n = (size_t)pr.nfaces * S3;
-    g_nccl.Send(L.ovl + ((size_t)h->plan.nstrips + pr.send_begin) * S3, n, ncclFloat64, pr.part, h->comm, h->stream);
-    g_nccl.Recv(L.ovl + (size_t)pr.strip_begin * S3, n, ncclFloat64, pr.part, h->comm, h->stream);
+    g_nccl.Send(ovl + ((size_t)h->plan.nstrips + pr.send_begin) * S3, n, ncclFloat64, pr.part, h->comm, h->stream);
+    g_nccl.Recv(ovl + (size_t)pr.strip_begin * S3, n, ncclFloat64, pr.part, h->comm, h->stream);
   }
   if (g_nccl.GroupEnd() != ncclSuccess) return fail(h, PAMG_ERR_CUDA, "ncclGroupEnd failed in halo exchange");
   return PAMG_OK;
 }
 
-int launch_halo(pamg_handle* h, int level) {
+// what: 0 = update_overlaps as written (every face, tnew and told strips); 1 = Dirichlet faces only (static data,
+// written once per level into both strip buffers); 3 = every face between parents.  The sweeps themselves refresh
+// the strips of the next sweep (strips_write in the kernels), so this kernel only runs when the field was changed
+// by something else than a sweep (upload, fill, prolongation) or through the pamg_update_overlaps entry.
+int launch_halo(pamg_handle* h, int level, int what) {
   LevelDev& L = h->lev[level - 1];
   HaloArgs a;
-  a.tnew = tnew_ptr(L); a.told = L.told; a.ovl = L.ovl; a.ovl_old = L.ovl_old; a.xg = h->xg;
+  a.tnew = tnew_ptr(L); a.told = L.told; a.ovl = L.ovlb[L.ovl_cur]; a.ovl_old = L.ovl_old; a.xg = h->xg;
   a.dst_strip = h->dst_strip; a.rev = h->rev; a.strip_of = h->strip_of;
   a.bc_scale = (h->p.coarse_bc_zero && level > 1) ? 0.0 : 1.0;
-  a.U = h->U; a.s = L.s; a.with_old = 1;
+  a.U = h->U; a.s = L.s; a.with_old = (what == 0) ? 1 : 0; a.what = what; a.nstrips = h->plan.nstrips;
   const long long n = (long long)h->U * 3 * L.S;
   k_halo<<<grid_for(h, n), TPB, 0, h->stream>>>(a);
   h->launches++;
   CK(cudaGetLastError());
-  return exchange_halo(h, L);
+  if (what == 1) return PAMG_OK;
+  L.strips_valid = true;
+  return exchange_halo(h, L, L.ovlb[L.ovl_cur]);
+}
+
+// strips of the current iterate, refreshed only if something other than a sweep touched the field
+int ensure_strips(pamg_handle* h, int level) {
+  LevelDev& L = h->lev[level - 1];
+  if (L.strips_valid || !h->p.face_terms) return PAMG_OK;
+  return launch_halo(h, level, 3);
 }
 
 int launch_build_rhs(pamg_handle* h) {
@@ -287,9 +305,10 @@ int launch_build_rhs(pamg_handle* h) {
 }
 
 template <int MODE>
-int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout, int colour, int grid) {
+int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout, int colour, int grid, bool write_strips = false) {
   ElemArgs a;
-  a.Tin = Tin; a.Tout = Tout; a.rhs = L.rhs; a.ovl = L.ovl; a.pc = L.pc; a.strip_of = h->strip_of; a.hmap = h->hmap;
+  a.Tin = Tin; a.Tout = Tout; a.rhs = L.rhs; a.ovl = L.ovlb[L.ovl_cur]; a.pc = L.pc; a.strip_of = h->strip_of; a.hmap = h->hmap;
+  a.ovl_next = (write_strips && h->p.face_terms) ? L.ovlb[L.ovl_cur ^ 1] : nullptr; a.dst_strip = h->dst_strip; a.rev = h->rev;
   a.partial = h->partial; a.omega = h->p.omega; a.rsign = (double)h->p.residual_sign; a.nelem = L.nelem; a.s = L.s;
   a.colour = colour;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("PAMG_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
@@ -337,14 +356,18 @@ int do_smooth(pamg_handle* h, int level, int solver, int nsweeps) {
   LevelDev& L = h->lev[level - 1];
   if (level == 1 && !L.rhs_valid) { int rc = launch_build_rhs(h); if (rc) return rc; }
   const int grid = grid_for(h, L.nelem);
+  // optional (PAMG_FUSED_HALO=1): the default kernel families write the next sweep's strips themselves; otherwise
+  // one k_halo launch per sweep refreshes the strips of the faces between parents (Dirichlet strips are static)
+  const bool fused = h->fused_halo && (h->kernel_mode == 1 || h->kernel_mode == 3);
   for (int sw = 0; sw < nsweeps; ++sw) {
     // tnew <- tnew_nonlin (:550) is the buffer swap below for Jacobi; halo from it (:555)
     L.tnew_alias = true;
-    int rc = launch_halo(h, level);
+    if (!fused) L.strips_valid = false;
+    int rc = ensure_strips(h, level);
     if (rc) return rc;
     if (solver == 1 || solver == 2) {
-      rc = (solver == 1) ? launch_element<MODE_JACOBI>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid)
-                         : launch_element<MODE_RICH>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid);
+      rc = (solver == 1) ? launch_element<MODE_JACOBI>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid, fused)
+                         : launch_element<MODE_RICH>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid, fused);
       if (rc) return rc;
       L.cur ^= 1;
       L.tnew_alias = false;  // the old buffer now holds the start-of-sweep field = tracer%tnew
@@ -352,12 +375,20 @@ int do_smooth(pamg_handle* h, int level, int solver, int nsweeps) {
       // two-colour ordering of the reference's Gauss-Seidel sweep: all down children, then all up children;
       // values across parent faces stay lagged through the halo strips exactly as at :647-655.
       if (sw == nsweeps - 1 && h->p.keep_tnew_gs) { rc = materialise_tnew(h, L); if (rc) return rc; }  // keep tracer%tnew observable
-      rc = launch_element<MODE_GS>(h, L, L.T[L.cur], L.T[L.cur], 0, grid);
+      rc = launch_element<MODE_GS>(h, L, L.T[L.cur], L.T[L.cur], 0, grid, false);
       if (rc) return rc;
-      rc = launch_element<MODE_GS>(h, L, L.T[L.cur], L.T[L.cur], 1, grid);
+      rc = launch_element<MODE_GS>(h, L, L.T[L.cur], L.T[L.cur], 1, grid, fused);   // all children on parent faces are "up"
       if (rc) return rc;
     } else {
       return fail(h, PAMG_ERR_ARG, "solver must be 1 (Jacobi), 2 (Richardson) or 3 (Gauss-Seidel)");
+    }
+    if (fused && h->p.face_terms) {
+      L.ovl_cur ^= 1;                 // the sweep wrote the strips of the new iterate (incl. the send slots)
+      rc = exchange_halo(h, L, L.ovlb[L.ovl_cur]);
+      if (rc) return rc;
+      L.strips_valid = true;
+    } else {
+      L.strips_valid = false;
     }
   }
   return PAMG_OK;
@@ -424,6 +455,7 @@ int do_prolong(pamg_handle* h, int fine_level, bool keep_tnew = true) {
       F.tnew_alias = true;            // inside the V-cycle nothing reads the pre-correction field
     }
     a.src = Cc.T[Cc.cur]; a.dst = F.T[F.cur];
+    F.strips_valid = false;           // the iterate changes outside a sweep
     k_prolong_p1<<<grid_for(h, F.nelem), TPB, 0, h->stream>>>(a);
   }
   h->launches++;
@@ -460,12 +492,13 @@ int vcycle_rec(pamg_handle* h, int level, int solver, int nu1, int nu2, int ncoa
   }
   if ((rc = do_smooth(h, level, solver, nu1))) return rc;
   L.tnew_alias = true;                                   // tnew = tnew_nonlin
-  if ((rc = launch_halo(h, level))) return rc;
+  if ((rc = ensure_strips(h, level))) return rc;
   if ((rc = do_residual(h, level, nullptr, nullptr, nullptr))) return rc;
   if ((rc = do_restrict(h, level))) return rc;
   LevelDev& Cc = h->lev[level];
   if ((rc = do_fill(h, Cc.T[Cc.cur], Cc.ndof, 0.0))) return rc;
   Cc.tnew_alias = true;
+  Cc.strips_valid = false;
   if ((rc = vcycle_rec(h, level + 1, solver, nu1, nu2, ncoarse))) return rc;
   if ((rc = do_prolong(h, level, false))) return rc;
   if ((rc = do_smooth(h, level, solver, nu2))) return rc;
@@ -478,7 +511,7 @@ int vcycle_body(pamg_handle* h, int solver, int nu1, int nu2, int ncoarse) {
   if ((rc = vcycle_rec(h, 1, solver, nu1, nu2, ncoarse))) return rc;
   LevelDev& L = h->lev[0];
   L.tnew_alias = true;
-  if ((rc = launch_halo(h, 1))) return rc;
+  if ((rc = ensure_strips(h, 1))) return rc;
   double dummy;
   const bool cap = h->capturing;
   h->capturing = true;    // do_residual: queue the read-back only
@@ -492,7 +525,7 @@ void free_levels(pamg_handle* h) {
   h->vc_graphs.clear();
   for (auto& L : h->lev) {
     cudaFree(L.T[0]); cudaFree(L.T[1]); cudaFree(L.told); cudaFree(L.rhs); cudaFree(L.res);
-    cudaFree(L.ovl); cudaFree(L.ovl_old); cudaFree(L.pc); cudaFree(L.items);
+    cudaFree(L.ovlb[0]); cudaFree(L.ovlb[1]); cudaFree(L.ovl_old); cudaFree(L.pc); cudaFree(L.items);
   }
   h->lev.clear();
   cudaFree(h->xg); cudaFree(h->strip_of); cudaFree(h->dst_strip); cudaFree(h->rev); cudaFree(h->hmap);
@@ -558,6 +591,8 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
     else if (e && !strcmp(e, "direct2")) h->kernel_mode = 3;
     const char* gr = getenv("PAMG_GRAPH");
     if (gr && gr[0] == '0') h->use_graph = false;
+    const char* fh = getenv("PAMG_FUSED_HALO");
+    if (fh && fh[0] == '1') h->fused_halo = true;
     const char* g = getenv("PAMG_GS");
     if (g && !strcmp(g, "direct")) h->gs_tma = false;
   }
@@ -627,8 +662,10 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
     CK(cudaMemsetAsync(L.told, 0, fb, h->stream)); CK(cudaMemsetAsync(L.rhs, 0, fb, h->stream));
     CK(cudaMemsetAsync(L.res, 0, fb, h->stream));
     const size_t ob = (size_t)(h->plan.nstrips + h->plan.nsend) * 3 * L.S * sizeof(double);
-    CK(cudaMalloc(&L.ovl, ob)); CK(cudaMalloc(&L.ovl_old, ob));
-    CK(cudaMemsetAsync(L.ovl, 0, ob, h->stream)); CK(cudaMemsetAsync(L.ovl_old, 0, ob, h->stream));  // :207
+    CK(cudaMalloc(&L.ovlb[0], ob)); CK(cudaMalloc(&L.ovlb[1], ob)); CK(cudaMalloc(&L.ovl_old, ob));
+    CK(cudaMemsetAsync(L.ovlb[0], 0, ob, h->stream)); CK(cudaMemsetAsync(L.ovlb[1], 0, ob, h->stream));
+    CK(cudaMemsetAsync(L.ovl_old, 0, ob, h->stream));  // :207
+    L.ovl_cur = 0; L.strips_valid = false;
     for (int u = 0; u < U; ++u) parent_coefficients(h->p, X, neig, first + u, L.s, &pc[(size_t)u * NPC]);
     CK(cudaMalloc(&L.pc, pc.size() * sizeof(double)));
     CK(cudaMemcpy(L.pc, pc.data(), pc.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -659,6 +696,14 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
   }
   CK(cudaMalloc(&h->counters, 2 * sizeof(int)));
   CK(cudaMemset(h->counters, 0, 2 * sizeof(int)));
+  // Dirichlet data sin(x+y) on domain-boundary faces never changes: fill those strips once per level
+  for (int il = 1; il <= h->p.multi_levels; ++il)
+    for (int bsel = 0; bsel < 2; ++bsel) {
+      h->lev[il - 1].ovl_cur = bsel;
+      int rc2 = launch_halo(h, il, 1);
+      if (rc2) return rc2;
+    }
+  for (auto& Lv : h->lev) Lv.ovl_cur = 0;
   h->npartial = h->nsm * 8;
   CK(cudaMalloc(&h->partial, (size_t)h->npartial * 3 * sizeof(double)));
   CK(cudaStreamSynchronize(h->stream));
@@ -714,7 +759,7 @@ int pamg_copy_field(pamg_handle* h, int level, int dst_field, int src_field) {
   if (dst_field == src_field) return PAMG_OK;
   if (dst_field == PAMG_TNEW && src_field == PAMG_TNONLIN) { L.tnew_alias = true; return PAMG_OK; }      // :550
   if (dst_field == PAMG_TNONLIN && src_field == PAMG_TNEW) {                                             // :327
-    if (!L.tnew_alias) { L.cur ^= 1; L.tnew_alias = true; }
+    if (!L.tnew_alias) { L.cur ^= 1; L.tnew_alias = true; L.strips_valid = false; }
     return PAMG_OK;
   }
   int rc;
@@ -732,7 +777,7 @@ int pamg_download_overlap(pamg_handle* h, int level, int old, double* host) {
   LevelDev& L = h->lev[level - 1];
   const size_t S3 = (size_t)3 * L.S;
   std::vector<double> tmp((size_t)h->plan.nstrips * S3);
-  CK(cudaMemcpyAsync(tmp.data(), old ? L.ovl_old : L.ovl, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(tmp.data(), old ? L.ovl_old : L.ovlb[L.ovl_cur], tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   for (int lf = 0; lf < h->U * 3; ++lf)
     std::memcpy(host + (size_t)lf * S3, &tmp[(size_t)h->plan.strip_of[lf] * S3], S3 * sizeof(double));
@@ -796,7 +841,8 @@ int pamg_vcycle_solve(pamg_handle* h, int solver, int nu1, int nu2, int ncoarse,
   LevelDev& L = h->lev[0];
   int rc;
   L.tnew_alias = true;
-  if ((rc = launch_halo(h, 1))) return rc;
+  L.strips_valid = false;
+  if ((rc = ensure_strips(h, 1))) return rc;
   double r0 = 0, r = 0;
   if ((rc = do_residual(h, 1, &r0, nullptr, nullptr))) return rc;
   if (hist) hist[0] = r0;
@@ -881,6 +927,7 @@ int pamg_timestep_host(pamg_handle* h, const double* tnew_in, double* tnew_out, 
   // told = tnew ; tnew_nonlin = tnew (transport_tri_semi.F90:316-317)
   CK(cudaMemcpyAsync(L.T[L.cur], tnew_in, bytes, cudaMemcpyHostToDevice, h->stream));
   L.tnew_alias = true;
+  L.strips_valid = false;
   CK(cudaMemcpyAsync(L.told, L.T[L.cur], bytes, cudaMemcpyDeviceToDevice, h->stream));
   L.rhs_valid = false;
   std::vector<double> hist((size_t)max_cycles + 2, 0.0);

@@ -36,6 +36,9 @@ struct ElemArgs {
   const double* pc;       // [U][NPC]
   const int32_t* strip_of;  // [U*3]
   const int32_t* hmap;      // [U*3]
+  double* ovl_next;         // strips of the NEXT sweep, written by the children on parent faces (nullptr: do not write)
+  const int32_t* dst_strip; // [U*3] strip (or send slot) my boundary children are copied to, -1 = domain boundary
+  const int32_t* rev;       // [U*3] slot reversal flag
   double* partial;        // residual: [nblocks][3] = sum r^2, max |r|, max r
   double omega;
   double rsign;
@@ -141,6 +144,37 @@ __device__ __forceinline__ void halo_pair(const ElemArgs& a, int u, int mf, int 
   const int hm = __ldg(a.hmap + u * 3 + mf);
   const double* e = a.ovl + ((size_t)__ldg(a.strip_of + u * 3 + mf) * S + slot0) * 3;
   va = __ldg(e + (hm & 3)); vb = __ldg(e + (hm >> 2));
+}
+
+// update_overlaps (splitting.F90:1255-1391) fused into the sweep: a child on parent face mf copies its NEW nodal
+// values into the neighbour parent's strip of the next sweep (double-buffered), so no halo kernel runs between
+// sweeps.  bmask has bit 0/1/2 set for child faces 1/2/3 on the parent boundary.
+__device__ __forceinline__ void strips_write(const ElemArgs& a, int u, int bmask, int r, int ipos, int S, double o1,
+                                             double o2, double o3) {
+  if (bmask & 1) {                      // child face 1 on parent side 1, position ipos/2+1
+    const int d = __ldg(a.dst_strip + u * 3 + 0);
+    if (d >= 0) {
+      const int p = ipos >> 1, slot = __ldg(a.rev + u * 3 + 0) ? (S - 1 - p) : p;
+      double* e = a.ovl_next + ((size_t)d * S + slot) * 3;
+      e[0] = o1; e[1] = o2; e[2] = o3;
+    }
+  }
+  if (bmask & 2) {                      // child face 2 on parent side 3, position irow
+    const int d = __ldg(a.dst_strip + u * 3 + 2);
+    if (d >= 0) {
+      const int slot = __ldg(a.rev + u * 3 + 2) ? (S - r) : (r - 1);
+      double* e = a.ovl_next + ((size_t)d * S + slot) * 3;
+      e[0] = o1; e[1] = o2; e[2] = o3;
+    }
+  }
+  if (bmask & 4) {                      // child face 3 on parent side 2, position irow
+    const int d = __ldg(a.dst_strip + u * 3 + 1);
+    if (d >= 0) {
+      const int slot = __ldg(a.rev + u * 3 + 1) ? (S - r) : (r - 1);
+      double* e = a.ovl_next + ((size_t)d * S + slot) * 3;
+      e[0] = o1; e[1] = o2; e[2] = o3;
+    }
+  }
 }
 
 // same with the strip index and node map already at hand (kept in shared memory by the tile kernel)
@@ -433,7 +467,6 @@ __global__ void __launch_bounds__(TPB, 3) k_element_tma(ElemArgs a) {
   double (*sO)[3 * TPB] = reinterpret_cast<double (*)[3 * TPB]>(dsm + sizeof(double) * NSTAGE * (TMA_T_DOUBLES + 3 * TPB));
   uint64_t* bar = reinterpret_cast<uint64_t*>(dsm + sizeof(double) * (NSTAGE * (TMA_T_DOUBLES + 3 * TPB) + 2 * 3 * TPB));
   __shared__ __align__(16) double sPC[NPC];
-  __shared__ int sStrip[3], sHmap[3];   // strip index / node map of the three faces of the current parent
   const ParentRegs& P = *reinterpret_cast<const ParentRegs*>(sPC);
   const int s = a.s, twos = 2 * s, b = 2 << s, S = 1 << s;
   const long long Cmask = (1ll << twos) - 1;
@@ -484,17 +517,6 @@ __global__ void __launch_bounds__(TPB, 3) k_element_tma(ElemArgs a) {
         const unsigned o1 = ((unsigned)(g - k) + (unsigned)nb) * 3u;         // offsets in doubles fit 32 bits
         p.va = __ldg(a.Tin + o1 + 2); p.vb = __ldg(a.Tin + o1);
       }
-      // children at a row end read a halo strip entry one tile later: pull it into L1 now, so that the
-      // single lane that needs it does not hold up its warp (and the CTA barrier) for a chain of L2 misses
-      if (p.up && (p.ipos == 1 || p.ipos == p.len)) {
-        const int mf = (p.ipos == 1) ? 2 : 1;
-        const double* e = halo_entry(a, __ldg(a.strip_of + p.u * 3 + mf), p.r - 1, S);
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(e));
-        if (p.ipos == 1 && p.len == 1) {
-          const double* e2 = halo_entry(a, __ldg(a.strip_of + p.u * 3 + 1), p.r - 1, S);
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(e2));
-        }
-      }
     }
   };
   Prep cur, nxt;
@@ -513,8 +535,6 @@ __global__ void __launch_bounds__(TPB, 3) k_element_tma(ElemArgs a) {
       if (u_tile != u_loaded) {
         __syncthreads();
         if (tid < NPC) sPC[tid] = __ldg(a.pc + (size_t)u_tile * NPC + tid);
-        else if (tid < NPC + 3) sStrip[tid - NPC] = __ldg(a.strip_of + u_tile * 3 + (tid - NPC));
-        else if (tid < NPC + 6) sHmap[tid - NPC - 3] = __ldg(a.hmap + u_tile * 3 + (tid - NPC - 3));
         __syncthreads();
         u_loaded = u_tile;
       }
@@ -537,22 +557,15 @@ __global__ void __launch_bounds__(TPB, 3) k_element_tma(ElemArgs a) {
         if (cur.up && (cur.r == 1 || cur.ipos == 1 || cur.ipos == cur.len)) {   // child on a parent face (rare)
           interior = false;
           if (cur.r == 1) { fi.pen1 = P.px1; bmask |= 1; }
-          if (cur.ipos == 1) {
-            const double* e = halo_entry(a, sStrip[2], cur.r - 1, S);
-            const int hm = sHmap[2];
-            fi.n2a = __ldg(e + (hm & 3)); fi.n2b = __ldg(e + (hm >> 2)); fi.pen2 = P.px2; bmask |= 2;
-          }
-          if (cur.ipos == cur.len) {
-            const double* e = halo_entry(a, sStrip[1], cur.r - 1, S);
-            const int hm = sHmap[1];
-            fi.n3a = __ldg(e + (hm & 3)); fi.n3b = __ldg(e + (hm >> 2)); fi.pen3 = P.px3; bmask |= 4;
-          }
+          if (cur.ipos == 1) { halo_pair(a, cur.u, 2, cur.r - 1, S, fi.n2a, fi.n2b); fi.pen2 = P.px2; bmask |= 2; }
+          if (cur.ipos == cur.len) { halo_pair(a, cur.u, 1, cur.r - 1, S, fi.n3a, fi.n3b); fi.pen3 = P.px3; bmask |= 4; }
         }
       }
       const double* bb = sB[st] + tid * 3;
       double o1, o2, o3;
       if (MODE == MODE_GS && (int)cur.up != a.colour) {
         o1 = T1; o2 = T2; o3 = T3;      // other colour: written back unchanged (in-place pass)
+        bmask = 0;
       } else if (FACE && MODE != MODE_RICH) {
         const Folded& F = *reinterpret_cast<const Folded*>(sPC + PC_FOLD + (cur.up ? 0 : 16));
         elem_apply_folded<MODE>(F, sPC + PC_DPEN, bmask, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
@@ -560,6 +573,7 @@ __global__ void __launch_bounds__(TPB, 3) k_element_tma(ElemArgs a) {
         elem_apply_regs<MODE, FACE>(P, cur.up, interior, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.omega, a.rsign, o1, o2, o3);
       }
       so[tid * 3] = o1; so[tid * 3 + 1] = o2; so[tid * 3 + 2] = o3;
+      if (MODE != MODE_RESID && bmask && a.ovl_next) strips_write(a, cur.u, bmask, cur.r, cur.ipos, S, o1, o2, o3);
       if (MODE == MODE_RESID) {
         acc_sum += o1 * o1 + o2 * o2 + o3 * o3;
         acc_abs = fmax(acc_abs, fmax(fabs(o1), fmax(fabs(o2), fabs(o3))));
@@ -636,6 +650,7 @@ __global__ void __launch_bounds__(TPB) k_element_direct2(ElemArgs a) {
       elem_apply_regs<MODE, FACE>(P, up, interior, T1, T2, T3, fi, b1, b2, b3, a.omega, a.rsign, o1v, o2v, o3v);
     }
     a.Tout[base] = o1v; a.Tout[base + 1] = o2v; a.Tout[base + 2] = o3v;
+    if (MODE != MODE_RESID && bmask && a.ovl_next) strips_write(a, u, bmask, r, ipos, S, o1v, o2v, o3v);
     if (MODE == MODE_RESID) {
       acc_sum += o1v * o1v + o2v * o2v + o3v * o3v;
       acc_abs = fmax(acc_abs, fmax(fabs(o1v), fmax(fabs(o2v), fabs(o3v))));
@@ -676,6 +691,9 @@ struct HaloArgs {
   const int32_t* dst_strip; const int32_t* rev; const int32_t* strip_of;
   double bc_scale;
   int U, s, with_old;
+  int what;   // 0 everything (update_overlaps as written); 1 Dirichlet faces only; 2 faces cut by the GPU partition only;
+              // 3 all faces between parents (no Dirichlet data)
+  int nstrips;
 };
 
 __device__ __forceinline__ void child_nodes(const double* __restrict__ xg, int s, int r, int ipos, double x[3][2]) {
@@ -710,6 +728,9 @@ __global__ void __launch_bounds__(TPB) k_halo(HaloArgs a) {
     const int ele = 1 + (r - 1) * (b + 1 - r) + ipos - 1;
     const int dst = __ldg(a.dst_strip + lf);
     const size_t S3 = (size_t)3 * S;
+    if (a.what == 1 && dst >= 0) continue;
+    if (a.what == 2 && dst < a.nstrips) continue;
+    if (a.what == 3 && dst < 0) continue;
     if (dst < 0) {
       // Dirichlet data sin(x+y) at the two face nodes (:1246-1252,1287-1293,1344-1350)
       double x[3][2];

@@ -1,0 +1,115 @@
+"""Full-size checks (BASELINE configs c4 = 4^11 and c5 = 4^12 elements) through size-independent properties:
+the oracle cannot run these sizes in seconds, so parity is carried by (i) affinity of the sweep, (ii) agreement of
+the three independently written kernel families on the same input, (iii) restriction/prolongation identities and
+(iv) mesh-independent V-cycle convergence with the cycle count the oracle measures on small meshes."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, rel_l2
+from pamg_pkg import pamg
+
+pytestmark = pytest.mark.gpu
+
+
+def big_solver(n, **kw):
+    mesh = pamg.Mesh.synthetic(4, 1)           # 256 parents
+    p = pamg.default_params(n_split=n, multi_levels=n, u_x=0.9, u_y=0.3, **kw)
+    return pamg.SemiImplicitIterative(p, mesh), mesh
+
+
+def rnd(shape, seed):
+    return np.random.Generator(np.random.MT19937(seed)).random(shape)
+
+
+@pytest.mark.parametrize("n", [7, 8])
+def test_sweep_is_affine_and_kernel_families_agree(n):
+    g, _ = big_solver(n)
+    shape = g.shape(1)
+    T1, T2, Told = rnd(shape, 1), rnd(shape, 2), rnd(shape, 3)
+    g.upload(pamg.TOLD, 1, Told)
+
+    def sweep(T, solver):
+        g.upload(pamg.TNONLIN, 1, T)
+        g.smoother(1, solver, 1)
+        return g.download(pamg.TNONLIN, 1)
+
+    for solver in (pamg.JACOBI, pamg.GAUSS_SEIDEL):
+        a = 0.3
+        s1, s2, s12 = sweep(T1, solver), sweep(T2, solver), sweep(a * T1 + (1 - a) * T2, solver)
+        assert rel_l2(s12, a * s1 + (1 - a) * s2) <= 1e-13          # S(aT1+(1-a)T2) = aS(T1)+(1-a)S(T2)
+    ref = sweep(T1, pamg.JACOBI)
+    g.close()
+    # the same sweep through the other kernel families (separate processes: the choice is read at handle creation)
+    code = ("import sys,numpy as np;sys.path.insert(0,'%s');from pamg_pkg import pamg;"
+            "m=pamg.Mesh.synthetic(4,1);p=pamg.default_params(n_split=%d,multi_levels=%d,u_x=0.9,u_y=0.3);"
+            "g=pamg.SemiImplicitIterative(p,m);r=lambda s:np.random.Generator(np.random.MT19937(s)).random(g.shape(1));"
+            "g.upload(pamg.TOLD,1,r(3));g.upload(pamg.TNONLIN,1,r(1));g.smoother(1,pamg.JACOBI,1);"
+            "np.save(sys.argv[1],g.download(pamg.TNONLIN,1))") % (os.path.join(ROOT, "tests"), n, n)
+    for fam in ("direct", "direct2", "stream"):
+        out = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"pamg_{fam}_{n}.npy")
+        r = subprocess.run([sys.executable, "-c", code, out], env=dict(os.environ, PAMG_KERNEL=fam),
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        other = np.load(out)
+        os.unlink(out)
+        assert rel_l2(other, ref) <= 1e-13, fam
+
+
+def test_transfer_identities_full_size():
+    g, _ = big_solver(7)
+    # restriction of a constant residual: every coarse node collects 1 + 6 * 1/2 = 4 fine contributions (P^T 1)
+    g.fill(pamg.RES, 1, 1.0)
+    g.restrictor(1)
+    rc = g.download(pamg.RHS, 2)
+    assert np.all(rc == 4.0)
+    # prolongation of a constant correction adds that constant everywhere (P 1 = 1)
+    g.fill(pamg.TNONLIN, 1, 2.0); g.fill(pamg.TNONLIN, 2, 0.5)
+    g.prolongator(1)
+    assert np.all(g.download(pamg.TNONLIN, 1) == 2.5)
+    # <P c, r> = <c, P^T r> on random fields
+    c, r = rnd(g.shape(2), 5), rnd(g.shape(1), 6)
+    g.fill(pamg.TNONLIN, 1, 0.0); g.upload(pamg.TNONLIN, 2, c); g.prolongator(1)
+    Pc = g.download(pamg.TNONLIN, 1)
+    g.upload(pamg.RES, 1, r); g.restrictor(1)
+    Ptr = g.download(pamg.RHS, 2)
+    lhs, rhs = float(np.sum(Pc * r)), float(np.sum(c * Ptr))
+    assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
+
+
+@pytest.mark.parametrize("n,solver,expect", [(7, pamg.GAUSS_SEIDEL, 8), (8, pamg.GAUSS_SEIDEL, 8), (8, pamg.JACOBI, 14)])
+def test_vcycle_converges_mesh_independently(n, solver, expect):
+    """16.7M elements (c5) and 4.2M (c4): 1e-8 in the same number of cycles (+-2) as the small oracle runs."""
+    g, _ = big_solver(n)
+    cyc, hist = g.vcycle_solve(solver=solver, nu1=4, nu2=4, ncoarse=15, max_cycles=40, tol=1e-8)
+    assert hist[-1] / hist[0] <= 1e-8
+    assert abs(cyc - expect) <= 2
+    rates = hist[1:] / hist[:-1]
+    assert np.all(rates < 0.6)
+    # the converged field is a fixed point of the smoother: one more sweep changes it by <= 1e-8 relative
+    before = g.download(pamg.TNONLIN, 1)
+    g.smoother(1, solver, 1)
+    after = g.download(pamg.TNONLIN, 1)
+    assert rel_l2(after, before) <= 1e-7
+
+
+def test_manufactured_solution_error_is_bounded():
+    """get_error (transport_tri_semi.F90:531-540): |T - sin(x+y)| of the steady solve stays at the level the oracle
+    measures for this (penalty-only) discretisation, DESIGN.md section 1."""
+    import oracle_api as orc
+    mesh = pamg.Mesh.synthetic(1, 2)
+    n = 5
+    p = pamg.default_params(n_split=n, multi_levels=n, dt=1e6)
+    g = pamg.SemiImplicitIterative(p, mesh)
+    cyc, hist = g.vcycle_solve(solver=pamg.GAUSS_SEIDEL, ncoarse=30, max_cycles=80, tol=1e-10)
+    assert hist[-1] / hist[0] <= 1e-10
+    T = g.download(pamg.TNONLIN, 1)
+    x = np.zeros((3, 2)); err = 0.0
+    for u in range(mesh.U):
+        for e in range(1, 4 ** n + 1, 7):
+            orc.lib().orc_get_splitting(np.ascontiguousarray(mesh.X[u]), n, e, x)
+            err = max(err, float(np.abs(T[u, e - 1] - np.sin(x[:, 0] + x[:, 1])).max()))
+    assert err < 0.2
