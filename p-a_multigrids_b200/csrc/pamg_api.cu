@@ -93,6 +93,7 @@ struct pamg_handle {
   bool use_graph = true;    // replay the V-cycle as a CUDA graph from the second cycle on (PAMG_GRAPH=0 disables)
   struct VcGraph { long long key; cudaGraphExec_t exec; long long launches; };
   std::vector<VcGraph> vc_graphs;   // a few cached V-cycle graphs (solver / sweep counts / buffer parity)
+  bool split_boundary = false;  // PAMG_SPLIT=1: tile kernel + k_boundary_fix for the children on parent faces (measured: no gain for Jacobi)
   bool fused_halo = false;  // PAMG_FUSED_HALO=1: sweeps write the next sweep's strips themselves (measured slower: the extra work
                             // of the few children on parent faces delays the per-tile barrier; profiles/README.md)
   bool gs_tma = true;   // coloured GS pass through the TMA tile kernel (PAMG_GS=direct selects the direct kernel)
@@ -311,6 +312,7 @@ int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout,
   a.ovl_next = (write_strips && h->p.face_terms) ? L.ovlb[L.ovl_cur ^ 1] : nullptr; a.dst_strip = h->dst_strip; a.rev = h->rev;
   a.partial = h->partial; a.omega = h->p.omega; a.rsign = (double)h->p.residual_sign; a.nelem = L.nelem; a.s = L.s;
   a.colour = colour;
+  a.split_boundary = 0; a.partial_off = 0;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("PAMG_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
   const bool prof = h->profiling && h->pev_used + 2 <= (int)h->pev.size();
   if (prof) CK(cudaEventRecord(h->pev[h->pev_used], h->stream));
@@ -334,8 +336,20 @@ int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout,
       if (resident < 1) resident = 1;
     }
     const int tgrid = (int)std::max(1ll, std::min((L.nelem + TPB - 1) / TPB, (long long)h->nsm * resident));
+    const bool split = h->split_boundary && h->p.face_terms;
+    a.split_boundary = split ? 1 : 0;
     kern<<<tgrid, TPB, TMA_SMEM_BYTES, h->stream>>>(a);
-    if (MODE == MODE_RESID) h->last_partials = tgrid;
+    int fgrid = 0;
+    if (split && !(MODE == MODE_GS && colour == 0)) {     // every child on a parent face is an "up" child
+      // children on parent faces: separate small launch (their halo look-ups would stall whole tiles)
+      h->launches++;
+      CK(cudaGetLastError());
+      ElemArgs f = a;
+      f.split_boundary = 0; f.partial_off = tgrid;
+      fgrid = grid_for(h, (long long)h->U * 3 * L.S);
+      k_boundary_fix<MODE><<<fgrid, TPB, 0, h->stream>>>(f, h->U);
+    }
+    if (MODE == MODE_RESID) h->last_partials = tgrid + fgrid;
   } else if (h->kernel_mode != 0) {
     // branch-free direct kernel (all loads of a child in flight at once); also the coloured GS pass
     if (MODE == MODE_RESID) h->last_partials = grid;
@@ -398,7 +412,7 @@ int do_residual(pamg_handle* h, int level, double* l2, double* linf, double* sma
   LevelDev& L = h->lev[level - 1];
   if (level == 1 && !L.rhs_valid) { int rc = launch_build_rhs(h); if (rc) return rc; }
   const int grid = grid_for(h, L.nelem);
-  if (grid > h->npartial) return fail(h, PAMG_ERR_STATE, "partial buffer too small");
+  if (2 * grid > h->npartial) return fail(h, PAMG_ERR_STATE, "partial buffer too small");
   int rc = launch_element<MODE_RESID>(h, L, tnew_ptr(L), L.res, 0, grid);
   if (rc) return rc;
   if (l2 || linf || smax) {
@@ -591,6 +605,8 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
     else if (e && !strcmp(e, "direct2")) h->kernel_mode = 3;
     const char* gr = getenv("PAMG_GRAPH");
     if (gr && gr[0] == '0') h->use_graph = false;
+    const char* sp = getenv("PAMG_SPLIT");
+    if (sp && sp[0] == '1') h->split_boundary = true;
     const char* fh = getenv("PAMG_FUSED_HALO");
     if (fh && fh[0] == '1') h->fused_halo = true;
     const char* g = getenv("PAMG_GS");
@@ -704,7 +720,7 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
       if (rc2) return rc2;
     }
   for (auto& Lv : h->lev) Lv.ovl_cur = 0;
-  h->npartial = h->nsm * 8;
+  h->npartial = h->nsm * 16;
   CK(cudaMalloc(&h->partial, (size_t)h->npartial * 3 * sizeof(double)));
   CK(cudaStreamSynchronize(h->stream));
   return PAMG_OK;

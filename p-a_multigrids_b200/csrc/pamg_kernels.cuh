@@ -46,6 +46,8 @@ struct ElemArgs {
   int s;                  // split of this level
   int colour;             // GS: 0 = down children, 1 = up children
   int dbg;                // experiments only (PAMG_DBG): 1 = skip the vertical-neighbour loads of the tile kernel
+  int split_boundary;     // 1: the tile kernel leaves children on parent faces untouched, k_boundary_fix updates them
+  int partial_off;        // first partial slot this launch writes (residual norms)
 };
 
 // flat child index t in [0, 4^s) -> row r (1-based), position ipos (1-based), element id ele (1-based)
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(TPB) k_element(ElemArgs a) {
       acc_max = fmax(acc_max, fmax(o1, fmax(o2, o3)));
     }
   }
-  if (MODE == MODE_RESID) block_partial(acc_sum, acc_abs, acc_max, a.partial);
+  if (MODE == MODE_RESID) block_partial(acc_sum, acc_abs, acc_max, a.partial + (size_t)3 * a.partial_off);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -512,7 +514,7 @@ __global__ void __launch_bounds__(TPB, 3) k_element_tma(ElemArgs a) {
       // up children of row 1 sit on parent face 1 and read the halo strip instead
       const int nb = p.up ? (k - b - 2 + 2 * p.r) : (k + b - 2 * p.r);       // 0-based child index
       if (p.up && p.r == 1) {
-        halo_pair(a, p.u, 0, p.ipos >> 1, S, p.va, p.vb);
+        if (!a.split_boundary) halo_pair(a, p.u, 0, p.ipos >> 1, S, p.va, p.vb);
       } else if (a.dbg != 1) {
         const unsigned o1 = ((unsigned)(g - k) + (unsigned)nb) * 3u;         // offsets in doubles fit 32 bits
         p.va = __ldg(a.Tin + o1 + 2); p.vb = __ldg(a.Tin + o1);
@@ -545,16 +547,17 @@ __global__ void __launch_bounds__(TPB, 3) k_element_tma(ElemArgs a) {
       const double* t = sT[st] + off0 + tid * 3;
       const double T1 = t[0], T2 = t[1], T3 = t[2];
       FaceIn fi;
-      bool interior = true;
+      bool interior = true, bnd = false;
       int bmask = 0;
       if (FACE) {
         fi.n1a = cur.va; fi.n1b = cur.vb;
         fi.pen1 = P.pi1; fi.pen2 = P.pi2; fi.pen3 = P.pi3;
         // face 2 looks left for an up child and right for a down child, face 3 the other way (splitting.F90:749-769)
-        const int d = cur.up ? -3 : 3;
+        bnd = cur.up && (cur.r == 1 || cur.ipos == 1 || cur.ipos == cur.len);   // child on a parent face (rare)
+        const int d = (bnd && a.split_boundary) ? 0 : (cur.up ? -3 : 3);
         fi.n2a = t[d + 1]; fi.n2b = t[d + 2];
         fi.n3a = t[-d]; fi.n3b = t[-d + 1];
-        if (cur.up && (cur.r == 1 || cur.ipos == 1 || cur.ipos == cur.len)) {   // child on a parent face (rare)
+        if (bnd && !a.split_boundary) {
           interior = false;
           if (cur.r == 1) { fi.pen1 = P.px1; bmask |= 1; }
           if (cur.ipos == 1) { halo_pair(a, cur.u, 2, cur.r - 1, S, fi.n2a, fi.n2b); fi.pen2 = P.px2; bmask |= 2; }
@@ -571,6 +574,10 @@ __global__ void __launch_bounds__(TPB, 3) k_element_tma(ElemArgs a) {
         elem_apply_folded<MODE>(F, sPC + PC_DPEN, bmask, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
       } else {
         elem_apply_regs<MODE, FACE>(P, cur.up, interior, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.omega, a.rsign, o1, o2, o3);
+      }
+      if (bnd && a.split_boundary) {      // k_boundary_fix owns this child: pass it through (residual: excluded)
+        const bool res = MODE == MODE_RESID;
+        o1 = res ? 0.0 : T1; o2 = res ? 0.0 : T2; o3 = res ? 0.0 : T3;
       }
       so[tid * 3] = o1; so[tid * 3 + 1] = o2; so[tid * 3 + 2] = o3;
       if (MODE != MODE_RESID && bmask && a.ovl_next) strips_write(a, cur.u, bmask, cur.r, cur.ipos, S, o1, o2, o3);
@@ -592,7 +599,7 @@ __global__ void __launch_bounds__(TPB, 3) k_element_tma(ElemArgs a) {
     cur = nxt;
   }
   if (tid == 0) tma_store_wait_all();
-  if (MODE == MODE_RESID) block_partial(acc_sum, acc_abs, acc_max, a.partial);
+  if (MODE == MODE_RESID) block_partial(acc_sum, acc_abs, acc_max, a.partial + (size_t)3 * a.partial_off);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -601,9 +608,60 @@ __global__ void __launch_bounds__(TPB, 3) k_element_tma(ElemArgs a) {
 // chain of two or three; children on a parent face patch their neighbour values from the halo strips in a
 // rare branch.  Coefficients come straight from the per-parent table (L1-resident).  Used for the coloured
 // Gauss-Seidel pass (in place) and selectable for the other modes (PAMG_KERNEL=direct2).
+// one child, everything from global memory: used by the direct kernel and by the boundary fix-up kernel
+template <int MODE, bool FACE>
+__device__ __forceinline__ void child_update(const ElemArgs& a, int u, int r, int ipos, int ele, int len, double& acc_sum,
+                                             double& acc_abs, double& acc_max) {
+  const int s = a.s, twos = 2 * s, b = 2 << s, S = 1 << s;
+  const bool up = ipos & 1;
+  const unsigned pbase = (unsigned)u << twos;
+  const unsigned e0 = pbase + (unsigned)(ele - 1);
+  // neighbour children; a missing neighbour (parent face) falls back to the child itself (valid address)
+  const int nb1 = up ? (r > 1 ? ele - b - 2 + 2 * r : ele) : ele + b - 2 * r;
+  const int nb2 = up ? (ipos > 1 ? ele - 1 : ele) : ele + 1;
+  const int nb3 = up ? (ipos < len ? ele + 1 : ele) : ele - 1;
+  const unsigned base = e0 * 3u;
+  auto ldT = [&](unsigned i) -> double { return MODE == MODE_GS ? a.Tin[i] : __ldg(a.Tin + i); };
+  const double T1 = ldT(base), T2 = ldT(base + 1), T3 = ldT(base + 2);
+  const double b1 = __ldg(a.rhs + base), b2 = __ldg(a.rhs + base + 1), b3 = __ldg(a.rhs + base + 2);
+  FaceIn fi;
+  const ParentRegs& P = *reinterpret_cast<const ParentRegs*>(a.pc + (size_t)u * NPC);
+  bool interior = true;
+  int bmask = 0;
+  if (FACE) {
+    const unsigned o1 = (pbase + (unsigned)(nb1 - 1)) * 3u, o2 = (pbase + (unsigned)(nb2 - 1)) * 3u,
+                   o3 = (pbase + (unsigned)(nb3 - 1)) * 3u;
+    fi.n1a = ldT(o1 + 2); fi.n1b = ldT(o1);        // my node 1 <-> its node 3, my node 3 <-> its node 1
+    fi.n2a = ldT(o2 + 1); fi.n2b = ldT(o2 + 2);    // my 3 <-> its 2, my 2 <-> its 3
+    fi.n3a = ldT(o3); fi.n3b = ldT(o3 + 1);        // my 2 <-> its 1, my 1 <-> its 2
+    fi.pen1 = P.pi1; fi.pen2 = P.pi2; fi.pen3 = P.pi3;
+    if (up && (r == 1 || ipos == 1 || ipos == len)) {   // child on a parent face (rare): halo strips
+      interior = false;
+      if (r == 1) { halo_pair(a, u, 0, ipos >> 1, S, fi.n1a, fi.n1b); fi.pen1 = P.px1; bmask |= 1; }
+      if (ipos == 1) { halo_pair(a, u, 2, r - 1, S, fi.n2a, fi.n2b); fi.pen2 = P.px2; bmask |= 2; }
+      if (ipos == len) { halo_pair(a, u, 1, r - 1, S, fi.n3a, fi.n3b); fi.pen3 = P.px3; bmask |= 4; }
+    }
+  }
+  double o1v, o2v, o3v;
+  if (FACE && MODE != MODE_RICH) {
+    const double* pcu = a.pc + (size_t)u * NPC;
+    const Folded& F = *reinterpret_cast<const Folded*>(pcu + PC_FOLD + (up ? 0 : 16));
+    elem_apply_folded<MODE>(F, pcu + PC_DPEN, bmask, T1, T2, T3, fi, b1, b2, b3, a.rsign, o1v, o2v, o3v);
+  } else {
+    elem_apply_regs<MODE, FACE>(P, up, interior, T1, T2, T3, fi, b1, b2, b3, a.omega, a.rsign, o1v, o2v, o3v);
+  }
+  a.Tout[base] = o1v; a.Tout[base + 1] = o2v; a.Tout[base + 2] = o3v;
+  if (MODE != MODE_RESID && bmask && a.ovl_next) strips_write(a, u, bmask, r, ipos, S, o1v, o2v, o3v);
+  if (MODE == MODE_RESID) {
+    acc_sum += o1v * o1v + o2v * o2v + o3v * o3v;
+    acc_abs = fmax(acc_abs, fmax(fabs(o1v), fmax(fabs(o2v), fabs(o3v))));
+    acc_max = fmax(acc_max, fmax(o1v, fmax(o2v, o3v)));
+  }
+}
+
 template <int MODE, bool FACE>
 __global__ void __launch_bounds__(TPB) k_element_direct2(ElemArgs a) {
-  const int s = a.s, twos = 2 * s, b = 2 << s, S = 1 << s;
+  const int s = a.s, twos = 2 * s;
   const unsigned Cmask = (1u << twos) - 1u;
   double acc_sum = 0.0, acc_abs = 0.0, acc_max = 0.0;
   const unsigned nelem = (unsigned)a.nelem;
@@ -611,53 +669,35 @@ __global__ void __launch_bounds__(TPB) k_element_direct2(ElemArgs a) {
     const int u = (int)(gid >> twos);
     int r, ipos, ele, len;
     child_from_flat((int)(gid & Cmask), s, r, ipos, ele, len);
-    const bool up = ipos & 1;
-    if (MODE == MODE_GS && (int)up != a.colour) continue;
-    const unsigned pbase = (unsigned)u << twos;
-    const unsigned e0 = pbase + (unsigned)(ele - 1);
-    // neighbour children; a missing neighbour (parent face) falls back to the child itself (valid address)
-    const int nb1 = up ? (r > 1 ? ele - b - 2 + 2 * r : ele) : ele + b - 2 * r;
-    const int nb2 = up ? (ipos > 1 ? ele - 1 : ele) : ele + 1;
-    const int nb3 = up ? (ipos < len ? ele + 1 : ele) : ele - 1;
-    const unsigned base = e0 * 3u;
-    auto ldT = [&](unsigned i) -> double { return MODE == MODE_GS ? a.Tin[i] : __ldg(a.Tin + i); };
-    const double T1 = ldT(base), T2 = ldT(base + 1), T3 = ldT(base + 2);
-    const double b1 = __ldg(a.rhs + base), b2 = __ldg(a.rhs + base + 1), b3 = __ldg(a.rhs + base + 2);
-    FaceIn fi;
-    const ParentRegs& P = *reinterpret_cast<const ParentRegs*>(a.pc + (size_t)u * NPC);
-    bool interior = true;
-    int bmask = 0;
-    if (FACE) {
-      const unsigned o1 = (pbase + (unsigned)(nb1 - 1)) * 3u, o2 = (pbase + (unsigned)(nb2 - 1)) * 3u,
-                     o3 = (pbase + (unsigned)(nb3 - 1)) * 3u;
-      fi.n1a = ldT(o1 + 2); fi.n1b = ldT(o1);        // my node 1 <-> its node 3, my node 3 <-> its node 1
-      fi.n2a = ldT(o2 + 1); fi.n2b = ldT(o2 + 2);    // my 3 <-> its 2, my 2 <-> its 3
-      fi.n3a = ldT(o3); fi.n3b = ldT(o3 + 1);        // my 2 <-> its 1, my 1 <-> its 2
-      fi.pen1 = P.pi1; fi.pen2 = P.pi2; fi.pen3 = P.pi3;
-      if (up && (r == 1 || ipos == 1 || ipos == len)) {   // child on a parent face (rare): halo strips
-        interior = false;
-        if (r == 1) { halo_pair(a, u, 0, ipos >> 1, S, fi.n1a, fi.n1b); fi.pen1 = P.px1; bmask |= 1; }
-        if (ipos == 1) { halo_pair(a, u, 2, r - 1, S, fi.n2a, fi.n2b); fi.pen2 = P.px2; bmask |= 2; }
-        if (ipos == len) { halo_pair(a, u, 1, r - 1, S, fi.n3a, fi.n3b); fi.pen3 = P.px3; bmask |= 4; }
-      }
-    }
-    double o1v, o2v, o3v;
-    if (FACE && MODE != MODE_RICH) {
-      const double* pcu = a.pc + (size_t)u * NPC;
-      const Folded& F = *reinterpret_cast<const Folded*>(pcu + PC_FOLD + (up ? 0 : 16));
-      elem_apply_folded<MODE>(F, pcu + PC_DPEN, bmask, T1, T2, T3, fi, b1, b2, b3, a.rsign, o1v, o2v, o3v);
-    } else {
-      elem_apply_regs<MODE, FACE>(P, up, interior, T1, T2, T3, fi, b1, b2, b3, a.omega, a.rsign, o1v, o2v, o3v);
-    }
-    a.Tout[base] = o1v; a.Tout[base + 1] = o2v; a.Tout[base + 2] = o3v;
-    if (MODE != MODE_RESID && bmask && a.ovl_next) strips_write(a, u, bmask, r, ipos, S, o1v, o2v, o3v);
-    if (MODE == MODE_RESID) {
-      acc_sum += o1v * o1v + o2v * o2v + o3v * o3v;
-      acc_abs = fmax(acc_abs, fmax(fabs(o1v), fmax(fabs(o2v), fabs(o3v))));
-      acc_max = fmax(acc_max, fmax(o1v, fmax(o2v, o3v)));
-    }
+    if (MODE == MODE_GS && (ipos & 1) != a.colour) continue;
+    child_update<MODE, FACE>(a, u, r, ipos, ele, len, acc_sum, acc_abs, acc_max);
   }
-  if (MODE == MODE_RESID) block_partial(acc_sum, acc_abs, acc_max, a.partial);
+  if (MODE == MODE_RESID) block_partial(acc_sum, acc_abs, acc_max, a.partial + (size_t)3 * a.partial_off);
+}
+
+// Children on parent faces (3 * 2^s of the 4^s children of a parent) handled apart from the tile kernel: their
+// halo-strip look-ups and boundary coefficients are a chain of dependent loads that would hold up a whole tile
+// at its barrier.  One thread per (parent, side, position); children on two sides are taken by the lower side.
+template <int MODE>
+__global__ void __launch_bounds__(TPB) k_boundary_fix(ElemArgs a, int U) {
+  const int S = 1 << a.s, b = 2 << a.s;
+  const long long n = (long long)U * 3 * S;
+  double acc_sum = 0.0, acc_abs = 0.0, acc_max = 0.0;
+  for (long long tid = (long long)blockIdx.x * TPB + threadIdx.x; tid < n; tid += (long long)gridDim.x * TPB) {
+    const int i = (int)(tid & (S - 1));
+    const int lf = (int)(tid >> a.s);
+    const int u = lf / 3, mf = lf - 3 * u;
+    const int pos = i + 1;
+    int r, ipos;
+    if (mf == 0) { r = 1; ipos = 2 * pos - 1; }
+    else if (mf == 2) { r = pos; ipos = 1; }
+    else { r = pos; ipos = b + 1 - 2 * pos; }
+    if ((mf == 1 && r == 1) || (mf == 2 && (r == 1 || r == S))) continue;   // also on a lower-numbered side
+    const int len = b + 1 - 2 * r;
+    const int ele = 1 + (r - 1) * (b + 1 - r) + ipos - 1;
+    child_update<MODE, true>(a, u, r, ipos, ele, len, acc_sum, acc_abs, acc_max);
+  }
+  if (MODE == MODE_RESID) block_partial(acc_sum, acc_abs, acc_max, a.partial + (size_t)3 * a.partial_off);
 }
 
 // second stage of the norm reduction: one CTA
