@@ -313,7 +313,6 @@ int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout,
   a.partial = h->partial; a.omega = h->p.omega; a.rsign = (double)h->p.residual_sign; a.nelem = L.nelem; a.s = L.s;
   a.colour = colour;
   a.split_boundary = 0; a.partial_off = 0;
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("PAMG_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
   const bool prof = h->profiling && h->pev_used + 2 <= (int)h->pev.size();
   if (prof) CK(cudaEventRecord(h->pev[h->pev_used], h->stream));
   if (MODE != MODE_GS && h->kernel_mode == 2 && L.nitems > 0) {

@@ -45,7 +45,6 @@ struct ElemArgs {
   long long nelem;        // U * C
   int s;                  // split of this level
   int colour;             // GS: 0 = down children, 1 = up children
-  int dbg;                // experiments only (PAMG_DBG): 1 = skip the vertical-neighbour loads of the tile kernel
   int split_boundary;     // 1: the tile kernel leaves children on parent faces untouched, k_boundary_fix updates them
   int partial_off;        // first partial slot this launch writes (residual norms)
 };
@@ -515,7 +514,7 @@ __global__ void __launch_bounds__(TPB, 3) k_element_tma(ElemArgs a) {
       const int nb = p.up ? (k - b - 2 + 2 * p.r) : (k + b - 2 * p.r);       // 0-based child index
       if (p.up && p.r == 1) {
         if (!a.split_boundary) halo_pair(a, p.u, 0, p.ipos >> 1, S, p.va, p.vb);
-      } else if (a.dbg != 1) {
+      } else {
         const unsigned o1 = ((unsigned)(g - k) + (unsigned)nb) * 3u;         // offsets in doubles fit 32 bits
         p.va = __ldg(a.Tin + o1 + 2); p.vb = __ldg(a.Tin + o1);
       }

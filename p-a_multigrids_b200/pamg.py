@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpamg_cuda.so")
+LIB_PATH = os.environ.get("PAMG_LIB") or os.path.join(_HERE, "lib", "libpamg_cuda.so")   # PAMG_LIB: A/B builds
 
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_IO, ERR_SINGULAR, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 TNEW, TOLD, RHS, RES, TNONLIN = 0, 1, 2, 3, 5
