@@ -93,6 +93,7 @@ struct pamg_handle {
   bool use_graph = true;    // replay the V-cycle as a CUDA graph from the second cycle on (PAMG_GRAPH=0 disables)
   struct VcGraph { long long key; cudaGraphExec_t exec; long long launches; };
   std::vector<VcGraph> vc_graphs;   // a few cached V-cycle graphs (solver / sweep counts / buffer parity)
+  bool graph_nccl = true;       // try to capture NCCL calls into the V-cycle graph (PAMG_GRAPH_NCCL=0 disables)
   bool split_boundary = false;  // PAMG_SPLIT=1: tile kernel + k_boundary_fix for the children on parent faces (measured: no gain for Jacobi)
   bool fused_halo = false;  // PAMG_FUSED_HALO=1: sweeps write the next sweep's strips themselves (measured slower: the extra work
                             // of the few children on parent faces delays the per-tile barrier; profiles/README.md)
@@ -103,6 +104,13 @@ struct pamg_handle {
   int pev_used = 0;
   // distributed
   ncclComm_t comm = nullptr; int nranks = 1, rank = 0;
+  // coarse-level agglomeration: levels >= agg_level are solved on part 0 for the whole mesh
+  pamg_handle* agg = nullptr;       // part 0 only: handle over ALL parents whose level 1 is my level agg_level
+  int agg_level = 0;                // 0 = none
+  int level_offset = 0;             // agg handle: its level l is level l + level_offset of the owner
+  bool shared_stream = false;
+  std::vector<int32_t> part_first;  // copy of the partition table
+  int U_global = 0;
   // unstructured
   UnstrDev un;
 };
@@ -275,7 +283,7 @@ int launch_halo(pamg_handle* h, int level, int what) {
   HaloArgs a;
   a.tnew = tnew_ptr(L); a.told = L.told; a.ovl = L.ovlb[L.ovl_cur]; a.ovl_old = L.ovl_old; a.xg = h->xg;
   a.dst_strip = h->dst_strip; a.rev = h->rev; a.strip_of = h->strip_of;
-  a.bc_scale = (h->p.coarse_bc_zero && level > 1) ? 0.0 : 1.0;
+  a.bc_scale = (h->p.coarse_bc_zero && level + h->level_offset > 1) ? 0.0 : 1.0;
   a.U = h->U; a.s = L.s; a.with_old = (what == 0) ? 1 : 0; a.what = what; a.nstrips = h->plan.nstrips;
   const long long n = (long long)h->U * 3 * L.S;
   k_halo<<<grid_for(h, n), TPB, 0, h->stream>>>(a);
@@ -484,6 +492,51 @@ int do_fill(pamg_handle* h, double* p, long long n, double v) {
   return PAMG_OK;
 }
 
+int vcycle_rec(pamg_handle* h, int level, int solver, int nu1, int nu2, int ncoarse);
+
+// Coarse-level agglomeration: below agg_level every kernel is launch-latency bound and every sweep
+// would pay an NCCL exchange, so the restricted right-hand side of all parts is gathered on part 0, the remaining
+// levels of the V-cycle run there on the whole mesh (no exchange at all), and the correction is scattered back.
+int agg_coarse_solve(pamg_handle* h, int solver, int nu1, int nu2, int ncoarse) {
+  LevelDev& Lc = h->lev[h->agg_level - 1];
+  const size_t per_parent = (size_t)3 * Lc.C;
+  if (!h->comm) return fail(h, PAMG_ERR_STATE, "agglomeration needs pamg_comm_init");
+  g_nccl.GroupStart();
+  if (h->rank == 0) {
+    LevelDev& A = h->agg->lev[0];
+    for (int p = 1; p < h->nranks; ++p)
+      g_nccl.Recv(A.rhs + per_parent * h->part_first[p], per_parent * (h->part_first[p + 1] - h->part_first[p]), ncclFloat64, p,
+                  h->comm, h->stream);
+  } else {
+    g_nccl.Send(Lc.rhs, per_parent * h->U, ncclFloat64, 0, h->comm, h->stream);
+  }
+  if (g_nccl.GroupEnd() != ncclSuccess) return fail(h, PAMG_ERR_CUDA, "ncclGroupEnd failed in coarse gather");
+  if (h->rank == 0) {
+    pamg_handle* g = h->agg;
+    LevelDev& A = g->lev[0];
+    CK(cudaMemcpyAsync(A.rhs, Lc.rhs, per_parent * h->U * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemsetAsync(A.T[A.cur], 0, A.ndof * sizeof(double), h->stream));
+    A.tnew_alias = true; A.strips_valid = false; A.rhs_valid = true;
+    const long long l0 = g->launches;
+    int rc = vcycle_rec(g, 1, solver, nu1, nu2, ncoarse);
+    h->launches += g->launches - l0;
+    if (rc) return fail(h, rc, g->err);
+    CK(cudaMemcpyAsync(Lc.T[Lc.cur], A.T[A.cur], per_parent * h->U * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  g_nccl.GroupStart();
+  if (h->rank == 0) {
+    LevelDev& A = h->agg->lev[0];
+    for (int p = 1; p < h->nranks; ++p)
+      g_nccl.Send(A.T[A.cur] + per_parent * h->part_first[p], per_parent * (h->part_first[p + 1] - h->part_first[p]), ncclFloat64,
+                  p, h->comm, h->stream);
+  } else {
+    g_nccl.Recv(Lc.T[Lc.cur], per_parent * h->U, ncclFloat64, 0, h->comm, h->stream);
+  }
+  if (g_nccl.GroupEnd() != ncclSuccess) return fail(h, PAMG_ERR_CUDA, "ncclGroupEnd failed in coarse scatter");
+  Lc.tnew_alias = true; Lc.strips_valid = false;
+  return PAMG_OK;
+}
+
 // Jacobi / Richardson sweeps ping-pong between the two T buffers; a cycle that ends on the other buffer would not
 // be replayable as a CUDA graph (pointers are baked in), so the iterate is moved back when the sweep count is odd.
 int normalise_parity(pamg_handle* h, LevelDev& L, int cur0) {
@@ -512,7 +565,11 @@ int vcycle_rec(pamg_handle* h, int level, int solver, int nu1, int nu2, int ncoa
   if ((rc = do_fill(h, Cc.T[Cc.cur], Cc.ndof, 0.0))) return rc;
   Cc.tnew_alias = true;
   Cc.strips_valid = false;
-  if ((rc = vcycle_rec(h, level + 1, solver, nu1, nu2, ncoarse))) return rc;
+  if (h->agg_level && level + 1 == h->agg_level) {
+    if ((rc = agg_coarse_solve(h, solver, nu1, nu2, ncoarse))) return rc;
+  } else {
+    if ((rc = vcycle_rec(h, level + 1, solver, nu1, nu2, ncoarse))) return rc;
+  }
   if ((rc = do_prolong(h, level, false))) return rc;
   if ((rc = do_smooth(h, level, solver, nu2))) return rc;
   return normalise_parity(h, L, cur0);
@@ -604,6 +661,8 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
     else if (e && !strcmp(e, "direct2")) h->kernel_mode = 3;
     const char* gr = getenv("PAMG_GRAPH");
     if (gr && gr[0] == '0') h->use_graph = false;
+    const char* gn = getenv("PAMG_GRAPH_NCCL");
+    if (gn && gn[0] == '0') h->graph_nccl = false;
     const char* sp = getenv("PAMG_SPLIT");
     if (sp && sp[0] == '1') h->split_boundary = true;
     const char* fh = getenv("PAMG_FUSED_HALO");
@@ -626,6 +685,11 @@ void pamg_destroy(pamg_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  // graphs that contain NCCL nodes must go before the communicator
+  for (auto& g : h->vc_graphs) cudaGraphExecDestroy(g.exec);
+  h->vc_graphs.clear();
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->agg) { pamg_destroy(h->agg); h->agg = nullptr; }
   if (h->comm) g_nccl.CommDestroy(h->comm);
   free_levels(h);
   unstr_free(h->un);
@@ -633,7 +697,7 @@ void pamg_destroy(pamg_handle* h) {
   if (h->stage) cudaFreeHost(h->stage);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->pev) if (e) cudaEventDestroy(e);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream && !h->shared_stream) cudaStreamDestroy(h->stream);
   delete h;
 }
 
@@ -647,9 +711,13 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
   int rc = build_halo_plan(U_global, X, neig, fneig, dir, h->p.halo_rule, nparts, part_first, my_part, h->plan);
   if (rc) return fail(h, rc, "inconsistent parent arrays (X / Neig / fNeig)");
   free_levels(h);
+  if (h->agg) { pamg_destroy(h->agg); h->agg = nullptr; }
+  h->agg_level = 0;
   const int U = h->plan.U_local, first = h->plan.first;
   if (U < 1) return fail(h, PAMG_ERR_ARG, "empty partition");
-  h->U = U;
+  h->U = U; h->U_global = U_global;
+  h->part_first.assign(nparts + 1, 0);
+  if (part_first) for (int i = 0; i <= nparts; ++i) h->part_first[i] = part_first[i]; else h->part_first[1] = U_global;
   std::vector<double> xg((size_t)U * 6);
   for (int u = 0; u < U; ++u) {
     const double* P = X + (size_t)(first + u) * 6;
@@ -719,6 +787,31 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
       if (rc2) return rc2;
     }
   for (auto& Lv : h->lev) Lv.ovl_cur = 0;
+  // coarse-level agglomeration on part 0: first level whose GLOBAL size is small enough to be launch-bound
+  if (nparts > 1 && h->level_offset == 0) {
+    const char* e = getenv("PAMG_AGG_ELEMS");
+    const long long limit = e ? atoll(e) : (1ll << 21);     // elements of the whole mesh on that level; 0 disables
+    int lvl = 0;
+    for (int il = 2; il <= h->p.multi_levels; ++il)
+      if (limit > 0 && (long long)U_global * h->lev[il - 1].C <= limit) { lvl = il; break; }
+    if (lvl) {
+      h->agg_level = lvl;
+      if (my_part == 0) {
+        pamg_params ap = h->p;
+        ap.n_split = h->lev[lvl - 1].s;
+        ap.multi_levels = h->p.multi_levels - lvl + 1;
+        pamg_handle* g = new pamg_handle();
+        g->p = ap; g->device = h->device; g->nsm = h->nsm; g->kernel_mode = h->kernel_mode; g->gs_tma = h->gs_tma;
+        g->stream = h->stream; g->shared_stream = true; g->level_offset = lvl - 1;
+        for (auto& ev : g->ev) cudaEventCreate(&ev);
+        cudaMalloc(&g->out3, 3 * sizeof(double));
+        cudaMallocHost(&g->out3_host, 3 * sizeof(double));
+        h->agg = g;
+        int rc3 = pamg_set_parents_partition(g, U_global, X, neig, fneig, dir, 1, nullptr, 0);
+        if (rc3) return fail(h, rc3, std::string("agglomerated coarse problem: ") + g->err);
+      }
+    }
+  }
   h->npartial = h->nsm * 16;
   CK(cudaMalloc(&h->partial, (size_t)h->npartial * 3 * sizeof(double)));
   CK(cudaStreamSynchronize(h->stream));
@@ -866,7 +959,9 @@ int pamg_vcycle_solve(pamg_handle* h, int solver, int nu1, int nu2, int ncoarse,
   // cycle 1 runs eagerly (it also sets the kernels' attributes); from cycle 2 on the identical launch sequence
   // (~170 launches, most of them on launch-bound coarse levels) is replayed as one CUDA graph
   const long long key0 = ((((long long)solver * 64 + nu1) * 64 + nu2) * 64 + ncoarse);
-  const bool graph_ok = h->use_graph && !h->comm && !h->profiling;
+  // with NCCL in the cycle (halo exchange, coarse gather/scatter) the capture is attempted once; if the library
+  // refuses, the handle falls back to eager launches for good
+  const bool graph_ok = h->use_graph && !h->profiling && (!h->comm || h->graph_nccl);
   for (int c = 1; c <= max_cycles; ++c) {
     if (c >= 2 && graph_ok) {
       long long key = key0;                      // the graph bakes in which of the two T buffers holds the iterate
@@ -882,13 +977,23 @@ int pamg_vcycle_solve(pamg_handle* h, int solver, int nu1, int nu2, int ncoarse,
         rc = vcycle_body(h, solver, nu1, nu2, ncoarse);
         h->capturing = false;
         cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-        if (ce != cudaSuccess) return fail(h, PAMG_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
         pamg_handle::VcGraph ng{key, nullptr, h->launches - l0};
         h->launches = l0;
-        ce = cudaGraphInstantiate(&ng.exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (ce != cudaSuccess) return fail(h, PAMG_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+        if (!rc && ce == cudaSuccess) {
+          ce = cudaGraphInstantiate(&ng.exec, graph, 0);
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (rc || ce != cudaSuccess) {
+          if (!h->comm) {
+            if (rc) return rc;
+            return fail(h, PAMG_ERR_CUDA, std::string("CUDA graph capture of the V-cycle: ") + cudaGetErrorString(ce));
+          }
+          // NCCL inside the capture was refused: run eagerly from now on (host-side state is periodic per cycle)
+          (void)cudaGetLastError();
+          h->graph_nccl = false;
+          if ((rc = vcycle_body(h, solver, nu1, nu2, ncoarse))) return rc;
+          goto cycle_done;
+        }
         h->vc_graphs.push_back(ng);
         vg = &h->vc_graphs.back();
       }
@@ -897,6 +1002,7 @@ int pamg_vcycle_solve(pamg_handle* h, int solver, int nu1, int nu2, int ncoarse,
     } else {
       if ((rc = vcycle_body(h, solver, nu1, nu2, ncoarse))) return rc;
     }
+  cycle_done:
     CK(cudaStreamSynchronize(h->stream));
     r = std::sqrt(h->out3_host[0]);
     if (hist) hist[c] = r;
