@@ -346,7 +346,7 @@ def main():
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_element<JACOBI,face>", "kernel_avg_ms": kern_avg_ms,
+                         "traffic": None, "kernel": "k_element_tma<JACOBI,face> (pipelined 1-D TMA tiles)", "kernel_avg_ms": kern_avg_ms,
                          "kernel_launches_timed": kern_n, "algorithmic_bytes_per_launch": BYTES_PER_DOF_JACOBI * ndof,
                          "peak_source": peak_src,
                          "whole_step_frac": (BYTES_PER_DOF_JACOBI * ndof * NSMOOTH * args.steps / (ms * 1e-3) / 1e9) / peak},
