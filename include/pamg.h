@@ -147,6 +147,19 @@ int pamg_unstr_download(pamg_handle* h, double* tnew);
 int pamg_explicit_step(pamg_handle* h, double dt, double u_x, double u_y, double t_bc, int ntime, int nits,
                        int njac_its, int use_exact_minv, int use_dir);
 
+/* ---- unstructured implicit operator in block-CSR (unstr_implicit, transport_tri_unstr.F90:214-387) --
+ * Replaces add_to_CSR / add_to_CSR_flux / make_sparse_matrix_flux (matrices.F90:12-161), csr_to_dense and the dense
+ * FINDInv of the whole (3E)^2 matrix (:366-378).  Row e holds 4 blocks of 3x3 (row-major): block 0 = own columns
+ * (mass/dt - stiffness + outflow flux), block 1+f = inflow flux of gmsh face f+1 in the neighbour's columns.
+ * Needs pamg_set_unstructured first.  The time loop works on the field of pamg_unstr_upload / _download. */
+int pamg_implicit_assemble(pamg_handle* h, double dt, double u_x, double u_y, int use_dir);
+int pamg_implicit_get_bsr(pamg_handle* h, double* val /* [E][4][9] or NULL */, int32_t* col /* [E][4], 0-based, -1 = none, or NULL */);
+int pamg_implicit_apply(pamg_handle* h, const double* x /* host (3,E) */, double* y /* host: (lhs + flux) x */);
+/* ntime x nits passes of: told = tnew ; solve (lhs + flux) tnew = (M/dt) told by block-Jacobi-preconditioned
+ * BiCGStab to ||r|| <= tol ||rhs|| (at most max_iters iterations per solve).  iters_total / relres (worst solve)
+ * may be NULL. */
+int pamg_implicit_step(pamg_handle* h, int ntime, int nits, double tol, int max_iters, int* iters_total, double* relres);
+
 /* ---- batched element-local inverse (FINDInv, matrix_inversion.F90:50-148) ----------------------- */
 /* M, x, rhs on the HOST; n in {3,4,6}; M row-major [batch][n][n].  x = M^-1 rhs (Minv optional out).
  * status[b] = 0 or -1 (singular) like errorflag. */

@@ -1180,6 +1180,91 @@ void orc_unstr_explicit(int E, const double* X, const int32_t* neig, const int32
   }
 }
 
+// ------------------------------------------------------------------ unstructured implicit
+// Assembly of unstr_implicit, transport_tri_unstr.F90:270-364: per element the block mass/dt - stiff (:270-292) and
+// per face the 3x3 upwind block flux_ele(iloc,jloc) (:344-362) that lands in the columns of the element itself
+// (outflow) or of the neighbour (inflow), `target_ele` (:339-342).  The CSR containers of the reference
+// (add_to_CSR assigns, add_to_CSR_flux accumulates in a fixed window, SURVEY B-15) are replaced by plain accumulation
+// into dense row-major matrices A (lhs + flux) and Mdt (mass/dt) of size (3E)^2 - small meshes only.
+void orc_unstr_implicit_assemble(int E, const double* X, const int32_t* neig, const int32_t* fneig, double u_x,
+                                 double u_y, double dt, int use_dir, double* A, double* Mdt) {
+  const size_t N = (size_t)3 * E;
+  std::fill(A, A + N * N, 0.0);
+  std::fill(Mdt, Mdt + N * N, 0.0);
+  for (int e = 0; e < E; ++e) {
+    const double (*x)[2] = reinterpret_cast<const double (*)[2]>(&X[(size_t)e * 6]);
+    double nx[3][2][3], detwei[3];
+    tri_det_nlx(x, nx, detwei);
+    double ugi[3][2];
+    for (int g = 0; g < 3; ++g) {
+      ugi[g][0] = (TB.n[g][0] + TB.n[g][1] + TB.n[g][2]) * u_x;
+      ugi[g][1] = (TB.n[g][0] + TB.n[g][1] + TB.n[g][2]) * u_y;
+    }
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        double mass = 0, stiff = 0;
+        for (int g = 0; g < 3; ++g) {
+          mass += TB.n[g][i] * TB.n[g][j] * detwei[g] / dt;
+          for (int d = 0; d < 2; ++d) stiff += nx[g][d][i] * ugi[g][d] * detwei[g] * TB.n[g][j];
+        }
+        Mdt[(size_t)(3 * e + i) * N + 3 * e + j] += mass;
+        A[(size_t)(3 * e + i) * N + 3 * e + j] += mass - stiff;
+      }
+    for (int f = 1; f <= 3; ++f) {
+      const int npos = neig[e * 3 + f - 1], nside = fneig[e * 3 + f - 1];
+      double sn[2][3] = {{0, 0, 0}, {0, 0, 0}}, sn2[2][3] = {{0, 0, 0}, {0, 0, 0}};
+      const int l1 = UN_FACE_NODES[f - 1][0] - 1, l2 = UN_FACE_NODES[f - 1][1] - 1;
+      for (int s = 0; s < 2; ++s) { sn[s][l1] = TB.sn[s][0]; sn[s][l2] = TB.sn[s][1]; }
+      const int N2[3][2] = {{3, 1}, {1, 2}, {2, 3}};
+      if (nside >= 1) {
+        int m1 = N2[nside - 1][0] - 1, m2 = N2[nside - 1][1] - 1;
+        if (use_dir && npos != 0) {
+          const double (*xn)[2] = reinterpret_cast<const double (*)[2]>(&X[(size_t)(npos - 1) * 6]);
+          if (!are_equal2(xn[m1], x[l1])) std::swap(m1, m2);
+        }
+        for (int s = 0; s < 2; ++s) { sn2[s][m1] = TB.sn[s][0]; sn2[s][m2] = TB.sn[s][1]; }
+      }
+      double sdet[2], snorm[2][2], income[2], us[2][2], us2[2][2];
+      face_geometry(x, f, sdet, snorm);
+      for (int s = 0; s < 2; ++s) {
+        double sum2 = 0;
+        for (int q = 0; q < 3; ++q) sum2 += sn2[s][q];
+        us[s][0] = u_x; us[s][1] = u_y; us2[s][0] = sum2 * u_x; us2[s][1] = sum2 * u_y;
+        const double un = snorm[s][0] * 0.5 * (us[s][0] + us2[s][0]) + snorm[s][1] * 0.5 * (us[s][1] + us2[s][1]);
+        income[s] = 0.5 + 0.5 * std::copysign(1.0, -un);
+      }
+      int target = (int)((1.0 - income[0]) * (e + 1) + income[0] * npos);   // :339
+      if (target == 0) target = e + 1;                                      // :340-342
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+          double fl = 0;
+          for (int d = 0; d < 2; ++d)
+            for (int s = 0; s < 2; ++s)
+              fl += snorm[s][d] * sdet[s] * sn[s][i] *
+                    ((1.0 - income[s]) * sn[s][j] * us[s][d] + income[s] * sn2[s][j] * us2[s][d]);
+          A[(size_t)(3 * e + i) * N + 3 * (target - 1) + j] += fl;
+        }
+    }
+  }
+}
+
+// time loop of unstr_implicit (:214-387): told = tnew ; rhs = (M/dt) told ; tnew = inverse(lhs + flux) rhs by FINDInv
+int orc_unstr_implicit(int E, const double* X, const int32_t* neig, const int32_t* fneig, double u_x, double u_y,
+                       double dt, int ntime, int nits, int use_dir, double* tnew) {
+  const size_t N = (size_t)3 * E;
+  std::vector<double> A(N * N), M(N * N), inv(N * N), rhs(N), told(N);
+  orc_unstr_implicit_assemble(E, X, neig, fneig, u_x, u_y, dt, use_dir, A.data(), M.data());
+  if (findinv(A.data(), inv.data(), (int)N) != 0) return -1;
+  for (int it = 0; it < ntime; ++it) {
+    std::copy(tnew, tnew + N, told.begin());
+    for (int k = 0; k < nits; ++k) {
+      for (size_t i = 0; i < N; ++i) { double s = 0; for (size_t j = 0; j < N; ++j) s += M[i * N + j] * told[j]; rhs[i] = s; }
+      for (size_t i = 0; i < N; ++i) { double s = 0; for (size_t j = 0; j < N; ++j) s += inv[i * N + j] * rhs[j]; tnew[i] = s; }
+    }
+  }
+  return 0;
+}
+
 // transport_rect.F90:48-52,83,101-105,337-344 ; structured_meshgen.F90:25-33 (one row of quads)
 void orc_rect_analytical(double CFL, int no_ele_row, double x_length, double u_x, double time,
                          double* x_out, double* t_out) {

@@ -91,6 +91,12 @@ void orc_unstr_explicit(int E, const double* X, const int32_t* neig, const int32
                         const int32_t* dir, double u_x, double u_y, double dt, int ntime, int nits,
                         int njac_its, int exact_minv, int use_dir, double t_bc, double* tnew /* (3,E) in/out */);
 
+/* ---- unstructured implicit assembly + dense solve (transport_tri_unstr.F90:214-387); dense (3E)^2, small E only */
+void orc_unstr_implicit_assemble(int E, const double* X, const int32_t* neig, const int32_t* fneig, double u_x,
+                                 double u_y, double dt, int use_dir, double* A, double* Mdt);
+int orc_unstr_implicit(int E, const double* X, const int32_t* neig, const int32_t* fneig, double u_x, double u_y,
+                       double dt, int ntime, int nits, int use_dir, double* tnew);
+
 /* ---- analytic cases ----------------------------------------------------------- */
 /* transport_rect.F90:83,101-105,337-344 : fills x[800], t[800] */
 void orc_rect_analytical(double CFL, int no_ele_row, double x_length, double u_x, double time,

@@ -1135,6 +1135,57 @@ int pamg_explicit_step(pamg_handle* h, double dt, double u_x, double u_y, double
   return PAMG_OK;
 }
 
+// ---- unstructured implicit operator in block-CSR (unstr_implicit, transport_tri_unstr.F90:214-387) --------
+int pamg_implicit_assemble(pamg_handle* h, double dt, double u_x, double u_y, int use_dir) {
+  if (!h || h->un.E < 1 || !(dt > 0.0)) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  std::string e;
+  long long nl = 0;
+  int rc = implicit_assemble(h->un, dt, u_x, u_y, use_dir, h->nsm, h->stream, nl, e);
+  h->launches += nl;
+  if (rc) return fail(h, rc, e);
+  return PAMG_OK;
+}
+
+int pamg_implicit_get_bsr(pamg_handle* h, double* val, int32_t* col) {
+  if (!h || h->un.E < 1 || (!val && !col)) return PAMG_ERR_ARG;
+  if (!h->un.assembled) return fail(h, PAMG_ERR_STATE, "pamg_implicit_assemble has not been called");
+  CK(cudaSetDevice(h->device));
+  const size_t E = (size_t)h->un.E;
+  if (val) CK(cudaMemcpyAsync(val, h->un.bsr_val, E * 36 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (col) CK(cudaMemcpyAsync(col, h->un.bsr_col, E * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PAMG_OK;
+}
+
+int pamg_implicit_apply(pamg_handle* h, const double* x, double* y) {
+  if (!h || h->un.E < 1 || !x || !y) return PAMG_ERR_ARG;
+  if (!h->un.assembled) return fail(h, PAMG_ERR_STATE, "pamg_implicit_assemble has not been called");
+  CK(cudaSetDevice(h->device));
+  const size_t nb = (size_t)h->un.E * 3 * sizeof(double);
+  double* W = h->un.work;
+  CK(cudaMemcpyAsync(W, x, nb, cudaMemcpyHostToDevice, h->stream));
+  const int grid = std::max(1, std::min((h->un.E + TPB - 1) / TPB, h->nsm * 8));
+  k_bsr_spmv<<<grid, TPB, 0, h->stream>>>(h->un.bsr_val, h->un.bsr_col, W, nullptr, W + (size_t)h->un.E * 3, h->un.E, 0);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(y, W + (size_t)h->un.E * 3, nb, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PAMG_OK;
+}
+
+int pamg_implicit_step(pamg_handle* h, int ntime, int nits, double tol, int max_iters, int* iters_total, double* relres) {
+  if (!h || h->un.E < 1 || ntime < 0 || nits < 1 || !(tol > 0.0) || max_iters < 1) return PAMG_ERR_ARG;
+  if (!h->un.assembled) return fail(h, PAMG_ERR_STATE, "pamg_implicit_assemble has not been called");
+  CK(cudaSetDevice(h->device));
+  std::string e;
+  long long nl = 0;
+  int rc = implicit_step(h->un, ntime, nits, tol, max_iters, iters_total, relres, h->nsm, h->stream, nl, e);
+  h->launches += nl;
+  if (rc) return fail(h, rc, e);
+  return PAMG_OK;
+}
+
 int pamg_apply_local_minv(pamg_handle* h, int n, int batch, const double* M, const double* rhs, double* x,
                           double* Minv, int32_t* status) {
   if (!h || batch < 1 || !M || !(n == 3 || n == 4 || n == 6)) return PAMG_ERR_ARG;

@@ -26,6 +26,15 @@ struct UnstrDev {
   double* T[2] = {nullptr, nullptr};
   double* told = nullptr;
   int cur = 0;
+  // implicit operator in block-CSR: 4 blocks of 3x3 per element row (own, face 1, face 2, face 3)
+  double* bsr_val = nullptr;   // [E][4][9] row-major blocks
+  int32_t* bsr_col = nullptr;  // [E][4] 0-based element of the block column, -1 = no block
+  double* dinv = nullptr;      // [E][9] inverse of the diagonal block (block-Jacobi preconditioner)
+  double* mdt = nullptr;       // [E] A/(12 dt): M/dt = mdt (I + J) per element
+  double* work = nullptr;      // 9 vectors of 3E doubles for BiCGStab
+  double* dots = nullptr;      // [4] device results of k_dots
+  double* dots_host = nullptr; // pinned mirror
+  bool assembled = false;
 };
 
 struct UnstrArgs {
@@ -116,6 +125,8 @@ __global__ void __launch_bounds__(TPB) k_unstr_explicit(UnstrArgs a) {
 
 inline void unstr_free(UnstrDev& u) {
   cudaFree(u.X); cudaFree(u.neig); cudaFree(u.nside); cudaFree(u.T[0]); cudaFree(u.T[1]); cudaFree(u.told);
+  cudaFree(u.bsr_val); cudaFree(u.bsr_col); cudaFree(u.dinv); cudaFree(u.mdt); cudaFree(u.work); cudaFree(u.dots);
+  if (u.dots_host) cudaFreeHost(u.dots_host);
   u = UnstrDev();
 }
 
@@ -171,6 +182,267 @@ inline int unstr_step(UnstrDev& u, double dt, double ux, double uy, double t_bc,
       u.cur ^= 1;
     }
   }
+  return PAMG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Implicit "Jacobian" of unstr_implicit (transport_tri_unstr.F90:270-364) assembled straight into block-CSR on the
+// device: one thread per element writes its diagonal block mass/dt - stiff (+ the outflow part of the
+// upwind flux, :344-360 with income = 0) and one 3x3 block per inflow face in the neighbour's columns
+// (`target_ele`, :339-342).  The reference builds three scalar CSR matrices, converts them to dense and inverts
+// the dense (3E)^2 matrix with FINDInv (:366-378); here the operator never leaves its 4-blocks-per-row form.
+struct BsrArgs {
+  const double* X; const int32_t* neig; const int32_t* nside;
+  double* val; int32_t* col; double* dinv; double* mdt;
+  double dt, ux, uy;
+  int E, use_dir;
+};
+
+__global__ void __launch_bounds__(TPB) k_assemble_bsr(BsrArgs a) {
+  const double al = 0.78867513459481288, be = 0.21132486540518712;
+  const double w2 = al * al + be * be, w1 = 2.0 * al * be;
+  for (int e = blockIdx.x * TPB + threadIdx.x; e < a.E; e += gridDim.x * TPB) {
+    const double* __restrict__ X = a.X + (size_t)e * 6;
+    const double x1 = __ldg(X), y1 = __ldg(X + 1), x2 = __ldg(X + 2), y2 = __ldg(X + 3), x3 = __ldg(X + 4), y3 = __ldg(X + 5);
+    const double A = x1 - x3, B = y1 - y3, C = x2 - x3, D = y2 - y3;
+    const double detj = A * D - B * C;
+    const double area = 0.5 * fabs(detj);
+    const double gx[3] = {D / detj, -B / detj, -(D / detj) - (-B / detj)};
+    const double gy[3] = {-C / detj, A / detj, -(-C / detj) - (A / detj)};
+    const double m12 = area / (12.0 * a.dt);
+    double blk[4][9];
+#pragma unroll
+    for (int bq = 0; bq < 4; ++bq)
+#pragma unroll
+      for (int q = 0; q < 9; ++q) blk[bq][q] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double st = (gx[i] * a.ux + gy[i] * a.uy) * (area / 3.0);   // stiff(i,j): the same for every j (:281-283)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) blk[0][i * 3 + j] = m12 * (i == j ? 2.0 : 1.0) - st;
+    }
+    const double cx = (x1 + x2 + x3) / 3.0, cy = (y1 + y2 + y3) / 3.0;
+    const double px[3] = {x1, x2, x3}, py[3] = {y1, y2, y3};
+    const int L1[3] = {0, 1, 2}, L2[3] = {2, 0, 1};
+    int cols[4] = {e, -1, -1, -1};
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      const int l1 = L1[f], l2 = L2[f];
+      const double ex = px[l2] - px[l1], ey = py[l2] - py[l1];
+      const double len = sqrt(ex * ex + ey * ey);
+      double nx = ey / len, ny = -ex / len;
+      const double mx = 0.5 * (px[l1] + px[l2]) - cx, my = 0.5 * (py[l1] + py[l2]) - cy;
+      if (nx * mx + ny * my < 0.0) { nx = -nx; ny = -ny; }
+      const double sdet = 0.5 * len;
+      const int q = __ldg(a.neig + (size_t)e * 3 + f);
+      const int enc = __ldg(a.nside + (size_t)e * 3 + f);
+      const int ns = enc & 3;
+      const double has2 = ns >= 1 ? 1.0 : 0.0;
+      const double unn = nx * a.ux + ny * a.uy;
+      const double un = 0.5 * (unn + has2 * unn);
+      const bool in = signbit(-un) == 0;
+      const double c = sdet * unn;
+      if (!in) {                       // outflow: own columns
+        blk[0][l1 * 3 + l1] += c * w2; blk[0][l1 * 3 + l2] += c * w1;
+        blk[0][l2 * 3 + l1] += c * w1; blk[0][l2 * 3 + l2] += c * w2;
+      } else if (ns >= 1) {            // inflow: the neighbour's columns, its nodes paired as in get_unstr_sn2
+        int m1 = (ns == 1) ? 2 : (ns == 2 ? 0 : 1), m2 = (ns == 1) ? 0 : (ns == 2 ? 1 : 2);
+        if (a.use_dir && (enc >> 2)) { const int t = m1; m1 = m2; m2 = t; }
+        const int b = (q != 0) ? 1 + f : 0;   // target_ele == 0 falls back to the element itself (:340-342)
+        blk[b][l1 * 3 + m1] += c * w2; blk[b][l1 * 3 + m2] += c * w1;
+        blk[b][l2 * 3 + m1] += c * w1; blk[b][l2 * 3 + m2] += c * w2;
+        if (q != 0) cols[1 + f] = q - 1;
+      }                                // inflow through the domain boundary (Nside = 0): sn2 = 0 -> no block
+    }
+#pragma unroll
+    for (int bq = 0; bq < 4; ++bq) {
+      a.col[(size_t)e * 4 + bq] = cols[bq];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) a.val[((size_t)e * 4 + bq) * 9 + q] = blk[bq][q];
+    }
+    // inverse of the diagonal block by its adjugate
+    const double* d = blk[0];
+    const double c00 = d[4] * d[8] - d[5] * d[7], c01 = d[5] * d[6] - d[3] * d[8], c02 = d[3] * d[7] - d[4] * d[6];
+    const double det = d[0] * c00 + d[1] * c01 + d[2] * c02, id = 1.0 / det;
+    double* o = a.dinv + (size_t)e * 9;
+    o[0] = c00 * id; o[1] = (d[2] * d[7] - d[1] * d[8]) * id; o[2] = (d[1] * d[5] - d[2] * d[4]) * id;
+    o[3] = c01 * id; o[4] = (d[0] * d[8] - d[2] * d[6]) * id; o[5] = (d[2] * d[3] - d[0] * d[5]) * id;
+    o[6] = c02 * id; o[7] = (d[1] * d[6] - d[0] * d[7]) * id; o[8] = (d[0] * d[4] - d[1] * d[3]) * id;
+    a.mdt[e] = m12;
+  }
+}
+
+// y = A x (block-CSR) ; mode 1: y = b - A x
+__global__ void __launch_bounds__(TPB) k_bsr_spmv(const double* __restrict__ val, const int32_t* __restrict__ col,
+                                                  const double* __restrict__ x, const double* __restrict__ b,
+                                                  double* __restrict__ y, int E, int mode) {
+  for (int e = blockIdx.x * TPB + threadIdx.x; e < E; e += gridDim.x * TPB) {
+    double s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+    for (int bq = 0; bq < 4; ++bq) {
+      const int c = __ldg(col + (size_t)e * 4 + bq);
+      if (c < 0) continue;
+      const double* v = val + ((size_t)e * 4 + bq) * 9;
+      const double x0 = __ldg(x + (size_t)c * 3), x1 = __ldg(x + (size_t)c * 3 + 1), x2 = __ldg(x + (size_t)c * 3 + 2);
+      s0 += v[0] * x0 + v[1] * x1 + v[2] * x2;
+      s1 += v[3] * x0 + v[4] * x1 + v[5] * x2;
+      s2 += v[6] * x0 + v[7] * x1 + v[8] * x2;
+    }
+    if (mode == 1) { s0 = b[(size_t)e * 3] - s0; s1 = b[(size_t)e * 3 + 1] - s1; s2 = b[(size_t)e * 3 + 2] - s2; }
+    y[(size_t)e * 3] = s0; y[(size_t)e * 3 + 1] = s1; y[(size_t)e * 3 + 2] = s2;
+  }
+}
+
+// y = Dinv x (block-Jacobi preconditioner) ; mode 1: y = (M/dt) x with M/dt = mdt (I + J) per element (:366-369)
+__global__ void __launch_bounds__(TPB) k_block_apply(const double* __restrict__ dinv, const double* __restrict__ mdt,
+                                                     const double* __restrict__ x, double* __restrict__ y, int E, int mode) {
+  for (int e = blockIdx.x * TPB + threadIdx.x; e < E; e += gridDim.x * TPB) {
+    const double x0 = x[(size_t)e * 3], x1 = x[(size_t)e * 3 + 1], x2 = x[(size_t)e * 3 + 2];
+    if (mode == 1) {
+      const double m = mdt[e], sx = x0 + x1 + x2;
+      y[(size_t)e * 3] = m * (x0 + sx); y[(size_t)e * 3 + 1] = m * (x1 + sx); y[(size_t)e * 3 + 2] = m * (x2 + sx);
+    } else {
+      const double* d = dinv + (size_t)e * 9;
+      y[(size_t)e * 3] = d[0] * x0 + d[1] * x1 + d[2] * x2;
+      y[(size_t)e * 3 + 1] = d[3] * x0 + d[4] * x1 + d[5] * x2;
+      y[(size_t)e * 3 + 2] = d[6] * x0 + d[7] * x1 + d[8] * x2;
+    }
+  }
+}
+
+// z = a x + b y + c w   (w may be null; z may alias any input)
+__global__ void __launch_bounds__(TPB) k_lincomb(double* z, double a, const double* x, double b, const double* y, double c,
+                                                 const double* w, long long n) {
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += (long long)gridDim.x * TPB)
+    z[i] = a * x[i] + b * y[i] + (w ? c * w[i] : 0.0);
+}
+
+// two dot products per pass: partial[2*blockIdx.x + {0,1}] = x.y , u.v  (u may be null)
+__global__ void __launch_bounds__(TPB) k_dots(const double* __restrict__ x, const double* __restrict__ y,
+                                              const double* __restrict__ u, const double* __restrict__ v, long long n,
+                                              double* __restrict__ partial) {
+  double s0 = 0, s1 = 0;
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += (long long)gridDim.x * TPB) {
+    s0 += x[i] * y[i];
+    if (u) s1 += u[i] * v[i];
+  }
+  for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+  __shared__ double sh[2][TPB / 32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh[0][w] = s0; sh[1][w] = s1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s0 = 0; s1 = 0;
+    for (int i = 0; i < TPB / 32; ++i) { s0 += sh[0][i]; s1 += sh[1][i]; }
+    partial[2 * blockIdx.x] = s0; partial[2 * blockIdx.x + 1] = s1;
+  }
+}
+
+// fixed-order final sum of the per-CTA partials (deterministic)
+__global__ void k_dots_final(const double* __restrict__ partial, int nblk, double* __restrict__ out) {
+  if (threadIdx.x < 2) {
+    double s = 0;
+    for (int i = 0; i < nblk; ++i) s += partial[2 * i + threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+}
+
+inline int implicit_assemble(UnstrDev& u, double dt, double ux, double uy, int use_dir, int nsm, cudaStream_t st,
+                             long long& nlaunch, std::string& err) {
+  const size_t E = (size_t)u.E;
+  if (!u.bsr_val) {
+    UCK(cudaMalloc(&u.bsr_val, E * 36 * sizeof(double)));
+    UCK(cudaMalloc(&u.bsr_col, E * 4 * sizeof(int32_t)));
+    UCK(cudaMalloc(&u.dinv, E * 9 * sizeof(double)));
+    UCK(cudaMalloc(&u.mdt, E * sizeof(double)));
+    UCK(cudaMalloc(&u.work, E * 3 * 9 * sizeof(double)));
+    UCK(cudaMalloc(&u.dots, (size_t)(2 * nsm * 8 + 2) * sizeof(double)));
+    UCK(cudaMallocHost(&u.dots_host, 2 * sizeof(double)));
+  }
+  BsrArgs a;
+  a.X = u.X; a.neig = u.neig; a.nside = u.nside; a.val = u.bsr_val; a.col = u.bsr_col; a.dinv = u.dinv; a.mdt = u.mdt;
+  a.dt = dt; a.ux = ux; a.uy = uy; a.E = u.E; a.use_dir = use_dir;
+  const int grid = std::max(1, std::min((u.E + TPB - 1) / TPB, nsm * 8));
+  k_assemble_bsr<<<grid, TPB, 0, st>>>(a);
+  nlaunch++;
+  UCK(cudaGetLastError());
+  u.assembled = true;
+  return PAMG_OK;
+}
+
+// time loop of unstr_implicit (:214-387): told = tnew ; rhs = (M/dt) told ; solve (lhs + flux) tnew = rhs.
+// The reference inverts the dense matrix; here: BiCGStab right-preconditioned with the inverse diagonal blocks,
+// started from told, stopped at ||r|| <= tol ||rhs||.
+inline int implicit_step(UnstrDev& u, int ntime, int nits, double tol, int max_iters, int* iters_total, double* relres,
+                         int nsm, cudaStream_t st, long long& nlaunch, std::string& err) {
+  const int E = u.E;
+  const long long n = 3LL * E;
+  const int grid = std::max(1, std::min((E + TPB - 1) / TPB, nsm * 8));
+  const int gridv = (int)std::max(1LL, std::min((n + TPB - 1) / TPB, (long long)nsm * 8));
+  double* W = u.work;
+  double *b = W, *r = W + n, *rh = W + 2 * n, *p = W + 3 * n, *v = W + 4 * n, *s = W + 5 * n, *t = W + 6 * n, *y = W + 7 * n;
+  double* z = W + 8 * n;
+  auto dots = [&](const double* x1, const double* y1, const double* x2, const double* y2, double& d0, double& d1) -> int {
+    k_dots<<<gridv, TPB, 0, st>>>(x1, y1, x2, y2, n, u.dots + 2);
+    k_dots_final<<<1, 32, 0, st>>>(u.dots + 2, gridv, u.dots);
+    nlaunch += 2;
+    UCK(cudaMemcpyAsync(u.dots_host, u.dots, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    UCK(cudaStreamSynchronize(st));
+    d0 = u.dots_host[0]; d1 = u.dots_host[1];
+    return PAMG_OK;
+  };
+  int total = 0, rc;
+  double worst = 0.0;
+  for (int it = 0; it < ntime; ++it) {
+    for (int k = 0; k < nits; ++k) {
+      double* x = u.T[u.cur];
+      // the scheme is linear and rhs depends on told only: passes k > 0 of the reference's nonlinear loop re-solve
+      // the same system, which here starts converged and costs one residual evaluation
+      if (k == 0) {
+        UCK(cudaMemcpyAsync(u.told, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        k_block_apply<<<grid, TPB, 0, st>>>(u.dinv, u.mdt, u.told, b, E, 1); nlaunch++;
+      }
+      k_bsr_spmv<<<grid, TPB, 0, st>>>(u.bsr_val, u.bsr_col, x, b, r, E, 1); nlaunch++;
+      UCK(cudaMemcpyAsync(rh, r, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      UCK(cudaMemsetAsync(p, 0, (size_t)n * sizeof(double), st));
+      UCK(cudaMemsetAsync(v, 0, (size_t)n * sizeof(double), st));
+      double bb, rr;
+      if ((rc = dots(b, b, r, r, bb, rr)) != PAMG_OK) return rc;
+      const double stop2 = tol * tol * bb;
+      double rho = 1.0, alpha = 1.0, omega = 1.0;
+      int iter = 0;
+      while (rr > stop2 && iter < max_iters) {
+        double rho_new, dummy;
+        if ((rc = dots(rh, r, nullptr, nullptr, rho_new, dummy)) != PAMG_OK) return rc;
+        if (rho_new == 0.0 || omega == 0.0) break;   // breakdown: report what was reached
+        const double beta = (rho_new / rho) * (alpha / omega);
+        k_lincomb<<<gridv, TPB, 0, st>>>(p, 1.0, r, beta, p, -beta * omega, v, n); nlaunch++;
+        k_block_apply<<<grid, TPB, 0, st>>>(u.dinv, u.mdt, p, y, E, 0); nlaunch++;
+        k_bsr_spmv<<<grid, TPB, 0, st>>>(u.bsr_val, u.bsr_col, y, nullptr, v, E, 0); nlaunch++;
+        double rhv;
+        if ((rc = dots(rh, v, nullptr, nullptr, rhv, dummy)) != PAMG_OK) return rc;
+        if (rhv == 0.0) break;
+        alpha = rho_new / rhv;
+        k_lincomb<<<gridv, TPB, 0, st>>>(s, 1.0, r, -alpha, v, 0.0, nullptr, n); nlaunch++;
+        k_block_apply<<<grid, TPB, 0, st>>>(u.dinv, u.mdt, s, z, E, 0); nlaunch++;
+        k_bsr_spmv<<<grid, TPB, 0, st>>>(u.bsr_val, u.bsr_col, z, nullptr, t, E, 0); nlaunch++;
+        double ts, tt;
+        if ((rc = dots(t, s, t, t, ts, tt)) != PAMG_OK) return rc;
+        omega = (tt > 0.0) ? ts / tt : 0.0;
+        k_lincomb<<<gridv, TPB, 0, st>>>(x, 1.0, x, alpha, y, omega, z, n); nlaunch++;
+        k_lincomb<<<gridv, TPB, 0, st>>>(r, 1.0, s, -omega, t, 0.0, nullptr, n); nlaunch++;
+        if ((rc = dots(r, r, nullptr, nullptr, rr, dummy)) != PAMG_OK) return rc;
+        rho = rho_new;
+        ++iter;
+      }
+      UCK(cudaGetLastError());
+      total += iter;
+      const double rel = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+      worst = std::max(worst, rel);
+    }
+  }
+  if (iters_total) *iters_total = total;
+  if (relres) *relres = worst;
   return PAMG_OK;
 }
 

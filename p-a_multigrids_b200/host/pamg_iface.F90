@@ -157,6 +157,38 @@ module pamg_iface
       integer(c_int), value :: ntime, nits, njac_its, use_exact_minv, use_dir
     end function
 
+    ! unstr_implicit (transport_tri_unstr.F90:214-387): block-CSR assembly and solve on the device
+    integer(c_int) function pamg_implicit_assemble(handle, dt, u_x, u_y, use_dir) bind(c, name="pamg_implicit_assemble")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), value :: dt, u_x, u_y
+      integer(c_int), value :: use_dir
+    end function
+
+    integer(c_int) function pamg_implicit_get_bsr(handle, val, col) bind(c, name="pamg_implicit_get_bsr")
+      import :: c_int, c_ptr, c_double, c_int32_t
+      type(c_ptr), value :: handle
+      real(c_double), intent(out) :: val(9, 4, *)        ! block entries row-major inside a block
+      integer(c_int32_t), intent(out) :: col(4, *)       ! 0-based element of the block column, -1 = none
+    end function
+
+    integer(c_int) function pamg_implicit_apply(handle, x, y) bind(c, name="pamg_implicit_apply")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), intent(in) :: x(3, *)
+      real(c_double), intent(out) :: y(3, *)
+    end function
+
+    integer(c_int) function pamg_implicit_step(handle, ntime, nits, tol, max_iters, iters_total, relres) &
+        bind(c, name="pamg_implicit_step")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      integer(c_int), value :: ntime, nits, max_iters
+      real(c_double), value :: tol
+      integer(c_int), intent(out) :: iters_total
+      real(c_double), intent(out) :: relres
+    end function
+
     ! FINDInv (matrices.F90:1618), batched
     integer(c_int) function pamg_apply_local_minv(handle, n, batch, M, rhs, x, Minv, status) &
         bind(c, name="pamg_apply_local_minv")

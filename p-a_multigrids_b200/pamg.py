@@ -98,6 +98,10 @@ def lib():
         "pamg_unstr_upload": (ci, [vp, _f64]),
         "pamg_unstr_download": (ci, [vp, _f64]),
         "pamg_explicit_step": (ci, [vp, cd, cd, cd, cd, ci, ci, ci, ci, ci]),
+        "pamg_implicit_assemble": (ci, [vp, cd, cd, cd, ci]),
+        "pamg_implicit_get_bsr": (ci, [vp, vp, vp]),
+        "pamg_implicit_apply": (ci, [vp, _f64, _f64]),
+        "pamg_implicit_step": (ci, [vp, ci, ci, cd, ci, pint, pdbl]),
         "pamg_apply_local_minv": (ci, [vp, ci, ci, _f64, vp, vp, vp, vp]),
         "pamg_sync": (ci, [vp]),
         "pamg_event_record": (ci, [vp, ci]),
@@ -386,6 +390,33 @@ class SemiImplicitIterative:
         out = np.empty_like(t)
         self._ck(self.L.pamg_unstr_download(self.h, out))
         return out
+
+    # -- unstructured implicit (unstr_implicit, transport_tri_unstr.F90:18) --------------------------
+    def implicit_assemble(self, dt, u_x, u_y, use_dir=False):
+        """Assemble (mass/dt - stiffness + upwind flux) into block-CSR on the device (:270-364)."""
+        self._ck(self.L.pamg_implicit_assemble(self.h, dt, u_x, u_y, int(use_dir)))
+
+    def implicit_bsr(self):
+        """(val[E,4,3,3], col[E,4]) of the assembled operator; col is 0-based, -1 where a block is absent."""
+        val = np.zeros((self._E, 4, 3, 3)); col = np.zeros((self._E, 4), np.int32)
+        self._ck(self.L.pamg_implicit_get_bsr(self.h, _ptr(val), _ptr(col)))
+        return val, col
+
+    def implicit_apply(self, x):
+        x = np.ascontiguousarray(x, np.float64); y = np.empty_like(x)
+        self._ck(self.L.pamg_implicit_apply(self.h, x, y))
+        return y
+
+    def unstr_implicit(self, tnew, dt, u_x, u_y, ntime=2, nits=1, use_dir=False, tol=1e-13, max_iters=500):
+        """Time loop of unstr_implicit; returns (tnew, Krylov iterations in total, worst relative residual)."""
+        t = np.ascontiguousarray(tnew, np.float64)
+        self.implicit_assemble(dt, u_x, u_y, use_dir)
+        self._ck(self.L.pamg_unstr_upload(self.h, t))
+        it = C.c_int(0); rr = C.c_double(0.0)
+        self._ck(self.L.pamg_implicit_step(self.h, ntime, nits, tol, max_iters, C.byref(it), C.byref(rr)))
+        out = np.empty_like(t)
+        self._ck(self.L.pamg_unstr_download(self.h, out))
+        return out, it.value, rr.value
 
     def findinv(self, M, rhs=None):
         """Batched FINDInv (matrices.F90:1618): returns (Minv, x, status)."""

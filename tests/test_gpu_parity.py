@@ -247,6 +247,85 @@ def test_unstr_explicit_random_field_long(meshes):
     assert rel_l2(got, ref) <= TOL
 
 
+def _bsr_to_dense(val, col):
+    E = val.shape[0]
+    A = np.zeros((3 * E, 3 * E))
+    for e in range(E):
+        for b in range(4):
+            c = col[e, b]
+            if c >= 0:
+                A[3 * e:3 * e + 3, 3 * c:3 * c + 3] += val[e, b]
+    return A
+
+
+@pytest.mark.parametrize("name", ["split1", "test_sn2", "irregular", "900_ele"])
+@pytest.mark.parametrize("use_dir", [0, 1])
+def test_unstr_implicit_bsr_assembly(meshes, name, use_dir):
+    """Device block-CSR of unstr_implicit's lhs + flux (transport_tri_unstr.F90:270-364) == the oracle's dense matrix."""
+    mesh = meshes[name]
+    E = mesh.U
+    g = pamg.SemiImplicitIterative(pamg.default_params(), pamg.Mesh.synthetic(0, 1))
+    g.set_unstructured(mesh)
+    u, dt = (0.9, 0.3), 1e-2
+    g.implicit_assemble(dt, u[0], u[1], use_dir=bool(use_dir))
+    val, col = g.implicit_bsr()
+    assert np.array_equal(col[:, 0], np.arange(E))
+    A = np.zeros((3 * E, 3 * E)); M = np.zeros((3 * E, 3 * E))
+    orc.lib().orc_unstr_implicit_assemble(E, mesh.X, mesh.neig, mesh.fneig, u[0], u[1], dt, use_dir, A, M)
+    got = _bsr_to_dense(val, col)
+    assert np.max(np.abs(got - A)) <= 1e-13 * np.max(np.abs(A))
+    # inflow blocks exist exactly where the dense matrix couples to a neighbour
+    for e in range(E):
+        for f in range(3):
+            q = mesh.neig[e, f]
+            if q:
+                assert (col[e, 1 + f] == q - 1) == bool(np.any(A[3 * e:3 * e + 3, 3 * (q - 1):3 * q]))
+            else:
+                assert col[e, 1 + f] == -1
+    x = rng_field((E, 3), 11)
+    y = g.implicit_apply(x)
+    assert rel_l2(y.ravel(), A @ x.ravel()) <= TOL
+
+
+@pytest.mark.parametrize("name,use_dir,u", [("split1", 1, (0.4, -0.7)), ("irregular", 0, (0.9, 0.3)),
+                                            ("900_ele", 1, (0.9, 0.0)), ("test_sn2", 0, (-0.5, 0.8))])
+def test_unstr_implicit_time_loop(meshes, name, use_dir, u):
+    """Krylov solve on the device block-CSR vs the reference's dense FINDInv solve (:366-378), 3 time steps."""
+    mesh = meshes[name]
+    E = mesh.U
+    g = pamg.SemiImplicitIterative(pamg.default_params(), pamg.Mesh.synthetic(0, 1))
+    g.set_unstructured(mesh)
+    area = 0.5 * np.abs((mesh.X[:, 0, 0] - mesh.X[:, 2, 0]) * (mesh.X[:, 1, 1] - mesh.X[:, 2, 1])
+                        - (mesh.X[:, 0, 1] - mesh.X[:, 2, 1]) * (mesh.X[:, 1, 0] - mesh.X[:, 2, 0]))
+    dt = 2.0 * float(np.sqrt(area.min()))          # CFL ~ 2: out of reach of the explicit step
+    T0 = rng_field((E, 3), 7)
+    ref = T0.copy()
+    if E <= 100:
+        assert orc.lib().orc_unstr_implicit(E, mesh.X, mesh.neig, mesh.fneig, u[0], u[1], dt, 3, 1, use_dir, ref) == 0
+    else:   # the oracle's O(N^3) FINDInv is too slow here; LAPACK on the oracle's own matrices (pinned equal on CPU)
+        A = np.zeros((3 * E, 3 * E)); M = np.zeros((3 * E, 3 * E))
+        orc.lib().orc_unstr_implicit_assemble(E, mesh.X, mesh.neig, mesh.fneig, u[0], u[1], dt, use_dir, A, M)
+        r = T0.ravel().copy()
+        for _ in range(3):
+            r = np.linalg.solve(A, M @ r)
+        ref = r.reshape(E, 3)
+    got, iters, relres = g.unstr_implicit(T0, dt, u[0], u[1], ntime=3, nits=1, use_dir=bool(use_dir), tol=1e-13)
+    assert relres <= 1e-13 and 0 < iters < 3 * 500
+    assert rel_l2(got, ref) <= 1e-10
+    # nits = 2 re-solves the same linear system: same answer, no extra Krylov iterations
+    got2, iters2, _ = g.unstr_implicit(T0, dt, u[0], u[1], ntime=3, nits=2, use_dir=bool(use_dir), tol=1e-13)
+    assert rel_l2(got2, ref) <= 1e-10 and iters2 == iters
+
+
+def test_unstr_implicit_errors(meshes):
+    g = pamg.SemiImplicitIterative(pamg.default_params(), pamg.Mesh.synthetic(0, 1))
+    L = pamg.lib()
+    assert L.pamg_implicit_assemble(g.h, 1e-2, 1.0, 0.0, 0) == pamg.ERR_ARG          # no unstructured mesh yet
+    g.set_unstructured(meshes["split0"])
+    assert L.pamg_implicit_step(g.h, 1, 1, 1e-12, 10, None, None) == pamg.ERR_STATE  # not assembled
+    assert L.pamg_implicit_assemble(g.h, 0.0, 1.0, 0.0, 0) == pamg.ERR_ARG
+
+
 @pytest.mark.parametrize("n", [3, 4, 6])
 def test_batched_local_inverse(n):
     g = pamg.SemiImplicitIterative(pamg.default_params(), pamg.Mesh.synthetic(0, 1))

@@ -206,3 +206,55 @@ def test_read_msh_facts_and_neighbours(name, tmp_path):
     if name == "900_ele":
         assert np.allclose(0.5 * np.abs(det), 1.125)
         assert sorted(set(reg)) == [9, 10]
+
+
+def _implicit_dense(m, u, dt, use_dir):
+    E = m["X"].shape[0]
+    fneig, _ = orc.neig_data(m["neig"], m["dir"])
+    A = np.zeros((3 * E, 3 * E)); M = np.zeros((3 * E, 3 * E))
+    orc.lib().orc_unstr_implicit_assemble(E, np.ascontiguousarray(m["X"]), np.ascontiguousarray(m["neig"]), fneig,
+                                          u[0], u[1], dt, use_dir, A, M)
+    return A, M, fneig
+
+
+@pytest.mark.parametrize("name", ["split1", "test_sn2"])
+@pytest.mark.parametrize("use_dir", [0, 1])
+def test_unstr_implicit_operator_invariants(name, use_dir, tmp_path):
+    """The assembled unstr_implicit operator (transport_tri_unstr.F90:270-364): pure advection keeps constants on
+    elements away from the boundary ((A - M/dt) 1 = 0 there) and is conservative (columns of elements without an
+    outflow boundary face sum to the mass column sum)."""
+    m = orc.read_msh(write_msh(name, str(tmp_path / (name + ".msh"))))
+    u, dt = (0.9, 0.3), 1e-2
+    A, M, _ = _implicit_dense(m, u, dt, use_dir)
+    E = m["X"].shape[0]
+    interior = np.repeat(np.all(m["neig"] != 0, axis=1), 3)
+    assert interior.any() or name == "test_sn2"
+    r = (A - M) @ np.ones(3 * E)
+    assert np.max(np.abs(r[interior]), initial=0.0) <= 1e-14
+    assert np.max(np.abs(r[~interior])) > 1e-3          # inflow boundary rows do lose the constant (t_bc = 0)
+    c = np.ones(3 * E) @ (A - M)
+    assert np.max(np.abs(c[interior]), initial=0.0) <= 1e-14
+    # mass/dt block: (A/12dt)(1 + delta), row sums = area/(3 dt)
+    X = m["X"]
+    area = 0.5 * np.abs((X[:, 0, 0] - X[:, 2, 0]) * (X[:, 1, 1] - X[:, 2, 1]) - (X[:, 0, 1] - X[:, 2, 1]) * (X[:, 1, 0] - X[:, 2, 0]))
+    assert np.allclose(M @ np.ones(3 * E), np.repeat(area / (3 * dt), 3), rtol=1e-13)
+
+
+def test_unstr_implicit_solve_is_backward_euler(tmp_path):
+    """orc_unstr_implicit == dense solve of (lhs + flux) tnew = (M/dt) told per step, and a second nonlinear pass
+    (nits = 2) changes nothing because the scheme is linear (:247-387)."""
+    m = orc.read_msh(write_msh("split1", str(tmp_path / "s.msh")))
+    u, dt = (0.4, -0.7), 5e-3
+    A, M, fneig = _implicit_dense(m, u, dt, 1)
+    E = m["X"].shape[0]
+    rng = np.random.default_rng(5)
+    T0 = rng.random(3 * E)
+    ref = T0.copy()
+    for _ in range(3):
+        ref = np.linalg.solve(A, M @ ref)
+    for nits in (1, 2):
+        T = T0.copy()
+        rc = orc.lib().orc_unstr_implicit(E, np.ascontiguousarray(m["X"]), np.ascontiguousarray(m["neig"]), fneig,
+                                          u[0], u[1], dt, 3, nits, 1, T)
+        assert rc == 0
+        assert np.linalg.norm(T - ref) <= 1e-12 * np.linalg.norm(ref)
