@@ -12,6 +12,7 @@ n_smooth = 4 Jacobi sweeps, each preceded by update_overlaps.  Fields (403 MB ea
 the 126 MB L2, so no flush is needed between timed iterations.
 """
 import argparse
+import ctypes as C
 import importlib
 import json
 import os
@@ -313,6 +314,34 @@ def main():
         extra["unstr_explicit_pass"] = {"elements": um.U, "ms": t_ms, "dof_updates_per_s": 3 * um.U / (t_ms * 1e-3),
                                         "algorithmic_GBps": 144.0 * um.U / (t_ms * 1e-3) / 1e9, "bytes_per_element": 144.0,
                                         "note": "fits in L2 (1M elements = 150 MB of streams): not an HBM number"}
+
+    # unstructured implicit step (unstr_implicit): block-CSR assembly + BiCGStab on the same 4^10 triangles
+    if rank == 0:
+        area = 0.5 * np.abs((um.X[:, 0, 0] - um.X[:, 2, 0]) * (um.X[:, 1, 1] - um.X[:, 2, 1])
+                            - (um.X[:, 0, 1] - um.X[:, 2, 1]) * (um.X[:, 1, 0] - um.X[:, 2, 0]))
+        dt_i = 4.0 * float(np.sqrt(area.min()))
+        g.implicit_assemble(dt_i, 0.9, 0.3, use_dir=True)                             # warm-up
+        g.sync()
+        g.event_record(8)
+        for _ in range(10):
+            g.implicit_assemble(dt_i, 0.9, 0.3, use_dir=True)
+        g.event_record(9)
+        g.sync()
+        t_asm = g.elapsed_ms(8, 9) / 10.0
+        g._ck(g.L.pamg_unstr_upload(g.h, T0))
+        it = C.c_int(0); rr = C.c_double(0.0)
+        g._ck(g.L.pamg_implicit_step(g.h, 1, 1, 1e-10, 400, C.byref(it), C.byref(rr)))   # warm-up
+        g._ck(g.L.pamg_unstr_upload(g.h, T0))
+        g.sync()
+        g.event_record(8)
+        g._ck(g.L.pamg_implicit_step(g.h, 1, 1, 1e-10, 400, C.byref(it), C.byref(rr)))
+        g.event_record(9)
+        g.sync()
+        t_solve = g.elapsed_ms(8, 9)
+        extra["unstr_implicit"] = {"elements": um.U, "assemble_ms": t_asm,
+                                   "assemble_GBps": 456.0 * um.U / (t_asm * 1e-3) / 1e9, "assemble_bytes_per_element": 456.0,
+                                   "solve_ms": t_solve, "bicgstab_iters": it.value, "relres": rr.value, "cfl": 4.0,
+                                   "note": "reference: dense (3E)^2 FINDInv, impossible at this size"}
 
     # ---- V-cycle time to 1e-8 (second half of the BASELINE metric) ----------------------------------------
     vc = None
