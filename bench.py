@@ -32,6 +32,13 @@ METRIC = "DG DOF-updates/s per smoother sweep"
 UNIT = "DOF-updates/s"
 
 
+KERNEL_NAMES = {
+    "win": "k_element_win<JACOBI,face> (ring of 8 field tiles in shared memory via 1-D TMA, all neighbours from the ring)",
+    "tma1d": "k_element_tma<JACOBI,face> (pipelined 1-D TMA tiles, vertical neighbour by global load)",
+    "stream": "k_stream<JACOBI,face> (row streaming)", "direct2": "k_element_direct2<JACOBI,face>", "direct": "k_element<JACOBI,face>",
+}
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -375,7 +382,7 @@ def main():
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_element_tma<JACOBI,face> (pipelined 1-D TMA tiles)", "kernel_avg_ms": kern_avg_ms,
+                         "traffic": None, "kernel": KERNEL_NAMES.get(os.environ.get("PAMG_KERNEL", "win"), os.environ.get("PAMG_KERNEL")), "kernel_avg_ms": kern_avg_ms,
                          "kernel_launches_timed": kern_n, "algorithmic_bytes_per_launch": BYTES_PER_DOF_JACOBI * ndof,
                          "peak_source": peak_src,
                          "whole_step_frac": (BYTES_PER_DOF_JACOBI * ndof * NSMOOTH * args.steps / (ms * 1e-3) / 1e9) / peak},
@@ -386,8 +393,9 @@ def main():
         try:   # DRAM bytes of the dominant kernel from the committed ncu --set full capture (per launch)
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
                 tr = json.load(f)
-            line["roofline"]["traffic"] = tr.get("k_element_tma_jacobi_face_dram_bytes_per_launch")
-            line["roofline"]["traffic_source"] = tr.get("source")
+            if os.environ.get("PAMG_KERNEL", "win") == tr.get("kernel_mode"):
+                line["roofline"]["traffic"] = tr.get("jacobi_face_dram_bytes_per_launch")
+                line["roofline"]["traffic_source"] = tr.get("source")
         except Exception:
             pass
         if not args.no_cpu_baseline:

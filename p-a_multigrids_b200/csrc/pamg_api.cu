@@ -87,7 +87,8 @@ struct pamg_handle {
   double* out3_host = nullptr;    // pinned
   double* scratch = nullptr; size_t scratch_bytes = 0;  // L2 flush
   double* stage = nullptr; size_t stage_bytes = 0;      // pinned staging for host-buffer entry points
-  int kernel_mode = 1;  // 1 pipelined 1-D TMA tiles (default), 2 row-streaming, 0 direct loads; PAMG_KERNEL=direct|tma1d|stream
+  int kernel_mode = 4;  // 4 window kernel (default; 1-D TMA tile ring, all neighbours from shared memory), 1 pipelined 1-D TMA tiles,
+                        // 2 row-streaming, 3 branch-free direct, 0 direct loads; PAMG_KERNEL=win|tma1d|stream|direct2|direct
   int* counters = nullptr;
   bool capturing = false;   // stream capture in progress: no synchronisation, no per-launch error polling
   bool use_graph = true;    // replay the V-cycle as a CUDA graph from the second cycle on (PAMG_GRAPH=0 disables)
@@ -331,7 +332,21 @@ int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout,
     if (h->p.face_terms) k_stream<MODE, true><<<sgrid, SW, 0, h->stream>>>(sa);
     else k_stream<MODE, false><<<sgrid, SW, 0, h->stream>>>(sa);
     if (MODE == MODE_RESID) h->last_partials = sgrid;
-  } else if ((MODE != MODE_GS || h->gs_tma) && (h->kernel_mode == 1 || h->kernel_mode == 2) && L.C >= TPB) {
+  } else if ((MODE != MODE_GS || h->gs_tma) && h->kernel_mode == 4 && L.C >= TPB && L.s <= 8) {
+    // (a vertical neighbour is up to 2^(s+1) children away: the 8-tile ring covers s <= 8)
+    // window kernel: ring of 8 field tiles in shared memory, every neighbour value read from it
+    auto kern = h->p.face_terms ? k_element_win<MODE, true> : k_element_win<MODE, false>;
+    static int resident_win[2] = {0, 0};
+    int& resident = resident_win[h->p.face_terms ? 1 : 0];
+    if (resident == 0) {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM_BYTES));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, TPB, WIN_SMEM_BYTES));
+      if (resident < 1) resident = 1;
+    }
+    const int tgrid = (int)std::max(1ll, std::min(L.nelem / TPB, (long long)h->nsm * resident));
+    kern<<<tgrid, TPB, WIN_SMEM_BYTES, h->stream>>>(a);
+    if (MODE == MODE_RESID) h->last_partials = tgrid;
+  } else if ((MODE != MODE_GS || h->gs_tma) && (h->kernel_mode == 1 || h->kernel_mode == 2 || h->kernel_mode == 4) && L.C >= TPB) {
     // 1-D TMA tiles: contiguous 6 KB spans through shared memory (pamg_kernels.cuh)
     // contiguous tile ranges per CTA: exactly one wave of resident CTAs (occupancy from the runtime)
     auto kern = h->p.face_terms ? k_element_tma<MODE, true> : k_element_tma<MODE, false>;
@@ -659,6 +674,7 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
     else if (e && !strcmp(e, "tma1d")) h->kernel_mode = 1;
     else if (e && !strcmp(e, "stream")) h->kernel_mode = 2;
     else if (e && !strcmp(e, "direct2")) h->kernel_mode = 3;
+    else if (e && !strcmp(e, "win")) h->kernel_mode = 4;
     const char* gr = getenv("PAMG_GRAPH");
     if (gr && gr[0] == '0') h->use_graph = false;
     const char* gn = getenv("PAMG_GRAPH_NCCL");

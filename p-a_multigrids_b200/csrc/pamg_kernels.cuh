@@ -602,6 +602,176 @@ __global__ void __launch_bounds__(TPB, 3) k_element_tma(ElemArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Window kernel: like k_element_tma, but the field tiles live in a RING of WIN_NT tiles addressed by the global
+// child index (child c sits at sT[(c mod 2048) * 3]), and tile t is only computed once tiles t-2 .. t+2 have
+// landed.  A vertical neighbour is at most one row (< 512 children = 2 tiles) away, so ALL six neighbour values
+// of a child come from shared memory: no global load on the critical path of an interior child.  The strip
+// entries of the few children on parent faces are fetched one tile ahead into registers.  The rhs tile ring is
+// also the output staging area: a thread overwrites its own three rhs values with its result and the tile
+// leaves through one bulk store from that slot.
+constexpr int WIN_NT = 8;                    // field tiles resident (power of two)
+constexpr int WIN_NB = 4;                    // rhs / output tiles (power of two)
+constexpr int WIN_CH = WIN_NT * TPB;
+constexpr size_t WIN_SMEM_BYTES = sizeof(double) * 3 * TPB * (WIN_NT + WIN_NB) + 8 * (WIN_NT + WIN_NB) + 64;
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+template <int MODE, bool FACE>
+__global__ void __launch_bounds__(TPB, 3) k_element_win(ElemArgs a) {
+  extern __shared__ __align__(128) unsigned char dsm[];   // WIN_SMEM_BYTES
+  double* sT = reinterpret_cast<double*>(dsm);
+  double* sB = sT + 3 * WIN_CH;
+  uint64_t* barT = reinterpret_cast<uint64_t*>(sB + 3 * TPB * WIN_NB);
+  uint64_t* barB = barT + WIN_NT;
+  __shared__ __align__(16) double sPC[NPC];
+  __shared__ int sIdx[8];                                 // strip_of[0..2], hmap[4..6] of the loaded parent
+  const int s = a.s, twos = 2 * s, b = 2 << s, S = 1 << s;
+  const long long Cmask = (1ll << twos) - 1;
+  const int tid = threadIdx.x;
+  constexpr uint32_t TILE_BYTES = 3 * TPB * sizeof(double);
+  double acc_sum = 0.0, acc_abs = 0.0, acc_max = 0.0;
+  if (tid == 0) {
+    for (int i = 0; i < WIN_NT + WIN_NB; ++i) mbar_init(&barT[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long ntiles = a.nelem / TPB;                 // the host only launches this kernel when TPB | 4^s
+  const long long per = (ntiles + gridDim.x - 1) / gridDim.x;
+  const long long tbeg = (long long)blockIdx.x * per, tend = min(ntiles, tbeg + per);
+  const long long tlo = max(0ll, tbeg - 2), thi = min(ntiles, tend + 2);
+
+  auto issueT = [&](long long tile) {   // tid 0 only
+    const int sl = (int)(tile & (WIN_NT - 1));
+    mbar_expect_tx(&barT[sl], TILE_BYTES);
+    tma_load_1d(sT + sl * 3 * TPB, a.Tin + tile * 3 * TPB, TILE_BYTES, &barT[sl]);
+  };
+  auto issueB = [&](long long tile) {
+    const int sl = (int)((tile - tbeg) & (WIN_NB - 1));
+    mbar_expect_tx(&barB[sl], TILE_BYTES);
+    tma_load_1d(sB + sl * 3 * TPB, a.rhs + tile * 3 * TPB, TILE_BYTES, &barB[sl]);
+  };
+  if (tid == 0 && tbeg < tend) {
+    for (long long t = tlo; t < min(thi, tbeg + 5); ++t) issueT(t);
+    for (long long t = tbeg; t < min(tend, tbeg + 2); ++t) issueB(t);
+  }
+
+  int u_loaded = -1;
+  // numbering of a tile's child and, for children on parent faces, their strip entries
+  struct Prep { int r, ipos, len; double h1a, h1b, h2a, h2b; };
+  auto prepare = [&](long long tile, Prep& p) {
+    p.r = 2; p.ipos = 2; p.len = 3; p.h1a = 0.0; p.h1b = 0.0; p.h2a = 0.0; p.h2b = 0.0;
+    if (tile >= tend) return;
+    const long long g = tile * TPB + tid;
+    child_from_ele0((int)(g & Cmask), s, p.r, p.ipos, p.len);
+    if (!FACE || !(p.ipos & 1) || (MODE == MODE_GS && a.colour != 1)) return;
+    const bool f1 = p.r == 1, side = p.ipos == 1 || p.ipos == p.len;
+    if (f1 | side) {
+      const int u = (int)(g >> twos);
+      const bool same = u == u_loaded;
+      if (f1) {       // child face 1 on parent side 1, position ipos/2
+        const int strip = same ? sIdx[0] : __ldg(a.strip_of + u * 3), hm = same ? sIdx[4] : __ldg(a.hmap + u * 3);
+        const double* e = a.ovl + ((size_t)strip * S + (p.ipos >> 1)) * 3;
+        p.h1a = __ldg(e + (hm & 3)); p.h1b = __ldg(e + (hm >> 2));
+      }
+      if (side) {     // first child of a row: face 2 on parent side 3; last child: face 3 on parent side 2
+        const int mf = (p.ipos == 1) ? 2 : 1;
+        const int strip = same ? sIdx[mf] : __ldg(a.strip_of + u * 3 + mf), hm = same ? sIdx[4 + mf] : __ldg(a.hmap + u * 3 + mf);
+        const double* e = a.ovl + ((size_t)strip * S + (p.r - 1)) * 3;
+        p.h2a = __ldg(e + (hm & 3)); p.h2b = __ldg(e + (hm >> 2));
+      }
+    }
+  };
+  Prep cur, nxt;
+  prepare(tbeg, cur);
+  for (long long tile = tbeg; tile < tend; ++tile) {
+    const int it = (int)(tile - tbeg);
+    const long long g0 = tile * TPB;
+    if (tid == 0) {
+      if (tile + 5 < thi) issueT(tile + 5);          // slot of tile-3: last read while tile-1 was computed
+      if (tile + 2 < tend) { tma_store_wait_read1(); issueB(tile + 2); }   // slot of tile-2: its store has been read
+    }
+    {
+      const int u_tile = (int)(g0 >> twos);          // uniform over the CTA (a tile never spans two parents)
+      if (u_tile != u_loaded) {
+        __syncthreads();
+        if (tid < NPC) sPC[tid] = __ldg(a.pc + (size_t)u_tile * NPC + tid);
+        else if (tid < NPC + 3) sIdx[tid - NPC] = __ldg(a.strip_of + u_tile * 3 + (tid - NPC));
+        else if (tid < NPC + 6) sIdx[4 + tid - NPC - 3] = __ldg(a.hmap + u_tile * 3 + (tid - NPC - 3));
+        __syncthreads();
+        u_loaded = u_tile;
+      }
+    }
+    prepare(tile + 1, nxt);
+    if (it == 0) {
+      for (long long tw = tlo; tw <= min(tile + 2, thi - 1); ++tw) mbar_wait(&barT[tw & (WIN_NT - 1)], (uint32_t)(((tw - tlo) >> 3) & 1));
+    } else if (tile + 2 < thi) {
+      mbar_wait(&barT[(tile + 2) & (WIN_NT - 1)], (uint32_t)(((tile + 2 - tlo) >> 3) & 1));
+    }
+    mbar_wait(&barB[it & (WIN_NB - 1)], (uint32_t)((it / WIN_NB) & 1));
+    double* bb = sB + (it & (WIN_NB - 1)) * 3 * TPB + tid * 3;
+    {
+      const int cw = (int)(g0 & (WIN_CH - 1)) + tid;           // my slot in the ring (g0 is a multiple of TPB)
+      const double* t = sT + cw * 3;
+      const double T1 = t[0], T2 = t[1], T3 = t[2];
+      const bool up = cur.ipos & 1;
+      double o1, o2, o3;
+      if (MODE == MODE_GS && (int)up != a.colour) {
+        o1 = T1; o2 = T2; o3 = T3;      // other colour: written back unchanged (in-place pass)
+      } else {
+        FaceIn fi;
+        int bmask = 0;
+        bool interior = true;
+        const ParentRegs& P = *reinterpret_cast<const ParentRegs*>(sPC);
+        if (FACE) {
+          fi.pen1 = P.pi1; fi.pen2 = P.pi2; fi.pen3 = P.pi3;
+          // vertical neighbour: child above for a down child, child below for an up child (splitting.F90:749-769)
+          const int dv = up ? (2 * cur.r - b - 2) : (b - 2 * cur.r);
+          const double* tv = sT + ((cw + dv) & (WIN_CH - 1)) * 3;
+          fi.n1a = tv[2]; fi.n1b = tv[0];
+          // face 2 looks left for an up child and right for a down child, face 3 the other way
+          const double* tl = sT + ((cw - 1) & (WIN_CH - 1)) * 3;
+          const double* tr = sT + ((cw + 1) & (WIN_CH - 1)) * 3;
+          const double* t2 = up ? tl : tr;
+          const double* t3 = up ? tr : tl;
+          fi.n2a = t2[1]; fi.n2b = t2[2];
+          fi.n3a = t3[0]; fi.n3b = t3[1];
+          if (up && (cur.r == 1 || cur.ipos == 1 || cur.ipos == cur.len)) {   // child on a parent face (rare)
+            interior = false;
+            if (cur.r == 1) { fi.n1a = cur.h1a; fi.n1b = cur.h1b; fi.pen1 = P.px1; bmask |= 1; }
+            if (cur.ipos == 1) { fi.n2a = cur.h2a; fi.n2b = cur.h2b; fi.pen2 = P.px2; bmask |= 2; }
+            if (cur.ipos == cur.len) {
+              if (cur.len == 1) halo_pair(a, (int)(g0 >> twos), 1, cur.r - 1, S, fi.n3a, fi.n3b);   // apex child: both sides
+              else { fi.n3a = cur.h2a; fi.n3b = cur.h2b; }
+              fi.pen3 = P.px3; bmask |= 4;
+            }
+          }
+        }
+        if (FACE && MODE != MODE_RICH) {
+          const Folded& F = *reinterpret_cast<const Folded*>(sPC + PC_FOLD + (up ? 0 : 16));
+          elem_apply_folded<MODE>(F, sPC + PC_DPEN, bmask, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
+        } else {
+          elem_apply_regs<MODE, FACE>(P, up, interior, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.omega, a.rsign, o1, o2, o3);
+        }
+      }
+      bb[0] = o1; bb[1] = o2; bb[2] = o3;
+      if (MODE == MODE_RESID) {
+        acc_sum += o1 * o1 + o2 * o2 + o3 * o3;
+        acc_abs = fmax(acc_abs, fmax(fabs(o1), fmax(fabs(o2), fabs(o3))));
+        acc_max = fmax(acc_max, fmax(o1, fmax(o2, o3)));
+      }
+    }
+    fence_async_smem();
+    __syncthreads();                       // result tile complete; every read of the window for this tile is done
+    if (tid == 0) {
+      tma_store_1d(a.Tout + g0 * 3, sB + (it & (WIN_NB - 1)) * 3 * TPB, TILE_BYTES);
+      tma_store_commit();
+    }
+    cur = nxt;
+  }
+  if (tid == 0) tma_store_wait_all();
+  if (MODE == MODE_RESID) block_partial(acc_sum, acc_abs, acc_max, a.partial + (size_t)3 * a.partial_off);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Branch-free direct kernel: thread per child, every load of the child (own values, rhs, the three
 // neighbours) is issued before the first use so that one memory latency is exposed per child instead of a
 // chain of two or three; children on a parent face patch their neighbour values from the halo strips in a
