@@ -338,13 +338,18 @@ __global__ void __launch_bounds__(TPB) k_dots(const double* __restrict__ x, cons
   }
 }
 
-// fixed-order final sum of the per-CTA partials (deterministic)
-__global__ void k_dots_final(const double* __restrict__ partial, int nblk, double* __restrict__ out) {
-  if (threadIdx.x < 2) {
-    double s = 0;
-    for (int i = 0; i < nblk; ++i) s += partial[2 * i + threadIdx.x];
-    out[threadIdx.x] = s;
+// fixed-order final sum of the per-CTA partials (deterministic): strided partial sums, then a shared-memory tree
+__global__ void __launch_bounds__(256) k_dots_final(const double* __restrict__ partial, int nblk, double* __restrict__ out) {
+  __shared__ double sh[2][256];
+  double s0 = 0, s1 = 0;
+  for (int i = threadIdx.x; i < nblk; i += 256) { s0 += partial[2 * i]; s1 += partial[2 * i + 1]; }
+  sh[0][threadIdx.x] = s0; sh[1][threadIdx.x] = s1;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) { sh[0][threadIdx.x] += sh[0][threadIdx.x + w]; sh[1][threadIdx.x] += sh[1][threadIdx.x + w]; }
+    __syncthreads();
   }
+  if (threadIdx.x < 2) out[threadIdx.x] = sh[threadIdx.x][0];
 }
 
 inline int implicit_assemble(UnstrDev& u, double dt, double ux, double uy, int use_dir, int nsm, cudaStream_t st,
@@ -384,7 +389,7 @@ inline int implicit_step(UnstrDev& u, int ntime, int nits, double tol, int max_i
   double* z = W + 8 * n;
   auto dots = [&](const double* x1, const double* y1, const double* x2, const double* y2, double& d0, double& d1) -> int {
     k_dots<<<gridv, TPB, 0, st>>>(x1, y1, x2, y2, n, u.dots + 2);
-    k_dots_final<<<1, 32, 0, st>>>(u.dots + 2, gridv, u.dots);
+    k_dots_final<<<1, 256, 0, st>>>(u.dots + 2, gridv, u.dots);
     nlaunch += 2;
     UCK(cudaMemcpyAsync(u.dots_host, u.dots, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     UCK(cudaStreamSynchronize(st));
