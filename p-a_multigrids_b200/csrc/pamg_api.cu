@@ -99,6 +99,7 @@ struct pamg_handle {
   bool fused_halo = false;  // PAMG_FUSED_HALO=1: sweeps write the next sweep's strips themselves (measured slower: the extra work
                             // of the few children on parent faces delays the per-tile barrier; profiles/README.md)
   bool gs_tma = true;   // coloured GS pass through the TMA tile kernel (PAMG_GS=direct selects the direct kernel)
+  bool gs_fused = true; // both colours in one pass (k_gs_win); PAMG_GS=twopass keeps the two in-place passes
   // per-kernel timing (element kernels only)
   bool profiling = false;
   std::vector<cudaEvent_t> pev;  // pairs
@@ -388,6 +389,33 @@ int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout,
   return PAMG_OK;
 }
 
+// coloured Gauss-Seidel sweep in one pass (k_gs_win), out of place
+bool gs_fused_ok(const pamg_handle* h, const LevelDev& L) {
+  return h->gs_fused && h->kernel_mode == 4 && h->p.face_terms && L.C >= TPB && L.s <= 8;
+}
+
+int launch_gs_fused(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout) {
+  ElemArgs a;
+  a.Tin = Tin; a.Tout = Tout; a.rhs = L.rhs; a.ovl = L.ovlb[L.ovl_cur]; a.pc = L.pc; a.strip_of = h->strip_of; a.hmap = h->hmap;
+  a.ovl_next = nullptr; a.dst_strip = h->dst_strip; a.rev = h->rev;
+  a.partial = h->partial; a.omega = h->p.omega; a.rsign = (double)h->p.residual_sign; a.nelem = L.nelem; a.s = L.s;
+  a.colour = 1; a.split_boundary = 0; a.partial_off = 0;
+  static int resident = 0;
+  if (resident == 0) {
+    CK(cudaFuncSetAttribute(k_gs_win, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GSW_SMEM_BYTES));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_gs_win, TPB, GSW_SMEM_BYTES));
+    if (resident < 1) resident = 1;
+  }
+  const bool prof = h->profiling && h->pev_used + 2 <= (int)h->pev.size();
+  if (prof) CK(cudaEventRecord(h->pev[h->pev_used], h->stream));
+  const int tgrid = (int)std::max(1ll, std::min(L.nelem / TPB, (long long)h->nsm * resident));
+  k_gs_win<<<tgrid, TPB, GSW_SMEM_BYTES, h->stream>>>(a);
+  if (prof) { CK(cudaEventRecord(h->pev[h->pev_used + 1], h->stream)); h->pev_used += 2; }
+  h->launches++;
+  CK(cudaGetLastError());
+  return PAMG_OK;
+}
+
 int do_smooth(pamg_handle* h, int level, int solver, int nsweeps) {
   LevelDev& L = h->lev[level - 1];
   if (level == 1 && !L.rhs_valid) { int rc = launch_build_rhs(h); if (rc) return rc; }
@@ -410,11 +438,19 @@ int do_smooth(pamg_handle* h, int level, int solver, int nsweeps) {
     } else if (solver == 3 || solver == 4) {
       // two-colour ordering of the reference's Gauss-Seidel sweep: all down children, then all up children;
       // values across parent faces stay lagged through the halo strips exactly as at :647-655.
-      if (sw == nsweeps - 1 && h->p.keep_tnew_gs) { rc = materialise_tnew(h, L); if (rc) return rc; }  // keep tracer%tnew observable
-      rc = launch_element<MODE_GS>(h, L, L.T[L.cur], L.T[L.cur], 0, grid, false);
-      if (rc) return rc;
-      rc = launch_element<MODE_GS>(h, L, L.T[L.cur], L.T[L.cur], 1, grid, fused);   // all children on parent faces are "up"
-      if (rc) return rc;
+      if (gs_fused_ok(h, L)) {
+        // both colours in one pass over memory, written to the other buffer (which then holds tracer%tnew, as for Jacobi)
+        rc = launch_gs_fused(h, L, L.T[L.cur], L.T[L.cur ^ 1]);
+        if (rc) return rc;
+        L.cur ^= 1;
+        L.tnew_alias = false;
+      } else {
+        if (sw == nsweeps - 1 && h->p.keep_tnew_gs) { rc = materialise_tnew(h, L); if (rc) return rc; }  // keep tracer%tnew observable
+        rc = launch_element<MODE_GS>(h, L, L.T[L.cur], L.T[L.cur], 0, grid, false);
+        if (rc) return rc;
+        rc = launch_element<MODE_GS>(h, L, L.T[L.cur], L.T[L.cur], 1, grid, fused);   // all children on parent faces are "up"
+        if (rc) return rc;
+      }
     } else {
       return fail(h, PAMG_ERR_ARG, "solver must be 1 (Jacobi), 2 (Richardson) or 3 (Gauss-Seidel)");
     }
@@ -684,7 +720,8 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
     const char* fh = getenv("PAMG_FUSED_HALO");
     if (fh && fh[0] == '1') h->fused_halo = true;
     const char* g = getenv("PAMG_GS");
-    if (g && !strcmp(g, "direct")) h->gs_tma = false;
+    if (g && !strcmp(g, "direct")) { h->gs_tma = false; h->gs_fused = false; }
+    if (g && !strcmp(g, "twopass")) h->gs_fused = false;
   }
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return PAMG_ERR_CUDA; }
   cudaDeviceProp prop;
@@ -817,7 +854,7 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
         ap.n_split = h->lev[lvl - 1].s;
         ap.multi_levels = h->p.multi_levels - lvl + 1;
         pamg_handle* g = new pamg_handle();
-        g->p = ap; g->device = h->device; g->nsm = h->nsm; g->kernel_mode = h->kernel_mode; g->gs_tma = h->gs_tma;
+        g->p = ap; g->device = h->device; g->nsm = h->nsm; g->kernel_mode = h->kernel_mode; g->gs_tma = h->gs_tma; g->gs_fused = h->gs_fused;
         g->stream = h->stream; g->shared_stream = true; g->level_offset = lvl - 1;
         for (auto& ev : g->ev) cudaEventCreate(&ev);
         cudaMalloc(&g->out3, 3 * sizeof(double));

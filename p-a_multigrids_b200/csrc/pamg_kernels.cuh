@@ -772,6 +772,183 @@ __global__ void __launch_bounds__(TPB, 3) k_element_win(ElemArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Coloured Gauss-Seidel sweep in ONE pass over memory (out of place: Tin -> Tout).  Same ring as k_element_win.
+// In iteration t every thread first relaxes its child of tile t+2 if that is a DOWN child (reads the old up
+// values in tiles t+1 .. t+4, writes the new down values into the ring), then its child of tile t if that is an
+// UP child (reads the new down values in tiles t-2 .. t+1, which earlier iterations produced, writes the new up
+// values into the ring); the two updates touch disjoint data, so one CTA barrier per tile suffices.  Tile t is
+// then final and leaves through a bulk store straight from the ring.  This is the reference's sweep in
+// two-colour order (all down children, then all up children, values across parent faces lagged through the
+// halo strips) with 24 B/DOF of traffic instead of 48.  A CTA relaxes the down children of the two tiles before
+// and the one tile after its own range redundantly (in shared memory only) so that CTAs stay independent.
+constexpr size_t GSW_SMEM_BYTES = WIN_SMEM_BYTES;
+__device__ __forceinline__ void tma_store_wait_read2() { asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); }
+
+__global__ void __launch_bounds__(TPB, 3) k_gs_win(ElemArgs a) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  double* sT = reinterpret_cast<double*>(dsm);
+  double* sB = sT + 3 * WIN_CH;
+  uint64_t* barT = reinterpret_cast<uint64_t*>(sB + 3 * TPB * WIN_NB);
+  uint64_t* barB = barT + WIN_NT;
+  __shared__ __align__(16) double sPC[NPC];       // parent of the tile whose up children are relaxed
+  __shared__ __align__(16) double sPD[16];        // folded "down" operator of the parent of tile t+2
+  __shared__ int sIdx[8];
+  const int s = a.s, twos = 2 * s, b = 2 << s, S = 1 << s;
+  const long long Cmask = (1ll << twos) - 1;
+  const int tid = threadIdx.x;
+  constexpr uint32_t TILE_BYTES = 3 * TPB * sizeof(double);
+  if (tid == 0) {
+    for (int i = 0; i < WIN_NT + WIN_NB; ++i) mbar_init(&barT[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long ntiles = a.nelem / TPB;
+  const long long per = (ntiles + gridDim.x - 1) / gridDim.x;
+  const long long tbeg = (long long)blockIdx.x * per, tend = min(ntiles, tbeg + per);
+  if (tbeg >= tend) return;
+  const long long dlo = max(0ll, tbeg - 2), dhi = min(ntiles - 1, tend);       // tiles whose down children I relax
+  const long long tlo = max(0ll, dlo - 1), thi = min(ntiles, dhi + 3);         // field tiles I load: [tlo, thi)
+  const long long t0 = dlo - 2;                                                // first iteration
+
+  auto issueT = [&](long long tile) {
+    const int sl = (int)(tile & (WIN_NT - 1));
+    mbar_expect_tx(&barT[sl], TILE_BYTES);
+    tma_load_1d(sT + sl * 3 * TPB, a.Tin + tile * 3 * TPB, TILE_BYTES, &barT[sl]);
+  };
+  auto issueB = [&](long long tile) {
+    const int sl = (int)((tile - dlo) & (WIN_NB - 1));
+    mbar_expect_tx(&barB[sl], TILE_BYTES);
+    tma_load_1d(sB + sl * 3 * TPB, a.rhs + tile * 3 * TPB, TILE_BYTES, &barB[sl]);
+  };
+  auto waitT = [&](long long tile) { mbar_wait(&barT[tile & (WIN_NT - 1)], (uint32_t)(((tile - tlo) >> 3) & 1)); };
+  auto waitB = [&](long long tile) { mbar_wait(&barB[(tile - dlo) & (WIN_NB - 1)], (uint32_t)(((tile - dlo) >> 2) & 1)); };
+  if (tid == 0) {
+    for (long long t = tlo; t < min(thi, t0 + 6); ++t) issueT(t);        // iteration t0 needs tiles <= t0 + 4; one ahead
+    for (long long t = dlo; t <= min(dhi, dlo + 3); ++t) issueB(t);      // all four rhs slots
+  }
+
+  int u_up = -1, u_dn = -1;
+  struct Prep { int r, ipos, len; double h1a, h1b, h2a, h2b; };
+  auto prepare = [&](long long tile, Prep& p) {    // my child of `tile` as an up child: numbering + strip entries
+    p.r = 2; p.ipos = 2; p.len = 3; p.h1a = 0.0; p.h1b = 0.0; p.h2a = 0.0; p.h2b = 0.0;
+    if (tile < tbeg || tile >= tend) return;
+    const long long g = tile * TPB + tid;
+    child_from_ele0((int)(g & Cmask), s, p.r, p.ipos, p.len);
+    if (!(p.ipos & 1)) return;
+    const bool f1 = p.r == 1, side = p.ipos == 1 || p.ipos == p.len;
+    if (f1 | side) {
+      const int u = (int)(g >> twos);
+      const bool same = u == u_up;
+      if (f1) {
+        const int strip = same ? sIdx[0] : __ldg(a.strip_of + u * 3), hm = same ? sIdx[4] : __ldg(a.hmap + u * 3);
+        const double* e = a.ovl + ((size_t)strip * S + (p.ipos >> 1)) * 3;
+        p.h1a = __ldg(e + (hm & 3)); p.h1b = __ldg(e + (hm >> 2));
+      }
+      if (side) {
+        const int mf = (p.ipos == 1) ? 2 : 1;
+        const int strip = same ? sIdx[mf] : __ldg(a.strip_of + u * 3 + mf), hm = same ? sIdx[4 + mf] : __ldg(a.hmap + u * 3 + mf);
+        const double* e = a.ovl + ((size_t)strip * S + (p.r - 1)) * 3;
+        p.h2a = __ldg(e + (hm & 3)); p.h2b = __ldg(e + (hm >> 2));
+      }
+    }
+  };
+  Prep cur, nxt;
+  prepare(t0, cur);
+  for (long long tile = t0; tile < tend; ++tile) {
+    const long long td = tile + 2;                       // tile whose down children are relaxed now
+    const bool doD = td >= dlo && td <= dhi, doU = tile >= tbeg;
+    if (tid == 0 && tile > t0) {
+      // field slot of tile-3: last read while tile-1 was relaxed; its store (three groups ago) has been read
+      if (tile + 5 < thi) { tma_store_wait_read2(); issueT(tile + 5); }
+      // rhs slot of tile-1 (= td-3): consumed by the up children of tile-1
+      if (td + 1 >= dlo + 4 && td + 1 <= dhi) issueB(td + 1);
+    }
+    {
+      const int ud = doD ? (int)((td * TPB) >> twos) : u_dn;
+      const int uu = doU ? (int)((tile * TPB) >> twos) : u_up;
+      if (ud != u_dn || uu != u_up) {                    // uniform over the CTA
+        __syncthreads();
+        if (uu != u_up) {
+          if (tid < NPC) sPC[tid] = __ldg(a.pc + (size_t)uu * NPC + tid);
+          else if (tid < NPC + 3) sIdx[tid - NPC] = __ldg(a.strip_of + uu * 3 + (tid - NPC));
+          else if (tid < NPC + 6) sIdx[4 + tid - NPC - 3] = __ldg(a.hmap + uu * 3 + (tid - NPC - 3));
+        }
+        if (ud != u_dn && tid >= 128 && tid < 144) sPD[tid - 128] = __ldg(a.pc + (size_t)ud * NPC + PC_FOLD + 16 + (tid - 128));
+        __syncthreads();
+        u_dn = ud; u_up = uu;
+      }
+    }
+    prepare(tile + 1, nxt);
+    if (tile == t0) {
+      for (long long tw = tlo; tw < min(thi, tile + 5); ++tw) waitT(tw);
+    } else if (tile + 4 < thi) {
+      waitT(tile + 4);
+    }
+    if (doD) {
+      waitB(td);
+      const long long g = td * TPB + tid;
+      int r, ipos, len;
+      child_from_ele0((int)(g & Cmask), s, r, ipos, len);
+      if (!(ipos & 1)) {                                  // down child: all three faces inside the parent
+        const int cw = (int)((td * TPB) & (WIN_CH - 1)) + tid;
+        double* t = sT + cw * 3;
+        const double T1 = t[0], T2 = t[1], T3 = t[2];
+        FaceIn fi;
+        const double* tv = sT + ((cw + b - 2 * r) & (WIN_CH - 1)) * 3;      // up child of the row above
+        fi.n1a = tv[2]; fi.n1b = tv[0];
+        const double* tr = sT + ((cw + 1) & (WIN_CH - 1)) * 3;
+        const double* tl = sT + ((cw - 1) & (WIN_CH - 1)) * 3;
+        fi.n2a = tr[1]; fi.n2b = tr[2];
+        fi.n3a = tl[0]; fi.n3b = tl[1];
+        const double* bb = sB + ((td - dlo) & (WIN_NB - 1)) * 3 * TPB + tid * 3;
+        const Folded& F = *reinterpret_cast<const Folded*>(sPD);
+        double o1, o2, o3;
+        elem_apply_folded<MODE_GS>(F, sPD, 0, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
+        t[0] = o1; t[1] = o2; t[2] = o3;
+      }
+    }
+    if (doU) {
+      // rhs of `tile` landed when its down children were relaxed two iterations ago
+      if (cur.ipos & 1) {
+        const int cw = (int)((tile * TPB) & (WIN_CH - 1)) + tid;
+        double* t = sT + cw * 3;
+        const double T1 = t[0], T2 = t[1], T3 = t[2];
+        FaceIn fi;
+        int bmask = 0;
+        const double* tv = sT + ((cw + 2 * cur.r - b - 2) & (WIN_CH - 1)) * 3;   // down child of the row below
+        fi.n1a = tv[2]; fi.n1b = tv[0];
+        const double* tl = sT + ((cw - 1) & (WIN_CH - 1)) * 3;
+        const double* tr = sT + ((cw + 1) & (WIN_CH - 1)) * 3;
+        fi.n2a = tl[1]; fi.n2b = tl[2];
+        fi.n3a = tr[0]; fi.n3b = tr[1];
+        if (cur.r == 1 || cur.ipos == 1 || cur.ipos == cur.len) {               // child on a parent face (rare)
+          if (cur.r == 1) { fi.n1a = cur.h1a; fi.n1b = cur.h1b; bmask |= 1; }
+          if (cur.ipos == 1) { fi.n2a = cur.h2a; fi.n2b = cur.h2b; bmask |= 2; }
+          if (cur.ipos == cur.len) {
+            if (cur.len == 1) halo_pair(a, (int)((tile * TPB) >> twos), 1, cur.r - 1, S, fi.n3a, fi.n3b);
+            else { fi.n3a = cur.h2a; fi.n3b = cur.h2b; }
+            bmask |= 4;
+          }
+        }
+        const double* bb = sB + ((tile - dlo) & (WIN_NB - 1)) * 3 * TPB + tid * 3;
+        const Folded& F = *reinterpret_cast<const Folded*>(sPC + PC_FOLD);
+        double o1, o2, o3;
+        elem_apply_folded<MODE_GS>(F, sPC + PC_DPEN, bmask, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
+        t[0] = o1; t[1] = o2; t[2] = o3;
+      }
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0 && doU) {
+      tma_store_1d(a.Tout + tile * 3 * TPB, sT + (tile & (WIN_NT - 1)) * 3 * TPB, TILE_BYTES);
+      tma_store_commit();
+    }
+    cur = nxt;
+  }
+  if (tid == 0) tma_store_wait_all();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Branch-free direct kernel: thread per child, every load of the child (own values, rhs, the three
 // neighbours) is issued before the first use so that one memory latency is exposed per child instead of a
 // chain of two or three; children on a parent face patch their neighbour values from the halo strips in a
