@@ -160,6 +160,14 @@ int pamg_implicit_apply(pamg_handle* h, const double* x /* host (3,E) */, double
  * may be NULL. */
 int pamg_implicit_step(pamg_handle* h, int ntime, int nits, double tol, int max_iters, int* iters_total, double* relres);
 
+/* ---- Petrov-Galerkin residual-based stabilisation (transport_tri_unstr.F90:239-267,278; semi_str_implicit.F90:290-318) --
+ * diff_coe(gi) and stab(iloc,jloc) of every element from tnew = the field of pamg_unstr_upload and the given told.
+ * HEAD computes stab and never applies it (:367-368 are commented out); pamg_implicit_set_stab(h, 1) applies it the
+ * intended way: every nonlinear pass of pamg_implicit_step adds stab(tnew_nonlin, told) to the diagonal blocks. */
+int pamg_unstr_stab(pamg_handle* h, const double* told /* host (3,E) */, double dt, double u_x, double u_y,
+                    double* diff_coe /* host (3,E) or NULL */, double* stab /* host [E][3][3] or NULL */);
+int pamg_implicit_set_stab(pamg_handle* h, int with_stab);
+
 /* ---- batched element-local inverse (FINDInv, matrix_inversion.F90:50-148) ----------------------- */
 /* M, x, rhs on the HOST; n in {3,4,6}; M row-major [batch][n][n].  x = M^-1 rhs (Minv optional out).
  * status[b] = 0 or -1 (singular) like errorflag. */

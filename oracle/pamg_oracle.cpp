@@ -1265,6 +1265,76 @@ int orc_unstr_implicit(int E, const double* X, const int32_t* neig, const int32_
   return 0;
 }
 
+// Petrov-Galerkin residual-based stabilisation of unstr_implicit (transport_tri_unstr.F90:239-267,278): per Gauss point
+// rgi, a_star, p_star (eq 23 form with inv_jac), diff_coe, and the element matrix stab(i,j) = sum_g diff_coe(g)
+// grad(phi_j).grad(phi_i) detwei(g).  HEAD computes stab and never uses it (the only use, :367-368, is commented out).
+static void stab_element(const double x[3][2], const double* tn, const double* to, double u_x, double u_y, double dt,
+                         double diff_coe[3], double stab[9]) {
+  const double toler = 0.00000000001;   // :93
+  double nx[3][2][3], detwei[3];
+  tri_det_nlx(x, nx, detwei);
+  // inv_jac (ShapFun.F90:1440-1450): (1,1)=D/detJ (1,2)=-C/detJ (2,1)=-B/detJ (2,2)=A/detJ, the same at every Gauss point
+  double A = 0, B = 0, C = 0, D = 0;
+  for (int l = 0; l < 3; ++l) {
+    A += TB.nlx[0][0][l] * x[l][0]; B += TB.nlx[0][0][l] * x[l][1];
+    C += TB.nlx[0][1][l] * x[l][0]; D += TB.nlx[0][1][l] * x[l][1];
+  }
+  const double detj = A * D - B * C;
+  const double ij[2][2] = {{D / detj, -C / detj}, {-B / detj, A / detj}};
+  for (int g = 0; g < 3; ++g) {
+    double ugi[2] = {0, 0}, txgi[2] = {0, 0}, tgi = 0, togi = 0;
+    for (int l = 0; l < 3; ++l) {
+      ugi[0] += TB.n[g][l] * u_x; ugi[1] += TB.n[g][l] * u_y;
+      txgi[0] += nx[g][0][l] * tn[l]; txgi[1] += nx[g][1][l] * tn[l];
+      tgi += TB.n[g][l] * tn[l]; togi += TB.n[g][l] * to[l];
+    }
+    const double rgi = (tgi - togi) / dt + (ugi[0] * txgi[0] + ugi[1] * txgi[1]);
+    const double g2 = txgi[0] * txgi[0] + txgi[1] * txgi[1];
+    const double a_coef = rgi / std::max(toler, g2);
+    const double as[2] = {a_coef * txgi[0], a_coef * txgi[1]};
+    double ps = 0.0;
+    for (int d = 0; d < 2; ++d) ps = std::max(ps, std::fabs(as[0] * ij[0][d] + as[1] * ij[1][d]));
+    ps = std::min(1.0 / toler, 0.25 / ps);
+    diff_coe[g] = 0.25 * rgi * rgi * ps / std::max(toler, g2);
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double v = 0;
+      for (int g = 0; g < 3; ++g) v += diff_coe[g] * (nx[g][0][j] * nx[g][0][i] + nx[g][1][j] * nx[g][1][i]) * detwei[g];
+      stab[i * 3 + j] = v;
+    }
+}
+
+void orc_unstr_stab(int E, const double* X, const double* tnew, const double* told, double u_x, double u_y, double dt,
+                    double* diff_coe, double* stab) {
+  for (int e = 0; e < E; ++e)
+    stab_element(reinterpret_cast<const double (*)[2]>(&X[(size_t)e * 6]), tnew + (size_t)e * 3, told + (size_t)e * 3, u_x,
+                 u_y, dt, diff_coe + (size_t)e * 3, stab + (size_t)e * 9);
+}
+
+// INTENDED use of the stabilisation (what the commented `mat_loc = mass_ele + dt*stab` at :367-368 amounts to for the
+// implicit system): every nonlinear pass adds stab(tnew_nonlin, told) to the diagonal blocks of lhs + flux and re-solves.
+int orc_unstr_implicit_stab(int E, const double* X, const int32_t* neig, const int32_t* fneig, double u_x, double u_y,
+                            double dt, int ntime, int nits, int use_dir, double* tnew) {
+  const size_t N = (size_t)3 * E;
+  std::vector<double> A(N * N), As(N * N), M(N * N), inv(N * N), rhs(N), told(N), dc(N), st((size_t)9 * E);
+  orc_unstr_implicit_assemble(E, X, neig, fneig, u_x, u_y, dt, use_dir, A.data(), M.data());
+  for (int it = 0; it < ntime; ++it) {
+    std::copy(tnew, tnew + N, told.begin());
+    for (size_t i = 0; i < N; ++i) { double s = 0; for (size_t j = 0; j < N; ++j) s += M[i * N + j] * told[j]; rhs[i] = s; }
+    for (int k = 0; k < nits; ++k) {
+      orc_unstr_stab(E, X, tnew, told.data(), u_x, u_y, dt, dc.data(), st.data());
+      As = A;
+      for (int e = 0; e < E; ++e)
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 3; ++j) As[(size_t)(3 * e + i) * N + 3 * e + j] += st[(size_t)e * 9 + i * 3 + j];
+      if (findinv(As.data(), inv.data(), (int)N) != 0) return -1;
+      for (size_t i = 0; i < N; ++i) { double s = 0; for (size_t j = 0; j < N; ++j) s += inv[i * N + j] * rhs[j]; tnew[i] = s; }
+    }
+  }
+  return 0;
+}
+
 // transport_rect.F90:48-52,83,101-105,337-344 ; structured_meshgen.F90:25-33 (one row of quads)
 void orc_rect_analytical(double CFL, int no_ele_row, double x_length, double u_x, double time,
                          double* x_out, double* t_out) {

@@ -97,6 +97,13 @@ void orc_unstr_implicit_assemble(int E, const double* X, const int32_t* neig, co
 int orc_unstr_implicit(int E, const double* X, const int32_t* neig, const int32_t* fneig, double u_x, double u_y,
                        double dt, int ntime, int nits, int use_dir, double* tnew);
 
+/* ---- Petrov-Galerkin stabilisation (transport_tri_unstr.F90:239-267,278): diff_coe (3,E), stab [E][3][3] row-major */
+void orc_unstr_stab(int E, const double* X, const double* tnew, const double* told, double u_x, double u_y, double dt,
+                    double* diff_coe, double* stab);
+/* INTENDED: lhs + flux + blockdiag(stab(tnew_nonlin, told)) re-solved nits times per step (dense, small E only) */
+int orc_unstr_implicit_stab(int E, const double* X, const int32_t* neig, const int32_t* fneig, double u_x, double u_y,
+                            double dt, int ntime, int nits, int use_dir, double* tnew);
+
 /* ---- analytic cases ----------------------------------------------------------- */
 /* transport_rect.F90:83,101-105,337-344 : fills x[800], t[800] */
 void orc_rect_analytical(double CFL, int no_ele_row, double x_length, double u_x, double time,

@@ -115,6 +115,7 @@ struct pamg_handle {
   int U_global = 0;
   // unstructured
   UnstrDev un;
+  int un_use_dir = 0;
 };
 
 namespace {
@@ -1191,6 +1192,8 @@ int pamg_explicit_step(pamg_handle* h, double dt, double u_x, double u_y, double
 // ---- unstructured implicit operator in block-CSR (unstr_implicit, transport_tri_unstr.F90:214-387) --------
 int pamg_implicit_assemble(pamg_handle* h, double dt, double u_x, double u_y, int use_dir) {
   if (!h || h->un.E < 1 || !(dt > 0.0)) return PAMG_ERR_ARG;
+  if (use_dir < 0) use_dir = h->un_use_dir;   // internal: re-assemble with the previous pairing rule
+  h->un_use_dir = use_dir; h->un.with_stab = false;
   CK(cudaSetDevice(h->device));
   std::string e;
   long long nl = 0;
@@ -1224,6 +1227,39 @@ int pamg_implicit_apply(pamg_handle* h, const double* x, double* y) {
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(y, W + (size_t)h->un.E * 3, nb, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  return PAMG_OK;
+}
+
+int pamg_implicit_set_stab(pamg_handle* h, int with_stab) {
+  if (!h || h->un.E < 1) return PAMG_ERR_ARG;
+  if (!h->un.assembled) return fail(h, PAMG_ERR_STATE, "pamg_implicit_assemble has not been called");
+  CK(cudaSetDevice(h->device));
+  if (h->un.with_stab && !with_stab)   // back to the plain operator: restore the diagonal blocks and their inverses
+    return pamg_implicit_assemble(h, h->un.dt, h->un.ux, h->un.uy, -1);
+  h->un.with_stab = with_stab != 0;
+  return PAMG_OK;
+}
+
+int pamg_unstr_stab(pamg_handle* h, const double* told, double dt, double u_x, double u_y, double* diff_coe, double* stab) {
+  if (!h || h->un.E < 1 || !told || !(dt > 0.0) || (!diff_coe && !stab)) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  const size_t E = (size_t)h->un.E;
+  double *d_old = nullptr, *d_out = nullptr;
+  CK(cudaMalloc(&d_old, E * 3 * sizeof(double)));
+  if (cudaMalloc(&d_out, E * 12 * sizeof(double)) != cudaSuccess) { cudaFree(d_old); return fail(h, PAMG_ERR_CUDA, "cudaMalloc"); }
+  cudaMemcpyAsync(d_old, told, E * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  StabArgs sa;
+  sa.X = h->un.X; sa.tnew = h->un.T[h->un.cur]; sa.told = d_old; sa.diff_coe = d_out + E * 9; sa.stab = d_out; sa.diag0 = nullptr;
+  sa.val = nullptr; sa.dinv = nullptr; sa.dt = dt; sa.ux = u_x; sa.uy = u_y; sa.E = h->un.E; sa.mode = 0;
+  const int grid = std::max(1, std::min((h->un.E + TPB - 1) / TPB, h->nsm * 8));
+  k_unstr_stab<<<grid, TPB, 0, h->stream>>>(sa);
+  h->launches++;
+  cudaError_t e1 = cudaGetLastError();
+  if (stab) cudaMemcpyAsync(stab, d_out, E * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (diff_coe) cudaMemcpyAsync(diff_coe, d_out + E * 9, E * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e2 = cudaStreamSynchronize(h->stream);
+  cudaFree(d_old); cudaFree(d_out);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(h, PAMG_ERR_CUDA, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
   return PAMG_OK;
 }
 

@@ -35,6 +35,10 @@ struct UnstrDev {
   double* dots = nullptr;      // [4] device results of k_dots
   double* dots_host = nullptr; // pinned mirror
   bool assembled = false;
+  double* diag0 = nullptr;     // [E][9] diagonal blocks without stabilisation
+  double* stab = nullptr;      // [E][9] Petrov-Galerkin element matrices ; [E][3] diff_coe behind them
+  bool with_stab = false;
+  double dt = 0.0, ux = 0.0, uy = 0.0;
 };
 
 struct UnstrArgs {
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(TPB) k_unstr_explicit(UnstrArgs a) {
 
 inline void unstr_free(UnstrDev& u) {
   cudaFree(u.X); cudaFree(u.neig); cudaFree(u.nside); cudaFree(u.T[0]); cudaFree(u.T[1]); cudaFree(u.told);
-  cudaFree(u.bsr_val); cudaFree(u.bsr_col); cudaFree(u.dinv); cudaFree(u.mdt); cudaFree(u.work); cudaFree(u.dots);
+  cudaFree(u.bsr_val); cudaFree(u.bsr_col); cudaFree(u.dinv); cudaFree(u.mdt); cudaFree(u.work); cudaFree(u.dots); cudaFree(u.diag0); cudaFree(u.stab);
   if (u.dots_host) cudaFreeHost(u.dots_host);
   u = UnstrDev();
 }
@@ -352,6 +356,77 @@ __global__ void __launch_bounds__(256) k_dots_final(const double* __restrict__ p
   if (threadIdx.x < 2) out[threadIdx.x] = sh[threadIdx.x][0];
 }
 
+// Petrov-Galerkin residual-based stabilisation (transport_tri_unstr.F90:239-267,278): one thread per element.
+// For P1 the gradient of T and inv_jac are constant over the element; rgi differs per Gauss point through T(gi).
+// mode 0: write diff_coe (3 per element) and stab (9 per element).
+// mode 1: additionally write diagonal block = diag0 + stab into the block-CSR and refresh its inverse.
+struct StabArgs {
+  const double* X; const double* tnew; const double* told;
+  double* diff_coe; double* stab; const double* diag0; double* val; double* dinv;
+  double dt, ux, uy;
+  int E, mode;
+};
+
+__global__ void __launch_bounds__(TPB) k_unstr_stab(StabArgs a) {
+  const double toler = 0.00000000001;
+  for (int e = blockIdx.x * TPB + threadIdx.x; e < a.E; e += gridDim.x * TPB) {
+    const double* __restrict__ X = a.X + (size_t)e * 6;
+    const double x1 = __ldg(X), y1 = __ldg(X + 1), x2 = __ldg(X + 2), y2 = __ldg(X + 3), x3 = __ldg(X + 4), y3 = __ldg(X + 5);
+    const double A = x1 - x3, B = y1 - y3, C = x2 - x3, D = y2 - y3;
+    const double detj = A * D - B * C;
+    const double dw = 0.5 * fabs(detj) * (1.0 / 3.0);
+    const double a11 = D / detj, a21 = -C / detj, a12 = -B / detj, a22 = A / detj;
+    // nx(g,1,l) = a11 nlx1 + a12 nlx2 ; nx(g,2,l) = a21 nlx1 + a22 nlx2 with nlx1 = (1,0,-1), nlx2 = (0,1,-1)
+    const double gx[3] = {a11 * 1.0 + a12 * 0.0, a11 * 0.0 + a12 * 1.0, a11 * -1.0 + a12 * -1.0};
+    const double gy[3] = {a21 * 1.0 + a22 * 0.0, a21 * 0.0 + a22 * 1.0, a21 * -1.0 + a22 * -1.0};
+    const double tn[3] = {a.tnew[(size_t)e * 3], a.tnew[(size_t)e * 3 + 1], a.tnew[(size_t)e * 3 + 2]};
+    const double to[3] = {a.told[(size_t)e * 3], a.told[(size_t)e * 3 + 1], a.told[(size_t)e * 3 + 2]};
+    double tx = 0.0, ty = 0.0;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) { tx += gx[l] * tn[l]; ty += gy[l] * tn[l]; }
+    const double g2 = tx * tx + ty * ty;
+    const double N[3][3] = {{0.5, 0.5, 0.0}, {0.0, 0.5, 0.5}, {0.5, 0.0, 0.5}};   // n(gi, iloc), ShapFun.F90:1038-1040
+    double dc[3];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      double ugx = 0.0, ugy = 0.0, tgi = 0.0, togi = 0.0;
+#pragma unroll
+      for (int l = 0; l < 3; ++l) { ugx += N[g][l] * a.ux; ugy += N[g][l] * a.uy; tgi += N[g][l] * tn[l]; togi += N[g][l] * to[l]; }
+      const double rgi = (tgi - togi) / a.dt + (ugx * tx + ugy * ty);
+      const double ac = rgi / fmax(toler, g2);
+      const double as1 = ac * tx, as2 = ac * ty;
+      double ps = fmax(fabs(as1 * a11 + as2 * a12), fabs(as1 * a21 + as2 * a22));
+      ps = fmin(1.0 / toler, 0.25 / ps);
+      dc[g] = 0.25 * rgi * rgi * ps / fmax(toler, g2);
+    }
+    double st[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        double v = 0.0;
+#pragma unroll
+        for (int g = 0; g < 3; ++g) v += dc[g] * (gx[j] * gx[i] + gy[j] * gy[i]) * dw;
+        st[i * 3 + j] = v;
+      }
+    if (a.diff_coe) { a.diff_coe[(size_t)e * 3] = dc[0]; a.diff_coe[(size_t)e * 3 + 1] = dc[1]; a.diff_coe[(size_t)e * 3 + 2] = dc[2]; }
+    if (a.stab)
+#pragma unroll
+      for (int q = 0; q < 9; ++q) a.stab[(size_t)e * 9 + q] = st[q];
+    if (a.mode == 1) {
+      double d[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) { d[q] = a.diag0[(size_t)e * 9 + q] + st[q]; a.val[(size_t)e * 36 + q] = d[q]; }
+      const double c00 = d[4] * d[8] - d[5] * d[7], c01 = d[5] * d[6] - d[3] * d[8], c02 = d[3] * d[7] - d[4] * d[6];
+      const double id = 1.0 / (d[0] * c00 + d[1] * c01 + d[2] * c02);
+      double* o = a.dinv + (size_t)e * 9;
+      o[0] = c00 * id; o[1] = (d[2] * d[7] - d[1] * d[8]) * id; o[2] = (d[1] * d[5] - d[2] * d[4]) * id;
+      o[3] = c01 * id; o[4] = (d[0] * d[8] - d[2] * d[6]) * id; o[5] = (d[2] * d[3] - d[0] * d[5]) * id;
+      o[6] = c02 * id; o[7] = (d[1] * d[6] - d[0] * d[7]) * id; o[8] = (d[0] * d[4] - d[1] * d[3]) * id;
+    }
+  }
+}
+
 inline int implicit_assemble(UnstrDev& u, double dt, double ux, double uy, int use_dir, int nsm, cudaStream_t st,
                              long long& nlaunch, std::string& err) {
   const size_t E = (size_t)u.E;
@@ -363,6 +438,8 @@ inline int implicit_assemble(UnstrDev& u, double dt, double ux, double uy, int u
     UCK(cudaMalloc(&u.work, E * 3 * 9 * sizeof(double)));
     UCK(cudaMalloc(&u.dots, (size_t)(2 * nsm * 8 + 2) * sizeof(double)));
     UCK(cudaMallocHost(&u.dots_host, 2 * sizeof(double)));
+    UCK(cudaMalloc(&u.diag0, E * 9 * sizeof(double)));
+    UCK(cudaMalloc(&u.stab, E * 12 * sizeof(double)));
   }
   BsrArgs a;
   a.X = u.X; a.neig = u.neig; a.nside = u.nside; a.val = u.bsr_val; a.col = u.bsr_col; a.dinv = u.dinv; a.mdt = u.mdt;
@@ -371,7 +448,9 @@ inline int implicit_assemble(UnstrDev& u, double dt, double ux, double uy, int u
   k_assemble_bsr<<<grid, TPB, 0, st>>>(a);
   nlaunch++;
   UCK(cudaGetLastError());
-  u.assembled = true;
+  // keep the unstabilised diagonal blocks (block 0 of every row: 9 doubles at a stride of 36)
+  UCK(cudaMemcpy2DAsync(u.diag0, 9 * sizeof(double), u.bsr_val, 36 * sizeof(double), 9 * sizeof(double), E, cudaMemcpyDeviceToDevice, st));
+  u.assembled = true; u.dt = dt; u.ux = ux; u.uy = uy;
   return PAMG_OK;
 }
 
@@ -406,6 +485,12 @@ inline int implicit_step(UnstrDev& u, int ntime, int nits, double tol, int max_i
       if (k == 0) {
         UCK(cudaMemcpyAsync(u.told, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
         k_block_apply<<<grid, TPB, 0, st>>>(u.dinv, u.mdt, u.told, b, E, 1); nlaunch++;
+      }
+      if (u.with_stab) {   // INTENDED use (:367-368 commented at HEAD): diagonal blocks += stab(tnew_nonlin, told)
+        StabArgs sa;
+        sa.X = u.X; sa.tnew = x; sa.told = u.told; sa.diff_coe = u.stab + (size_t)E * 9; sa.stab = u.stab; sa.diag0 = u.diag0;
+        sa.val = u.bsr_val; sa.dinv = u.dinv; sa.dt = u.dt; sa.ux = u.ux; sa.uy = u.uy; sa.E = E; sa.mode = 1;
+        k_unstr_stab<<<grid, TPB, 0, st>>>(sa); nlaunch++;
       }
       k_bsr_spmv<<<grid, TPB, 0, st>>>(u.bsr_val, u.bsr_col, x, b, r, E, 1); nlaunch++;
       UCK(cudaMemcpyAsync(rh, r, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));

@@ -189,6 +189,22 @@ module pamg_iface
       real(c_double), intent(out) :: relres
     end function
 
+    ! Petrov-Galerkin stabilisation (transport_tri_unstr.F90:239-267,278)
+    integer(c_int) function pamg_unstr_stab(handle, told, dt, u_x, u_y, diff_coe, stab) bind(c, name="pamg_unstr_stab")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), intent(in) :: told(3, *)
+      real(c_double), value :: dt, u_x, u_y
+      real(c_double), intent(out) :: diff_coe(3, *)      ! (ngi, ele)
+      real(c_double), intent(out) :: stab(3, 3, *)       ! (jloc, iloc, ele): row-major blocks
+    end function
+
+    integer(c_int) function pamg_implicit_set_stab(handle, with_stab) bind(c, name="pamg_implicit_set_stab")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int), value :: with_stab
+    end function
+
     ! FINDInv (matrices.F90:1618), batched
     integer(c_int) function pamg_apply_local_minv(handle, n, batch, M, rhs, x, Minv, status) &
         bind(c, name="pamg_apply_local_minv")

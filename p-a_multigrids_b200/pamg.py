@@ -102,6 +102,8 @@ def lib():
         "pamg_implicit_get_bsr": (ci, [vp, vp, vp]),
         "pamg_implicit_apply": (ci, [vp, _f64, _f64]),
         "pamg_implicit_step": (ci, [vp, ci, ci, cd, ci, pint, pdbl]),
+        "pamg_unstr_stab": (ci, [vp, _f64, cd, cd, cd, vp, vp]),
+        "pamg_implicit_set_stab": (ci, [vp, ci]),
         "pamg_apply_local_minv": (ci, [vp, ci, ci, _f64, vp, vp, vp, vp]),
         "pamg_sync": (ci, [vp]),
         "pamg_event_record": (ci, [vp, ci]),
@@ -407,10 +409,20 @@ class SemiImplicitIterative:
         self._ck(self.L.pamg_implicit_apply(self.h, x, y))
         return y
 
-    def unstr_implicit(self, tnew, dt, u_x, u_y, ntime=2, nits=1, use_dir=False, tol=1e-13, max_iters=500):
+    def unstr_stab(self, tnew, told, dt, u_x, u_y):
+        """Petrov-Galerkin diff_coe (E,3) and stab (E,3,3) (transport_tri_unstr.F90:239-267,278)."""
+        t = np.ascontiguousarray(tnew, np.float64); o = np.ascontiguousarray(told, np.float64)
+        self._ck(self.L.pamg_unstr_upload(self.h, t))
+        dc = np.zeros((self._E, 3)); st = np.zeros((self._E, 3, 3))
+        self._ck(self.L.pamg_unstr_stab(self.h, o, dt, u_x, u_y, _ptr(dc), _ptr(st)))
+        return dc, st
+
+    def unstr_implicit(self, tnew, dt, u_x, u_y, ntime=2, nits=1, use_dir=False, tol=1e-13, max_iters=500, with_stab=False):
         """Time loop of unstr_implicit; returns (tnew, Krylov iterations in total, worst relative residual)."""
         t = np.ascontiguousarray(tnew, np.float64)
         self.implicit_assemble(dt, u_x, u_y, use_dir)
+        if with_stab:
+            self._ck(self.L.pamg_implicit_set_stab(self.h, 1))
         self._ck(self.L.pamg_unstr_upload(self.h, t))
         it = C.c_int(0); rr = C.c_double(0.0)
         self._ck(self.L.pamg_implicit_step(self.h, ntime, nits, tol, max_iters, C.byref(it), C.byref(rr)))

@@ -317,6 +317,46 @@ def test_unstr_implicit_time_loop(meshes, name, use_dir, u):
     assert rel_l2(got2, ref) <= 1e-10 and iters2 == iters
 
 
+@pytest.mark.parametrize("name", ["split1", "irregular", "900_ele", "untitled8192"])
+def test_unstr_stabilisation_arrays(meshes, name):
+    """diff_coe / stab of transport_tri_unstr.F90:239-267,278 on the device == oracle (HEAD computes them and stops)."""
+    mesh = meshes[name]
+    E = mesh.U
+    g = pamg.SemiImplicitIterative(pamg.default_params(), pamg.Mesh.synthetic(0, 1))
+    g.set_unstructured(mesh)
+    Tn = rng_field((E, 3), 21); To = rng_field((E, 3), 22)
+    dt = 1e-2
+    dc, st = g.unstr_stab(Tn, To, dt, 0.9, 0.3)
+    rdc = np.zeros((E, 3)); rst = np.zeros((E, 9))
+    orc.lib().orc_unstr_stab(E, mesh.X, Tn, To, 0.9, 0.3, dt, rdc, rst)
+    assert np.allclose(dc, rdc, rtol=1e-10, atol=1e-12 * np.max(np.abs(rdc)))
+    assert np.allclose(st.reshape(E, 9), rst, rtol=1e-10, atol=1e-12 * np.max(np.abs(rst)))
+    # zero residual -> exactly no diffusion
+    dc0, st0 = g.unstr_stab(np.ones((E, 3)), np.ones((E, 3)), dt, 0.9, 0.3)
+    assert np.all(dc0 == 0.0) and np.all(st0 == 0.0)
+
+
+@pytest.mark.parametrize("name,use_dir", [("split1", 1), ("test_sn2", 0)])
+def test_unstr_implicit_with_stabilisation(meshes, name, use_dir):
+    """INTENDED use of the stabilisation: diagonal blocks += stab(tnew_nonlin, told) in every nonlinear pass."""
+    mesh = meshes[name]
+    E = mesh.U
+    g = pamg.SemiImplicitIterative(pamg.default_params(), pamg.Mesh.synthetic(0, 1))
+    g.set_unstructured(mesh)
+    T0 = rng_field((E, 3), 9)
+    dt, u = 5e-2, (0.4, -0.7)
+    ref = T0.copy()
+    assert orc.lib().orc_unstr_implicit_stab(E, mesh.X, mesh.neig, mesh.fneig, u[0], u[1], dt, 2, 2, use_dir, ref) == 0
+    got, iters, relres = g.unstr_implicit(T0, dt, u[0], u[1], ntime=2, nits=2, use_dir=bool(use_dir), tol=1e-13, with_stab=True)
+    assert relres <= 1e-13 and iters > 0
+    assert rel_l2(got, ref) <= 1e-9
+    plain, _, _ = g.unstr_implicit(T0, dt, u[0], u[1], ntime=2, nits=2, use_dir=bool(use_dir), tol=1e-13)
+    assert rel_l2(plain, ref) > 1e-6            # the stabilisation really changed the answer, and switching it off works
+    ref2 = T0.copy()
+    assert orc.lib().orc_unstr_implicit(E, mesh.X, mesh.neig, mesh.fneig, u[0], u[1], dt, 2, 2, use_dir, ref2) == 0
+    assert rel_l2(plain, ref2) <= 1e-10
+
+
 def test_unstr_implicit_errors(meshes):
     g = pamg.SemiImplicitIterative(pamg.default_params(), pamg.Mesh.synthetic(0, 1))
     L = pamg.lib()

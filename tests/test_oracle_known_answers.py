@@ -258,3 +258,35 @@ def test_unstr_implicit_solve_is_backward_euler(tmp_path):
                                           u[0], u[1], dt, 3, nits, 1, T)
         assert rc == 0
         assert np.linalg.norm(T - ref) <= 1e-12 * np.linalg.norm(ref)
+
+
+def test_unstr_stab_known_answer_and_invariants(tmp_path):
+    """Petrov-Galerkin stabilisation (transport_tri_unstr.F90:239-267,278).  Unit triangle x1=(1,0) x2=(0,1) x3=(0,0):
+    inv_jac = I, grad phi = (1,0),(0,1),(-1,-1).  T=(1,0,0)=told, u=(2,0): rgi = 2, a_star = (2,0), p_star = 0.125,
+    diff_coe = 0.25*4*0.125 = 0.125, stab = 0.125 * area * grad_j.grad_i."""
+    X = np.array([[[1.0, 0.0], [0.0, 1.0], [0.0, 0.0]]])
+    T = np.array([[1.0, 0.0, 0.0]])
+    dc = np.zeros((1, 3)); st = np.zeros((1, 9))
+    orc.lib().orc_unstr_stab(1, X, T, T.copy(), 2.0, 0.0, 1e-2, dc, st)
+    assert np.allclose(dc, 0.125, rtol=1e-14)
+    G = np.array([[1.0, 0.0], [0.0, 1.0], [-1.0, -1.0]])
+    assert np.allclose(st.reshape(3, 3), 0.125 * 0.5 * G @ G.T, rtol=1e-14)
+    # zero residual (steady, gradient perpendicular to u) -> no diffusion at all
+    orc.lib().orc_unstr_stab(1, X, T, T.copy(), 0.0, 3.0, 1e-2, dc, st)
+    assert np.all(dc == 0.0) and np.all(st == 0.0)
+    # flat field: |grad T|^2 < toler, the 1/toler clamps apply: a_star = 0 -> p_star = 1e11, diff = .25 r^2 1e11 / 1e-11
+    Tn = np.array([[1.0, 1.0, 1.0]]); To = np.zeros((1, 3))
+    orc.lib().orc_unstr_stab(1, X, Tn, To, 1.0, 1.0, 0.5, dc, st)
+    assert np.allclose(dc, 0.25 * 4.0 * 1e11 / 1e-11, rtol=1e-12)
+    # random fields on a real mesh: symmetric, positive semi-definite, constants in the kernel
+    m = orc.read_msh(write_msh("irregular", str(tmp_path / "i.msh")))
+    E = m["X"].shape[0]
+    rng = np.random.default_rng(3)
+    Tn = rng.random((E, 3)); To = rng.random((E, 3))
+    dc = np.zeros((E, 3)); st = np.zeros((E, 9))
+    orc.lib().orc_unstr_stab(E, np.ascontiguousarray(m["X"]), Tn, To, 0.9, 0.3, 1e-2, dc, st)
+    S = st.reshape(E, 3, 3)
+    assert np.all(dc >= 0.0)
+    assert np.allclose(S, S.transpose(0, 2, 1), rtol=1e-12, atol=0)
+    assert np.max(np.abs(S.sum(axis=2))) <= 1e-12 * np.max(np.abs(S))
+    assert np.min(np.linalg.eigvalsh(S)) >= -1e-12 * np.max(np.abs(S))
