@@ -174,6 +174,15 @@ int pamg_implicit_set_stab(pamg_handle* h, int with_stab);
 int pamg_apply_local_minv(pamg_handle* h, int n, int batch, const double* M, const double* rhs, double* x,
                           double* Minv, int32_t* status);
 
+/* ---- output (get_vtu, get_vtk_files.F90:10-140; call site transport_tri_semi.F90:299-312) ---------------------
+ * level-1 child coordinates x_all_str (2,3,C*U) (:274), analytical = sin(x+y) (:278) and get_error = |tnew - analytical|
+ * (:531-540), computed on the device; any pointer may be NULL. */
+int pamg_output_fields(pamg_handle* h, double* x_all, double* analytical, double* error);
+/* one .vtu piece of level 1 with the reference's arrays (<solve_for>, error, analytical; points; triangles).
+ * binary = 0: ASCII in the reference's layout and number formats (F12.10 / F10.7 / F10.3, one value per line);
+ * binary = 1: raw appended Float64. */
+int pamg_write_vtu(pamg_handle* h, const char* path, const char* solve_for, int binary);
+
 /* ---- timing helpers (CUDA events on the handle's stream) ---------------------------------------- */
 int pamg_sync(pamg_handle* h);
 int pamg_event_record(pamg_handle* h, int slot);       /* slot 0..15 */

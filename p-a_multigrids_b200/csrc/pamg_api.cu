@@ -1288,6 +1288,101 @@ int pamg_apply_local_minv(pamg_handle* h, int n, int batch, const double* M, con
   return PAMG_OK;
 }
 
+// ---- output (get_vtu, get_vtk_files.F90:10-140; get_error transport_tri_semi.F90:531-540) ---------------------
+namespace {
+int output_fields(pamg_handle* h, double* x_all, double* analytical, double* error) {
+  LevelDev& L = h->lev[0];
+  const size_t n = (size_t)L.nelem;
+  double* d = nullptr;
+  CK(cudaMalloc(&d, n * 12 * sizeof(double)));
+  OutArgs a;
+  a.xg = h->xg; a.T = tnew_ptr(L); a.x_all = x_all ? d : nullptr; a.analytical = analytical ? d + n * 6 : nullptr;
+  a.error = error ? d + n * 9 : nullptr; a.nelem = L.nelem; a.s = L.s;
+  k_output_fields<<<grid_for(h, L.nelem), TPB, 0, h->stream>>>(a);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (x_all) cudaMemcpyAsync(x_all, d, n * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (analytical) cudaMemcpyAsync(analytical, d + n * 6, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (error) cudaMemcpyAsync(error, d + n * 9, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e2 = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  if (e != cudaSuccess || e2 != cudaSuccess) return fail(h, PAMG_ERR_CUDA, cudaGetErrorString(e != cudaSuccess ? e : e2));
+  return PAMG_OK;
+}
+}  // namespace
+
+int pamg_output_fields(pamg_handle* h, double* x_all, double* analytical, double* error) {
+  if (!h || h->lev.empty() || (!x_all && !analytical && !error)) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  return output_fields(h, x_all, analytical, error);
+}
+
+int pamg_write_vtu(pamg_handle* h, const char* path, const char* solve_for, int binary) {
+  if (!h || h->lev.empty() || !path || !solve_for) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  LevelDev& L = h->lev[0];
+  const size_t n = (size_t)L.nelem;
+  std::vector<double> X(n * 6), T(n * 3), An(n * 3), Er(n * 3);
+  int rc = output_fields(h, X.data(), An.data(), Er.data());
+  if (rc) return rc;
+  CK(cudaMemcpy(T.data(), tnew_ptr(L), n * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+  FILE* f = fopen(path, binary ? "wb" : "w");
+  if (!f) return fail(h, PAMG_ERR_IO, std::string("cannot open ") + path);
+  const unsigned long long npts = 3ull * n;
+  fprintf(f, "<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\"%s>\n", binary ? " header_type=\"UInt64\"" : "");
+  fprintf(f, "  <UnstructuredGrid>\n    <Piece NumberOfPoints=\"%llu\" NumberOfCells=\"%llu\">\n", npts, (unsigned long long)n);
+  fprintf(f, "      <PointData Scalars=\"scalars\">\n");
+  if (!binary) {
+    // the reference's layout: one value per line, F12.10 for the unknown, F10.7 for error / analytical, F10.3 coordinates
+    const double* arr[3] = {T.data(), Er.data(), An.data()};
+    const char* names[3] = {solve_for, "error", "analytical"};
+    for (int k = 0; k < 3; ++k) {
+      fprintf(f, "        <DataArray type=\"Float32\" Name=\"%s\" Format=\"ascii\">\n", names[k]);
+      for (size_t i = 0; i < n * 3; ++i) fprintf(f, k == 0 ? "          %12.10f  \n" : "          %10.7f  \n", arr[k][i]);
+      fprintf(f, "        </DataArray>\n");
+    }
+    fprintf(f, "      </PointData>\n      <Points>\n        <DataArray type=\"Float32\" NumberOfComponents=\"3\" Format=\"ascii\">\n");
+    for (size_t i = 0; i < n * 3; ++i) fprintf(f, "          %.3f %.3f %.3f   \n", X[2 * i], X[2 * i + 1], 0.0);
+    fprintf(f, "        </DataArray>\n      </Points>\n      <Cells>\n        <DataArray type=\"Int32\" Name=\"connectivity\" Format=\"ascii\">\n");
+    for (size_t e = 0; e < n; ++e) fprintf(f, "          %zu %zu %zu\n", 3 * e, 3 * e + 1, 3 * e + 2);
+    fprintf(f, "        </DataArray>\n        <DataArray type=\"Int32\" Name=\"offsets\" Format=\"ascii\">\n          ");
+    for (size_t e = 1; e <= n; ++e) fprintf(f, e == 1 ? "%zu" : "  %zu", 3 * e);
+    fprintf(f, "\n        </DataArray>\n        <DataArray type=\"Int32\" Name=\"types\" Format=\"ascii\">\n          ");
+    for (size_t e = 0; e < n; ++e) fprintf(f, e == 0 ? "5" : " 5");                  // cell_type 5 = VTK_TRIANGLE (main.F90)
+    fprintf(f, "\n        </DataArray>\n      </Cells>\n    </Piece>\n  </UnstructuredGrid>\n</VTKFile>\n");
+  } else {
+    // raw appended data, Float64 fields: [UInt64 byte count][payload] per array, offsets relative to the '_' marker
+    unsigned long long off = 0;
+    const char* names[3] = {solve_for, "error", "analytical"};
+    for (int k = 0; k < 3; ++k) {
+      fprintf(f, "        <DataArray type=\"Float64\" Name=\"%s\" format=\"appended\" offset=\"%llu\"/>\n", names[k], off);
+      off += 8 + npts * 8;
+    }
+    fprintf(f, "      </PointData>\n      <Points>\n        <DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"appended\" offset=\"%llu\"/>\n      </Points>\n", off);
+    off += 8 + npts * 24;
+    fprintf(f, "      <Cells>\n        <DataArray type=\"Int64\" Name=\"connectivity\" format=\"appended\" offset=\"%llu\"/>\n", off);
+    off += 8 + npts * 8;
+    fprintf(f, "        <DataArray type=\"Int64\" Name=\"offsets\" format=\"appended\" offset=\"%llu\"/>\n", off);
+    off += 8 + n * 8;
+    fprintf(f, "        <DataArray type=\"UInt8\" Name=\"types\" format=\"appended\" offset=\"%llu\"/>\n", off);
+    fprintf(f, "      </Cells>\n    </Piece>\n  </UnstructuredGrid>\n  <AppendedData encoding=\"raw\">\n   _");
+    auto block = [&](const void* p, unsigned long long bytes) { fwrite(&bytes, 8, 1, f); fwrite(p, 1, bytes, f); };
+    block(T.data(), npts * 8); block(Er.data(), npts * 8); block(An.data(), npts * 8);
+    std::vector<double> P3(npts * 3);
+    for (size_t i = 0; i < npts; ++i) { P3[3 * i] = X[2 * i]; P3[3 * i + 1] = X[2 * i + 1]; P3[3 * i + 2] = 0.0; }
+    block(P3.data(), npts * 24);
+    std::vector<long long> conn(npts), offs(n);
+    for (size_t i = 0; i < npts; ++i) conn[i] = (long long)i;
+    for (size_t e = 0; e < n; ++e) offs[e] = 3ll * (long long)(e + 1);
+    block(conn.data(), npts * 8); block(offs.data(), n * 8);
+    std::vector<unsigned char> types(n, 5);
+    block(types.data(), n);
+    fprintf(f, "\n  </AppendedData>\n</VTKFile>\n");
+  }
+  if (fclose(f) != 0) return fail(h, PAMG_ERR_IO, std::string("write failed: ") + path);
+  return PAMG_OK;
+}
+
 // ---- timing helpers --------------------------------------------------------------------------------
 int pamg_sync(pamg_handle* h) {
   if (!h) return PAMG_ERR_ARG;

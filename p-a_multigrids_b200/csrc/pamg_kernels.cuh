@@ -1296,6 +1296,38 @@ __global__ void __launch_bounds__(TPB) k_prolong_p1(XferArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// output side (get_vtu call site transport_tri_semi.F90:299-312): child coordinates x_all_str (:274), the
+// analytical field boundary(x,y) = sin(x+y) (:278, splitting.F90:1401-1405) and get_error (:531-540).
+struct OutArgs {
+  const double* xg; const double* T;
+  double* x_all;     // [nelem][3][2] or nullptr
+  double* analytical;  // [nelem][3] or nullptr
+  double* error;       // [nelem][3] or nullptr
+  long long nelem; int s;
+};
+
+__global__ void __launch_bounds__(TPB) k_output_fields(OutArgs a) {
+  const int twos = 2 * a.s;
+  const long long Cmask = (1ll << twos) - 1;
+  for (long long g = (long long)blockIdx.x * TPB + threadIdx.x; g < a.nelem; g += (long long)gridDim.x * TPB) {
+    const int u = (int)(g >> twos);
+    int r, ipos, len;
+    child_from_ele0((int)(g & Cmask), a.s, r, ipos, len);
+    double x[3][2];
+    child_nodes(a.xg + (size_t)u * 6, a.s, r, ipos, x);
+    if (a.x_all)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { a.x_all[g * 6 + 2 * i] = x[i][0]; a.x_all[g * 6 + 2 * i + 1] = x[i][1]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double an = sin(x[i][0] + x[i][1]);
+      if (a.analytical) a.analytical[g * 3 + i] = an;
+      if (a.error) a.error[g * 3 + i] = fabs(a.T[g * 3 + i] - an);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(TPB) k_fill(double* p, long long n, double v) {
   for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += (long long)gridDim.x * TPB) p[i] = v;
 }

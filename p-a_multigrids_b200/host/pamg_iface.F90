@@ -205,6 +205,20 @@ module pamg_iface
       integer(c_int), value :: with_stab
     end function
 
+    ! get_vtu / get_error (get_vtk_files.F90:10, transport_tri_semi.F90:531)
+    integer(c_int) function pamg_output_fields(handle, x_all, analytical, error) bind(c, name="pamg_output_fields")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), intent(out) :: x_all(2, 3, *), analytical(3, *), error(3, *)
+    end function
+
+    integer(c_int) function pamg_write_vtu(handle, path, solve_for, binary) bind(c, name="pamg_write_vtu")
+      import :: c_int, c_ptr, c_char
+      type(c_ptr), value :: handle
+      character(kind=c_char), intent(in) :: path(*), solve_for(*)    ! null-terminated
+      integer(c_int), value :: binary
+    end function
+
     ! FINDInv (matrices.F90:1618), batched
     integer(c_int) function pamg_apply_local_minv(handle, n, batch, M, rhs, x, Minv, status) &
         bind(c, name="pamg_apply_local_minv")

@@ -105,6 +105,8 @@ def lib():
         "pamg_unstr_stab": (ci, [vp, _f64, cd, cd, cd, vp, vp]),
         "pamg_implicit_set_stab": (ci, [vp, ci]),
         "pamg_apply_local_minv": (ci, [vp, ci, ci, _f64, vp, vp, vp, vp]),
+        "pamg_output_fields": (ci, [vp, vp, vp, vp]),
+        "pamg_write_vtu": (ci, [vp, C.c_char_p, C.c_char_p, ci]),
         "pamg_sync": (ci, [vp]),
         "pamg_event_record": (ci, [vp, ci]),
         "pamg_event_elapsed_ms": (ci, [vp, ci, ci, C.POINTER(C.c_float)]),
@@ -377,6 +379,17 @@ class SemiImplicitIterative:
 
     def download_ptr(self, field, level, host_ptr):
         self._ck(self.L.pamg_download_field(self.h, field, level, host_ptr))
+
+    # -- output (get_vtu / get_error) --------------------------------------------------------------
+    def output_fields(self):
+        """(x_all_str (U,C,3,2), analytical, error) of level 1 (transport_tri_semi.F90:274,278,531-540)."""
+        sh = self.shape(1)
+        x = np.zeros(sh + (2,)); an = np.zeros(sh); er = np.zeros(sh)
+        self._ck(self.L.pamg_output_fields(self.h, _ptr(x), _ptr(an), _ptr(er)))
+        return x, an, er
+
+    def get_vtu(self, path, solve_for="Concentration", binary=False):
+        self._ck(self.L.pamg_write_vtu(self.h, str(path).encode(), solve_for.encode(), int(binary)))
 
     # -- unstructured explicit (unstr_explicit, transport_tri_unstr.F90:413) ------------------------
     def set_unstructured(self, mesh):
