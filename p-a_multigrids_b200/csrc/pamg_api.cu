@@ -24,7 +24,7 @@ using namespace pamg;
 namespace {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
-enum { ncclFloat64 = 8, ncclSum = 0, ncclMax = 2, ncclSuccess = 0 };
+enum { ncclUint8 = 1, ncclInt32 = 2, ncclFloat64 = 8, ncclSum = 0, ncclMax = 2, ncclMin = 3, ncclSuccess = 0 };
 struct NcclApi {
   void* lib = nullptr;
   int (*GetUniqueId)(ncclUniqueId*) = nullptr;
@@ -52,6 +52,9 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 }  // namespace
+
+struct pamg_handle;
+namespace { void p2p_close(pamg_handle* h); }
 
 // ------------------------------------------------------------------ handle
 struct LevelDev {
@@ -116,6 +119,16 @@ struct pamg_handle {
   // unstructured
   UnstrDev un;
   int un_use_dir = 0;
+  // halo exchange by direct stores into peer memory (CUDA IPC over NVLink); PAMG_P2P=0 keeps ncclSend/ncclRecv
+  bool p2p_enabled = true, p2p_ready = false, p2p_failed = false;
+  bool p2p_fuse = true;                // cut-face values go to the peers from inside k_halo (PAMG_P2P_FUSE=0: separate kernel)
+  unsigned long long* p2p_sync = nullptr;   // exchange number, block counter, error word (local)
+  uint4* p2p_stage = nullptr;               // flagged receive staging, 2 parities x p2p_stage_words (IPC-exported)
+  long long p2p_stage_words = 0;
+  struct P2PPeer { int slot_at_peer = -1, strip_begin_at_peer = 0; uint4* stage = nullptr; };
+  std::vector<P2PPeer> p2p_peers;      // same order as plan.peers
+  std::vector<void*> p2p_opened;       // IPC mappings to close
+  unsigned long long p2p_timeout_ns = 20000000000ull;
 };
 
 namespace {
@@ -261,11 +274,108 @@ void parent_coefficients(const pamg_params& p, const double* Xall, const int32_t
 
 int launch_halo(pamg_handle* h, int level, int what = 0);
 
+void p2p_close(pamg_handle* h) {
+  for (void* p : h->p2p_opened) cudaIpcCloseMemHandle(p);
+  h->p2p_opened.clear();
+  if (h->p2p_sync) { cudaFree(h->p2p_sync); h->p2p_sync = nullptr; }
+  if (h->p2p_stage) { cudaFree(h->p2p_stage); h->p2p_stage = nullptr; }
+  h->p2p_ready = false; h->p2p_failed = false;
+  for (auto& pp : h->p2p_peers) pp.stage = nullptr;
+}
+
+// collective over all ranks (called at the first exchange, never during stream capture): allocate the flagged
+// staging buffer, exchange its CUDA IPC handle, map the peers' buffers, agree on the outcome
+int p2p_setup(pamg_handle* h) {
+  const int R = h->nranks;
+  int ok = 1;
+  if ((int)h->plan.peers.size() > P2P_MAXP) ok = 0;
+  for (const auto& pp : h->p2p_peers) if (pp.slot_at_peer < 0) ok = 0;
+  long long strips = 0;
+  for (const auto& pr : h->plan.peers) strips = std::max(strips, (long long)pr.strip_begin + pr.nfaces);
+  h->p2p_stage_words = strips * 3 * h->lev[0].S;
+  const size_t stage_bytes = (size_t)std::max(1ll, 2 * h->p2p_stage_words) * sizeof(uint4);
+  if (cudaMalloc(&h->p2p_sync, P2P_WORDS * sizeof(unsigned long long)) != cudaSuccess) { h->p2p_sync = nullptr; ok = 0; }
+  else CK(cudaMemset(h->p2p_sync, 0, P2P_WORDS * sizeof(unsigned long long)));
+  if (cudaMalloc(&h->p2p_stage, stage_bytes) != cudaSuccess) { h->p2p_stage = nullptr; ok = 0; }
+  else CK(cudaMemset(h->p2p_stage, 0, stage_bytes));
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  if (ok && cudaIpcGetMemHandle(&mine, h->p2p_stage) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+  // all-gather of the handles with grouped send / recv (R <= 8)
+  const size_t hb = sizeof(cudaIpcMemHandle_t);
+  std::vector<cudaIpcMemHandle_t> all(R);
+  unsigned char *d_mine = nullptr, *d_all = nullptr;
+  int* d_ok = nullptr;
+  CK(cudaMalloc(&d_mine, hb)); CK(cudaMalloc(&d_all, hb * R)); CK(cudaMalloc(&d_ok, sizeof(int)));
+  CK(cudaMemcpy(d_mine, &mine, hb, cudaMemcpyHostToDevice));
+  g_nccl.GroupStart();
+  for (int r = 0; r < R; ++r) {
+    g_nccl.Send(d_mine, hb, ncclUint8, r, h->comm, h->stream);
+    g_nccl.Recv(d_all + hb * r, hb, ncclUint8, r, h->comm, h->stream);
+  }
+  if (g_nccl.GroupEnd() != ncclSuccess) return fail(h, PAMG_ERR_CUDA, "handle exchange failed");
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(all.data(), d_all, hb * R, cudaMemcpyDeviceToHost));
+  if (ok) {
+    for (size_t i = 0; i < h->plan.peers.size(); ++i) {
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[h->plan.peers[i].part], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+      h->p2p_opened.push_back(ptr);
+      h->p2p_peers[i].stage = (uint4*)ptr;
+    }
+  }
+  // every rank must take the same path
+  CK(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+  if (g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, h->comm, h->stream) != ncclSuccess) return fail(h, PAMG_ERR_CUDA, "ncclAllReduce failed");
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(d_mine); cudaFree(d_all); cudaFree(d_ok);
+  if (ok) h->p2p_ready = true; else h->p2p_failed = true;
+  return PAMG_OK;
+}
+
+int p2p_args(pamg_handle* h, LevelDev& L, double* ovl, P2PArgs& a) {
+  const long long S3 = 3ll * L.S;
+  const int base = h->plan.peers[0].send_begin;
+  a.send = ovl + ((size_t)h->plan.nstrips + base) * S3;
+  a.strips = ovl; a.stage = h->p2p_stage; a.stage_words = h->p2p_stage_words;
+  a.sync = h->p2p_sync; a.npeers = (int)h->plan.peers.size(); a.timeout_ns = h->p2p_timeout_ns;
+  long long so = 0, ro = 0;
+  for (int i = 0; i < a.npeers; ++i) {
+    const auto& pr = h->plan.peers[i];
+    if ((long long)(pr.send_begin - base) * S3 != so) return fail(h, PAMG_ERR_STATE, "send slots are not contiguous per peer");
+    a.remote[i] = h->p2p_peers[i].stage + (long long)h->p2p_peers[i].strip_begin_at_peer * S3;
+    a.soff[i] = so; a.roff[i] = ro; a.rbeg[i] = (long long)pr.strip_begin * S3;
+    so += pr.nfaces * S3; ro += pr.nfaces * S3;
+  }
+  a.soff[a.npeers] = so; a.roff[a.npeers] = ro;
+  a.send_base = base;
+  return PAMG_OK;
+}
+
+int p2p_exchange(pamg_handle* h, LevelDev& L, double* ovl) {
+  P2PArgs a;
+  int rc = p2p_args(h, L, ovl, a);
+  if (rc) return rc;
+  const long long so = a.soff[a.npeers];
+  static const int maxgrid = getenv("PAMG_P2P_GRID") ? std::max(1, atoi(getenv("PAMG_P2P_GRID"))) : 32;
+  const int grid = (int)std::max(1ll, std::min((so + 2 * TPB - 1) / (2 * TPB), (long long)maxgrid));
+  k_p2p_exchange<<<grid, TPB, 0, h->stream>>>(a);
+  h->launches++;
+  CK(cudaGetLastError());
+  return PAMG_OK;
+}
+
 // exchange of the cut-face strips (one process per GPU): the send slots follow the local strips in the
 // strip space; the receive range of a peer is a contiguous range of my own strips (pamg_plan.cpp)
 int exchange_halo(pamg_handle* h, LevelDev& L, double* ovl) {
   if (h->plan.peers.empty()) return PAMG_OK;
   if (!h->comm) return fail(h, PAMG_ERR_STATE, "partitioned mesh but pamg_comm_init was not called");
+  if (h->p2p_enabled && !h->p2p_ready && !h->p2p_failed && !h->capturing && h->level_offset == 0) {
+    int rc = p2p_setup(h);
+    if (rc) return rc;
+  }
+  if (h->p2p_ready) return p2p_exchange(h, L, ovl);
   const size_t S3 = (size_t)3 * L.S;
   g_nccl.GroupStart();
   for (const auto& pr : h->plan.peers) {
@@ -289,11 +399,30 @@ int launch_halo(pamg_handle* h, int level, int what) {
   a.bc_scale = (h->p.coarse_bc_zero && level + h->level_offset > 1) ? 0.0 : 1.0;
   a.U = h->U; a.s = L.s; a.with_old = (what == 0) ? 1 : 0; a.what = what; a.nstrips = h->plan.nstrips;
   const long long n = (long long)h->U * 3 * L.S;
-  k_halo<<<grid_for(h, n), TPB, 0, h->stream>>>(a);
+  a.x.npeers = 0;
+  const bool cut = what != 1 && !h->plan.peers.empty();
+  if (cut && h->comm && h->p2p_enabled && !h->p2p_ready && !h->p2p_failed && !h->capturing && h->level_offset == 0) {
+    int rc = p2p_setup(h);      // collective, first exchange only
+    if (rc) return rc;
+  }
+  const bool fused_x = cut && h->p2p_ready && h->p2p_fuse;
+  if (fused_x) { int rc = p2p_args(h, L, L.ovlb[L.ovl_cur], a.x); if (rc) return rc; }
+  // with the exchange fused in, blocks poll for remote data after their own work: keep the grid within one wave
+  int hgrid = grid_for(h, n);
+  if (fused_x) {
+    static int halo_resident = 0;
+    if (halo_resident == 0) {
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&halo_resident, k_halo, TPB, 0));
+      if (halo_resident < 1) halo_resident = 1;
+    }
+    hgrid = std::min(hgrid, h->nsm * std::min(halo_resident, 4));
+  }
+  k_halo<<<hgrid, TPB, 0, h->stream>>>(a);
   h->launches++;
   CK(cudaGetLastError());
   if (what == 1) return PAMG_OK;
   L.strips_valid = true;
+  if (fused_x) return PAMG_OK;
   return exchange_halo(h, L, L.ovlb[L.ovl_cur]);
 }
 
@@ -712,6 +841,10 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
     else if (e && !strcmp(e, "stream")) h->kernel_mode = 2;
     else if (e && !strcmp(e, "direct2")) h->kernel_mode = 3;
     else if (e && !strcmp(e, "win")) h->kernel_mode = 4;
+    const char* pp = getenv("PAMG_P2P");
+    if (pp && pp[0] == '0') h->p2p_enabled = false;
+    const char* pf = getenv("PAMG_P2P_FUSE");
+    if (pf && pf[0] == '0') h->p2p_fuse = false;
     const char* gr = getenv("PAMG_GRAPH");
     if (gr && gr[0] == '0') h->use_graph = false;
     const char* gn = getenv("PAMG_GRAPH_NCCL");
@@ -745,6 +878,7 @@ void pamg_destroy(pamg_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->agg) { pamg_destroy(h->agg); h->agg = nullptr; }
   if (h->comm) g_nccl.CommDestroy(h->comm);
+  p2p_close(h);
   free_levels(h);
   unstr_free(h->un);
   cudaFree(h->out3); cudaFreeHost(h->out3_host); cudaFree(h->scratch);
@@ -767,6 +901,18 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
   free_levels(h);
   if (h->agg) { pamg_destroy(h->agg); h->agg = nullptr; }
   h->agg_level = 0;
+  // where my cut-face strips live in every peer's strip space (the peer's own plan, rebuilt here on the host)
+  p2p_close(h);
+  h->p2p_peers.assign(h->plan.peers.size(), pamg_handle::P2PPeer());
+  for (size_t i = 0; i < h->plan.peers.size(); ++i) {
+    HaloPlan theirs;
+    if (build_halo_plan(U_global, X, neig, fneig, dir, h->p.halo_rule, nparts, part_first, h->plan.peers[i].part, theirs)) continue;
+    for (size_t j = 0; j < theirs.peers.size(); ++j)
+      if (theirs.peers[j].part == my_part && theirs.peers[j].nfaces == h->plan.peers[i].nfaces) {
+        h->p2p_peers[i].slot_at_peer = (int)j;
+        h->p2p_peers[i].strip_begin_at_peer = theirs.peers[j].strip_begin;
+      }
+  }
   const int U = h->plan.U_local, first = h->plan.first;
   if (U < 1) return fail(h, PAMG_ERR_ARG, "empty partition");
   h->U = U; h->U_global = U_global;
@@ -1388,6 +1534,11 @@ int pamg_sync(pamg_handle* h) {
   if (!h) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
+  if (h->p2p_ready) {      // a halo exchange that gave up waiting for a peer raised the error word instead of hanging
+    unsigned long long err = 0;
+    CK(cudaMemcpy(&err, h->p2p_sync + P2P_ERR, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err) return fail(h, PAMG_ERR_CUDA, "halo exchange timed out waiting for a peer GPU");
+  }
   return PAMG_OK;
 }
 

@@ -1070,7 +1070,95 @@ __global__ void __launch_bounds__(1024) k_reduce_partials(const double* partial,
 
 // ------------------------------------------------------------------------------------------------
 // update_overlaps (splitting.F90:1210-1397): one thread per (parent, side, position)
+// ------------------------------------------------------------------------------------------------
+// update_overlaps across GPUs without a library collective.  Every GPU STORES its cut-face strips straight into
+// a staging buffer of its peers over NVLink (peer pointers from CUDA IPC) in a flagged format: a double travels as
+// two 8-byte words {low 32 bits, exchange number} {high 32 bits, exchange number}; an aligned 8-byte store is
+// atomic, so the receiver simply polls every word of its own staging buffer until it carries the number of this
+// exchange and unpacks it into the strip buffer.  No fence, no separate flag, no credit: the latency is one
+// NVLink one-way trip.  The staging buffer is double-buffered by the parity of the exchange number (a sender can
+// only be one exchange ahead of a receiver because it needs the receiver's data to get any further), and the
+// exchange number lives in device memory so that a captured CUDA graph replays correctly.  Polling has a time-out
+// that raises sync[P2P_ERR] instead of hanging the GPU.
+constexpr int P2P_MAXP = 16;
+enum { P2P_EPOCH = 0, P2P_COUNT = 1, P2P_ERR = 2, P2P_WORDS = 8 };
+struct P2PArgs {
+  const double* send;                 // my send slots of this level (contiguous, grouped per peer)
+  int send_base;                      // first send slot (in strips) of peer 0, relative to the send-slot space
+  double* strips;                     // my strip buffer of this level (receive side)
+  uint4* remote[P2P_MAXP];            // each peer's staging buffer (parity 0), already offset to my range there
+  long long soff[P2P_MAXP + 1];       // prefix offsets (doubles) of the per-peer send ranges
+  long long rbeg[P2P_MAXP];           // first double of the strips I receive from each peer
+  long long roff[P2P_MAXP + 1];       // prefix offsets (doubles) of the per-peer receive ranges
+  uint4* stage;                       // my staging buffer (parity 0)
+  long long stage_words;              // words per parity
+  unsigned long long* sync;           // exchange number, block counter, error word
+  int npeers;
+  unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ unsigned long long p2p_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// one double into the staging buffer of peer p (idx = offset in doubles inside my range there)
+__device__ __forceinline__ void p2p_put(const P2PArgs& a, long long par, unsigned e, int p, long long idx, double val) {
+  const unsigned long long v = (unsigned long long)__double_as_longlong(val);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(a.remote[p] + par + idx), "r"((unsigned)v), "r"(e),
+               "r"((unsigned)(v >> 32)), "r"(e) : "memory");
+}
+
+// poll my staging buffer, unpack into the strips, and let the last block advance the exchange number
+__device__ __forceinline__ void p2p_receive(const P2PArgs& a, unsigned long long e64) {
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  const unsigned e = (unsigned)e64;
+  const long long par = (long long)(e64 & 1) * a.stage_words;
+  const long long nr = a.roff[a.npeers];
+  volatile unsigned long long* err = a.sync + P2P_ERR;
+  for (long long i = (long long)blockIdx.x * TPB + tid; i < nr; i += (long long)gridDim.x * TPB) {
+    int p = 0;
+    while (i >= a.roff[p + 1]) ++p;
+    const long long j = a.rbeg[p] + (i - a.roff[p]);
+    const uint4* src = a.stage + par + j;
+    uint4 w;
+    unsigned long long t0 = 0;
+    bool ok = true;
+    for (unsigned spins = 0;; ++spins) {
+      asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(src) : "memory");
+      if (w.y == e && w.w == e) break;
+      if ((spins & 1023u) == 1023u) {
+        if (*err) { ok = false; break; }
+        const unsigned long long t = p2p_now();
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > a.timeout_ns) { *err = 1; ok = false; break; }
+      }
+    }
+    if (ok) a.strips[j] = __longlong_as_double((long long)(((unsigned long long)w.z << 32) | w.x));
+  }
+  __syncthreads();
+  if (tid == 0) { __threadfence(); s_last = (atomicAdd(a.sync + P2P_COUNT, 1ull) == (unsigned long long)gridDim.x - 1); }
+  __syncthreads();
+  if (s_last && tid == 0) { a.sync[P2P_COUNT] = 0; *(volatile unsigned long long*)(a.sync + P2P_EPOCH) = e64; __threadfence(); }
+}
+
+// stand-alone exchange of already packed send slots
+__global__ void __launch_bounds__(TPB) k_p2p_exchange(P2PArgs a) {
+  const unsigned long long e64 = *(volatile unsigned long long*)(a.sync + P2P_EPOCH) + 1;   // this exchange
+  const long long par = (long long)(e64 & 1) * a.stage_words;
+  const long long ns = a.soff[a.npeers];
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < ns; i += (long long)gridDim.x * TPB) {
+    int p = 0;
+    while (i >= a.soff[p + 1]) ++p;
+    p2p_put(a, par, (unsigned)e64, p, i - a.soff[p], a.send[i]);
+  }
+  p2p_receive(a, e64);
+}
+
 struct HaloArgs {
+  P2PArgs x;                               // x.npeers > 0: cut-face strips go straight to the peers (fused exchange)
   const double* tnew; const double* told;
   double* ovl; double* ovl_old;           // strip space: local strips then send slots
   const double* xg;                        // [U][6] X3, X1-X3, X2-X3
@@ -1102,6 +1190,9 @@ __device__ __forceinline__ void child_nodes(const double* __restrict__ xg, int s
 __global__ void __launch_bounds__(TPB) k_halo(HaloArgs a) {
   const int S = 1 << a.s, b = 2 << a.s;
   const long long n = (long long)a.U * 3 * S;
+  unsigned long long e64 = 0;
+  if (a.x.npeers > 0) e64 = *(volatile unsigned long long*)(a.x.sync + P2P_EPOCH) + 1;
+  const long long par = (long long)(e64 & 1) * a.x.stage_words;
   for (long long tid = (long long)blockIdx.x * TPB + threadIdx.x; tid < n; tid += (long long)gridDim.x * TPB) {
     const int i = (int)(tid & (S - 1));           // position - 1
     const int lf = (int)(tid >> a.s);             // u*3 + mf
@@ -1131,10 +1222,21 @@ __global__ void __launch_bounds__(TPB) k_halo(HaloArgs a) {
       const int slot = __ldg(a.rev + lf) ? (S - pos) : (pos - 1);
       const size_t o = (size_t)dst * S3 + (size_t)slot * 3;
       const size_t src = (((size_t)u << (2 * a.s)) + ele - 1) * 3;
-      a.ovl[o] = a.tnew[src]; a.ovl[o + 1] = a.tnew[src + 1]; a.ovl[o + 2] = a.tnew[src + 2];
+      const double v0 = a.tnew[src], v1 = a.tnew[src + 1], v2 = a.tnew[src + 2];
+      a.ovl[o] = v0; a.ovl[o + 1] = v1; a.ovl[o + 2] = v2;
       if (a.with_old) { a.ovl_old[o] = a.told[src]; a.ovl_old[o + 1] = a.told[src + 1]; a.ovl_old[o + 2] = a.told[src + 2]; }
+      if (a.x.npeers > 0 && dst >= a.nstrips) {
+        // face cut by the GPU partition: the same three values also go straight into the neighbour GPU's staging buffer
+        const long long q = (long long)(dst - a.nstrips - a.x.send_base) * (long long)S3 + (long long)slot * 3;
+        int p = 0;
+        while (q >= a.x.soff[p + 1]) ++p;
+        p2p_put(a.x, par, (unsigned)e64, p, q - a.x.soff[p], v0);
+        p2p_put(a.x, par, (unsigned)e64, p, q - a.x.soff[p] + 1, v1);
+        p2p_put(a.x, par, (unsigned)e64, p, q - a.x.soff[p] + 2, v2);
+      }
     }
   }
+  if (a.x.npeers > 0) p2p_receive(a.x, e64);
 }
 
 // ------------------------------------------------------------------------------------------------
