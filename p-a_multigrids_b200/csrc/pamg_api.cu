@@ -125,7 +125,7 @@ struct pamg_handle {
   unsigned long long* p2p_sync = nullptr;   // exchange number, block counter, error word (local)
   uint4* p2p_stage = nullptr;               // flagged receive staging, 2 parities x p2p_stage_words (IPC-exported)
   long long p2p_stage_words = 0;
-  struct P2PPeer { int slot_at_peer = -1, strip_begin_at_peer = 0; uint4* stage = nullptr; };
+  struct P2PPeer { int slot_at_peer = -1, strip_begin_at_peer = 0; long long recv_strips_at_peer = 0; uint4* stage = nullptr; };
   std::vector<P2PPeer> p2p_peers;      // same order as plan.peers
   std::vector<void*> p2p_opened;       // IPC mappings to close
   unsigned long long p2p_timeout_ns = 20000000000ull;
@@ -345,6 +345,7 @@ int p2p_args(pamg_handle* h, LevelDev& L, double* ovl, P2PArgs& a) {
     const auto& pr = h->plan.peers[i];
     if ((long long)(pr.send_begin - base) * S3 != so) return fail(h, PAMG_ERR_STATE, "send slots are not contiguous per peer");
     a.remote[i] = h->p2p_peers[i].stage + (long long)h->p2p_peers[i].strip_begin_at_peer * S3;
+    a.rstride[i] = h->p2p_peers[i].recv_strips_at_peer * 3 * h->lev[0].S;   // the peer's own p2p_stage_words
     a.soff[i] = so; a.roff[i] = ro; a.rbeg[i] = (long long)pr.strip_begin * S3;
     so += pr.nfaces * S3; ro += pr.nfaces * S3;
   }
@@ -907,6 +908,8 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
   for (size_t i = 0; i < h->plan.peers.size(); ++i) {
     HaloPlan theirs;
     if (build_halo_plan(U_global, X, neig, fneig, dir, h->p.halo_rule, nparts, part_first, h->plan.peers[i].part, theirs)) continue;
+    for (size_t j = 0; j < theirs.peers.size(); ++j)
+      h->p2p_peers[i].recv_strips_at_peer = std::max(h->p2p_peers[i].recv_strips_at_peer, (long long)theirs.peers[j].strip_begin + theirs.peers[j].nfaces);
     for (size_t j = 0; j < theirs.peers.size(); ++j)
       if (theirs.peers[j].part == my_part && theirs.peers[j].nfaces == h->plan.peers[i].nfaces) {
         h->p2p_peers[i].slot_at_peer = (int)j;

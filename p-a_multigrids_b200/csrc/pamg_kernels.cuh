@@ -1087,6 +1087,7 @@ struct P2PArgs {
   int send_base;                      // first send slot (in strips) of peer 0, relative to the send-slot space
   double* strips;                     // my strip buffer of this level (receive side)
   uint4* remote[P2P_MAXP];            // each peer's staging buffer (parity 0), already offset to my range there
+  long long rstride[P2P_MAXP];        // words per parity of each peer's staging buffer
   long long soff[P2P_MAXP + 1];       // prefix offsets (doubles) of the per-peer send ranges
   long long rbeg[P2P_MAXP];           // first double of the strips I receive from each peer
   long long roff[P2P_MAXP + 1];       // prefix offsets (doubles) of the per-peer receive ranges
@@ -1104,9 +1105,9 @@ __device__ __forceinline__ unsigned long long p2p_now() {
 }
 
 // one double into the staging buffer of peer p (idx = offset in doubles inside my range there)
-__device__ __forceinline__ void p2p_put(const P2PArgs& a, long long par, unsigned e, int p, long long idx, double val) {
+__device__ __forceinline__ void p2p_put(const P2PArgs& a, unsigned e, int p, long long idx, double val) {
   const unsigned long long v = (unsigned long long)__double_as_longlong(val);
-  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(a.remote[p] + par + idx), "r"((unsigned)v), "r"(e),
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(a.remote[p] + (long long)(e & 1u) * a.rstride[p] + idx), "r"((unsigned)v), "r"(e),
                "r"((unsigned)(v >> 32)), "r"(e) : "memory");
 }
 
@@ -1147,12 +1148,11 @@ __device__ __forceinline__ void p2p_receive(const P2PArgs& a, unsigned long long
 // stand-alone exchange of already packed send slots
 __global__ void __launch_bounds__(TPB) k_p2p_exchange(P2PArgs a) {
   const unsigned long long e64 = *(volatile unsigned long long*)(a.sync + P2P_EPOCH) + 1;   // this exchange
-  const long long par = (long long)(e64 & 1) * a.stage_words;
   const long long ns = a.soff[a.npeers];
   for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < ns; i += (long long)gridDim.x * TPB) {
     int p = 0;
     while (i >= a.soff[p + 1]) ++p;
-    p2p_put(a, par, (unsigned)e64, p, i - a.soff[p], a.send[i]);
+    p2p_put(a, (unsigned)e64, p, i - a.soff[p], a.send[i]);
   }
   p2p_receive(a, e64);
 }
@@ -1192,7 +1192,6 @@ __global__ void __launch_bounds__(TPB) k_halo(HaloArgs a) {
   const long long n = (long long)a.U * 3 * S;
   unsigned long long e64 = 0;
   if (a.x.npeers > 0) e64 = *(volatile unsigned long long*)(a.x.sync + P2P_EPOCH) + 1;
-  const long long par = (long long)(e64 & 1) * a.x.stage_words;
   for (long long tid = (long long)blockIdx.x * TPB + threadIdx.x; tid < n; tid += (long long)gridDim.x * TPB) {
     const int i = (int)(tid & (S - 1));           // position - 1
     const int lf = (int)(tid >> a.s);             // u*3 + mf
@@ -1230,9 +1229,9 @@ __global__ void __launch_bounds__(TPB) k_halo(HaloArgs a) {
         const long long q = (long long)(dst - a.nstrips - a.x.send_base) * (long long)S3 + (long long)slot * 3;
         int p = 0;
         while (q >= a.x.soff[p + 1]) ++p;
-        p2p_put(a.x, par, (unsigned)e64, p, q - a.x.soff[p], v0);
-        p2p_put(a.x, par, (unsigned)e64, p, q - a.x.soff[p] + 1, v1);
-        p2p_put(a.x, par, (unsigned)e64, p, q - a.x.soff[p] + 2, v2);
+        p2p_put(a.x, (unsigned)e64, p, q - a.x.soff[p], v0);
+        p2p_put(a.x, (unsigned)e64, p, q - a.x.soff[p] + 1, v1);
+        p2p_put(a.x, (unsigned)e64, p, q - a.x.soff[p] + 2, v2);
       }
     }
   }

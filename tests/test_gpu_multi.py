@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4])
 def test_partitioned_smoother_and_vcycle_match_single_gpu(world):
     if pamg.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
