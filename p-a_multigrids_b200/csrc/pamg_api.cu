@@ -993,7 +993,9 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
   // coarse-level agglomeration on part 0: first level whose GLOBAL size is small enough to be launch-bound
   if (nparts > 1 && h->level_offset == 0) {
     const char* e = getenv("PAMG_AGG_ELEMS");
-    const long long limit = e ? atoll(e) : (1ll << 21);     // elements of the whole mesh on that level; 0 disables
+    // elements of the whole mesh on that level; 0 disables.  With the halo exchange at ~1.5 us per sweep the break-even
+    // moved down: 2^21 cost 2.6 ms per solve at 4 GPUs against 2^17 (profiles/README.md)
+    const long long limit = e ? atoll(e) : (1ll << 17);
     int lvl = 0;
     for (int il = 2; il <= h->p.multi_levels; ++il)
       if (limit > 0 && (long long)U_global * h->lev[il - 1].C <= limit) { lvl = il; break; }
