@@ -33,7 +33,7 @@ UNIT = "DOF-updates/s"
 
 
 KERNEL_NAMES = {
-    "win": "k_element_win<JACOBI,face> (ring of 8 field tiles in shared memory via 1-D TMA, all neighbours from the ring)",
+    "win": "k_element_win2<JACOBI,face> (ring of 8 field tiles in shared memory via 1-D TMA, all neighbours from the ring, producer warp + named barriers)",
     "tma1d": "k_element_tma<JACOBI,face> (pipelined 1-D TMA tiles, vertical neighbour by global load)",
     "stream": "k_stream<JACOBI,face> (row streaming)", "direct2": "k_element_direct2<JACOBI,face>", "direct": "k_element<JACOBI,face>",
 }

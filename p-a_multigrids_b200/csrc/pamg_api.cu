@@ -102,6 +102,7 @@ struct pamg_handle {
   bool fused_halo = false;  // PAMG_FUSED_HALO=1: sweeps write the next sweep's strips themselves (measured slower: the extra work
                             // of the few children on parent faces delays the per-tile barrier; profiles/README.md)
   bool gs_tma = true;   // coloured GS pass through the TMA tile kernel (PAMG_GS=direct selects the direct kernel)
+  bool win_producer = true;  // window kernel with a producer warp (k_element_win2); PAMG_WIN=barrier: k_element_win
   bool gs_fused = true; // both colours in one pass (k_gs_win); PAMG_GS=twopass keeps the two in-place passes
   // per-kernel timing (element kernels only)
   bool profiling = false;
@@ -464,6 +465,19 @@ int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout,
     if (h->p.face_terms) k_stream<MODE, true><<<sgrid, SW, 0, h->stream>>>(sa);
     else k_stream<MODE, false><<<sgrid, SW, 0, h->stream>>>(sa);
     if (MODE == MODE_RESID) h->last_partials = sgrid;
+  } else if (MODE != MODE_GS && h->kernel_mode == 4 && h->win_producer && L.s >= 6 && L.s <= 8) {
+    // window kernel with a producer warp (no CTA-wide barrier between tiles)
+    auto kern = h->p.face_terms ? k_element_win2<MODE, true> : k_element_win2<MODE, false>;
+    static int resident_win2[2] = {0, 0};
+    int& resident = resident_win2[h->p.face_terms ? 1 : 0];
+    if (resident == 0) {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM_BYTES));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, WIN2_THREADS, WIN_SMEM_BYTES));
+      if (resident < 1) resident = 1;
+    }
+    const int tgrid = (int)std::max(1ll, std::min(L.nelem / TPB, (long long)h->nsm * resident));
+    kern<<<tgrid, WIN2_THREADS, WIN_SMEM_BYTES, h->stream>>>(a);
+    if (MODE == MODE_RESID) h->last_partials = tgrid;
   } else if ((MODE != MODE_GS || h->gs_tma) && h->kernel_mode == 4 && L.C >= TPB && L.s <= 8) {
     // (a vertical neighbour is up to 2^(s+1) children away: the 8-tile ring covers s <= 8)
     // window kernel: ring of 8 field tiles in shared memory, every neighbour value read from it
@@ -842,6 +856,9 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
     else if (e && !strcmp(e, "stream")) h->kernel_mode = 2;
     else if (e && !strcmp(e, "direct2")) h->kernel_mode = 3;
     else if (e && !strcmp(e, "win")) h->kernel_mode = 4;
+    const char* wp = getenv("PAMG_WIN");
+    if (wp && !strcmp(wp, "producer")) h->win_producer = true;
+    if (wp && !strcmp(wp, "barrier")) h->win_producer = false;
     const char* pp = getenv("PAMG_P2P");
     if (pp && pp[0] == '0') h->p2p_enabled = false;
     const char* pf = getenv("PAMG_P2P_FUSE");
@@ -1006,7 +1023,7 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
         ap.n_split = h->lev[lvl - 1].s;
         ap.multi_levels = h->p.multi_levels - lvl + 1;
         pamg_handle* g = new pamg_handle();
-        g->p = ap; g->device = h->device; g->nsm = h->nsm; g->kernel_mode = h->kernel_mode; g->gs_tma = h->gs_tma; g->gs_fused = h->gs_fused;
+        g->p = ap; g->device = h->device; g->nsm = h->nsm; g->kernel_mode = h->kernel_mode; g->gs_tma = h->gs_tma; g->gs_fused = h->gs_fused; g->win_producer = h->win_producer;
         g->stream = h->stream; g->shared_stream = true; g->level_offset = lvl - 1;
         for (auto& ev : g->ev) cudaEventCreate(&ev);
         cudaMalloc(&g->out3, 3 * sizeof(double));

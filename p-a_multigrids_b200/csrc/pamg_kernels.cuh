@@ -772,6 +772,194 @@ __global__ void __launch_bounds__(TPB, 3) k_element_win(ElemArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Window kernel with a PRODUCER WARP.  Same ring and arithmetic as k_element_win, but the ninth warp of the CTA does
+// all the copy-engine work (bulk loads, bulk stores, per-parent coefficient reloads) and the eight consumer warps
+// never wait for each other: after writing its results a consumer only ARRIVES on a named barrier (bar.arrive) and
+// goes on to the next tile as soon as that tile's data has landed; the producer is the one that waits (bar.sync)
+// before it stores the tile and refills the freed ring slots.  Per-parent coefficients are double-buffered by the
+// parity of the parent and published through the mbarrier of the first rhs tile of the parent, so the kernel needs
+// at least 8 tiles per parent (n_split >= 6 on the level); smaller levels use k_element_win.
+constexpr int WIN2_THREADS = TPB + 32;
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <int MODE, bool FACE>
+__global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
+  extern __shared__ __align__(128) unsigned char dsm[];   // WIN_SMEM_BYTES
+  double* sT = reinterpret_cast<double*>(dsm);
+  double* sB = sT + 3 * WIN_CH;
+  uint64_t* barT = reinterpret_cast<uint64_t*>(sB + 3 * TPB * WIN_NB);
+  uint64_t* barB = barT + WIN_NT;
+  __shared__ __align__(16) double sPC2[2][NPC];
+  __shared__ int sIdx2[2][8];
+  __shared__ double shp[3][TPB / 32];
+  const int s = a.s, twos = 2 * s, b = 2 << s, S = 1 << s;
+  const long long Cmask = (1ll << twos) - 1;
+  const int tid = threadIdx.x;
+  constexpr uint32_t TILE_BYTES = 3 * TPB * sizeof(double);
+  double acc_sum = 0.0, acc_abs = 0.0, acc_max = 0.0;
+  if (tid == 0) {
+    for (int i = 0; i < WIN_NT + WIN_NB; ++i) mbar_init(&barT[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long ntiles = a.nelem / TPB;
+  const long long per = (ntiles + gridDim.x - 1) / gridDim.x;
+  const long long tbeg = (long long)blockIdx.x * per, tend = min(ntiles, tbeg + per);
+  const long long tlo = max(0ll, tbeg - 2), thi = min(ntiles, tend + 2);
+
+  if (tid >= TPB) {
+    // ------------------------------------------------------------------ producer warp
+    const int lane = tid - TPB;
+    int u_loaded = -1;
+    auto issueT = [&](long long tile) {   // lane 0
+      const int sl = (int)(tile & (WIN_NT - 1));
+      mbar_expect_tx(&barT[sl], TILE_BYTES);
+      tma_load_1d(sT + sl * 3 * TPB, a.Tin + tile * 3 * TPB, TILE_BYTES, &barT[sl]);
+    };
+    auto issueB = [&](long long tile) {   // whole warp: a new parent's coefficients go out with its first rhs tile
+      const int u = (int)((tile * TPB) >> twos);
+      if (u != u_loaded) {
+        for (int i = lane; i < NPC; i += 32) sPC2[u & 1][i] = __ldg(a.pc + (size_t)u * NPC + i);
+        if (lane < 3) { sIdx2[u & 1][lane] = __ldg(a.strip_of + u * 3 + lane); sIdx2[u & 1][4 + lane] = __ldg(a.hmap + u * 3 + lane); }
+        u_loaded = u;
+        __syncwarp();
+      }
+      if (lane == 0) {
+        const int sl = (int)((tile - tbeg) & (WIN_NB - 1));
+        mbar_expect_tx(&barB[sl], TILE_BYTES);    // release: the coefficient writes above are visible to whoever waits on it
+        tma_load_1d(sB + sl * 3 * TPB, a.rhs + tile * 3 * TPB, TILE_BYTES, &barB[sl]);
+      }
+    };
+    if (tbeg < tend) {
+      if (lane == 0) for (long long t = tlo; t < min(thi, tbeg + 6); ++t) issueT(t);
+      for (long long t = tbeg; t < min(tend, tbeg + 3); ++t) issueB(t);
+    }
+    for (long long p = tbeg; p < tend; ++p) {
+      const int it = (int)(p - tbeg);
+      named_sync(1 + (it & 3), WIN2_THREADS);            // every consumer warp has written tile p
+      if (lane == 0) {
+        tma_store_1d(a.Tout + p * 3 * TPB, sB + (it & (WIN_NB - 1)) * 3 * TPB, TILE_BYTES);
+        tma_store_commit();
+        if (p + 6 < thi) issueT(p + 6);                  // ring slot of tile p-2: no consumer is behind tile p+1
+        if (p + 3 < tend) tma_store_wait_read1();        // rhs slot of tile p-1: its store has been read
+      }
+      __syncwarp();
+      if (p + 3 < tend) issueB(p + 3);
+    }
+    if (lane == 0) tma_store_wait_all();
+  } else {
+    // ------------------------------------------------------------------ consumer warps
+    struct Prep { int r, ipos, len; double h1a, h1b, h2a, h2b; };
+    auto prepare = [&](long long tile, int u_cur, Prep& p) {
+      p.r = 2; p.ipos = 2; p.len = 3; p.h1a = 0.0; p.h1b = 0.0; p.h2a = 0.0; p.h2b = 0.0;
+      if (tile >= tend) return;
+      const long long g = tile * TPB + tid;
+      child_from_ele0((int)(g & Cmask), s, p.r, p.ipos, p.len);
+      if (!FACE || !(p.ipos & 1)) return;
+      const bool f1 = p.r == 1, side = p.ipos == 1 || p.ipos == p.len;
+      if (f1 | side) {
+        const int u = (int)(g >> twos);
+        const bool same = u == u_cur;                    // the coefficients of u_cur have been acquired by this thread
+        const int* ix = sIdx2[u & 1];
+        if (f1) {
+          const int strip = same ? ix[0] : __ldg(a.strip_of + u * 3), hm = same ? ix[4] : __ldg(a.hmap + u * 3);
+          const double* e = a.ovl + ((size_t)strip * S + (p.ipos >> 1)) * 3;
+          p.h1a = __ldg(e + (hm & 3)); p.h1b = __ldg(e + (hm >> 2));
+        }
+        if (side) {
+          const int mf = (p.ipos == 1) ? 2 : 1;
+          const int strip = same ? ix[mf] : __ldg(a.strip_of + u * 3 + mf), hm = same ? ix[4 + mf] : __ldg(a.hmap + u * 3 + mf);
+          const double* e = a.ovl + ((size_t)strip * S + (p.r - 1)) * 3;
+          p.h2a = __ldg(e + (hm & 3)); p.h2b = __ldg(e + (hm >> 2));
+        }
+      }
+    };
+    Prep cur, nxt;
+    prepare(tbeg, -1, cur);
+    for (long long tile = tbeg; tile < tend; ++tile) {
+      const int it = (int)(tile - tbeg);
+      const long long g0 = tile * TPB;
+      const int u_tile = (int)(g0 >> twos);
+      if (it == 0) {
+        for (long long tw = tlo; tw <= min(tile + 2, thi - 1); ++tw) mbar_wait(&barT[tw & (WIN_NT - 1)], (uint32_t)(((tw - tlo) >> 3) & 1));
+      } else if (tile + 2 < thi) {
+        mbar_wait(&barT[(tile + 2) & (WIN_NT - 1)], (uint32_t)(((tile + 2 - tlo) >> 3) & 1));
+      }
+      mbar_wait(&barB[it & (WIN_NB - 1)], (uint32_t)((it / WIN_NB) & 1));     // also acquires the coefficients of u_tile
+      prepare(tile + 1, u_tile, nxt);
+      const double* sPC = sPC2[u_tile & 1];
+      double* bb = sB + (it & (WIN_NB - 1)) * 3 * TPB + tid * 3;
+      {
+        const int cw = (int)(g0 & (WIN_CH - 1)) + tid;
+        const double* t = sT + cw * 3;
+        const double T1 = t[0], T2 = t[1], T3 = t[2];
+        const bool up = cur.ipos & 1;
+        double o1, o2, o3;
+        FaceIn fi;
+        int bmask = 0;
+        bool interior = true;
+        const ParentRegs& P = *reinterpret_cast<const ParentRegs*>(sPC);
+        if (FACE) {
+          fi.pen1 = P.pi1; fi.pen2 = P.pi2; fi.pen3 = P.pi3;
+          const int dv = up ? (2 * cur.r - b - 2) : (b - 2 * cur.r);
+          const double* tv = sT + ((cw + dv) & (WIN_CH - 1)) * 3;
+          fi.n1a = tv[2]; fi.n1b = tv[0];
+          const double* tl = sT + ((cw - 1) & (WIN_CH - 1)) * 3;
+          const double* tr = sT + ((cw + 1) & (WIN_CH - 1)) * 3;
+          const double* t2 = up ? tl : tr;
+          const double* t3 = up ? tr : tl;
+          fi.n2a = t2[1]; fi.n2b = t2[2];
+          fi.n3a = t3[0]; fi.n3b = t3[1];
+          if (up && (cur.r == 1 || cur.ipos == 1 || cur.ipos == cur.len)) {
+            interior = false;
+            if (cur.r == 1) { fi.n1a = cur.h1a; fi.n1b = cur.h1b; fi.pen1 = P.px1; bmask |= 1; }
+            if (cur.ipos == 1) { fi.n2a = cur.h2a; fi.n2b = cur.h2b; fi.pen2 = P.px2; bmask |= 2; }
+            if (cur.ipos == cur.len) {
+              if (cur.len == 1) halo_pair(a, u_tile, 1, cur.r - 1, S, fi.n3a, fi.n3b);
+              else { fi.n3a = cur.h2a; fi.n3b = cur.h2b; }
+              fi.pen3 = P.px3; bmask |= 4;
+            }
+          }
+        }
+        if (FACE && MODE != MODE_RICH) {
+          const Folded& F = *reinterpret_cast<const Folded*>(sPC + PC_FOLD + (up ? 0 : 16));
+          elem_apply_folded<MODE>(F, sPC + PC_DPEN, bmask, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
+        } else {
+          elem_apply_regs<MODE, FACE>(P, up, interior, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.omega, a.rsign, o1, o2, o3);
+        }
+        bb[0] = o1; bb[1] = o2; bb[2] = o3;
+        if (MODE == MODE_RESID) {
+          acc_sum += o1 * o1 + o2 * o2 + o3 * o3;
+          acc_abs = fmax(acc_abs, fmax(fabs(o1), fmax(fabs(o2), fabs(o3))));
+          acc_max = fmax(acc_max, fmax(o1, fmax(o2, o3)));
+        }
+      }
+      fence_async_smem();
+      named_arrive(1 + (it & 3), WIN2_THREADS);          // no waiting: on to the next tile
+      cur = nxt;
+    }
+  }
+  if (MODE == MODE_RESID) {
+    if (tid < TPB) {
+      for (int o = 16; o > 0; o >>= 1) {
+        acc_sum += __shfl_xor_sync(0xffffffffu, acc_sum, o);
+        acc_abs = fmax(acc_abs, __shfl_xor_sync(0xffffffffu, acc_abs, o));
+        acc_max = fmax(acc_max, __shfl_xor_sync(0xffffffffu, acc_max, o));
+      }
+      if ((tid & 31) == 0) { shp[0][tid >> 5] = acc_sum; shp[1][tid >> 5] = acc_abs; shp[2][tid >> 5] = acc_max; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double s0 = 0, s1 = 0, s2 = 0;
+      for (int i = 0; i < TPB / 32; ++i) { s0 += shp[0][i]; s1 = fmax(s1, shp[1][i]); s2 = fmax(s2, shp[2][i]); }
+      double* partial = a.partial + (size_t)3 * a.partial_off;
+      partial[(size_t)blockIdx.x * 3 + 0] = s0; partial[(size_t)blockIdx.x * 3 + 1] = s1; partial[(size_t)blockIdx.x * 3 + 2] = s2;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Coloured Gauss-Seidel sweep in ONE pass over memory (out of place: Tin -> Tout).  Same ring as k_element_win.
 // In iteration t every thread first relaxes its child of tile t+2 if that is a DOWN child (reads the old up
 // values in tiles t+1 .. t+4, writes the new down values into the ring), then its child of tile t if that is an
