@@ -545,16 +545,24 @@ int launch_gs_fused(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout
   a.ovl_next = nullptr; a.dst_strip = h->dst_strip; a.rev = h->rev;
   a.partial = h->partial; a.omega = h->p.omega; a.rsign = (double)h->p.residual_sign; a.nelem = L.nelem; a.s = L.s;
   a.colour = 1; a.split_boundary = 0; a.partial_off = 0;
-  static int resident = 0;
+  const bool producer = h->win_producer && L.s >= 6;
+  static int resident2[2] = {0, 0};
+  int& resident = resident2[producer ? 1 : 0];
   if (resident == 0) {
-    CK(cudaFuncSetAttribute(k_gs_win, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GSW_SMEM_BYTES));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_gs_win, TPB, GSW_SMEM_BYTES));
+    if (producer) {
+      CK(cudaFuncSetAttribute(k_gs_win2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GSW_SMEM_BYTES));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_gs_win2, WIN2_THREADS, GSW_SMEM_BYTES));
+    } else {
+      CK(cudaFuncSetAttribute(k_gs_win, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GSW_SMEM_BYTES));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_gs_win, TPB, GSW_SMEM_BYTES));
+    }
     if (resident < 1) resident = 1;
   }
   const bool prof = h->profiling && h->pev_used + 2 <= (int)h->pev.size();
   if (prof) CK(cudaEventRecord(h->pev[h->pev_used], h->stream));
   const int tgrid = (int)std::max(1ll, std::min(L.nelem / TPB, (long long)h->nsm * resident));
-  k_gs_win<<<tgrid, TPB, GSW_SMEM_BYTES, h->stream>>>(a);
+  if (producer) k_gs_win2<<<tgrid, WIN2_THREADS, GSW_SMEM_BYTES, h->stream>>>(a);
+  else k_gs_win<<<tgrid, TPB, GSW_SMEM_BYTES, h->stream>>>(a);
   if (prof) { CK(cudaEventRecord(h->pev[h->pev_used + 1], h->stream)); h->pev_used += 2; }
   h->launches++;
   CK(cudaGetLastError());

@@ -1137,6 +1137,192 @@ __global__ void __launch_bounds__(TPB, 3) k_gs_win(ElemArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// One-pass coloured Gauss-Seidel with a producer warp (see k_gs_win for the algorithm, k_element_win2 for the roles).
+// The consumer warps of one CTA do depend on each other here - the up children of tile t read the down value that
+// the down phase of the previous iteration wrote at the first child of tile t+1, and the down phase reads an up value
+// that the next iteration's up phase overwrites - but only across one phase: a consumer arrives on an mbarrier when
+// its DOWN phase of an iteration is done, and waits before its UP phase for the down phases of the PREVIOUS iteration.
+// That leaves a whole phase of slack instead of a CTA-wide barrier per tile.
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  double* sT = reinterpret_cast<double*>(dsm);
+  double* sB = sT + 3 * WIN_CH;
+  uint64_t* barT = reinterpret_cast<uint64_t*>(sB + 3 * TPB * WIN_NB);
+  uint64_t* barB = barT + WIN_NT;
+  __shared__ __align__(16) double sPC2[2][NPC];
+  __shared__ int sIdx2[2][8];
+  __shared__ __align__(8) uint64_t doneD[4];
+  const int s = a.s, twos = 2 * s, b = 2 << s, S = 1 << s;
+  const long long Cmask = (1ll << twos) - 1;
+  const int tid = threadIdx.x;
+  constexpr uint32_t TILE_BYTES = 3 * TPB * sizeof(double);
+  if (tid == 0) {
+    for (int i = 0; i < WIN_NT + WIN_NB; ++i) mbar_init(&barT[i], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&doneD[i], TPB / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long ntiles = a.nelem / TPB;
+  const long long per = (ntiles + gridDim.x - 1) / gridDim.x;
+  const long long tbeg = (long long)blockIdx.x * per, tend = min(ntiles, tbeg + per);
+  if (tbeg >= tend) return;
+  const long long dlo = max(0ll, tbeg - 2), dhi = min(ntiles - 1, tend);       // tiles whose down children I relax
+  const long long tlo = max(0ll, dlo - 1), thi = min(ntiles, dhi + 3);         // field tiles I load: [tlo, thi)
+  const long long t0 = dlo - 2;                                                // first iteration
+
+  if (tid >= TPB) {
+    // ------------------------------------------------------------------ producer warp
+    const int lane = tid - TPB;
+    int u_loaded = -1;
+    auto issueT = [&](long long tile) {
+      const int sl = (int)(tile & (WIN_NT - 1));
+      mbar_expect_tx(&barT[sl], TILE_BYTES);
+      tma_load_1d(sT + sl * 3 * TPB, a.Tin + tile * 3 * TPB, TILE_BYTES, &barT[sl]);
+    };
+    auto issueB = [&](long long tile) {   // whole warp
+      const int u = (int)((tile * TPB) >> twos);
+      if (u != u_loaded) {
+        for (int i = lane; i < NPC; i += 32) sPC2[u & 1][i] = __ldg(a.pc + (size_t)u * NPC + i);
+        if (lane < 3) { sIdx2[u & 1][lane] = __ldg(a.strip_of + u * 3 + lane); sIdx2[u & 1][4 + lane] = __ldg(a.hmap + u * 3 + lane); }
+        u_loaded = u;
+        __syncwarp();
+      }
+      if (lane == 0) {
+        const int sl = (int)((tile - dlo) & (WIN_NB - 1));
+        mbar_expect_tx(&barB[sl], TILE_BYTES);
+        tma_load_1d(sB + sl * 3 * TPB, a.rhs + tile * 3 * TPB, TILE_BYTES, &barB[sl]);
+      }
+    };
+    if (lane == 0) for (long long t = tlo; t < min(thi, t0 + 6); ++t) issueT(t);
+    for (long long t = dlo; t <= min(dhi, dlo + 3); ++t) issueB(t);
+    for (long long tile = t0; tile < tend; ++tile) {
+      const int it = (int)(tile - t0);
+      named_sync(1 + (it & 3), WIN2_THREADS);            // every consumer warp has finished iteration `tile`
+      if (lane == 0) {
+        if (tile >= tbeg) {
+          tma_store_1d(a.Tout + tile * 3 * TPB, sT + (tile & (WIN_NT - 1)) * 3 * TPB, TILE_BYTES);
+          tma_store_commit();
+        }
+        // ring slot of tile-2: nobody is behind iteration tile+1; its store (two groups ago) has been read
+        if (tile + 6 < thi) { asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); issueT(tile + 6); }
+      }
+      __syncwarp();
+      if (tile + 4 >= dlo + 4 && tile + 4 <= dhi) issueB(tile + 4);   // rhs slot of tile: consumed by its up children
+    }
+    if (lane == 0) tma_store_wait_all();
+  } else {
+    // ------------------------------------------------------------------ consumer warps
+    auto waitT = [&](long long tile) { mbar_wait(&barT[tile & (WIN_NT - 1)], (uint32_t)(((tile - tlo) >> 3) & 1)); };
+    auto waitB = [&](long long tile) { mbar_wait(&barB[(tile - dlo) & (WIN_NB - 1)], (uint32_t)(((tile - dlo) >> 2) & 1)); };
+    struct Prep { int r, ipos, len; double h1a, h1b, h2a, h2b; };
+    auto prepare = [&](long long tile, Prep& p) {   // the parent of `tile` has been acquired through an rhs tile by then
+      p.r = 2; p.ipos = 2; p.len = 3; p.h1a = 0.0; p.h1b = 0.0; p.h2a = 0.0; p.h2b = 0.0;
+      if (tile < tbeg || tile >= tend) return;
+      const long long g = tile * TPB + tid;
+      child_from_ele0((int)(g & Cmask), s, p.r, p.ipos, p.len);
+      if (!(p.ipos & 1)) return;
+      const bool f1 = p.r == 1, side = p.ipos == 1 || p.ipos == p.len;
+      if (f1 | side) {
+        const int u = (int)(g >> twos);
+        const int* ix = sIdx2[u & 1];
+        if (f1) {
+          const int strip = ix[0], hm = ix[4];
+          const double* e = a.ovl + ((size_t)strip * S + (p.ipos >> 1)) * 3;
+          p.h1a = __ldg(e + (hm & 3)); p.h1b = __ldg(e + (hm >> 2));
+        }
+        if (side) {
+          const int mf = (p.ipos == 1) ? 2 : 1;
+          const int strip = ix[mf], hm = ix[4 + mf];
+          const double* e = a.ovl + ((size_t)strip * S + (p.r - 1)) * 3;
+          p.h2a = __ldg(e + (hm & 3)); p.h2b = __ldg(e + (hm >> 2));
+        }
+      }
+    };
+    Prep cur, nxt;
+    prepare(t0, cur);                                    // t0 < tbeg: defaults
+    for (long long tile = t0; tile < tend; ++tile) {
+      const int it = (int)(tile - t0);
+      const long long td = tile + 2;
+      const bool doD = td >= dlo && td <= dhi, doU = tile >= tbeg;
+      if (tile == t0) {
+        for (long long tw = tlo; tw < min(thi, tile + 5); ++tw) waitT(tw);
+      } else if (tile + 4 < thi) {
+        waitT(tile + 4);
+      }
+      if (doD) {
+        waitB(td);                                       // also acquires the coefficients of the parent of td
+        const int u_acq = (int)((td * TPB) >> twos);
+        const long long g = td * TPB + tid;
+        int r, ipos, len;
+        child_from_ele0((int)(g & Cmask), s, r, ipos, len);
+        if (!(ipos & 1)) {                               // down child: all three faces inside the parent
+          const int cw = (int)((td * TPB) & (WIN_CH - 1)) + tid;
+          double* t = sT + cw * 3;
+          const double T1 = t[0], T2 = t[1], T3 = t[2];
+          FaceIn fi;
+          const double* tv = sT + ((cw + b - 2 * r) & (WIN_CH - 1)) * 3;
+          fi.n1a = tv[2]; fi.n1b = tv[0];
+          const double* tr = sT + ((cw + 1) & (WIN_CH - 1)) * 3;
+          const double* tl = sT + ((cw - 1) & (WIN_CH - 1)) * 3;
+          fi.n2a = tr[1]; fi.n2b = tr[2];
+          fi.n3a = tl[0]; fi.n3b = tl[1];
+          const double* bb = sB + ((td - dlo) & (WIN_NB - 1)) * 3 * TPB + tid * 3;
+          const double* pd = sPC2[u_acq & 1] + PC_FOLD + 16;
+          const Folded& F = *reinterpret_cast<const Folded*>(pd);
+          double o1, o2, o3;
+          elem_apply_folded<MODE_GS>(F, pd, 0, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
+          t[0] = o1; t[1] = o2; t[2] = o3;
+        }
+      }
+      // down phase of this iteration done (also when there was nothing to do): tell the other warps
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive_cta(&doneD[it & 3]);
+      const int u_tile = doU ? (int)((tile * TPB) >> twos) : -1;
+      prepare(tile + 1, nxt);
+      if (doU) {
+        // every warp has finished the down phase of the PREVIOUS iteration (first child of tile+1, last child of tile-1 ...)
+        if (it > 0) mbar_wait(&doneD[(it - 1) & 3], (uint32_t)(((it - 1) >> 2) & 1));
+        if (cur.ipos & 1) {
+          const int cw = (int)((tile * TPB) & (WIN_CH - 1)) + tid;
+          double* t = sT + cw * 3;
+          const double T1 = t[0], T2 = t[1], T3 = t[2];
+          FaceIn fi;
+          int bmask = 0;
+          const double* tv = sT + ((cw + 2 * cur.r - b - 2) & (WIN_CH - 1)) * 3;
+          fi.n1a = tv[2]; fi.n1b = tv[0];
+          const double* tl = sT + ((cw - 1) & (WIN_CH - 1)) * 3;
+          const double* tr = sT + ((cw + 1) & (WIN_CH - 1)) * 3;
+          fi.n2a = tl[1]; fi.n2b = tl[2];
+          fi.n3a = tr[0]; fi.n3b = tr[1];
+          if (cur.r == 1 || cur.ipos == 1 || cur.ipos == cur.len) {
+            if (cur.r == 1) { fi.n1a = cur.h1a; fi.n1b = cur.h1b; bmask |= 1; }
+            if (cur.ipos == 1) { fi.n2a = cur.h2a; fi.n2b = cur.h2b; bmask |= 2; }
+            if (cur.ipos == cur.len) {
+              if (cur.len == 1) halo_pair(a, u_tile, 1, cur.r - 1, S, fi.n3a, fi.n3b);
+              else { fi.n3a = cur.h2a; fi.n3b = cur.h2b; }
+              bmask |= 4;
+            }
+          }
+          const double* bb = sB + ((tile - dlo) & (WIN_NB - 1)) * 3 * TPB + tid * 3;
+          const double* pu = sPC2[u_tile & 1];
+          const Folded& F = *reinterpret_cast<const Folded*>(pu + PC_FOLD);
+          double o1, o2, o3;
+          elem_apply_folded<MODE_GS>(F, pu + PC_DPEN, bmask, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
+          t[0] = o1; t[1] = o2; t[2] = o3;
+        }
+      }
+      fence_async_smem();
+      named_arrive(1 + (it & 3), WIN2_THREADS);
+      cur = nxt;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Branch-free direct kernel: thread per child, every load of the child (own values, rhs, the three
 // neighbours) is issued before the first use so that one memory latency is exposed per child instead of a
 // chain of two or three; children on a parent face patch their neighbour values from the halo strips in a
