@@ -197,7 +197,7 @@ inline int unstr_step(UnstrDev& u, double dt, double ux, double uy, double t_bc,
 // the dense (3E)^2 matrix with FINDInv (:366-378); here the operator never leaves its 4-blocks-per-row form.
 struct BsrArgs {
   const double* X; const int32_t* neig; const int32_t* nside;
-  double* val; int32_t* col; double* dinv; double* mdt;
+  double* val; int32_t* col; double* dinv; double* mdt; double* diag0;
   double dt, ux, uy;
   int E, use_dir;
 };
@@ -264,6 +264,8 @@ __global__ void __launch_bounds__(TPB) k_assemble_bsr(BsrArgs a) {
 #pragma unroll
       for (int q = 0; q < 9; ++q) a.val[((size_t)e * 4 + bq) * 9 + q] = blk[bq][q];
     }
+#pragma unroll
+    for (int q = 0; q < 9; ++q) a.diag0[(size_t)e * 9 + q] = blk[0][q];     // diagonal block without stabilisation
     // inverse of the diagonal block by its adjugate
     const double* d = blk[0];
     const double c00 = d[4] * d[8] - d[5] * d[7], c01 = d[5] * d[6] - d[3] * d[8], c02 = d[3] * d[7] - d[4] * d[6];
@@ -442,14 +444,12 @@ inline int implicit_assemble(UnstrDev& u, double dt, double ux, double uy, int u
     UCK(cudaMalloc(&u.stab, E * 12 * sizeof(double)));
   }
   BsrArgs a;
-  a.X = u.X; a.neig = u.neig; a.nside = u.nside; a.val = u.bsr_val; a.col = u.bsr_col; a.dinv = u.dinv; a.mdt = u.mdt;
+  a.X = u.X; a.neig = u.neig; a.nside = u.nside; a.val = u.bsr_val; a.col = u.bsr_col; a.dinv = u.dinv; a.mdt = u.mdt; a.diag0 = u.diag0;
   a.dt = dt; a.ux = ux; a.uy = uy; a.E = u.E; a.use_dir = use_dir;
   const int grid = std::max(1, std::min((u.E + TPB - 1) / TPB, nsm * 8));
   k_assemble_bsr<<<grid, TPB, 0, st>>>(a);
   nlaunch++;
   UCK(cudaGetLastError());
-  // keep the unstabilised diagonal blocks (block 0 of every row: 9 doubles at a stride of 36)
-  UCK(cudaMemcpy2DAsync(u.diag0, 9 * sizeof(double), u.bsr_val, 36 * sizeof(double), 9 * sizeof(double), E, cudaMemcpyDeviceToDevice, st));
   u.assembled = true; u.dt = dt; u.ux = ux; u.uy = uy;
   return PAMG_OK;
 }
