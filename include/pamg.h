@@ -126,6 +126,12 @@ int pamg_literal_timestep(pamg_handle* h, int solver, int n_multigrid, int n_smo
 int pamg_timestep_host(pamg_handle* h, const double* tnew_in, double* tnew_out, int max_cycles, double tol,
                        int* cycles, double* relres);
 
+/* smoother with HOST buffers (pinned memory recommended), pipelined across calls: the upload of call k+1 overlaps the
+ * download of call k.  tnew_out of a call is complete once pamg_sync has returned (or the next call that reuses
+ * the buffer has been queued - the copies are stream-ordered).  Any other entry that reads or writes level-1
+ * fields must be preceded by pamg_sync. */
+int pamg_smooth_host(pamg_handle* h, int solver, int nsweeps, const double* tnew_in, double* tnew_out);
+
 /* ---- distributed halo (update_overlaps across GPUs; Generic.F90:387-401 sketches the block partition) -- */
 /* host-only: where every halo strip lives and how cut faces are ordered per peer (no CUDA needed).
  * arrays are [U_local*3]; peers is [npeers][4] = part, nfaces, strip_begin, send_begin;

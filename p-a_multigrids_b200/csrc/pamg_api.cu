@@ -120,6 +120,10 @@ struct pamg_handle {
   // unstructured
   UnstrDev un;
   int un_use_dir = 0;
+  // pamg_smooth_host: copies on their own streams so that the upload of call k+1 overlaps the download of call k
+  cudaStream_t up_stream = nullptr, down_stream = nullptr;
+  cudaEvent_t ev_up = nullptr, ev_comp = nullptr, ev_down = nullptr;
+  bool pipe_busy = false;
   // halo exchange by direct stores into peer memory (CUDA IPC over NVLink); PAMG_P2P=0 keeps ncclSend/ncclRecv
   bool p2p_enabled = true, p2p_ready = false, p2p_failed = false;
   bool p2p_fuse = true;                // cut-face values go to the peers from inside k_halo (PAMG_P2P_FUSE=0: separate kernel)
@@ -911,6 +915,7 @@ void pamg_destroy(pamg_handle* h) {
   if (h->stage) cudaFreeHost(h->stage);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->pev) if (e) cudaEventDestroy(e);
+  if (h->up_stream) { cudaStreamSynchronize(h->up_stream); cudaStreamSynchronize(h->down_stream); cudaStreamDestroy(h->up_stream); cudaStreamDestroy(h->down_stream); cudaEventDestroy(h->ev_up); cudaEventDestroy(h->ev_comp); cudaEventDestroy(h->ev_down); }
   if (h->stream && !h->shared_stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1293,6 +1298,41 @@ int pamg_timestep_host(pamg_handle* h, const double* tnew_in, double* tnew_out, 
   return PAMG_OK;
 }
 
+// smoother with HOST buffers, pipelined across calls: upload(k+1) runs while download(k) is still in flight (PCIe is full
+// duplex); tnew_out of call k is complete after the next call that reuses it has returned, or after pamg_sync
+int pamg_smooth_host(pamg_handle* h, int solver, int nsweeps, const double* tnew_in, double* tnew_out) {
+  if (!valid_level(h, 1) || !tnew_in || !tnew_out || nsweeps < 1) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  LevelDev& L = h->lev[0];
+  const size_t bytes = (size_t)L.ndof * sizeof(double);
+  if (!h->up_stream) {
+    CK(cudaStreamCreateWithFlags(&h->up_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->down_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_up, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_comp, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_down, cudaEventDisableTiming));
+  }
+  // the buffer that does not hold the current iterate receives the new field once every earlier kernel is done with it
+  CK(cudaEventRecord(h->ev_comp, h->stream));
+  CK(cudaStreamWaitEvent(h->up_stream, h->ev_comp, 0));
+  double* U = L.T[L.cur ^ 1];
+  CK(cudaMemcpyAsync(U, tnew_in, bytes, cudaMemcpyHostToDevice, h->up_stream));
+  CK(cudaEventRecord(h->ev_up, h->up_stream));
+  CK(cudaStreamWaitEvent(h->stream, h->ev_up, 0));
+  if (h->pipe_busy) CK(cudaStreamWaitEvent(h->stream, h->ev_down, 0));   // the previous result is still being read out of T[cur]
+  L.cur ^= 1;                 // tnew_nonlin = tnew = the uploaded field (transport_tri_semi.F90:317)
+  L.tnew_alias = true;
+  L.strips_valid = false;
+  int rc = do_smooth(h, 1, solver, nsweeps);
+  if (rc) return rc;
+  CK(cudaEventRecord(h->ev_comp, h->stream));
+  CK(cudaStreamWaitEvent(h->down_stream, h->ev_comp, 0));
+  CK(cudaMemcpyAsync(tnew_out, L.T[L.cur], bytes, cudaMemcpyDeviceToHost, h->down_stream));
+  CK(cudaEventRecord(h->ev_down, h->down_stream));
+  h->pipe_busy = true;
+  return PAMG_OK;
+}
+
 // ---- distributed ------------------------------------------------------------------------------
 int pamg_comm_unique_id(char* id128) {
   if (!id128) return PAMG_ERR_ARG;
@@ -1564,6 +1604,7 @@ int pamg_sync(pamg_handle* h) {
   if (!h) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
+  if (h->up_stream) { CK(cudaStreamSynchronize(h->up_stream)); CK(cudaStreamSynchronize(h->down_stream)); h->pipe_busy = false; }
   if (h->p2p_ready) {      // a halo exchange that gave up waiting for a peer raised the error word instead of hanging
     unsigned long long err = 0;
     CK(cudaMemcpy(&err, h->p2p_sync + P2P_ERR, sizeof(err), cudaMemcpyDeviceToHost));

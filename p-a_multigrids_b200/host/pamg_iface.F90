@@ -219,6 +219,15 @@ module pamg_iface
       integer(c_int), value :: binary
     end function
 
+    ! smoother on host arrays, pipelined across calls (call pamg_sync before reading tnew_out)
+    integer(c_int) function pamg_smooth_host(handle, solver, nsweeps, tnew_in, tnew_out) bind(c, name="pamg_smooth_host")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      integer(c_int), value :: solver, nsweeps
+      real(c_double), intent(in) :: tnew_in(*)
+      real(c_double), intent(inout) :: tnew_out(*)
+    end function
+
     ! FINDInv (matrices.F90:1618), batched
     integer(c_int) function pamg_apply_local_minv(handle, n, batch, M, rhs, x, Minv, status) &
         bind(c, name="pamg_apply_local_minv")

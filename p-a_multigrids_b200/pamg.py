@@ -89,6 +89,7 @@ def lib():
         "pamg_vcycle_solve": (ci, [vp, ci, ci, ci, ci, ci, cd, pint, _f64]),
         "pamg_literal_timestep": (ci, [vp, ci, ci, ci]),
         "pamg_timestep_host": (ci, [vp, vp, vp, ci, cd, pint, pdbl]),
+        "pamg_smooth_host": (ci, [vp, ci, ci, vp, vp]),
         "pamg_halo_plan": (ci, [ci, _f64, _i32, _i32, _i32, ci, ci, _i32, ci, _i32, _i32, _i32, _i32, _i32, _i32]),
         "pamg_comm_unique_id": (ci, [C.c_char_p]),
         "pamg_comm_init": (ci, [vp, C.c_char_p, ci, ci]),
@@ -379,6 +380,10 @@ class SemiImplicitIterative:
 
     def download_ptr(self, field, level, host_ptr):
         self._ck(self.L.pamg_download_field(self.h, field, level, host_ptr))
+
+    def smooth_host(self, solver, nsweeps, in_ptr, out_ptr):
+        """Smoother on a HOST field (pointers, e.g. PinnedBuffer.ptr); asynchronous: call sync() before reading out."""
+        self._ck(self.L.pamg_smooth_host(self.h, solver, nsweeps, in_ptr, out_ptr))
 
     # -- output (get_vtu / get_error) --------------------------------------------------------------
     def output_fields(self):

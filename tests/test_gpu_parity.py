@@ -247,6 +247,35 @@ def test_unstr_explicit_random_field_long(meshes):
     assert rel_l2(got, ref) <= TOL
 
 
+@pytest.mark.parametrize("solver", [pamg.JACOBI, pamg.GAUSS_SEIDEL])
+def test_smooth_host_pipelined_equals_blocking_calls(meshes, solver):
+    """pamg_smooth_host (upload / sweeps / download on three streams, pipelined across calls) == the blocking sequence
+    upload_field, smoother, download_field - bit for bit, for several different fields in a row."""
+    mesh = meshes["irregular"]
+    p = pamg.default_params(n_split=5, multi_levels=1, u_x=0.9, u_y=0.3)
+    g = pamg.SemiImplicitIterative(p, mesh)
+    shape = g.shape(1)
+    n = int(np.prod(shape))
+    g.upload(pamg.TOLD, 1, rng_field(shape, 1))
+    fields = [rng_field(shape, 10 + i) for i in range(4)]
+    want = []
+    for f in fields:
+        g.upload(pamg.TNONLIN, 1, f); g.copy(1, pamg.TNEW, pamg.TNONLIN)
+        g.smoother(1, solver, 3)
+        want.append(g.download(pamg.TNONLIN, 1).copy())
+    ins = [pamg.PinnedBuffer(n) for _ in fields]
+    outs = [pamg.PinnedBuffer(n) for _ in fields]
+    for b, f in zip(ins, fields):
+        b.array[:] = f.ravel()
+    for b, o in zip(ins, outs):
+        g.smooth_host(solver, 3, b.ptr, o.ptr)          # no synchronisation in between
+    g.sync()
+    for o, w in zip(outs, want):
+        assert np.array_equal(o.array.reshape(shape), w)
+    # the handle is in a consistent state afterwards: the iterate is the last result
+    assert np.array_equal(g.download(pamg.TNONLIN, 1), want[-1])
+
+
 def _bsr_to_dense(val, col):
     E = val.shape[0]
     A = np.zeros((3 * E, 3 * E))
