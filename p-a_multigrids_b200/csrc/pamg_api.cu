@@ -71,6 +71,7 @@ struct LevelDev {
   double* pc = nullptr;               // [U][NPC]
   int2* items = nullptr; int nitems = 0;  // work list of the row-streaming kernel (levels with s >= STREAM_MIN_S)
   bool rhs_valid = false;             // level 1: RHS matches TOLD
+  double* spare = nullptr;            // third field buffer of pamg_smooth_host (level 1, allocated on first use)
 };
 
 struct pamg_handle {
@@ -122,8 +123,8 @@ struct pamg_handle {
   int un_use_dir = 0;
   // pamg_smooth_host: copies on their own streams so that the upload of call k+1 overlaps the download of call k
   cudaStream_t up_stream = nullptr, down_stream = nullptr;
-  cudaEvent_t ev_up = nullptr, ev_comp = nullptr, ev_down = nullptr;
-  bool pipe_busy = false;
+  cudaEvent_t ev_up = nullptr, ev_comp = nullptr, ev_down[2] = {nullptr, nullptr};
+  unsigned pipe_calls = 0;             // calls since the last pamg_sync
   // halo exchange by direct stores into peer memory (CUDA IPC over NVLink); PAMG_P2P=0 keeps ncclSend/ncclRecv
   bool p2p_enabled = true, p2p_ready = false, p2p_failed = false;
   bool p2p_fuse = true;                // cut-face values go to the peers from inside k_halo (PAMG_P2P_FUSE=0: separate kernel)
@@ -802,7 +803,7 @@ void free_levels(pamg_handle* h) {
   for (auto& g : h->vc_graphs) cudaGraphExecDestroy(g.exec);
   h->vc_graphs.clear();
   for (auto& L : h->lev) {
-    cudaFree(L.T[0]); cudaFree(L.T[1]); cudaFree(L.told); cudaFree(L.rhs); cudaFree(L.res);
+    cudaFree(L.T[0]); cudaFree(L.T[1]); cudaFree(L.spare); cudaFree(L.told); cudaFree(L.rhs); cudaFree(L.res);
     cudaFree(L.ovlb[0]); cudaFree(L.ovlb[1]); cudaFree(L.ovl_old); cudaFree(L.pc); cudaFree(L.items);
   }
   h->lev.clear();
@@ -915,7 +916,7 @@ void pamg_destroy(pamg_handle* h) {
   if (h->stage) cudaFreeHost(h->stage);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->pev) if (e) cudaEventDestroy(e);
-  if (h->up_stream) { cudaStreamSynchronize(h->up_stream); cudaStreamSynchronize(h->down_stream); cudaStreamDestroy(h->up_stream); cudaStreamDestroy(h->down_stream); cudaEventDestroy(h->ev_up); cudaEventDestroy(h->ev_comp); cudaEventDestroy(h->ev_down); }
+  if (h->up_stream) { cudaStreamSynchronize(h->up_stream); cudaStreamSynchronize(h->down_stream); cudaStreamDestroy(h->up_stream); cudaStreamDestroy(h->down_stream); cudaEventDestroy(h->ev_up); cudaEventDestroy(h->ev_comp); cudaEventDestroy(h->ev_down[0]); cudaEventDestroy(h->ev_down[1]); }
   if (h->stream && !h->shared_stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1310,26 +1311,29 @@ int pamg_smooth_host(pamg_handle* h, int solver, int nsweeps, const double* tnew
     CK(cudaStreamCreateWithFlags(&h->down_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_up, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_comp, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&h->ev_down, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_down[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_down[1], cudaEventDisableTiming));
   }
-  // the buffer that does not hold the current iterate receives the new field once every earlier kernel is done with it
-  CK(cudaEventRecord(h->ev_comp, h->stream));
-  CK(cudaStreamWaitEvent(h->up_stream, h->ev_comp, 0));
-  double* U = L.T[L.cur ^ 1];
-  CK(cudaMemcpyAsync(U, tnew_in, bytes, cudaMemcpyHostToDevice, h->up_stream));
+  if (!L.spare) CK(cudaMalloc(&L.spare, bytes));
+  // Three field buffers rotate: the result of call k is downloaded out of one while call k+1 sweeps between the
+  // other two and call k+2 uploads into the first again - so the upload only waits for the download issued two calls ago.
+  if (h->pipe_calls >= 2) CK(cudaStreamWaitEvent(h->up_stream, h->ev_down[h->pipe_calls & 1], 0));
+  else { CK(cudaEventRecord(h->ev_comp, h->stream)); CK(cudaStreamWaitEvent(h->up_stream, h->ev_comp, 0)); }
+  CK(cudaMemcpyAsync(L.spare, tnew_in, bytes, cudaMemcpyHostToDevice, h->up_stream));
   CK(cudaEventRecord(h->ev_up, h->up_stream));
   CK(cudaStreamWaitEvent(h->stream, h->ev_up, 0));
-  if (h->pipe_busy) CK(cudaStreamWaitEvent(h->stream, h->ev_down, 0));   // the previous result is still being read out of T[cur]
-  L.cur ^= 1;                 // tnew_nonlin = tnew = the uploaded field (transport_tri_semi.F90:317)
-  L.tnew_alias = true;
+  // cached V-cycle graphs have the old buffer addresses baked in
+  if (!h->vc_graphs.empty()) { CK(cudaStreamSynchronize(h->stream)); for (auto& g : h->vc_graphs) cudaGraphExecDestroy(g.exec); h->vc_graphs.clear(); }
+  std::swap(L.T[L.cur], L.spare);   // the uploaded field becomes the iterate; the previous result stays in `spare` for its download
+  L.tnew_alias = true;              // tnew_nonlin = tnew = the uploaded field (transport_tri_semi.F90:317)
   L.strips_valid = false;
   int rc = do_smooth(h, 1, solver, nsweeps);
   if (rc) return rc;
   CK(cudaEventRecord(h->ev_comp, h->stream));
   CK(cudaStreamWaitEvent(h->down_stream, h->ev_comp, 0));
   CK(cudaMemcpyAsync(tnew_out, L.T[L.cur], bytes, cudaMemcpyDeviceToHost, h->down_stream));
-  CK(cudaEventRecord(h->ev_down, h->down_stream));
-  h->pipe_busy = true;
+  CK(cudaEventRecord(h->ev_down[h->pipe_calls & 1], h->down_stream));
+  h->pipe_calls++;
   return PAMG_OK;
 }
 
@@ -1604,7 +1608,7 @@ int pamg_sync(pamg_handle* h) {
   if (!h) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
-  if (h->up_stream) { CK(cudaStreamSynchronize(h->up_stream)); CK(cudaStreamSynchronize(h->down_stream)); h->pipe_busy = false; }
+  if (h->up_stream) { CK(cudaStreamSynchronize(h->up_stream)); CK(cudaStreamSynchronize(h->down_stream)); h->pipe_calls = 0; }
   if (h->p2p_ready) {      // a halo exchange that gave up waiting for a peer raised the error word instead of hanging
     unsigned long long err = 0;
     CK(cudaMemcpy(&err, h->p2p_sync + P2P_ERR, sizeof(err), cudaMemcpyDeviceToHost));
