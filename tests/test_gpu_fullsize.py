@@ -49,9 +49,12 @@ def test_sweep_is_affine_and_kernel_families_agree(n):
             "g=pamg.SemiImplicitIterative(p,m);r=lambda s:np.random.Generator(np.random.MT19937(s)).random(g.shape(1));"
             "g.upload(pamg.TOLD,1,r(3));g.upload(pamg.TNONLIN,1,r(1));g.smoother(1,pamg.JACOBI,1);"
             "np.save(sys.argv[1],g.download(pamg.TNONLIN,1))") % (os.path.join(ROOT, "tests"), n, n)
-    for fam in ("direct", "direct2", "stream"):
-        out = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"pamg_{fam}_{n}.npy")
-        r = subprocess.run([sys.executable, "-c", code, out], env=dict(os.environ, PAMG_KERNEL=fam),
+    for fam in ("direct", "direct2", "stream", "tma1d", "win:barrier"):
+        out = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"pamg_{fam.replace(':', '_')}_{n}.npy")
+        env = dict(os.environ, PAMG_KERNEL=fam.split(":")[0])
+        if ":" in fam:
+            env["PAMG_WIN"] = fam.split(":")[1]
+        r = subprocess.run([sys.executable, "-c", code, out], env=env,
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         other = np.load(out)

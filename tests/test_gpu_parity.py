@@ -94,11 +94,13 @@ SWEEP_CASES = [
     ("900_ele", 1, False, (0.0, 0.0)),
     ("irregular", 3, True, (-0.4, 0.7)),
     ("syn", 5, True, (0.9, 0.3)),
-    # levels with s >= 6 run the TMA row-streaming kernel (pamg_stream.cuh)
+    # levels with 6 <= s <= 8 run the window kernel with a producer warp (k_element_win2), s = 4, 5 k_element_win
     ("test_sn2", 6, True, (0.9, 0.3)),
     ("split0", 7, True, (-0.5, 0.8)),
     ("split0", 6, False, (0.1, 0.1)),
     ("syn", 8, True, (0.9, 0.3)),
+    # n_split 9: rows of 1023 children do not fit the 8-tile ring - these levels run k_element_tma
+    ("split0", 9, True, (0.9, 0.3)),
 ]
 
 
@@ -123,7 +125,12 @@ def test_jacobi_sweep_and_residual(meshes, name, n, intended, u):
 
 
 @pytest.mark.parametrize("name,n,u", [("test_sn2", 3, (0.9, 0.3)), ("split0", 5, (0.0, 0.0)), ("900_ele", 2, (0.1, 0.1)),
-                                      ("syn", 4, (0.9, 0.3))])
+                                      ("syn", 4, (0.9, 0.3)),
+                                      # one-pass kernel with a producer warp (k_gs_win2): 6 <= n_split <= 8
+                                      ("test_sn2", 6, (0.9, 0.3)), ("split0", 7, (-0.5, 0.8)), ("syn", 8, (0.9, 0.3)),
+                                      ("irregular", 6, (0.3, -0.2)),
+                                      # n_split 9: two in-place passes through k_element_tma
+                                      ("split0", 9, (0.9, 0.3))])
 def test_two_colour_gauss_seidel_sweep(meshes, name, n, u):
     o, g = make_pair(meshes[name], n, 1, True, u=u, keep_tnew_gs=1)
     seed_fields(o, g)
@@ -144,8 +151,9 @@ def test_literal_head_gs_equals_reference_order(meshes):
     assert rel_l2(g.download(pamg.TNONLIN), o.field(orc.TNONLIN)) <= TOL
 
 
-def test_richardson_sweep(meshes):
-    o, g = make_pair(meshes["split0"], 3, 1, True, u=(0.9, 0.3), omega=1e-6)
+@pytest.mark.parametrize("n", [3, 4, 6])
+def test_richardson_sweep(meshes, n):
+    o, g = make_pair(meshes["split0"], n, 1, True, u=(0.9, 0.3), omega=1e-6)
     seed_fields(o, g)
     o.smooth(1, 2, 2)
     g.smoother(1, pamg.RICHARDSON, 2)
