@@ -76,6 +76,9 @@ int pamg_mesh_read_msh(const char* path, pamg_mesh** out);
  * get_splitting numbering (Msh2Tri.F90:69-107) into 4**kp parents: SURVEY 8(d) synthetic input */
 int pamg_mesh_synthetic(int kp, int G, pamg_mesh** out);
 int pamg_mesh_from_arrays(int U, const double* X /* [U][3][2] */, const int32_t* region, pamg_mesh** out);
+/* structured triangles of str_explicit (transport_tri.F90:354; structured_meshgen.F90:190-298: tri_ele_info2,
+ * str_tri_X_nodes): no_ele_row triangles per row (even), no_ele_col rows; feed it to pamg_set_unstructured */
+int pamg_mesh_structured_tri(int no_ele_row, int no_ele_col, double dx, double dy, pamg_mesh** out);
 int pamg_mesh_size(const pamg_mesh* m, int* U);
 /* any output pointer may be NULL.  X [U][3][2]; neig/fneig/dir [U][3]; region [U] */
 int pamg_mesh_get(const pamg_mesh* m, double* X, int32_t* neig, int32_t* fneig, int32_t* dir, int32_t* region);

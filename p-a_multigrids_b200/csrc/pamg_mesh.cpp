@@ -215,6 +215,35 @@ int pamg_mesh_synthetic(int kp, int G, pamg_mesh** out) {
   return PAMG_OK;
 }
 
+// structured triangular mesh of str_explicit (transport_tri.F90:354): no_ele_row triangles per row (odd = pointing up,
+// even = pointing down), node coordinates as in str_tri_X_nodes (structured_meshgen.F90:276-298); the neighbour
+// arrays come from the same edge hash as for gmsh input and reproduce tri_ele_info2 (:190-272) with the structured face
+// numbers 1, 2, 3 appearing as gmsh sides 1, 3, 2.
+int pamg_mesh_structured_tri(int no_ele_row, int no_ele_col, double dx, double dy, pamg_mesh** out) {
+  if (no_ele_row < 2 || (no_ele_row & 1) || no_ele_col < 1 || !(dx > 0.0) || !(dy > 0.0) || !out) return PAMG_ERR_ARG;
+  const int totele = no_ele_row * no_ele_col;
+  pamg_mesh* pm = new pamg_mesh();
+  pm->m.X.resize((size_t)totele * 6);
+  pm->m.region.assign(totele, 0);
+  for (int ele = 1; ele <= totele; ++ele) {
+    const int row = (ele + no_ele_row - 1) / no_ele_row;
+    const int col = ele - no_ele_row * (row - 1);
+    double* x = &pm->m.X[(size_t)(ele - 1) * 6];
+    if (ele & 1) {
+      x[0] = dx * (col / 2 + 1); x[1] = dy * (row - 1);
+      x[2] = dx * (col / 2);     x[3] = dy * row;
+      x[4] = dx * (col / 2);     x[5] = dy * (row - 1);
+    } else {
+      x[0] = dx * (col / 2 - 1); x[1] = dy * row;
+      x[2] = dx * (col / 2);     x[3] = dy * (row - 1);
+      x[4] = dx * (col / 2);     x[5] = dy * row;
+    }
+  }
+  pm->m.build_neighbours();
+  *out = pm;
+  return PAMG_OK;
+}
+
 int pamg_mesh_from_arrays(int U, const double* X, const int32_t* region, pamg_mesh** out) {
   if (U < 1 || !X || !out) return PAMG_ERR_ARG;
   pamg_mesh* pm = new pamg_mesh();

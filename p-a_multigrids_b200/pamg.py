@@ -64,6 +64,7 @@ def lib():
         "pamg_mesh_read_msh": (ci, [C.c_char_p, pvp]),
         "pamg_mesh_synthetic": (ci, [ci, ci, pvp]),
         "pamg_mesh_from_arrays": (ci, [ci, _f64, vp, pvp]),
+        "pamg_mesh_structured_tri": (ci, [ci, ci, cd, cd, pvp]),
         "pamg_mesh_size": (ci, [vp, pint]),
         "pamg_mesh_get": (ci, [vp, vp, vp, vp, vp, vp]),
         "pamg_mesh_free": (None, [vp]),
@@ -184,6 +185,15 @@ class Mesh:
         rc = lib().pamg_mesh_synthetic(kp, G, C.byref(h))
         if rc != OK:
             raise PamgError(rc, "pamg_mesh_synthetic")
+        return cls(h)
+
+    @classmethod
+    def structured_tri(cls, no_ele_row, no_ele_col, dx, dy):
+        """Structured triangles of str_explicit (structured_meshgen.F90:190-298)."""
+        h = C.c_void_p()
+        rc = lib().pamg_mesh_structured_tri(no_ele_row, no_ele_col, dx, dy, C.byref(h))
+        if rc != OK:
+            raise PamgError(rc, "pamg_mesh_structured_tri")
         return cls(h)
 
     @classmethod

@@ -403,6 +403,24 @@ def test_unstr_implicit_errors(meshes):
     assert L.pamg_implicit_assemble(g.h, 0.0, 1.0, 0.0, 0) == pamg.ERR_ARG
 
 
+def test_str_explicit_front_end():
+    """str_explicit (transport_tri.F90:354) = structured triangles (pamg_mesh_structured_tri) + the same explicit DG
+    step; t_bc = 0 and u_bc = u as at :100,120, initial box pulse, 3 time steps of 2 nonlinear passes."""
+    ner, nec = 40, 10
+    mesh = pamg.Mesh.structured_tri(ner, nec, 0.05, 0.1)
+    g = pamg.SemiImplicitIterative(pamg.default_params(), pamg.Mesh.synthetic(0, 1))
+    g.set_unstructured(mesh)
+    T0 = np.zeros((mesh.U, 3))
+    cx = mesh.X[:, :, 0].mean(axis=1)
+    T0[(cx > 0.2) & (cx < 0.5)] = 1.0
+    dt = 0.05 * 0.05
+    ref = T0.copy()
+    orc.lib().orc_unstr_explicit(mesh.U, mesh.X, mesh.neig, mesh.fneig, mesh.dir, 1.0, 0.0, dt, 3, 2, 10, 0, 0, 0.0, ref)
+    got = g.unstr_explicit(T0, dt, 1.0, 0.0, ntime=3, nits=2, njac_its=10)
+    assert rel_l2(got, ref) <= TOL
+    assert abs(got.sum() - T0.sum()) <= 1e-10 * T0.sum()      # the pulse has not reached the outflow side: mass is conserved
+
+
 @pytest.mark.parametrize("n", [3, 4, 6])
 def test_batched_local_inverse(n):
     g = pamg.SemiImplicitIterative(pamg.default_params(), pamg.Mesh.synthetic(0, 1))

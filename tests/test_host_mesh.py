@@ -151,3 +151,44 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".F90")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "liboracle" not in txt and "oracle_api" not in txt and "pamg_oracle" not in txt, f
+
+
+def _tri_ele_info2(totele, ele, iface, no_ele_row):
+    """structured_meshgen.F90:190-272 restated: neighbour across structured face iface (0 = boundary)."""
+    import math
+    row = math.ceil(ele / no_ele_row)
+    if ele % 2 > 0:
+        if iface == 1:
+            e2 = ele - no_ele_row + 1
+            return e2 if e2 >= 1 else 0
+        e2 = ele - 1 if iface == 2 else ele + 1
+    else:
+        if iface == 1:
+            e2 = ele + no_ele_row - 1
+            return e2 if e2 <= totele else 0
+        e2 = ele + 1 if iface == 2 else ele - 1
+    return e2 if math.ceil(e2 / no_ele_row) == row else 0
+
+
+@pytest.mark.parametrize("ner,nec,dx,dy", [(8, 4, 0.25, 0.5), (2, 1, 1.0, 1.0), (20, 10, 0.1, 0.1)])
+def test_structured_triangle_mesh_matches_reference_generator(ner, nec, dx, dy):
+    """pamg_mesh_structured_tri: coordinates of str_tri_X_nodes (:276-298) and the neighbours of tri_ele_info2
+    (structured faces 1, 2, 3 are gmsh sides 1, 3, 2)."""
+    m = pamg.Mesh.structured_tri(ner, nec, dx, dy)
+    tot = ner * nec
+    assert m.U == tot
+    for ele in range(1, tot + 1):
+        row = (ele + ner - 1) // ner
+        col = ele - ner * (row - 1)
+        if ele % 2:
+            want = [(dx * (col // 2 + 1), dy * (row - 1)), (dx * (col // 2), dy * row), (dx * (col // 2), dy * (row - 1))]
+        else:
+            want = [(dx * (col // 2 - 1), dy * row), (dx * (col // 2), dy * (row - 1)), (dx * (col // 2), dy * row)]
+        assert np.array_equal(m.X[ele - 1], np.array(want))
+        for iface, side in ((1, 1), (2, 3), (3, 2)):
+            assert m.neig[ele - 1, side - 1] == _tri_ele_info2(tot, ele, iface, ner), (ele, iface)
+    # right triangles of area dx*dy/2 tiling the rectangle
+    X = m.X
+    det = (X[:, 0, 0] - X[:, 2, 0]) * (X[:, 1, 1] - X[:, 2, 1]) - (X[:, 0, 1] - X[:, 2, 1]) * (X[:, 1, 0] - X[:, 2, 0])
+    assert np.allclose(0.5 * np.abs(det), 0.5 * dx * dy)
+    assert pamg.lib().pamg_mesh_structured_tri(7, 2, 1.0, 1.0, None) == pamg.ERR_ARG
