@@ -1335,6 +1335,172 @@ int orc_unstr_implicit_stab(int E, const double* X, const int32_t* neig, const i
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// trans_rec (transport_rect.F90:7-380): explicit DG on bilinear quadrilaterals (nloc = 4, 2x2 Gauss points, 2 Gauss points
+// per face) of a structured rectangular grid, element-local solve by FINDInv or by Jacobi iterations on the lumped mass.
+//   RE2DN4, NGI = 4 branch (ShapFun.F90:72-215); ele_info (structured_meshgen.F90:6-71); surface_pointers_sn
+//   (ShapFun.F90:258-367); det_nlx (:1245-1386, 2-D); det_snlx_all / NORMGI / XPROD1 (:1554-1590, :2012-2054).
+// volume_term = 0 is HEAD: the line that sets tnew_gi (:157) is commented out, so the advection VOLUME integral (:206-208)
+// multiplies a zero array.  That is the version that wrote the shipped output file DG-rectangular_structured
+// (main.F90:19: CFL .7, 200 x 1 elements, u = (2*0.01428571, 0), time 250, nits 2, 10 Jacobi iterations), which this
+// restatement reproduces to the reference's single precision - the one pin against an output of the reference binary.
+// volume_term = 1 is the intended scheme.
+int orc_trans_rec(double CFL, int no_ele_row, int no_ele_col, double x_length, double y_length, double u_x, double u_y,
+                  double time, int nits, int njac_its, int direct_solver, int volume_term, double* x_all, double* tnew_out) {
+  const int nloc = 4, ngi = 4, sngi = 2, nface = 4;
+  const int totele = no_ele_row * no_ele_col;
+  const double dx = x_length / no_ele_row, dy = y_length / no_ele_col, dt = CFL * dx;
+  const int ntime = (int)(time / dt);
+  // RE2DN4
+  const double lxp[4] = {-1, 1, -1, 1}, lyp[4] = {-1, -1, 1, 1};
+  const double posi = 1.0 / std::sqrt(3.0), lx[2] = {-posi, posi};
+  double n[4][4], nlx[4][2][4], weight[4];
+  for (int q = 0; q < 2; ++q)
+    for (int pq = 0; pq < 2; ++pq)
+      for (int c = 0; c < 4; ++c) {
+        const int g = q * 2 + pq;
+        weight[g] = 1.0;
+        n[g][c] = 0.25 * (1.0 + lxp[c] * lx[pq]) * (1.0 + lyp[c] * lx[q]);
+        nlx[g][0][c] = 0.25 * lxp[c] * (1.0 + lyp[c] * lx[q]);
+        nlx[g][1][c] = 0.25 * lyp[c] * (1.0 + lxp[c] * lx[pq]);
+      }
+  double sn_o[2][2], snlx_o[2][2];
+  for (int pq = 0; pq < 2; ++pq)
+    for (int c = 0; c < 2; ++c) { sn_o[pq][c] = 0.5 * (1.0 + lxp[c] * lx[pq]); snlx_o[pq][c] = 0.5 * lxp[c]; }
+  // surface_pointers_sn: (lnod1, lnod2) of my side and of the neighbour's side, 1-based
+  const int FN[4][2] = {{2, 1}, {1, 3}, {4, 2}, {3, 4}}, FN2[4][2] = {{4, 3}, {2, 4}, {3, 1}, {1, 2}};
+  double face_sn[4][2][4] = {}, face_snlx[4][2][4] = {}, face_sn2[4][2][4] = {};
+  for (int f = 0; f < 4; ++f)
+    for (int sg = 0; sg < 2; ++sg) {
+      face_sn[f][sg][FN[f][0] - 1] = sn_o[sg][0]; face_sn[f][sg][FN[f][1] - 1] = sn_o[sg][1];
+      face_snlx[f][sg][FN[f][0] - 1] = snlx_o[sg][0]; face_snlx[f][sg][FN[f][1] - 1] = snlx_o[sg][1];
+      face_sn2[f][sg][FN2[f][0] - 1] = sn_o[sg][0]; face_sn2[f][sg][FN2[f][1] - 1] = sn_o[sg][1];
+    }
+  // ele_info
+  std::vector<int> face_ele((size_t)totele * 4);
+  for (int ele = 1; ele <= totele; ++ele) {
+    const int row = (ele + no_ele_row - 1) / no_ele_row, col = ele - no_ele_row * (row - 1);
+    double* x = x_all + (size_t)(ele - 1) * 8;
+    x[0] = dx * (col - 1); x[1] = dy * (row - 1);
+    x[2] = dx * col;       x[3] = dy * (row - 1);
+    x[4] = dx * (col - 1); x[5] = dy * row;
+    x[6] = dx * col;       x[7] = dy * row;
+    auto rowof = [&](int e) { return (int)std::ceil((double)e / no_ele_row); };
+    int* fe = &face_ele[(size_t)(ele - 1) * 4];
+    fe[0] = ele - no_ele_row;
+    fe[1] = ele - 1; if (rowof(fe[1]) != row) fe[1] = -fe[1];
+    fe[2] = ele + 1; if (rowof(fe[2]) != row) fe[2] = -fe[2];
+    fe[3] = ele + no_ele_row; if (fe[3] > totele) fe[3] = -fe[3];
+  }
+  std::vector<double> tnew((size_t)totele * 4, 0.0), told, tnl;
+  for (int ele = no_ele_row / 5; ele <= no_ele_row / 2; ++ele)        // tnew(:, no_ele_row/5 : no_ele_row/2) = 1 (:83)
+    if (ele >= 1 && ele <= totele) for (int i = 0; i < 4; ++i) tnew[(size_t)(ele - 1) * 4 + i] = 1.0;
+  for (int itime = 0; itime < ntime; ++itime) {
+    told = tnew; tnl = tnew;
+    for (int its = 0; its < nits; ++its) {
+      tnew = tnl;
+      for (int ele = 1; ele <= totele; ++ele) {
+        const double* xl = x_all + (size_t)(ele - 1) * 8;
+        // det_nlx
+        double nx[4][2][4], detwei[4];
+        for (int g = 0; g < ngi; ++g) {
+          double A = 0, B = 0, Cc = 0, D = 0;
+          for (int l = 0; l < nloc; ++l) {
+            A += nlx[g][0][l] * xl[2 * l]; B += nlx[g][0][l] * xl[2 * l + 1];
+            Cc += nlx[g][1][l] * xl[2 * l]; D += nlx[g][1][l] * xl[2 * l + 1];
+          }
+          const double detj = A * D - B * Cc;
+          detwei[g] = std::fabs(detj) * weight[g];
+          const double a11 = D / detj, a21 = -B / detj, a12 = -Cc / detj, a22 = A / detj;
+          for (int l = 0; l < nloc; ++l) {
+            nx[g][0][l] = a11 * nlx[g][0][l] + a12 * nlx[g][1][l];
+            nx[g][1][l] = a21 * nlx[g][0][l] + a22 * nlx[g][1][l];
+          }
+        }
+        const double* tl = &tnew[(size_t)(ele - 1) * 4];
+        const double* to = &told[(size_t)(ele - 1) * 4];
+        double ugi[4][2], tgi[4];
+        for (int g = 0; g < ngi; ++g) {
+          double sx = 0, sy = 0, tt = 0;
+          for (int l = 0; l < nloc; ++l) { sx += n[g][l] * u_x; sy += n[g][l] * u_y; tt += n[g][l] * tl[l]; }
+          ugi[g][0] = sx; ugi[g][1] = sy;
+          tgi[g] = volume_term ? tt : 0.0;
+        }
+        double mass[4][4], ml[4], rhs[4];
+        for (int i = 0; i < nloc; ++i) {
+          for (int j = 0; j < nloc; ++j) {
+            double m = 0;
+            for (int g = 0; g < ngi; ++g) m += n[g][i] * n[g][j] * detwei[g];
+            mass[i][j] = m;
+          }
+          double l = 0, r = 0;
+          for (int g = 0; g < ngi; ++g) {
+            l += n[g][i] * detwei[g];
+            for (int d = 0; d < 2; ++d) r += nx[g][d][i] * ugi[g][d] * tgi[g] * detwei[g];
+          }
+          ml[i] = l; rhs[i] = r;
+        }
+        for (int f = 0; f < nface; ++f) {
+          const int e22 = face_ele[(size_t)(ele - 1) * 4 + f];
+          const bool bnd = e22 <= 0;                                   // (sign(1, -ele22) + 1) / 2
+          const double* t2 = bnd ? nullptr : &tnew[(size_t)(e22 - 1) * 4];
+          double usgi[2][2] = {}, usgi2[2][2] = {}, xsgi[2][2] = {}, tsgi[2] = {}, tsgi2[2] = {};
+          for (int l = 0; l < nloc; ++l)
+            for (int sg = 0; sg < sngi; ++sg) {
+              usgi[sg][0] += face_sn[f][sg][l] * u_x; usgi[sg][1] += face_sn[f][sg][l] * u_y;
+              usgi2[sg][0] += face_sn2[f][sg][l] * u_x; usgi2[sg][1] += face_sn2[f][sg][l] * u_y;   // u_bc = u_ele (:93)
+              xsgi[sg][0] += face_sn[f][sg][l] * xl[2 * l]; xsgi[sg][1] += face_sn[f][sg][l] * xl[2 * l + 1];
+              tsgi[sg] += face_sn[f][sg][l] * tl[l];
+              tsgi2[sg] += face_sn2[f][sg][l] * (bnd ? 0.0 : t2[l]);                                  // t_bc = 0 (:80)
+            }
+          double norm[2];
+          for (int d = 0; d < 2; ++d)
+            norm[d] = (xsgi[0][d] + xsgi[1][d]) / 2.0 - (xl[d] + xl[2 + d] + xl[4 + d] + xl[6 + d]) / 4.0;
+          double sdet[2], snorm[2][2];
+          for (int sg = 0; sg < sngi; ++sg) {
+            double dxdlx = 0, dydlx = 0;
+            for (int l = 0; l < nloc; ++l) { dxdlx += face_snlx[f][sg][l] * xl[2 * l]; dydlx += face_snlx[f][sg][l] * xl[2 * l + 1]; }
+            sdet[sg] = std::sqrt(dydlx * dydlx + dxdlx * dxdlx) * 1.0;
+            const double ax = dydlx, ay = -dxdlx;
+            const double rn = std::sqrt(ax * ax + ay * ay);
+            const double sirn = std::copysign(1.0 / rn, ax * norm[0] + ay * norm[1]);
+            snorm[sg][0] = sirn * ax; snorm[sg][1] = sirn * ay;
+          }
+          for (int sg = 0; sg < sngi; ++sg) {
+            const double un = snorm[sg][0] * 0.5 * (usgi[sg][0] + usgi2[sg][0]) + snorm[sg][1] * 0.5 * (usgi[sg][1] + usgi2[sg][1]);
+            const double income = 0.5 + 0.5 * std::copysign(1.0, -un);
+            for (int d = 0; d < 2; ++d) {
+              const double sc = snorm[sg][d] * sdet[sg] * ((1.0 - income) * usgi[sg][d] * tsgi[sg] + income * usgi2[sg][d] * tsgi2[sg]);
+              for (int i = 0; i < nloc; ++i) rhs[i] -= face_sn[f][sg][i] * sc;
+            }
+          }
+        }
+        double* out = &tnl[(size_t)(ele - 1) * 4];
+        if (direct_solver) {
+          double inv[16], m16[16];
+          for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) m16[i * 4 + j] = mass[i][j];
+          if (findinv(m16, inv, 4) != 0) return -1;
+          double v[4];
+          for (int i = 0; i < 4; ++i) { double sm = 0; for (int j = 0; j < 4; ++j) sm += mass[i][j] * to[j]; v[i] = sm + dt * rhs[i]; }
+          for (int i = 0; i < 4; ++i) { double sm = 0; for (int j = 0; j < 4; ++j) sm += inv[i * 4 + j] * v[j]; out[i] = sm; }
+        } else {
+          double rj[4], x4[4] = {out[0], out[1], out[2], out[3]};
+          for (int i = 0; i < 4; ++i) { double sm = 0; for (int j = 0; j < 4; ++j) sm += mass[i][j] * to[j]; rj[i] = sm + dt * rhs[i]; }
+          for (int k = 0; k < njac_its; ++k) {
+            double mt[4];
+            for (int i = 0; i < 4; ++i) { double sm = 0; for (int j = 0; j < 4; ++j) sm += mass[i][j] * x4[j]; mt[i] = sm; }
+            for (int i = 0; i < 4; ++i) x4[i] = (ml[i] * x4[i] - mt[i] + rj[i]) / ml[i];
+          }
+          for (int i = 0; i < 4; ++i) out[i] = x4[i];
+        }
+      }
+      tnew = tnl;
+    }
+  }
+  std::copy(tnew.begin(), tnew.end(), tnew_out);
+  return ntime;
+}
+
 // transport_rect.F90:48-52,83,101-105,337-344 ; structured_meshgen.F90:25-33 (one row of quads)
 void orc_rect_analytical(double CFL, int no_ele_row, double x_length, double u_x, double time,
                          double* x_out, double* t_out) {

@@ -104,6 +104,12 @@ void orc_unstr_stab(int E, const double* X, const double* tnew, const double* to
 int orc_unstr_implicit_stab(int E, const double* X, const int32_t* neig, const int32_t* fneig, double u_x, double u_y,
                             double dt, int ntime, int nits, int use_dir, double* tnew);
 
+/* ---- trans_rec (transport_rect.F90:7-380): explicit Q1 DG on a structured rectangular grid; returns ntime.
+ * volume_term 0 = HEAD (tnew_gi never set; the version that wrote DG-rectangular_structured), 1 = intended.
+ * x_all [totele][4][2], tnew_out [totele][4] */
+int orc_trans_rec(double CFL, int no_ele_row, int no_ele_col, double x_length, double y_length, double u_x, double u_y,
+                  double time, int nits, int njac_its, int direct_solver, int volume_term, double* x_all, double* tnew_out);
+
 /* ---- analytic cases ----------------------------------------------------------- */
 /* transport_rect.F90:83,101-105,337-344 : fills x[800], t[800] */
 void orc_rect_analytical(double CFL, int no_ele_row, double x_length, double u_x, double time,

@@ -86,6 +86,9 @@ def lib():
     L.orc_unstr_stab.argtypes = [C.c_int, f64p, f64p, f64p, C.c_double, C.c_double, C.c_double, f64p, f64p]
     L.orc_unstr_implicit_stab.argtypes = [C.c_int, f64p, i32p, i32p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, f64p]
     L.orc_unstr_implicit_stab.restype = C.c_int
+    L.orc_trans_rec.argtypes = [C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                C.c_int, C.c_int, C.c_int, C.c_int, f64p, f64p]
+    L.orc_trans_rec.restype = C.c_int
     L.orc_rect_analytical.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, f64p, f64p]
     L.orc_thermal_analytical.argtypes = [C.c_double] * 4
     L.orc_thermal_analytical.restype = C.c_double
