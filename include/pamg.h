@@ -177,6 +177,16 @@ int pamg_unstr_stab(pamg_handle* h, const double* told /* host (3,E) */, double 
                     double* diff_coe /* host (3,E) or NULL */, double* stab /* host [E][3][3] or NULL */);
 int pamg_implicit_set_stab(pamg_handle* h, int with_stab);
 
+/* ---- trans_rec front-end (transport_rect.F90:7-380): explicit DG on bilinear quadrilaterals of a structured
+ * no_ele_row x no_ele_col grid over x_length x y_length, dt = CFL dx, ntime = int(time / dt) steps of nits passes; initial
+ * box pulse of :83, t_bc = 0.  direct_solver != 0: FINDInv of the 4x4 mass matrix, else njac_its Jacobi iterations on the
+ * lumped mass.  volume_term = 0 reproduces HEAD (tnew_gi is never set, :157: no advection volume integral - the version
+ * that wrote the shipped DG-rectangular_structured), 1 is the intended scheme.  x_all [totele][4][2] (may be NULL) and
+ * tnew [totele][4] are HOST arrays in the order of the reference's dump (:320-330). */
+int pamg_trans_rec(pamg_handle* h, double CFL, int no_ele_row, int no_ele_col, double x_length, double y_length, double u_x,
+                   double u_y, double time, int nits, int njac_its, int direct_solver, int volume_term, double* x_all,
+                   double* tnew, int* ntime);
+
 /* ---- batched element-local inverse (FINDInv, matrix_inversion.F90:50-148) ----------------------- */
 /* M, x, rhs on the HOST; n in {3,4,6}; M row-major [batch][n][n].  x = M^-1 rhs (Minv optional out).
  * status[b] = 0 or -1 (singular) like errorflag. */

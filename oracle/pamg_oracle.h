@@ -6,12 +6,16 @@
  * cpu_baseline / --impl reference legs may load it.  The product path
  * (libpamg_cuda.so) never links, loads or calls anything in oracle/.
  *
- * PARITY UNPINNED: the reference is Fortran 90 with no tests and cannot be compiled in
- * this image (no Fortran compiler), so this oracle cannot be checked against outputs of
- * the reference binary.  It is pinned instead against the known answers the reference
- * formulas imply, the reconstructible golden dump
- * DG-rectangular_structured_analytical, the manufactured solution sin(x+y) and
- * geometric invariants (tests/test_oracle_*.py).
+ * PARITY: the reference is Fortran 90 with no tests and cannot be compiled in this image (no Fortran
+ * compiler), so the oracle cannot be run against the reference binary.  It is pinned against the ONE
+ * output of the reference binary that the repository ships: the dump DG-rectangular_structured of
+ * trans_rec (main.F90:19), which orc_trans_rec reproduces to the reference's single precision
+ * (tests/test_oracle_known_answers.py::test_trans_rec_reproduces_the_reference_output_file; that path
+ * shares the shape-function / face-geometry / upwind-flux / local-solve / time-loop structure with the
+ * triangle path).  For the triangle multigrid path itself no reference output exists: PARITY UNPINNED
+ * there; it is pinned instead against the known answers the reference formulas imply (SURVEY.md
+ * appendix C), the reconstructible dump DG-rectangular_structured_analytical, the manufactured
+ * solution sin(x+y) and geometric / algebraic invariants (tests/test_oracle_*.py).
  *
  * Every function cites the reference file:line it follows.  Two behaviours exist
  * where the reference is work-in-progress:

@@ -1495,6 +1495,23 @@ int pamg_implicit_step(pamg_handle* h, int ntime, int nits, double tol, int max_
   return PAMG_OK;
 }
 
+// ---- trans_rec front-end (transport_rect.F90:7) -------------------------------------------------------------
+int pamg_trans_rec(pamg_handle* h, double CFL, int no_ele_row, int no_ele_col, double x_length, double y_length, double u_x,
+                   double u_y, double time, int nits, int njac_its, int direct_solver, int volume_term, double* x_all,
+                   double* tnew, int* ntime) {
+  if (!h || !tnew || no_ele_row < 1 || no_ele_col < 1 || !(CFL > 0.0) || !(x_length > 0.0) || !(y_length > 0.0) || time < 0.0 ||
+      nits < 1 || njac_its < 0)
+    return PAMG_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  std::string e;
+  long long nl = 0;
+  int rc = rect_run(CFL, no_ele_row, no_ele_col, x_length, y_length, u_x, u_y, time, nits, njac_its, direct_solver, volume_term,
+                    x_all, tnew, ntime, h->nsm, h->stream, nl, e);
+  h->launches += nl;
+  if (rc) return fail(h, rc, e);
+  return PAMG_OK;
+}
+
 int pamg_apply_local_minv(pamg_handle* h, int n, int batch, const double* M, const double* rhs, double* x,
                           double* Minv, int32_t* status) {
   if (!h || batch < 1 || !M || !(n == 3 || n == 4 || n == 6)) return PAMG_ERR_ARG;

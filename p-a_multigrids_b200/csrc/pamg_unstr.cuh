@@ -537,6 +537,230 @@ inline int implicit_step(UnstrDev& u, int ntime, int nits, double tol, int max_i
 }
 
 // ------------------------------------------------------------------------------------------------
+// trans_rec (transport_rect.F90:122-316): explicit DG on bilinear quadrilaterals of a structured rectangular grid,
+// one thread per element.  Shape functions of RE2DN4 (ShapFun.F90:72-215, 2x2 Gauss points), face tables of
+// surface_pointers_sn (:305-357), neighbours of ele_info (structured_meshgen.F90:19-67) by index arithmetic, det_nlx
+// (:1245-1300) and det_snlx_all / NORMGI (:1554-1590, :2012-2054).  volume_term = 0 is HEAD (tnew_gi is never set, :157).
+struct RectArgs {
+  const double* tin; const double* told; double* tout;
+  double dx, dy, dt, ux, uy;
+  int ner, nec, njac, direct, volume_term;
+};
+
+__global__ void __launch_bounds__(128) k_rect_explicit(RectArgs a) {
+  const int totele = a.ner * a.nec;
+  const double posi = 0.57735026918962584;     // 1 / sqrt(3)
+  const double lxp[4] = {-1, 1, -1, 1}, lyp[4] = {-1, -1, 1, 1}, lx[2] = {-posi, posi};
+  const int FN[4][2] = {{1, 0}, {0, 2}, {3, 1}, {2, 3}}, FN2[4][2] = {{3, 2}, {1, 3}, {2, 0}, {0, 1}};   // 0-based
+  for (int e = blockIdx.x * 128 + threadIdx.x; e < totele; e += gridDim.x * 128) {
+    const int ele = e + 1;
+    const int row = (ele + a.ner - 1) / a.ner, col = ele - a.ner * (row - 1);
+    const double xl[4][2] = {{a.dx * (col - 1), a.dy * (row - 1)}, {a.dx * col, a.dy * (row - 1)},
+                             {a.dx * (col - 1), a.dy * row}, {a.dx * col, a.dy * row}};
+    double n[4][4], nx[4][2][4], detwei[4];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int pq = 0; pq < 2; ++pq) {
+        const int g = q * 2 + pq;
+        double nlx[2][4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          n[g][c] = 0.25 * (1.0 + lxp[c] * lx[pq]) * (1.0 + lyp[c] * lx[q]);
+          nlx[0][c] = 0.25 * lxp[c] * (1.0 + lyp[c] * lx[q]);
+          nlx[1][c] = 0.25 * lyp[c] * (1.0 + lxp[c] * lx[pq]);
+        }
+        double A = 0, B = 0, Cc = 0, D = 0;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) { A += nlx[0][l] * xl[l][0]; B += nlx[0][l] * xl[l][1]; Cc += nlx[1][l] * xl[l][0]; D += nlx[1][l] * xl[l][1]; }
+        const double detj = A * D - B * Cc;
+        detwei[g] = fabs(detj);
+        const double a11 = D / detj, a21 = -B / detj, a12 = -Cc / detj, a22 = A / detj;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) { nx[g][0][l] = a11 * nlx[0][l] + a12 * nlx[1][l]; nx[g][1][l] = a21 * nlx[0][l] + a22 * nlx[1][l]; }
+      }
+    double tl[4], to[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { tl[i] = a.tin[(size_t)e * 4 + i]; to[i] = a.told[(size_t)e * 4 + i]; }
+    double mass[4][4], ml[4], rhs[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double m = 0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) m += n[g][i] * n[g][j] * detwei[g];
+        mass[i][j] = m;
+      }
+      double l = 0, r = 0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        l += n[g][i] * detwei[g];
+        double ugx = 0, ugy = 0, tt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { ugx += n[g][k] * a.ux; ugy += n[g][k] * a.uy; tt += n[g][k] * tl[k]; }
+        const double tg = a.volume_term ? tt : 0.0;
+        r += nx[g][0][i] * ugx * tg * detwei[g];
+        r += nx[g][1][i] * ugy * tg * detwei[g];
+      }
+      ml[i] = l; rhs[i] = r;
+    }
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      int e22;
+      if (f == 0) e22 = ele - a.ner;
+      else if (f == 1) { e22 = ele - 1; if ((e22 + a.ner - 1) / a.ner != row || e22 < 1) e22 = 0; }
+      else if (f == 2) { e22 = ele + 1; if ((e22 + a.ner - 1) / a.ner != row) e22 = 0; }
+      else { e22 = ele + a.ner; if (e22 > totele) e22 = 0; }
+      const bool bnd = e22 <= 0;
+      const int l1 = FN[f][0], l2 = FN[f][1], m1 = FN2[f][0], m2 = FN2[f][1];
+      const double t2a = bnd ? 0.0 : a.tin[(size_t)(e22 - 1) * 4 + m1], t2b = bnd ? 0.0 : a.tin[(size_t)(e22 - 1) * 4 + m2];
+      double norm[2], xs[2][2];
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        xs[0][d] = 0; xs[1][d] = 0;
+      }
+      double sdet[2], snorm[2][2], tsg[2], tsg2[2], us[2][2], us2[2][2];
+#pragma unroll
+      for (int sg = 0; sg < 2; ++sg) {
+        const double s1 = 0.5 * (1.0 - lx[sg]), s2 = 0.5 * (1.0 + lx[sg]);     // sn_orig(sg, 1:2)
+        // sums over all four nodes in node order, like the reference (zeros for the nodes off the face)
+        double ux_ = 0, uy_ = 0, ux2 = 0, uy2 = 0, xx = 0, xy = 0, tt = 0, tt2 = 0, dxl = 0, dyl = 0;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          const double fs = (l == l1) ? s1 : ((l == l2) ? s2 : 0.0);
+          const double fs2 = (l == m1) ? s1 : ((l == m2) ? s2 : 0.0);
+          const double fl = (l == l1) ? -0.5 : ((l == l2) ? 0.5 : 0.0);
+          ux_ += fs * a.ux; uy_ += fs * a.uy; ux2 += fs2 * a.ux; uy2 += fs2 * a.uy;
+          xx += fs * xl[l][0]; xy += fs * xl[l][1];
+          tt += fs * tl[l];
+          tt2 += fs2 * ((l == m1) ? t2a : ((l == m2) ? t2b : 0.0));
+          dxl += fl * xl[l][0]; dyl += fl * xl[l][1];
+        }
+        us[sg][0] = ux_; us[sg][1] = uy_; us2[sg][0] = ux2; us2[sg][1] = uy2; xs[sg][0] = xx; xs[sg][1] = xy;
+        tsg[sg] = tt; tsg2[sg] = tt2;
+        sdet[sg] = sqrt(dyl * dyl + dxl * dxl);
+        snorm[sg][0] = dyl; snorm[sg][1] = -dxl;
+      }
+#pragma unroll
+      for (int d = 0; d < 2; ++d) norm[d] = (xs[0][d] + xs[1][d]) / 2.0 - (xl[0][d] + xl[1][d] + xl[2][d] + xl[3][d]) / 4.0;
+#pragma unroll
+      for (int sg = 0; sg < 2; ++sg) {
+        const double ax = snorm[sg][0], ay = snorm[sg][1];
+        const double rn = sqrt(ax * ax + ay * ay);
+        const double sirn = copysign(1.0 / rn, ax * norm[0] + ay * norm[1]);
+        const double nxs = sirn * ax, nys = sirn * ay;
+        const double un = nxs * 0.5 * (us[sg][0] + us2[sg][0]) + nys * 0.5 * (us[sg][1] + us2[sg][1]);
+        const double income = 0.5 + 0.5 * copysign(1.0, -un);
+        const double s1 = 0.5 * (1.0 - lx[sg]), s2 = 0.5 * (1.0 + lx[sg]);
+        const double scx = nxs * sdet[sg] * ((1.0 - income) * us[sg][0] * tsg[sg] + income * us2[sg][0] * tsg2[sg]);
+        const double scy = nys * sdet[sg] * ((1.0 - income) * us[sg][1] * tsg[sg] + income * us2[sg][1] * tsg2[sg]);
+        rhs[l1] -= s1 * scx; rhs[l2] -= s2 * scx;
+        rhs[l1] -= s1 * scy; rhs[l2] -= s2 * scy;
+      }
+    }
+    double out[4];
+    double v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { double sm = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sm += mass[i][j] * to[j];
+      v[i] = sm + a.dt * rhs[i]; }
+    if (a.direct) {
+      // FINDInv on the 4x4 mass matrix (no zero pivots for a positive definite matrix), then M^-1 v
+      double m[4][8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[i][j] = (j < 4) ? mass[i][j] : ((i + 4) == j ? 1.0 : 0.0);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int j = k + 1; j < 4; ++j) {
+          const double mm = m[j][k] / m[k][k];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) if (i >= k) m[j][i] -= mm * m[k][i];
+        }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const double mm = m[i][i];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j >= i) m[i][j] /= mm; }
+#pragma unroll
+      for (int k = 2; k >= 0; --k)
+#pragma unroll
+        for (int i = 0; i <= k; ++i) { const double mm = m[i][k + 1];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (j >= k) m[i][j] -= m[k + 1][j] * mm; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { double sm = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sm += m[i][4 + j] * v[j];
+        out[i] = sm; }
+    } else {
+      double x4[4] = {tl[0], tl[1], tl[2], tl[3]};      // tnew_nonlin(:,ele) == tnew(:,ele) at this point (:126,297)
+      for (int k = 0; k < a.njac; ++k) {
+        double mt[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { double sm = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sm += mass[i][j] * x4[j];
+          mt[i] = sm; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x4[i] = (ml[i] * x4[i] - mt[i] + v[i]) / ml[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) out[i] = x4[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a.tout[(size_t)e * 4 + i] = out[i];
+  }
+}
+
+// time loop of trans_rec (:122-316): told = tnew ; nits x { tnew = tnew_nonlin ; element loop } ; returns ntime
+inline int rect_run(double CFL, int ner, int nec, double x_length, double y_length, double ux, double uy, double time, int nits,
+                    int njac, int direct, int volume_term, double* x_all, double* tnew_host, int* ntime_out, int nsm,
+                    cudaStream_t st, long long& nlaunch, std::string& err) {
+  const int totele = ner * nec;
+  const double dx = x_length / ner, dy = y_length / nec, dt = CFL * dx;
+  const int ntime = (int)(time / dt);
+  std::vector<double> t0((size_t)totele * 4, 0.0);
+  for (int ele = ner / 5; ele <= ner / 2; ++ele)                 // tnew(:, no_ele_row/5 : no_ele_row/2) = 1 (:83)
+    if (ele >= 1 && ele <= totele) for (int i = 0; i < 4; ++i) t0[(size_t)(ele - 1) * 4 + i] = 1.0;
+  if (x_all)
+    for (int ele = 1; ele <= totele; ++ele) {
+      const int row = (ele + ner - 1) / ner, col = ele - ner * (row - 1);
+      double* x = x_all + (size_t)(ele - 1) * 8;
+      x[0] = dx * (col - 1); x[1] = dy * (row - 1); x[2] = dx * col; x[3] = dy * (row - 1);
+      x[4] = dx * (col - 1); x[5] = dy * row;       x[6] = dx * col; x[7] = dy * row;
+    }
+  double *T[2] = {nullptr, nullptr}, *told = nullptr;
+  const size_t bytes = (size_t)totele * 4 * sizeof(double);
+  auto done = [&]() { cudaFree(T[0]); cudaFree(T[1]); cudaFree(told); };
+#define RCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); done(); return PAMG_ERR_CUDA; } } while (0)
+  RCK(cudaMalloc(&T[0], bytes)); RCK(cudaMalloc(&T[1], bytes)); RCK(cudaMalloc(&told, bytes));
+  RCK(cudaMemcpyAsync(T[0], t0.data(), bytes, cudaMemcpyHostToDevice, st));
+  int cur = 0;
+  const int grid = std::max(1, std::min((totele + 127) / 128, nsm * 8));
+  for (int it = 0; it < ntime; ++it) {
+    RCK(cudaMemcpyAsync(told, T[cur], bytes, cudaMemcpyDeviceToDevice, st));
+    for (int k = 0; k < nits; ++k) {
+      RectArgs a;
+      a.tin = T[cur]; a.told = told; a.tout = T[cur ^ 1]; a.dx = dx; a.dy = dy; a.dt = dt; a.ux = ux; a.uy = uy;
+      a.ner = ner; a.nec = nec; a.njac = njac; a.direct = direct; a.volume_term = volume_term;
+      k_rect_explicit<<<grid, 128, 0, st>>>(a);
+      nlaunch++;
+      cur ^= 1;
+    }
+  }
+  RCK(cudaGetLastError());
+  RCK(cudaMemcpyAsync(tnew_host, T[cur], bytes, cudaMemcpyDeviceToHost, st));
+  RCK(cudaStreamSynchronize(st));
+  done();
+  if (ntime_out) *ntime_out = ntime;
+  return PAMG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // FINDInv: Gauss-Jordan on [M I], NO partial pivoting; a zero pivot is repaired by ADDING the first lower
 // row with a non-zero entry (matrices.F90:1661-1676); errorflag -1 when singular.
 template <int N>

@@ -228,6 +228,17 @@ module pamg_iface
       real(c_double), intent(inout) :: tnew_out(*)
     end function
 
+    ! trans_rec (transport_rect.F90:7)
+    integer(c_int) function pamg_trans_rec(handle, CFL, no_ele_row, no_ele_col, x_length, y_length, u_x, u_y, time, nits, &
+                                           njac_its, direct_solver, volume_term, x_all, tnew, ntime) bind(c, name="pamg_trans_rec")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), value :: CFL, x_length, y_length, u_x, u_y, time
+      integer(c_int), value :: no_ele_row, no_ele_col, nits, njac_its, direct_solver, volume_term
+      real(c_double), intent(out) :: x_all(2, 4, *), tnew(4, *)
+      integer(c_int), intent(out) :: ntime
+    end function
+
     ! FINDInv (matrices.F90:1618), batched
     integer(c_int) function pamg_apply_local_minv(handle, n, batch, M, rhs, x, Minv, status) &
         bind(c, name="pamg_apply_local_minv")

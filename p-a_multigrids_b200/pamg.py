@@ -106,6 +106,7 @@ def lib():
         "pamg_implicit_step": (ci, [vp, ci, ci, cd, ci, pint, pdbl]),
         "pamg_unstr_stab": (ci, [vp, _f64, cd, cd, cd, vp, vp]),
         "pamg_implicit_set_stab": (ci, [vp, ci]),
+        "pamg_trans_rec": (ci, [vp, cd, ci, ci, cd, cd, cd, cd, cd, ci, ci, ci, ci, vp, vp, pint]),
         "pamg_apply_local_minv": (ci, [vp, ci, ci, _f64, vp, vp, vp, vp]),
         "pamg_output_fields": (ci, [vp, vp, vp, vp]),
         "pamg_write_vtu": (ci, [vp, C.c_char_p, C.c_char_p, ci]),
@@ -457,6 +458,15 @@ class SemiImplicitIterative:
         out = np.empty_like(t)
         self._ck(self.L.pamg_unstr_download(self.h, out))
         return out, it.value, rr.value
+
+    def trans_rec(self, CFL, no_ele_row, no_ele_col, u_x, u_y, time, nits=2, njac_its=10, direct_solver=False,
+                  volume_term=False, x_length=100.0, y_length=100.0):
+        """trans_rec (transport_rect.F90:7); returns (x_all (E,4,2), tnew (E,4), ntime)."""
+        E = no_ele_row * no_ele_col
+        x = np.zeros((E, 4, 2)); t = np.zeros((E, 4)); nt = C.c_int(0)
+        self._ck(self.L.pamg_trans_rec(self.h, CFL, no_ele_row, no_ele_col, x_length, y_length, u_x, u_y, time, nits, njac_its,
+                                       int(direct_solver), int(volume_term), _ptr(x), _ptr(t), C.byref(nt)))
+        return x, t, nt.value
 
     def findinv(self, M, rhs=None):
         """Batched FINDInv (matrices.F90:1618): returns (Minv, x, status)."""

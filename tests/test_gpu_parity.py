@@ -1,11 +1,13 @@
 """GPU parity tests proper: every kernel of the hot path, called through the C ABI (ctypes), against the
 CPU oracle on identical seeded inputs.  Tolerance for floating point: relative L2 <= 1e-12 per Jacobi
 sweep and per residual evaluation (BASELINE.json north_star); copies are bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
 import oracle_api as orc
-from helpers import rel_l2, rng_field, write_msh
+from helpers import GOLDEN, rel_l2, rng_field, write_msh
 from pamg_pkg import pamg
 
 pytestmark = pytest.mark.gpu
@@ -419,6 +421,25 @@ def test_str_explicit_front_end():
     got = g.unstr_explicit(T0, dt, 1.0, 0.0, ntime=3, nits=2, njac_its=10)
     assert rel_l2(got, ref) <= TOL
     assert abs(got.sum() - T0.sum()) <= 1e-10 * T0.sum()      # the pulse has not reached the outflow side: mass is conserved
+
+
+@pytest.mark.parametrize("direct,volume,ner,nec,u", [(0, 0, 200, 1, (2 * 0.01428571, 0.0)), (0, 1, 200, 1, (2 * 0.01428571, 0.0)),
+                                                        (1, 1, 200, 1, (2 * 0.01428571, 0.0)), (0, 1, 40, 6, (0.02, 0.013)),
+                                                        (1, 0, 30, 4, (-0.02, 0.01))])
+def test_trans_rec_front_end(direct, volume, ner, nec, u):
+    """trans_rec (transport_rect.F90:7) on the device == oracle; the first case is main.F90:19, whose oracle result is
+    pinned against the reference's shipped output file on the CPU side."""
+    g = pamg.SemiImplicitIterative(pamg.default_params(), pamg.Mesh.synthetic(0, 1))
+    time = 250.0 if nec == 1 else 40.0
+    x, t, nt = g.trans_rec(0.7, ner, nec, u[0], u[1], time, nits=2, njac_its=10, direct_solver=bool(direct),
+                           volume_term=bool(volume))
+    rx = np.zeros((ner * nec, 4, 2)); rt = np.zeros((ner * nec, 4))
+    rnt = orc.lib().orc_trans_rec(0.7, ner, nec, 100.0, 100.0, u[0], u[1], time, 2, 10, direct, volume, rx, rt)
+    assert nt == rnt and np.array_equal(x, rx)
+    assert rel_l2(t, rt) <= 1e-11
+    if (direct, volume, ner, nec) == (0, 0, 200, 1):
+        num = np.load(os.path.join(GOLDEN, "rect_golden.npz"))["numerical"]
+        assert np.max(np.abs(t.ravel() - num[:, 2])) <= 3e-5      # the device result against the reference's own file
 
 
 @pytest.mark.parametrize("n", [3, 4, 6])
