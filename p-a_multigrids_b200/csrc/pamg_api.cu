@@ -134,7 +134,7 @@ struct pamg_handle {
   struct P2PPeer { int slot_at_peer = -1, strip_begin_at_peer = 0; long long recv_strips_at_peer = 0; uint4* stage = nullptr; };
   std::vector<P2PPeer> p2p_peers;      // same order as plan.peers
   std::vector<void*> p2p_opened;       // IPC mappings to close
-  unsigned long long p2p_timeout_ns = 20000000000ull;
+  unsigned long long p2p_timeout_ns = 60000000000ull;   // PAMG_P2P_TIMEOUT_S: how long a halo kernel polls for a peer before it gives up
 };
 
 namespace {
@@ -874,6 +874,8 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
     if (wp && !strcmp(wp, "barrier")) h->win_producer = false;
     const char* pp = getenv("PAMG_P2P");
     if (pp && pp[0] == '0') h->p2p_enabled = false;
+    const char* pt = getenv("PAMG_P2P_TIMEOUT_S");
+    if (pt && atof(pt) > 0.0) h->p2p_timeout_ns = (unsigned long long)(atof(pt) * 1e9);
     const char* pf = getenv("PAMG_P2P_FUSE");
     if (pf && pf[0] == '0') h->p2p_fuse = false;
     const char* gr = getenv("PAMG_GRAPH");
