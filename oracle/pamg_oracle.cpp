@@ -1086,7 +1086,7 @@ void orc_semi_literal_timestep(orc_semi* h, int solver, int n_multigrid, int n_s
 // ------------------------------------------------------------------ unstructured explicit
 // transport_tri_unstr.F90:588-795.  use_dir=0 reproduces get_unstr_sn2 ignoring Dir (SURVEY B-9).
 void orc_unstr_explicit(int E, const double* X, const int32_t* neig, const int32_t* fneig,
-                        const int32_t* dir, double u_x, double u_y, double dt, int ntime, int nits,
+                        const int32_t* /*dir: unstr_explicit ignores Dir, SURVEY B-9*/, double u_x, double u_y, double dt, int ntime, int nits,
                         int njac_its, int exact_minv, int use_dir, double t_bc, double* tnew) {
   std::vector<double> told((size_t)3 * E), tnl((size_t)3 * E);
   for (int it = 0; it < ntime; ++it) {
