@@ -109,3 +109,47 @@ def test_output_errors(tmp_path):
     L = pamg.lib()
     assert L.pamg_output_fields(g.h, None, None, None) == pamg.ERR_ARG
     assert L.pamg_write_vtu(g.h, str(tmp_path / "nodir" / "x.vtu").encode(), b"c", 0) == pamg.ERR_IO
+
+
+def test_semi_structured_children_through_the_implicit_operator(tmp_path):
+    """Semi_implicit_direct (transport_tri_semi.F90:1366-1783) assembles mass/dt - stiffness + upwind flux over the
+    children of the semi-structured mesh.  Here: expand the children (pamg_output_fields), hand them to the block-CSR
+    machinery (pamg_mesh_from_arrays -> pamg_set_unstructured -> pamg_implicit_*), and check against (a) the oracle's
+    dense solve on the same arrays and (b) the same step on the gmsh-refined mesh 1_split.msh, whose triangles are the
+    children of 0_split.msh at n_split = 1 in another order."""
+    g, mesh0, _ = make(tmp_path, "split0", 1)
+    x, _, _ = g.output_fields()
+    kids = pamg.Mesh.from_arrays(x.reshape(-1, 3, 2))
+    E = kids.U
+    assert E == 4 * mesh0.U
+    g.set_unstructured(kids)
+
+    def field(X):      # a smooth nodal field evaluated at the nodes, so that it is the same function on both meshes
+        return np.sin(3.0 * X[..., 0]) * np.cos(2.0 * X[..., 1]) + 0.5
+
+    u, dt = (0.4, -0.7), 2e-2
+    T0 = field(kids.X)
+    got, iters, relres = g.unstr_implicit(T0, dt, u[0], u[1], ntime=2, nits=1, use_dir=True, tol=1e-13)
+    ref = T0.copy()
+    assert orc.lib().orc_unstr_implicit(E, kids.X, kids.neig, kids.fneig, u[0], u[1], dt, 2, 1, 1, ref) == 0
+    assert np.linalg.norm(got - ref) <= 1e-10 * np.linalg.norm(ref)
+    # (b) the independently refined mesh
+    fine = pamg.Mesh.read_msh(write_msh("split1", str(tmp_path / "split1.msh")))
+    assert fine.U == E
+    g2 = pamg.SemiImplicitIterative(pamg.default_params(), pamg.Mesh.synthetic(0, 1))
+    g2.set_unstructured(fine)
+    got2, _, _ = g2.unstr_implicit(field(fine.X), dt, u[0], u[1], ntime=2, nits=1, use_dir=True, tol=1e-13)
+    key = lambda X: np.round(X, 9)
+    a = {tuple(key(p)): v for p, v in zip(kids.X.reshape(-1, 2), got.ravel())}
+    # DG: a node value belongs to (element, node); match elements by their sorted vertex sets
+    def by_element(X, T):
+        out = {}
+        for e in range(X.shape[0]):
+            k = tuple(sorted(tuple(key(p)) for p in X[e]))
+            out[k] = {tuple(key(p)): T[e, i] for i, p in enumerate(X[e])}
+        return out
+    A, B = by_element(kids.X, got), by_element(fine.X, got2)
+    assert set(A) == set(B)
+    worst = max(abs(A[k][p] - B[k][p]) for k in A for p in A[k])
+    assert worst <= 1e-10
+    assert len(a) > 0
