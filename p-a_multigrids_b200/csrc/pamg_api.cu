@@ -103,7 +103,6 @@ struct pamg_handle {
   bool fused_halo = false;  // PAMG_FUSED_HALO=1: sweeps write the next sweep's strips themselves (measured slower: the extra work
                             // of the few children on parent faces delays the per-tile barrier; profiles/README.md)
   bool gs_tma = true;   // coloured GS pass through the TMA tile kernel (PAMG_GS=direct selects the direct kernel)
-  bool fused_win = false;    // PAMG_FUSED_HALO=1: producer-warp kernels write the next sweep's strips themselves (measured slower)
   bool win_producer = true;  // window kernel with a producer warp (k_element_win2); PAMG_WIN=barrier: k_element_win
   bool gs_fused = true; // both colours in one pass (k_gs_win); PAMG_GS=twopass keeps the two in-place passes
   // per-kernel timing (element kernels only)
@@ -545,13 +544,13 @@ bool gs_fused_ok(const pamg_handle* h, const LevelDev& L) {
   return h->gs_fused && h->kernel_mode == 4 && h->p.face_terms && L.C >= TPB && L.s <= 8;
 }
 
-int launch_gs_fused(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout, bool write_strips) {
+int launch_gs_fused(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout) {
   ElemArgs a;
   a.Tin = Tin; a.Tout = Tout; a.rhs = L.rhs; a.ovl = L.ovlb[L.ovl_cur]; a.pc = L.pc; a.strip_of = h->strip_of; a.hmap = h->hmap;
-  const bool producer = h->win_producer && L.s >= 6;
-  a.ovl_next = (write_strips && producer) ? L.ovlb[L.ovl_cur ^ 1] : nullptr; a.dst_strip = h->dst_strip; a.rev = h->rev;
+  a.ovl_next = nullptr; a.dst_strip = h->dst_strip; a.rev = h->rev;
   a.partial = h->partial; a.omega = h->p.omega; a.rsign = (double)h->p.residual_sign; a.nelem = L.nelem; a.s = L.s;
   a.colour = 1; a.split_boundary = 0; a.partial_off = 0;
+  const bool producer = h->win_producer && L.s >= 6;
   static int resident2[2] = {0, 0};
   int& resident = resident2[producer ? 1 : 0];
   if (resident == 0) {
@@ -581,12 +580,7 @@ int do_smooth(pamg_handle* h, int level, int solver, int nsweeps) {
   const int grid = grid_for(h, L.nelem);
   // optional (PAMG_FUSED_HALO=1): the default kernel families write the next sweep's strips themselves; otherwise
   // one k_halo launch per sweep refreshes the strips of the faces between parents (Dirichlet strips are static)
-  // PAMG_FUSED_HALO=1: the sweep kernels write the next sweep's strips themselves (three plain stores per child on a parent
-  // face) and no k_halo runs between the sweeps of one call.  Measured slower every time - with the producer-warp kernels
-  // the sweep grows by 12 us while the k_halo it replaces costs 10.6 us (profiles/README.md) - so it stays an option.
-  const bool win2_level = h->kernel_mode == 4 && h->win_producer && L.s >= 6 && L.s <= 8 && h->p.face_terms &&
-                          ((solver == 1 || solver == 2) || gs_fused_ok(h, L));
-  const bool fused = (h->fused_halo && (h->kernel_mode == 1 || h->kernel_mode == 3)) || (win2_level && h->fused_win);
+  const bool fused = h->fused_halo && (h->kernel_mode == 1 || h->kernel_mode == 3);
   for (int sw = 0; sw < nsweeps; ++sw) {
     // tnew <- tnew_nonlin (:550) is the buffer swap below for Jacobi; halo from it (:555)
     L.tnew_alias = true;
@@ -604,7 +598,7 @@ int do_smooth(pamg_handle* h, int level, int solver, int nsweeps) {
       // values across parent faces stay lagged through the halo strips exactly as at :647-655.
       if (gs_fused_ok(h, L)) {
         // both colours in one pass over memory, written to the other buffer (which then holds tracer%tnew, as for Jacobi)
-        rc = launch_gs_fused(h, L, L.T[L.cur], L.T[L.cur ^ 1], fused);
+        rc = launch_gs_fused(h, L, L.T[L.cur], L.T[L.cur ^ 1]);
         if (rc) return rc;
         L.cur ^= 1;
         L.tnew_alias = false;
@@ -891,7 +885,7 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
     const char* sp = getenv("PAMG_SPLIT");
     if (sp && sp[0] == '1') h->split_boundary = true;
     const char* fh = getenv("PAMG_FUSED_HALO");
-    if (fh && fh[0] == '1') { h->fused_halo = true; h->fused_win = true; }
+    if (fh && fh[0] == '1') h->fused_halo = true;
     const char* g = getenv("PAMG_GS");
     if (g && !strcmp(g, "direct")) { h->gs_tma = false; h->gs_fused = false; }
     if (g && !strcmp(g, "twopass")) h->gs_fused = false;
@@ -1045,7 +1039,7 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
         ap.n_split = h->lev[lvl - 1].s;
         ap.multi_levels = h->p.multi_levels - lvl + 1;
         pamg_handle* g = new pamg_handle();
-        g->p = ap; g->device = h->device; g->nsm = h->nsm; g->kernel_mode = h->kernel_mode; g->gs_tma = h->gs_tma; g->gs_fused = h->gs_fused; g->win_producer = h->win_producer; g->fused_win = h->fused_win; g->fused_halo = h->fused_halo;
+        g->p = ap; g->device = h->device; g->nsm = h->nsm; g->kernel_mode = h->kernel_mode; g->gs_tma = h->gs_tma; g->gs_fused = h->gs_fused; g->win_producer = h->win_producer;
         g->stream = h->stream; g->shared_stream = true; g->level_offset = lvl - 1;
         for (auto& ev : g->ev) cudaEventCreate(&ev);
         cudaMalloc(&g->out3, 3 * sizeof(double));

@@ -178,36 +178,6 @@ __device__ __forceinline__ void strips_write(const ElemArgs& a, int u, int bmask
   }
 }
 
-// strips_write with the destination strips / reversal flags of the parent already in shared memory
-// (ix[8..10] = dst_strip of parent sides 1..3, ix[12..14] = rev): three plain stores per face, nothing to wait for
-__device__ __forceinline__ void strips_write_ix(const ElemArgs& a, const int* ix, int bmask, int r, int ipos, int S, double o1,
-                                                double o2, double o3) {
-  if (bmask & 1) {                      // child face 1 on parent side 1, position ipos/2
-    const int d = ix[8];
-    if (d >= 0) {
-      const int p = ipos >> 1, slot = ix[12] ? (S - 1 - p) : p;
-      double* e = a.ovl_next + ((size_t)d * S + slot) * 3;
-      e[0] = o1; e[1] = o2; e[2] = o3;
-    }
-  }
-  if (bmask & 2) {                      // child face 2 on parent side 3, position irow
-    const int d = ix[10];
-    if (d >= 0) {
-      const int slot = ix[14] ? (S - r) : (r - 1);
-      double* e = a.ovl_next + ((size_t)d * S + slot) * 3;
-      e[0] = o1; e[1] = o2; e[2] = o3;
-    }
-  }
-  if (bmask & 4) {                      // child face 3 on parent side 2, position irow
-    const int d = ix[9];
-    if (d >= 0) {
-      const int slot = ix[13] ? (S - r) : (r - 1);
-      double* e = a.ovl_next + ((size_t)d * S + slot) * 3;
-      e[0] = o1; e[1] = o2; e[2] = o3;
-    }
-  }
-}
-
 // same with the strip index and node map already at hand (kept in shared memory by the tile kernel)
 __device__ __forceinline__ const double* halo_entry(const ElemArgs& a, int strip, int slot0, int S) {
   return a.ovl + ((size_t)strip * S + slot0) * 3;
@@ -821,7 +791,7 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
   uint64_t* barT = reinterpret_cast<uint64_t*>(sB + 3 * TPB * WIN_NB);
   uint64_t* barB = barT + WIN_NT;
   __shared__ __align__(16) double sPC2[2][NPC];
-  __shared__ int sIdx2[2][16];
+  __shared__ int sIdx2[2][8];
   __shared__ double shp[3][TPB / 32];
   const int s = a.s, twos = 2 * s, b = 2 << s, S = 1 << s;
   const long long Cmask = (1ll << twos) - 1;
@@ -851,10 +821,7 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
       const int u = (int)((tile * TPB) >> twos);
       if (u != u_loaded) {
         for (int i = lane; i < NPC; i += 32) sPC2[u & 1][i] = __ldg(a.pc + (size_t)u * NPC + i);
-        if (lane < 3) {
-          sIdx2[u & 1][lane] = __ldg(a.strip_of + u * 3 + lane); sIdx2[u & 1][4 + lane] = __ldg(a.hmap + u * 3 + lane);
-          sIdx2[u & 1][8 + lane] = __ldg(a.dst_strip + u * 3 + lane); sIdx2[u & 1][12 + lane] = __ldg(a.rev + u * 3 + lane);
-        }
+        if (lane < 3) { sIdx2[u & 1][lane] = __ldg(a.strip_of + u * 3 + lane); sIdx2[u & 1][4 + lane] = __ldg(a.hmap + u * 3 + lane); }
         u_loaded = u;
         __syncwarp();
       }
@@ -962,8 +929,6 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
           elem_apply_regs<MODE, FACE>(P, up, interior, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.omega, a.rsign, o1, o2, o3);
         }
         bb[0] = o1; bb[1] = o2; bb[2] = o3;
-        // children on parent faces also deposit their new values in the strips the NEXT sweep reads (update_overlaps fused)
-        if (MODE != MODE_RESID && bmask && a.ovl_next) strips_write_ix(a, sIdx2[u_tile & 1], bmask, cur.r, cur.ipos, S, o1, o2, o3);
         if (MODE == MODE_RESID) {
           acc_sum += o1 * o1 + o2 * o2 + o3 * o3;
           acc_abs = fmax(acc_abs, fmax(fabs(o1), fmax(fabs(o2), fabs(o3))));
@@ -1189,7 +1154,7 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
   uint64_t* barT = reinterpret_cast<uint64_t*>(sB + 3 * TPB * WIN_NB);
   uint64_t* barB = barT + WIN_NT;
   __shared__ __align__(16) double sPC2[2][NPC];
-  __shared__ int sIdx2[2][16];
+  __shared__ int sIdx2[2][8];
   __shared__ __align__(8) uint64_t doneD[4];
   const int s = a.s, twos = 2 * s, b = 2 << s, S = 1 << s;
   const long long Cmask = (1ll << twos) - 1;
@@ -1222,10 +1187,7 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
       const int u = (int)((tile * TPB) >> twos);
       if (u != u_loaded) {
         for (int i = lane; i < NPC; i += 32) sPC2[u & 1][i] = __ldg(a.pc + (size_t)u * NPC + i);
-        if (lane < 3) {
-          sIdx2[u & 1][lane] = __ldg(a.strip_of + u * 3 + lane); sIdx2[u & 1][4 + lane] = __ldg(a.hmap + u * 3 + lane);
-          sIdx2[u & 1][8 + lane] = __ldg(a.dst_strip + u * 3 + lane); sIdx2[u & 1][12 + lane] = __ldg(a.rev + u * 3 + lane);
-        }
+        if (lane < 3) { sIdx2[u & 1][lane] = __ldg(a.strip_of + u * 3 + lane); sIdx2[u & 1][4 + lane] = __ldg(a.hmap + u * 3 + lane); }
         u_loaded = u;
         __syncwarp();
       }
@@ -1351,7 +1313,6 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
           double o1, o2, o3;
           elem_apply_folded<MODE_GS>(F, pu + PC_DPEN, bmask, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
           t[0] = o1; t[1] = o2; t[2] = o3;
-          if (bmask && a.ovl_next) strips_write_ix(a, sIdx2[u_tile & 1], bmask, cur.r, cur.ipos, S, o1, o2, o3);
         }
       }
       fence_async_smem();
