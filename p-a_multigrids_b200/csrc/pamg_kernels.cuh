@@ -1219,11 +1219,13 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
     auto waitT = [&](long long tile) { mbar_wait(&barT[tile & (WIN_NT - 1)], (uint32_t)(((tile - tlo) >> 3) & 1)); };
     auto waitB = [&](long long tile) { mbar_wait(&barB[(tile - dlo) & (WIN_NB - 1)], (uint32_t)(((tile - dlo) >> 2) & 1)); };
     struct Prep { int r, ipos, len; double h1a, h1b, h2a, h2b; };
-    auto prepare = [&](long long tile, Prep& p) {   // the parent of `tile` has been acquired through an rhs tile by then
+    // numbering (r, ipos) of my child of `tile` comes from the down phase that relaxed the tile one iteration earlier;
+    // the parent of `tile` has been acquired through an rhs tile by then
+    auto prepare = [&](long long tile, int r, int ipos, Prep& p) {
       p.r = 2; p.ipos = 2; p.len = 3; p.h1a = 0.0; p.h1b = 0.0; p.h2a = 0.0; p.h2b = 0.0;
       if (tile < tbeg || tile >= tend) return;
       const long long g = tile * TPB + tid;
-      child_from_ele0((int)(g & Cmask), s, p.r, p.ipos, p.len);
+      p.r = r; p.ipos = ipos; p.len = b + 1 - 2 * r;
       if (!(p.ipos & 1)) return;
       const bool f1 = p.r == 1, side = p.ipos == 1 || p.ipos == p.len;
       if (f1 | side) {
@@ -1243,7 +1245,8 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
       }
     };
     Prep cur, nxt;
-    prepare(t0, cur);                                    // t0 < tbeg: defaults
+    prepare(t0, 2, 2, cur);                              // t0 < tbeg: defaults
+    int rD = 2, iposD = 2;                               // numbering of my child of the tile relaxed by the last down phase
     for (long long tile = t0; tile < tend; ++tile) {
       const int it = (int)(tile - t0);
       const long long td = tile + 2;
@@ -1253,12 +1256,14 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
       } else if (tile + 4 < thi) {
         waitT(tile + 4);
       }
+      const int rP = rD, iposP = iposD;                  // my child of tile+1 (down phase of the previous iteration)
       if (doD) {
         waitB(td);                                       // also acquires the coefficients of the parent of td
         const int u_acq = (int)((td * TPB) >> twos);
         const long long g = td * TPB + tid;
         int r, ipos, len;
         child_from_ele0((int)(g & Cmask), s, r, ipos, len);
+        rD = r; iposD = ipos;
         if (!(ipos & 1)) {                               // down child: all three faces inside the parent
           const int cw = (int)((td * TPB) & (WIN_CH - 1)) + tid;
           double* t = sT + cw * 3;
@@ -1282,7 +1287,7 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive_cta(&doneD[it & 3]);
       const int u_tile = doU ? (int)((tile * TPB) >> twos) : -1;
-      prepare(tile + 1, nxt);
+      prepare(tile + 1, rP, iposP, nxt);
       if (doU) {
         // every warp has finished the down phase of the PREVIOUS iteration (first child of tile+1, last child of tile-1 ...)
         if (it > 0) mbar_wait(&doneD[(it - 1) & 3], (uint32_t)(((it - 1) >> 2) & 1));
