@@ -328,6 +328,16 @@ __device__ __forceinline__ void child_from_ele0(int k, int s, int& r, int& ipos,
   len = b + 1 - 2 * r;
 }
 
+// numbering of "my child of the next tile" from that of the current one: TPB positions further along the rows of the
+// parent.  Rows are at least TPB long except near the apex, so the loop usually runs zero or one time; the closed form
+// (with its square root) is only needed when the walk enters the next parent.
+__device__ __forceinline__ void child_advance(int s, int b, int k_next, int& r, int& ipos) {
+  if (k_next < TPB) { int len; child_from_ele0(k_next, s, r, ipos, len); return; }   // first tile of a parent (uniform)
+  ipos += TPB;
+  int len = b + 1 - 2 * r;
+  while (ipos > len) { ipos -= len; len -= 2; ++r; }
+}
+
 constexpr int TMA_T_DOUBLES = 3 * TPB + 8;   // tile + one child of halo on each side, padded to 16-byte spans
 constexpr int NSTAGE = 3;                    // tiles in flight per CTA
 constexpr size_t TMA_SMEM_BYTES = sizeof(double) * (NSTAGE * (TMA_T_DOUBLES + 3 * TPB) + 2 * 3 * TPB) + 16 * NSTAGE + 64;
@@ -851,11 +861,14 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
   } else {
     // ------------------------------------------------------------------ consumer warps
     struct Prep { int r, ipos, len; double h1a, h1b, h2a, h2b; };
-    auto prepare = [&](long long tile, int u_cur, Prep& p) {
-      p.r = 2; p.ipos = 2; p.len = 3; p.h1a = 0.0; p.h1b = 0.0; p.h2a = 0.0; p.h2b = 0.0;
+    // p.r / p.ipos come in as the numbering of my child of the PREVIOUS tile and leave as that of `tile`
+    auto prepare = [&](long long tile, int u_cur, bool first, Prep& p) {
+      p.h1a = 0.0; p.h1b = 0.0; p.h2a = 0.0; p.h2b = 0.0;
       if (tile >= tend) return;
       const long long g = tile * TPB + tid;
-      child_from_ele0((int)(g & Cmask), s, p.r, p.ipos, p.len);
+      if (first) child_from_ele0((int)(g & Cmask), s, p.r, p.ipos, p.len);
+      else child_advance(s, b, (int)(g & Cmask), p.r, p.ipos);
+      p.len = b + 1 - 2 * p.r;
       if (!FACE || !(p.ipos & 1)) return;
       const bool f1 = p.r == 1, side = p.ipos == 1 || p.ipos == p.len;
       if (f1 | side) {
@@ -876,7 +889,8 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
       }
     };
     Prep cur, nxt;
-    prepare(tbeg, -1, cur);
+    cur.r = 2; cur.ipos = 2; cur.len = 3;
+    prepare(tbeg, -1, true, cur);
     for (long long tile = tbeg; tile < tend; ++tile) {
       const int it = (int)(tile - tbeg);
       const long long g0 = tile * TPB;
@@ -887,7 +901,8 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
         mbar_wait(&barT[(tile + 2) & (WIN_NT - 1)], (uint32_t)(((tile + 2 - tlo) >> 3) & 1));
       }
       mbar_wait(&barB[it & (WIN_NB - 1)], (uint32_t)((it / WIN_NB) & 1));     // also acquires the coefficients of u_tile
-      prepare(tile + 1, u_tile, nxt);
+      nxt.r = cur.r; nxt.ipos = cur.ipos;
+      prepare(tile + 1, u_tile, false, nxt);
       const double* sPC = sPC2[u_tile & 1];
       double* bb = sB + (it & (WIN_NB - 1)) * 3 * TPB + tid * 3;
       {
@@ -1261,9 +1276,9 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
         waitB(td);                                       // also acquires the coefficients of the parent of td
         const int u_acq = (int)((td * TPB) >> twos);
         const long long g = td * TPB + tid;
-        int r, ipos, len;
-        child_from_ele0((int)(g & Cmask), s, r, ipos, len);
-        rD = r; iposD = ipos;
+        if (td == dlo) { int len; child_from_ele0((int)(g & Cmask), s, rD, iposD, len); }
+        else child_advance(s, b, (int)(g & Cmask), rD, iposD);
+        const int r = rD, ipos = iposD;
         if (!(ipos & 1)) {                               // down child: all three faces inside the parent
           const int cw = (int)((td * TPB) & (WIN_CH - 1)) + tid;
           double* t = sT + cw * 3;
