@@ -1231,21 +1231,23 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
     if (lane == 0) tma_store_wait_all();
   } else {
     // ------------------------------------------------------------------ consumer warps
-    auto waitT = [&](long long tile) { mbar_wait(&barT[tile & (WIN_NT - 1)], (uint32_t)(((tile - tlo) >> 3) & 1)); };
-    auto waitB = [&](long long tile) { mbar_wait(&barB[(tile - dlo) & (WIN_NB - 1)], (uint32_t)(((tile - dlo) >> 2) & 1)); };
+    // (all per-tile index arithmetic in 32-bit: this branch is issue-bound and cannot use the uniform datapath)
+    const int t0i = (int)t0, tbegi = (int)tbeg, tendi = (int)tend, dloi = (int)dlo, dhii = (int)dhi, tloi = (int)tlo, thii = (int)thi;
+    const int pshift = twos - 8;                          // tiles per parent = 2^pshift (TPB = 2^8)
+    const unsigned kmask = (unsigned)Cmask;
+    auto waitT = [&](int tile) { mbar_wait(&barT[tile & (WIN_NT - 1)], (uint32_t)(((tile - tloi) >> 3) & 1)); };
+    auto waitB = [&](int tile) { mbar_wait(&barB[(tile - dloi) & (WIN_NB - 1)], (uint32_t)(((tile - dloi) >> 2) & 1)); };
     struct Prep { int r, ipos, len; double h1a, h1b, h2a, h2b; };
     // numbering (r, ipos) of my child of `tile` comes from the down phase that relaxed the tile one iteration earlier;
     // the parent of `tile` has been acquired through an rhs tile by then
-    auto prepare = [&](long long tile, int r, int ipos, Prep& p) {
+    auto prepare = [&](int tile, int r, int ipos, Prep& p) {
       p.r = 2; p.ipos = 2; p.len = 3; p.h1a = 0.0; p.h1b = 0.0; p.h2a = 0.0; p.h2b = 0.0;
-      if (tile < tbeg || tile >= tend) return;
-      const long long g = tile * TPB + tid;
+      if (tile < tbegi || tile >= tendi) return;
       p.r = r; p.ipos = ipos; p.len = b + 1 - 2 * r;
       if (!(p.ipos & 1)) return;
       const bool f1 = p.r == 1, side = p.ipos == 1 || p.ipos == p.len;
       if (f1 | side) {
-        const int u = (int)(g >> twos);
-        const int* ix = sIdx2[u & 1];
+        const int* ix = sIdx2[(tile >> pshift) & 1];
         if (f1) {
           const int strip = ix[0], hm = ix[4];
           const double* e = a.ovl + ((size_t)strip * S + (p.ipos >> 1)) * 3;
@@ -1260,27 +1262,26 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
       }
     };
     Prep cur, nxt;
-    prepare(t0, 2, 2, cur);                              // t0 < tbeg: defaults
+    prepare(t0i, 2, 2, cur);                             // t0 < tbeg: defaults
     int rD = 2, iposD = 2;                               // numbering of my child of the tile relaxed by the last down phase
-    for (long long tile = t0; tile < tend; ++tile) {
-      const int it = (int)(tile - t0);
-      const long long td = tile + 2;
-      const bool doD = td >= dlo && td <= dhi, doU = tile >= tbeg;
-      if (tile == t0) {
-        for (long long tw = tlo; tw < min(thi, tile + 5); ++tw) waitT(tw);
-      } else if (tile + 4 < thi) {
+    for (int tile = t0i; tile < tendi; ++tile) {
+      const int it = tile - t0i;
+      const int td = tile + 2;
+      const bool doD = td >= dloi && td <= dhii, doU = tile >= tbegi;
+      if (tile == t0i) {
+        for (int tw = tloi; tw < min(thii, tile + 5); ++tw) waitT(tw);
+      } else if (tile + 4 < thii) {
         waitT(tile + 4);
       }
       const int rP = rD, iposP = iposD;                  // my child of tile+1 (down phase of the previous iteration)
       if (doD) {
         waitB(td);                                       // also acquires the coefficients of the parent of td
-        const int u_acq = (int)((td * TPB) >> twos);
-        const long long g = td * TPB + tid;
-        if (td == dlo) { int len; child_from_ele0((int)(g & Cmask), s, rD, iposD, len); }
-        else child_advance(s, b, (int)(g & Cmask), rD, iposD);
+        const int kD = (int)((((unsigned)td << 8) + (unsigned)tid) & kmask);
+        if (td == dloi) { int len; child_from_ele0(kD, s, rD, iposD, len); }
+        else child_advance(s, b, kD, rD, iposD);
         const int r = rD, ipos = iposD;
         if (!(ipos & 1)) {                               // down child: all three faces inside the parent
-          const int cw = (int)((td * TPB) & (WIN_CH - 1)) + tid;
+          const int cw = ((td & (WIN_NT - 1)) << 8) + tid;
           double* t = sT + cw * 3;
           const double T1 = t[0], T2 = t[1], T3 = t[2];
           FaceIn fi;
@@ -1290,8 +1291,8 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
           const double* tl = sT + ((cw - 1) & (WIN_CH - 1)) * 3;
           fi.n2a = tr[1]; fi.n2b = tr[2];
           fi.n3a = tl[0]; fi.n3b = tl[1];
-          const double* bb = sB + ((td - dlo) & (WIN_NB - 1)) * 3 * TPB + tid * 3;
-          const double* pd = sPC2[u_acq & 1] + PC_FOLD + 16;
+          const double* bb = sB + ((td - dloi) & (WIN_NB - 1)) * (3 * TPB) + tid * 3;
+          const double* pd = sPC2[(td >> pshift) & 1] + PC_FOLD + 16;
           const Folded& F = *reinterpret_cast<const Folded*>(pd);
           double o1, o2, o3;
           elem_apply_folded<MODE_GS>(F, pd, 0, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
@@ -1301,13 +1302,13 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
       // down phase of this iteration done (also when there was nothing to do): tell the other warps
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive_cta(&doneD[it & 3]);
-      const int u_tile = doU ? (int)((tile * TPB) >> twos) : -1;
       prepare(tile + 1, rP, iposP, nxt);
       if (doU) {
         // every warp has finished the down phase of the PREVIOUS iteration (first child of tile+1, last child of tile-1 ...)
         if (it > 0) mbar_wait(&doneD[(it - 1) & 3], (uint32_t)(((it - 1) >> 2) & 1));
         if (cur.ipos & 1) {
-          const int cw = (int)((tile * TPB) & (WIN_CH - 1)) + tid;
+          const int u_tile = tile >> pshift;
+          const int cw = ((tile & (WIN_NT - 1)) << 8) + tid;
           double* t = sT + cw * 3;
           const double T1 = t[0], T2 = t[1], T3 = t[2];
           FaceIn fi;
@@ -1327,7 +1328,7 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
               bmask |= 4;
             }
           }
-          const double* bb = sB + ((tile - dlo) & (WIN_NB - 1)) * 3 * TPB + tid * 3;
+          const double* bb = sB + ((tile - dloi) & (WIN_NB - 1)) * (3 * TPB) + tid * 3;
           const double* pu = sPC2[u_tile & 1];
           const Folded& F = *reinterpret_cast<const Folded*>(pu + PC_FOLD);
           double o1, o2, o3;
