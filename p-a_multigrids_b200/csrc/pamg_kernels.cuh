@@ -860,19 +860,23 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
     if (lane == 0) tma_store_wait_all();
   } else {
     // ------------------------------------------------------------------ consumer warps
+    // (per-tile index arithmetic in 32-bit: this branch cannot use the uniform datapath)
+    const int tbegi = (int)tbeg, tendi = (int)tend, tloi = (int)tlo, thii = (int)thi;
+    const int pshift = twos - 8;                          // tiles per parent = 2^pshift (TPB = 2^8)
+    const unsigned kmask = (unsigned)Cmask;
     struct Prep { int r, ipos, len; double h1a, h1b, h2a, h2b; };
     // p.r / p.ipos come in as the numbering of my child of the PREVIOUS tile and leave as that of `tile`
-    auto prepare = [&](long long tile, int u_cur, bool first, Prep& p) {
+    auto prepare = [&](int tile, int u_cur, bool first, Prep& p) {
       p.h1a = 0.0; p.h1b = 0.0; p.h2a = 0.0; p.h2b = 0.0;
-      if (tile >= tend) return;
-      const long long g = tile * TPB + tid;
-      if (first) child_from_ele0((int)(g & Cmask), s, p.r, p.ipos, p.len);
-      else child_advance(s, b, (int)(g & Cmask), p.r, p.ipos);
+      if (tile >= tendi) return;
+      const int kk = (int)((((unsigned)tile << 8) + (unsigned)tid) & kmask);
+      if (first) child_from_ele0(kk, s, p.r, p.ipos, p.len);
+      else child_advance(s, b, kk, p.r, p.ipos);
       p.len = b + 1 - 2 * p.r;
       if (!FACE || !(p.ipos & 1)) return;
       const bool f1 = p.r == 1, side = p.ipos == 1 || p.ipos == p.len;
       if (f1 | side) {
-        const int u = (int)(g >> twos);
+        const int u = tile >> pshift;
         const bool same = u == u_cur;                    // the coefficients of u_cur have been acquired by this thread
         const int* ix = sIdx2[u & 1];
         if (f1) {
@@ -890,23 +894,22 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
     };
     Prep cur, nxt;
     cur.r = 2; cur.ipos = 2; cur.len = 3;
-    prepare(tbeg, -1, true, cur);
-    for (long long tile = tbeg; tile < tend; ++tile) {
-      const int it = (int)(tile - tbeg);
-      const long long g0 = tile * TPB;
-      const int u_tile = (int)(g0 >> twos);
+    prepare(tbegi, -1, true, cur);
+    for (int tile = tbegi; tile < tendi; ++tile) {
+      const int it = tile - tbegi;
+      const int u_tile = tile >> pshift;
       if (it == 0) {
-        for (long long tw = tlo; tw <= min(tile + 2, thi - 1); ++tw) mbar_wait(&barT[tw & (WIN_NT - 1)], (uint32_t)(((tw - tlo) >> 3) & 1));
-      } else if (tile + 2 < thi) {
-        mbar_wait(&barT[(tile + 2) & (WIN_NT - 1)], (uint32_t)(((tile + 2 - tlo) >> 3) & 1));
+        for (int tw = tloi; tw <= min(tile + 2, thii - 1); ++tw) mbar_wait(&barT[tw & (WIN_NT - 1)], (uint32_t)(((tw - tloi) >> 3) & 1));
+      } else if (tile + 2 < thii) {
+        mbar_wait(&barT[(tile + 2) & (WIN_NT - 1)], (uint32_t)(((tile + 2 - tloi) >> 3) & 1));
       }
       mbar_wait(&barB[it & (WIN_NB - 1)], (uint32_t)((it / WIN_NB) & 1));     // also acquires the coefficients of u_tile
       nxt.r = cur.r; nxt.ipos = cur.ipos;
       prepare(tile + 1, u_tile, false, nxt);
       const double* sPC = sPC2[u_tile & 1];
-      double* bb = sB + (it & (WIN_NB - 1)) * 3 * TPB + tid * 3;
+      double* bb = sB + (it & (WIN_NB - 1)) * (3 * TPB) + tid * 3;
       {
-        const int cw = (int)(g0 & (WIN_CH - 1)) + tid;
+        const int cw = ((tile & (WIN_NT - 1)) << 8) + tid;
         const double* t = sT + cw * 3;
         const double T1 = t[0], T2 = t[1], T3 = t[2];
         const bool up = cur.ipos & 1;
