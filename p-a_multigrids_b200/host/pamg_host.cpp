@@ -1,7 +1,8 @@
 // pamg_host.cpp -- C++ host driver above the C ABI (include/pamg.h), mirroring the reference's own driver:
 // program Transport_equation (main.F90:16-51) selects a solver with `mode`; mode 9 runs
 // Semi_implicit_iterative (transport_tri_semi.F90:14-391: ReadMSH, initial condition by region id, time
-// loop, n_multigrid "V-cycles" per step) and mode 4 runs unstr_explicit (transport_tri_unstr.F90:413-795).
+// loop, n_multigrid "V-cycles" per step), mode 4 runs unstr_explicit (transport_tri_unstr.F90:413-795) and mode 1 runs
+// trans_rec (transport_rect.F90:7) and writes its two dump files.
 // The reference hard-codes every parameter and is recompiled to change them; here they are flags whose
 // defaults are the literals of main.F90:28,46-47.  Everything numerical happens on the GPU through pamg_*.
 #include <chrono>
@@ -77,6 +78,43 @@ int main(int argc, char** argv) {
   // literal defaults of main.F90:28 (mode 4) and :46-47 (mode 9)
   if (a.mode == 4) { if (a.cfl < 0) a.cfl = 0.07; if (a.dx < 0) a.dx = 1e-3; if (a.region < 0) a.region = 12; if (a.ux == 0 && a.uy == 0) a.ux = 0.9; }
   else { if (a.cfl < 0) a.cfl = 1.0; if (a.dx < 0) a.dx = a.literal ? 1.25e-5 : 1e-3; if (a.region < 0) a.region = 4; }
+
+  if (a.mode == 1) {
+    // case(1) of main.F90:19: call trans_rec(0.7, 2, .false., 10, 250., 2, 2*100, 1, ..., 2*0.01428571, 0.0, .false.)
+    // and the two dumps of transport_rect.F90:320-344 (x y t of the four nodes of every element; x t of the analytical pulse)
+    const int ner = 200, nec = 1;
+    const double CFL = a.cfl > 0 ? a.cfl : 0.7, ux = (a.ux == 0 && a.uy == 0) ? 2 * 0.01428571 : a.ux, uy = a.uy, time = 250.0;
+    pamg_params p1;
+    pamg_default_params(&p1, 1);
+    pamg_handle* h1 = nullptr;
+    int rc1 = pamg_create(&p1, a.device, &h1);
+    if (rc1 != PAMG_OK) return die(nullptr, "pamg_create (no CUDA device? there is no CPU fallback)", rc1);
+    std::vector<double> xa((size_t)ner * nec * 8), t((size_t)ner * nec * 4);
+    int ntime = 0;
+    if ((rc1 = pamg_trans_rec(h1, CFL, ner, nec, 100.0, 100.0, ux, uy, time, a.nits, a.njac, a.exact_minv, a.literal ? 0 : 1, xa.data(),
+                              t.data(), &ntime)))
+      return die(h1, "pamg_trans_rec", rc1);
+    const std::string dir = a.mesh.empty() ? std::string(".") : a.mesh;      // --mesh doubles as the output directory here
+    FILE* f = std::fopen((dir + "/DG-rectangular_structured").c_str(), "w");
+    if (!f) { std::fprintf(stderr, "cannot write into %s\n", dir.c_str()); return 1; }
+    for (int e = 0; e < ner * nec; ++e)
+      for (int i = 0; i < 4; ++i) std::fprintf(f, " %16.9g %16.9g %16.9g\n", xa[(size_t)e * 8 + 2 * i], xa[(size_t)e * 8 + 2 * i + 1], t[(size_t)e * 4 + i]);
+    std::fclose(f);
+    // analytical pulse: shifted by the distance travelled, in whole elements (:101-105)
+    const double dx = 100.0 / ner, dt = CFL * dx;
+    const int off = (int)(ux * dt * ntime * ner / 100.0 + 1);
+    f = std::fopen((dir + "/DG-rectangular_structured_analytical").c_str(), "w");
+    if (!f) { std::fprintf(stderr, "cannot write into %s\n", dir.c_str()); return 1; }
+    for (int e = 1; e <= ner * nec; ++e)
+      for (int i = 0; i < 4; ++i)
+        std::fprintf(f, " %16.9g %16.9g\n", xa[(size_t)(e - 1) * 8 + 2 * i], (e >= off + ner / 5 && e <= off + ner / 2) ? 1.0 : 0.0);
+    std::fclose(f);
+    double sum = 0, mx = -1e300, mn = 1e300;
+    for (double v : t) { sum += v; mx = std::fmax(mx, v); mn = std::fmin(mn, v); }
+    std::printf("trans_rec: ntime = %d\ntnew: sum %.12e min %.6e max %.6e\n", ntime, sum, mn, mx);
+    pamg_destroy(h1);
+    return 0;
+  }
 
   std::printf("---------------------------------------------------------\n|       Reading the .msh file     |\n");
   const double t0 = now();
@@ -157,7 +195,7 @@ int main(int argc, char** argv) {
     for (double v : T) { sum += v; mx = std::fmax(mx, v); mn = std::fmin(mn, v); }
     std::printf("cpu_time for time_loop = %g\ntnew: sum %.12e min %.6e max %.6e\n", t2 - t1, sum, mn, mx);
   } else {
-    std::fprintf(stderr, "mode %d is outside the hot path (modes 4 and 9 are implemented; see DESIGN.md)\n", a.mode);
+    std::fprintf(stderr, "mode %d is outside the hot path (modes 1, 4 and 9 are implemented; see DESIGN.md)\n", a.mode);
     pamg_destroy(h);
     return 2;
   }

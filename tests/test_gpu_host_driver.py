@@ -62,3 +62,17 @@ def test_mode4_unstr_explicit(tmp_path):
     orc.lib().orc_unstr_explicit(mesh.U, mesh.X, mesh.neig, mesh.fneig, mesh.dir, 0.9, 0.0, 0.07e-3, 2, 2, 10, 0, 0, 0.0, T)
     assert abs(float(m.group(1)) - T.sum()) <= 1e-9 * abs(T.sum())
     assert "totele = 8192" in out
+
+
+def test_mode1_trans_rec_writes_the_reference_dumps(tmp_path):
+    """pamg_host --mode 1 = case(1) of main.F90:19; its two dump files against the files the reference ships."""
+    out = run_host("--mode", 1, "--mesh", str(tmp_path))
+    assert "ntime = 714" in out
+    from helpers import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "rect_golden.npz"))
+    num = np.loadtxt(tmp_path / "DG-rectangular_structured")
+    ana = np.loadtxt(tmp_path / "DG-rectangular_structured_analytical")
+    assert num.shape == (800, 3) and ana.shape == (800, 2)
+    assert np.array_equal(num[:, :2], g["numerical"][:, :2])
+    assert np.max(np.abs(num[:, 2] - g["numerical"][:, 2])) <= 3e-5       # the reference computed in single precision
+    assert np.allclose(ana[:, 0], g["analytical"][:, 0], atol=1e-5) and np.array_equal(ana[:, 1], g["analytical"][:, 1])
