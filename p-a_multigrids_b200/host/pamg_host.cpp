@@ -77,6 +77,7 @@ int main(int argc, char** argv) {
   }
   // literal defaults of main.F90:28 (mode 4) and :46-47 (mode 9)
   if (a.mode == 4) { if (a.cfl < 0) a.cfl = 0.07; if (a.dx < 0) a.dx = 1e-3; if (a.region < 0) a.region = 12; if (a.ux == 0 && a.uy == 0) a.ux = 0.9; }
+  else if (a.mode == 1) { if (a.cfl < 0) a.cfl = 0.7; }
   else { if (a.cfl < 0) a.cfl = 1.0; if (a.dx < 0) a.dx = a.literal ? 1.25e-5 : 1e-3; if (a.region < 0) a.region = 4; }
 
   if (a.mode == 1) {
