@@ -86,6 +86,13 @@ void pamg_mesh_free(pamg_mesh* m);
 
 /* ---- handle ------------------------------------------------------------------------------------ */
 int pamg_create(const pamg_params* p, int device, pamg_handle** out);
+/* One host thread driving ngpus devices (the reference's driver is one serial process, main.F90:16-51): devices[i] is the CUDA
+ * device of part i (NULL = 0..ngpus-1; a device may appear more than once).  pamg_set_parents cuts the mesh into ngpus contiguous
+ * blocks of parents (the scheme Generic.F90:387-401 sketches); every other entry takes and returns WHOLE-mesh arrays and fans out
+ * inside the library.  The halo strips of cut faces travel by direct stores into the neighbour GPU's memory (peer access, no
+ * library collective), norms are combined on the host, small coarse levels are agglomerated on part 0.  Entries that exist on a
+ * single device only (unstructured front-ends, trans_rec, local inverse) run on part 0. */
+int pamg_create_multi(const pamg_params* p, int ngpus, const int* devices, pamg_handle** out);
 void pamg_destroy(pamg_handle* h);
 const char* pamg_last_error(const pamg_handle* h);
 /* Mesh%X, Neig, fNeig, Dir (Structures.F90:143-170).  Builds per-parent geometry for every level
@@ -98,6 +105,12 @@ int pamg_set_parents(pamg_handle* h, int U, const double* X, const int32_t* neig
 int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, const int32_t* neig,
                                const int32_t* fneig, const int32_t* dir, int nparts, const int32_t* part_first,
                                int my_part);
+/* Dirichlet data of the domain-boundary parent faces (Neig == 0), [U_global][3] in gmsh face order.  update_overlaps carries
+ * a t_bc argument (splitting.F90:1210) that HEAD overwrites with boundary(x,y) = sin(x+y) (:1246-1252); this entry makes it
+ * data: kind 0 = sin(x+y) (the default everywhere), 1 = the constant value[], 2 = open face (no data and no penalty term; only
+ * for faces with n.u >= 0, else pamg_set_parents returns PAMG_ERR_UNSUPPORTED).  value may be NULL (zeros).  Must precede
+ * pamg_set_parents / pamg_set_parents_partition. */
+int pamg_set_boundary_data(pamg_handle* h, int U_global, const int32_t* kind, const double* value);
 int pamg_ndof(const pamg_handle* h, int level, int64_t* ndof);
 
 int pamg_upload_field(pamg_handle* h, int field, int level, const double* host);
@@ -129,10 +142,14 @@ int pamg_literal_timestep(pamg_handle* h, int solver, int n_multigrid, int n_smo
 int pamg_timestep_host(pamg_handle* h, const double* tnew_in, double* tnew_out, int max_cycles, double tol,
                        int* cycles, double* relres);
 
-/* smoother with HOST buffers (pinned memory recommended), pipelined across calls: the upload of call k+1 overlaps the
- * download of call k.  tnew_out of a call is complete once pamg_sync has returned (or the next call that reuses
- * the buffer has been queued - the copies are stream-ordered).  Any other entry that reads or writes level-1
- * fields must be preceded by pamg_sync. */
+/* smoother with HOST buffers, blocking like the reference's call (transport_tri_semi.F90:331): upload tnew_in, nsweeps sweeps,
+ * download into tnew_out; both buffers are free again when it returns. */
+int pamg_smoother_host(pamg_handle* h, int solver, int nsweeps, const double* tnew_in, double* tnew_out);
+/* the same, ASYNCHRONOUS and pipelined across calls (pinned memory required for any overlap): the call returns once the
+ * work is queued.  tnew_in must stay untouched and tnew_out is not valid until pamg_sync has returned.  The upload of
+ * call k+1 overlaps the sweeps and the download of call k - unless tnew_in overlaps the tnew_out of the previous call (a
+ * dependent loop, or one buffer for both), in which case the library orders the upload after that download.  Any other
+ * entry that reads or writes level-1 fields must be preceded by pamg_sync. */
 int pamg_smooth_host(pamg_handle* h, int solver, int nsweeps, const double* tnew_in, double* tnew_out);
 
 /* ---- distributed halo (update_overlaps across GPUs; Generic.F90:387-401 sketches the block partition) -- */

@@ -423,6 +423,11 @@ struct orc_semi {
   // geometric halo maps per parent gmsh face: reversed flag for the writer, node map for the reader
   std::vector<int> halo_rev;    // [u][mface]: 1 -> slot S-p+1, 0 -> slot p
   std::vector<int> halo_node;   // [u][mface][2]: strip entry (0..2) coincident with my face nodes a, b
+  // Dirichlet data of domain-boundary parent faces (update_overlaps carries a t_bc argument, splitting.F90:1210, that HEAD
+  // overwrites with boundary(x,y) = sin(x+y) at :1246-1252).  kind 0: sin(x+y) (HEAD); 1: the constant bc_val; 2: no data
+  // (open face: no penalty term, the exterior trace equals the interior one)
+  std::vector<int> bc_kind;     // [u][mface]
+  std::vector<double> bc_val;   // [u][mface]
 };
 
 static int g_threads = 1;
@@ -603,10 +608,14 @@ void element_terms(const orc_semi* h, const orc_semi::Level& L, int level, int u
     int a = FACE_NODES[f - 1][0] - 1, b = FACE_NODES[f - 1][1] - 1;
     double T2a, T2b, delta_x;
     int mface = MFACE[f - 1];
+    bool open_face = false;
     if (ele22 != 0) {
       const double* Tn = &Tnbr_field[((size_t)u * L.C + (ele22 - 1)) * 3];
       T2a = Tn[b]; T2b = Tn[a];  // shared nodes appear reversed on the other side (transport_tri.F90:610-611)
       delta_x = h->dc_str[u * 3 + f - 1] * lvl_scale;
+    } else if (h->neig[u * 3 + mface - 1] == 0 && h->bc_kind[u * 3 + mface - 1] == 2) {
+      T2a = Town[a]; T2b = Town[b];   // open boundary face: exterior trace = interior trace, no penalty
+      delta_x = 1.0; open_face = true;
     } else {
       int sp = (f == 1) ? ipos / 2 + 1 : irow;   // :629-638
       const double* e = &ovl[(size_t)(mface - 1) * 3 * L.S + (size_t)(sp - 1) * 3];
@@ -630,7 +639,7 @@ void element_terms(const orc_semi* h, const orc_semi::Level& L, int level, int u
         for (int s = 0; s < 2; ++s)
           op.flux[q] += TB.sn[s][c] * snorm[s][d] * sdet[s] *
                         ((1.0 - income[s]) * uu[d] * Ts[s] + income[s] * uu[d] * T2s[s]);
-      double kd = h->p.k / delta_x;
+      double kd = open_face ? 0.0 : h->p.k / delta_x;
       for (int s = 0; s < 2; ++s) {
         op.dsurf[q] += kd * TB.sn[s][c] * sdet[s] * (Ts[s] - T2s[s]);   // matrices.F90:113-115 form
         op.mydiag[q] += kd * TB.sn[s][c] * TB.sn[s][c] * sdet[s];      // my_diff_surf(i,i,f), :471-472
@@ -766,7 +775,13 @@ orc_semi* orc_semi_create(const orc_params* p, int U, const double* X, const int
   }
   build_geometry(h);
   build_halo_maps(h);
+  h->bc_kind.assign((size_t)U * 3, 0);
+  h->bc_val.assign((size_t)U * 3, 0.0);
   return h;
+}
+void orc_semi_set_boundary(orc_semi* h, const int32_t* kind, const double* value) {
+  for (size_t i = 0; i < (size_t)h->U * 3; ++i) { h->bc_kind[i] = kind[i]; h->bc_val[i] = value ? value[i] : 0.0; }
+  for (auto& L : h->lev) { std::fill(L.ovl.begin(), L.ovl.end(), 0.0); std::fill(L.ovl_old.begin(), L.ovl_old.end(), 0.0); }
 }
 void orc_semi_destroy(orc_semi* h) { delete h; }
 int64_t orc_semi_ndof(orc_semi* h, int level) { return (int64_t)3 * h->lev[level - 1].C * h->U; }
@@ -803,10 +818,13 @@ void orc_semi_update_overlaps(orc_semi* h, int level) {
         int pos = (mf == 1) ? ipos / 2 + 1 : irow;
         int npos = h->neig[u * 3 + mf - 1];
         if (npos == 0) {
+          const int kind = h->bc_kind[u * 3 + mf - 1];
+          if (kind == 2) continue;                                           // open face: no Dirichlet data
           double x[3][2];
           get_splitting(X, L.s, ele, x);
           int a = SIDE_NODES[mf - 1][0] - 1, b = SIDE_NODES[mf - 1][1] - 1;  // :1246-1249,1287-1290,1344-1347
           double ta = bc_scale * boundary_fn(x[a][0], x[a][1]), tb = bc_scale * boundary_fn(x[b][0], x[b][1]);
+          if (kind == 1) ta = tb = bc_scale * h->bc_val[u * 3 + mf - 1];      // t_bc as data (splitting.F90:1210)
           size_t o = ((size_t)u * 3 + (mf - 1)) * 3 * S + (size_t)(pos - 1) * 3;
           L.ovl[o + a] = ta; L.ovl[o + b] = tb;
           L.ovl_old[o + a] = ta; L.ovl_old[o + b] = tb;
@@ -965,6 +983,7 @@ void orc_semi_restrict(orc_semi* h, int fine_level) {
   if (fine_level >= h->p.multi_levels) return;  // splitting.F90:18
   orc_semi::Level& F = h->lev[fine_level - 1];
   orc_semi::Level& Cc = h->lev[fine_level];
+#pragma omp parallel for num_threads(g_threads) schedule(static)
   for (int u = 0; u < h->U; ++u)
     for (int c = 1; c <= Cc.C; ++c) {
       int fin[4];
@@ -993,6 +1012,7 @@ void orc_semi_prolong(orc_semi* h, int fine_level) {
   // literal acts on tracer%tnew (splitting.F90:59-88); intended acts on the iterate (tnonlin)
   std::vector<double>& ft = h->p.transfer == 0 ? F.tnew : F.tnonlin;
   const std::vector<double>& ct = h->p.transfer == 0 ? Cc.tnew : Cc.tnonlin;
+#pragma omp parallel for num_threads(g_threads) schedule(static)
   for (int u = 0; u < h->U; ++u)
     for (int c = 1; c <= Cc.C; ++c) {
       int fin[4];

@@ -72,6 +72,10 @@ enum { ORC_TNEW = 0, ORC_TOLD = 1, ORC_RHS = 2, ORC_RES = 3, ORC_SRC = 4, ORC_TN
 orc_semi* orc_semi_create(const orc_params* p, int U, const double* X, const int32_t* neig,
                           const int32_t* fneig, const int32_t* dir);
 void orc_semi_destroy(orc_semi*);
+/* Dirichlet data per parent face [U][3] (gmsh face order), used where Neig == 0: kind 0 = sin(x+y) (HEAD,
+ * splitting.F90:1246-1252), 1 = the constant value[] (update_overlaps' t_bc argument, :1210), 2 = open face (no data,
+ * no penalty term; exterior trace = interior trace).  Clears the halo strips. */
+void orc_semi_set_boundary(orc_semi*, const int32_t* kind, const double* value);
 double* orc_semi_field(orc_semi*, int field, int level);      /* (3, 4^s, U) Fortran order */
 double* orc_semi_overlap(orc_semi*, int level, int old);     /* [u][face][3*2^s] */
 int64_t orc_semi_ndof(orc_semi*, int level);

@@ -12,7 +12,7 @@ LIB = os.path.join(LIBDIR, "libpamg_cuda.so")
 HOST_BIN = os.path.join(LIBDIR, "pamg_host")
 
 SOURCES = ["pamg_api.cu", "pamg_mesh.cpp", "pamg_plan.cpp"]
-DEPS = SOURCES + ["pamg_kernels.cuh", "pamg_stream.cuh", "pamg_unstr.cuh", "pamg_internal.h"]
+DEPS = SOURCES + ["pamg_kernels.cuh", "pamg_unstr.cuh", "pamg_internal.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -14,7 +14,6 @@
 
 #include "pamg_internal.h"
 #include "pamg_kernels.cuh"
-#include "pamg_stream.cuh"
 #include "pamg_unstr.cuh"
 
 using namespace pamg;
@@ -55,6 +54,9 @@ NcclApi g_nccl;
 
 struct pamg_handle;
 namespace { void p2p_close(pamg_handle* h); }
+// words of pamg_handle::agg_words (device memory): block counter, per-destination transfer numbers, per-sender flags
+// and the number of transfers already consumed per sender
+enum { AGG_COUNTER = 0, AGG_EPOCH = 8, AGG_FLAGS = 40, AGG_EXPECT = 72, AGG_WORDS = 104 };
 
 // ------------------------------------------------------------------ handle
 struct LevelDev {
@@ -66,10 +68,10 @@ struct LevelDev {
   double *told = nullptr, *rhs = nullptr, *res = nullptr;
   double* ovlb[2] = {nullptr, nullptr};       // halo strips, double-buffered: (nstrips + nsend) * 3S doubles each
   int ovl_cur = 0;                            // ovlb[ovl_cur] holds the strips of the current iterate when strips_valid
-  bool strips_valid = false;
+  bool strips_valid = false;                  // strips of the faces between local parents hold the current iterate
+  bool cut_valid = false;                     // strips of the faces cut by the GPU partition hold the current iterate
   double* ovl_old = nullptr;                  // told strips (update_overlaps as written only)
   double* pc = nullptr;               // [U][NPC]
-  int2* items = nullptr; int nitems = 0;  // work list of the row-streaming kernel (levels with s >= STREAM_MIN_S)
   bool rhs_valid = false;             // level 1: RHS matches TOLD
   double* spare = nullptr;            // third field buffer of pamg_smooth_host (level 1, allocated on first use)
 };
@@ -84,7 +86,10 @@ struct pamg_handle {
   HaloPlan plan;
   int U = 0;  // local parents
   double* xg = nullptr;
-  int32_t *strip_of = nullptr, *dst_strip = nullptr, *rev = nullptr, *hmap = nullptr;
+  int32_t *strip_of = nullptr, *dst_strip = nullptr, *rev = nullptr, *hmap = nullptr, *nsrc = nullptr, *cut_lf = nullptr;
+  // Dirichlet data of domain-boundary faces (pamg_set_boundary_data): global [U_global][3] on the host, local copy on the device
+  std::vector<int32_t> bc_kind_h; std::vector<double> bc_val_h;
+  int32_t* bc_kind = nullptr; double* bc_val = nullptr;
   std::vector<LevelDev> lev;
   double* partial = nullptr; int npartial = 0; int last_partials = 0;
   double* out3 = nullptr;         // device
@@ -92,16 +97,16 @@ struct pamg_handle {
   double* scratch = nullptr; size_t scratch_bytes = 0;  // L2 flush
   double* stage = nullptr; size_t stage_bytes = 0;      // pinned staging for host-buffer entry points
   int kernel_mode = 4;  // 4 window kernel (default; 1-D TMA tile ring, all neighbours from shared memory), 1 pipelined 1-D TMA tiles,
-                        // 2 row-streaming, 3 branch-free direct, 0 direct loads; PAMG_KERNEL=win|tma1d|stream|direct2|direct
-  int* counters = nullptr;
+                        // 3 branch-free direct; PAMG_KERNEL=win|tma1d|direct2 (A/B and the families used on small / deep levels)
+  bool direct_halo = true;  // out-of-place sweeps read the exterior values of faces between local parents straight from the
+                            // neighbour parent's field, no k_halo launch per sweep (PAMG_HALO=strips restores the strips)
+  // resident CTAs per SM of the shared-memory kernels on THIS device ([face_terms]); set once per handle in configure_kernels
+  struct KernelCfg { int win2[2] = {0, 0}, win[2] = {0, 0}, tma[2] = {0, 0}, gs2 = 0, gs = 0, halo = 0; bool done = false; } kc;
   bool capturing = false;   // stream capture in progress: no synchronisation, no per-launch error polling
   bool use_graph = true;    // replay the V-cycle as a CUDA graph from the second cycle on (PAMG_GRAPH=0 disables)
-  struct VcGraph { long long key; cudaGraphExec_t exec; long long launches; };
+  struct VcGraph { long long key; std::vector<cudaGraphExec_t> exec; std::vector<long long> launches; };   // one graph per GPU of the group
   std::vector<VcGraph> vc_graphs;   // a few cached V-cycle graphs (solver / sweep counts / buffer parity)
   bool graph_nccl = true;       // try to capture NCCL calls into the V-cycle graph (PAMG_GRAPH_NCCL=0 disables)
-  bool split_boundary = false;  // PAMG_SPLIT=1: tile kernel + k_boundary_fix for the children on parent faces (measured: no gain for Jacobi)
-  bool fused_halo = false;  // PAMG_FUSED_HALO=1: sweeps write the next sweep's strips themselves (measured slower: the extra work
-                            // of the few children on parent faces delays the per-tile barrier; profiles/README.md)
   bool gs_tma = true;   // coloured GS pass through the TMA tile kernel (PAMG_GS=direct selects the direct kernel)
   bool win_producer = true;  // window kernel with a producer warp (k_element_win2); PAMG_WIN=barrier: k_element_win
   bool gs_fused = true; // both colours in one pass (k_gs_win); PAMG_GS=twopass keeps the two in-place passes
@@ -118,6 +123,11 @@ struct pamg_handle {
   bool shared_stream = false;
   std::vector<int32_t> part_first;  // copy of the partition table
   int U_global = 0;
+  // single-process multi-GPU (pamg_create_multi): the root owns one sub-handle per device and fans every entry out
+  std::vector<pamg_handle*> parts;  // root only
+  bool is_root = false;
+  bool in_group = false;            // sub-handle of such a root: its peers are driven by the same host thread
+  unsigned long long* agg_words = nullptr;   // sub-handle: counters / flags of the device-initiated block transfers
   // unstructured
   UnstrDev un;
   int un_use_dir = 0;
@@ -125,10 +135,12 @@ struct pamg_handle {
   cudaStream_t up_stream = nullptr, down_stream = nullptr;
   cudaEvent_t ev_up = nullptr, ev_comp = nullptr, ev_down[2] = {nullptr, nullptr};
   unsigned pipe_calls = 0;             // calls since the last pamg_sync
+  const double* last_out = nullptr;    // host buffer the most recent call downloads into
   // halo exchange by direct stores into peer memory (CUDA IPC over NVLink); PAMG_P2P=0 keeps ncclSend/ncclRecv
   bool p2p_enabled = true, p2p_ready = false, p2p_failed = false;
-  bool p2p_fuse = true;                // cut-face values go to the peers from inside k_halo (PAMG_P2P_FUSE=0: separate kernel)
-  unsigned long long* p2p_sync = nullptr;   // exchange number, block counter, error word (local)
+  unsigned long long* p2p_sync = nullptr;   // exchange number, block counter (device)
+  unsigned long long* p2p_err_host = nullptr;   // error word raised by a halo kernel that timed out: mapped pinned memory, so
+  unsigned long long* p2p_err_dev = nullptr;    // every host synchronisation point can check it without a copy
   uint4* p2p_stage = nullptr;               // flagged receive staging, 2 parities x p2p_stage_words (IPC-exported)
   long long p2p_stage_words = 0;
   struct P2PPeer { int slot_at_peer = -1, strip_begin_at_peer = 0; long long recv_strips_at_peer = 0; uint4* stage = nullptr; };
@@ -143,6 +155,12 @@ int fail(pamg_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
   return code;
 }
+ #define CK_(hh, call)                                                                            \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      return fail(hh, PAMG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
 #define CK(call)                                                                                 \
   do {                                                                                           \
     cudaError_t e_ = (call);                                                                     \
@@ -173,10 +191,10 @@ double* field_ptr(pamg_handle* h, int field, int level, bool for_write, int* rc)
   LevelDev& L = h->lev[level - 1];
   switch (field) {
     case PAMG_TNEW:
-      if (for_write) { *rc = materialise_tnew(h, L); L.strips_valid = false; return L.T[L.cur ^ 1]; }
+      if (for_write) { *rc = materialise_tnew(h, L); L.strips_valid = false; L.cut_valid = false; return L.T[L.cur ^ 1]; }
       return tnew_ptr(L);
     case PAMG_TNONLIN:
-      if (for_write) { *rc = materialise_tnew(h, L); L.strips_valid = false; }
+      if (for_write) { *rc = materialise_tnew(h, L); L.strips_valid = false; L.cut_valid = false; }
       return L.T[L.cur];
     case PAMG_TOLD: if (for_write) L.rhs_valid = false; return L.told;
     case PAMG_RHS: if (for_write) L.rhs_valid = true; return L.rhs;
@@ -189,8 +207,12 @@ double* field_ptr(pamg_handle* h, int field, int level, bool for_write, int* rc)
 // ---- per-parent geometry in closed form (tri_det_nlx ShapFun.F90:1414-1454; det_snlx_all :1554-1590;
 //      level scaling :1678-1683,1751-1780; get_d_center Msh2Tri.F90:358-383; add_diffusion_surf
 //      matrices.F90:84-110).  One row of NPC coefficients per parent per level.
-void parent_coefficients(const pamg_params& p, const double* Xall, const int32_t* neig, int g /*global parent*/,
-                         int s, double* pc) {
+// bc_kind: [U_global][3] kinds of the domain-boundary faces (nullptr = Dirichlet everywhere); an open face (kind 2) has no
+// penalty term.  Returns false for an open face with inflow (n.u < 0): the exterior trace would have to follow the interior
+// one inside the kernels, which is not supported.
+bool parent_coefficients(const pamg_params& p, const double* Xall, const int32_t* neig, const int32_t* bc_kind,
+                         int g /*global parent*/, int s, double* pc) {
+  bool supported = true;
   const double* X = Xall + (size_t)g * 6;
   const double x1 = X[0], y1 = X[1], x2 = X[2], y2 = X[3], x3 = X[4], y3 = X[5];
   const double A = x1 - x3, B = y1 - y3, Cc = x2 - x3, D = y2 - y3;
@@ -232,6 +254,10 @@ void parent_coefficients(const pamg_params& p, const double* Xall, const int32_t
       dcX = std::sqrt((cx - mx) * (cx - mx) + (cy - my) * (cy - my));
     }
     pc[PC_PENX + f] = p.k * lhalf / (3.0 * dcX);
+    if (q == 0 && bc_kind && bc_kind[(size_t)g * 3 + mface[f]] == 2) {
+      pc[PC_PENX + f] = 0.0;                                 // open face: no data, no penalty
+      if (p.face_terms && pc[PC_FL + f] < 0.0) supported = false;
+    }
   }
   // omega / D of children with all three faces inside the parent (get_diagonal :481-486): node 1 sits on
   // faces 1,3; node 2 on faces 2,3; node 3 on faces 1,2.  The penalty diagonal exists only with the face block.
@@ -276,6 +302,7 @@ void parent_coefficients(const pamg_params& p, const double* Xall, const int32_t
     pc[PC_WB + mask * 3 + 2] = p.omega / (4.0 * pc[PC_CM] + pc[PC_K33] + 2.0 * (pen[0] + pen[1]));
   }
   for (int i = PC_WB + 24; i < NPC; ++i) pc[i] = 0.0;
+  return supported;
 }
 
 int launch_halo(pamg_handle* h, int level, int what = 0);
@@ -285,57 +312,84 @@ void p2p_close(pamg_handle* h) {
   h->p2p_opened.clear();
   if (h->p2p_sync) { cudaFree(h->p2p_sync); h->p2p_sync = nullptr; }
   if (h->p2p_stage) { cudaFree(h->p2p_stage); h->p2p_stage = nullptr; }
+  if (h->p2p_err_host) { cudaFreeHost(h->p2p_err_host); h->p2p_err_host = nullptr; h->p2p_err_dev = nullptr; }
   h->p2p_ready = false; h->p2p_failed = false;
   for (auto& pp : h->p2p_peers) pp.stage = nullptr;
 }
 
-// collective over all ranks (called at the first exchange, never during stream capture): allocate the flagged
-// staging buffer, exchange its CUDA IPC handle, map the peers' buffers, agree on the outcome
+// a halo kernel that gave up waiting for a peer GPU raised the error word; every host synchronisation point of the
+// partitioned path (residual norms, V-cycle control, downloads, pamg_sync) reports it instead of returning stale numbers
+int p2p_check(pamg_handle* h) {
+  if (h->p2p_err_host && *(volatile unsigned long long*)h->p2p_err_host)
+    return fail(h, PAMG_ERR_CUDA, "halo exchange timed out waiting for a peer GPU");
+  return PAMG_OK;
+}
+
+// local part of the set-up: exchange counters, the flagged receive staging buffer (2 parities) and the error word
+int p2p_alloc_local(pamg_handle* h) {
+  long long strips = 0;
+  for (const auto& pr : h->plan.peers) strips = std::max(strips, (long long)pr.strip_begin + pr.nfaces);
+  h->p2p_stage_words = strips * 3 * h->lev[0].S;
+  const size_t stage_bytes = (size_t)std::max(1ll, 2 * h->p2p_stage_words) * sizeof(uint4);
+  CK(cudaMalloc(&h->p2p_sync, P2P_WORDS * sizeof(unsigned long long)));
+  CK(cudaMemset(h->p2p_sync, 0, P2P_WORDS * sizeof(unsigned long long)));
+  CK(cudaMalloc(&h->p2p_stage, stage_bytes));
+  CK(cudaMemset(h->p2p_stage, 0, stage_bytes));
+  CK(cudaHostAlloc(&h->p2p_err_host, sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable));
+  *h->p2p_err_host = 0;
+  CK(cudaHostGetDevicePointer((void**)&h->p2p_err_dev, h->p2p_err_host, 0));
+  return PAMG_OK;
+}
+
+// collective over all ranks (one process per GPU; called at the first exchange, never during stream capture): allocate
+// the staging buffer, exchange its CUDA IPC handle, map the peers' buffers, agree on the outcome.  A local failure is
+// folded into the agreement (ok = 0 everywhere -> NCCL send/recv path) instead of leaving the other ranks in a collective.
 int p2p_setup(pamg_handle* h) {
   const int R = h->nranks;
   int ok = 1;
   if ((int)h->plan.peers.size() > P2P_MAXP) ok = 0;
   for (const auto& pp : h->p2p_peers) if (pp.slot_at_peer < 0) ok = 0;
-  long long strips = 0;
-  for (const auto& pr : h->plan.peers) strips = std::max(strips, (long long)pr.strip_begin + pr.nfaces);
-  h->p2p_stage_words = strips * 3 * h->lev[0].S;
-  const size_t stage_bytes = (size_t)std::max(1ll, 2 * h->p2p_stage_words) * sizeof(uint4);
-  if (cudaMalloc(&h->p2p_sync, P2P_WORDS * sizeof(unsigned long long)) != cudaSuccess) { h->p2p_sync = nullptr; ok = 0; }
-  else CK(cudaMemset(h->p2p_sync, 0, P2P_WORDS * sizeof(unsigned long long)));
-  if (cudaMalloc(&h->p2p_stage, stage_bytes) != cudaSuccess) { h->p2p_stage = nullptr; ok = 0; }
-  else CK(cudaMemset(h->p2p_stage, 0, stage_bytes));
+  if (p2p_alloc_local(h) != PAMG_OK) { ok = 0; (void)cudaGetLastError(); }
   cudaIpcMemHandle_t mine;
   std::memset(&mine, 0, sizeof(mine));
-  if (ok && cudaIpcGetMemHandle(&mine, h->p2p_stage) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+  if (ok && cudaIpcGetMemHandle(&mine, h->p2p_stage) != cudaSuccess) { ok = 0; (void)cudaGetLastError(); }
   // all-gather of the handles with grouped send / recv (R <= 8)
   const size_t hb = sizeof(cudaIpcMemHandle_t);
   std::vector<cudaIpcMemHandle_t> all(R);
-  unsigned char *d_mine = nullptr, *d_all = nullptr;
-  int* d_ok = nullptr;
-  CK(cudaMalloc(&d_mine, hb)); CK(cudaMalloc(&d_all, hb * R)); CK(cudaMalloc(&d_ok, sizeof(int)));
-  CK(cudaMemcpy(d_mine, &mine, hb, cudaMemcpyHostToDevice));
+  unsigned char* d_buf = nullptr;      // [mine][all R][ok]
+  const bool have_buf = cudaMalloc(&d_buf, hb * (R + 1) + sizeof(int)) == cudaSuccess;
+  int rc = PAMG_OK;
+  if (!have_buf) {
+    // without device memory this rank cannot even take part in the agreement
+    return fail(h, PAMG_ERR_CUDA, "cudaMalloc failed in the halo-exchange set-up");
+  }
+  unsigned char* d_mine = d_buf; unsigned char* d_all = d_buf + hb; int* d_ok = (int*)(d_buf + hb * (R + 1));
+  if (cudaMemcpy(d_mine, &mine, hb, cudaMemcpyHostToDevice) != cudaSuccess) ok = 0;
   g_nccl.GroupStart();
   for (int r = 0; r < R; ++r) {
     g_nccl.Send(d_mine, hb, ncclUint8, r, h->comm, h->stream);
     g_nccl.Recv(d_all + hb * r, hb, ncclUint8, r, h->comm, h->stream);
   }
-  if (g_nccl.GroupEnd() != ncclSuccess) return fail(h, PAMG_ERR_CUDA, "handle exchange failed");
-  CK(cudaStreamSynchronize(h->stream));
-  CK(cudaMemcpy(all.data(), d_all, hb * R, cudaMemcpyDeviceToHost));
-  if (ok) {
+  if (g_nccl.GroupEnd() != ncclSuccess) rc = fail(h, PAMG_ERR_CUDA, "handle exchange failed");
+  if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) ok = 0;
+  if (!rc && cudaMemcpy(all.data(), d_all, hb * R, cudaMemcpyDeviceToHost) != cudaSuccess) ok = 0;
+  if (!rc && ok) {
     for (size_t i = 0; i < h->plan.peers.size(); ++i) {
       void* ptr = nullptr;
-      if (cudaIpcOpenMemHandle(&ptr, all[h->plan.peers[i].part], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+      if (cudaIpcOpenMemHandle(&ptr, all[h->plan.peers[i].part], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; (void)cudaGetLastError(); break; }
       h->p2p_opened.push_back(ptr);
       h->p2p_peers[i].stage = (uint4*)ptr;
     }
   }
   // every rank must take the same path
-  CK(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
-  if (g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, h->comm, h->stream) != ncclSuccess) return fail(h, PAMG_ERR_CUDA, "ncclAllReduce failed");
-  CK(cudaStreamSynchronize(h->stream));
-  CK(cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
-  cudaFree(d_mine); cudaFree(d_all); cudaFree(d_ok);
+  if (!rc) {
+    if (cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) ok = 0;
+    if (g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, h->comm, h->stream) != ncclSuccess) rc = fail(h, PAMG_ERR_CUDA, "ncclAllReduce failed");
+    else if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = fail(h, PAMG_ERR_CUDA, "halo-exchange set-up: reading the agreement failed");
+  }
+  cudaFree(d_buf);
+  if (rc) return rc;
   if (ok) h->p2p_ready = true; else h->p2p_failed = true;
   return PAMG_OK;
 }
@@ -345,7 +399,7 @@ int p2p_args(pamg_handle* h, LevelDev& L, double* ovl, P2PArgs& a) {
   const int base = h->plan.peers[0].send_begin;
   a.send = ovl + ((size_t)h->plan.nstrips + base) * S3;
   a.strips = ovl; a.stage = h->p2p_stage; a.stage_words = h->p2p_stage_words;
-  a.sync = h->p2p_sync; a.npeers = (int)h->plan.peers.size(); a.timeout_ns = h->p2p_timeout_ns;
+  a.sync = h->p2p_sync; a.err = h->p2p_err_dev; a.npeers = (int)h->plan.peers.size(); a.timeout_ns = h->p2p_timeout_ns;
   long long so = 0, ro = 0;
   for (int i = 0; i < a.npeers; ++i) {
     const auto& pr = h->plan.peers[i];
@@ -360,29 +414,10 @@ int p2p_args(pamg_handle* h, LevelDev& L, double* ovl, P2PArgs& a) {
   return PAMG_OK;
 }
 
-int p2p_exchange(pamg_handle* h, LevelDev& L, double* ovl) {
-  P2PArgs a;
-  int rc = p2p_args(h, L, ovl, a);
-  if (rc) return rc;
-  const long long so = a.soff[a.npeers];
-  static const int maxgrid = getenv("PAMG_P2P_GRID") ? std::max(1, atoi(getenv("PAMG_P2P_GRID"))) : 32;
-  const int grid = (int)std::max(1ll, std::min((so + 2 * TPB - 1) / (2 * TPB), (long long)maxgrid));
-  k_p2p_exchange<<<grid, TPB, 0, h->stream>>>(a);
-  h->launches++;
-  CK(cudaGetLastError());
-  return PAMG_OK;
-}
-
-// exchange of the cut-face strips (one process per GPU): the send slots follow the local strips in the
-// strip space; the receive range of a peer is a contiguous range of my own strips (pamg_plan.cpp)
-int exchange_halo(pamg_handle* h, LevelDev& L, double* ovl) {
-  if (h->plan.peers.empty()) return PAMG_OK;
+// library exchange of the cut-face strips (one process per GPU, when peer memory is not available): the send slots
+// follow the local strips in the strip space; the receive range of a peer is a contiguous range of my own strips
+int exchange_halo_nccl(pamg_handle* h, LevelDev& L, double* ovl) {
   if (!h->comm) return fail(h, PAMG_ERR_STATE, "partitioned mesh but pamg_comm_init was not called");
-  if (h->p2p_enabled && !h->p2p_ready && !h->p2p_failed && !h->capturing && h->level_offset == 0) {
-    int rc = p2p_setup(h);
-    if (rc) return rc;
-  }
-  if (h->p2p_ready) return p2p_exchange(h, L, ovl);
   const size_t S3 = (size_t)3 * L.S;
   g_nccl.GroupStart();
   for (const auto& pr : h->plan.peers) {
@@ -395,9 +430,8 @@ int exchange_halo(pamg_handle* h, LevelDev& L, double* ovl) {
 }
 
 // what: 0 = update_overlaps as written (every face, tnew and told strips); 1 = Dirichlet faces only (static data,
-// written once per level into both strip buffers); 3 = every face between parents.  The sweeps themselves refresh
-// the strips of the next sweep (strips_write in the kernels), so this kernel only runs when the field was changed
-// by something else than a sweep (upload, fill, prolongation) or through the pamg_update_overlaps entry.
+// written once per level); 2 = faces cut by the GPU partition only (the exchange step of a sweep that reads its local
+// neighbours straight from the field); 3 = every face between parents.
 int launch_halo(pamg_handle* h, int level, int what) {
   LevelDev& L = h->lev[level - 1];
   HaloArgs a;
@@ -405,39 +439,39 @@ int launch_halo(pamg_handle* h, int level, int what) {
   a.dst_strip = h->dst_strip; a.rev = h->rev; a.strip_of = h->strip_of;
   a.bc_scale = (h->p.coarse_bc_zero && level + h->level_offset > 1) ? 0.0 : 1.0;
   a.U = h->U; a.s = L.s; a.with_old = (what == 0) ? 1 : 0; a.what = what; a.nstrips = h->plan.nstrips;
-  const long long n = (long long)h->U * 3 * L.S;
-  a.x.npeers = 0;
+  a.cut_lf = h->cut_lf; a.ncut = (int)h->plan.cut_lf.size();
+  a.bc_kind = h->bc_kind; a.bc_val = h->bc_val;
   const bool cut = what != 1 && !h->plan.peers.empty();
+  if (what == 2 && !cut) { L.cut_valid = true; return PAMG_OK; }
+  const long long n = (what == 2 ? (long long)a.ncut : (long long)h->U * 3) * L.S;
+  a.x.npeers = 0;
   if (cut && h->comm && h->p2p_enabled && !h->p2p_ready && !h->p2p_failed && !h->capturing && h->level_offset == 0) {
     int rc = p2p_setup(h);      // collective, first exchange only
     if (rc) return rc;
   }
-  const bool fused_x = cut && h->p2p_ready && h->p2p_fuse;
+  const bool fused_x = cut && h->p2p_ready;
   if (fused_x) { int rc = p2p_args(h, L, L.ovlb[L.ovl_cur], a.x); if (rc) return rc; }
   // with the exchange fused in, blocks poll for remote data after their own work: keep the grid within one wave
   int hgrid = grid_for(h, n);
-  if (fused_x) {
-    static int halo_resident = 0;
-    if (halo_resident == 0) {
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&halo_resident, k_halo, TPB, 0));
-      if (halo_resident < 1) halo_resident = 1;
-    }
-    hgrid = std::min(hgrid, h->nsm * std::min(halo_resident, 4));
-  }
+  if (fused_x) hgrid = std::min(hgrid, h->nsm * std::min(std::max(h->kc.halo, 1), 4));
   k_halo<<<hgrid, TPB, 0, h->stream>>>(a);
   h->launches++;
   CK(cudaGetLastError());
   if (what == 1) return PAMG_OK;
-  L.strips_valid = true;
-  if (fused_x) return PAMG_OK;
-  return exchange_halo(h, L, L.ovlb[L.ovl_cur]);
+  if (cut && !fused_x) { int rc = exchange_halo_nccl(h, L, L.ovlb[L.ovl_cur]); if (rc) return rc; }
+  L.cut_valid = true;
+  if (what != 2) L.strips_valid = true;
+  return PAMG_OK;
 }
 
-// strips of the current iterate, refreshed only if something other than a sweep touched the field
-int ensure_strips(pamg_handle* h, int level) {
+// halo data of the current iterate, refreshed only if something touched the field since: `all` = the strips of every
+// face between parents (in-place sweeps and the kernels that do not read their neighbours' field), otherwise only the
+// strips of the faces cut by the GPU partition
+int ensure_strips(pamg_handle* h, int level, bool all = true) {
   LevelDev& L = h->lev[level - 1];
-  if (L.strips_valid || !h->p.face_terms) return PAMG_OK;
-  return launch_halo(h, level, 3);
+  if (!h->p.face_terms) return PAMG_OK;
+  if (all || !h->direct_halo) return L.strips_valid ? PAMG_OK : launch_halo(h, level, 3);
+  return L.cut_valid ? PAMG_OK : launch_halo(h, level, 2);
 }
 
 int launch_build_rhs(pamg_handle* h) {
@@ -452,86 +486,80 @@ int launch_build_rhs(pamg_handle* h) {
   return PAMG_OK;
 }
 
+// opt-in shared memory and resident CTAs per SM of every shared-memory kernel, once per handle (the attribute is per
+// device and must not be set during stream capture)
+template <typename K>
+int configure_one(pamg_handle* h, K kern, int threads, size_t smem, int& resident) {
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, threads, smem));
+  if (resident < 1) resident = 1;
+  return PAMG_OK;
+}
+template <bool FACE>
+int configure_face(pamg_handle* h) {
+  int rc, dummy = 0;
+  const int f = FACE ? 1 : 0;
+  if ((rc = configure_one(h, k_element_win2<MODE_JACOBI, FACE>, WIN2_THREADS, WIN_SMEM_BYTES, h->kc.win2[f]))) return rc;
+  if ((rc = configure_one(h, k_element_win2<MODE_RESID, FACE>, WIN2_THREADS, WIN_SMEM_BYTES, dummy))) return rc;
+  if ((rc = configure_one(h, k_element_win2<MODE_RICH, FACE>, WIN2_THREADS, WIN_SMEM_BYTES, dummy))) return rc;
+  if ((rc = configure_one(h, k_element_win<MODE_JACOBI, FACE>, TPB, WIN_SMEM_BYTES, h->kc.win[f]))) return rc;
+  if ((rc = configure_one(h, k_element_win<MODE_RESID, FACE>, TPB, WIN_SMEM_BYTES, dummy))) return rc;
+  if ((rc = configure_one(h, k_element_win<MODE_RICH, FACE>, TPB, WIN_SMEM_BYTES, dummy))) return rc;
+  if ((rc = configure_one(h, k_element_win<MODE_GS, FACE>, TPB, WIN_SMEM_BYTES, dummy))) return rc;
+  if ((rc = configure_one(h, k_element_tma<MODE_JACOBI, FACE>, TPB, TMA_SMEM_BYTES, h->kc.tma[f]))) return rc;
+  if ((rc = configure_one(h, k_element_tma<MODE_RESID, FACE>, TPB, TMA_SMEM_BYTES, dummy))) return rc;
+  if ((rc = configure_one(h, k_element_tma<MODE_RICH, FACE>, TPB, TMA_SMEM_BYTES, dummy))) return rc;
+  if ((rc = configure_one(h, k_element_tma<MODE_GS, FACE>, TPB, TMA_SMEM_BYTES, dummy))) return rc;
+  return PAMG_OK;
+}
+int configure_kernels(pamg_handle* h) {
+  if (h->kc.done) return PAMG_OK;
+  int rc;
+  if ((rc = configure_face<true>(h))) return rc;
+  if ((rc = configure_face<false>(h))) return rc;
+  if ((rc = configure_one(h, k_gs_win2, WIN2_THREADS, GSW_SMEM_BYTES, h->kc.gs2))) return rc;
+  if ((rc = configure_one(h, k_gs_win, TPB, GSW_SMEM_BYTES, h->kc.gs))) return rc;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->kc.halo, k_halo, TPB, 0));
+  if (h->kc.halo < 1) h->kc.halo = 1;
+  h->kc.done = true;
+  return PAMG_OK;
+}
+
 template <int MODE>
-int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout, int colour, int grid, bool write_strips = false) {
+int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout, int colour, int grid) {
   ElemArgs a;
   a.Tin = Tin; a.Tout = Tout; a.rhs = L.rhs; a.ovl = L.ovlb[L.ovl_cur]; a.pc = L.pc; a.strip_of = h->strip_of; a.hmap = h->hmap;
-  a.ovl_next = (write_strips && h->p.face_terms) ? L.ovlb[L.ovl_cur ^ 1] : nullptr; a.dst_strip = h->dst_strip; a.rev = h->rev;
+  // an in-place pass (the two-pass coloured GS) must see start-of-sweep values across parent faces: strips only
+  a.nsrc = (h->direct_halo && Tin != Tout) ? h->nsrc : nullptr;
   a.partial = h->partial; a.omega = h->p.omega; a.rsign = (double)h->p.residual_sign; a.nelem = L.nelem; a.s = L.s;
-  a.colour = colour;
-  a.split_boundary = 0; a.partial_off = 0;
+  a.colour = colour; a.partial_off = 0;
+  const int f = h->p.face_terms ? 1 : 0;
   const bool prof = h->profiling && h->pev_used + 2 <= (int)h->pev.size();
   if (prof) CK(cudaEventRecord(h->pev[h->pev_used], h->stream));
-  if (MODE != MODE_GS && h->kernel_mode == 2 && L.nitems > 0) {
-    // row-streaming kernel: TMA-prefetched ring of row segments, all neighbours from shared memory
-    StreamArgs sa;
-    sa.e = a; sa.items = L.items; sa.nitems = L.nitems; sa.counters = h->counters;
-    const int sgrid = std::min(L.nitems, std::min(grid, h->nsm * 5));
-    if (h->p.face_terms) k_stream<MODE, true><<<sgrid, SW, 0, h->stream>>>(sa);
-    else k_stream<MODE, false><<<sgrid, SW, 0, h->stream>>>(sa);
-    if (MODE == MODE_RESID) h->last_partials = sgrid;
-  } else if (MODE != MODE_GS && h->kernel_mode == 4 && h->win_producer && L.s >= 6 && L.s <= 8) {
+  if (MODE != MODE_GS && h->kernel_mode == 4 && h->win_producer && L.s >= 6 && L.s <= 8) {
     // window kernel with a producer warp (no CTA-wide barrier between tiles)
     auto kern = h->p.face_terms ? k_element_win2<MODE, true> : k_element_win2<MODE, false>;
-    static int resident_win2[2] = {0, 0};
-    int& resident = resident_win2[h->p.face_terms ? 1 : 0];
-    if (resident == 0) {
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM_BYTES));
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, WIN2_THREADS, WIN_SMEM_BYTES));
-      if (resident < 1) resident = 1;
-    }
-    const int tgrid = (int)std::max(1ll, std::min(L.nelem / TPB, (long long)h->nsm * resident));
+    const int tgrid = (int)std::max(1ll, std::min(L.nelem / TPB, (long long)h->nsm * h->kc.win2[f]));
     kern<<<tgrid, WIN2_THREADS, WIN_SMEM_BYTES, h->stream>>>(a);
     if (MODE == MODE_RESID) h->last_partials = tgrid;
   } else if ((MODE != MODE_GS || h->gs_tma) && h->kernel_mode == 4 && L.C >= TPB && L.s <= 8) {
     // (a vertical neighbour is up to 2^(s+1) children away: the 8-tile ring covers s <= 8)
     // window kernel: ring of 8 field tiles in shared memory, every neighbour value read from it
     auto kern = h->p.face_terms ? k_element_win<MODE, true> : k_element_win<MODE, false>;
-    static int resident_win[2] = {0, 0};
-    int& resident = resident_win[h->p.face_terms ? 1 : 0];
-    if (resident == 0) {
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM_BYTES));
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, TPB, WIN_SMEM_BYTES));
-      if (resident < 1) resident = 1;
-    }
-    const int tgrid = (int)std::max(1ll, std::min(L.nelem / TPB, (long long)h->nsm * resident));
+    const int tgrid = (int)std::max(1ll, std::min(L.nelem / TPB, (long long)h->nsm * h->kc.win[f]));
     kern<<<tgrid, TPB, WIN_SMEM_BYTES, h->stream>>>(a);
     if (MODE == MODE_RESID) h->last_partials = tgrid;
-  } else if ((MODE != MODE_GS || h->gs_tma) && (h->kernel_mode == 1 || h->kernel_mode == 2 || h->kernel_mode == 4) && L.C >= TPB) {
-    // 1-D TMA tiles: contiguous 6 KB spans through shared memory (pamg_kernels.cuh)
-    // contiguous tile ranges per CTA: exactly one wave of resident CTAs (occupancy from the runtime)
+  } else if ((MODE != MODE_GS || h->gs_tma) && (h->kernel_mode == 1 || h->kernel_mode == 4) && L.C >= TPB) {
+    // 1-D TMA tiles: contiguous 6 KB spans through shared memory; contiguous tile ranges per CTA, one wave of resident CTAs
     auto kern = h->p.face_terms ? k_element_tma<MODE, true> : k_element_tma<MODE, false>;
-    static int resident_by_face[2] = {0, 0};   // per instantiation
-    int& resident = resident_by_face[h->p.face_terms ? 1 : 0];
-    if (resident == 0) {
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_BYTES));
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, TPB, TMA_SMEM_BYTES));
-      if (resident < 1) resident = 1;
-    }
-    const int tgrid = (int)std::max(1ll, std::min((L.nelem + TPB - 1) / TPB, (long long)h->nsm * resident));
-    const bool split = h->split_boundary && h->p.face_terms;
-    a.split_boundary = split ? 1 : 0;
+    const int tgrid = (int)std::max(1ll, std::min((L.nelem + TPB - 1) / TPB, (long long)h->nsm * h->kc.tma[f]));
     kern<<<tgrid, TPB, TMA_SMEM_BYTES, h->stream>>>(a);
-    int fgrid = 0;
-    if (split && !(MODE == MODE_GS && colour == 0)) {     // every child on a parent face is an "up" child
-      // children on parent faces: separate small launch (their halo look-ups would stall whole tiles)
-      h->launches++;
-      CK(cudaGetLastError());
-      ElemArgs f = a;
-      f.split_boundary = 0; f.partial_off = tgrid;
-      fgrid = grid_for(h, (long long)h->U * 3 * L.S);
-      k_boundary_fix<MODE><<<fgrid, TPB, 0, h->stream>>>(f, h->U);
-    }
-    if (MODE == MODE_RESID) h->last_partials = tgrid + fgrid;
-  } else if (h->kernel_mode != 0) {
-    // branch-free direct kernel (all loads of a child in flight at once); also the coloured GS pass
+    if (MODE == MODE_RESID) h->last_partials = tgrid;
+  } else {
+    // branch-free direct kernel (all loads of a child in flight at once): levels with fewer than 256 children per parent
     if (MODE == MODE_RESID) h->last_partials = grid;
     if (h->p.face_terms) k_element_direct2<MODE, true><<<grid, TPB, 0, h->stream>>>(a);
     else k_element_direct2<MODE, false><<<grid, TPB, 0, h->stream>>>(a);
-  } else {
-    if (MODE == MODE_RESID) h->last_partials = grid;
-    if (h->p.face_terms) k_element<MODE, true><<<grid, TPB, 0, h->stream>>>(a);
-    else k_element<MODE, false><<<grid, TPB, 0, h->stream>>>(a);
   }
   if (prof) { CK(cudaEventRecord(h->pev[h->pev_used + 1], h->stream)); h->pev_used += 2; }
   h->launches++;
@@ -539,7 +567,7 @@ int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout,
   return PAMG_OK;
 }
 
-// coloured Gauss-Seidel sweep in one pass (k_gs_win), out of place
+// coloured Gauss-Seidel sweep in one pass (k_gs_win / k_gs_win2), out of place
 bool gs_fused_ok(const pamg_handle* h, const LevelDev& L) {
   return h->gs_fused && h->kernel_mode == 4 && h->p.face_terms && L.C >= TPB && L.s <= 8;
 }
@@ -547,22 +575,11 @@ bool gs_fused_ok(const pamg_handle* h, const LevelDev& L) {
 int launch_gs_fused(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout) {
   ElemArgs a;
   a.Tin = Tin; a.Tout = Tout; a.rhs = L.rhs; a.ovl = L.ovlb[L.ovl_cur]; a.pc = L.pc; a.strip_of = h->strip_of; a.hmap = h->hmap;
-  a.ovl_next = nullptr; a.dst_strip = h->dst_strip; a.rev = h->rev;
+  a.nsrc = h->direct_halo ? h->nsrc : nullptr;
   a.partial = h->partial; a.omega = h->p.omega; a.rsign = (double)h->p.residual_sign; a.nelem = L.nelem; a.s = L.s;
-  a.colour = 1; a.split_boundary = 0; a.partial_off = 0;
+  a.colour = 1; a.partial_off = 0;
   const bool producer = h->win_producer && L.s >= 6;
-  static int resident2[2] = {0, 0};
-  int& resident = resident2[producer ? 1 : 0];
-  if (resident == 0) {
-    if (producer) {
-      CK(cudaFuncSetAttribute(k_gs_win2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GSW_SMEM_BYTES));
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_gs_win2, WIN2_THREADS, GSW_SMEM_BYTES));
-    } else {
-      CK(cudaFuncSetAttribute(k_gs_win, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GSW_SMEM_BYTES));
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_gs_win, TPB, GSW_SMEM_BYTES));
-    }
-    if (resident < 1) resident = 1;
-  }
+  const int resident = producer ? h->kc.gs2 : h->kc.gs;
   const bool prof = h->profiling && h->pev_used + 2 <= (int)h->pev.size();
   if (prof) CK(cudaEventRecord(h->pev[h->pev_used], h->stream));
   const int tgrid = (int)std::max(1ll, std::min(L.nelem / TPB, (long long)h->nsm * resident));
@@ -578,58 +595,51 @@ int do_smooth(pamg_handle* h, int level, int solver, int nsweeps) {
   LevelDev& L = h->lev[level - 1];
   if (level == 1 && !L.rhs_valid) { int rc = launch_build_rhs(h); if (rc) return rc; }
   const int grid = grid_for(h, L.nelem);
-  // optional (PAMG_FUSED_HALO=1): the default kernel families write the next sweep's strips themselves; otherwise
-  // one k_halo launch per sweep refreshes the strips of the faces between parents (Dirichlet strips are static)
-  const bool fused = h->fused_halo && (h->kernel_mode == 1 || h->kernel_mode == 3);
+  if (solver < 1 || solver > 4) return fail(h, PAMG_ERR_ARG, "solver must be 1 (Jacobi), 2 (Richardson) or 3 (Gauss-Seidel)");
   for (int sw = 0; sw < nsweeps; ++sw) {
-    // tnew <- tnew_nonlin (:550) is the buffer swap below for Jacobi; halo from it (:555)
+    // tnew <- tnew_nonlin (:550) is the buffer swap below; halo from it (:555).  Out-of-place sweeps read the exterior
+    // values of faces between local parents straight from tnew (the values update_overlaps would copy), so only faces
+    // cut by the GPU partition need their strips refreshed; an in-place sweep needs every strip.
     L.tnew_alias = true;
-    if (!fused) L.strips_valid = false;
-    int rc = ensure_strips(h, level);
+    const bool in_place = (solver == 3 || solver == 4) && !gs_fused_ok(h, L);
+    int rc = ensure_strips(h, level, in_place);
     if (rc) return rc;
     if (solver == 1 || solver == 2) {
-      rc = (solver == 1) ? launch_element<MODE_JACOBI>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid, fused)
-                         : launch_element<MODE_RICH>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid, fused);
+      rc = (solver == 1) ? launch_element<MODE_JACOBI>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid)
+                         : launch_element<MODE_RICH>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid);
       if (rc) return rc;
       L.cur ^= 1;
       L.tnew_alias = false;  // the old buffer now holds the start-of-sweep field = tracer%tnew
-    } else if (solver == 3 || solver == 4) {
-      // two-colour ordering of the reference's Gauss-Seidel sweep: all down children, then all up children;
-      // values across parent faces stay lagged through the halo strips exactly as at :647-655.
-      if (gs_fused_ok(h, L)) {
-        // both colours in one pass over memory, written to the other buffer (which then holds tracer%tnew, as for Jacobi)
-        rc = launch_gs_fused(h, L, L.T[L.cur], L.T[L.cur ^ 1]);
-        if (rc) return rc;
-        L.cur ^= 1;
-        L.tnew_alias = false;
-      } else {
-        if (sw == nsweeps - 1 && h->p.keep_tnew_gs) { rc = materialise_tnew(h, L); if (rc) return rc; }  // keep tracer%tnew observable
-        rc = launch_element<MODE_GS>(h, L, L.T[L.cur], L.T[L.cur], 0, grid, false);
-        if (rc) return rc;
-        rc = launch_element<MODE_GS>(h, L, L.T[L.cur], L.T[L.cur], 1, grid, fused);   // all children on parent faces are "up"
-        if (rc) return rc;
-      }
-    } else {
-      return fail(h, PAMG_ERR_ARG, "solver must be 1 (Jacobi), 2 (Richardson) or 3 (Gauss-Seidel)");
-    }
-    if (fused && h->p.face_terms) {
-      L.ovl_cur ^= 1;                 // the sweep wrote the strips of the new iterate (incl. the send slots)
-      rc = exchange_halo(h, L, L.ovlb[L.ovl_cur]);
+    } else if (!in_place) {
+      // two-colour ordering of the reference's Gauss-Seidel sweep (all down children, then all up children; values across
+      // parent faces stay lagged exactly as at :647-655), both colours in one pass over memory, written to the other
+      // buffer (which then holds tracer%tnew, as for Jacobi)
+      rc = launch_gs_fused(h, L, L.T[L.cur], L.T[L.cur ^ 1]);
       if (rc) return rc;
-      L.strips_valid = true;
+      L.cur ^= 1;
+      L.tnew_alias = false;
     } else {
-      L.strips_valid = false;
+      if (sw == nsweeps - 1 && h->p.keep_tnew_gs) { rc = materialise_tnew(h, L); if (rc) return rc; }  // keep tracer%tnew observable
+      rc = launch_element<MODE_GS>(h, L, L.T[L.cur], L.T[L.cur], 0, grid);
+      if (rc) return rc;
+      rc = launch_element<MODE_GS>(h, L, L.T[L.cur], L.T[L.cur], 1, grid);   // all children on parent faces are "up"
+      if (rc) return rc;
     }
+    L.strips_valid = false; L.cut_valid = false;
   }
   return PAMG_OK;
 }
 
-int do_residual(pamg_handle* h, int level, double* l2, double* linf, double* smax) {
+int do_residual(pamg_handle* h, int level, double* l2, double* linf, double* smax, bool queue_only = false) {
   LevelDev& L = h->lev[level - 1];
   if (level == 1 && !L.rhs_valid) { int rc = launch_build_rhs(h); if (rc) return rc; }
   const int grid = grid_for(h, L.nelem);
   if (2 * grid > h->npartial) return fail(h, PAMG_ERR_STATE, "partial buffer too small");
-  int rc = launch_element<MODE_RESID>(h, L, tnew_ptr(L), L.res, 0, grid);
+  // exterior values of faces between local parents come straight from TNEW (what update_overlaps copies); the strips of
+  // faces cut by the GPU partition are refreshed here if something touched the field since the last exchange
+  int rc = ensure_strips(h, level, false);
+  if (rc) return rc;
+  rc = launch_element<MODE_RESID>(h, L, tnew_ptr(L), L.res, 0, grid);
   if (rc) return rc;
   if (l2 || linf || smax) {
     k_reduce_partials<<<1, 1024, 0, h->stream>>>(h->partial, h->last_partials, h->out3);
@@ -643,8 +653,9 @@ int do_residual(pamg_handle* h, int level, double* l2, double* linf, double* sma
       if (g_nccl.GroupEnd() != ncclSuccess) return fail(h, PAMG_ERR_CUDA, "ncclAllReduce failed");
     }
     CK(cudaMemcpyAsync(h->out3_host, h->out3, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (h->capturing) return PAMG_OK;      // the caller synchronises after the graph launch
+    if (queue_only || h->capturing) return PAMG_OK;      // the caller synchronises (after the graph launch / for the whole group)
     CK(cudaStreamSynchronize(h->stream));
+    if ((rc = p2p_check(h))) return rc;
     if (l2) *l2 = std::sqrt(h->out3_host[0]);
     if (linf) *linf = h->out3_host[1];
     if (smax) *smax = h->out3_host[2];
@@ -685,7 +696,7 @@ int do_prolong(pamg_handle* h, int fine_level, bool keep_tnew = true) {
       F.tnew_alias = true;            // inside the V-cycle nothing reads the pre-correction field
     }
     a.src = Cc.T[Cc.cur]; a.dst = F.T[F.cur];
-    F.strips_valid = false;           // the iterate changes outside a sweep
+    F.strips_valid = false; F.cut_valid = false;           // the iterate changes outside a sweep
     k_prolong_p1<<<grid_for(h, F.nelem), TPB, 0, h->stream>>>(a);
   }
   h->launches++;
@@ -701,48 +712,139 @@ int do_fill(pamg_handle* h, double* p, long long n, double v) {
   return PAMG_OK;
 }
 
-int vcycle_rec(pamg_handle* h, int level, int solver, int nu1, int nu2, int ncoarse);
+// ---- groups -------------------------------------------------------------------------------------------------------
+// Everything from here on works on a GROUP of handles that advance in lockstep: a plain handle is a group of one (its
+// peers, if any, live in other processes and meet it inside the exchange kernels / NCCL calls); the root of a
+// single-process multi-GPU handle (pamg_create_multi) is the group of its parts.  The host thread queues each step for
+// every part before it moves on, never blocks in between, and all cross-GPU ordering happens on the devices (flagged
+// NVLink stores polled by the receiving kernel), so part 0's stream may run ahead of the others without deadlock.
+typedef std::vector<pamg_handle*> Group;
+Group group_of(pamg_handle* h) { return h->parts.empty() ? Group{h} : h->parts; }
+int gfail(pamg_handle* owner, pamg_handle* q, int rc) { if (owner != q) owner->err = q->err; return rc; }
+#define GALL(G, owner, q, expr)                                            \
+  do {                                                                     \
+    for (pamg_handle* q : G) {                                             \
+      if (q->in_group) cudaSetDevice(q->device);                           \
+      int rc_ = (expr);                                                    \
+      if (rc_) return gfail(owner, q, rc_);                                \
+    }                                                                      \
+  } while (0)
+
+int vcycle_rec(const Group& G, pamg_handle* owner, int level, int solver, int nu1, int nu2, int ncoarse);
+
+int launch_push(pamg_handle* q, const double* src, double* dst, long long n, int channel, unsigned long long* peer_flag) {
+  PushArgs a;
+  a.src = src; a.dst = dst; a.n = n; a.counter = q->agg_words + AGG_COUNTER; a.epoch = q->agg_words + AGG_EPOCH + channel;
+  a.flag = peer_flag;
+  const int grid = (int)std::max(1ll, std::min((n + TPB - 1) / TPB, (long long)q->nsm * 2));
+  k_push<<<grid, TPB, 0, q->stream>>>(a);
+  q->launches++;
+  CK_(q, cudaGetLastError());
+  return PAMG_OK;
+}
+
+int launch_wait(pamg_handle* q, unsigned senders) {
+  WaitArgs a;
+  a.flags = q->agg_words + AGG_FLAGS; a.expect = q->agg_words + AGG_EXPECT; a.err = q->p2p_err_dev;
+  a.timeout_ns = q->p2p_timeout_ns; a.senders = senders;
+  k_wait_flags<<<1, 32, 0, q->stream>>>(a);
+  q->launches++;
+  CK_(q, cudaGetLastError());
+  return PAMG_OK;
+}
 
 // Coarse-level agglomeration: below agg_level every kernel is launch-latency bound and every sweep
-// would pay an NCCL exchange, so the restricted right-hand side of all parts is gathered on part 0, the remaining
+// would pay an exchange, so the restricted right-hand side of all parts is gathered on part 0, the remaining
 // levels of the V-cycle run there on the whole mesh (no exchange at all), and the correction is scattered back.
-int agg_coarse_solve(pamg_handle* h, int solver, int nu1, int nu2, int ncoarse) {
-  LevelDev& Lc = h->lev[h->agg_level - 1];
-  const size_t per_parent = (size_t)3 * Lc.C;
-  if (!h->comm) return fail(h, PAMG_ERR_STATE, "agglomeration needs pamg_comm_init");
-  g_nccl.GroupStart();
-  if (h->rank == 0) {
-    LevelDev& A = h->agg->lev[0];
-    for (int p = 1; p < h->nranks; ++p)
-      g_nccl.Recv(A.rhs + per_parent * h->part_first[p], per_parent * (h->part_first[p + 1] - h->part_first[p]), ncclFloat64, p,
-                  h->comm, h->stream);
-  } else {
-    g_nccl.Send(Lc.rhs, per_parent * h->U, ncclFloat64, 0, h->comm, h->stream);
+int agg_coarse_solve(const Group& G, pamg_handle* owner, int solver, int nu1, int nu2, int ncoarse) {
+  pamg_handle* h0 = G[0];
+  const int lvl = h0->agg_level;
+  const size_t per_parent = (size_t)3 * h0->lev[lvl - 1].C;
+  if (G.size() == 1) {
+    // one process per GPU: gather / scatter with grouped ncclSend / ncclRecv
+    pamg_handle* h = h0;
+    LevelDev& Lc = h->lev[lvl - 1];
+    if (!h->comm) return fail(h, PAMG_ERR_STATE, "agglomeration needs pamg_comm_init");
+    g_nccl.GroupStart();
+    if (h->rank == 0) {
+      LevelDev& A = h->agg->lev[0];
+      for (int p = 1; p < h->nranks; ++p)
+        g_nccl.Recv(A.rhs + per_parent * h->part_first[p], per_parent * (h->part_first[p + 1] - h->part_first[p]), ncclFloat64, p,
+                    h->comm, h->stream);
+    } else {
+      g_nccl.Send(Lc.rhs, per_parent * h->U, ncclFloat64, 0, h->comm, h->stream);
+    }
+    if (g_nccl.GroupEnd() != ncclSuccess) return fail(h, PAMG_ERR_CUDA, "ncclGroupEnd failed in coarse gather");
+    if (h->rank == 0) {
+      pamg_handle* g = h->agg;
+      LevelDev& A = g->lev[0];
+      CK(cudaMemcpyAsync(A.rhs, Lc.rhs, per_parent * h->U * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      CK(cudaMemsetAsync(A.T[A.cur], 0, A.ndof * sizeof(double), h->stream));
+      A.tnew_alias = true; A.strips_valid = false; A.cut_valid = false; A.rhs_valid = true;
+      const long long l0 = g->launches;
+      int rc = vcycle_rec(Group{g}, g, 1, solver, nu1, nu2, ncoarse);
+      h->launches += g->launches - l0;
+      if (rc) return fail(h, rc, g->err);
+      CK(cudaMemcpyAsync(Lc.T[Lc.cur], A.T[A.cur], per_parent * h->U * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    g_nccl.GroupStart();
+    if (h->rank == 0) {
+      LevelDev& A = h->agg->lev[0];
+      for (int p = 1; p < h->nranks; ++p)
+        g_nccl.Send(A.T[A.cur] + per_parent * h->part_first[p], per_parent * (h->part_first[p + 1] - h->part_first[p]), ncclFloat64,
+                    p, h->comm, h->stream);
+    } else {
+      g_nccl.Recv(Lc.T[Lc.cur], per_parent * h->U, ncclFloat64, 0, h->comm, h->stream);
+    }
+    if (g_nccl.GroupEnd() != ncclSuccess) return fail(h, PAMG_ERR_CUDA, "ncclGroupEnd failed in coarse scatter");
+    Lc.tnew_alias = true; Lc.strips_valid = false; Lc.cut_valid = false;
+    return PAMG_OK;
   }
-  if (g_nccl.GroupEnd() != ncclSuccess) return fail(h, PAMG_ERR_CUDA, "ncclGroupEnd failed in coarse gather");
-  if (h->rank == 0) {
-    pamg_handle* g = h->agg;
-    LevelDev& A = g->lev[0];
+  // single process, several GPUs: the parts push their slices into part 0's memory (k_push), part 0 waits for the
+  // flags, solves, and pushes the corrections back
+  pamg_handle* g = h0->agg;
+  LevelDev& A = g->lev[0];
+  unsigned all = 0;
+  for (size_t p = 1; p < G.size(); ++p) {
+    pamg_handle* q = G[p];
+    cudaSetDevice(q->device);
+    LevelDev& Lc = q->lev[lvl - 1];
+    int rc = launch_push(q, Lc.rhs, A.rhs + per_parent * q->part_first[p], (long long)(per_parent * q->U), 0,
+                         h0->agg_words + AGG_FLAGS + p);
+    if (rc) return gfail(owner, q, rc);
+    all |= 1u << p;
+  }
+  {
+    pamg_handle* h = h0;
+    cudaSetDevice(h->device);
+    LevelDev& Lc = h->lev[lvl - 1];
     CK(cudaMemcpyAsync(A.rhs, Lc.rhs, per_parent * h->U * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaMemsetAsync(A.T[A.cur], 0, A.ndof * sizeof(double), h->stream));
-    A.tnew_alias = true; A.strips_valid = false; A.rhs_valid = true;
+    int rc = launch_wait(h, all);
+    if (rc) return gfail(owner, h, rc);
+    A.tnew_alias = true; A.strips_valid = false; A.cut_valid = false; A.rhs_valid = true;
     const long long l0 = g->launches;
-    int rc = vcycle_rec(g, 1, solver, nu1, nu2, ncoarse);
+    rc = vcycle_rec(Group{g}, g, 1, solver, nu1, nu2, ncoarse);
     h->launches += g->launches - l0;
-    if (rc) return fail(h, rc, g->err);
+    if (rc) { h->err = g->err; return gfail(owner, h, rc); }
     CK(cudaMemcpyAsync(Lc.T[Lc.cur], A.T[A.cur], per_parent * h->U * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    Lc.tnew_alias = true; Lc.strips_valid = false; Lc.cut_valid = false;
+    for (size_t p = 1; p < G.size(); ++p) {
+      pamg_handle* q = G[p];
+      LevelDev& Lq = q->lev[lvl - 1];
+      rc = launch_push(h, A.T[A.cur] + per_parent * q->part_first[p], Lq.T[Lq.cur], (long long)(per_parent * q->U), (int)p,
+                       q->agg_words + AGG_FLAGS + 0);
+      if (rc) return gfail(owner, h, rc);
+    }
   }
-  g_nccl.GroupStart();
-  if (h->rank == 0) {
-    LevelDev& A = h->agg->lev[0];
-    for (int p = 1; p < h->nranks; ++p)
-      g_nccl.Send(A.T[A.cur] + per_parent * h->part_first[p], per_parent * (h->part_first[p + 1] - h->part_first[p]), ncclFloat64,
-                  p, h->comm, h->stream);
-  } else {
-    g_nccl.Recv(Lc.T[Lc.cur], per_parent * h->U, ncclFloat64, 0, h->comm, h->stream);
+  for (size_t p = 1; p < G.size(); ++p) {
+    pamg_handle* q = G[p];
+    cudaSetDevice(q->device);
+    int rc = launch_wait(q, 1u);
+    if (rc) return gfail(owner, q, rc);
+    LevelDev& Lq = q->lev[lvl - 1];
+    Lq.tnew_alias = true; Lq.strips_valid = false; Lq.cut_valid = false;
   }
-  if (g_nccl.GroupEnd() != ncclSuccess) return fail(h, PAMG_ERR_CUDA, "ncclGroupEnd failed in coarse scatter");
-  Lc.tnew_alias = true; Lc.strips_valid = false;
   return PAMG_OK;
 }
 
@@ -756,60 +858,86 @@ int normalise_parity(pamg_handle* h, LevelDev& L, int cur0) {
   return PAMG_OK;
 }
 
-int vcycle_rec(pamg_handle* h, int level, int solver, int nu1, int nu2, int ncoarse) {
-  const int Lmax = (int)h->lev.size();
-  int rc;
-  LevelDev& L = h->lev[level - 1];
-  const int cur0 = L.cur;
+int vcycle_rec(const Group& G, pamg_handle* owner, int level, int solver, int nu1, int nu2, int ncoarse) {
+  const int Lmax = (int)G[0]->lev.size();
+  std::vector<int> cur0(G.size());
+  for (size_t i = 0; i < G.size(); ++i) cur0[i] = G[i]->lev[level - 1].cur;
+  auto restore = [&]() -> int {
+    for (size_t i = 0; i < G.size(); ++i) {
+      if (G[i]->in_group) cudaSetDevice(G[i]->device);
+      int rc = normalise_parity(G[i], G[i]->lev[level - 1], cur0[i]);
+      if (rc) return gfail(owner, G[i], rc);
+    }
+    return PAMG_OK;
+  };
   if (level == Lmax) {
-    if ((rc = do_smooth(h, level, solver, ncoarse))) return rc;
-    return normalise_parity(h, L, cur0);
+    GALL(G, owner, q, do_smooth(q, level, solver, ncoarse));
+    return restore();
   }
-  if ((rc = do_smooth(h, level, solver, nu1))) return rc;
-  L.tnew_alias = true;                                   // tnew = tnew_nonlin
-  if ((rc = ensure_strips(h, level))) return rc;
-  if ((rc = do_residual(h, level, nullptr, nullptr, nullptr))) return rc;
-  if ((rc = do_restrict(h, level))) return rc;
-  LevelDev& Cc = h->lev[level];
-  if ((rc = do_fill(h, Cc.T[Cc.cur], Cc.ndof, 0.0))) return rc;
-  Cc.tnew_alias = true;
-  Cc.strips_valid = false;
-  if (h->agg_level && level + 1 == h->agg_level) {
-    if ((rc = agg_coarse_solve(h, solver, nu1, nu2, ncoarse))) return rc;
+  GALL(G, owner, q, do_smooth(q, level, solver, nu1));
+  for (pamg_handle* q : G) q->lev[level - 1].tnew_alias = true;   // tnew = tnew_nonlin
+  GALL(G, owner, q, do_residual(q, level, nullptr, nullptr, nullptr));
+  GALL(G, owner, q, do_restrict(q, level));
+  for (pamg_handle* q : G) {
+    if (q->in_group) cudaSetDevice(q->device);
+    LevelDev& Cc = q->lev[level];
+    int rc = do_fill(q, Cc.T[Cc.cur], Cc.ndof, 0.0);
+    if (rc) return gfail(owner, q, rc);
+    Cc.tnew_alias = true;
+    Cc.strips_valid = false; Cc.cut_valid = false;
+  }
+  int rc;
+  if (G[0]->agg_level && level + 1 == G[0]->agg_level) {
+    if ((rc = agg_coarse_solve(G, owner, solver, nu1, nu2, ncoarse))) return rc;
   } else {
-    if ((rc = vcycle_rec(h, level + 1, solver, nu1, nu2, ncoarse))) return rc;
+    if ((rc = vcycle_rec(G, owner, level + 1, solver, nu1, nu2, ncoarse))) return rc;
   }
-  if ((rc = do_prolong(h, level, false))) return rc;
-  if ((rc = do_smooth(h, level, solver, nu2))) return rc;
-  return normalise_parity(h, L, cur0);
+  GALL(G, owner, q, do_prolong(q, level, false));
+  GALL(G, owner, q, do_smooth(q, level, solver, nu2));
+  return restore();
 }
 
 // one V-cycle followed by the residual norms of level 1 (the copy to pinned memory is queued, not awaited)
-int vcycle_body(pamg_handle* h, int solver, int nu1, int nu2, int ncoarse) {
+int vcycle_body(const Group& G, pamg_handle* owner, int solver, int nu1, int nu2, int ncoarse) {
   int rc;
-  if ((rc = vcycle_rec(h, 1, solver, nu1, nu2, ncoarse))) return rc;
-  LevelDev& L = h->lev[0];
-  L.tnew_alias = true;
-  if ((rc = ensure_strips(h, 1))) return rc;
+  if ((rc = vcycle_rec(G, owner, 1, solver, nu1, nu2, ncoarse))) return rc;
+  for (pamg_handle* q : G) q->lev[0].tnew_alias = true;
   double dummy;
-  const bool cap = h->capturing;
-  h->capturing = true;    // do_residual: queue the read-back only
-  rc = do_residual(h, 1, &dummy, nullptr, nullptr);
-  h->capturing = cap;
-  return rc;
+  GALL(G, owner, q, do_residual(q, 1, &dummy, nullptr, nullptr, /*queue_only=*/true));
+  return PAMG_OK;
+}
+
+// wait for every part, surface a failed exchange, combine the norms (the parts of one process hold partial sums;
+// ranks of a multi-process run have already all-reduced theirs)
+int group_norms(const Group& G, pamg_handle* owner, double* l2, double* linf, double* smax) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (pamg_handle* q : G) {
+    if (q->in_group) cudaSetDevice(q->device);
+    CK_(q, cudaStreamSynchronize(q->stream));
+    int rc = p2p_check(q);
+    if (rc) return gfail(owner, q, rc);
+    s0 += q->out3_host[0]; s1 = std::max(s1, q->out3_host[1]); s2 = std::max(s2, q->out3_host[2]);
+  }
+  for (pamg_handle* q : G) if (q != owner && !q->err.empty()) { owner->err = q->err; }
+  if (l2) *l2 = std::sqrt(s0);
+  if (linf) *linf = s1;
+  if (smax) *smax = s2;
+  return PAMG_OK;
 }
 
 void free_levels(pamg_handle* h) {
-  for (auto& g : h->vc_graphs) cudaGraphExecDestroy(g.exec);
+  for (auto& g : h->vc_graphs) for (auto e : g.exec) cudaGraphExecDestroy(e);
   h->vc_graphs.clear();
   for (auto& L : h->lev) {
     cudaFree(L.T[0]); cudaFree(L.T[1]); cudaFree(L.spare); cudaFree(L.told); cudaFree(L.rhs); cudaFree(L.res);
-    cudaFree(L.ovlb[0]); cudaFree(L.ovlb[1]); cudaFree(L.ovl_old); cudaFree(L.pc); cudaFree(L.items);
+    cudaFree(L.ovlb[0]); cudaFree(L.ovlb[1]); cudaFree(L.ovl_old); cudaFree(L.pc);
   }
   h->lev.clear();
   cudaFree(h->xg); cudaFree(h->strip_of); cudaFree(h->dst_strip); cudaFree(h->rev); cudaFree(h->hmap);
-  cudaFree(h->partial); cudaFree(h->counters); h->counters = nullptr;
-  h->xg = nullptr; h->strip_of = h->dst_strip = h->rev = h->hmap = nullptr; h->partial = nullptr;
+  cudaFree(h->nsrc); cudaFree(h->cut_lf); cudaFree(h->bc_kind); cudaFree(h->bc_val);
+  cudaFree(h->partial);
+  h->xg = nullptr; h->strip_of = h->dst_strip = h->rev = h->hmap = h->nsrc = h->cut_lf = h->bc_kind = nullptr;
+  h->bc_val = nullptr; h->partial = nullptr;
 }
 
 int ensure_stage(pamg_handle* h, size_t bytes) {
@@ -824,6 +952,15 @@ int ensure_stage(pamg_handle* h, size_t bytes) {
 }  // namespace
 
 // ================================================================== C ABI
+// root of a single-process multi-GPU handle: run the entry on every part
+#define FANOUT(h, q, expr)                                                              \
+  if ((h) && !(h)->parts.empty()) {                                                     \
+    for (pamg_handle* q : (h)->parts) { int rc_ = (expr); if (rc_) return gfail((h), q, rc_); } \
+    return PAMG_OK;                                                                     \
+  }
+// entries that only exist on a single device (unstructured front-ends, local inverse ...) run on part 0
+#define ON_PART0(h) if ((h) && !(h)->parts.empty()) (h) = (h)->parts[0]
+
 extern "C" {
 
 const char* pamg_version(void) { return "pamg-b200 0.1 (sm_100a)"; }
@@ -864,9 +1001,7 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
   h->p = *p; h->device = device;
   {
     const char* e = getenv("PAMG_KERNEL");
-    if (e && !strcmp(e, "direct")) h->kernel_mode = 0;
-    else if (e && !strcmp(e, "tma1d")) h->kernel_mode = 1;
-    else if (e && !strcmp(e, "stream")) h->kernel_mode = 2;
+    if (e && !strcmp(e, "tma1d")) h->kernel_mode = 1;
     else if (e && !strcmp(e, "direct2")) h->kernel_mode = 3;
     else if (e && !strcmp(e, "win")) h->kernel_mode = 4;
     const char* wp = getenv("PAMG_WIN");
@@ -876,16 +1011,12 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
     if (pp && pp[0] == '0') h->p2p_enabled = false;
     const char* pt = getenv("PAMG_P2P_TIMEOUT_S");
     if (pt && atof(pt) > 0.0) h->p2p_timeout_ns = (unsigned long long)(atof(pt) * 1e9);
-    const char* pf = getenv("PAMG_P2P_FUSE");
-    if (pf && pf[0] == '0') h->p2p_fuse = false;
+    const char* hl = getenv("PAMG_HALO");
+    if (hl && !strcmp(hl, "strips")) h->direct_halo = false;
     const char* gr = getenv("PAMG_GRAPH");
     if (gr && gr[0] == '0') h->use_graph = false;
     const char* gn = getenv("PAMG_GRAPH_NCCL");
     if (gn && gn[0] == '0') h->graph_nccl = false;
-    const char* sp = getenv("PAMG_SPLIT");
-    if (sp && sp[0] == '1') h->split_boundary = true;
-    const char* fh = getenv("PAMG_FUSED_HALO");
-    if (fh && fh[0] == '1') h->fused_halo = true;
     const char* g = getenv("PAMG_GS");
     if (g && !strcmp(g, "direct")) { h->gs_tma = false; h->gs_fused = false; }
     if (g && !strcmp(g, "twopass")) h->gs_fused = false;
@@ -894,24 +1025,90 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->nsm = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return PAMG_ERR_CUDA; }
-  for (auto& e : h->ev) cudaEventCreate(&e);
-  cudaMalloc(&h->out3, 3 * sizeof(double));
-  cudaMallocHost(&h->out3_host, 3 * sizeof(double));
+  bool ok = true;
+  for (auto& e : h->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+  ok = ok && cudaMalloc(&h->out3, 3 * sizeof(double)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&h->out3_host, 3 * sizeof(double)) == cudaSuccess;
+  ok = ok && configure_kernels(h) == PAMG_OK;
+  if (!ok) { pamg_destroy(h); return PAMG_ERR_CUDA; }
   *out = h;
+  return PAMG_OK;
+}
+
+// ---- single process, several GPUs (one host thread drives 1-8 devices; main.F90:16-51 is serial) ----------
+namespace {
+// peer pointers are plain device pointers here: enable peer access between the devices of the group, give every part its
+// staging buffer / counters, and point the peers at each other
+int group_p2p_setup(pamg_handle* root) {
+  const Group& G = root->parts;
+  for (pamg_handle* a : G)
+    for (pamg_handle* b : G) {
+      if (a->device == b->device) continue;
+      int can = 0;
+      CK_(root, cudaDeviceCanAccessPeer(&can, a->device, b->device));
+      if (!can) return fail(root, PAMG_ERR_UNSUPPORTED, "the GPUs of the group cannot access each other's memory (no NVLink / PCIe peer access)");
+      CK_(root, cudaSetDevice(a->device));
+      cudaError_t e = cudaDeviceEnablePeerAccess(b->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(root, PAMG_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+      (void)cudaGetLastError();
+    }
+  for (pamg_handle* q : G) {
+    CK_(root, cudaSetDevice(q->device));
+    if ((int)q->plan.peers.size() > P2P_MAXP) return fail(root, PAMG_ERR_UNSUPPORTED, "too many neighbour parts");
+    int rc = p2p_alloc_local(q);
+    if (rc) return gfail(root, q, rc);
+    CK_(root, cudaMalloc(&q->agg_words, AGG_WORDS * sizeof(unsigned long long)));
+    CK_(root, cudaMemset(q->agg_words, 0, AGG_WORDS * sizeof(unsigned long long)));
+  }
+  for (pamg_handle* q : G) {
+    for (size_t i = 0; i < q->plan.peers.size(); ++i) {
+      if (q->p2p_peers[i].slot_at_peer < 0) return fail(root, PAMG_ERR_STATE, "inconsistent halo plans between parts");
+      q->p2p_peers[i].stage = G[q->plan.peers[i].part]->p2p_stage;
+    }
+    q->p2p_ready = true;
+  }
+  return PAMG_OK;
+}
+}  // namespace
+
+int pamg_create_multi(const pamg_params* p, int ngpus, const int* devices, pamg_handle** out) {
+  if (!p || !out || ngpus < 1 || ngpus > 16) return PAMG_ERR_ARG;
+  *out = nullptr;
+  pamg_handle* root = new pamg_handle();
+  root->p = *p; root->is_root = true;
+  for (int i = 0; i < ngpus; ++i) {
+    pamg_handle* q = nullptr;
+    int rc = pamg_create(p, devices ? devices[i] : i, &q);
+    if (rc) { pamg_destroy(root); return rc; }
+    q->in_group = true; q->nranks = ngpus; q->rank = i;
+    root->parts.push_back(q);
+  }
+  root->device = root->parts[0]->device; root->nsm = root->parts[0]->nsm; root->use_graph = root->parts[0]->use_graph;
+  *out = root;
   return PAMG_OK;
 }
 
 void pamg_destroy(pamg_handle* h) {
   if (!h) return;
+  if (h->is_root) {
+    // root of a group (owns no device memory of its own besides cached graphs)
+    for (pamg_handle* q : h->parts) { cudaSetDevice(q->device); if (q->stream) cudaStreamSynchronize(q->stream); }
+    for (auto& g : h->vc_graphs) for (auto e : g.exec) cudaGraphExecDestroy(e);
+    h->vc_graphs.clear();
+    for (pamg_handle* q : h->parts) pamg_destroy(q);
+    delete h;
+    return;
+  }
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   // graphs that contain NCCL nodes must go before the communicator
-  for (auto& g : h->vc_graphs) cudaGraphExecDestroy(g.exec);
+  for (auto& g : h->vc_graphs) for (auto e : g.exec) cudaGraphExecDestroy(e);
   h->vc_graphs.clear();
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->agg) { pamg_destroy(h->agg); h->agg = nullptr; }
   if (h->comm) g_nccl.CommDestroy(h->comm);
   p2p_close(h);
+  if (h->agg_words) { cudaFree(h->agg_words); h->agg_words = nullptr; }
   free_levels(h);
   unstr_free(h->un);
   cudaFree(h->out3); cudaFreeHost(h->out3_host); cudaFree(h->scratch);
@@ -929,6 +1126,7 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
                                const int32_t* fneig, const int32_t* dir, int nparts, const int32_t* part_first,
                                int my_part) {
   if (!h) return PAMG_ERR_ARG;
+  if (h->is_root) return fail(h, PAMG_ERR_ARG, "a multi-GPU handle partitions the mesh itself: call pamg_set_parents");
   CK(cudaSetDevice(h->device));
   int rc = build_halo_plan(U_global, X, neig, fneig, dir, h->p.halo_rule, nparts, part_first, my_part, h->plan);
   if (rc) return fail(h, rc, "inconsistent parent arrays (X / Neig / fNeig)");
@@ -968,6 +1166,21 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
   CK(cudaMemcpy(h->dst_strip, h->plan.dst_strip.data(), n3, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->rev, h->plan.rev.data(), n3, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->hmap, h->plan.hmap.data(), n3, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&h->nsrc, n3));
+  CK(cudaMemcpy(h->nsrc, h->plan.nsrc.data(), n3, cudaMemcpyHostToDevice));
+  if (!h->plan.cut_lf.empty()) {
+    CK(cudaMalloc(&h->cut_lf, h->plan.cut_lf.size() * sizeof(int32_t)));
+    CK(cudaMemcpy(h->cut_lf, h->plan.cut_lf.data(), h->plan.cut_lf.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  // Dirichlet data of the domain-boundary faces (pamg_set_boundary_data), local slice on the device
+  const int32_t* bc_glob = nullptr;
+  if (!h->bc_kind_h.empty()) {
+    if ((int)h->bc_kind_h.size() != U_global * 3) return fail(h, PAMG_ERR_ARG, "pamg_set_boundary_data was given a different number of parents");
+    bc_glob = h->bc_kind_h.data();
+    CK(cudaMalloc(&h->bc_kind, n3)); CK(cudaMalloc(&h->bc_val, (size_t)U * 3 * sizeof(double)));
+    CK(cudaMemcpy(h->bc_kind, h->bc_kind_h.data() + (size_t)first * 3, n3, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->bc_val, h->bc_val_h.data() + (size_t)first * 3, (size_t)U * 3 * sizeof(double), cudaMemcpyHostToDevice));
+  }
   h->lev.resize(h->p.multi_levels);
   std::vector<double> pc((size_t)U * NPC);
   for (int il = 0; il < h->p.multi_levels; ++il) {
@@ -984,37 +1197,14 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
     CK(cudaMalloc(&L.ovlb[0], ob)); CK(cudaMalloc(&L.ovlb[1], ob)); CK(cudaMalloc(&L.ovl_old, ob));
     CK(cudaMemsetAsync(L.ovlb[0], 0, ob, h->stream)); CK(cudaMemsetAsync(L.ovlb[1], 0, ob, h->stream));
     CK(cudaMemsetAsync(L.ovl_old, 0, ob, h->stream));  // :207
-    L.ovl_cur = 0; L.strips_valid = false;
-    for (int u = 0; u < U; ++u) parent_coefficients(h->p, X, neig, first + u, L.s, &pc[(size_t)u * NPC]);
+    L.ovl_cur = 0; L.strips_valid = false; L.cut_valid = false;
+    for (int u = 0; u < U; ++u)
+      if (!parent_coefficients(h->p, X, neig, bc_glob, first + u, L.s, &pc[(size_t)u * NPC]))
+        return fail(h, PAMG_ERR_UNSUPPORTED, "open boundary face (kind 2) with inflow: give it Dirichlet data instead");
     CK(cudaMalloc(&L.pc, pc.size() * sizeof(double)));
     CK(cudaMemcpy(L.pc, pc.data(), pc.size() * sizeof(double), cudaMemcpyHostToDevice));
     L.cur = 0; L.tnew_alias = true; L.rhs_valid = (il != 0);
-    // work list of the row-streaming kernel: (parent, row chunk, column strip) cut out of the triangle of
-    // children in (r, x = ipos + r - 1) coordinates; largest items first (dynamic scheduling)
-    if (L.s >= STREAM_MIN_S) {
-      const int b = 2 << L.s;
-      struct It { int u, r0, x0, n; };
-      std::vector<It> its;
-      for (int u = 0; u < U; ++u)
-        for (int r0 = 1; r0 <= L.S; r0 += SR)
-          for (int x0 = 1; x0 <= b - 1; x0 += SW) {
-            const int x1 = x0 + SW - 1;
-            const int rend = std::min(std::min(r0 + SR - 1, L.S), std::min(x1, b - x0));
-            if (rend < r0) continue;
-            int n = 0;
-            for (int r = r0; r <= rend; ++r) n += std::min(x1, b - r) - std::max(x0, r) + 1;
-            its.push_back(It{u, r0, x0, n});
-          }
-      std::stable_sort(its.begin(), its.end(), [](const It& p, const It& q) { return p.n > q.n; });
-      std::vector<int2> packed(its.size());
-      for (size_t i = 0; i < its.size(); ++i) packed[i] = make_int2(its[i].u, (its[i].r0 << 16) | its[i].x0);
-      L.nitems = (int)packed.size();
-      CK(cudaMalloc(&L.items, packed.size() * sizeof(int2)));
-      CK(cudaMemcpy(L.items, packed.data(), packed.size() * sizeof(int2), cudaMemcpyHostToDevice));
-    }
   }
-  CK(cudaMalloc(&h->counters, 2 * sizeof(int)));
-  CK(cudaMemset(h->counters, 0, 2 * sizeof(int)));
   // Dirichlet data sin(x+y) on domain-boundary faces never changes: fill those strips once per level
   for (int il = 1; il <= h->p.multi_levels; ++il)
     for (int bsel = 0; bsel < 2; ++bsel) {
@@ -1040,11 +1230,13 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
         ap.multi_levels = h->p.multi_levels - lvl + 1;
         pamg_handle* g = new pamg_handle();
         g->p = ap; g->device = h->device; g->nsm = h->nsm; g->kernel_mode = h->kernel_mode; g->gs_tma = h->gs_tma; g->gs_fused = h->gs_fused; g->win_producer = h->win_producer;
-        g->stream = h->stream; g->shared_stream = true; g->level_offset = lvl - 1;
-        for (auto& ev : g->ev) cudaEventCreate(&ev);
-        cudaMalloc(&g->out3, 3 * sizeof(double));
-        cudaMallocHost(&g->out3_host, 3 * sizeof(double));
+        g->stream = h->stream; g->shared_stream = true; g->level_offset = lvl - 1; g->direct_halo = h->direct_halo;
+        g->bc_kind_h = h->bc_kind_h; g->bc_val_h = h->bc_val_h;
         h->agg = g;
+        for (auto& ev : g->ev) CK(cudaEventCreate(&ev));
+        CK(cudaMalloc(&g->out3, 3 * sizeof(double)));
+        CK(cudaMallocHost(&g->out3_host, 3 * sizeof(double)));
+        if (configure_kernels(g)) return fail(h, PAMG_ERR_CUDA, g->err);
         int rc3 = pamg_set_parents_partition(g, U_global, X, neig, fneig, dir, 1, nullptr, 0);
         if (rc3) return fail(h, rc3, std::string("agglomerated coarse problem: ") + g->err);
       }
@@ -1056,18 +1248,61 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
   return PAMG_OK;
 }
 
+int pamg_set_boundary_data(pamg_handle* h, int U_global, const int32_t* kind, const double* value) {
+  if (!h || U_global < 1 || !kind) return PAMG_ERR_ARG;
+  for (size_t i = 0; i < (size_t)U_global * 3; ++i)
+    if (kind[i] < 0 || kind[i] > 2) return fail(h, PAMG_ERR_ARG, "boundary kind must be 0 (sin(x+y)), 1 (constant) or 2 (open)");
+  h->bc_kind_h.assign(kind, kind + (size_t)U_global * 3);
+  if (value) h->bc_val_h.assign(value, value + (size_t)U_global * 3);
+  else h->bc_val_h.assign((size_t)U_global * 3, 0.0);
+  FANOUT(h, q, pamg_set_boundary_data(q, U_global, kind, value));
+  if (!h->lev.empty()) return fail(h, PAMG_ERR_STATE, "pamg_set_boundary_data must precede pamg_set_parents (the coefficient tables depend on it)");
+  return PAMG_OK;
+}
+
 int pamg_set_parents(pamg_handle* h, int U, const double* X, const int32_t* neig, const int32_t* fneig,
                      const int32_t* dir) {
+  if (h && h->is_root) {
+    // contiguous blocks of parents per GPU (the scheme Generic.F90:387-401 sketches); one part per device
+    const int n = (int)h->parts.size();
+    if (U < n) return fail(h, PAMG_ERR_ARG, "fewer parents than GPUs");
+    std::vector<int32_t> pf(n + 1);
+    for (int i = 0; i <= n; ++i) pf[i] = (int32_t)((long long)U * i / n);
+    for (auto& g : h->vc_graphs) for (auto e : g.exec) cudaGraphExecDestroy(e);
+    h->vc_graphs.clear();
+    for (int i = 0; i < n; ++i) {
+      pamg_handle* q = h->parts[i];
+      if (q->agg_words) { cudaSetDevice(q->device); cudaFree(q->agg_words); q->agg_words = nullptr; }
+      int rc = pamg_set_parents_partition(q, U, X, neig, fneig, dir, n, pf.data(), i);
+      if (rc) return gfail(h, q, rc);
+    }
+    h->U = U; h->U_global = U;
+    return n > 1 ? group_p2p_setup(h) : PAMG_OK;
+  }
   return pamg_set_parents_partition(h, U, X, neig, fneig, dir, 1, nullptr, 0);
 }
 
 int pamg_ndof(const pamg_handle* h, int level, int64_t* ndof) {
+  if (h && h->is_root && ndof) {
+    *ndof = 0;
+    for (const pamg_handle* q : h->parts) { if (!valid_level(q, level)) return PAMG_ERR_ARG; *ndof += q->lev[level - 1].ndof; }
+    return PAMG_OK;
+  }
   if (!valid_level(h, level) || !ndof) return PAMG_ERR_ARG;
   *ndof = h->lev[level - 1].ndof;
   return PAMG_OK;
 }
 
 int pamg_upload_field(pamg_handle* h, int field, int level, const double* host) {
+  if (h && h->is_root && host) {    // parts own contiguous blocks of parents = contiguous ranges of the field
+    size_t off = 0;
+    for (pamg_handle* q : h->parts) {
+      int rc = pamg_upload_field(q, field, level, host + off);
+      if (rc) return gfail(h, q, rc);
+      off += (size_t)q->lev[level - 1].ndof;
+    }
+    return PAMG_OK;
+  }
   if (!valid_level(h, level) || !host) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   int rc;
@@ -1079,6 +1314,15 @@ int pamg_upload_field(pamg_handle* h, int field, int level, const double* host) 
 }
 
 int pamg_download_field(pamg_handle* h, int field, int level, double* host) {
+  if (h && h->is_root && host) {
+    size_t off = 0;
+    for (pamg_handle* q : h->parts) {
+      int rc = pamg_download_field(q, field, level, host + off);
+      if (rc) return gfail(h, q, rc);
+      off += (size_t)q->lev[level - 1].ndof;
+    }
+    return PAMG_OK;
+  }
   if (!valid_level(h, level) || !host) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   int rc;
@@ -1086,10 +1330,11 @@ int pamg_download_field(pamg_handle* h, int field, int level, double* host) {
   if (rc) return rc;
   CK(cudaMemcpyAsync(host, d, h->lev[level - 1].ndof * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  return PAMG_OK;
+  return p2p_check(h);
 }
 
 int pamg_fill_field(pamg_handle* h, int field, int level, double value) {
+  FANOUT(h, q, pamg_fill_field(q, field, level, value));
   if (!valid_level(h, level)) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   int rc;
@@ -1099,13 +1344,14 @@ int pamg_fill_field(pamg_handle* h, int field, int level, double value) {
 }
 
 int pamg_copy_field(pamg_handle* h, int level, int dst_field, int src_field) {
+  FANOUT(h, q, pamg_copy_field(q, level, dst_field, src_field));
   if (!valid_level(h, level)) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   LevelDev& L = h->lev[level - 1];
   if (dst_field == src_field) return PAMG_OK;
   if (dst_field == PAMG_TNEW && src_field == PAMG_TNONLIN) { L.tnew_alias = true; return PAMG_OK; }      // :550
   if (dst_field == PAMG_TNONLIN && src_field == PAMG_TNEW) {                                             // :327
-    if (!L.tnew_alias) { L.cur ^= 1; L.tnew_alias = true; L.strips_valid = false; }
+    if (!L.tnew_alias) { L.cur ^= 1; L.tnew_alias = true; L.strips_valid = false; L.cut_valid = false; }
     return PAMG_OK;
   }
   int rc;
@@ -1118,6 +1364,15 @@ int pamg_copy_field(pamg_handle* h, int level, int dst_field, int src_field) {
 }
 
 int pamg_download_overlap(pamg_handle* h, int level, int old, double* host) {
+  if (h && h->is_root && host) {
+    size_t off = 0;
+    for (pamg_handle* q : h->parts) {
+      int rc = pamg_download_overlap(q, level, old, host + off);
+      if (rc) return gfail(h, q, rc);
+      off += (size_t)q->U * 9 * q->lev[level - 1].S;
+    }
+    return PAMG_OK;
+  }
   if (!valid_level(h, level) || !host) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   LevelDev& L = h->lev[level - 1];
@@ -1131,6 +1386,7 @@ int pamg_download_overlap(pamg_handle* h, int level, int old, double* host) {
 }
 
 int pamg_device_ptr(pamg_handle* h, int field, int level, void** dptr) {
+  if (h && h->is_root) return fail(h, PAMG_ERR_UNSUPPORTED, "a multi-GPU handle has no single device pointer per field");
   if (!valid_level(h, level) || !dptr) return PAMG_ERR_ARG;
   int rc;
   *dptr = field_ptr(h, field, level, false, &rc);
@@ -1138,30 +1394,53 @@ int pamg_device_ptr(pamg_handle* h, int field, int level, void** dptr) {
 }
 
 int pamg_update_overlaps(pamg_handle* h, int level) {
+  FANOUT(h, q, pamg_update_overlaps(q, level));
   if (!valid_level(h, level)) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   return launch_halo(h, level);
 }
 
 int pamg_build_rhs(pamg_handle* h) {
+  FANOUT(h, q, pamg_build_rhs(q));
   if (!valid_level(h, 1)) return PAMG_ERR_STATE;
   CK(cudaSetDevice(h->device));
   return launch_build_rhs(h);
 }
 
 int pamg_smooth(pamg_handle* h, int level, int solver, int nsweeps) {
+  if (h && h->is_root) {
+    // lockstep in small batches: a part whose exchange kernel waits for a peer must never have so many launches queued
+    // behind it that the host blocks before it has queued the peer's work
+    for (int done = 0; done < nsweeps; done += 4)
+      for (pamg_handle* q : h->parts) { int rc = pamg_smooth(q, level, solver, std::min(4, nsweeps - done)); if (rc) return gfail(h, q, rc); }
+    return PAMG_OK;
+  }
   if (!valid_level(h, level) || nsweeps < 0) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   return do_smooth(h, level, solver, nsweeps);
 }
 
 int pamg_residual(pamg_handle* h, int level, double* l2, double* linf) {
+  if (h && h->is_root) {
+    const Group& G = h->parts;
+    if (!valid_level(G[0], level)) return PAMG_ERR_ARG;
+    double dummy;
+    GALL(G, h, q, do_residual(q, level, &dummy, nullptr, nullptr, true));
+    return group_norms(G, h, l2, linf, nullptr);
+  }
   if (!valid_level(h, level)) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   return do_residual(h, level, l2, linf, nullptr);
 }
 
 int pamg_convergence(pamg_handle* h, int level, double* conv) {
+  if (h && h->is_root && conv) {
+    const Group& G = h->parts;
+    if (!valid_level(G[0], level)) return PAMG_ERR_ARG;
+    double dummy;
+    GALL(G, h, q, do_residual(q, level, &dummy, nullptr, nullptr, true));
+    return group_norms(G, h, nullptr, nullptr, conv);
+  }
   if (!valid_level(h, level) || !conv) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   double l2, li;
@@ -1169,12 +1448,14 @@ int pamg_convergence(pamg_handle* h, int level, double* conv) {
 }
 
 int pamg_restrict(pamg_handle* h, int fine_level) {
+  FANOUT(h, q, pamg_restrict(q, fine_level));
   if (!valid_level(h, fine_level)) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   return do_restrict(h, fine_level);
 }
 
 int pamg_prolong(pamg_handle* h, int fine_level) {
+  FANOUT(h, q, pamg_prolong(q, fine_level));
   if (!valid_level(h, fine_level)) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   return do_prolong(h, fine_level);
@@ -1182,67 +1463,89 @@ int pamg_prolong(pamg_handle* h, int fine_level) {
 
 int pamg_vcycle_solve(pamg_handle* h, int solver, int nu1, int nu2, int ncoarse, int max_cycles, double tol,
                       int* cycles, double* hist) {
-  if (!valid_level(h, 1) || max_cycles < 0) return PAMG_ERR_ARG;
-  CK(cudaSetDevice(h->device));
-  LevelDev& L = h->lev[0];
+  if (!h || max_cycles < 0) return PAMG_ERR_ARG;
+  const Group G = group_of(h);
+  if (!valid_level(G[0], 1)) return PAMG_ERR_ARG;
+  CK(cudaSetDevice(G[0]->device));
   int rc;
-  L.tnew_alias = true;
-  L.strips_valid = false;
-  if ((rc = ensure_strips(h, 1))) return rc;
-  double r0 = 0, r = 0;
-  if ((rc = do_residual(h, 1, &r0, nullptr, nullptr))) return rc;
+  for (pamg_handle* q : G) { LevelDev& L = q->lev[0]; L.tnew_alias = true; L.strips_valid = false; L.cut_valid = false; }
+  double r0 = 0, r = 0, dummy;
+  GALL(G, h, q, do_residual(q, 1, &dummy, nullptr, nullptr, true));
+  if ((rc = group_norms(G, h, &r0, nullptr, nullptr))) return rc;
   if (hist) hist[0] = r0;
   if (cycles) *cycles = 0;
   if (r0 == 0.0) return PAMG_OK;
-  // cycle 1 runs eagerly (it also sets the kernels' attributes); from cycle 2 on the identical launch sequence
-  // (~170 launches, most of them on launch-bound coarse levels) is replayed as one CUDA graph
+  // cycle 1 runs eagerly; from cycle 2 on the identical launch sequence (most of it on launch-bound coarse levels) is
+  // replayed as one CUDA graph per GPU
   const long long key0 = ((((long long)solver * 64 + nu1) * 64 + nu2) * 64 + ncoarse);
-  // with NCCL in the cycle (halo exchange, coarse gather/scatter) the capture is attempted once; if the library
+  // with NCCL in the cycle (halo exchange fallback, coarse gather/scatter) the capture is attempted once; if the library
   // refuses, the handle falls back to eager launches for good
-  const bool graph_ok = h->use_graph && !h->profiling && (!h->comm || h->graph_nccl);
+  bool graph_ok = h->use_graph;
+  for (pamg_handle* q : G) graph_ok = graph_ok && !q->profiling && (!q->comm || q->graph_nccl);
   for (int c = 1; c <= max_cycles; ++c) {
     if (c >= 2 && graph_ok) {
       long long key = key0;                      // the graph bakes in which of the two T buffers holds the iterate
-      for (auto& Lv : h->lev) key = key * 2 + Lv.cur;
+      for (pamg_handle* q : G) for (auto& Lv : q->lev) key = key * 2 + Lv.cur;
       pamg_handle::VcGraph* vg = nullptr;
       for (auto& g : h->vc_graphs) if (g.key == key) vg = &g;
       if (!vg) {
-        if (h->vc_graphs.size() >= 8) { cudaGraphExecDestroy(h->vc_graphs.front().exec); h->vc_graphs.erase(h->vc_graphs.begin()); }
-        cudaGraph_t graph = nullptr;
-        const long long l0 = h->launches;
-        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        h->capturing = true;
-        rc = vcycle_body(h, solver, nu1, nu2, ncoarse);
-        h->capturing = false;
-        cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-        pamg_handle::VcGraph ng{key, nullptr, h->launches - l0};
-        h->launches = l0;
-        if (!rc && ce == cudaSuccess) {
-          ce = cudaGraphInstantiate(&ng.exec, graph, 0);
+        if (h->vc_graphs.size() >= 8) { for (auto e : h->vc_graphs.front().exec) cudaGraphExecDestroy(e); h->vc_graphs.erase(h->vc_graphs.begin()); }
+        std::vector<long long> l0(G.size());
+        size_t begun = 0;
+        cudaError_t ce = cudaSuccess;
+        for (; begun < G.size(); ++begun) {
+          pamg_handle* q = G[begun];
+          if (q->in_group) cudaSetDevice(q->device);
+          l0[begun] = q->launches;
+          ce = cudaStreamBeginCapture(q->stream, G.size() > 1 ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal);
+          if (ce != cudaSuccess) break;
+          q->capturing = true;
         }
-        if (graph) cudaGraphDestroy(graph);
+        rc = (ce == cudaSuccess) ? vcycle_body(G, h, solver, nu1, nu2, ncoarse) : PAMG_ERR_CUDA;
+        pamg_handle::VcGraph ng;
+        ng.key = key;
+        for (size_t i = 0; i < begun; ++i) {
+          pamg_handle* q = G[i];
+          if (q->in_group) cudaSetDevice(q->device);
+          q->capturing = false;
+          cudaGraph_t graph = nullptr;
+          cudaError_t e2 = cudaStreamEndCapture(q->stream, &graph);
+          ng.launches.push_back(q->launches - l0[i]);
+          q->launches = l0[i];
+          cudaGraphExec_t ex = nullptr;
+          if (!rc && ce == cudaSuccess && e2 == cudaSuccess) e2 = cudaGraphInstantiate(&ex, graph, 0);
+          if (graph) cudaGraphDestroy(graph);
+          if (e2 != cudaSuccess && ce == cudaSuccess) ce = e2;
+          if (ex) ng.exec.push_back(ex);
+        }
         if (rc || ce != cudaSuccess) {
-          if (!h->comm) {
-            if (rc) return rc;
+          for (auto e : ng.exec) cudaGraphExecDestroy(e);
+          (void)cudaGetLastError();
+          bool nccl = false;
+          for (pamg_handle* q : G) nccl = nccl || q->comm;
+          if (!nccl) {
+            if (rc && rc != PAMG_ERR_CUDA) return rc;
             return fail(h, PAMG_ERR_CUDA, std::string("CUDA graph capture of the V-cycle: ") + cudaGetErrorString(ce));
           }
           // NCCL inside the capture was refused: run eagerly from now on (host-side state is periodic per cycle)
-          (void)cudaGetLastError();
-          h->graph_nccl = false;
-          if ((rc = vcycle_body(h, solver, nu1, nu2, ncoarse))) return rc;
+          for (pamg_handle* q : G) q->graph_nccl = false;
+          graph_ok = false;
+          if ((rc = vcycle_body(G, h, solver, nu1, nu2, ncoarse))) return rc;
           goto cycle_done;
         }
         h->vc_graphs.push_back(ng);
         vg = &h->vc_graphs.back();
       }
-      CK(cudaGraphLaunch(vg->exec, h->stream));
-      h->launches += vg->launches;
+      for (size_t i = 0; i < G.size(); ++i) {
+        if (G[i]->in_group) cudaSetDevice(G[i]->device);
+        CK(cudaGraphLaunch(vg->exec[i], G[i]->stream));
+        G[i]->launches += vg->launches[i];
+      }
     } else {
-      if ((rc = vcycle_body(h, solver, nu1, nu2, ncoarse))) return rc;
+      if ((rc = vcycle_body(G, h, solver, nu1, nu2, ncoarse))) return rc;
     }
   cycle_done:
-    CK(cudaStreamSynchronize(h->stream));
-    r = std::sqrt(h->out3_host[0]);
+    if ((rc = group_norms(G, h, &r, nullptr, nullptr))) return rc;
     if (hist) hist[c] = r;
     if (cycles) *cycles = c;
     if (r / r0 <= tol) return PAMG_OK;
@@ -1252,26 +1555,27 @@ int pamg_vcycle_solve(pamg_handle* h, int solver, int nu1, int nu2, int ncoarse,
 }
 
 int pamg_literal_timestep(pamg_handle* h, int solver, int n_multigrid, int n_smooth) {
-  if (!valid_level(h, 1)) return PAMG_ERR_STATE;
-  CK(cudaSetDevice(h->device));
-  const int ML = (int)h->lev.size();
-  int rc;
-  if ((rc = pamg_copy_field(h, 1, PAMG_TOLD, PAMG_TNEW))) return rc;      // :316
-  if ((rc = pamg_copy_field(h, 1, PAMG_TNONLIN, PAMG_TNEW))) return rc;   // :317
+  if (!h) return PAMG_ERR_ARG;
+  const Group G = group_of(h);
+  if (!valid_level(G[0], 1)) return PAMG_ERR_STATE;
+  CK(cudaSetDevice(G[0]->device));
+  const int ML = (int)G[0]->lev.size();
+  GALL(G, h, q, pamg_copy_field(q, 1, PAMG_TOLD, PAMG_TNEW));      // :316
+  GALL(G, h, q, pamg_copy_field(q, 1, PAMG_TNONLIN, PAMG_TNEW));   // :317
   for (int mg = 0; mg < n_multigrid; ++mg) {
     for (int il = 1; il <= ML; ++il) {
-      if ((rc = pamg_copy_field(h, il, PAMG_TNONLIN, PAMG_TNEW))) return rc;   // :327
-      if ((rc = do_smooth(h, il, solver, n_smooth))) return rc;                // :331
-      if ((rc = do_restrict(h, il))) return rc;                                // :336
-      if ((rc = do_residual(h, il, nullptr, nullptr, nullptr))) return rc;     // :338
+      GALL(G, h, q, pamg_copy_field(q, il, PAMG_TNONLIN, PAMG_TNEW));   // :327
+      GALL(G, h, q, do_smooth(q, il, solver, n_smooth));                // :331
+      GALL(G, h, q, do_restrict(q, il));                                // :336
+      GALL(G, h, q, do_residual(q, il, nullptr, nullptr, nullptr));     // :338
     }
-    if ((rc = pamg_copy_field(h, ML, PAMG_TNONLIN, PAMG_TNEW))) return rc;     // :348
-    for (int i = 0; i < h->p.n_coarse_smooth; ++i)
-      if ((rc = do_smooth(h, ML, solver, n_smooth))) return rc;                // :351-352
+    GALL(G, h, q, pamg_copy_field(q, ML, PAMG_TNONLIN, PAMG_TNEW));     // :348
+    for (int i = 0; i < G[0]->p.n_coarse_smooth; ++i)
+      GALL(G, h, q, do_smooth(q, ML, solver, n_smooth));                // :351-352
     for (int il = ML - 1; il >= 1; --il) {
-      if ((rc = pamg_copy_field(h, il, PAMG_TNONLIN, PAMG_TNEW))) return rc;   // :367
-      if ((rc = do_prolong(h, il))) return rc;                                 // :370
-      if ((rc = do_smooth(h, il, solver, n_smooth))) return rc;                // :376
+      GALL(G, h, q, pamg_copy_field(q, il, PAMG_TNONLIN, PAMG_TNEW));   // :367
+      GALL(G, h, q, do_prolong(q, il));                                 // :370
+      GALL(G, h, q, do_smooth(q, il, solver, n_smooth));                // :376
     }
   }
   return PAMG_OK;
@@ -1279,31 +1583,62 @@ int pamg_literal_timestep(pamg_handle* h, int solver, int n_multigrid, int n_smo
 
 int pamg_timestep_host(pamg_handle* h, const double* tnew_in, double* tnew_out, int max_cycles, double tol,
                        int* cycles, double* relres) {
-  if (!valid_level(h, 1) || !tnew_in || !tnew_out) return PAMG_ERR_ARG;
-  CK(cudaSetDevice(h->device));
-  LevelDev& L = h->lev[0];
-  const size_t bytes = (size_t)L.ndof * sizeof(double);
+  if (!h || !tnew_in || !tnew_out) return PAMG_ERR_ARG;
+  const Group G = group_of(h);
+  if (!valid_level(G[0], 1)) return PAMG_ERR_ARG;
   // told = tnew ; tnew_nonlin = tnew (transport_tri_semi.F90:316-317)
-  CK(cudaMemcpyAsync(L.T[L.cur], tnew_in, bytes, cudaMemcpyHostToDevice, h->stream));
-  L.tnew_alias = true;
-  L.strips_valid = false;
-  CK(cudaMemcpyAsync(L.told, L.T[L.cur], bytes, cudaMemcpyDeviceToDevice, h->stream));
-  L.rhs_valid = false;
+  size_t off = 0;
+  for (pamg_handle* q : G) {
+    CK_(q, cudaSetDevice(q->device));
+    LevelDev& L = q->lev[0];
+    const size_t bytes = (size_t)L.ndof * sizeof(double);
+    CK_(q, cudaMemcpyAsync(L.T[L.cur], tnew_in + off, bytes, cudaMemcpyHostToDevice, q->stream));
+    L.tnew_alias = true;
+    L.strips_valid = false; L.cut_valid = false;
+    CK_(q, cudaMemcpyAsync(L.told, L.T[L.cur], bytes, cudaMemcpyDeviceToDevice, q->stream));
+    L.rhs_valid = false;
+    off += (size_t)L.ndof;
+  }
   std::vector<double> hist((size_t)max_cycles + 2, 0.0);
   int cyc = 0;
-  int rc = pamg_vcycle_solve(h, h->p.solver, h->p.n_smooth, h->p.n_smooth, h->p.n_coarse_smooth, max_cycles, tol, &cyc,
-                             hist.data());
+  const pamg_params& P = G[0]->p;
+  int rc = pamg_vcycle_solve(h, P.solver, P.n_smooth, P.n_smooth, P.n_coarse_smooth, max_cycles, tol, &cyc, hist.data());
   if (rc) return rc;
   if (cycles) *cycles = cyc;
   if (relres) *relres = hist[0] > 0 ? hist[std::min(cyc, max_cycles)] / hist[0] : 0.0;
-  CK(cudaMemcpyAsync(tnew_out, L.T[L.cur], bytes, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  off = 0;
+  for (pamg_handle* q : G) {
+    CK_(q, cudaSetDevice(q->device));
+    LevelDev& L = q->lev[0];
+    CK_(q, cudaMemcpyAsync(tnew_out + off, L.T[L.cur], (size_t)L.ndof * sizeof(double), cudaMemcpyDeviceToHost, q->stream));
+    off += (size_t)L.ndof;
+  }
+  for (pamg_handle* q : G) {
+    CK_(q, cudaSetDevice(q->device));
+    CK_(q, cudaStreamSynchronize(q->stream));
+    if ((rc = p2p_check(q))) return gfail(h, q, rc);
+  }
   return PAMG_OK;
 }
 
 // smoother with HOST buffers, pipelined across calls: upload(k+1) runs while download(k) is still in flight (PCIe is full
 // duplex); tnew_out of call k is complete after the next call that reuses it has returned, or after pamg_sync
 int pamg_smooth_host(pamg_handle* h, int solver, int nsweeps, const double* tnew_in, double* tnew_out) {
+  if (h && h->is_root && tnew_in && tnew_out) {
+    // (the parts rotate their field buffers: V-cycle graphs cached on the root have the old addresses baked in)
+    if (!h->vc_graphs.empty()) {
+      for (pamg_handle* q : h->parts) { cudaSetDevice(q->device); cudaStreamSynchronize(q->stream); }
+      for (auto& g : h->vc_graphs) for (auto e : g.exec) cudaGraphExecDestroy(e);
+      h->vc_graphs.clear();
+    }
+    size_t off = 0;
+    for (pamg_handle* q : h->parts) {
+      int rc = pamg_smooth_host(q, solver, nsweeps, tnew_in + off, tnew_out + off);
+      if (rc) return gfail(h, q, rc);
+      off += (size_t)q->lev[0].ndof;
+    }
+    return PAMG_OK;
+  }
   if (!valid_level(h, 1) || !tnew_in || !tnew_out || nsweeps < 1) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   LevelDev& L = h->lev[0];
@@ -1321,14 +1656,21 @@ int pamg_smooth_host(pamg_handle* h, int solver, int nsweeps, const double* tnew
   // other two and call k+2 uploads into the first again - so the upload only waits for the download issued two calls ago.
   if (h->pipe_calls >= 2) CK(cudaStreamWaitEvent(h->up_stream, h->ev_down[h->pipe_calls & 1], 0));
   else { CK(cudaEventRecord(h->ev_comp, h->stream)); CK(cudaStreamWaitEvent(h->up_stream, h->ev_comp, 0)); }
+  // a dependent loop feeds the result of call k back as the input of call k+1 (or passes one buffer for both): then
+  // the upload must also wait for the download that is still writing that host range
+  if (h->pipe_calls >= 1 && h->last_out) {
+    const char *a0 = (const char*)tnew_in, *a1 = a0 + bytes, *b0 = (const char*)h->last_out, *b1 = b0 + bytes;
+    if (a0 < b1 && b0 < a1) CK(cudaStreamWaitEvent(h->up_stream, h->ev_down[(h->pipe_calls - 1) & 1], 0));
+  }
+  h->last_out = tnew_out;
   CK(cudaMemcpyAsync(L.spare, tnew_in, bytes, cudaMemcpyHostToDevice, h->up_stream));
   CK(cudaEventRecord(h->ev_up, h->up_stream));
   CK(cudaStreamWaitEvent(h->stream, h->ev_up, 0));
   // cached V-cycle graphs have the old buffer addresses baked in
-  if (!h->vc_graphs.empty()) { CK(cudaStreamSynchronize(h->stream)); for (auto& g : h->vc_graphs) cudaGraphExecDestroy(g.exec); h->vc_graphs.clear(); }
+  if (!h->vc_graphs.empty()) { CK(cudaStreamSynchronize(h->stream)); for (auto& g : h->vc_graphs) for (auto e : g.exec) cudaGraphExecDestroy(e); h->vc_graphs.clear(); }
   std::swap(L.T[L.cur], L.spare);   // the uploaded field becomes the iterate; the previous result stays in `spare` for its download
   L.tnew_alias = true;              // tnew_nonlin = tnew = the uploaded field (transport_tri_semi.F90:317)
-  L.strips_valid = false;
+  L.strips_valid = false; L.cut_valid = false;
   int rc = do_smooth(h, 1, solver, nsweeps);
   if (rc) return rc;
   CK(cudaEventRecord(h->ev_comp, h->stream));
@@ -1337,6 +1679,13 @@ int pamg_smooth_host(pamg_handle* h, int solver, int nsweeps, const double* tnew
   CK(cudaEventRecord(h->ev_down[h->pipe_calls & 1], h->down_stream));
   h->pipe_calls++;
   return PAMG_OK;
+}
+
+// the reference-facing blocking form: when it returns, tnew_out holds the result and tnew_in may be reused
+int pamg_smoother_host(pamg_handle* h, int solver, int nsweeps, const double* tnew_in, double* tnew_out) {
+  int rc = pamg_smooth_host(h, solver, nsweeps, tnew_in, tnew_out);
+  if (rc) return rc;
+  return pamg_sync(h);
 }
 
 // ---- distributed ------------------------------------------------------------------------------
@@ -1351,11 +1700,23 @@ int pamg_comm_unique_id(char* id128) {
 
 int pamg_comm_init(pamg_handle* h, const char* id128, int nranks, int rank) {
   if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return PAMG_ERR_ARG;
+  if (h->is_root || h->in_group) return fail(h, PAMG_ERR_ARG, "a multi-GPU handle of one process needs no communicator");
   if (!g_nccl.load()) return fail(h, PAMG_ERR_STATE, "libnccl.so.2 could not be loaded");
   CK(cudaSetDevice(h->device));
+  // the halo plan uses part numbers as ranks and the coarse levels are agglomerated on part 0 = rank 0
+  if (h->lev.empty()) return fail(h, PAMG_ERR_STATE, "pamg_comm_init needs pamg_set_parents_partition first");
+  if (nranks != h->plan.nparts || rank != h->plan.my_part)
+    return fail(h, PAMG_ERR_ARG, "pamg_comm_init: (nranks, rank) must equal (nparts, my_part) of pamg_set_parents_partition");
+  if (h->comm) {     // re-initialisation: graphs with NCCL nodes and the peer mappings go with the old communicator
+    CK(cudaStreamSynchronize(h->stream));
+    for (auto& g : h->vc_graphs) for (auto e : g.exec) cudaGraphExecDestroy(e);
+    h->vc_graphs.clear();
+    g_nccl.CommDestroy(h->comm); h->comm = nullptr;
+    p2p_close(h);
+  }
   ncclUniqueId id;
   std::memcpy(id.internal, id128, 128);
-  if (g_nccl.CommInitRank(&h->comm, nranks, id, rank) != ncclSuccess) return fail(h, PAMG_ERR_CUDA, "ncclCommInitRank failed");
+  if (g_nccl.CommInitRank(&h->comm, nranks, id, rank) != ncclSuccess) { h->comm = nullptr; return fail(h, PAMG_ERR_CUDA, "ncclCommInitRank failed"); }
   h->nranks = nranks; h->rank = rank;
   return PAMG_OK;
 }
@@ -1375,6 +1736,7 @@ int pamg_halo_peer_info(const pamg_handle* h, int idx, int* peer_part, int* nfac
 
 // ---- unstructured explicit step ------------------------------------------------------------------
 int pamg_set_unstructured(pamg_handle* h, int E, const double* X, const int32_t* neig, const int32_t* fneig) {
+  ON_PART0(h);
   if (!h || E < 1 || !X || !neig || !fneig) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   std::string e;
@@ -1384,6 +1746,7 @@ int pamg_set_unstructured(pamg_handle* h, int E, const double* X, const int32_t*
 }
 
 int pamg_unstr_upload(pamg_handle* h, const double* tnew) {
+  ON_PART0(h);
   if (!h || !tnew || h->un.E < 1) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   CK(cudaMemcpyAsync(h->un.T[h->un.cur], tnew, (size_t)h->un.E * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -1392,6 +1755,7 @@ int pamg_unstr_upload(pamg_handle* h, const double* tnew) {
 }
 
 int pamg_unstr_download(pamg_handle* h, double* tnew) {
+  ON_PART0(h);
   if (!h || !tnew || h->un.E < 1) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   CK(cudaMemcpyAsync(tnew, h->un.T[h->un.cur], (size_t)h->un.E * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1401,6 +1765,7 @@ int pamg_unstr_download(pamg_handle* h, double* tnew) {
 
 int pamg_explicit_step(pamg_handle* h, double dt, double u_x, double u_y, double t_bc, int ntime, int nits,
                        int njac_its, int use_exact_minv, int use_dir) {
+  ON_PART0(h);
   if (!h || h->un.E < 1 || ntime < 0 || nits < 1 || njac_its < 0) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   std::string e;
@@ -1413,6 +1778,7 @@ int pamg_explicit_step(pamg_handle* h, double dt, double u_x, double u_y, double
 
 // ---- unstructured implicit operator in block-CSR (unstr_implicit, transport_tri_unstr.F90:214-387) --------
 int pamg_implicit_assemble(pamg_handle* h, double dt, double u_x, double u_y, int use_dir) {
+  ON_PART0(h);
   if (!h || h->un.E < 1 || !(dt > 0.0)) return PAMG_ERR_ARG;
   if (use_dir < 0) use_dir = h->un_use_dir;   // internal: re-assemble with the previous pairing rule
   h->un_use_dir = use_dir; h->un.with_stab = false;
@@ -1426,6 +1792,7 @@ int pamg_implicit_assemble(pamg_handle* h, double dt, double u_x, double u_y, in
 }
 
 int pamg_implicit_get_bsr(pamg_handle* h, double* val, int32_t* col) {
+  ON_PART0(h);
   if (!h || h->un.E < 1 || (!val && !col)) return PAMG_ERR_ARG;
   if (!h->un.assembled) return fail(h, PAMG_ERR_STATE, "pamg_implicit_assemble has not been called");
   CK(cudaSetDevice(h->device));
@@ -1437,6 +1804,7 @@ int pamg_implicit_get_bsr(pamg_handle* h, double* val, int32_t* col) {
 }
 
 int pamg_implicit_apply(pamg_handle* h, const double* x, double* y) {
+  ON_PART0(h);
   if (!h || h->un.E < 1 || !x || !y) return PAMG_ERR_ARG;
   if (!h->un.assembled) return fail(h, PAMG_ERR_STATE, "pamg_implicit_assemble has not been called");
   CK(cudaSetDevice(h->device));
@@ -1453,6 +1821,7 @@ int pamg_implicit_apply(pamg_handle* h, const double* x, double* y) {
 }
 
 int pamg_implicit_set_stab(pamg_handle* h, int with_stab) {
+  ON_PART0(h);
   if (!h || h->un.E < 1) return PAMG_ERR_ARG;
   if (!h->un.assembled) return fail(h, PAMG_ERR_STATE, "pamg_implicit_assemble has not been called");
   CK(cudaSetDevice(h->device));
@@ -1463,6 +1832,7 @@ int pamg_implicit_set_stab(pamg_handle* h, int with_stab) {
 }
 
 int pamg_unstr_stab(pamg_handle* h, const double* told, double dt, double u_x, double u_y, double* diff_coe, double* stab) {
+  ON_PART0(h);
   if (!h || h->un.E < 1 || !told || !(dt > 0.0) || (!diff_coe && !stab)) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   const size_t E = (size_t)h->un.E;
@@ -1486,6 +1856,7 @@ int pamg_unstr_stab(pamg_handle* h, const double* told, double dt, double u_x, d
 }
 
 int pamg_implicit_step(pamg_handle* h, int ntime, int nits, double tol, int max_iters, int* iters_total, double* relres) {
+  ON_PART0(h);
   if (!h || h->un.E < 1 || ntime < 0 || nits < 1 || !(tol > 0.0) || max_iters < 1) return PAMG_ERR_ARG;
   if (!h->un.assembled) return fail(h, PAMG_ERR_STATE, "pamg_implicit_assemble has not been called");
   CK(cudaSetDevice(h->device));
@@ -1501,6 +1872,7 @@ int pamg_implicit_step(pamg_handle* h, int ntime, int nits, double tol, int max_
 int pamg_trans_rec(pamg_handle* h, double CFL, int no_ele_row, int no_ele_col, double x_length, double y_length, double u_x,
                    double u_y, double time, int nits, int njac_its, int direct_solver, int volume_term, double* x_all,
                    double* tnew, int* ntime) {
+  ON_PART0(h);
   if (!h || !tnew || no_ele_row < 1 || no_ele_col < 1 || !(CFL > 0.0) || !(x_length > 0.0) || !(y_length > 0.0) || time < 0.0 ||
       nits < 1 || njac_its < 0)
     return PAMG_ERR_ARG;
@@ -1516,6 +1888,7 @@ int pamg_trans_rec(pamg_handle* h, double CFL, int no_ele_row, int no_ele_col, d
 
 int pamg_apply_local_minv(pamg_handle* h, int n, int batch, const double* M, const double* rhs, double* x,
                           double* Minv, int32_t* status) {
+  ON_PART0(h);
   if (!h || batch < 1 || !M || !(n == 3 || n == 4 || n == 6)) return PAMG_ERR_ARG;
   if (!rhs != !x) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
@@ -1551,20 +1924,30 @@ int output_fields(pamg_handle* h, double* x_all, double* analytical, double* err
 }  // namespace
 
 int pamg_output_fields(pamg_handle* h, double* x_all, double* analytical, double* error) {
+  if (h && h->is_root) {
+    size_t off = 0;
+    for (pamg_handle* q : h->parts) {
+      int rc = pamg_output_fields(q, x_all ? x_all + off * 6 : nullptr, analytical ? analytical + off * 3 : nullptr,
+                                  error ? error + off * 3 : nullptr);
+      if (rc) return gfail(h, q, rc);
+      off += (size_t)q->lev[0].nelem;
+    }
+    return PAMG_OK;
+  }
   if (!h || h->lev.empty() || (!x_all && !analytical && !error)) return PAMG_ERR_ARG;
   CK(cudaSetDevice(h->device));
   return output_fields(h, x_all, analytical, error);
 }
 
 int pamg_write_vtu(pamg_handle* h, const char* path, const char* solve_for, int binary) {
-  if (!h || h->lev.empty() || !path || !solve_for) return PAMG_ERR_ARG;
-  CK(cudaSetDevice(h->device));
-  LevelDev& L = h->lev[0];
-  const size_t n = (size_t)L.nelem;
-  std::vector<double> X(n * 6), T(n * 3), An(n * 3), Er(n * 3);
-  int rc = output_fields(h, X.data(), An.data(), Er.data());
+  if (!h || !path || !solve_for) return PAMG_ERR_ARG;
+  int64_t nd = 0;
+  int rc = pamg_ndof(h, 1, &nd);
   if (rc) return rc;
-  CK(cudaMemcpy(T.data(), tnew_ptr(L), n * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+  const size_t n = (size_t)nd / 3;
+  std::vector<double> X(n * 6), T(n * 3), An(n * 3), Er(n * 3);
+  if ((rc = pamg_output_fields(h, X.data(), An.data(), Er.data()))) return rc;
+  if ((rc = pamg_download_field(h, PAMG_TNEW, 1, T.data()))) return rc;
   FILE* f = fopen(path, binary ? "wb" : "w");
   if (!f) return fail(h, PAMG_ERR_IO, std::string("cannot open ") + path);
   const unsigned long long npts = 3ull * n;
@@ -1625,25 +2008,29 @@ int pamg_write_vtu(pamg_handle* h, const char* path, const char* solve_for, int 
 // ---- timing helpers --------------------------------------------------------------------------------
 int pamg_sync(pamg_handle* h) {
   if (!h) return PAMG_ERR_ARG;
+  FANOUT(h, q, pamg_sync(q));
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
-  if (h->up_stream) { CK(cudaStreamSynchronize(h->up_stream)); CK(cudaStreamSynchronize(h->down_stream)); h->pipe_calls = 0; }
-  if (h->p2p_ready) {      // a halo exchange that gave up waiting for a peer raised the error word instead of hanging
-    unsigned long long err = 0;
-    CK(cudaMemcpy(&err, h->p2p_sync + P2P_ERR, sizeof(err), cudaMemcpyDeviceToHost));
-    if (err) return fail(h, PAMG_ERR_CUDA, "halo exchange timed out waiting for a peer GPU");
-  }
-  return PAMG_OK;
+  if (h->up_stream) { CK(cudaStreamSynchronize(h->up_stream)); CK(cudaStreamSynchronize(h->down_stream)); h->pipe_calls = 0; h->last_out = nullptr; }
+  return p2p_check(h);   // a halo exchange that gave up waiting for a peer raised the error word instead of hanging
 }
 
 int pamg_event_record(pamg_handle* h, int slot) {
   if (!h || slot < 0 || slot >= 16) return PAMG_ERR_ARG;
+  FANOUT(h, q, pamg_event_record(q, slot));
+  CK(cudaSetDevice(h->device));
   CK(cudaEventRecord(h->ev[slot], h->stream));
   return PAMG_OK;
 }
 
 int pamg_event_elapsed_ms(pamg_handle* h, int a, int b, float* ms) {
   if (!h || !ms || a < 0 || a >= 16 || b < 0 || b >= 16) return PAMG_ERR_ARG;
+  if (h->is_root) {      // the slowest GPU of the group
+    *ms = 0.f;
+    for (pamg_handle* q : h->parts) { float m = 0.f; int rc = pamg_event_elapsed_ms(q, a, b, &m); if (rc) return gfail(h, q, rc); *ms = std::max(*ms, m); }
+    return PAMG_OK;
+  }
+  CK(cudaSetDevice(h->device));
   CK(cudaEventSynchronize(h->ev[b]));
   CK(cudaEventElapsedTime(ms, h->ev[a], h->ev[b]));
   return PAMG_OK;
@@ -1652,11 +2039,13 @@ int pamg_event_elapsed_ms(pamg_handle* h, int a, int b, float* ms) {
 int pamg_launch_count(const pamg_handle* h, int64_t* n) {
   if (!h || !n) return PAMG_ERR_ARG;
   *n = h->launches;
+  for (const pamg_handle* q : h->parts) *n += q->launches;
   return PAMG_OK;
 }
 
 int pamg_profile(pamg_handle* h, int on) {
   if (!h) return PAMG_ERR_ARG;
+  FANOUT(h, q, pamg_profile(q, on));
   CK(cudaSetDevice(h->device));
   if (on && h->pev.empty()) {
     h->pev.resize(2048);
@@ -1669,6 +2058,11 @@ int pamg_profile(pamg_handle* h, int on) {
 
 int pamg_profile_read(pamg_handle* h, double* total_ms, int* launches) {
   if (!h || !total_ms || !launches) return PAMG_ERR_ARG;
+  if (h->is_root) {
+    *total_ms = 0.0; *launches = 0;
+    for (pamg_handle* q : h->parts) { double t = 0; int l = 0; int rc = pamg_profile_read(q, &t, &l); if (rc) return gfail(h, q, rc); *total_ms += t; *launches += l; }
+    return PAMG_OK;
+  }
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
   double tot = 0.0;
@@ -1691,6 +2085,7 @@ int pamg_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? PAMG_OK : 
 
 int pamg_flush_l2(pamg_handle* h) {
   if (!h) return PAMG_ERR_ARG;
+  FANOUT(h, q, pamg_flush_l2(q));
   CK(cudaSetDevice(h->device));
   if (!h->scratch) {
     h->scratch_bytes = (size_t)256 << 20;

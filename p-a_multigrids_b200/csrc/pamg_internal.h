@@ -29,6 +29,10 @@ struct HaloPlan {
                                    //   < nstrips : local strip ; >= nstrips : send slot ; -1 : domain boundary
   std::vector<int32_t> rev;        // [U_local*3] 1: slot S-p+1, 0: slot p  (splitting.F90:1256-1391)
   std::vector<int32_t> hmap;       // [U_local*3] strip entry coincident with my face nodes: a | b<<2
+  std::vector<int32_t> nsrc;       // [U_local*3] where a sweep reads the exterior values of (u,mf) WITHOUT a strip: the neighbour
+                                   //   parent's boundary children in the start-of-sweep field.  -1: strip (domain boundary or a
+                                   //   face cut by the GPU partition); else hmap | rev_of_neighbour<<4 | (Nside-1)<<5 | q_local<<7
+  std::vector<int32_t> cut_lf;     // (u*3+mf) of the faces cut by the partition, in strip order
   struct Peer { int part; int nfaces; int strip_begin; int send_begin; };
   std::vector<Peer> peers;
   int nstrips = 0, nsend = 0;

@@ -36,16 +36,13 @@ struct ElemArgs {
   const double* pc;       // [U][NPC]
   const int32_t* strip_of;  // [U*3]
   const int32_t* hmap;      // [U*3]
-  double* ovl_next;         // strips of the NEXT sweep, written by the children on parent faces (nullptr: do not write)
-  const int32_t* dst_strip; // [U*3] strip (or send slot) my boundary children are copied to, -1 = domain boundary
-  const int32_t* rev;       // [U*3] slot reversal flag
+  const int32_t* nsrc;      // [U*3] strip-free source of the exterior values of (u, side), or nullptr: strips only (HaloPlan::nsrc)
   double* partial;        // residual: [nblocks][3] = sum r^2, max |r|, max r
   double omega;
   double rsign;
   long long nelem;        // U * C
   int s;                  // split of this level
   int colour;             // GS: 0 = down children, 1 = up children
-  int split_boundary;     // 1: the tile kernel leaves children on parent faces untouched, k_boundary_fix updates them
   int partial_off;        // first partial slot this launch writes (residual norms)
 };
 
@@ -140,47 +137,33 @@ __device__ __forceinline__ void elem_apply(const double* __restrict__ pc, bool u
   }
 }
 
-// halo strip entry of an up child on a parent face: mf = gmsh side (0..2), slot0 = 0-based strip position
-__device__ __forceinline__ void halo_pair(const ElemArgs& a, int u, int mf, int slot0, int S, double& va, double& vb) {
-  const int hm = __ldg(a.hmap + u * 3 + mf);
-  const double* e = a.ovl + ((size_t)__ldg(a.strip_of + u * 3 + mf) * S + slot0) * 3;
+// Exterior values of a parent face WITHOUT a halo strip.  update_overlaps (splitting.F90:1255-1391) copies the nodal values
+// of the neighbour parent's boundary children from the start-of-sweep field into my strip; a sweep that writes to another
+// buffer (Jacobi, Richardson, residual, the one-pass coloured GS) can read those same values straight from that field.
+// d = HaloPlan::nsrc (>= 0): nodes | reversal << 4 | (Nside-1) << 5 | neighbour parent << 7; p = my 0-based strip position.
+__device__ __forceinline__ void nbr_pair(const double* __restrict__ T, int d, int p, int s, double& va, double& vb) {
+  const int S = 1 << s, b = 2 << s;
+  const int m = (d & 16) ? (S - 1 - p) : p;              // the neighbour's own position along the shared edge
+  const int ns = (d >> 5) & 3;
+  // its boundary child there (surf_ele, splitting.F90:434-449), 0-based in memory order: side 1 = odd children of row 1,
+  // side 3 = first child of row m+1, side 2 = last child of row m+1; row m+1 starts at m (b - m)
+  const int e0 = (ns == 0) ? 2 * m : (m * (b - m) + (ns == 1 ? b - 2 - 2 * m : 0));
+  const size_t o = ((((size_t)(d >> 7)) << (2 * s)) + (size_t)e0) * 3;
+  va = __ldg(T + o + (d & 3)); vb = __ldg(T + o + ((d >> 2) & 3));
+}
+
+// exterior values of parent side mf at 0-based position p: neighbour field (d >= 0) or halo strip (Dirichlet data, faces cut by
+// the GPU partition, in-place sweeps)
+__device__ __forceinline__ void ext_pair(const ElemArgs& a, int d, int strip, int hm, int p, int S, double& va, double& vb) {
+  if (d >= 0) { nbr_pair(a.Tin, d, p, a.s, va, vb); return; }
+  const double* e = a.ovl + ((size_t)strip * S + p) * 3;
   va = __ldg(e + (hm & 3)); vb = __ldg(e + (hm >> 2));
 }
 
-// update_overlaps (splitting.F90:1255-1391) fused into the sweep: a child on parent face mf copies its NEW nodal
-// values into the neighbour parent's strip of the next sweep (double-buffered), so no halo kernel runs between
-// sweeps.  bmask has bit 0/1/2 set for child faces 1/2/3 on the parent boundary.
-__device__ __forceinline__ void strips_write(const ElemArgs& a, int u, int bmask, int r, int ipos, int S, double o1,
-                                             double o2, double o3) {
-  if (bmask & 1) {                      // child face 1 on parent side 1, position ipos/2+1
-    const int d = __ldg(a.dst_strip + u * 3 + 0);
-    if (d >= 0) {
-      const int p = ipos >> 1, slot = __ldg(a.rev + u * 3 + 0) ? (S - 1 - p) : p;
-      double* e = a.ovl_next + ((size_t)d * S + slot) * 3;
-      e[0] = o1; e[1] = o2; e[2] = o3;
-    }
-  }
-  if (bmask & 2) {                      // child face 2 on parent side 3, position irow
-    const int d = __ldg(a.dst_strip + u * 3 + 2);
-    if (d >= 0) {
-      const int slot = __ldg(a.rev + u * 3 + 2) ? (S - r) : (r - 1);
-      double* e = a.ovl_next + ((size_t)d * S + slot) * 3;
-      e[0] = o1; e[1] = o2; e[2] = o3;
-    }
-  }
-  if (bmask & 4) {                      // child face 3 on parent side 2, position irow
-    const int d = __ldg(a.dst_strip + u * 3 + 1);
-    if (d >= 0) {
-      const int slot = __ldg(a.rev + u * 3 + 1) ? (S - r) : (r - 1);
-      double* e = a.ovl_next + ((size_t)d * S + slot) * 3;
-      e[0] = o1; e[1] = o2; e[2] = o3;
-    }
-  }
-}
-
-// same with the strip index and node map already at hand (kept in shared memory by the tile kernel)
-__device__ __forceinline__ const double* halo_entry(const ElemArgs& a, int strip, int slot0, int S) {
-  return a.ovl + ((size_t)strip * S + slot0) * 3;
+// same with the per-parent tables still in global memory: mf = gmsh side (0..2), slot0 = 0-based strip position
+__device__ __forceinline__ void halo_pair(const ElemArgs& a, int u, int mf, int slot0, int S, double& va, double& vb) {
+  const int d = a.nsrc ? __ldg(a.nsrc + u * 3 + mf) : -1;
+  ext_pair(a, d, __ldg(a.strip_of + u * 3 + mf), __ldg(a.hmap + u * 3 + mf), slot0, S, va, vb);
 }
 
 // deterministic two-stage norm reduction: warp shuffle, then one partial per CTA
@@ -201,78 +184,6 @@ __device__ __forceinline__ void block_partial(double acc_sum, double acc_abs, do
     partial[(size_t)blockIdx.x * 3 + 1] = s1;
     partial[(size_t)blockIdx.x * 3 + 2] = s2;
   }
-}
-
-// ---- direct kernel: thread per child, 8-byte loads through L1 (used for the in-place coloured GS pass)
-template <int MODE, bool FACE>
-__global__ void __launch_bounds__(TPB) k_element(ElemArgs a) {
-  const int s = a.s;
-  const int twos = 2 * s;
-  const int b = 2 << s;
-  const int S = 1 << s;
-  const long long Cmask = (1ll << twos) - 1;
-  double acc_sum = 0.0, acc_abs = 0.0, acc_max = 0.0;
-
-  for (long long gid = (long long)blockIdx.x * TPB + threadIdx.x; gid < a.nelem; gid += (long long)gridDim.x * TPB) {
-    const int u = (int)(gid >> twos);
-    const int t = (int)(gid & Cmask);
-    int r, ipos, ele, len;
-    child_from_flat(t, s, r, ipos, ele, len);
-    const bool up = ipos & 1;
-    if (MODE == MODE_GS && (int)up != a.colour) continue;
-
-    const long long pbase = ((long long)u << twos);       // first child of the parent
-    const long long base = (pbase + ele - 1) * 3;
-    // read-only (non-coherent) path unless the pass updates the field in place (coloured GS)
-    auto ldT = [&](long long i) -> double { return MODE == MODE_GS ? a.Tin[i] : __ldg(a.Tin + i); };
-    const double T1 = ldT(base), T2 = ldT(base + 1), T3 = ldT(base + 2);
-    const double* __restrict__ pc = a.pc + (size_t)u * NPC;
-    FaceIn fi;
-    if (FACE) {
-      if (!up) {
-        // down child: f1 -> child above, f2 -> ele+1, f3 -> ele-1 (splitting.F90:766); never on a parent face
-        const long long o1 = (pbase + (ele + b - 2 * r) - 1) * 3;
-        const long long o2 = base + 3, o3 = base - 3;
-        fi.n1a = ldT(o1 + 2); fi.n1b = ldT(o1 + 0);   // my node 1 <-> its node 3, my node 3 <-> its node 1
-        fi.n2a = ldT(o2 + 1); fi.n2b = ldT(o2 + 2);   // my 3 <-> its 2, my 2 <-> its 3
-        fi.n3a = ldT(o3 + 0); fi.n3b = ldT(o3 + 1);   // my 2 <-> its 1, my 1 <-> its 2
-        fi.pen1 = __ldg(pc + PC_PENI + 0); fi.pen2 = __ldg(pc + PC_PENI + 1); fi.pen3 = __ldg(pc + PC_PENI + 2);
-      } else {
-        if (r > 1) {
-          const long long o1 = (pbase + (ele - b - 2 + 2 * r) - 1) * 3;
-          fi.n1a = ldT(o1 + 2); fi.n1b = ldT(o1 + 0);
-          fi.pen1 = __ldg(pc + PC_PENI + 0);
-        } else {  // parent face 1, slot ipos/2+1 (:629-631)
-          halo_pair(a, u, 0, ipos >> 1, S, fi.n1a, fi.n1b);
-          fi.pen1 = __ldg(pc + PC_PENX + 0);
-        }
-        if (ipos > 1) {
-          fi.n2a = ldT(base - 3 + 1); fi.n2b = ldT(base - 3 + 2);
-          fi.pen2 = __ldg(pc + PC_PENI + 1);
-        } else {  // parent face 3, slot irow (:632-634)
-          halo_pair(a, u, 2, r - 1, S, fi.n2a, fi.n2b);
-          fi.pen2 = __ldg(pc + PC_PENX + 1);
-        }
-        if (ipos < len) {
-          fi.n3a = ldT(base + 3 + 0); fi.n3b = ldT(base + 3 + 1);
-          fi.pen3 = __ldg(pc + PC_PENI + 2);
-        } else {  // parent face 2, slot irow (:635-637)
-          halo_pair(a, u, 1, r - 1, S, fi.n3a, fi.n3b);
-          fi.pen3 = __ldg(pc + PC_PENX + 2);
-        }
-      }
-    }
-    const double b1 = __ldg(a.rhs + base), b2 = __ldg(a.rhs + base + 1), b3 = __ldg(a.rhs + base + 2);
-    double o1, o2, o3;
-    elem_apply<MODE, FACE>(pc, up, T1, T2, T3, fi, b1, b2, b3, a.omega, a.rsign, o1, o2, o3);
-    a.Tout[base] = o1; a.Tout[base + 1] = o2; a.Tout[base + 2] = o3;
-    if (MODE == MODE_RESID) {
-      acc_sum += o1 * o1 + o2 * o2 + o3 * o3;
-      acc_abs = fmax(acc_abs, fmax(fabs(o1), fmax(fabs(o2), fabs(o3))));
-      acc_max = fmax(acc_max, fmax(o1, fmax(o2, o3)));
-    }
-  }
-  if (MODE == MODE_RESID) block_partial(acc_sum, acc_abs, acc_max, a.partial + (size_t)3 * a.partial_off);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -523,7 +434,7 @@ __global__ void __launch_bounds__(TPB, 3) k_element_tma(ElemArgs a) {
       // up children of row 1 sit on parent face 1 and read the halo strip instead
       const int nb = p.up ? (k - b - 2 + 2 * p.r) : (k + b - 2 * p.r);       // 0-based child index
       if (p.up && p.r == 1) {
-        if (!a.split_boundary) halo_pair(a, p.u, 0, p.ipos >> 1, S, p.va, p.vb);
+        halo_pair(a, p.u, 0, p.ipos >> 1, S, p.va, p.vb);
       } else {
         const unsigned o1 = ((unsigned)(g - k) + (unsigned)nb) * 3u;         // offsets in doubles fit 32 bits
         p.va = __ldg(a.Tin + o1 + 2); p.vb = __ldg(a.Tin + o1);
@@ -563,10 +474,10 @@ __global__ void __launch_bounds__(TPB, 3) k_element_tma(ElemArgs a) {
         fi.pen1 = P.pi1; fi.pen2 = P.pi2; fi.pen3 = P.pi3;
         // face 2 looks left for an up child and right for a down child, face 3 the other way (splitting.F90:749-769)
         bnd = cur.up && (cur.r == 1 || cur.ipos == 1 || cur.ipos == cur.len);   // child on a parent face (rare)
-        const int d = (bnd && a.split_boundary) ? 0 : (cur.up ? -3 : 3);
+        const int d = cur.up ? -3 : 3;
         fi.n2a = t[d + 1]; fi.n2b = t[d + 2];
         fi.n3a = t[-d]; fi.n3b = t[-d + 1];
-        if (bnd && !a.split_boundary) {
+        if (bnd) {
           interior = false;
           if (cur.r == 1) { fi.pen1 = P.px1; bmask |= 1; }
           if (cur.ipos == 1) { halo_pair(a, cur.u, 2, cur.r - 1, S, fi.n2a, fi.n2b); fi.pen2 = P.px2; bmask |= 2; }
@@ -584,12 +495,7 @@ __global__ void __launch_bounds__(TPB, 3) k_element_tma(ElemArgs a) {
       } else {
         elem_apply_regs<MODE, FACE>(P, cur.up, interior, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.omega, a.rsign, o1, o2, o3);
       }
-      if (bnd && a.split_boundary) {      // k_boundary_fix owns this child: pass it through (residual: excluded)
-        const bool res = MODE == MODE_RESID;
-        o1 = res ? 0.0 : T1; o2 = res ? 0.0 : T2; o3 = res ? 0.0 : T3;
-      }
       so[tid * 3] = o1; so[tid * 3 + 1] = o2; so[tid * 3 + 2] = o3;
-      if (MODE != MODE_RESID && bmask && a.ovl_next) strips_write(a, cur.u, bmask, cur.r, cur.ipos, S, o1, o2, o3);
       if (MODE == MODE_RESID) {
         acc_sum += o1 * o1 + o2 * o2 + o3 * o3;
         acc_abs = fmax(acc_abs, fmax(fabs(o1), fmax(fabs(o2), fabs(o3))));
@@ -633,7 +539,7 @@ __global__ void __launch_bounds__(TPB, 3) k_element_win(ElemArgs a) {
   uint64_t* barT = reinterpret_cast<uint64_t*>(sB + 3 * TPB * WIN_NB);
   uint64_t* barB = barT + WIN_NT;
   __shared__ __align__(16) double sPC[NPC];
-  __shared__ int sIdx[8];                                 // strip_of[0..2], hmap[4..6] of the loaded parent
+  __shared__ int sIdx[12];                                // strip_of[0..2], hmap[4..6], nsrc[8..10] of the loaded parent
   const int s = a.s, twos = 2 * s, b = 2 << s, S = 1 << s;
   const long long Cmask = (1ll << twos) - 1;
   const int tid = threadIdx.x;
@@ -679,14 +585,14 @@ __global__ void __launch_bounds__(TPB, 3) k_element_win(ElemArgs a) {
       const bool same = u == u_loaded;
       if (f1) {       // child face 1 on parent side 1, position ipos/2
         const int strip = same ? sIdx[0] : __ldg(a.strip_of + u * 3), hm = same ? sIdx[4] : __ldg(a.hmap + u * 3);
-        const double* e = a.ovl + ((size_t)strip * S + (p.ipos >> 1)) * 3;
-        p.h1a = __ldg(e + (hm & 3)); p.h1b = __ldg(e + (hm >> 2));
+        const int d = same ? sIdx[8] : (a.nsrc ? __ldg(a.nsrc + u * 3) : -1);
+        ext_pair(a, d, strip, hm, p.ipos >> 1, S, p.h1a, p.h1b);
       }
       if (side) {     // first child of a row: face 2 on parent side 3; last child: face 3 on parent side 2
         const int mf = (p.ipos == 1) ? 2 : 1;
         const int strip = same ? sIdx[mf] : __ldg(a.strip_of + u * 3 + mf), hm = same ? sIdx[4 + mf] : __ldg(a.hmap + u * 3 + mf);
-        const double* e = a.ovl + ((size_t)strip * S + (p.r - 1)) * 3;
-        p.h2a = __ldg(e + (hm & 3)); p.h2b = __ldg(e + (hm >> 2));
+        const int d = same ? sIdx[8 + mf] : (a.nsrc ? __ldg(a.nsrc + u * 3 + mf) : -1);
+        ext_pair(a, d, strip, hm, p.r - 1, S, p.h2a, p.h2b);
       }
     }
   };
@@ -706,6 +612,7 @@ __global__ void __launch_bounds__(TPB, 3) k_element_win(ElemArgs a) {
         if (tid < NPC) sPC[tid] = __ldg(a.pc + (size_t)u_tile * NPC + tid);
         else if (tid < NPC + 3) sIdx[tid - NPC] = __ldg(a.strip_of + u_tile * 3 + (tid - NPC));
         else if (tid < NPC + 6) sIdx[4 + tid - NPC - 3] = __ldg(a.hmap + u_tile * 3 + (tid - NPC - 3));
+        else if (tid < NPC + 9) sIdx[8 + tid - NPC - 6] = a.nsrc ? __ldg(a.nsrc + u_tile * 3 + (tid - NPC - 6)) : -1;
         __syncthreads();
         u_loaded = u_tile;
       }
@@ -801,7 +708,7 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
   uint64_t* barT = reinterpret_cast<uint64_t*>(sB + 3 * TPB * WIN_NB);
   uint64_t* barB = barT + WIN_NT;
   __shared__ __align__(16) double sPC2[2][NPC];
-  __shared__ int sIdx2[2][8];
+  __shared__ int sIdx2[2][12];
   __shared__ double shp[3][TPB / 32];
   const int s = a.s, twos = 2 * s, b = 2 << s, S = 1 << s;
   const long long Cmask = (1ll << twos) - 1;
@@ -831,7 +738,10 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
       const int u = (int)((tile * TPB) >> twos);
       if (u != u_loaded) {
         for (int i = lane; i < NPC; i += 32) sPC2[u & 1][i] = __ldg(a.pc + (size_t)u * NPC + i);
-        if (lane < 3) { sIdx2[u & 1][lane] = __ldg(a.strip_of + u * 3 + lane); sIdx2[u & 1][4 + lane] = __ldg(a.hmap + u * 3 + lane); }
+        if (lane < 3) {
+          sIdx2[u & 1][lane] = __ldg(a.strip_of + u * 3 + lane); sIdx2[u & 1][4 + lane] = __ldg(a.hmap + u * 3 + lane);
+          sIdx2[u & 1][8 + lane] = a.nsrc ? __ldg(a.nsrc + u * 3 + lane) : -1;
+        }
         u_loaded = u;
         __syncwarp();
       }
@@ -881,14 +791,14 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
         const int* ix = sIdx2[u & 1];
         if (f1) {
           const int strip = same ? ix[0] : __ldg(a.strip_of + u * 3), hm = same ? ix[4] : __ldg(a.hmap + u * 3);
-          const double* e = a.ovl + ((size_t)strip * S + (p.ipos >> 1)) * 3;
-          p.h1a = __ldg(e + (hm & 3)); p.h1b = __ldg(e + (hm >> 2));
+          const int d = same ? ix[8] : (a.nsrc ? __ldg(a.nsrc + u * 3) : -1);
+          ext_pair(a, d, strip, hm, p.ipos >> 1, S, p.h1a, p.h1b);
         }
         if (side) {
           const int mf = (p.ipos == 1) ? 2 : 1;
           const int strip = same ? ix[mf] : __ldg(a.strip_of + u * 3 + mf), hm = same ? ix[4 + mf] : __ldg(a.hmap + u * 3 + mf);
-          const double* e = a.ovl + ((size_t)strip * S + (p.r - 1)) * 3;
-          p.h2a = __ldg(e + (hm & 3)); p.h2b = __ldg(e + (hm >> 2));
+          const int d = same ? ix[8 + mf] : (a.nsrc ? __ldg(a.nsrc + u * 3 + mf) : -1);
+          ext_pair(a, d, strip, hm, p.r - 1, S, p.h2a, p.h2b);
         }
       }
     };
@@ -998,7 +908,7 @@ __global__ void __launch_bounds__(TPB, 3) k_gs_win(ElemArgs a) {
   uint64_t* barB = barT + WIN_NT;
   __shared__ __align__(16) double sPC[NPC];       // parent of the tile whose up children are relaxed
   __shared__ __align__(16) double sPD[16];        // folded "down" operator of the parent of tile t+2
-  __shared__ int sIdx[8];
+  __shared__ int sIdx[12];
   const int s = a.s, twos = 2 * s, b = 2 << s, S = 1 << s;
   const long long Cmask = (1ll << twos) - 1;
   const int tid = threadIdx.x;
@@ -1047,14 +957,14 @@ __global__ void __launch_bounds__(TPB, 3) k_gs_win(ElemArgs a) {
       const bool same = u == u_up;
       if (f1) {
         const int strip = same ? sIdx[0] : __ldg(a.strip_of + u * 3), hm = same ? sIdx[4] : __ldg(a.hmap + u * 3);
-        const double* e = a.ovl + ((size_t)strip * S + (p.ipos >> 1)) * 3;
-        p.h1a = __ldg(e + (hm & 3)); p.h1b = __ldg(e + (hm >> 2));
+        const int d = same ? sIdx[8] : (a.nsrc ? __ldg(a.nsrc + u * 3) : -1);
+        ext_pair(a, d, strip, hm, p.ipos >> 1, S, p.h1a, p.h1b);
       }
       if (side) {
         const int mf = (p.ipos == 1) ? 2 : 1;
         const int strip = same ? sIdx[mf] : __ldg(a.strip_of + u * 3 + mf), hm = same ? sIdx[4 + mf] : __ldg(a.hmap + u * 3 + mf);
-        const double* e = a.ovl + ((size_t)strip * S + (p.r - 1)) * 3;
-        p.h2a = __ldg(e + (hm & 3)); p.h2b = __ldg(e + (hm >> 2));
+        const int d = same ? sIdx[8 + mf] : (a.nsrc ? __ldg(a.nsrc + u * 3 + mf) : -1);
+        ext_pair(a, d, strip, hm, p.r - 1, S, p.h2a, p.h2b);
       }
     }
   };
@@ -1078,6 +988,7 @@ __global__ void __launch_bounds__(TPB, 3) k_gs_win(ElemArgs a) {
           if (tid < NPC) sPC[tid] = __ldg(a.pc + (size_t)uu * NPC + tid);
           else if (tid < NPC + 3) sIdx[tid - NPC] = __ldg(a.strip_of + uu * 3 + (tid - NPC));
           else if (tid < NPC + 6) sIdx[4 + tid - NPC - 3] = __ldg(a.hmap + uu * 3 + (tid - NPC - 3));
+          else if (tid < NPC + 9) sIdx[8 + tid - NPC - 6] = a.nsrc ? __ldg(a.nsrc + uu * 3 + (tid - NPC - 6)) : -1;
         }
         if (ud != u_dn && tid >= 128 && tid < 144) sPD[tid - 128] = __ldg(a.pc + (size_t)ud * NPC + PC_FOLD + 16 + (tid - 128));
         __syncthreads();
@@ -1172,7 +1083,7 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
   uint64_t* barT = reinterpret_cast<uint64_t*>(sB + 3 * TPB * WIN_NB);
   uint64_t* barB = barT + WIN_NT;
   __shared__ __align__(16) double sPC2[2][NPC];
-  __shared__ int sIdx2[2][8];
+  __shared__ int sIdx2[2][12];
   __shared__ __align__(8) uint64_t doneD[4];
   const int s = a.s, twos = 2 * s, b = 2 << s, S = 1 << s;
   const long long Cmask = (1ll << twos) - 1;
@@ -1205,7 +1116,10 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
       const int u = (int)((tile * TPB) >> twos);
       if (u != u_loaded) {
         for (int i = lane; i < NPC; i += 32) sPC2[u & 1][i] = __ldg(a.pc + (size_t)u * NPC + i);
-        if (lane < 3) { sIdx2[u & 1][lane] = __ldg(a.strip_of + u * 3 + lane); sIdx2[u & 1][4 + lane] = __ldg(a.hmap + u * 3 + lane); }
+        if (lane < 3) {
+          sIdx2[u & 1][lane] = __ldg(a.strip_of + u * 3 + lane); sIdx2[u & 1][4 + lane] = __ldg(a.hmap + u * 3 + lane);
+          sIdx2[u & 1][8 + lane] = a.nsrc ? __ldg(a.nsrc + u * 3 + lane) : -1;
+        }
         u_loaded = u;
         __syncwarp();
       }
@@ -1252,15 +1166,11 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
       if (f1 | side) {
         const int* ix = sIdx2[(tile >> pshift) & 1];
         if (f1) {
-          const int strip = ix[0], hm = ix[4];
-          const double* e = a.ovl + ((size_t)strip * S + (p.ipos >> 1)) * 3;
-          p.h1a = __ldg(e + (hm & 3)); p.h1b = __ldg(e + (hm >> 2));
+          ext_pair(a, ix[8], ix[0], ix[4], p.ipos >> 1, S, p.h1a, p.h1b);
         }
         if (side) {
           const int mf = (p.ipos == 1) ? 2 : 1;
-          const int strip = ix[mf], hm = ix[4 + mf];
-          const double* e = a.ovl + ((size_t)strip * S + (p.r - 1)) * 3;
-          p.h2a = __ldg(e + (hm & 3)); p.h2b = __ldg(e + (hm >> 2));
+          ext_pair(a, ix[8 + mf], ix[mf], ix[4 + mf], p.r - 1, S, p.h2a, p.h2b);
         }
       }
     };
@@ -1395,7 +1305,6 @@ __device__ __forceinline__ void child_update(const ElemArgs& a, int u, int r, in
     elem_apply_regs<MODE, FACE>(P, up, interior, T1, T2, T3, fi, b1, b2, b3, a.omega, a.rsign, o1v, o2v, o3v);
   }
   a.Tout[base] = o1v; a.Tout[base + 1] = o2v; a.Tout[base + 2] = o3v;
-  if (MODE != MODE_RESID && bmask && a.ovl_next) strips_write(a, u, bmask, r, ipos, S, o1v, o2v, o3v);
   if (MODE == MODE_RESID) {
     acc_sum += o1v * o1v + o2v * o2v + o3v * o3v;
     acc_abs = fmax(acc_abs, fmax(fabs(o1v), fmax(fabs(o2v), fabs(o3v))));
@@ -1415,31 +1324,6 @@ __global__ void __launch_bounds__(TPB) k_element_direct2(ElemArgs a) {
     child_from_flat((int)(gid & Cmask), s, r, ipos, ele, len);
     if (MODE == MODE_GS && (ipos & 1) != a.colour) continue;
     child_update<MODE, FACE>(a, u, r, ipos, ele, len, acc_sum, acc_abs, acc_max);
-  }
-  if (MODE == MODE_RESID) block_partial(acc_sum, acc_abs, acc_max, a.partial + (size_t)3 * a.partial_off);
-}
-
-// Children on parent faces (3 * 2^s of the 4^s children of a parent) handled apart from the tile kernel: their
-// halo-strip look-ups and boundary coefficients are a chain of dependent loads that would hold up a whole tile
-// at its barrier.  One thread per (parent, side, position); children on two sides are taken by the lower side.
-template <int MODE>
-__global__ void __launch_bounds__(TPB) k_boundary_fix(ElemArgs a, int U) {
-  const int S = 1 << a.s, b = 2 << a.s;
-  const long long n = (long long)U * 3 * S;
-  double acc_sum = 0.0, acc_abs = 0.0, acc_max = 0.0;
-  for (long long tid = (long long)blockIdx.x * TPB + threadIdx.x; tid < n; tid += (long long)gridDim.x * TPB) {
-    const int i = (int)(tid & (S - 1));
-    const int lf = (int)(tid >> a.s);
-    const int u = lf / 3, mf = lf - 3 * u;
-    const int pos = i + 1;
-    int r, ipos;
-    if (mf == 0) { r = 1; ipos = 2 * pos - 1; }
-    else if (mf == 2) { r = pos; ipos = 1; }
-    else { r = pos; ipos = b + 1 - 2 * pos; }
-    if ((mf == 1 && r == 1) || (mf == 2 && (r == 1 || r == S))) continue;   // also on a lower-numbered side
-    const int len = b + 1 - 2 * r;
-    const int ele = 1 + (r - 1) * (b + 1 - r) + ipos - 1;
-    child_update<MODE, true>(a, u, r, ipos, ele, len, acc_sum, acc_abs, acc_max);
   }
   if (MODE == MODE_RESID) block_partial(acc_sum, acc_abs, acc_max, a.partial + (size_t)3 * a.partial_off);
 }
@@ -1477,9 +1361,9 @@ __global__ void __launch_bounds__(1024) k_reduce_partials(const double* partial,
 // NVLink one-way trip.  The staging buffer is double-buffered by the parity of the exchange number (a sender can
 // only be one exchange ahead of a receiver because it needs the receiver's data to get any further), and the
 // exchange number lives in device memory so that a captured CUDA graph replays correctly.  Polling has a time-out
-// that raises sync[P2P_ERR] instead of hanging the GPU.
+// that raises the error word (host-mapped memory, checked at every host synchronisation point) instead of hanging the GPU.
 constexpr int P2P_MAXP = 16;
-enum { P2P_EPOCH = 0, P2P_COUNT = 1, P2P_ERR = 2, P2P_WORDS = 8 };
+enum { P2P_EPOCH = 0, P2P_COUNT = 1, P2P_WORDS = 8 };
 struct P2PArgs {
   const double* send;                 // my send slots of this level (contiguous, grouped per peer)
   int send_base;                      // first send slot (in strips) of peer 0, relative to the send-slot space
@@ -1491,7 +1375,8 @@ struct P2PArgs {
   long long roff[P2P_MAXP + 1];       // prefix offsets (doubles) of the per-peer receive ranges
   uint4* stage;                       // my staging buffer (parity 0)
   long long stage_words;              // words per parity
-  unsigned long long* sync;           // exchange number, block counter, error word
+  unsigned long long* sync;           // exchange number, block counter
+  unsigned long long* err;            // error word (mapped host memory): a poll that timed out raises it instead of hanging
   int npeers;
   unsigned long long timeout_ns;
 };
@@ -1516,7 +1401,7 @@ __device__ __forceinline__ void p2p_receive(const P2PArgs& a, unsigned long long
   const unsigned e = (unsigned)e64;
   const long long par = (long long)(e64 & 1) * a.stage_words;
   const long long nr = a.roff[a.npeers];
-  volatile unsigned long long* err = a.sync + P2P_ERR;
+  volatile unsigned long long* err = a.err;
   for (long long i = (long long)blockIdx.x * TPB + tid; i < nr; i += (long long)gridDim.x * TPB) {
     int p = 0;
     while (i >= a.roff[p + 1]) ++p;
@@ -1543,16 +1428,60 @@ __device__ __forceinline__ void p2p_receive(const P2PArgs& a, unsigned long long
   if (s_last && tid == 0) { a.sync[P2P_COUNT] = 0; *(volatile unsigned long long*)(a.sync + P2P_EPOCH) = e64; __threadfence(); }
 }
 
-// stand-alone exchange of already packed send slots
-__global__ void __launch_bounds__(TPB) k_p2p_exchange(P2PArgs a) {
-  const unsigned long long e64 = *(volatile unsigned long long*)(a.sync + P2P_EPOCH) + 1;   // this exchange
-  const long long ns = a.soff[a.npeers];
-  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < ns; i += (long long)gridDim.x * TPB) {
-    int p = 0;
-    while (i >= a.soff[p + 1]) ++p;
-    p2p_put(a, (unsigned)e64, p, i - a.soff[p], a.send[i]);
+// ------------------------------------------------------------------------------------------------
+// Device-initiated block transfer between the GPUs of one process (coarse-level agglomeration): the sender
+// stores a contiguous range straight into the receiver's memory over NVLink, fences at system scope, and the last block
+// publishes the transfer number in a flag word on the receiver; the receiver's stream runs k_wait_flags before it touches
+// the data.  Both counters live in device memory, so captured CUDA graphs replay correctly, and there is no host
+// synchronisation, event or library call between the GPUs.
+struct PushArgs {
+  const double* src; double* dst;          // dst: peer memory
+  long long n;
+  unsigned long long* counter;             // local: blocks done
+  unsigned long long* epoch;               // local: transfers sent on this channel so far
+  unsigned long long* flag;                // peer: transfer number of the last complete transfer
+};
+
+__global__ void __launch_bounds__(TPB) k_push(PushArgs a) {
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < a.n; i += (long long)gridDim.x * TPB) a.dst[i] = a.src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(a.counter, 1ull) == (unsigned long long)gridDim.x - 1) {
+      __threadfence_system();
+      const unsigned long long e = *a.epoch + 1;
+      *a.epoch = e; *a.counter = 0;
+      __threadfence_system();
+      *(volatile unsigned long long*)a.flag = e;
+    }
   }
-  p2p_receive(a, e64);
+}
+
+struct WaitArgs {
+  unsigned long long* flags;               // local: one word per sender
+  unsigned long long* expect;              // local: transfers received per sender so far
+  unsigned long long* err;                 // mapped host memory
+  unsigned long long timeout_ns;
+  unsigned senders;                        // bit p set: wait for sender p
+};
+
+__global__ void k_wait_flags(WaitArgs a) {
+  const int p = threadIdx.x;
+  if (p < 32 && ((a.senders >> p) & 1u)) {
+    const unsigned long long want = a.expect[p] + 1;
+    a.expect[p] = want;
+    unsigned long long t0 = 0;
+    for (unsigned spins = 0;; ++spins) {
+      if (*(volatile unsigned long long*)(a.flags + p) >= want) break;
+      if ((spins & 1023u) == 1023u) {
+        if (*(volatile unsigned long long*)a.err) break;
+        const unsigned long long t = p2p_now();
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > a.timeout_ns) { *(volatile unsigned long long*)a.err = 2; break; }
+      }
+    }
+  }
+  __threadfence_system();
 }
 
 struct HaloArgs {
@@ -1563,9 +1492,13 @@ struct HaloArgs {
   const int32_t* dst_strip; const int32_t* rev; const int32_t* strip_of;
   double bc_scale;
   int U, s, with_old;
-  int what;   // 0 everything (update_overlaps as written); 1 Dirichlet faces only; 2 faces cut by the GPU partition only;
-              // 3 all faces between parents (no Dirichlet data)
+  int what;   // 0 everything (update_overlaps as written); 1 Dirichlet faces only; 2 faces cut by the GPU partition only
+              // (one thread per position of the faces listed in cut_lf); 3 all faces between parents (no Dirichlet data)
   int nstrips;
+  const int32_t* cut_lf; int ncut;         // what == 2: (u*3+mf) of the cut faces
+  // Dirichlet data of domain-boundary faces per (u, side): kind 0 = sin(x+y) (splitting.F90:1246-1252), 1 = the constant
+  // bc_val (update_overlaps' t_bc argument, :1210), 2 = open face, no data; nullptr = kind 0 everywhere
+  const int32_t* bc_kind; const double* bc_val;
 };
 
 __device__ __forceinline__ void child_nodes(const double* __restrict__ xg, int s, int r, int ipos, double x[3][2]) {
@@ -1587,12 +1520,12 @@ __device__ __forceinline__ void child_nodes(const double* __restrict__ xg, int s
 
 __global__ void __launch_bounds__(TPB) k_halo(HaloArgs a) {
   const int S = 1 << a.s, b = 2 << a.s;
-  const long long n = (long long)a.U * 3 * S;
+  const long long n = (a.what == 2 ? (long long)a.ncut : (long long)a.U * 3) * S;
   unsigned long long e64 = 0;
   if (a.x.npeers > 0) e64 = *(volatile unsigned long long*)(a.x.sync + P2P_EPOCH) + 1;
   for (long long tid = (long long)blockIdx.x * TPB + threadIdx.x; tid < n; tid += (long long)gridDim.x * TPB) {
     const int i = (int)(tid & (S - 1));           // position - 1
-    const int lf = (int)(tid >> a.s);             // u*3 + mf
+    const int lf = (a.what == 2) ? __ldg(a.cut_lf + (tid >> a.s)) : (int)(tid >> a.s);   // u*3 + mf
     const int u = lf / 3, mf = lf - 3 * u;
     const int pos = i + 1;
     int r, ipos;
@@ -1606,12 +1539,15 @@ __global__ void __launch_bounds__(TPB) k_halo(HaloArgs a) {
     if (a.what == 2 && dst < a.nstrips) continue;
     if (a.what == 3 && dst < 0) continue;
     if (dst < 0) {
-      // Dirichlet data sin(x+y) at the two face nodes (:1246-1252,1287-1293,1344-1350)
+      // Dirichlet data at the two face nodes (:1246-1252,1287-1293,1344-1350): sin(x+y), or the constant t_bc of the face
+      const int kind = a.bc_kind ? __ldg(a.bc_kind + lf) : 0;
+      if (kind == 2) continue;                    // open face: no data (its penalty coefficient is zero)
       double x[3][2];
       child_nodes(a.xg + (size_t)u * 6, a.s, r, ipos, x);
       const int na = (mf == 2) ? 1 : 0, nb = (mf == 0) ? 2 : (mf == 1 ? 1 : 2);
-      const double ta = a.bc_scale * sin(x[na][0] + x[na][1]);
-      const double tb = a.bc_scale * sin(x[nb][0] + x[nb][1]);
+      double ta = a.bc_scale * sin(x[na][0] + x[na][1]);
+      double tb = a.bc_scale * sin(x[nb][0] + x[nb][1]);
+      if (kind == 1) ta = tb = a.bc_scale * __ldg(a.bc_val + lf);
       const size_t o = (size_t)__ldg(a.strip_of + lf) * S3 + (size_t)i * 3;
       a.ovl[o + na] = ta; a.ovl[o + nb] = tb;
       if (a.with_old) { a.ovl_old[o + na] = ta; a.ovl_old[o + nb] = tb; }

@@ -91,6 +91,8 @@ int build_halo_plan(int U_global, const double* X, const int32_t* neig, const in
     plan.strip_of[cuts[i].lf] = next++;
   }
   plan.nsend = next;
+  plan.cut_lf.resize(cuts.size());
+  for (size_t i = 0; i < cuts.size(); ++i) plan.cut_lf[i] = cuts[i].lf;
   for (int lf = 0; lf < UL * 3; ++lf)
     if (plan.strip_of[lf] < 0) plan.strip_of[lf] = next++;
   plan.nstrips = next;
@@ -103,6 +105,19 @@ int build_halo_plan(int U_global, const double* X, const int32_t* neig, const in
       const int ns = fneig[(size_t)g * 3 + mf];
       if (owner(q - 1) == my_part) plan.dst_strip[lf] = plan.strip_of[(q - 1 - first) * 3 + (ns - 1)];
       else plan.dst_strip[lf] = plan.nstrips + plan.strip_of[lf];  // send slot i <-> my cut strip i
+    }
+  // strip-free read of a local neighbour: slot p of my strip is written by the neighbour's child at position p or S-1-p
+  // according to the NEIGHBOUR's reversal flag (splitting.F90:1256-1391), entries in its local node order
+  plan.nsrc.assign((size_t)UL * 3, -1);
+  for (int u = 0; u < UL; ++u)
+    for (int mf = 0; mf < 3; ++mf) {
+      const int g = first + u, lf = u * 3 + mf;
+      const int q = neig[(size_t)g * 3 + mf];
+      if (q == 0 || owner(q - 1) != my_part) continue;
+      const int ns = fneig[(size_t)g * 3 + mf];
+      const int ql = q - 1 - first;
+      if (ql >= (1 << 24)) continue;                       // does not fit the descriptor: keep the strip
+      plan.nsrc[lf] = plan.hmap[lf] | (plan.rev[ql * 3 + (ns - 1)] << 4) | ((ns - 1) << 5) | (ql << 7);
     }
   return PAMG_OK;
 }

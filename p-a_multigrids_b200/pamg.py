@@ -69,6 +69,8 @@ def lib():
         "pamg_mesh_get": (ci, [vp, vp, vp, vp, vp, vp]),
         "pamg_mesh_free": (None, [vp]),
         "pamg_create": (ci, [C.POINTER(Params), ci, pvp]),
+        "pamg_create_multi": (ci, [C.POINTER(Params), ci, vp, pvp]),
+        "pamg_set_boundary_data": (ci, [vp, ci, _i32, vp]),
         "pamg_destroy": (None, [vp]),
         "pamg_last_error": (C.c_char_p, [vp]),
         "pamg_set_parents": (ci, [vp, ci, _f64, _i32, _i32, _i32]),
@@ -91,6 +93,7 @@ def lib():
         "pamg_literal_timestep": (ci, [vp, ci, ci, ci]),
         "pamg_timestep_host": (ci, [vp, vp, vp, ci, cd, pint, pdbl]),
         "pamg_smooth_host": (ci, [vp, ci, ci, vp, vp]),
+        "pamg_smoother_host": (ci, [vp, ci, ci, vp, vp]),
         "pamg_halo_plan": (ci, [ci, _f64, _i32, _i32, _i32, ci, ci, _i32, ci, _i32, _i32, _i32, _i32, _i32, _i32]),
         "pamg_comm_unique_id": (ci, [C.c_char_p]),
         "pamg_comm_init": (ci, [vp, C.c_char_p, ci, ci]),
@@ -148,7 +151,9 @@ def default_params(literal_head=False, **kw):
 
 
 def _ptr(a):
-    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+    if a is None or isinstance(a, (C.c_void_p, int)):
+        return a
+    return a.ctypes.data_as(C.c_void_p)
 
 
 # ------------------------------------------------------------------------------ mesh (host)
@@ -230,15 +235,27 @@ class SemiImplicitIterative:
     """GPU implementation of Semi_implicit_iterative's contained procedures
     (transport_tri_semi.F90:14-891).  Method names follow the reference."""
 
-    def __init__(self, params, mesh, device=0, nparts=1, part_first=None, my_part=0):
+    def __init__(self, params, mesh, device=0, nparts=1, part_first=None, my_part=0, devices=None, bc_kind=None,
+                 bc_value=None):
+        """devices: list of CUDA devices driven by THIS process (pamg_create_multi; the mesh is partitioned inside the
+        library); nparts / part_first / my_part: one process per GPU (torchrun), this handle owns block my_part.
+        bc_kind / bc_value: (U,3) Dirichlet data of the domain-boundary faces (pamg_set_boundary_data)."""
         self.L = lib()
         self.params = params
         self.mesh = mesh
         h = C.c_void_p()
-        rc = self.L.pamg_create(C.byref(params), device, C.byref(h))
+        if devices is not None:
+            dev = np.ascontiguousarray(devices, np.int32)
+            rc = self.L.pamg_create_multi(C.byref(params), len(dev), _ptr(dev), C.byref(h))
+        else:
+            rc = self.L.pamg_create(C.byref(params), device, C.byref(h))
         if rc != OK:
             raise PamgError(rc, "pamg_create failed (no CUDA device? there is no CPU fallback)")
         self.h = h
+        if bc_kind is not None:
+            kind = np.ascontiguousarray(bc_kind, np.int32).reshape(-1)
+            val = None if bc_value is None else np.ascontiguousarray(bc_value, np.float64).reshape(-1)
+            self._ck(self.L.pamg_set_boundary_data(h, mesh.U, kind, _ptr(val)))
         if nparts == 1:
             self._ck(self.L.pamg_set_parents(h, mesh.U, mesh.X, mesh.neig, mesh.fneig, mesh.dir))
             self.U = mesh.U
@@ -391,6 +408,10 @@ class SemiImplicitIterative:
 
     def download_ptr(self, field, level, host_ptr):
         self._ck(self.L.pamg_download_field(self.h, field, level, host_ptr))
+
+    def smoother_host(self, solver, nsweeps, in_ptr, out_ptr):
+        """Blocking smoother call on HOST fields (the reference-facing form): out is valid on return."""
+        self._ck(self.L.pamg_smoother_host(self.h, solver, nsweeps, in_ptr, out_ptr))
 
     def smooth_host(self, solver, nsweeps, in_ptr, out_ptr):
         """Smoother on a HOST field (pointers, e.g. PinnedBuffer.ptr); asynchronous: call sync() before reading out."""

@@ -60,6 +60,7 @@ def lib():
     L.orc_semi_create.argtypes = [C.POINTER(OrcParams), C.c_int, f64p, i32p, i32p, i32p]
     L.orc_semi_create.restype = C.c_void_p
     L.orc_semi_destroy.argtypes = [C.c_void_p]
+    L.orc_semi_set_boundary.argtypes = [C.c_void_p, i32p, f64p]
     L.orc_semi_field.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.orc_semi_field.restype = C.POINTER(C.c_double)
     L.orc_semi_overlap.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -150,6 +151,10 @@ class Semi:
         if getattr(self, "h", None):
             self.L.orc_semi_destroy(self.h)
             self.h = None
+
+    def set_boundary(self, kind, value):
+        self.L.orc_semi_set_boundary(self.h, np.ascontiguousarray(kind, np.int32).reshape(-1),
+                                     np.ascontiguousarray(value, np.float64).reshape(-1))
 
     def split(self, level):
         return self.params.n_split - level + 1

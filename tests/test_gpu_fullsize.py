@@ -1,7 +1,10 @@
-"""Full-size checks (BASELINE configs c4 = 4^11 and c5 = 4^12 elements) through size-independent properties:
-the oracle cannot run these sizes in seconds, so parity is carried by (i) affinity of the sweep, (ii) agreement of
-the three independently written kernel families on the same input, (iii) restriction/prolongation identities and
-(iv) mesh-independent V-cycle convergence with the cycle count the oracle measures on small meshes."""
+"""Full-size checks at the BASELINE sizes c4 = 4^11 and c5 = 4^12 elements (256 parents x n_split 7 / 8).
+
+Direct parity with the CPU oracle on the SAME seeded inputs (the oracle, OpenMP over parents, needs about a second per
+sweep at c5): one Jacobi sweep, one residual evaluation, one two-colour Gauss-Seidel sweep (rel-L2 <= 1e-12 each, the
+north-star tolerance) and the residual history of the first V-cycles (rtol 1e-6).  Size-independent properties follow:
+affinity of the sweep, transfer identities, mesh-independent convergence, and the fall-back kernel families against the
+oracle-checked default."""
 import os
 import subprocess
 import sys
@@ -9,16 +12,24 @@ import sys
 import numpy as np
 import pytest
 
+import oracle_api as orc
 from helpers import ROOT, rel_l2
 from pamg_pkg import pamg
 
 pytestmark = pytest.mark.gpu
 
+U_VEL = (0.9, 0.3)
+
 
 def big_solver(n, **kw):
     mesh = pamg.Mesh.synthetic(4, 1)           # 256 parents
-    p = pamg.default_params(n_split=n, multi_levels=n, u_x=0.9, u_y=0.3, **kw)
+    p = pamg.default_params(n_split=n, multi_levels=n, u_x=U_VEL[0], u_y=U_VEL[1], **kw)
     return pamg.SemiImplicitIterative(p, mesh), mesh
+
+
+def big_oracle(n, mesh, dt):
+    orc.lib().orc_semi_set_threads(os.cpu_count() or 1)
+    return orc.Semi(orc.intended_params(n, n, dt=dt, u=U_VEL), mesh.X, mesh.neig, mesh.fneig, mesh.dir)
 
 
 def rnd(shape, seed):
@@ -26,7 +37,52 @@ def rnd(shape, seed):
 
 
 @pytest.mark.parametrize("n", [7, 8])
-def test_sweep_is_affine_and_kernel_families_agree(n):
+def test_oracle_parity_at_full_size(n):
+    """c4 (n=7, 4 194 304 elements) and c5 (n=8, 16 777 216 elements): the CUDA path against the oracle, same inputs."""
+    g, mesh = big_solver(n)
+    o = big_oracle(n, mesh, g.params.dt)
+    shape = g.shape(1)
+    T, Told = rnd(shape, 20221), rnd(shape, 20222)
+    try:
+        # ---- one Jacobi sweep (smoother :543-722 with solve_Jacobi :491-497)
+        o.field(orc.TNONLIN)[:] = T; o.field(orc.TOLD)[:] = Told
+        g.upload(pamg.TNONLIN, 1, T); g.upload(pamg.TOLD, 1, Told)
+        o.smooth(1, 1, 1); g.smoother(1, pamg.JACOBI, 1)
+        got = g.download(pamg.TNONLIN, 1)
+        assert rel_l2(got, o.field(orc.TNONLIN)) <= 1e-12
+        # ---- one residual evaluation (get_residual :725-873) of the swept field, norms by warp-shuffle reduction
+        o.field(orc.TNEW)[:] = o.field(orc.TNONLIN); o.update_overlaps(1)
+        l2o, lio = o.residual(1)
+        g.upload(pamg.TNEW, 1, got); g.update_overlaps(1)
+        l2g, lig = g.get_residual(1)
+        assert rel_l2(g.download(pamg.RES, 1), o.field(orc.RES)) <= 1e-12
+        assert abs(l2g - l2o) <= 1e-12 * l2o and abs(lig - lio) <= 1e-12 * lio
+        # ---- one two-colour Gauss-Seidel sweep (solve_Gauss_Seidel :501-507 in the GPU ordering, oracle solver 4)
+        o.field(orc.TNONLIN)[:] = T
+        g.upload(pamg.TNONLIN, 1, T)
+        o.smooth(1, 4, 1); g.smoother(1, pamg.GAUSS_SEIDEL, 1)
+        assert rel_l2(g.download(pamg.TNONLIN, 1), o.field(orc.TNONLIN)) <= 1e-12
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("n,solver,cycles", [(7, pamg.GAUSS_SEIDEL, 3), (7, pamg.JACOBI, 2), (8, pamg.GAUSS_SEIDEL, 2)])
+def test_vcycle_history_matches_the_oracle_at_full_size(n, solver, cycles):
+    """||r||_2 after each of the first V-cycles (T0 = 0, Dirichlet sin(x+y)): the same numbers as the oracle's cycle."""
+    g, mesh = big_solver(n)
+    o = big_oracle(n, mesh, g.params.dt)
+    try:
+        _, ho = o.vcycle_solve(solver=4 if solver == pamg.GAUSS_SEIDEL else 1, max_cycles=cycles, tol=1e-30)
+        _, hg = g.vcycle_solve(solver=solver, max_cycles=cycles, tol=1e-30)
+        assert len(ho) == len(hg) == cycles + 1
+        np.testing.assert_allclose(hg, ho, rtol=1e-6)
+        assert hg[-1] < hg[0] * 0.6 ** cycles
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("n", [7, 8])
+def test_sweep_is_affine_and_fallback_families_agree(n):
     g, _ = big_solver(n)
     shape = g.shape(1)
     T1, T2, Told = rnd(shape, 1), rnd(shape, 2), rnd(shape, 3)
@@ -41,19 +97,23 @@ def test_sweep_is_affine_and_kernel_families_agree(n):
         a = 0.3
         s1, s2, s12 = sweep(T1, solver), sweep(T2, solver), sweep(a * T1 + (1 - a) * T2, solver)
         assert rel_l2(s12, a * s1 + (1 - a) * s2) <= 1e-13          # S(aT1+(1-a)T2) = aS(T1)+(1-a)S(T2)
-    ref = sweep(T1, pamg.JACOBI)
+    ref = sweep(T1, pamg.JACOBI)       # the default kernel, checked against the oracle above
     g.close()
-    # the same sweep through the other kernel families (separate processes: the choice is read at handle creation)
+    # the same sweep through the families that serve the other level sizes, and with halo strips instead of
+    # neighbour-field reads (separate processes: the choice is read at handle creation)
     code = ("import sys,numpy as np;sys.path.insert(0,'%s');from pamg_pkg import pamg;"
             "m=pamg.Mesh.synthetic(4,1);p=pamg.default_params(n_split=%d,multi_levels=%d,u_x=0.9,u_y=0.3);"
             "g=pamg.SemiImplicitIterative(p,m);r=lambda s:np.random.Generator(np.random.MT19937(s)).random(g.shape(1));"
             "g.upload(pamg.TOLD,1,r(3));g.upload(pamg.TNONLIN,1,r(1));g.smoother(1,pamg.JACOBI,1);"
             "np.save(sys.argv[1],g.download(pamg.TNONLIN,1))") % (os.path.join(ROOT, "tests"), n, n)
-    for fam in ("direct", "direct2", "stream", "tma1d", "win:barrier"):
+    for fam in ("direct2", "tma1d", "win:barrier", "win:producer:strips"):
         out = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"pamg_{fam.replace(':', '_')}_{n}.npy")
-        env = dict(os.environ, PAMG_KERNEL=fam.split(":")[0])
-        if ":" in fam:
-            env["PAMG_WIN"] = fam.split(":")[1]
+        parts = fam.split(":")
+        env = dict(os.environ, PAMG_KERNEL=parts[0])
+        if len(parts) > 1:
+            env["PAMG_WIN"] = parts[1]
+        if len(parts) > 2:
+            env["PAMG_HALO"] = parts[2]
         r = subprocess.run([sys.executable, "-c", code, out], env=env,
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
@@ -99,10 +159,10 @@ def test_vcycle_converges_mesh_independently(n, solver, expect):
     assert rel_l2(after, before) <= 1e-7
 
 
-def test_manufactured_solution_error_is_bounded():
-    """get_error (transport_tri_semi.F90:531-540): |T - sin(x+y)| of the steady solve stays at the level the oracle
-    measures for this (penalty-only) discretisation, DESIGN.md section 1."""
-    import oracle_api as orc
+def test_manufactured_solution_error_equals_the_oracle():
+    """get_error (transport_tri_semi.F90:531-540): max |T - sin(x+y)| of the converged steady solve.  The reference's
+    penalty-only diffusion is not a consistent scheme, so the error does not vanish; the device must
+    land on the value the ORACLE's converged solve gives (within 1 %) and on its field."""
     mesh = pamg.Mesh.synthetic(1, 2)
     n = 5
     p = pamg.default_params(n_split=n, multi_levels=n, dt=1e6)
@@ -110,12 +170,16 @@ def test_manufactured_solution_error_is_bounded():
     cyc, hist = g.vcycle_solve(solver=pamg.GAUSS_SEIDEL, ncoarse=30, max_cycles=80, tol=1e-10)
     assert hist[-1] / hist[0] <= 1e-10
     T = g.download(pamg.TNONLIN, 1)
-    x = np.zeros((3, 2)); err = 0.0
-    for u in range(mesh.U):
-        for e in range(1, 4 ** n + 1, 7):
-            orc.lib().orc_get_splitting(np.ascontiguousarray(mesh.X[u]), n, e, x)
-            err = max(err, float(np.abs(T[u, e - 1] - np.sin(x[:, 0] + x[:, 1])).max()))
-    assert err < 0.2
+    _, an, er = g.output_fields()
+    err_g = float(er.max())
+    orc.lib().orc_semi_set_threads(os.cpu_count() or 1)
+    o = orc.Semi(orc.intended_params(n, n, dt=1e6), mesh.X, mesh.neig, mesh.fneig, mesh.dir)
+    o.vcycle_solve(solver=4, ncoarse=30, max_cycles=80, tol=1e-10)
+    To = o.field(orc.TNONLIN)
+    err_o = float(np.abs(To - an).max())
+    assert rel_l2(T, To) <= 1e-8
+    assert abs(err_g - err_o) <= 0.01 * err_o
+    assert 0.05 < err_o < 0.2        # the level DESIGN.md quotes for this discretisation (about 0.12)
 
 
 def test_unstr_implicit_full_size_properties():
