@@ -98,8 +98,12 @@ struct pamg_handle {
   double* stage = nullptr; size_t stage_bytes = 0;      // pinned staging for host-buffer entry points
   int kernel_mode = 4;  // 4 window kernel (default; 1-D TMA tile ring, all neighbours from shared memory), 1 pipelined 1-D TMA tiles,
                         // 3 branch-free direct; PAMG_KERNEL=win|tma1d|direct2 (A/B and the families used on small / deep levels)
-  bool direct_halo = true;  // out-of-place sweeps read the exterior values of faces between local parents straight from the
-                            // neighbour parent's field, no k_halo launch per sweep (PAMG_HALO=strips restores the strips)
+  // where a sweep takes the exterior values of faces between local parents from (PAMG_HALO=strips|direct|fused):
+  //   0 strips: one k_halo launch per sweep fills the halo strips (update_overlaps as a kernel of its own);
+  //   1 direct: out-of-place sweeps read the neighbour parent's boundary children straight from the start-of-sweep field;
+  //   2 fused (default): the producer warp of the window kernels writes the strips of the NEXT sweep from the finished
+  //     tiles, so no halo kernel runs between sweeps; kernels without a producer warp (small levels) read direct
+  int halo_mode = 2;
   // resident CTAs per SM of the shared-memory kernels on THIS device ([face_terms]); set once per handle in configure_kernels
   struct KernelCfg { int win2[2] = {0, 0}, win[2] = {0, 0}, tma[2] = {0, 0}, gs2 = 0, gs = 0, halo = 0; bool done = false; } kc;
   bool capturing = false;   // stream capture in progress: no synchronisation, no per-launch error polling
@@ -470,7 +474,7 @@ int launch_halo(pamg_handle* h, int level, int what) {
 int ensure_strips(pamg_handle* h, int level, bool all = true) {
   LevelDev& L = h->lev[level - 1];
   if (!h->p.face_terms) return PAMG_OK;
-  if (all || !h->direct_halo) return L.strips_valid ? PAMG_OK : launch_halo(h, level, 3);
+  if ((all || h->halo_mode == 0) && !L.strips_valid) return launch_halo(h, level, 3);
   return L.cut_valid ? PAMG_OK : launch_halo(h, level, 2);
 }
 
@@ -525,12 +529,22 @@ int configure_kernels(pamg_handle* h) {
   return PAMG_OK;
 }
 
+// whether a sweep of this solver on this level runs a window kernel with a producer warp (which can write the next strips)
+bool producer_kernel(const pamg_handle* h, const LevelDev& L, bool gs) {
+  if (!(h->kernel_mode == 4 && h->win_producer && L.s >= 6 && L.s <= 8)) return false;
+  return !gs || (h->gs_fused && h->p.face_terms);
+}
+
+// use_strips: every strip of the level holds the start-of-sweep values (else: neighbour-field reads where possible);
+// write_next: the kernel's producer warp writes the strips of the next sweep into the other strip buffer
 template <int MODE>
-int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout, int colour, int grid) {
+int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout, int colour, int grid, bool use_strips,
+                   bool write_next = false) {
   ElemArgs a;
   a.Tin = Tin; a.Tout = Tout; a.rhs = L.rhs; a.ovl = L.ovlb[L.ovl_cur]; a.pc = L.pc; a.strip_of = h->strip_of; a.hmap = h->hmap;
-  // an in-place pass (the two-pass coloured GS) must see start-of-sweep values across parent faces: strips only
-  a.nsrc = (h->direct_halo && Tin != Tout) ? h->nsrc : nullptr;
+  // (an in-place pass - the two-pass coloured GS - must see start-of-sweep values across parent faces: strips only)
+  a.nsrc = (use_strips || Tin == Tout) ? nullptr : h->nsrc;
+  a.ovl_next = write_next ? L.ovlb[L.ovl_cur ^ 1] : nullptr; a.dst_strip = h->dst_strip; a.rev = h->rev; a.nstrips = h->plan.nstrips;
   a.partial = h->partial; a.omega = h->p.omega; a.rsign = (double)h->p.residual_sign; a.nelem = L.nelem; a.s = L.s;
   a.colour = colour; a.partial_off = 0;
   const int f = h->p.face_terms ? 1 : 0;
@@ -572,10 +586,11 @@ bool gs_fused_ok(const pamg_handle* h, const LevelDev& L) {
   return h->gs_fused && h->kernel_mode == 4 && h->p.face_terms && L.C >= TPB && L.s <= 8;
 }
 
-int launch_gs_fused(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout) {
+int launch_gs_fused(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout, bool use_strips, bool write_next) {
   ElemArgs a;
   a.Tin = Tin; a.Tout = Tout; a.rhs = L.rhs; a.ovl = L.ovlb[L.ovl_cur]; a.pc = L.pc; a.strip_of = h->strip_of; a.hmap = h->hmap;
-  a.nsrc = h->direct_halo ? h->nsrc : nullptr;
+  a.nsrc = use_strips ? nullptr : h->nsrc;
+  a.ovl_next = write_next ? L.ovlb[L.ovl_cur ^ 1] : nullptr; a.dst_strip = h->dst_strip; a.rev = h->rev; a.nstrips = h->plan.nstrips;
   a.partial = h->partial; a.omega = h->p.omega; a.rsign = (double)h->p.residual_sign; a.nelem = L.nelem; a.s = L.s;
   a.colour = 1; a.partial_off = 0;
   const bool producer = h->win_producer && L.s >= 6;
@@ -597,16 +612,19 @@ int do_smooth(pamg_handle* h, int level, int solver, int nsweeps) {
   const int grid = grid_for(h, L.nelem);
   if (solver < 1 || solver > 4) return fail(h, PAMG_ERR_ARG, "solver must be 1 (Jacobi), 2 (Richardson) or 3 (Gauss-Seidel)");
   for (int sw = 0; sw < nsweeps; ++sw) {
-    // tnew <- tnew_nonlin (:550) is the buffer swap below; halo from it (:555).  Out-of-place sweeps read the exterior
-    // values of faces between local parents straight from tnew (the values update_overlaps would copy), so only faces
-    // cut by the GPU partition need their strips refreshed; an in-place sweep needs every strip.
+    // tnew <- tnew_nonlin (:550) is the buffer swap below; halo from it (:555): either the strips hold it (written by
+    // the previous sweep's producer warps or by k_halo), or the sweep reads its neighbours' field directly.  Faces cut
+    // by the GPU partition always go through their strips (the exchange step).
     L.tnew_alias = true;
-    const bool in_place = (solver == 3 || solver == 4) && !gs_fused_ok(h, L);
-    int rc = ensure_strips(h, level, in_place);
+    const bool gs = solver == 3 || solver == 4;
+    const bool in_place = gs && !gs_fused_ok(h, L);
+    const bool fusedk = h->halo_mode == 2 && h->p.face_terms && !in_place && producer_kernel(h, L, gs);
+    const bool use_strips = in_place || fusedk || h->halo_mode == 0;
+    int rc = ensure_strips(h, level, use_strips);
     if (rc) return rc;
     if (solver == 1 || solver == 2) {
-      rc = (solver == 1) ? launch_element<MODE_JACOBI>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid)
-                         : launch_element<MODE_RICH>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid);
+      rc = (solver == 1) ? launch_element<MODE_JACOBI>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid, use_strips, fusedk)
+                         : launch_element<MODE_RICH>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid, use_strips, fusedk);
       if (rc) return rc;
       L.cur ^= 1;
       L.tnew_alias = false;  // the old buffer now holds the start-of-sweep field = tracer%tnew
@@ -614,18 +632,23 @@ int do_smooth(pamg_handle* h, int level, int solver, int nsweeps) {
       // two-colour ordering of the reference's Gauss-Seidel sweep (all down children, then all up children; values across
       // parent faces stay lagged exactly as at :647-655), both colours in one pass over memory, written to the other
       // buffer (which then holds tracer%tnew, as for Jacobi)
-      rc = launch_gs_fused(h, L, L.T[L.cur], L.T[L.cur ^ 1]);
+      rc = launch_gs_fused(h, L, L.T[L.cur], L.T[L.cur ^ 1], use_strips, fusedk);
       if (rc) return rc;
       L.cur ^= 1;
       L.tnew_alias = false;
     } else {
       if (sw == nsweeps - 1 && h->p.keep_tnew_gs) { rc = materialise_tnew(h, L); if (rc) return rc; }  // keep tracer%tnew observable
-      rc = launch_element<MODE_GS>(h, L, L.T[L.cur], L.T[L.cur], 0, grid);
+      rc = launch_element<MODE_GS>(h, L, L.T[L.cur], L.T[L.cur], 0, grid, true);
       if (rc) return rc;
-      rc = launch_element<MODE_GS>(h, L, L.T[L.cur], L.T[L.cur], 1, grid);   // all children on parent faces are "up"
+      rc = launch_element<MODE_GS>(h, L, L.T[L.cur], L.T[L.cur], 1, grid, true);   // all children on parent faces are "up"
       if (rc) return rc;
     }
-    L.strips_valid = false; L.cut_valid = false;
+    if (fusedk) {
+      L.ovl_cur ^= 1;                        // the producer warps wrote the strips of the new iterate
+      L.strips_valid = true; L.cut_valid = h->plan.peers.empty();
+    } else {
+      L.strips_valid = false; L.cut_valid = false;
+    }
   }
   return PAMG_OK;
 }
@@ -637,9 +660,10 @@ int do_residual(pamg_handle* h, int level, double* l2, double* linf, double* sma
   if (2 * grid > h->npartial) return fail(h, PAMG_ERR_STATE, "partial buffer too small");
   // exterior values of faces between local parents come straight from TNEW (what update_overlaps copies); the strips of
   // faces cut by the GPU partition are refreshed here if something touched the field since the last exchange
-  int rc = ensure_strips(h, level, false);
+  const bool use_strips = L.strips_valid || h->halo_mode == 0;
+  int rc = ensure_strips(h, level, use_strips);
   if (rc) return rc;
-  rc = launch_element<MODE_RESID>(h, L, tnew_ptr(L), L.res, 0, grid);
+  rc = launch_element<MODE_RESID>(h, L, tnew_ptr(L), L.res, 0, grid, use_strips);
   if (rc) return rc;
   if (l2 || linf || smax) {
     k_reduce_partials<<<1, 1024, 0, h->stream>>>(h->partial, h->last_partials, h->out3);
@@ -1012,7 +1036,9 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
     const char* pt = getenv("PAMG_P2P_TIMEOUT_S");
     if (pt && atof(pt) > 0.0) h->p2p_timeout_ns = (unsigned long long)(atof(pt) * 1e9);
     const char* hl = getenv("PAMG_HALO");
-    if (hl && !strcmp(hl, "strips")) h->direct_halo = false;
+    if (hl && !strcmp(hl, "strips")) h->halo_mode = 0;
+    if (hl && !strcmp(hl, "direct")) h->halo_mode = 1;
+    if (hl && !strcmp(hl, "fused")) h->halo_mode = 2;
     const char* gr = getenv("PAMG_GRAPH");
     if (gr && gr[0] == '0') h->use_graph = false;
     const char* gn = getenv("PAMG_GRAPH_NCCL");
@@ -1230,7 +1256,7 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
         ap.multi_levels = h->p.multi_levels - lvl + 1;
         pamg_handle* g = new pamg_handle();
         g->p = ap; g->device = h->device; g->nsm = h->nsm; g->kernel_mode = h->kernel_mode; g->gs_tma = h->gs_tma; g->gs_fused = h->gs_fused; g->win_producer = h->win_producer;
-        g->stream = h->stream; g->shared_stream = true; g->level_offset = lvl - 1; g->direct_halo = h->direct_halo;
+        g->stream = h->stream; g->shared_stream = true; g->level_offset = lvl - 1; g->halo_mode = h->halo_mode;
         g->bc_kind_h = h->bc_kind_h; g->bc_val_h = h->bc_val_h;
         h->agg = g;
         for (auto& ev : g->ev) CK(cudaEventCreate(&ev));

@@ -201,3 +201,49 @@ class Semi:
 
     def literal_timestep(self, solver=3, n_multigrid=2, n_smooth=4):
         self.L.orc_semi_literal_timestep(self.h, solver, n_multigrid, n_smooth)
+
+
+def synthetic_mesh(kp, G=1, tmpdir=None):
+    """The synthetic input of SURVEY 8(d) built WITHOUT the product: G right super-triangles (G/2 unit squares in a strip), each
+    split kp times with the reference's get_splitting numbering (Msh2Tri.F90:69-107) into 4**kp parents; neighbours by the
+    oracle's restatement of ReadMSH / CheckNeig (all-pairs, fine for a few thousand parents).  Same vertices and parent
+    order as pamg_mesh_synthetic.  Returns dict(X, neig, fneig, dir, region)."""
+    import tempfile
+    per = 4 ** kp
+    X = np.zeros((G * per, 3, 2))
+    out = np.zeros(6)
+    L = lib()
+    for g in range(G):
+        sq = float(g // 2)
+        if g % 2 == 0:
+            P = np.array([sq + 1, 0, sq, 1, sq, 0], np.float64)          # X1, X2, X3
+        else:
+            P = np.array([sq, 1, sq + 1, 0, sq + 1, 1], np.float64)
+        for e in range(1, per + 1):
+            L.orc_get_splitting(P, kp, e, out)
+            X[g * per + e - 1] = out.reshape(3, 2)
+    ids, nodes, tris = {}, [], []
+    for t in X:
+        row = []
+        for p in t:
+            key = (float(p[0]), float(p[1]))
+            if key not in ids:
+                ids[key] = len(nodes) + 1
+                nodes.append(key)
+            row.append(ids[key])
+        tris.append(row)
+    fd, path = tempfile.mkstemp(suffix=".msh", dir=tmpdir)
+    with os.fdopen(fd, "w") as f:
+        f.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n%d\n" % len(nodes))
+        for i, (x, y) in enumerate(nodes):
+            f.write("%d %.17g %.17g 0\n" % (i + 1, x, y))
+        f.write("$EndNodes\n$Elements\n%d\n" % len(tris))
+        for i, t in enumerate(tris):
+            f.write("%d 2 2 1 1 %d %d %d\n" % (i + 1, t[0], t[1], t[2]))
+        f.write("$EndElements\n")
+    try:
+        m = read_msh(path, max_tri=len(tris) + 8)
+    finally:
+        os.unlink(path)
+    m["fneig"], _ = neig_data(m["neig"], m["dir"])
+    return m

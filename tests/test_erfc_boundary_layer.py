@@ -130,7 +130,7 @@ def test_boundary_data_kinds_sweep_parity(tmp_path):
     o.field(orc.TNEW)[:] = o.field(orc.TNONLIN); o.update_overlaps(1); l2o, _ = o.residual(1)
     g.copy(1, pamg.TNEW, pamg.TNONLIN); g.update_overlaps(1); l2g, _ = g.get_residual(1)
     assert rel_l2(g.download(pamg.RES, 1), o.field(orc.RES)) <= 1e-12 and abs(l2g - l2o) <= 1e-12 * l2o
-    assert rel_l2(g.overlap(1), o.overlap(1)) <= 1e-15
+    assert rel_l2(g.overlap(1), o.overlap(1)) <= 1e-13
     # an open face with inflow is refused (the kernels take the exterior trace from the strip)
     bad = kind.copy(); bad[kind == 1] = 2
     with pytest.raises(pamg.PamgError):

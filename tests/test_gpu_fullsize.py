@@ -106,7 +106,7 @@ def test_sweep_is_affine_and_fallback_families_agree(n):
             "g=pamg.SemiImplicitIterative(p,m);r=lambda s:np.random.Generator(np.random.MT19937(s)).random(g.shape(1));"
             "g.upload(pamg.TOLD,1,r(3));g.upload(pamg.TNONLIN,1,r(1));g.smoother(1,pamg.JACOBI,1);"
             "np.save(sys.argv[1],g.download(pamg.TNONLIN,1))") % (os.path.join(ROOT, "tests"), n, n)
-    for fam in ("direct2", "tma1d", "win:barrier", "win:producer:strips"):
+    for fam in ("direct2", "tma1d", "win:barrier", "win:producer:strips", "win:producer:direct"):
         out = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"pamg_{fam.replace(':', '_')}_{n}.npy")
         parts = fam.split(":")
         env = dict(os.environ, PAMG_KERNEL=parts[0])
