@@ -436,7 +436,7 @@ def main():
 
     # unstructured front-ends on one GPU: explicit DG step, block-CSR assembly, SpMV, BiCGStab
     if rank == 0 and not args.no_extras and not single:
-        kpu = int(os.environ.get("PAMG_BENCH_UNSTR_KP", "12"))      # 4^12 = 16.8M triangles: beyond L2
+        kpu = int(os.environ.get("PAMG_BENCH_UNSTR_KP", "11"))      # 4^11 = 4.2M triangles (1.2 GB of matrix blocks): beyond L2
         um = pkg.Mesh.synthetic(kpu, 1)
         g.set_unstructured(um)
         T0 = np.random.Generator(np.random.MT19937(7)).random((um.U, 3))

@@ -179,12 +179,22 @@ int pamg_explicit_step(pamg_handle* h, double dt, double u_x, double u_y, double
  * (mass/dt - stiffness + outflow flux), block 1+f = inflow flux of gmsh face f+1 in the neighbour's columns.
  * Needs pamg_set_unstructured first.  The time loop works on the field of pamg_unstr_upload / _download. */
 int pamg_implicit_assemble(pamg_handle* h, double dt, double u_x, double u_y, int use_dir);
+/* the same with the diffusion operator of the iterative path (get_A_x, transport_tri_semi.F90:412-448, face block on): the
+ * volume block k A grad(phi_i).grad(phi_j) (ShapFun_unstruc.F90:324-335) on the diagonal and the penalty term
+ * (k/dx) int sn_i (T - T2) (matrices.F90:84-115) on the own and the neighbour's columns, dx = centroid distance (centre ->
+ * edge midpoint on the domain boundary, where the exterior trace is right-hand-side data).  The reference's implicit drivers
+ * compute add_diffusion_vol and drop it (transport_tri_semi.F90:1627); this is the intended operator. */
+int pamg_implicit_assemble_diffusion(pamg_handle* h, double dt, double u_x, double u_y, double k, int use_dir);
 int pamg_implicit_get_bsr(pamg_handle* h, double* val /* [E][4][9] or NULL */, int32_t* col /* [E][4], 0-based, -1 = none, or NULL */);
 int pamg_implicit_apply(pamg_handle* h, const double* x /* host (3,E) */, double* y /* host: (lhs + flux) x */);
 /* ntime x nits passes of: told = tnew ; solve (lhs + flux) tnew = (M/dt) told by block-Jacobi-preconditioned
  * BiCGStab to ||r|| <= tol ||rhs|| (at most max_iters iterations per solve).  iters_total / relres (worst solve)
  * may be NULL. */
 int pamg_implicit_step(pamg_handle* h, int ntime, int nits, double tol, int max_iters, int* iters_total, double* relres);
+/* measurement aids: average device time (ms) of `reps` block-CSR products; host synchronisations of the Krylov solves so far
+ * (the scalars of the recurrence live on the device: one look at the convergence flag per 16 iterations) */
+int pamg_implicit_spmv_time(pamg_handle* h, int reps, float* ms);
+int pamg_implicit_host_syncs(pamg_handle* h, int64_t* n);
 
 /* ---- Petrov-Galerkin residual-based stabilisation (transport_tri_unstr.F90:239-267,278; semi_str_implicit.F90:290-318) --
  * diff_coe(gi) and stab(iloc,jloc) of every element from tnew = the field of pamg_unstr_upload and the given told.

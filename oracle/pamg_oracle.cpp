@@ -1208,6 +1208,16 @@ void orc_unstr_explicit(int E, const double* X, const int32_t* neig, const int32
 // into dense row-major matrices A (lhs + flux) and Mdt (mass/dt) of size (3E)^2 - small meshes only.
 void orc_unstr_implicit_assemble(int E, const double* X, const int32_t* neig, const int32_t* fneig, double u_x,
                                  double u_y, double dt, int use_dir, double* A, double* Mdt) {
+  orc_unstr_implicit_assemble_diff(E, X, neig, fneig, u_x, u_y, 0.0, dt, use_dir, A, Mdt);
+}
+
+// the same with the diffusion operator of the iterative path added (INTENDED: the implicit drivers call add_diffusion_vol and
+// drop its result, transport_tri_semi.F90:1627): volume term k nx.nx detwei (diff_vol_stcl, ShapFun_unstruc.F90:324-335) and the
+// face penalty (k/dx) sum_g sn_i (T - T2) sdetwei (matrices.F90:113-115, get_diff_surf_stencl transport_tri_semi.F90:468-477)
+// with dx = centroid distance to the neighbour, or centre -> edge midpoint on the domain boundary (matrices.F90:84-110), where
+// the exterior trace is Dirichlet data (right-hand side) and only the own part enters the matrix.
+void orc_unstr_implicit_assemble_diff(int E, const double* X, const int32_t* neig, const int32_t* fneig, double u_x,
+                                      double u_y, double k, double dt, int use_dir, double* A, double* Mdt) {
   const size_t N = (size_t)3 * E;
   std::fill(A, A + N * N, 0.0);
   std::fill(Mdt, Mdt + N * N, 0.0);
@@ -1227,8 +1237,11 @@ void orc_unstr_implicit_assemble(int E, const double* X, const int32_t* neig, co
           mass += TB.n[g][i] * TB.n[g][j] * detwei[g] / dt;
           for (int d = 0; d < 2; ++d) stiff += nx[g][d][i] * ugi[g][d] * detwei[g] * TB.n[g][j];
         }
+        double dvol = 0;
+        for (int g = 0; g < 3; ++g)
+          for (int d = 0; d < 2; ++d) dvol += k * nx[g][d][i] * detwei[g] * nx[g][d][j];
         Mdt[(size_t)(3 * e + i) * N + 3 * e + j] += mass;
-        A[(size_t)(3 * e + i) * N + 3 * e + j] += mass - stiff;
+        A[(size_t)(3 * e + i) * N + 3 * e + j] += mass - stiff + dvol;
       }
     for (int f = 1; f <= 3; ++f) {
       const int npos = neig[e * 3 + f - 1], nside = fneig[e * 3 + f - 1];
@@ -1264,6 +1277,28 @@ void orc_unstr_implicit_assemble(int E, const double* X, const int32_t* neig, co
                     ((1.0 - income[s]) * sn[s][j] * us[s][d] + income[s] * sn2[s][j] * us2[s][d]);
           A[(size_t)(3 * e + i) * N + 3 * (target - 1) + j] += fl;
         }
+      if (k != 0.0) {
+        const double cx = (x[0][0] + x[1][0] + x[2][0]) / 3, cy = (x[0][1] + x[1][1] + x[2][1]) / 3;
+        double dx;
+        if (npos != 0) {
+          const double (*xn)[2] = reinterpret_cast<const double (*)[2]>(&X[(size_t)(npos - 1) * 6]);
+          const double qx = (xn[0][0] + xn[1][0] + xn[2][0]) / 3, qy = (xn[0][1] + xn[1][1] + xn[2][1]) / 3;
+          dx = std::sqrt((cx - qx) * (cx - qx) + (cy - qy) * (cy - qy));
+        } else {
+          const double mx = (x[l1][0] + x[l2][0]) / 2, my = (x[l1][1] + x[l2][1]) / 2;
+          dx = std::sqrt((cx - mx) * (cx - mx) + (cy - my) * (cy - my));
+        }
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 3; ++j) {
+            double my_d = 0, ng_d = 0;
+            for (int s = 0; s < 2; ++s) {
+              my_d += (k / dx) * sn[s][i] * sn[s][j] * sdet[s];
+              ng_d += (k / dx) * sn[s][i] * sn2[s][j] * sdet[s];
+            }
+            A[(size_t)(3 * e + i) * N + 3 * e + j] += my_d;
+            if (npos != 0) A[(size_t)(3 * e + i) * N + 3 * (npos - 1) + j] -= ng_d;
+          }
+      }
     }
   }
 }

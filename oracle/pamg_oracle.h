@@ -102,6 +102,9 @@ void orc_unstr_explicit(int E, const double* X, const int32_t* neig, const int32
 /* ---- unstructured implicit assembly + dense solve (transport_tri_unstr.F90:214-387); dense (3E)^2, small E only */
 void orc_unstr_implicit_assemble(int E, const double* X, const int32_t* neig, const int32_t* fneig, double u_x,
                                  double u_y, double dt, int use_dir, double* A, double* Mdt);
+/* the same + the diffusion operator of the iterative path (volume term and face penalty, get_A_x transport_tri_semi.F90:412-448) */
+void orc_unstr_implicit_assemble_diff(int E, const double* X, const int32_t* neig, const int32_t* fneig, double u_x,
+                                      double u_y, double k, double dt, int use_dir, double* A, double* Mdt);
 int orc_unstr_implicit(int E, const double* X, const int32_t* neig, const int32_t* fneig, double u_x, double u_y,
                        double dt, int ntime, int nits, int use_dir, double* tnew);
 

@@ -104,6 +104,7 @@ struct pamg_handle {
   //   2 fused (default): the producer warp of the window kernels writes the strips of the NEXT sweep from the finished
   //     tiles, so no halo kernel runs between sweeps; kernels without a producer warp (small levels) read direct
   int halo_mode = 2;
+  long long debug_gap_ns = 0;   // PAMG_DEBUG_GAP_NS (measurement aid): a one-warp kernel that idles this long before every sweep
   // resident CTAs per SM of the shared-memory kernels on THIS device ([face_terms]); set once per handle in configure_kernels
   struct KernelCfg { int win2[2] = {0, 0}, win[2] = {0, 0}, tma[2] = {0, 0}, gs2 = 0, gs = 0, halo = 0; bool done = false; } kc;
   bool capturing = false;   // stream capture in progress: no synchronisation, no per-launch error polling
@@ -135,6 +136,7 @@ struct pamg_handle {
   // unstructured
   UnstrDev un;
   int un_use_dir = 0;
+  long long un_host_syncs = 0;
   // pamg_smooth_host: copies on their own streams so that the upload of call k+1 overlaps the download of call k
   cudaStream_t up_stream = nullptr, down_stream = nullptr;
   cudaEvent_t ev_up = nullptr, ev_comp = nullptr, ev_down[2] = {nullptr, nullptr};
@@ -616,6 +618,7 @@ int do_smooth(pamg_handle* h, int level, int solver, int nsweeps) {
     // the previous sweep's producer warps or by k_halo), or the sweep reads its neighbours' field directly.  Faces cut
     // by the GPU partition always go through their strips (the exchange step).
     L.tnew_alias = true;
+    if (h->debug_gap_ns > 0) { k_spin<<<1, 32, 0, h->stream>>>(h->debug_gap_ns); }   // experiment: idle time between sweeps
     const bool gs = solver == 3 || solver == 4;
     const bool in_place = gs && !gs_fused_ok(h, L);
     const bool fusedk = h->halo_mode == 2 && h->p.face_terms && !in_place && producer_kernel(h, L, gs);
@@ -1035,6 +1038,8 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
     if (pp && pp[0] == '0') h->p2p_enabled = false;
     const char* pt = getenv("PAMG_P2P_TIMEOUT_S");
     if (pt && atof(pt) > 0.0) h->p2p_timeout_ns = (unsigned long long)(atof(pt) * 1e9);
+    const char* dg = getenv("PAMG_DEBUG_GAP_NS");
+    if (dg) h->debug_gap_ns = atoll(dg);
     const char* hl = getenv("PAMG_HALO");
     if (hl && !strcmp(hl, "strips")) h->halo_mode = 0;
     if (hl && !strcmp(hl, "direct")) h->halo_mode = 1;
@@ -1803,18 +1808,22 @@ int pamg_explicit_step(pamg_handle* h, double dt, double u_x, double u_y, double
 }
 
 // ---- unstructured implicit operator in block-CSR (unstr_implicit, transport_tri_unstr.F90:214-387) --------
-int pamg_implicit_assemble(pamg_handle* h, double dt, double u_x, double u_y, int use_dir) {
+int pamg_implicit_assemble_diffusion(pamg_handle* h, double dt, double u_x, double u_y, double k, int use_dir) {
   ON_PART0(h);
-  if (!h || h->un.E < 1 || !(dt > 0.0)) return PAMG_ERR_ARG;
+  if (!h || h->un.E < 1 || !(dt > 0.0) || k < 0.0) return PAMG_ERR_ARG;
   if (use_dir < 0) use_dir = h->un_use_dir;   // internal: re-assemble with the previous pairing rule
   h->un_use_dir = use_dir; h->un.with_stab = false;
   CK(cudaSetDevice(h->device));
   std::string e;
   long long nl = 0;
-  int rc = implicit_assemble(h->un, dt, u_x, u_y, use_dir, h->nsm, h->stream, nl, e);
+  int rc = implicit_assemble(h->un, dt, u_x, u_y, k, use_dir, h->nsm, h->stream, nl, e);
   h->launches += nl;
   if (rc) return fail(h, rc, e);
   return PAMG_OK;
+}
+
+int pamg_implicit_assemble(pamg_handle* h, double dt, double u_x, double u_y, int use_dir) {
+  return pamg_implicit_assemble_diffusion(h, dt, u_x, u_y, 0.0, use_dir);
 }
 
 int pamg_implicit_get_bsr(pamg_handle* h, double* val, int32_t* col) {
@@ -1822,9 +1831,26 @@ int pamg_implicit_get_bsr(pamg_handle* h, double* val, int32_t* col) {
   if (!h || h->un.E < 1 || (!val && !col)) return PAMG_ERR_ARG;
   if (!h->un.assembled) return fail(h, PAMG_ERR_STATE, "pamg_implicit_assemble has not been called");
   CK(cudaSetDevice(h->device));
+  // the blocks live as 36 + 4 planes on the device: back to the [E][4][9] / [E][4] order of the ABI
   const size_t E = (size_t)h->un.E;
-  if (val) CK(cudaMemcpyAsync(val, h->un.bsr_val, E * 36 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  if (col) CK(cudaMemcpyAsync(col, h->un.bsr_col, E * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  std::string e;
+  int rc = unstr_xfer(h->un, E * 36 * sizeof(double), e);
+  if (rc) return fail(h, rc, e);
+  const int grid = std::max(1, std::min((h->un.E + TPB - 1) / TPB, h->nsm * 8));
+  if (val) {
+    k_from_planes<double><<<grid, TPB, 0, h->stream>>>(h->un.bsr_val, h->un.xfer, 36, h->un.E);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(val, h->un.xfer, E * 36 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (col) {
+    int32_t* tmp = reinterpret_cast<int32_t*>(h->un.xfer);
+    CK(cudaStreamSynchronize(h->stream));
+    k_from_planes<int32_t><<<grid, TPB, 0, h->stream>>>(h->un.bsr_col, tmp, 4, h->un.E);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(col, tmp, E * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  }
   CK(cudaStreamSynchronize(h->stream));
   return PAMG_OK;
 }
@@ -1852,7 +1878,7 @@ int pamg_implicit_set_stab(pamg_handle* h, int with_stab) {
   if (!h->un.assembled) return fail(h, PAMG_ERR_STATE, "pamg_implicit_assemble has not been called");
   CK(cudaSetDevice(h->device));
   if (h->un.with_stab && !with_stab)   // back to the plain operator: restore the diagonal blocks and their inverses
-    return pamg_implicit_assemble(h, h->un.dt, h->un.ux, h->un.uy, -1);
+    return pamg_implicit_assemble_diffusion(h, h->un.dt, h->un.ux, h->un.uy, h->un.kdiff, -1);
   h->un.with_stab = with_stab != 0;
   return PAMG_OK;
 }
@@ -1888,9 +1914,39 @@ int pamg_implicit_step(pamg_handle* h, int ntime, int nits, double tol, int max_
   CK(cudaSetDevice(h->device));
   std::string e;
   long long nl = 0;
-  int rc = implicit_step(h->un, ntime, nits, tol, max_iters, iters_total, relres, h->nsm, h->stream, nl, e);
+  int rc = implicit_step(h->un, ntime, nits, tol, max_iters, iters_total, relres, h->nsm, h->stream, nl, e, &h->un_host_syncs);
   h->launches += nl;
   if (rc) return fail(h, rc, e);
+  return PAMG_OK;
+}
+
+// measurement aids for the unstructured kernels: average device time of `reps` block-CSR products y = A x on the work
+// vectors, and the number of host synchronisations the Krylov solves have made so far
+int pamg_implicit_spmv_time(pamg_handle* h, int reps, float* ms) {
+  ON_PART0(h);
+  if (!h || h->un.E < 1 || reps < 1 || !ms) return PAMG_ERR_ARG;
+  if (!h->un.assembled) return fail(h, PAMG_ERR_STATE, "pamg_implicit_assemble has not been called");
+  CK(cudaSetDevice(h->device));
+  double* W = h->un.work;
+  const size_t n = (size_t)h->un.E * 3;
+  const int grid = std::max(1, std::min((h->un.E + TPB - 1) / TPB, h->nsm * 8));
+  CK(cudaMemcpyAsync(W, h->un.T[h->un.cur], n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  k_bsr_spmv<<<grid, TPB, 0, h->stream>>>(h->un.bsr_val, h->un.bsr_col, W, nullptr, W + n, h->un.E, 0);
+  CK(cudaEventRecord(h->ev[14], h->stream));
+  for (int i = 0; i < reps; ++i) k_bsr_spmv<<<grid, TPB, 0, h->stream>>>(h->un.bsr_val, h->un.bsr_col, W, nullptr, W + n, h->un.E, 0);
+  CK(cudaEventRecord(h->ev[15], h->stream));
+  h->launches += reps + 1;
+  CK(cudaGetLastError());
+  CK(cudaEventSynchronize(h->ev[15]));
+  CK(cudaEventElapsedTime(ms, h->ev[14], h->ev[15]));
+  *ms /= (float)reps;
+  return PAMG_OK;
+}
+
+int pamg_implicit_host_syncs(pamg_handle* h, int64_t* n) {
+  ON_PART0(h);
+  if (!h || !n) return PAMG_ERR_ARG;
+  *n = h->un_host_syncs;
   return PAMG_OK;
 }
 

@@ -1815,6 +1815,12 @@ __global__ void __launch_bounds__(TPB) k_output_fields(OutArgs a) {
   }
 }
 
+// measurement aid: one warp that does nothing for `ns` nanoseconds
+__global__ void k_spin(long long ns) {
+  const unsigned long long t0 = p2p_now();
+  while ((long long)(p2p_now() - t0) < ns) { }
+}
+
 __global__ void __launch_bounds__(TPB) k_fill(double* p, long long n, double v) {
   for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += (long long)gridDim.x * TPB) p[i] = v;
 }

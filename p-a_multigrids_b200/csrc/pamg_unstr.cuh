@@ -1,14 +1,20 @@
-// pamg_unstr.cuh -- fully unstructured explicit P1 DG step (unstr_explicit,
-// transport_tri_unstr.F90:588-795) and the batched element-local inverse (FINDInv,
-// matrix_inversion.F90:50-148 == matrices.F90:1618-1716) as sm_100a kernels.
+// pamg_unstr.cuh -- fully unstructured P1 DG front-ends as sm_100a kernels: the explicit step (unstr_explicit,
+// transport_tri_unstr.F90:588-795), the implicit operator in block-CSR (unstr_implicit :214-387 /
+// Semi_implicit_direct transport_tri_semi.F90:1607-1764), its Krylov solve, the Petrov-Galerkin stabilisation, trans_rec
+// and the batched element-local inverse (FINDInv, matrix_inversion.F90:50-148 == matrices.F90:1618-1716).
 //
-// One thread per element.  Geometry (tri_det_nlx ShapFun.F90:1414-1454, det_snlx_all :1554-1590) is
-// recomputed in registers from the 6 vertex coordinates - cheaper than streaming 19 stored doubles.
-// Neighbour values are gathered through L2.  The 3x3 / 4x4 / 6x6 local systems live entirely in
-// registers (fully unrolled Gauss-Jordan); tensor cores are pointless for blocks this small.
+// One thread per element.  Everything the library owns per element or per face lies in HBM as structure-of-arrays planes
+// (vertex coordinates [6][E], neighbour ids / sides [3][E], penalty lengths [3][E], matrix blocks [36][E], block columns
+// [4][E] ...), so every load and store of a warp is one contiguous 256-byte span.  The FIELDS keep the reference's
+// (nloc, E) layout - it is the ABI and it keeps the two face values of a neighbour inside one 32-byte sector; a warp
+// moves its own 32 records (768 contiguous bytes) through shared memory with fully coalesced accesses (warp_load3 /
+// warp_store3).  Geometry (tri_det_nlx ShapFun.F90:1414-1454, det_snlx_all :1554-1590) is recomputed in registers from the
+// 6 vertex coordinates - cheaper than streaming 19 stored doubles.  The 3x3 / 4x4 / 6x6 local systems live entirely
+// in registers (fully unrolled Gauss-Jordan); tensor cores are pointless for blocks this small.
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -20,26 +26,72 @@ namespace pamg {
 
 struct UnstrDev {
   int E = 0;
-  double* X = nullptr;        // [E][3][2]
-  int32_t* neig = nullptr;    // [E][3] 1-based, 0 = boundary
-  int32_t* nside = nullptr;   // [E][3] fNeig | swap<<2 (swap: geometric pairing differs from get_unstr_sn2)
-  double* T[2] = {nullptr, nullptr};
+  double* X = nullptr;        // [6][E] planes x1, y1, x2, y2, x3, y3
+  int32_t* neig = nullptr;    // [3][E] 1-based, 0 = boundary
+  int32_t* nside = nullptr;   // [3][E] fNeig | swap<<2 (swap: geometric pairing differs from get_unstr_sn2)
+  double* dcen = nullptr;     // [3][E] penalty length of the diffusion face term: centroid distance to the neighbour, or
+                              //        centroid -> edge midpoint on the domain boundary (matrices.F90:84-110)
+  double* T[2] = {nullptr, nullptr};   // (3, E) like tnew
   double* told = nullptr;
   int cur = 0;
   // implicit operator in block-CSR: 4 blocks of 3x3 per element row (own, face 1, face 2, face 3)
-  double* bsr_val = nullptr;   // [E][4][9] row-major blocks
-  int32_t* bsr_col = nullptr;  // [E][4] 0-based element of the block column, -1 = no block
-  double* dinv = nullptr;      // [E][9] inverse of the diagonal block (block-Jacobi preconditioner)
+  double* bsr_val = nullptr;   // [36][E]: plane (block * 9 + row * 3 + col)
+  int32_t* bsr_col = nullptr;  // [4][E] 0-based element of the block column, -1 = no block
+  double* dinv = nullptr;      // [9][E] inverse of the diagonal block (block-Jacobi preconditioner)
   double* mdt = nullptr;       // [E] A/(12 dt): M/dt = mdt (I + J) per element
   double* work = nullptr;      // 9 vectors of 3E doubles for BiCGStab
-  double* dots = nullptr;      // [4] device results of k_dots
+  double* dots = nullptr;      // device scalars and partial sums of the Krylov solve
   double* dots_host = nullptr; // pinned mirror
   bool assembled = false;
-  double* diag0 = nullptr;     // [E][9] diagonal blocks without stabilisation
-  double* stab = nullptr;      // [E][9] Petrov-Galerkin element matrices ; [E][3] diff_coe behind them
+  double* diag0 = nullptr;     // [9][E] diagonal blocks without stabilisation
+  double* stab = nullptr;      // [E][9] Petrov-Galerkin element matrices ; [E][3] diff_coe behind them (ABI order)
   bool with_stab = false;
-  double dt = 0.0, ux = 0.0, uy = 0.0;
+  double dt = 0.0, ux = 0.0, uy = 0.0, kdiff = 0.0;
+  double* xfer = nullptr; size_t xfer_bytes = 0;   // staging for the [E][..] <-> [..][E] conversions at the ABI
 };
+
+// ---- a warp's 32 consecutive (3, E) records through shared memory: every global access is a full line ----------------
+// base = field + 3 * (first element of the warp), nvalid = elements of this warp inside the array, sm = 96 doubles
+__device__ __forceinline__ void warp_load3(const double* __restrict__ base, int nvalid, double* sm, int lane, double& a,
+                                           double& b, double& c) {
+  const int n = nvalid * 3;
+  for (int i = lane; i < n; i += 32) sm[i] = __ldg(base + i);
+  __syncwarp();
+  if (lane < nvalid) { a = sm[lane * 3]; b = sm[lane * 3 + 1]; c = sm[lane * 3 + 2]; }
+  __syncwarp();
+}
+__device__ __forceinline__ void warp_store3(double* __restrict__ base, int nvalid, double* sm, int lane, double a, double b,
+                                            double c) {
+  if (lane < nvalid) { sm[lane * 3] = a; sm[lane * 3 + 1] = b; sm[lane * 3 + 2] = c; }
+  __syncwarp();
+  const int n = nvalid * 3;
+  for (int i = lane; i < n; i += 32) base[i] = sm[i];
+  __syncwarp();
+}
+
+// geometry of one P1 triangle in registers (tri_det_nlx, ShapFun.F90:1414-1454)
+struct TriGeo { double area, gx[3], gy[3], px[3], py[3], cx, cy; };
+__device__ __forceinline__ void tri_geo(const double* __restrict__ X, size_t E, size_t e, TriGeo& g, double& detj) {
+  const double x1 = __ldg(X + e), y1 = __ldg(X + E + e), x2 = __ldg(X + 2 * E + e), y2 = __ldg(X + 3 * E + e),
+               x3 = __ldg(X + 4 * E + e), y3 = __ldg(X + 5 * E + e);
+  const double A = x1 - x3, B = y1 - y3, C = x2 - x3, D = y2 - y3;
+  detj = A * D - B * C;
+  g.area = 0.5 * fabs(detj);
+  g.gx[0] = D / detj; g.gx[1] = -B / detj; g.gx[2] = -(D / detj) - (-B / detj);
+  g.gy[0] = -C / detj; g.gy[1] = A / detj; g.gy[2] = -(-C / detj) - (A / detj);
+  g.px[0] = x1; g.px[1] = x2; g.px[2] = x3; g.py[0] = y1; g.py[1] = y2; g.py[2] = y3;
+  g.cx = (x1 + x2 + x3) / 3.0; g.cy = (y1 + y2 + y3) / 3.0;
+}
+// face f (0..2) of the gmsh numbering: nodes (l1, l2) = (1,3), (2,1), (3,2) (ShapFun_unstruc.F90:160-188); outward unit
+// normal and half length (det_snlx_all / NORMGI, ShapFun.F90:1554-1590, 2012-2037)
+__device__ __forceinline__ void face_geo(const TriGeo& g, int l1, int l2, double& nx, double& ny, double& sdet) {
+  const double ex = g.px[l2] - g.px[l1], ey = g.py[l2] - g.py[l1];
+  const double len = sqrt(ex * ex + ey * ey);
+  nx = ey / len; ny = -ex / len;
+  const double mx = 0.5 * (g.px[l1] + g.px[l2]) - g.cx, my = 0.5 * (g.py[l1] + g.py[l2]) - g.cy;
+  if (nx * mx + ny * my < 0.0) { nx = -nx; ny = -ny; }
+  sdet = 0.5 * len;
+}
 
 struct UnstrArgs {
   const double* X; const int32_t* neig; const int32_t* nside;
@@ -49,89 +101,111 @@ struct UnstrArgs {
 };
 
 __global__ void __launch_bounds__(TPB) k_unstr_explicit(UnstrArgs a) {
+  __shared__ double smw[TPB / 32][96];
   const double al = 0.78867513459481288, be = 0.21132486540518712;  // sn_orig, ShapFun.F90:1100-1111
   // weights of int sn_c * trace over the face: (2/3, 1/3) -- exact products of the 2-point Gauss rule
   const double w2 = al * al + be * be, w1 = 2.0 * al * be;
-  for (int e = blockIdx.x * TPB + threadIdx.x; e < a.E; e += gridDim.x * TPB) {
-    const double* __restrict__ X = a.X + (size_t)e * 6;
-    const double x1 = __ldg(X), y1 = __ldg(X + 1), x2 = __ldg(X + 2), y2 = __ldg(X + 3), x3 = __ldg(X + 4), y3 = __ldg(X + 5);
-    const double A = x1 - x3, B = y1 - y3, C = x2 - x3, D = y2 - y3;
-    const double detj = A * D - B * C;
-    const double area = 0.5 * fabs(detj);
-    const double gx[3] = {D / detj, -B / detj, -(D / detj) - (-B / detj)};
-    const double gy[3] = {-C / detj, A / detj, -(-C / detj) - (A / detj)};
-    const double T[3] = {__ldg(a.Tin + (size_t)e * 3), __ldg(a.Tin + (size_t)e * 3 + 1), __ldg(a.Tin + (size_t)e * 3 + 2)};
-    const double To[3] = {__ldg(a.told + (size_t)e * 3), __ldg(a.told + (size_t)e * 3 + 1), __ldg(a.told + (size_t)e * 3 + 2)};
-    const double sumT = T[0] + T[1] + T[2];
-    double rhs[3];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* sm = smw[wib];
+  const size_t E = (size_t)a.E;
+  for (int e0 = (blockIdx.x * (TPB / 32) + wib) * 32; e0 < a.E; e0 += gridDim.x * TPB) {
+    const int nvalid = min(32, a.E - e0);
+    const int e = e0 + lane;
+    const bool act = lane < nvalid;
+    double T[3] = {0, 0, 0}, To[3] = {0, 0, 0};
+    warp_load3(a.Tin + (size_t)e0 * 3, nvalid, sm, lane, T[0], T[1], T[2]);
+    warp_load3(a.told + (size_t)e0 * 3, nvalid, sm, lane, To[0], To[1], To[2]);
+    double out[3] = {0, 0, 0};
+    if (act) {
+      TriGeo g; double detj;
+      tri_geo(a.X, E, (size_t)e, g, detj);
+      const double area = g.area;
+      const double sumT = T[0] + T[1] + T[2];
+      double rhs[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) rhs[i] = (gx[i] * a.ux + gy[i] * a.uy) * (area / 3.0) * sumT;  // :668-672
-    const double cx = (x1 + x2 + x3) / 3.0, cy = (y1 + y2 + y3) / 3.0;
-    const double px[3] = {x1, x2, x3}, py[3] = {y1, y2, y3};
-    // gmsh faces: 1 = nodes (1,3), 2 = (2,1), 3 = (3,2)  (ShapFun_unstruc.F90:160-188)
-    const int L1[3] = {0, 1, 2}, L2[3] = {2, 0, 1};
+      for (int i = 0; i < 3; ++i) rhs[i] = (g.gx[i] * a.ux + g.gy[i] * a.uy) * (area / 3.0) * sumT;  // :668-672
+      const int L1[3] = {0, 1, 2}, L2[3] = {2, 0, 1};
 #pragma unroll
-    for (int f = 0; f < 3; ++f) {
-      const int l1 = L1[f], l2 = L2[f];
-      const double ex = px[l2] - px[l1], ey = py[l2] - py[l1];
-      const double len = sqrt(ex * ex + ey * ey);
-      double nx = ey / len, ny = -ex / len;
-      const double mx = 0.5 * (px[l1] + px[l2]) - cx, my = 0.5 * (py[l1] + py[l2]) - cy;
-      if (nx * mx + ny * my < 0.0) { nx = -nx; ny = -ny; }
-      const double sdet = 0.5 * len;
-      const int q = __ldg(a.neig + (size_t)e * 3 + f);
-      const int enc = __ldg(a.nside + (size_t)e * 3 + f);
-      const int ns = enc & 3;
-      double T2a = 0.0, T2b = 0.0, has2 = 0.0;   // neighbour values paired with sn_orig(:,1), sn_orig(:,2)
-      if (ns >= 1) {
-        // get_unstr_sn2 (ShapFun_unstruc.F90:205-222): Nside 1 -> nodes (3,1), 2 -> (1,2), 3 -> (2,3)
-        int m1 = (ns == 1) ? 2 : (ns == 2 ? 0 : 1), m2 = (ns == 1) ? 0 : (ns == 2 ? 1 : 2);
-        if (a.use_dir && (enc >> 2)) { const int t = m1; m1 = m2; m2 = t; }
-        has2 = 1.0;
-        if (q != 0) { T2a = __ldg(a.Tin + (size_t)(q - 1) * 3 + m1); T2b = __ldg(a.Tin + (size_t)(q - 1) * 3 + m2); }
-        else { T2a = a.t_bc; T2b = a.t_bc; }
+      for (int f = 0; f < 3; ++f) {
+        const int l1 = L1[f], l2 = L2[f];
+        double nx, ny, sdet;
+        face_geo(g, l1, l2, nx, ny, sdet);
+        const int q = __ldg(a.neig + (size_t)f * E + e);
+        const int enc = __ldg(a.nside + (size_t)f * E + e);
+        const int ns = enc & 3;
+        double T2a = 0.0, T2b = 0.0, has2 = 0.0;   // neighbour values paired with sn_orig(:,1), sn_orig(:,2)
+        if (ns >= 1) {
+          // get_unstr_sn2 (ShapFun_unstruc.F90:205-222): Nside 1 -> nodes (3,1), 2 -> (1,2), 3 -> (2,3)
+          int m1 = (ns == 1) ? 2 : (ns == 2 ? 0 : 1), m2 = (ns == 1) ? 0 : (ns == 2 ? 1 : 2);
+          if (a.use_dir && (enc >> 2)) { const int t = m1; m1 = m2; m2 = t; }
+          has2 = 1.0;
+          if (q != 0) { T2a = __ldg(a.Tin + (size_t)(q - 1) * 3 + m1); T2b = __ldg(a.Tin + (size_t)(q - 1) * 3 + m2); }
+          else { T2a = a.t_bc; T2b = a.t_bc; }
+        }
+        const double unn = nx * a.ux + ny * a.uy;
+        const double un = 0.5 * (unn + has2 * unn);       // n . (u + u2)/2 ; u2 = 0 when sn2 = 0 (Nside = 0)
+        const bool in = signbit(-un) == 0;                // income = 0.5 + 0.5*sign(1, -un)  (:731)
+        double ca, cb;
+        if (in) { const double f2 = sdet * has2 * unn; ca = f2 * (w2 * T2a + w1 * T2b); cb = f2 * (w1 * T2a + w2 * T2b); }
+        else { const double f1 = sdet * unn; ca = f1 * (w2 * T[l1] + w1 * T[l2]); cb = f1 * (w1 * T[l1] + w2 * T[l2]); }
+        rhs[l1] -= ca; rhs[l2] -= cb;                     // :742-746
       }
-      const double unn = nx * a.ux + ny * a.uy;
-      const double un = 0.5 * (unn + has2 * unn);       // n . (u + u2)/2 ; u2 = 0 when sn2 = 0 (Nside = 0)
-      const bool in = signbit(-un) == 0;                // income = 0.5 + 0.5*sign(1, -un)  (:731)
-      double ca, cb;
-      if (in) { const double f2 = sdet * has2 * unn; ca = f2 * (w2 * T2a + w1 * T2b); cb = f2 * (w1 * T2a + w2 * T2b); }
-      else { const double f1 = sdet * unn; ca = f1 * (w2 * T[l1] + w1 * T[l2]); cb = f1 * (w1 * T[l1] + w2 * T[l2]); }
-      rhs[l1] -= ca; rhs[l2] -= cb;                     // :742-746
-    }
-    const double m12 = area / 12.0, ml = area / 3.0;
-    const double so = To[0] + To[1] + To[2];
-    double out[3];
-    if (a.exact) {
-      // T = M^-1 (M told + dt rhs), M^-1 = (12/A)(I - J/4)  (transport_rect.F90:277-291 semantics)
-      double v[3];
+      const double m12 = area / 12.0, ml = area / 3.0;
+      const double so = To[0] + To[1] + To[2];
+      if (a.exact) {
+        // T = M^-1 (M told + dt rhs), M^-1 = (12/A)(I - J/4)  (transport_rect.F90:277-291 semantics)
+        double v[3];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) v[i] = m12 * (To[i] + so) + a.dt * rhs[i];
-      const double sv = v[0] + v[1] + v[2];
+        for (int i = 0; i < 3; ++i) v[i] = m12 * (To[i] + so) + a.dt * rhs[i];
+        const double sv = v[0] + v[1] + v[2];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) out[i] = (12.0 / area) * (v[i] - 0.25 * sv);
-    } else {
-      double rj[3], tl[3] = {T[0], T[1], T[2]};         // tnew_nonlin(:,ele) == tnew(:,ele) here (:598,783)
+        for (int i = 0; i < 3; ++i) out[i] = (12.0 / area) * (v[i] - 0.25 * sv);
+      } else {
+        double rj[3], tl[3] = {T[0], T[1], T[2]};         // tnew_nonlin(:,ele) == tnew(:,ele) here (:598,783)
 #pragma unroll
-      for (int i = 0; i < 3; ++i) rj[i] = m12 * (To[i] + so) + a.dt * rhs[i];   // :774
-      for (int it = 0; it < a.njac; ++it) {
-        const double st = tl[0] + tl[1] + tl[2];
-        double nt[3];
+        for (int i = 0; i < 3; ++i) rj[i] = m12 * (To[i] + so) + a.dt * rhs[i];   // :774
+        for (int it = 0; it < a.njac; ++it) {
+          const double st = tl[0] + tl[1] + tl[2];
+          double nt[3];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) nt[i] = (ml * tl[i] - m12 * (tl[i] + st) + rj[i]) / ml;  // :780-787
-        tl[0] = nt[0]; tl[1] = nt[1]; tl[2] = nt[2];
+          for (int i = 0; i < 3; ++i) nt[i] = (ml * tl[i] - m12 * (tl[i] + st) + rj[i]) / ml;  // :780-787
+          tl[0] = nt[0]; tl[1] = nt[1]; tl[2] = nt[2];
+        }
+        out[0] = tl[0]; out[1] = tl[1]; out[2] = tl[2];
       }
-      out[0] = tl[0]; out[1] = tl[1]; out[2] = tl[2];
     }
-    a.Tout[(size_t)e * 3] = out[0]; a.Tout[(size_t)e * 3 + 1] = out[1]; a.Tout[(size_t)e * 3 + 2] = out[2];
+    warp_store3(a.Tout + (size_t)e0 * 3, nvalid, sm, lane, out[0], out[1], out[2]);
   }
 }
 
+// [E][K] (ABI order) <-> [K][E] planes; one thread per element (set-up and read-back only)
+template <typename Tp>
+__global__ void __launch_bounds__(TPB) k_to_planes(const Tp* __restrict__ aos, Tp* __restrict__ soa, int K, int E) {
+  for (int e = blockIdx.x * TPB + threadIdx.x; e < E; e += gridDim.x * TPB)
+    for (int k = 0; k < K; ++k) soa[(size_t)k * E + e] = aos[(size_t)e * K + k];
+}
+template <typename Tp>
+__global__ void __launch_bounds__(TPB) k_from_planes(const Tp* __restrict__ soa, Tp* __restrict__ aos, int K, int E) {
+  for (int e = blockIdx.x * TPB + threadIdx.x; e < E; e += gridDim.x * TPB)
+    for (int k = 0; k < K; ++k) aos[(size_t)e * K + k] = soa[(size_t)k * E + e];
+}
+
 inline void unstr_free(UnstrDev& u) {
-  cudaFree(u.X); cudaFree(u.neig); cudaFree(u.nside); cudaFree(u.T[0]); cudaFree(u.T[1]); cudaFree(u.told);
+  cudaFree(u.X); cudaFree(u.neig); cudaFree(u.nside); cudaFree(u.dcen); cudaFree(u.T[0]); cudaFree(u.T[1]); cudaFree(u.told);
   cudaFree(u.bsr_val); cudaFree(u.bsr_col); cudaFree(u.dinv); cudaFree(u.mdt); cudaFree(u.work); cudaFree(u.dots); cudaFree(u.diag0); cudaFree(u.stab);
+  cudaFree(u.xfer);
   if (u.dots_host) cudaFreeHost(u.dots_host);
   u = UnstrDev();
+}
+
+#define UCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); return PAMG_ERR_CUDA; } } while (0)
+
+inline int unstr_xfer(UnstrDev& u, size_t bytes, std::string& err) {
+  if (u.xfer_bytes >= bytes) return PAMG_OK;
+  cudaFree(u.xfer); u.xfer = nullptr; u.xfer_bytes = 0;
+  UCK(cudaMalloc(&u.xfer, bytes));
+  u.xfer_bytes = bytes;
+  return PAMG_OK;
 }
 
 inline int unstr_setup(UnstrDev& u, int E, const double* X, const int32_t* neig, const int32_t* fneig,
@@ -139,30 +213,47 @@ inline int unstr_setup(UnstrDev& u, int E, const double* X, const int32_t* neig,
   unstr_free(u);
   // geometric pairing flag per face: does the neighbour node that get_unstr_sn2 pairs with my first face
   // node actually coincide with it?  (SURVEY B-9: the reference ignores Dir here)
-  std::vector<int32_t> enc((size_t)E * 3);
-  const int L1[3] = {0, 1, 2};
-  for (int e = 0; e < E; ++e)
+  // penalty length of the diffusion face term (get_d_center Msh2Tri.F90:349-385, add_diffusion_surf matrices.F90:84-110)
+  std::vector<int32_t> enc((size_t)E * 3), ng((size_t)E * 3);
+  std::vector<double> xs((size_t)E * 6), dc((size_t)E * 3);
+  const int L1[3] = {0, 1, 2}, L2[3] = {2, 0, 1};
+  for (int e = 0; e < E; ++e) {
+    const double* P = X + (size_t)e * 6;
+    const double cx = (P[0] + P[2] + P[4]) / 3.0, cy = (P[1] + P[3] + P[5]) / 3.0;
+    for (int k = 0; k < 6; ++k) xs[(size_t)k * E + e] = P[k];
     for (int f = 0; f < 3; ++f) {
       const int q = neig[(size_t)e * 3 + f], ns = fneig[(size_t)e * 3 + f];
       int sw = 0;
+      double d;
       if (q != 0 && ns >= 1 && ns <= 3) {
         const int m1 = (ns == 1) ? 2 : (ns == 2 ? 0 : 1);
         const double* a = X + (size_t)e * 6 + 2 * L1[f];
-        const double* b = X + (size_t)(q - 1) * 6 + 2 * m1;
+        const double* Q = X + (size_t)(q - 1) * 6;
+        const double* b = Q + 2 * m1;
         sw = !(a[0] == b[0] && a[1] == b[1]);
+        const double qx = (Q[0] + Q[2] + Q[4]) / 3.0, qy = (Q[1] + Q[3] + Q[5]) / 3.0;
+        d = std::sqrt((cx - qx) * (cx - qx) + (cy - qy) * (cy - qy));
       } else if (q != 0) { err = "fNeig must be 1..3 where Neig != 0"; return PAMG_ERR_ARG; }
-      enc[(size_t)e * 3 + f] = (ns & 3) | (sw << 2);
+      else {
+        const double mx = 0.5 * (P[2 * L1[f]] + P[2 * L2[f]]), my = 0.5 * (P[2 * L1[f] + 1] + P[2 * L2[f] + 1]);
+        d = std::sqrt((cx - mx) * (cx - mx) + (cy - my) * (cy - my));
+      }
+      enc[(size_t)f * E + e] = (ns & 3) | (sw << 2);
+      ng[(size_t)f * E + e] = q;
+      dc[(size_t)f * E + e] = d;
     }
-#define UCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); return PAMG_ERR_CUDA; } } while (0)
+  }
   u.E = E;
   UCK(cudaMalloc(&u.X, (size_t)E * 6 * sizeof(double)));
   UCK(cudaMalloc(&u.neig, (size_t)E * 3 * sizeof(int32_t)));
   UCK(cudaMalloc(&u.nside, (size_t)E * 3 * sizeof(int32_t)));
+  UCK(cudaMalloc(&u.dcen, (size_t)E * 3 * sizeof(double)));
   for (int i = 0; i < 2; ++i) UCK(cudaMalloc(&u.T[i], (size_t)E * 3 * sizeof(double)));
   UCK(cudaMalloc(&u.told, (size_t)E * 3 * sizeof(double)));
-  UCK(cudaMemcpyAsync(u.X, X, (size_t)E * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
-  UCK(cudaMemcpyAsync(u.neig, neig, (size_t)E * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  UCK(cudaMemcpyAsync(u.X, xs.data(), (size_t)E * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
+  UCK(cudaMemcpyAsync(u.neig, ng.data(), (size_t)E * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   UCK(cudaMemcpyAsync(u.nside, enc.data(), (size_t)E * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  UCK(cudaMemcpyAsync(u.dcen, dc.data(), (size_t)E * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
   UCK(cudaMemsetAsync(u.T[0], 0, (size_t)E * 3 * sizeof(double), st));
   UCK(cudaMemsetAsync(u.T[1], 0, (size_t)E * 3 * sizeof(double), st));
   UCK(cudaStreamSynchronize(st));
@@ -193,26 +284,28 @@ inline int unstr_step(UnstrDev& u, double dt, double ux, double uy, double t_bc,
 // Implicit "Jacobian" of unstr_implicit (transport_tri_unstr.F90:270-364) assembled straight into block-CSR on the
 // device: one thread per element writes its diagonal block mass/dt - stiff (+ the outflow part of the
 // upwind flux, :344-360 with income = 0) and one 3x3 block per inflow face in the neighbour's columns
-// (`target_ele`, :339-342).  The reference builds three scalar CSR matrices, converts them to dense and inverts
-// the dense (3E)^2 matrix with FINDInv (:366-378); here the operator never leaves its 4-blocks-per-row form.
+// (`target_ele`, :339-342).  With kdiff > 0 the diffusion operator of the iterative path is added (the reference's
+// implicit drivers compute add_diffusion_vol and drop it, transport_tri_semi.F90:1627; this is the intended use): the
+// volume block k A grad(phi_i).grad(phi_j) (ShapFun_unstruc.F90:324-335) on the diagonal and the face penalty
+// (k/dx) int sn_i (T - T2) (matrices.F90:113-115, get_diff_surf_stencl transport_tri_semi.F90:468-477) on the own and
+// the neighbour's columns.  The reference builds three scalar CSR matrices, converts them to dense and inverts
+// the dense (3E)^2 matrix with FINDInv (:366-378); here the operator never leaves its 4-blocks-per-row form, stored as
+// 36 + 4 planes so that every store of a warp is one full line.
 struct BsrArgs {
-  const double* X; const int32_t* neig; const int32_t* nside;
+  const double* X; const int32_t* neig; const int32_t* nside; const double* dcen;
   double* val; int32_t* col; double* dinv; double* mdt; double* diag0;
-  double dt, ux, uy;
+  double dt, ux, uy, kdiff;
   int E, use_dir;
 };
 
 __global__ void __launch_bounds__(TPB) k_assemble_bsr(BsrArgs a) {
   const double al = 0.78867513459481288, be = 0.21132486540518712;
   const double w2 = al * al + be * be, w1 = 2.0 * al * be;
+  const size_t E = (size_t)a.E;
   for (int e = blockIdx.x * TPB + threadIdx.x; e < a.E; e += gridDim.x * TPB) {
-    const double* __restrict__ X = a.X + (size_t)e * 6;
-    const double x1 = __ldg(X), y1 = __ldg(X + 1), x2 = __ldg(X + 2), y2 = __ldg(X + 3), x3 = __ldg(X + 4), y3 = __ldg(X + 5);
-    const double A = x1 - x3, B = y1 - y3, C = x2 - x3, D = y2 - y3;
-    const double detj = A * D - B * C;
-    const double area = 0.5 * fabs(detj);
-    const double gx[3] = {D / detj, -B / detj, -(D / detj) - (-B / detj)};
-    const double gy[3] = {-C / detj, A / detj, -(-C / detj) - (A / detj)};
+    TriGeo g; double detj;
+    tri_geo(a.X, E, (size_t)e, g, detj);
+    const double area = g.area;
     const double m12 = area / (12.0 * a.dt);
     double blk[4][9];
 #pragma unroll
@@ -221,98 +314,128 @@ __global__ void __launch_bounds__(TPB) k_assemble_bsr(BsrArgs a) {
       for (int q = 0; q < 9; ++q) blk[bq][q] = 0.0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      const double st = (gx[i] * a.ux + gy[i] * a.uy) * (area / 3.0);   // stiff(i,j): the same for every j (:281-283)
+      const double st = (g.gx[i] * a.ux + g.gy[i] * a.uy) * (area / 3.0);   // stiff(i,j): the same for every j (:281-283)
 #pragma unroll
-      for (int j = 0; j < 3; ++j) blk[0][i * 3 + j] = m12 * (i == j ? 2.0 : 1.0) - st;
+      for (int j = 0; j < 3; ++j)
+        blk[0][i * 3 + j] = m12 * (i == j ? 2.0 : 1.0) - st + a.kdiff * area * (g.gx[i] * g.gx[j] + g.gy[i] * g.gy[j]);
     }
-    const double cx = (x1 + x2 + x3) / 3.0, cy = (y1 + y2 + y3) / 3.0;
-    const double px[3] = {x1, x2, x3}, py[3] = {y1, y2, y3};
     const int L1[3] = {0, 1, 2}, L2[3] = {2, 0, 1};
     int cols[4] = {e, -1, -1, -1};
 #pragma unroll
     for (int f = 0; f < 3; ++f) {
       const int l1 = L1[f], l2 = L2[f];
-      const double ex = px[l2] - px[l1], ey = py[l2] - py[l1];
-      const double len = sqrt(ex * ex + ey * ey);
-      double nx = ey / len, ny = -ex / len;
-      const double mx = 0.5 * (px[l1] + px[l2]) - cx, my = 0.5 * (py[l1] + py[l2]) - cy;
-      if (nx * mx + ny * my < 0.0) { nx = -nx; ny = -ny; }
-      const double sdet = 0.5 * len;
-      const int q = __ldg(a.neig + (size_t)e * 3 + f);
-      const int enc = __ldg(a.nside + (size_t)e * 3 + f);
+      double nx, ny, sdet;
+      face_geo(g, l1, l2, nx, ny, sdet);
+      const int q = __ldg(a.neig + (size_t)f * E + e);
+      const int enc = __ldg(a.nside + (size_t)f * E + e);
       const int ns = enc & 3;
       const double has2 = ns >= 1 ? 1.0 : 0.0;
       const double unn = nx * a.ux + ny * a.uy;
       const double un = 0.5 * (unn + has2 * unn);
       const bool in = signbit(-un) == 0;
       const double c = sdet * unn;
+      // neighbour nodes coincident with (l1, l2): as in get_unstr_sn2, or the geometric pairing with use_dir
+      int m1 = (ns == 1) ? 2 : (ns == 2 ? 0 : 1), m2 = (ns == 1) ? 0 : (ns == 2 ? 1 : 2);
+      if (a.use_dir && (enc >> 2)) { const int t = m1; m1 = m2; m2 = t; }
       if (!in) {                       // outflow: own columns
         blk[0][l1 * 3 + l1] += c * w2; blk[0][l1 * 3 + l2] += c * w1;
         blk[0][l2 * 3 + l1] += c * w1; blk[0][l2 * 3 + l2] += c * w2;
       } else if (ns >= 1) {            // inflow: the neighbour's columns, its nodes paired as in get_unstr_sn2
-        int m1 = (ns == 1) ? 2 : (ns == 2 ? 0 : 1), m2 = (ns == 1) ? 0 : (ns == 2 ? 1 : 2);
-        if (a.use_dir && (enc >> 2)) { const int t = m1; m1 = m2; m2 = t; }
         const int b = (q != 0) ? 1 + f : 0;   // target_ele == 0 falls back to the element itself (:340-342)
         blk[b][l1 * 3 + m1] += c * w2; blk[b][l1 * 3 + m2] += c * w1;
         blk[b][l2 * 3 + m1] += c * w1; blk[b][l2 * 3 + m2] += c * w2;
         if (q != 0) cols[1 + f] = q - 1;
       }                                // inflow through the domain boundary (Nside = 0): sn2 = 0 -> no block
+      if (a.kdiff != 0.0) {
+        // penalty diffusion: own block += (k/dx) F, neighbour block -= (k/dx) F, F = (L/2) [[w2, w1], [w1, w2]]; on the
+        // domain boundary the exterior trace is Dirichlet data (right-hand side), only the own part stays
+        const double kd = a.kdiff / __ldg(a.dcen + (size_t)f * E + e) * sdet;
+        blk[0][l1 * 3 + l1] += kd * w2; blk[0][l1 * 3 + l2] += kd * w1;
+        blk[0][l2 * 3 + l1] += kd * w1; blk[0][l2 * 3 + l2] += kd * w2;
+        if (q != 0 && ns >= 1) {
+          blk[1 + f][l1 * 3 + m1] -= kd * w2; blk[1 + f][l1 * 3 + m2] -= kd * w1;
+          blk[1 + f][l2 * 3 + m1] -= kd * w1; blk[1 + f][l2 * 3 + m2] -= kd * w2;
+          cols[1 + f] = q - 1;
+        }
+      }
     }
 #pragma unroll
     for (int bq = 0; bq < 4; ++bq) {
-      a.col[(size_t)e * 4 + bq] = cols[bq];
+      a.col[(size_t)bq * E + e] = cols[bq];
 #pragma unroll
-      for (int q = 0; q < 9; ++q) a.val[((size_t)e * 4 + bq) * 9 + q] = blk[bq][q];
+      for (int q = 0; q < 9; ++q) a.val[(size_t)(bq * 9 + q) * E + e] = blk[bq][q];
     }
 #pragma unroll
-    for (int q = 0; q < 9; ++q) a.diag0[(size_t)e * 9 + q] = blk[0][q];     // diagonal block without stabilisation
+    for (int q = 0; q < 9; ++q) a.diag0[(size_t)q * E + e] = blk[0][q];     // diagonal block without stabilisation
     // inverse of the diagonal block by its adjugate
     const double* d = blk[0];
     const double c00 = d[4] * d[8] - d[5] * d[7], c01 = d[5] * d[6] - d[3] * d[8], c02 = d[3] * d[7] - d[4] * d[6];
     const double det = d[0] * c00 + d[1] * c01 + d[2] * c02, id = 1.0 / det;
-    double* o = a.dinv + (size_t)e * 9;
+    double o[9];
     o[0] = c00 * id; o[1] = (d[2] * d[7] - d[1] * d[8]) * id; o[2] = (d[1] * d[5] - d[2] * d[4]) * id;
     o[3] = c01 * id; o[4] = (d[0] * d[8] - d[2] * d[6]) * id; o[5] = (d[2] * d[3] - d[0] * d[5]) * id;
     o[6] = c02 * id; o[7] = (d[1] * d[6] - d[0] * d[7]) * id; o[8] = (d[0] * d[4] - d[1] * d[3]) * id;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) a.dinv[(size_t)q * E + e] = o[q];
     a.mdt[e] = m12;
   }
 }
 
-// y = A x (block-CSR) ; mode 1: y = b - A x
+// y = A x (block-CSR planes) ; mode 1: y = b - A x.  x, b, y are (3, E) vectors.
 __global__ void __launch_bounds__(TPB) k_bsr_spmv(const double* __restrict__ val, const int32_t* __restrict__ col,
                                                   const double* __restrict__ x, const double* __restrict__ b,
-                                                  double* __restrict__ y, int E, int mode) {
-  for (int e = blockIdx.x * TPB + threadIdx.x; e < E; e += gridDim.x * TPB) {
+                                                  double* __restrict__ y, int En, int mode) {
+  __shared__ double smw[TPB / 32][96];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* sm = smw[wib];
+  const size_t E = (size_t)En;
+  for (int e0 = (blockIdx.x * (TPB / 32) + wib) * 32; e0 < En; e0 += gridDim.x * TPB) {
+    const int nvalid = min(32, En - e0);
+    const int e = e0 + lane;
     double s0 = 0, s1 = 0, s2 = 0;
+    double b0 = 0, b1 = 0, b2 = 0;
+    if (mode == 1) warp_load3(b + (size_t)e0 * 3, nvalid, sm, lane, b0, b1, b2);
+    if (lane < nvalid) {
 #pragma unroll
-    for (int bq = 0; bq < 4; ++bq) {
-      const int c = __ldg(col + (size_t)e * 4 + bq);
-      if (c < 0) continue;
-      const double* v = val + ((size_t)e * 4 + bq) * 9;
-      const double x0 = __ldg(x + (size_t)c * 3), x1 = __ldg(x + (size_t)c * 3 + 1), x2 = __ldg(x + (size_t)c * 3 + 2);
-      s0 += v[0] * x0 + v[1] * x1 + v[2] * x2;
-      s1 += v[3] * x0 + v[4] * x1 + v[5] * x2;
-      s2 += v[6] * x0 + v[7] * x1 + v[8] * x2;
+      for (int bq = 0; bq < 4; ++bq) {
+        const int c = __ldg(col + (size_t)bq * E + e);
+        if (c < 0) continue;
+        const double* v = val + (size_t)(bq * 9) * E + e;
+        const double x0 = __ldg(x + (size_t)c * 3), x1 = __ldg(x + (size_t)c * 3 + 1), x2 = __ldg(x + (size_t)c * 3 + 2);
+        s0 += __ldg(v) * x0 + __ldg(v + E) * x1 + __ldg(v + 2 * E) * x2;
+        s1 += __ldg(v + 3 * E) * x0 + __ldg(v + 4 * E) * x1 + __ldg(v + 5 * E) * x2;
+        s2 += __ldg(v + 6 * E) * x0 + __ldg(v + 7 * E) * x1 + __ldg(v + 8 * E) * x2;
+      }
+      if (mode == 1) { s0 = b0 - s0; s1 = b1 - s1; s2 = b2 - s2; }
     }
-    if (mode == 1) { s0 = b[(size_t)e * 3] - s0; s1 = b[(size_t)e * 3 + 1] - s1; s2 = b[(size_t)e * 3 + 2] - s2; }
-    y[(size_t)e * 3] = s0; y[(size_t)e * 3 + 1] = s1; y[(size_t)e * 3 + 2] = s2;
+    warp_store3(y + (size_t)e0 * 3, nvalid, sm, lane, s0, s1, s2);
   }
 }
 
 // y = Dinv x (block-Jacobi preconditioner) ; mode 1: y = (M/dt) x with M/dt = mdt (I + J) per element (:366-369)
 __global__ void __launch_bounds__(TPB) k_block_apply(const double* __restrict__ dinv, const double* __restrict__ mdt,
-                                                     const double* __restrict__ x, double* __restrict__ y, int E, int mode) {
-  for (int e = blockIdx.x * TPB + threadIdx.x; e < E; e += gridDim.x * TPB) {
-    const double x0 = x[(size_t)e * 3], x1 = x[(size_t)e * 3 + 1], x2 = x[(size_t)e * 3 + 2];
-    if (mode == 1) {
-      const double m = mdt[e], sx = x0 + x1 + x2;
-      y[(size_t)e * 3] = m * (x0 + sx); y[(size_t)e * 3 + 1] = m * (x1 + sx); y[(size_t)e * 3 + 2] = m * (x2 + sx);
-    } else {
-      const double* d = dinv + (size_t)e * 9;
-      y[(size_t)e * 3] = d[0] * x0 + d[1] * x1 + d[2] * x2;
-      y[(size_t)e * 3 + 1] = d[3] * x0 + d[4] * x1 + d[5] * x2;
-      y[(size_t)e * 3 + 2] = d[6] * x0 + d[7] * x1 + d[8] * x2;
+                                                     const double* __restrict__ x, double* __restrict__ y, int En, int mode) {
+  __shared__ double smw[TPB / 32][96];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* sm = smw[wib];
+  const size_t E = (size_t)En;
+  for (int e0 = (blockIdx.x * (TPB / 32) + wib) * 32; e0 < En; e0 += gridDim.x * TPB) {
+    const int nvalid = min(32, En - e0);
+    const int e = e0 + lane;
+    double x0 = 0, x1 = 0, x2 = 0, y0 = 0, y1 = 0, y2 = 0;
+    warp_load3(x + (size_t)e0 * 3, nvalid, sm, lane, x0, x1, x2);
+    if (lane < nvalid) {
+      if (mode == 1) {
+        const double m = mdt[e], sx = x0 + x1 + x2;
+        y0 = m * (x0 + sx); y1 = m * (x1 + sx); y2 = m * (x2 + sx);
+      } else {
+        const double* d = dinv + e;
+        y0 = __ldg(d) * x0 + __ldg(d + E) * x1 + __ldg(d + 2 * E) * x2;
+        y1 = __ldg(d + 3 * E) * x0 + __ldg(d + 4 * E) * x1 + __ldg(d + 5 * E) * x2;
+        y2 = __ldg(d + 6 * E) * x0 + __ldg(d + 7 * E) * x1 + __ldg(d + 8 * E) * x2;
+      }
     }
+    warp_store3(y + (size_t)e0 * 3, nvalid, sm, lane, y0, y1, y2);
   }
 }
 
@@ -323,45 +446,219 @@ __global__ void __launch_bounds__(TPB) k_lincomb(double* z, double a, const doub
     z[i] = a * x[i] + b * y[i] + (w ? c * w[i] : 0.0);
 }
 
-// two dot products per pass: partial[2*blockIdx.x + {0,1}] = x.y , u.v  (u may be null)
-__global__ void __launch_bounds__(TPB) k_dots(const double* __restrict__ x, const double* __restrict__ y,
-                                              const double* __restrict__ u, const double* __restrict__ v, long long n,
-                                              double* __restrict__ partial) {
-  double s0 = 0, s1 = 0;
-  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += (long long)gridDim.x * TPB) {
-    s0 += x[i] * y[i];
-    if (u) s1 += u[i] * v[i];
-  }
+// ---- BiCGStab with device-resident scalars -----------------------------------------------------------------------------
+// The reference inverts the dense (3E)^2 matrix (FINDInv, transport_tri_unstr.F90:366-378).  Here: BiCGStab, right-
+// preconditioned with the inverse diagonal blocks.  Every scalar of the recurrence (rho, alpha, omega, the norms, the
+// convergence flag) lives in device memory: a kernel that ends with a dot product leaves its partial sums per CTA and the
+// LAST CTA to finish adds them up in a fixed order (deterministic) and derives the scalars the next kernel needs.  One
+// iteration is 5 kernels and no host round trip; the host looks at the flag once per batch of iterations.
+enum { KS_RHO = 0, KS_ALPHA, KS_OMEGA, KS_RHONEW, KS_RR, KS_BB, KS_STOP2, KS_DONE, KS_ITER, KS_MAXIT, KS_COUNTER = 16, KS_PARTIAL = 32 };
+
+// sum of two per-thread values over the grid: returns true in every thread of the last CTA, with the totals in t0, t1
+__device__ __forceinline__ bool grid_sum2(double s0, double s1, double* ks, double& t0, double& t1) {
+  __shared__ double sh[2][TPB];
+  __shared__ int s_last;
   for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
-  __shared__ double sh[2][TPB / 32];
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   if (l == 0) { sh[0][w] = s0; sh[1][w] = s1; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    s0 = 0; s1 = 0;
-    for (int i = 0; i < TPB / 32; ++i) { s0 += sh[0][i]; s1 += sh[1][i]; }
-    partial[2 * blockIdx.x] = s0; partial[2 * blockIdx.x + 1] = s1;
+    double a = 0, b = 0;
+    for (int i = 0; i < TPB / 32; ++i) { a += sh[0][i]; b += sh[1][i]; }
+    ks[KS_PARTIAL + 2 * blockIdx.x] = a; ks[KS_PARTIAL + 2 * blockIdx.x + 1] = b;
+    __threadfence();
+    s_last = atomicAdd(reinterpret_cast<unsigned long long*>(ks + KS_COUNTER), 1ull) == (unsigned long long)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  double a = 0, b = 0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += TPB) {
+    a += *(volatile double*)(ks + KS_PARTIAL + 2 * i); b += *(volatile double*)(ks + KS_PARTIAL + 2 * i + 1);
+  }
+  __syncthreads();
+  sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = b;
+  __syncthreads();
+  for (int s = TPB / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { sh[0][threadIdx.x] += sh[0][threadIdx.x + s]; sh[1][threadIdx.x] += sh[1][threadIdx.x + s]; }
+    __syncthreads();
+  }
+  t0 = sh[0][0]; t1 = sh[1][0];
+  if (threadIdx.x == 0) *reinterpret_cast<unsigned long long*>(ks + KS_COUNTER) = 0ull;
+  return true;
+}
+
+struct KryArgs {
+  const double* val; const int32_t* col; const double* dinv;
+  double *x, *b, *r, *rh, *p, *v, *s, *t, *y, *z;
+  double* ks;
+  int E;
+};
+
+// start of a solve: r = b - A x ; rh = r ; p = v = 0 ; bb = (b, b) ; rr = (r, r) ; rho_new = (rh, r) = rr
+__global__ void __launch_bounds__(TPB) k_kry_init(KryArgs a, double tol) {
+  __shared__ double smw[TPB / 32][96];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* sm = smw[wib];
+  const size_t E = (size_t)a.E;
+  double sbb = 0, srr = 0;
+  for (int e0 = (blockIdx.x * (TPB / 32) + wib) * 32; e0 < a.E; e0 += gridDim.x * TPB) {
+    const int nvalid = min(32, a.E - e0);
+    const int e = e0 + lane;
+    double b0 = 0, b1 = 0, b2 = 0, s0 = 0, s1 = 0, s2 = 0;
+    warp_load3(a.b + (size_t)e0 * 3, nvalid, sm, lane, b0, b1, b2);
+    if (lane < nvalid) {
+#pragma unroll
+      for (int bq = 0; bq < 4; ++bq) {
+        const int c = __ldg(a.col + (size_t)bq * E + e);
+        if (c < 0) continue;
+        const double* v = a.val + (size_t)(bq * 9) * E + e;
+        const double x0 = a.x[(size_t)c * 3], x1 = a.x[(size_t)c * 3 + 1], x2 = a.x[(size_t)c * 3 + 2];
+        s0 += __ldg(v) * x0 + __ldg(v + E) * x1 + __ldg(v + 2 * E) * x2;
+        s1 += __ldg(v + 3 * E) * x0 + __ldg(v + 4 * E) * x1 + __ldg(v + 5 * E) * x2;
+        s2 += __ldg(v + 6 * E) * x0 + __ldg(v + 7 * E) * x1 + __ldg(v + 8 * E) * x2;
+      }
+      s0 = b0 - s0; s1 = b1 - s1; s2 = b2 - s2;
+      sbb += b0 * b0 + b1 * b1 + b2 * b2; srr += s0 * s0 + s1 * s1 + s2 * s2;
+    }
+    warp_store3(a.r + (size_t)e0 * 3, nvalid, sm, lane, s0, s1, s2);
+    warp_store3(a.rh + (size_t)e0 * 3, nvalid, sm, lane, s0, s1, s2);
+    warp_store3(a.p + (size_t)e0 * 3, nvalid, sm, lane, 0.0, 0.0, 0.0);
+    warp_store3(a.v + (size_t)e0 * 3, nvalid, sm, lane, 0.0, 0.0, 0.0);
+  }
+  double bb, rr;
+  if (grid_sum2(sbb, srr, a.ks, bb, rr) && threadIdx.x == 0) {
+    a.ks[KS_BB] = bb; a.ks[KS_RR] = rr; a.ks[KS_STOP2] = tol * tol * bb;
+    a.ks[KS_RHO] = 1.0; a.ks[KS_ALPHA] = 1.0; a.ks[KS_OMEGA] = 1.0; a.ks[KS_RHONEW] = rr;
+    a.ks[KS_ITER] = 0.0;
+    a.ks[KS_DONE] = (rr <= tol * tol * bb) ? 1.0 : 0.0;
   }
 }
 
-// fixed-order final sum of the per-CTA partials (deterministic): strided partial sums, then a shared-memory tree
-__global__ void __launch_bounds__(256) k_dots_final(const double* __restrict__ partial, int nblk, double* __restrict__ out) {
-  __shared__ double sh[2][256];
-  double s0 = 0, s1 = 0;
-  for (int i = threadIdx.x; i < nblk; i += 256) { s0 += partial[2 * i]; s1 += partial[2 * i + 1]; }
-  sh[0][threadIdx.x] = s0; sh[1][threadIdx.x] = s1;
-  __syncthreads();
-  for (int w = 128; w > 0; w >>= 1) {
-    if (threadIdx.x < w) { sh[0][threadIdx.x] += sh[0][threadIdx.x + w]; sh[1][threadIdx.x] += sh[1][threadIdx.x + w]; }
-    __syncthreads();
+// p = r + beta (p - omega v) ; y = Dinv p      (beta from the scalars; breakdown -> done = 2)
+__global__ void __launch_bounds__(TPB) k_kry_p(KryArgs a) {
+  if (a.ks[KS_DONE] != 0.0) return;
+  __shared__ double smw[TPB / 32][96];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* sm = smw[wib];
+  const size_t E = (size_t)a.E;
+  const double rho_new = a.ks[KS_RHONEW], rho = a.ks[KS_RHO], alpha = a.ks[KS_ALPHA], omega = a.ks[KS_OMEGA];
+  const double beta = (rho_new / rho) * (alpha / omega);
+  for (int e0 = (blockIdx.x * (TPB / 32) + wib) * 32; e0 < a.E; e0 += gridDim.x * TPB) {
+    const int nvalid = min(32, a.E - e0);
+    const int e = e0 + lane;
+    double r0 = 0, r1 = 0, r2 = 0, p0 = 0, p1 = 0, p2 = 0, v0 = 0, v1 = 0, v2 = 0, y0 = 0, y1 = 0, y2 = 0;
+    warp_load3(a.r + (size_t)e0 * 3, nvalid, sm, lane, r0, r1, r2);
+    warp_load3(a.p + (size_t)e0 * 3, nvalid, sm, lane, p0, p1, p2);
+    warp_load3(a.v + (size_t)e0 * 3, nvalid, sm, lane, v0, v1, v2);
+    p0 = r0 + beta * p0 + (-beta * omega) * v0; p1 = r1 + beta * p1 + (-beta * omega) * v1; p2 = r2 + beta * p2 + (-beta * omega) * v2;
+    if (lane < nvalid) {
+      const double* d = a.dinv + e;
+      y0 = __ldg(d) * p0 + __ldg(d + E) * p1 + __ldg(d + 2 * E) * p2;
+      y1 = __ldg(d + 3 * E) * p0 + __ldg(d + 4 * E) * p1 + __ldg(d + 5 * E) * p2;
+      y2 = __ldg(d + 6 * E) * p0 + __ldg(d + 7 * E) * p1 + __ldg(d + 8 * E) * p2;
+    }
+    warp_store3(a.p + (size_t)e0 * 3, nvalid, sm, lane, p0, p1, p2);
+    warp_store3(a.y + (size_t)e0 * 3, nvalid, sm, lane, y0, y1, y2);
   }
-  if (threadIdx.x < 2) out[threadIdx.x] = sh[threadIdx.x][0];
+}
+
+// out = A in, with up to two dot products of the result; WHICH = 0: v = A y, alpha = rho_new / (rh, v)
+//                                                         WHICH = 1: t = A z, omega = (t, s) / (t, t)
+template <int WHICH>
+__global__ void __launch_bounds__(TPB) k_kry_spmv(KryArgs a) {
+  if (a.ks[KS_DONE] != 0.0) return;
+  __shared__ double smw[TPB / 32][96];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* sm = smw[wib];
+  const size_t E = (size_t)a.E;
+  const double* in = WHICH == 0 ? a.y : a.z;
+  double* out = WHICH == 0 ? a.v : a.t;
+  const double* other = WHICH == 0 ? a.rh : a.s;
+  double d0 = 0, d1 = 0;
+  for (int e0 = (blockIdx.x * (TPB / 32) + wib) * 32; e0 < a.E; e0 += gridDim.x * TPB) {
+    const int nvalid = min(32, a.E - e0);
+    const int e = e0 + lane;
+    double s0 = 0, s1 = 0, s2 = 0, o0 = 0, o1 = 0, o2 = 0;
+    warp_load3(other + (size_t)e0 * 3, nvalid, sm, lane, o0, o1, o2);
+    if (lane < nvalid) {
+#pragma unroll
+      for (int bq = 0; bq < 4; ++bq) {
+        const int c = __ldg(a.col + (size_t)bq * E + e);
+        if (c < 0) continue;
+        const double* v = a.val + (size_t)(bq * 9) * E + e;
+        const double x0 = in[(size_t)c * 3], x1 = in[(size_t)c * 3 + 1], x2 = in[(size_t)c * 3 + 2];
+        s0 += __ldg(v) * x0 + __ldg(v + E) * x1 + __ldg(v + 2 * E) * x2;
+        s1 += __ldg(v + 3 * E) * x0 + __ldg(v + 4 * E) * x1 + __ldg(v + 5 * E) * x2;
+        s2 += __ldg(v + 6 * E) * x0 + __ldg(v + 7 * E) * x1 + __ldg(v + 8 * E) * x2;
+      }
+      d0 += o0 * s0 + o1 * s1 + o2 * s2;
+      if (WHICH == 1) d1 += s0 * s0 + s1 * s1 + s2 * s2;
+    }
+    warp_store3(out + (size_t)e0 * 3, nvalid, sm, lane, s0, s1, s2);
+  }
+  double t0, t1;
+  if (grid_sum2(d0, d1, a.ks, t0, t1) && threadIdx.x == 0) {
+    if (WHICH == 0) {
+      if (t0 == 0.0) a.ks[KS_DONE] = 2.0; else a.ks[KS_ALPHA] = a.ks[KS_RHONEW] / t0;
+    } else {
+      a.ks[KS_OMEGA] = (t1 > 0.0) ? t0 / t1 : 0.0;
+    }
+  }
+}
+
+// s = r - alpha v ; z = Dinv s
+__global__ void __launch_bounds__(TPB) k_kry_s(KryArgs a) {
+  if (a.ks[KS_DONE] != 0.0) return;
+  __shared__ double smw[TPB / 32][96];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* sm = smw[wib];
+  const size_t E = (size_t)a.E;
+  const double alpha = a.ks[KS_ALPHA];
+  for (int e0 = (blockIdx.x * (TPB / 32) + wib) * 32; e0 < a.E; e0 += gridDim.x * TPB) {
+    const int nvalid = min(32, a.E - e0);
+    const int e = e0 + lane;
+    double r0 = 0, r1 = 0, r2 = 0, v0 = 0, v1 = 0, v2 = 0, z0 = 0, z1 = 0, z2 = 0;
+    warp_load3(a.r + (size_t)e0 * 3, nvalid, sm, lane, r0, r1, r2);
+    warp_load3(a.v + (size_t)e0 * 3, nvalid, sm, lane, v0, v1, v2);
+    const double s0 = r0 - alpha * v0, s1 = r1 - alpha * v1, s2 = r2 - alpha * v2;
+    if (lane < nvalid) {
+      const double* d = a.dinv + e;
+      z0 = __ldg(d) * s0 + __ldg(d + E) * s1 + __ldg(d + 2 * E) * s2;
+      z1 = __ldg(d + 3 * E) * s0 + __ldg(d + 4 * E) * s1 + __ldg(d + 5 * E) * s2;
+      z2 = __ldg(d + 6 * E) * s0 + __ldg(d + 7 * E) * s1 + __ldg(d + 8 * E) * s2;
+    }
+    warp_store3(a.s + (size_t)e0 * 3, nvalid, sm, lane, s0, s1, s2);
+    warp_store3(a.z + (size_t)e0 * 3, nvalid, sm, lane, z0, z1, z2);
+  }
+}
+
+// x += alpha y + omega z ; r = s - omega t ; rr = (r, r) ; rho <- rho_new ; rho_new = (rh, r) ; convergence / breakdown
+__global__ void __launch_bounds__(TPB) k_kry_x(KryArgs a) {
+  if (a.ks[KS_DONE] != 0.0) return;
+  const double alpha = a.ks[KS_ALPHA], omega = a.ks[KS_OMEGA];
+  const long long n = 3LL * a.E;
+  double d0 = 0, d1 = 0;
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += (long long)gridDim.x * TPB) {
+    a.x[i] = a.x[i] + alpha * a.y[i] + omega * a.z[i];
+    const double r = a.s[i] + (-omega) * a.t[i];
+    a.r[i] = r;
+    d0 += r * r; d1 += a.rh[i] * r;
+  }
+  double rr, rho_new;
+  if (grid_sum2(d0, d1, a.ks, rr, rho_new) && threadIdx.x == 0) {
+    a.ks[KS_RR] = rr; a.ks[KS_RHO] = a.ks[KS_RHONEW]; a.ks[KS_RHONEW] = rho_new;
+    const double it = a.ks[KS_ITER] + 1.0;
+    a.ks[KS_ITER] = it;
+    if (rr <= a.ks[KS_STOP2] || it >= a.ks[KS_MAXIT]) a.ks[KS_DONE] = 1.0;
+    else if (rho_new == 0.0 || omega == 0.0) a.ks[KS_DONE] = 2.0;      // breakdown: report what was reached
+  }
 }
 
 // Petrov-Galerkin residual-based stabilisation (transport_tri_unstr.F90:239-267,278): one thread per element.
 // For P1 the gradient of T and inv_jac are constant over the element; rgi differs per Gauss point through T(gi).
-// mode 0: write diff_coe (3 per element) and stab (9 per element).
-// mode 1: additionally write diagonal block = diag0 + stab into the block-CSR and refresh its inverse.
+// mode 0: write diff_coe (3 per element) and stab (9 per element), both in ABI order [E][..].
+// mode 1: additionally write diagonal block = diag0 + stab into the block-CSR planes and refresh its inverse.
 struct StabArgs {
   const double* X; const double* tnew; const double* told;
   double* diff_coe; double* stab; const double* diag0; double* val; double* dinv;
@@ -371,9 +668,10 @@ struct StabArgs {
 
 __global__ void __launch_bounds__(TPB) k_unstr_stab(StabArgs a) {
   const double toler = 0.00000000001;
+  const size_t E = (size_t)a.E;
   for (int e = blockIdx.x * TPB + threadIdx.x; e < a.E; e += gridDim.x * TPB) {
-    const double* __restrict__ X = a.X + (size_t)e * 6;
-    const double x1 = __ldg(X), y1 = __ldg(X + 1), x2 = __ldg(X + 2), y2 = __ldg(X + 3), x3 = __ldg(X + 4), y3 = __ldg(X + 5);
+    const double x1 = __ldg(a.X + e), y1 = __ldg(a.X + E + e), x2 = __ldg(a.X + 2 * E + e), y2 = __ldg(a.X + 3 * E + e),
+                 x3 = __ldg(a.X + 4 * E + e), y3 = __ldg(a.X + 5 * E + e);
     const double A = x1 - x3, B = y1 - y3, C = x2 - x3, D = y2 - y3;
     const double detj = A * D - B * C;
     const double dw = 0.5 * fabs(detj) * (1.0 / 3.0);
@@ -418,18 +716,20 @@ __global__ void __launch_bounds__(TPB) k_unstr_stab(StabArgs a) {
     if (a.mode == 1) {
       double d[9];
 #pragma unroll
-      for (int q = 0; q < 9; ++q) { d[q] = a.diag0[(size_t)e * 9 + q] + st[q]; a.val[(size_t)e * 36 + q] = d[q]; }
+      for (int q = 0; q < 9; ++q) { d[q] = a.diag0[(size_t)q * E + e] + st[q]; a.val[(size_t)q * E + e] = d[q]; }
       const double c00 = d[4] * d[8] - d[5] * d[7], c01 = d[5] * d[6] - d[3] * d[8], c02 = d[3] * d[7] - d[4] * d[6];
       const double id = 1.0 / (d[0] * c00 + d[1] * c01 + d[2] * c02);
-      double* o = a.dinv + (size_t)e * 9;
+      double o[9];
       o[0] = c00 * id; o[1] = (d[2] * d[7] - d[1] * d[8]) * id; o[2] = (d[1] * d[5] - d[2] * d[4]) * id;
       o[3] = c01 * id; o[4] = (d[0] * d[8] - d[2] * d[6]) * id; o[5] = (d[2] * d[3] - d[0] * d[5]) * id;
       o[6] = c02 * id; o[7] = (d[1] * d[6] - d[0] * d[7]) * id; o[8] = (d[0] * d[4] - d[1] * d[3]) * id;
+#pragma unroll
+      for (int q = 0; q < 9; ++q) a.dinv[(size_t)q * E + e] = o[q];
     }
   }
 }
 
-inline int implicit_assemble(UnstrDev& u, double dt, double ux, double uy, int use_dir, int nsm, cudaStream_t st,
+inline int implicit_assemble(UnstrDev& u, double dt, double ux, double uy, double kdiff, int use_dir, int nsm, cudaStream_t st,
                              long long& nlaunch, std::string& err) {
   const size_t E = (size_t)u.E;
   if (!u.bsr_val) {
@@ -438,95 +738,75 @@ inline int implicit_assemble(UnstrDev& u, double dt, double ux, double uy, int u
     UCK(cudaMalloc(&u.dinv, E * 9 * sizeof(double)));
     UCK(cudaMalloc(&u.mdt, E * sizeof(double)));
     UCK(cudaMalloc(&u.work, E * 3 * 9 * sizeof(double)));
-    UCK(cudaMalloc(&u.dots, (size_t)(2 * nsm * 8 + 2) * sizeof(double)));
-    UCK(cudaMallocHost(&u.dots_host, 2 * sizeof(double)));
+    UCK(cudaMalloc(&u.dots, (size_t)(KS_PARTIAL + 2 * nsm * 8 + 2) * sizeof(double)));
+    UCK(cudaMemsetAsync(u.dots, 0, (size_t)(KS_PARTIAL + 2 * nsm * 8 + 2) * sizeof(double), st));
+    UCK(cudaMallocHost(&u.dots_host, KS_PARTIAL * sizeof(double)));
     UCK(cudaMalloc(&u.diag0, E * 9 * sizeof(double)));
     UCK(cudaMalloc(&u.stab, E * 12 * sizeof(double)));
   }
   BsrArgs a;
-  a.X = u.X; a.neig = u.neig; a.nside = u.nside; a.val = u.bsr_val; a.col = u.bsr_col; a.dinv = u.dinv; a.mdt = u.mdt; a.diag0 = u.diag0;
-  a.dt = dt; a.ux = ux; a.uy = uy; a.E = u.E; a.use_dir = use_dir;
+  a.X = u.X; a.neig = u.neig; a.nside = u.nside; a.dcen = u.dcen; a.val = u.bsr_val; a.col = u.bsr_col; a.dinv = u.dinv;
+  a.mdt = u.mdt; a.diag0 = u.diag0;
+  a.dt = dt; a.ux = ux; a.uy = uy; a.kdiff = kdiff; a.E = u.E; a.use_dir = use_dir;
   const int grid = std::max(1, std::min((u.E + TPB - 1) / TPB, nsm * 8));
   k_assemble_bsr<<<grid, TPB, 0, st>>>(a);
   nlaunch++;
   UCK(cudaGetLastError());
-  u.assembled = true; u.dt = dt; u.ux = ux; u.uy = uy;
+  u.assembled = true; u.dt = dt; u.ux = ux; u.uy = uy; u.kdiff = kdiff;
   return PAMG_OK;
 }
 
-// time loop of unstr_implicit (:214-387): told = tnew ; rhs = (M/dt) told ; solve (lhs + flux) tnew = rhs.
-// The reference inverts the dense matrix; here: BiCGStab right-preconditioned with the inverse diagonal blocks,
-// started from told, stopped at ||r|| <= tol ||rhs||.
+// time loop of unstr_implicit (:214-387): told = tnew ; rhs = (M/dt) told ; solve (lhs + flux) tnew = rhs, started
+// from told, stopped at ||r|| <= tol ||rhs|| (or after max_iters iterations / on a breakdown of the recurrence).
+// The host reads the convergence flag once per batch of KRY_BATCH iterations (kernels of a finished solve return at once).
+constexpr int KRY_BATCH = 16;
 inline int implicit_step(UnstrDev& u, int ntime, int nits, double tol, int max_iters, int* iters_total, double* relres,
-                         int nsm, cudaStream_t st, long long& nlaunch, std::string& err) {
+                         int nsm, cudaStream_t st, long long& nlaunch, std::string& err, long long* host_syncs = nullptr) {
   const int E = u.E;
   const long long n = 3LL * E;
   const int grid = std::max(1, std::min((E + TPB - 1) / TPB, nsm * 8));
-  const int gridv = (int)std::max(1LL, std::min((n + TPB - 1) / TPB, (long long)nsm * 8));
   double* W = u.work;
-  double *b = W, *r = W + n, *rh = W + 2 * n, *p = W + 3 * n, *v = W + 4 * n, *s = W + 5 * n, *t = W + 6 * n, *y = W + 7 * n;
-  double* z = W + 8 * n;
-  auto dots = [&](const double* x1, const double* y1, const double* x2, const double* y2, double& d0, double& d1) -> int {
-    k_dots<<<gridv, TPB, 0, st>>>(x1, y1, x2, y2, n, u.dots + 2);
-    k_dots_final<<<1, 256, 0, st>>>(u.dots + 2, gridv, u.dots);
-    nlaunch += 2;
-    UCK(cudaMemcpyAsync(u.dots_host, u.dots, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    UCK(cudaStreamSynchronize(st));
-    d0 = u.dots_host[0]; d1 = u.dots_host[1];
-    return PAMG_OK;
-  };
-  int total = 0, rc;
+  KryArgs a;
+  a.val = u.bsr_val; a.col = u.bsr_col; a.dinv = u.dinv; a.ks = u.dots; a.E = E;
+  a.b = W; a.r = W + n; a.rh = W + 2 * n; a.p = W + 3 * n; a.v = W + 4 * n; a.s = W + 5 * n; a.t = W + 6 * n; a.y = W + 7 * n;
+  a.z = W + 8 * n;
+  int total = 0;
   double worst = 0.0;
+  const double maxit = (double)max_iters;
   for (int it = 0; it < ntime; ++it) {
     for (int k = 0; k < nits; ++k) {
-      double* x = u.T[u.cur];
+      a.x = u.T[u.cur];
       // the scheme is linear and rhs depends on told only: passes k > 0 of the reference's nonlinear loop re-solve
       // the same system, which here starts converged and costs one residual evaluation
       if (k == 0) {
-        UCK(cudaMemcpyAsync(u.told, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        k_block_apply<<<grid, TPB, 0, st>>>(u.dinv, u.mdt, u.told, b, E, 1); nlaunch++;
+        UCK(cudaMemcpyAsync(u.told, a.x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        k_block_apply<<<grid, TPB, 0, st>>>(u.dinv, u.mdt, u.told, a.b, E, 1); nlaunch++;
       }
       if (u.with_stab) {   // INTENDED use (:367-368 commented at HEAD): diagonal blocks += stab(tnew_nonlin, told)
         StabArgs sa;
-        sa.X = u.X; sa.tnew = x; sa.told = u.told; sa.diff_coe = u.stab + (size_t)E * 9; sa.stab = u.stab; sa.diag0 = u.diag0;
+        sa.X = u.X; sa.tnew = a.x; sa.told = u.told; sa.diff_coe = u.stab + (size_t)E * 9; sa.stab = u.stab; sa.diag0 = u.diag0;
         sa.val = u.bsr_val; sa.dinv = u.dinv; sa.dt = u.dt; sa.ux = u.ux; sa.uy = u.uy; sa.E = E; sa.mode = 1;
         k_unstr_stab<<<grid, TPB, 0, st>>>(sa); nlaunch++;
       }
-      k_bsr_spmv<<<grid, TPB, 0, st>>>(u.bsr_val, u.bsr_col, x, b, r, E, 1); nlaunch++;
-      UCK(cudaMemcpyAsync(rh, r, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-      UCK(cudaMemsetAsync(p, 0, (size_t)n * sizeof(double), st));
-      UCK(cudaMemsetAsync(v, 0, (size_t)n * sizeof(double), st));
-      double bb, rr;
-      if ((rc = dots(b, b, r, r, bb, rr)) != PAMG_OK) return rc;
-      const double stop2 = tol * tol * bb;
-      double rho = 1.0, alpha = 1.0, omega = 1.0;
-      int iter = 0;
-      while (rr > stop2 && iter < max_iters) {
-        double rho_new, dummy;
-        if ((rc = dots(rh, r, nullptr, nullptr, rho_new, dummy)) != PAMG_OK) return rc;
-        if (rho_new == 0.0 || omega == 0.0) break;   // breakdown: report what was reached
-        const double beta = (rho_new / rho) * (alpha / omega);
-        k_lincomb<<<gridv, TPB, 0, st>>>(p, 1.0, r, beta, p, -beta * omega, v, n); nlaunch++;
-        k_block_apply<<<grid, TPB, 0, st>>>(u.dinv, u.mdt, p, y, E, 0); nlaunch++;
-        k_bsr_spmv<<<grid, TPB, 0, st>>>(u.bsr_val, u.bsr_col, y, nullptr, v, E, 0); nlaunch++;
-        double rhv;
-        if ((rc = dots(rh, v, nullptr, nullptr, rhv, dummy)) != PAMG_OK) return rc;
-        if (rhv == 0.0) break;
-        alpha = rho_new / rhv;
-        k_lincomb<<<gridv, TPB, 0, st>>>(s, 1.0, r, -alpha, v, 0.0, nullptr, n); nlaunch++;
-        k_block_apply<<<grid, TPB, 0, st>>>(u.dinv, u.mdt, s, z, E, 0); nlaunch++;
-        k_bsr_spmv<<<grid, TPB, 0, st>>>(u.bsr_val, u.bsr_col, z, nullptr, t, E, 0); nlaunch++;
-        double ts, tt;
-        if ((rc = dots(t, s, t, t, ts, tt)) != PAMG_OK) return rc;
-        omega = (tt > 0.0) ? ts / tt : 0.0;
-        k_lincomb<<<gridv, TPB, 0, st>>>(x, 1.0, x, alpha, y, omega, z, n); nlaunch++;
-        k_lincomb<<<gridv, TPB, 0, st>>>(r, 1.0, s, -omega, t, 0.0, nullptr, n); nlaunch++;
-        if ((rc = dots(r, r, nullptr, nullptr, rr, dummy)) != PAMG_OK) return rc;
-        rho = rho_new;
-        ++iter;
+      UCK(cudaMemcpyAsync(u.dots + KS_MAXIT, &maxit, sizeof(double), cudaMemcpyHostToDevice, st));
+      k_kry_init<<<grid, TPB, 0, st>>>(a, tol); nlaunch++;
+      for (;;) {
+        for (int j = 0; j < KRY_BATCH; ++j) {
+          k_kry_p<<<grid, TPB, 0, st>>>(a);
+          k_kry_spmv<0><<<grid, TPB, 0, st>>>(a);
+          k_kry_s<<<grid, TPB, 0, st>>>(a);
+          k_kry_spmv<1><<<grid, TPB, 0, st>>>(a);
+          k_kry_x<<<grid, TPB, 0, st>>>(a);
+          nlaunch += 5;
+        }
+        UCK(cudaMemcpyAsync(u.dots_host, u.dots, KS_PARTIAL * sizeof(double), cudaMemcpyDeviceToHost, st));
+        UCK(cudaStreamSynchronize(st));
+        if (host_syncs) ++*host_syncs;
+        if (u.dots_host[KS_DONE] != 0.0) break;
       }
       UCK(cudaGetLastError());
-      total += iter;
+      total += (int)u.dots_host[KS_ITER];
+      const double bb = u.dots_host[KS_BB], rr = u.dots_host[KS_RR];
       const double rel = bb > 0.0 ? sqrt(rr / bb) : 0.0;
       worst = std::max(worst, rel);
     }

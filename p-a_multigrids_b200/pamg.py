@@ -104,6 +104,9 @@ def lib():
         "pamg_unstr_download": (ci, [vp, _f64]),
         "pamg_explicit_step": (ci, [vp, cd, cd, cd, cd, ci, ci, ci, ci, ci]),
         "pamg_implicit_assemble": (ci, [vp, cd, cd, cd, ci]),
+        "pamg_implicit_assemble_diffusion": (ci, [vp, cd, cd, cd, cd, ci]),
+        "pamg_implicit_spmv_time": (ci, [vp, ci, C.POINTER(C.c_float)]),
+        "pamg_implicit_host_syncs": (ci, [vp, C.POINTER(C.c_int64)]),
         "pamg_implicit_get_bsr": (ci, [vp, vp, vp]),
         "pamg_implicit_apply": (ci, [vp, _f64, _f64]),
         "pamg_implicit_step": (ci, [vp, ci, ci, cd, ci, pint, pdbl]),
@@ -444,9 +447,20 @@ class SemiImplicitIterative:
         return out
 
     # -- unstructured implicit (unstr_implicit, transport_tri_unstr.F90:18) --------------------------
-    def implicit_assemble(self, dt, u_x, u_y, use_dir=False):
-        """Assemble (mass/dt - stiffness + upwind flux) into block-CSR on the device (:270-364)."""
-        self._ck(self.L.pamg_implicit_assemble(self.h, dt, u_x, u_y, int(use_dir)))
+    def implicit_assemble(self, dt, u_x, u_y, use_dir=False, k=0.0):
+        """Assemble (mass/dt - stiffness + upwind flux [+ k (volume diffusion + face penalty)]) into block-CSR on the
+        device (:270-364; the diffusion operator is that of get_A_x, transport_tri_semi.F90:412-448)."""
+        self._ck(self.L.pamg_implicit_assemble_diffusion(self.h, dt, u_x, u_y, float(k), int(use_dir)))
+
+    def implicit_spmv_ms(self, reps=20):
+        ms = C.c_float()
+        self._ck(self.L.pamg_implicit_spmv_time(self.h, reps, C.byref(ms)))
+        return ms.value
+
+    def implicit_host_syncs(self):
+        n = C.c_int64()
+        self._ck(self.L.pamg_implicit_host_syncs(self.h, C.byref(n)))
+        return n.value
 
     def implicit_bsr(self):
         """(val[E,4,3,3], col[E,4]) of the assembled operator; col is 0-based, -1 where a block is absent."""

@@ -82,6 +82,7 @@ def lib():
     L.orc_unstr_explicit.argtypes = [C.c_int, f64p, i32p, i32p, i32p, C.c_double, C.c_double, C.c_double,
                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, f64p]
     L.orc_unstr_implicit_assemble.argtypes = [C.c_int, f64p, i32p, i32p, C.c_double, C.c_double, C.c_double, C.c_int, f64p, f64p]
+    L.orc_unstr_implicit_assemble_diff.argtypes = [C.c_int, f64p, i32p, i32p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, f64p, f64p]
     L.orc_unstr_implicit.argtypes = [C.c_int, f64p, i32p, i32p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, f64p]
     L.orc_unstr_implicit.restype = C.c_int
     L.orc_unstr_stab.argtypes = [C.c_int, f64p, f64p, f64p, C.c_double, C.c_double, C.c_double, f64p, f64p]

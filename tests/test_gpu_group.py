@@ -85,8 +85,13 @@ def test_group_equals_single_gpu_and_oracle(label, devices, G_super):
     assert cg == cr and hg[-1] <= 1e-8 * hg[0]
     np.testing.assert_allclose(hg, hr, rtol=1e-6)
     assert np.max(np.abs(g.download(pamg.TNONLIN, 1) - ref.download(pamg.TNONLIN, 1))) <= 1e-10
-    cg2, _ = g.vcycle_solve(solver=pamg.JACOBI, max_cycles=40, tol=1e-8)      # already converged: graph path again
-    assert cg2 <= 1
+    # a second solve with the other smoother (another set of cached graphs), again from zero
+    for s in (g, ref):
+        s.fill(pamg.TNONLIN, 1, 0.0); s.copy(1, pamg.TNEW, pamg.TNONLIN)
+    cg2, hg2 = g.vcycle_solve(solver=pamg.JACOBI, max_cycles=40, tol=1e-8)
+    cr2, hr2 = ref.vcycle_solve(solver=pamg.JACOBI, max_cycles=40, tol=1e-8)
+    assert cg2 == cr2
+    np.testing.assert_allclose(hg2, hr2, rtol=1e-6)
     g.close(); ref.close()
 
 

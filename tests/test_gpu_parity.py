@@ -476,3 +476,83 @@ def test_errors_are_reported_not_swallowed(meshes):
         g.smoother(2, 1, 1)                                      # no such level
     with pytest.raises(pamg.PamgError):
         g.smoother(1, 9, 1)                                      # unknown solver (select case default)
+
+
+@pytest.mark.parametrize("name", ["split1", "test_sn2", "irregular", "900_ele"])
+@pytest.mark.parametrize("use_dir", [0, 1])
+def test_unstr_implicit_bsr_assembly_with_diffusion(meshes, name, use_dir):
+    """Block-CSR with the diffusion operator of the iterative path (volume term + face penalty, get_A_x
+    transport_tri_semi.F90:412-448 / matrices.F90:84-115) == the oracle's dense matrix; product and solve follow."""
+    mesh = meshes[name]
+    E = mesh.U
+    g = pamg.SemiImplicitIterative(pamg.default_params(), pamg.Mesh.synthetic(0, 1))
+    g.set_unstructured(mesh)
+    u, dt, k = (0.9, 0.3), 1e-2, 0.7
+    g.implicit_assemble(dt, u[0], u[1], use_dir=bool(use_dir), k=k)
+    val, col = g.implicit_bsr()
+    A = np.zeros((3 * E, 3 * E)); M = np.zeros((3 * E, 3 * E))
+    orc.lib().orc_unstr_implicit_assemble_diff(E, mesh.X, mesh.neig, mesh.fneig, u[0], u[1], k, dt, use_dir, A, M)
+    got = _bsr_to_dense(val, col)
+    assert np.max(np.abs(got - A)) <= 1e-13 * np.max(np.abs(A))
+    assert np.array_equal(col[:, 1:] >= 0, mesh.neig != 0)          # with diffusion every interior face couples
+    x = rng_field((E, 3), 11)
+    assert rel_l2(g.implicit_apply(x).ravel(), A @ x.ravel()) <= TOL
+    # one backward-Euler step: Krylov solve on the device (scalars of the recurrence device-resident) vs LAPACK
+    syncs0 = g.implicit_host_syncs()
+    g._ck(g.L.pamg_unstr_upload(g.h, x))
+    it, rr = np.zeros(1, np.int32), np.zeros(1)
+    import ctypes as C
+    g._ck(g.L.pamg_implicit_step(g.h, 1, 1, 1e-13, 800, it.ctypes.data_as(C.POINTER(C.c_int)), rr.ctypes.data_as(C.POINTER(C.c_double))))
+    sol = np.empty_like(x)
+    g._ck(g.L.pamg_unstr_download(g.h, sol))
+    ref = np.linalg.solve(A, M @ x.ravel())
+    assert rr[0] <= 1e-13 and rel_l2(sol.ravel(), ref) <= 1e-10
+    assert g.implicit_host_syncs() - syncs0 <= 1 + it[0] // 16       # one look at the flag per 16 iterations
+    # without advection the operator is symmetric
+    g.implicit_assemble(dt, 0.0, 0.0, use_dir=True, k=k)
+    S = _bsr_to_dense(*g.implicit_bsr())
+    assert np.max(np.abs(S - S.T)) <= 1e-13 * np.max(np.abs(S))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4])
+def test_semi_structured_operator_equals_unstructured_on_the_refined_mesh(tmp_path, n):
+    """`n_split.msh` fully unstructured == `0_split.msh` + n_split = n semi-structured (the same triangles
+    in another order).  The operator of the multigrid path (mass/dt - advection + upwind flux + diffusion + penalty, applied
+    through get_residual) must equal the block-CSR operator assembled on the gmsh-refined mesh, element by element (matched
+    by their vertex sets), for the same nodal function on both meshes."""
+    coarse = pamg.Mesh.read_msh(write_msh("split0", str(tmp_path / "split0.msh")))
+    fine = pamg.Mesh.read_msh(write_msh("split%d" % n, str(tmp_path / "fine.msh")))
+    assert fine.U == coarse.U * 4 ** n
+    u, dt, k = (0.4, -0.7), 2e-2, 0.9
+    gp = pamg.default_params(n_split=n, multi_levels=1, dt=dt, k=k, u_x=u[0], u_y=u[1])
+    g = pamg.SemiImplicitIterative(gp, coarse)
+    xc, _, _ = g.output_fields()                                  # child coordinates (U, C, 3, 2)
+
+    def field(X):      # a smooth nodal function: the same function on both meshes
+        return np.sin(3.0 * X[..., 0]) * np.cos(2.0 * X[..., 1]) + 0.5
+
+    def residual_of(T):
+        g.upload(pamg.TNEW, 1, T); g.copy(1, pamg.TNONLIN, pamg.TNEW); g.update_overlaps(1)
+        g.get_residual(1)
+        return g.download(pamg.RES, 1)
+    g.fill(pamg.TOLD, 1, 0.0)
+    d = field(xc)
+    # r = b - A T (+ boundary data): the difference of two residuals is -A d, right-hand side and Dirichlet data cancel
+    Ad_semi = residual_of(np.zeros_like(d)) - residual_of(d)
+    g2 = pamg.SemiImplicitIterative(pamg.default_params(), pamg.Mesh.synthetic(0, 1))
+    g2.set_unstructured(fine)
+    g2.implicit_assemble(dt, u[0], u[1], use_dir=True, k=k)
+    Ad_unstr = g2.implicit_apply(field(fine.X))
+    key = lambda p: (round(float(p[0]), 9), round(float(p[1]), 9))
+
+    def by_element(X, V):
+        out = {}
+        for e in range(X.shape[0]):
+            out[tuple(sorted(key(p) for p in X[e]))] = {key(p): V[e, i] for i, p in enumerate(X[e])}
+        return out
+    A = by_element(xc.reshape(-1, 3, 2), Ad_semi.reshape(-1, 3))
+    B = by_element(fine.X, Ad_unstr)
+    assert set(A) == set(B) and len(A) == fine.U
+    scale = float(np.max(np.abs(Ad_unstr)))
+    worst = max(abs(A[e][p] - B[e][p]) for e in A for p in A[e])
+    assert worst <= 1e-11 * scale, (worst, scale)

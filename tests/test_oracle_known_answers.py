@@ -315,3 +315,53 @@ def test_unstr_stab_known_answer_and_invariants(tmp_path):
     assert np.allclose(S, S.transpose(0, 2, 1), rtol=1e-12, atol=0)
     assert np.max(np.abs(S.sum(axis=2))) <= 1e-12 * np.max(np.abs(S))
     assert np.min(np.linalg.eigvalsh(S)) >= -1e-12 * np.max(np.abs(S))
+
+
+def test_unstr_implicit_diffusion_blocks(tmp_path):
+    """orc_unstr_implicit_assemble_diff: the diffusion part added to the implicit operator is the iterative path's (volume
+    term k A grad.grad + face penalty k/dx): symmetric, positive semi-definite, constants in its kernel away from the
+    domain boundary, zero for k = 0, linear in k, and - the anchor to the multigrid path - identical to what
+    orc_semi_residual applies on the same triangles (0_split.msh + n_split = 1 == 1_split.msh)."""
+    m = orc.read_msh(write_msh("split1", str(tmp_path / "s1.msh")))
+    fneig, _ = orc.neig_data(m["neig"], m["dir"])
+    E = m["X"].shape[0]; N = 3 * E
+    dt = 1e-2
+
+    def assemble(u, k):
+        A = np.zeros((N, N)); M = np.zeros((N, N))
+        orc.lib().orc_unstr_implicit_assemble_diff(E, m["X"], m["neig"], fneig, u[0], u[1], k, dt, 1, A, M)
+        return A, M
+    A0, M = assemble((0.0, 0.0), 0.0)
+    assert np.allclose(A0, M, atol=0)
+    A1, _ = assemble((0.0, 0.0), 1.0)
+    D = A1 - M                                                     # the diffusion operator alone
+    assert np.max(np.abs(D - D.T)) <= 1e-13 * np.max(np.abs(D))
+    assert np.linalg.eigvalsh(0.5 * (D + D.T)).min() >= -1e-10 * np.max(np.abs(D))
+    interior = np.all(m["neig"] != 0, axis=1)
+    rows = (D @ np.ones(N)).reshape(E, 3)
+    assert np.max(np.abs(rows[interior])) <= 1e-12 * np.max(np.abs(D))
+    assert np.max(np.abs(rows[~interior])) > 1e-3                   # Dirichlet faces keep their own penalty part
+    A3, _ = assemble((0.0, 0.0), 3.0)
+    assert np.allclose(A3 - M, 3.0 * D, rtol=1e-13, atol=1e-13 * np.max(np.abs(D)))
+    # against the semi-structured operator on the same triangles
+    u, k = (0.4, -0.7), 0.9
+    A, _ = assemble(u, k)
+    c = orc.read_msh(write_msh("split0", str(tmp_path / "s0.msh")))
+    cf, _ = orc.neig_data(c["neig"], c["dir"])
+    s = orc.Semi(orc.intended_params(1, 1, dt=dt, k=k, u=u), c["X"], c["neig"], cf, c["dir"])
+    from helpers import child_coordinates
+    xc = child_coordinates(orc, c["X"], 1)
+    f = lambda X: np.sin(3.0 * X[..., 0]) * np.cos(2.0 * X[..., 1]) + 0.5
+
+    def residual_of(T):
+        s.field(orc.TNEW)[:] = T; s.update_overlaps(1); s.residual(1)
+        return s.field(orc.RES).copy()
+    d = f(xc)
+    Ad_semi = (residual_of(np.zeros_like(d)) - residual_of(d)).reshape(-1, 3)
+    Ad_unstr = (A @ f(m["X"]).ravel()).reshape(E, 3)
+    key = lambda p: (round(float(p[0]), 9), round(float(p[1]), 9))
+    by = lambda X, V: {tuple(sorted(key(p) for p in X[e])): {key(p): V[e, i] for i, p in enumerate(X[e])} for e in range(X.shape[0])}
+    P, Q = by(xc.reshape(-1, 3, 2), Ad_semi), by(m["X"], Ad_unstr)
+    assert set(P) == set(Q)
+    worst = max(abs(P[e][p] - Q[e][p]) for e in P for p in P[e])
+    assert worst <= 1e-11 * np.max(np.abs(Ad_unstr))
