@@ -52,6 +52,12 @@ struct NcclApi {
 NcclApi g_nccl;
 }  // namespace
 
+// Kernels of different GPUs (or of two parts on one GPU) wait for each other's stores inside the halo exchange.  With lazy
+// module loading the FIRST launch of a function can block until running kernels have finished - a deadlock if the running
+// kernel is the one that waits.  Ask for eager loading unless the application has chosen a mode itself (this runs when the
+// library is loaded, normally before the CUDA context exists); configure_kernels additionally touches every kernel.
+__attribute__((constructor)) static void pamg_request_eager_loading() { setenv("CUDA_MODULE_LOADING", "EAGER", 0); }
+
 struct pamg_handle;
 namespace { void p2p_close(pamg_handle* h); }
 // words of pamg_handle::agg_words (device memory): block counter, per-destination transfer numbers, per-sender flags
@@ -90,12 +96,15 @@ struct pamg_handle {
   // Dirichlet data of domain-boundary faces (pamg_set_boundary_data): global [U_global][3] on the host, local copy on the device
   std::vector<int32_t> bc_kind_h; std::vector<double> bc_val_h;
   int32_t* bc_kind = nullptr; double* bc_val = nullptr;
+  // both halo-strip buffers of every level in ONE allocation, kept resident in L2 (access-policy window on the stream): the
+  // strips are written by one sweep and read by the next, a whole field of streaming traffic later
+  double* strip_arena = nullptr; size_t strip_arena_bytes = 0;
+  bool l2_persist = true;       // PAMG_L2_PERSIST=0 disables the window
   std::vector<LevelDev> lev;
   double* partial = nullptr; int npartial = 0; int last_partials = 0;
   double* out3 = nullptr;         // device
   double* out3_host = nullptr;    // pinned
   double* scratch = nullptr; size_t scratch_bytes = 0;  // L2 flush
-  double* stage = nullptr; size_t stage_bytes = 0;      // pinned staging for host-buffer entry points
   int kernel_mode = 4;  // 4 window kernel (default; 1-D TMA tile ring, all neighbours from shared memory), 1 pipelined 1-D TMA tiles,
                         // 3 branch-free direct; PAMG_KERNEL=win|tma1d|direct2 (A/B and the families used on small / deep levels)
   // where a sweep takes the exterior values of faces between local parents from (PAMG_HALO=strips|direct|fused):
@@ -465,6 +474,20 @@ int launch_halo(pamg_handle* h, int level, int what) {
   CK(cudaGetLastError());
   if (what == 1) return PAMG_OK;
   if (cut && !fused_x) { int rc = exchange_halo_nccl(h, L, L.ovlb[L.ovl_cur]); if (rc) return rc; }
+  if (what == 0 && cut) {
+    // update_overlaps as written also fills t_overlap_old (splitting.F90:1259-1262): a second exchange carries the told
+    // values of the cut faces into the neighbours' old strips (the sweeps never read them; the entry point returns them)
+    HaloArgs b = a;
+    b.tnew = L.told; b.ovl = L.ovl_old; b.with_old = 0; b.what = 2;
+    if (fused_x) { int rc = p2p_args(h, L, L.ovl_old, b.x); if (rc) return rc; }
+    const long long n2 = (long long)b.ncut * L.S;
+    int g2 = grid_for(h, n2);
+    if (fused_x) g2 = std::min(g2, h->nsm * std::min(std::max(h->kc.halo, 1), 4));
+    k_halo<<<g2, TPB, 0, h->stream>>>(b);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (!fused_x) { int rc = exchange_halo_nccl(h, L, L.ovl_old); if (rc) return rc; }
+  }
   L.cut_valid = true;
   if (what != 2) L.strips_valid = true;
   return PAMG_OK;
@@ -527,6 +550,29 @@ int configure_kernels(pamg_handle* h) {
   if ((rc = configure_one(h, k_gs_win, TPB, GSW_SMEM_BYTES, h->kc.gs))) return rc;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->kc.halo, k_halo, TPB, 0));
   if (h->kc.halo < 1) h->kc.halo = 1;
+  // Load every other kernel of the partitioned path NOW.  With lazy module loading (the CUDA 12 default) the first launch
+  // of a function may have to wait for running kernels to finish; a halo kernel of one part that is polling for a peer
+  // whose next kernel has never been launched in this process would then wait for ever (seen with two parts on one device).
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, k_halo));
+  CK(cudaFuncGetAttributes(&fa, k_build_rhs));
+  CK(cudaFuncGetAttributes(&fa, k_restrict));
+  CK(cudaFuncGetAttributes(&fa, k_prolong_literal));
+  CK(cudaFuncGetAttributes(&fa, k_prolong_p1));
+  CK(cudaFuncGetAttributes(&fa, k_reduce_partials));
+  CK(cudaFuncGetAttributes(&fa, k_fill));
+  CK(cudaFuncGetAttributes(&fa, k_push));
+  CK(cudaFuncGetAttributes(&fa, k_wait_flags));
+  CK(cudaFuncGetAttributes(&fa, k_spin));
+  CK(cudaFuncGetAttributes(&fa, k_output_fields));
+  CK(cudaFuncGetAttributes(&fa, k_element_direct2<MODE_JACOBI, true>));
+  CK(cudaFuncGetAttributes(&fa, k_element_direct2<MODE_JACOBI, false>));
+  CK(cudaFuncGetAttributes(&fa, k_element_direct2<MODE_RESID, true>));
+  CK(cudaFuncGetAttributes(&fa, k_element_direct2<MODE_RESID, false>));
+  CK(cudaFuncGetAttributes(&fa, k_element_direct2<MODE_RICH, true>));
+  CK(cudaFuncGetAttributes(&fa, k_element_direct2<MODE_RICH, false>));
+  CK(cudaFuncGetAttributes(&fa, k_element_direct2<MODE_GS, true>));
+  CK(cudaFuncGetAttributes(&fa, k_element_direct2<MODE_GS, false>));
   h->kc.done = true;
   return PAMG_OK;
 }
@@ -957,23 +1003,15 @@ void free_levels(pamg_handle* h) {
   h->vc_graphs.clear();
   for (auto& L : h->lev) {
     cudaFree(L.T[0]); cudaFree(L.T[1]); cudaFree(L.spare); cudaFree(L.told); cudaFree(L.rhs); cudaFree(L.res);
-    cudaFree(L.ovlb[0]); cudaFree(L.ovlb[1]); cudaFree(L.ovl_old); cudaFree(L.pc);
+    cudaFree(L.ovl_old); cudaFree(L.pc);
   }
   h->lev.clear();
+  cudaFree(h->strip_arena); h->strip_arena = nullptr; h->strip_arena_bytes = 0;
   cudaFree(h->xg); cudaFree(h->strip_of); cudaFree(h->dst_strip); cudaFree(h->rev); cudaFree(h->hmap);
   cudaFree(h->nsrc); cudaFree(h->cut_lf); cudaFree(h->bc_kind); cudaFree(h->bc_val);
   cudaFree(h->partial);
   h->xg = nullptr; h->strip_of = h->dst_strip = h->rev = h->hmap = h->nsrc = h->cut_lf = h->bc_kind = nullptr;
   h->bc_val = nullptr; h->partial = nullptr;
-}
-
-int ensure_stage(pamg_handle* h, size_t bytes) {
-  if (h->stage_bytes >= bytes) return PAMG_OK;
-  if (h->stage) cudaFreeHost(h->stage);
-  h->stage = nullptr; h->stage_bytes = 0;
-  CK(cudaMallocHost(&h->stage, bytes));
-  h->stage_bytes = bytes;
-  return PAMG_OK;
 }
 
 }  // namespace
@@ -1040,6 +1078,8 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
     if (pt && atof(pt) > 0.0) h->p2p_timeout_ns = (unsigned long long)(atof(pt) * 1e9);
     const char* dg = getenv("PAMG_DEBUG_GAP_NS");
     if (dg) h->debug_gap_ns = atoll(dg);
+    const char* lp = getenv("PAMG_L2_PERSIST");
+    if (lp && lp[0] == '0') h->l2_persist = false;
     const char* hl = getenv("PAMG_HALO");
     if (hl && !strcmp(hl, "strips")) h->halo_mode = 0;
     if (hl && !strcmp(hl, "direct")) h->halo_mode = 1;
@@ -1143,7 +1183,6 @@ void pamg_destroy(pamg_handle* h) {
   free_levels(h);
   unstr_free(h->un);
   cudaFree(h->out3); cudaFreeHost(h->out3_host); cudaFree(h->scratch);
-  if (h->stage) cudaFreeHost(h->stage);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->pev) if (e) cudaEventDestroy(e);
   if (h->up_stream) { cudaStreamSynchronize(h->up_stream); cudaStreamSynchronize(h->down_stream); cudaStreamDestroy(h->up_stream); cudaStreamDestroy(h->down_stream); cudaEventDestroy(h->ev_up); cudaEventDestroy(h->ev_comp); cudaEventDestroy(h->ev_down[0]); cudaEventDestroy(h->ev_down[1]); }
@@ -1213,6 +1252,34 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
     CK(cudaMemcpy(h->bc_val, h->bc_val_h.data() + (size_t)first * 3, (size_t)U * 3 * sizeof(double), cudaMemcpyHostToDevice));
   }
   h->lev.resize(h->p.multi_levels);
+  {
+    size_t tot = 0;
+    for (int il = 0; il < h->p.multi_levels; ++il) {
+      const size_t S = (size_t)1 << (h->p.n_split - il);
+      tot += 2 * (((size_t)(h->plan.nstrips + h->plan.nsend) * 3 * S * sizeof(double) + 255) / 256 * 256);
+    }
+    CK(cudaMalloc(&h->strip_arena, tot));
+    CK(cudaMemsetAsync(h->strip_arena, 0, tot, h->stream));
+    h->strip_arena_bytes = tot;
+    if (h->l2_persist && !h->shared_stream) {
+      // best effort: devices / driver modes without persisting L2 simply run without the window
+      cudaDeviceProp prop;
+      if (cudaGetDeviceProperties(&prop, h->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+        const size_t want = std::min((size_t)prop.persistingL2CacheMaxSize, std::max(tot, (size_t)1 << 20));
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+        cudaStreamAttrValue av;
+        std::memset(&av, 0, sizeof(av));
+        av.accessPolicyWindow.base_ptr = h->strip_arena;
+        av.accessPolicyWindow.num_bytes = std::min(tot, (size_t)prop.accessPolicyMaxWindowSize);
+        av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)std::max(tot, (size_t)1));
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        (void)cudaGetLastError();
+      }
+    }
+  }
+  size_t arena_off = 0;
   std::vector<double> pc((size_t)U * NPC);
   for (int il = 0; il < h->p.multi_levels; ++il) {
     LevelDev& L = h->lev[il];
@@ -1225,8 +1292,11 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
     CK(cudaMemsetAsync(L.told, 0, fb, h->stream)); CK(cudaMemsetAsync(L.rhs, 0, fb, h->stream));
     CK(cudaMemsetAsync(L.res, 0, fb, h->stream));
     const size_t ob = (size_t)(h->plan.nstrips + h->plan.nsend) * 3 * L.S * sizeof(double);
-    CK(cudaMalloc(&L.ovlb[0], ob)); CK(cudaMalloc(&L.ovlb[1], ob)); CK(cudaMalloc(&L.ovl_old, ob));
-    CK(cudaMemsetAsync(L.ovlb[0], 0, ob, h->stream)); CK(cudaMemsetAsync(L.ovlb[1], 0, ob, h->stream));
+    const size_t obp = (ob + 255) / 256 * 256;
+    L.ovlb[0] = reinterpret_cast<double*>(reinterpret_cast<char*>(h->strip_arena) + arena_off);
+    L.ovlb[1] = reinterpret_cast<double*>(reinterpret_cast<char*>(h->strip_arena) + arena_off + obp);
+    arena_off += 2 * obp;
+    CK(cudaMalloc(&L.ovl_old, ob));
     CK(cudaMemsetAsync(L.ovl_old, 0, ob, h->stream));  // :207
     L.ovl_cur = 0; L.strips_valid = false; L.cut_valid = false;
     for (int u = 0; u < U; ++u)

@@ -173,7 +173,7 @@ static void child_vertices(const double* P, int n, int ele, double* x /* [3][2] 
 }
 
 int Mesh::synthetic(int kp, int G, Mesh& out) {
-  if (kp < 0 || kp > 10 || G < 1) return PAMG_ERR_ARG;
+  if (kp < 0 || kp > 12 || G < 1 || (long long)G << (2 * kp) > (1ll << 26)) return PAMG_ERR_ARG;
   out = Mesh();
   const int per = 1 << (2 * kp);
   out.X.resize((size_t)G * per * 6);

@@ -55,6 +55,7 @@ def test_group_equals_single_gpu_and_oracle(label, devices, G_super):
     o.field(orc.TNEW)[:] = T; o.update_overlaps(1)
     ovg = g.overlap(1)
     assert np.array_equal(ovg, ref.overlap(1))
+    assert np.array_equal(g.overlap(1, old=True), ref.overlap(1, old=True))      # t_overlap_old travels too
     assert rel_l2(ovg, o.overlap(1)) <= 1e-13          # (Dirichlet entries: device sin() against libm)
     # sweeps: Jacobi then two-colour GS
     for s in (g, ref):
