@@ -698,32 +698,38 @@ __global__ void __launch_bounds__(TPB, 3) k_element_win(ElemArgs a) {
 // work.  `tile`: 256 results in shared memory, first child k0 (0-based inside parent u); m0: row of k0 (kept across
 // tiles of a parent).  Children on parent side 1 are the odd-ipos children of row 1, on side 3 the first and on side 2 the
 // last child of every row (surf_ele, splitting.F90:434-449); the slot is the position or its mirror image (:1256-1391).
-__device__ __forceinline__ void strips_from_tile(const ElemArgs& a, const double* __restrict__ tile, int u, int k0, int s, int& m0,
-                                                 int lane) {
+struct StripDst { int d0, d1, d2, rv; };     // destination strips of the parent's three sides (-1: none) and reversal bits
+__device__ __forceinline__ StripDst strip_dst_load(const ElemArgs& a, int u, int lane) {
+  int d = 0, rv = 0;
+  if (lane < 3) { d = __ldg(a.dst_strip + u * 3 + lane); rv = __ldg(a.rev + u * 3 + lane) << lane; }
+  StripDst o;
+  o.d0 = __shfl_sync(0xffffffffu, d, 0); o.d1 = __shfl_sync(0xffffffffu, d, 1); o.d2 = __shfl_sync(0xffffffffu, d, 2);
+  o.rv = __shfl_sync(0xffffffffu, rv, 0) | __shfl_sync(0xffffffffu, rv, 1) | __shfl_sync(0xffffffffu, rv, 2);
+  return o;
+}
+
+__device__ __forceinline__ void strips_from_tile(const ElemArgs& a, const double* __restrict__ tile, const StripDst& sd, int k0,
+                                                 int s, int& m0, int lane) {
   const int S = 1 << s, b = 2 << s;
   const int kend = k0 + TPB;
-  int d = 0, rv = 0;
-  if (lane < 3) { d = __ldg(a.dst_strip + u * 3 + lane); rv = __ldg(a.rev + u * 3 + lane); }
-  const int d0 = __shfl_sync(0xffffffffu, d, 0), d1 = __shfl_sync(0xffffffffu, d, 1), d2 = __shfl_sync(0xffffffffu, d, 2);
-  const int r0 = __shfl_sync(0xffffffffu, rv, 0), r1 = __shfl_sync(0xffffffffu, rv, 1), r2 = __shfl_sync(0xffffffffu, rv, 2);
   auto put = [&](int dst, int rvf, int pos, int k) {
     const int slot = rvf ? (S - 1 - pos) : pos;
     const double* t = tile + (k - k0) * 3;
     double* e = a.ovl_next + ((size_t)dst * S + slot) * 3;
     e[0] = t[0]; e[1] = t[1]; e[2] = t[2];
   };
-  if (d0 >= 0 && k0 < b - 1) {                       // row 1: children k = 0, 2, 4, .. b-2 at positions k/2
+  if (sd.d0 >= 0 && k0 < b - 1) {                    // row 1: children k = 0, 2, 4, .. b-2 at positions k/2
     const int e1 = min(kend, b - 1);
-    for (int k = k0 + 2 * lane; k < e1; k += 64) put(d0, r0, k >> 1, k);
+    for (int k = k0 + 2 * lane; k < e1; k += 64) put(sd.d0, sd.rv & 1, k >> 1, k);
   }
   while ((m0 + 1) * (b - m0 - 1) <= k0) ++m0;        // row (0-based) that holds child k0
-  if (d1 >= 0 || d2 >= 0) {
+  if (sd.d1 >= 0 || sd.d2 >= 0) {
     for (int m = m0 + lane; m < S; m += 32) {
       const int first = m * (b - m);
       if (first >= kend) break;
       const int last = (m + 1) * (b - m - 1) - 1;
-      if (d2 >= 0 && first >= k0) put(d2, r2, m, first);
-      if (d1 >= 0 && last < kend) put(d1, r1, m, last);
+      if (sd.d2 >= 0 && first >= k0) put(sd.d2, sd.rv & 4, m, first);
+      if (sd.d1 >= 0 && last < kend) put(sd.d1, sd.rv & 2, m, last);
     }
   }
 }
@@ -796,6 +802,7 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
       for (long long t = tbeg; t < min(tend, tbeg + 3); ++t) issueB(t);
     }
     int m0 = 0, u_m0 = -1;
+    StripDst sd = {-1, -1, -1, 0};
     for (long long p = tbeg; p < tend; ++p) {
       const int it = (int)(p - tbeg);
       named_sync(1 + (it & 3), WIN2_THREADS);            // every consumer warp has written tile p
@@ -809,8 +816,8 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
       if (p + 3 < tend) issueB(p + 3);
       if (MODE != MODE_RESID && a.ovl_next) {            // halo strips of the next sweep from the finished tile
         const int u = (int)((p * TPB) >> twos);
-        if (u != u_m0) { m0 = 0; u_m0 = u; }
-        strips_from_tile(a, sB + (it & (WIN_NB - 1)) * 3 * TPB, u, (int)((p * TPB) & Cmask), s, m0, lane);
+        if (u != u_m0) { m0 = 0; u_m0 = u; sd = strip_dst_load(a, u, lane); }      // once per parent
+        strips_from_tile(a, sB + (it & (WIN_NB - 1)) * 3 * TPB, sd, (int)((p * TPB) & Cmask), s, m0, lane);
       }
     }
     if (lane == 0) tma_store_wait_all();
@@ -1178,6 +1185,7 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
     if (lane == 0) for (long long t = tlo; t < min(thi, t0 + 6); ++t) issueT(t);
     for (long long t = dlo; t <= min(dhi, dlo + 3); ++t) issueB(t);
     int m0 = 0, u_m0 = -1;
+    StripDst sd = {-1, -1, -1, 0};
     for (long long tile = t0; tile < tend; ++tile) {
       const int it = (int)(tile - t0);
       named_sync(1 + (it & 3), WIN2_THREADS);            // every consumer warp has finished iteration `tile`
@@ -1193,8 +1201,8 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
       if (tile + 4 >= dlo + 4 && tile + 4 <= dhi) issueB(tile + 4);   // rhs slot of tile: consumed by its up children
       if (a.ovl_next && tile >= tbeg) {                  // halo strips of the next sweep from the finished tile
         const int u = (int)((tile * TPB) >> twos);
-        if (u != u_m0) { m0 = 0; u_m0 = u; }
-        strips_from_tile(a, sT + (tile & (WIN_NT - 1)) * 3 * TPB, u, (int)((tile * TPB) & Cmask), s, m0, lane);
+        if (u != u_m0) { m0 = 0; u_m0 = u; sd = strip_dst_load(a, u, lane); }      // once per parent
+        strips_from_tile(a, sT + (tile & (WIN_NT - 1)) * 3 * TPB, sd, (int)((tile * TPB) & Cmask), s, m0, lane);
       }
     }
     if (lane == 0) tma_store_wait_all();

@@ -27,6 +27,7 @@ struct Args {
   double cfl = -1, dx = -1, ux = 0, uy = 0, k = 1.0, tol = 1e-8;
   int nits = 2, njac = 10, exact_minv = 0, use_dir = 0, max_cycles = 50;
   int device = 0;
+  std::vector<int> devices;        // --gpus N / --devices a,b,..: this ONE process drives several GPUs (pamg_create_multi)
 };
 
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -73,6 +74,11 @@ int main(int argc, char** argv) {
     else if (flag(i, argc, argv, "--tol", v)) a.tol = std::atof(v.c_str());
     else if (flag(i, argc, argv, "--max_cycles", v)) a.max_cycles = std::atoi(v.c_str());
     else if (flag(i, argc, argv, "--device", v)) a.device = std::atoi(v.c_str());
+    else if (flag(i, argc, argv, "--gpus", v)) { a.devices.clear(); for (int d = 0; d < std::atoi(v.c_str()); ++d) a.devices.push_back(d); }
+    else if (flag(i, argc, argv, "--devices", v)) {
+      a.devices.clear();
+      for (size_t pos = 0; pos < v.size();) { a.devices.push_back(std::atoi(v.c_str() + pos)); pos = v.find(',', pos); if (pos == std::string::npos) break; ++pos; }
+    }
     else { std::fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
   }
   // literal defaults of main.F90:28 (mode 4) and :46-47 (mode 9)
@@ -136,7 +142,12 @@ int main(int argc, char** argv) {
   p.n_multigrid = a.n_multigrid; p.dt = a.cfl * a.dx; p.k = a.k; p.u_x = a.ux; p.u_y = a.uy;
   p.source_coef = (a.literal ? -2.0 : 2.0) * a.k;
   pamg_handle* h = nullptr;
-  if ((rc = pamg_create(&p, a.device, &h)) != PAMG_OK) return die(nullptr, "pamg_create (no CUDA device? there is no CPU fallback)", rc);
+  // the reference's driver is one serial process (main.F90:16-51): with --gpus N the same single host thread drives N
+  // devices through one handle; the library cuts the parents into N contiguous blocks and every call below stays as it is
+  if (a.devices.size() > 1 && a.mode == 9) rc = pamg_create_multi(&p, (int)a.devices.size(), a.devices.data(), &h);
+  else rc = pamg_create(&p, a.devices.size() == 1 ? a.devices[0] : a.device, &h);
+  if (rc != PAMG_OK) return die(nullptr, "pamg_create (no CUDA device? there is no CPU fallback)", rc);
+  if (a.devices.size() > 1) std::printf("|   GPUs driven by this process = %zu\n", a.devices.size());
 
   if (a.mode == 9) {
     if ((rc = pamg_set_parents(h, U, X.data(), neig.data(), fneig.data(), dir.data()))) return die(h, "pamg_set_parents", rc);

@@ -76,3 +76,24 @@ def test_mode1_trans_rec_writes_the_reference_dumps(tmp_path):
     assert np.array_equal(num[:, :2], g["numerical"][:, :2])
     assert np.max(np.abs(num[:, 2] - g["numerical"][:, 2])) <= 3e-5       # the reference computed in single precision
     assert np.allclose(ana[:, 0], g["analytical"][:, 0], atol=1e-5) and np.array_equal(ana[:, 1], g["analytical"][:, 1])
+
+
+def test_mode9_on_several_gpus_from_one_process(tmp_path):
+    """--devices 0,0,0 (or real GPUs when the box has them): the serial driver's call sequence, unchanged, on a handle that
+    fans out over several parts; the printed checksums equal the one-GPU run."""
+    path = write_msh("900_ele", str(tmp_path / "m.msh"))
+    n = pamg.device_count()
+    devs = ",".join(str(i) for i in range(min(n, 4))) if n >= 2 else "0,0,0"
+    common = ["--mode", 9, "--mesh", path, "--intended", "--n_split", 3, "--multi_levels", 3, "--ntime", 2, "--solver", 3,
+              "--region", 9, "--ux", 0.1, "--uy", 0.1]
+    env_timeout = dict(os.environ, PAMG_P2P_TIMEOUT_S="30")
+    one = subprocess.run([HOST, *map(str, common)], capture_output=True, text=True, timeout=300, env=env_timeout)
+    many = subprocess.run([HOST, *map(str, common), "--devices", devs], capture_output=True, text=True, timeout=300, env=env_timeout)
+    assert one.returncode == 0 and many.returncode == 0, one.stdout + one.stderr + many.stdout + many.stderr
+    pat = r"tnew: sum ([-+0-9.e]+) min ([-+0-9.e]+) max ([-+0-9.e]+)"
+    a, b = re.search(pat, one.stdout), re.search(pat, many.stdout)
+    assert a and b, many.stdout
+    for i in (1, 2, 3):
+        assert abs(float(a.group(i)) - float(b.group(i))) <= 1e-9 * max(1.0, abs(float(a.group(i))))
+    assert re.findall(r"V-cycles (\d+)", one.stdout) == re.findall(r"V-cycles (\d+)", many.stdout)
+    assert "GPUs driven by this process" in many.stdout
