@@ -77,8 +77,11 @@ __device__ __forceinline__ void tri_geo(const double* __restrict__ X, size_t E, 
   const double A = x1 - x3, B = y1 - y3, C = x2 - x3, D = y2 - y3;
   detj = A * D - B * C;
   g.area = 0.5 * fabs(detj);
-  g.gx[0] = D / detj; g.gx[1] = -B / detj; g.gx[2] = -(D / detj) - (-B / detj);
-  g.gy[0] = -C / detj; g.gy[1] = A / detj; g.gy[2] = -(-C / detj) - (A / detj);
+  // (fp64 division costs ~40 issue slots on sm_100a and this kernel family is issue-bound, not HBM-bound, with them: one
+  // reciprocal per element instead of six quotients - a last-bit difference to the reference's D/detj, far inside 1e-12)
+  const double idet = 1.0 / detj;
+  g.gx[0] = D * idet; g.gx[1] = -B * idet; g.gx[2] = -(g.gx[0] + g.gx[1]);
+  g.gy[0] = -C * idet; g.gy[1] = A * idet; g.gy[2] = -(g.gy[0] + g.gy[1]);
   g.px[0] = x1; g.px[1] = x2; g.px[2] = x3; g.py[0] = y1; g.py[1] = y2; g.py[2] = y3;
   g.cx = (x1 + x2 + x3) / 3.0; g.cy = (y1 + y2 + y3) / 3.0;
 }
@@ -86,11 +89,12 @@ __device__ __forceinline__ void tri_geo(const double* __restrict__ X, size_t E, 
 // normal and half length (det_snlx_all / NORMGI, ShapFun.F90:1554-1590, 2012-2037)
 __device__ __forceinline__ void face_geo(const TriGeo& g, int l1, int l2, double& nx, double& ny, double& sdet) {
   const double ex = g.px[l2] - g.px[l1], ey = g.py[l2] - g.py[l1];
-  const double len = sqrt(ex * ex + ey * ey);
-  nx = ey / len; ny = -ex / len;
+  const double len2 = ex * ex + ey * ey;
+  const double ilen = rsqrt(len2);
+  nx = ey * ilen; ny = -ex * ilen;
   const double mx = 0.5 * (g.px[l1] + g.px[l2]) - g.cx, my = 0.5 * (g.py[l1] + g.py[l2]) - g.cy;
   if (nx * mx + ny * my < 0.0) { nx = -nx; ny = -ny; }
-  sdet = 0.5 * len;
+  sdet = 0.5 * len2 * ilen;
 }
 
 struct UnstrArgs {
@@ -158,17 +162,19 @@ __global__ void __launch_bounds__(TPB) k_unstr_explicit(UnstrArgs a) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) v[i] = m12 * (To[i] + so) + a.dt * rhs[i];
         const double sv = v[0] + v[1] + v[2];
+        const double i12 = 12.0 / area;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) out[i] = (12.0 / area) * (v[i] - 0.25 * sv);
+        for (int i = 0; i < 3; ++i) out[i] = i12 * (v[i] - 0.25 * sv);
       } else {
         double rj[3], tl[3] = {T[0], T[1], T[2]};         // tnew_nonlin(:,ele) == tnew(:,ele) here (:598,783)
 #pragma unroll
         for (int i = 0; i < 3; ++i) rj[i] = m12 * (To[i] + so) + a.dt * rhs[i];   // :774
+        const double iml = 1.0 / ml;
         for (int it = 0; it < a.njac; ++it) {
           const double st = tl[0] + tl[1] + tl[2];
           double nt[3];
 #pragma unroll
-          for (int i = 0; i < 3; ++i) nt[i] = (ml * tl[i] - m12 * (tl[i] + st) + rj[i]) / ml;  // :780-787
+          for (int i = 0; i < 3; ++i) nt[i] = (ml * tl[i] - m12 * (tl[i] + st) + rj[i]) * iml;  // :780-787
           tl[0] = nt[0]; tl[1] = nt[1]; tl[2] = nt[2];
         }
         out[0] = tl[0]; out[1] = tl[1]; out[2] = tl[2];
