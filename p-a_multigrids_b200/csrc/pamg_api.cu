@@ -76,6 +76,7 @@ struct LevelDev {
   int ovl_cur = 0;                            // ovlb[ovl_cur] holds the strips of the current iterate when strips_valid
   bool strips_valid = false;                  // strips of the faces between local parents hold the current iterate
   bool cut_valid = false;                     // strips of the faces cut by the GPU partition hold the current iterate
+  bool stage_valid = false;                   // ... and the level's flagged staging buffer holds it under the current exchange number
   double* ovl_old = nullptr;                  // told strips (update_overlaps as written only)
   double* pc = nullptr;               // [U][NPC]
   bool rhs_valid = false;             // level 1: RHS matches TOLD
@@ -156,8 +157,11 @@ struct pamg_handle {
   unsigned long long* p2p_sync = nullptr;   // exchange number, block counter (device)
   unsigned long long* p2p_err_host = nullptr;   // error word raised by a halo kernel that timed out: mapped pinned memory, so
   unsigned long long* p2p_err_dev = nullptr;    // every host synchronisation point can check it without a copy
-  uint4* p2p_stage = nullptr;               // flagged receive staging, 2 parities x p2p_stage_words (IPC-exported)
-  long long p2p_stage_words = 0;
+  uint4* p2p_stage = nullptr;               // flagged receive staging of ALL levels (IPC-exported): per level 2 parities x
+  long long p2p_strips = 0;                 //   p2p_strips * 3 * S(level) words, levels one after the other
+  P2PArgs* d_xchg = nullptr;                // device copies of the per-level exchange descriptors for the sweep kernels
+  bool xchg_in_kernel = true;               // faces cut by the GPU partition are sent by the producer warps of the sweep and
+                                            // polled by the consumers that need them (PAMG_XCHG=kernel: separate k_halo launch)
   struct P2PPeer { int slot_at_peer = -1, strip_begin_at_peer = 0; long long recv_strips_at_peer = 0; uint4* stage = nullptr; };
   std::vector<P2PPeer> p2p_peers;      // same order as plan.peers
   std::vector<void*> p2p_opened;       // IPC mappings to close
@@ -327,6 +331,7 @@ void p2p_close(pamg_handle* h) {
   h->p2p_opened.clear();
   if (h->p2p_sync) { cudaFree(h->p2p_sync); h->p2p_sync = nullptr; }
   if (h->p2p_stage) { cudaFree(h->p2p_stage); h->p2p_stage = nullptr; }
+  if (h->d_xchg) { cudaFree(h->d_xchg); h->d_xchg = nullptr; }
   if (h->p2p_err_host) { cudaFreeHost(h->p2p_err_host); h->p2p_err_host = nullptr; h->p2p_err_dev = nullptr; }
   h->p2p_ready = false; h->p2p_failed = false;
   for (auto& pp : h->p2p_peers) pp.stage = nullptr;
@@ -340,14 +345,22 @@ int p2p_check(pamg_handle* h) {
   return PAMG_OK;
 }
 
-// local part of the set-up: exchange counters, the flagged receive staging buffer (2 parities) and the error word
+// first word of level il (0-based) inside a staging buffer that holds `strips` cut strips per level and parity
+long long stage_offset(long long strips, const std::vector<LevelDev>& lev, int il) {
+  long long off = 0;
+  for (int l = 0; l < il; ++l) off += 2 * strips * 3 * lev[l].S;
+  return off;
+}
+
+// local part of the set-up: exchange counters, the flagged receive staging buffers (per level, 2 parities) and the error word
 int p2p_alloc_local(pamg_handle* h) {
   long long strips = 0;
   for (const auto& pr : h->plan.peers) strips = std::max(strips, (long long)pr.strip_begin + pr.nfaces);
-  h->p2p_stage_words = strips * 3 * h->lev[0].S;
-  const size_t stage_bytes = (size_t)std::max(1ll, 2 * h->p2p_stage_words) * sizeof(uint4);
-  CK(cudaMalloc(&h->p2p_sync, P2P_WORDS * sizeof(unsigned long long)));
-  CK(cudaMemset(h->p2p_sync, 0, P2P_WORDS * sizeof(unsigned long long)));
+  h->p2p_strips = strips;
+  const size_t nlev = h->lev.size();
+  const size_t stage_bytes = (size_t)std::max(1ll, stage_offset(h->p2p_strips, h->lev, (int)nlev)) * sizeof(uint4);
+  CK(cudaMalloc(&h->p2p_sync, nlev * P2P_WORDS * sizeof(unsigned long long)));
+  CK(cudaMemset(h->p2p_sync, 0, nlev * P2P_WORDS * sizeof(unsigned long long)));
   CK(cudaMalloc(&h->p2p_stage, stage_bytes));
   CK(cudaMemset(h->p2p_stage, 0, stage_bytes));
   CK(cudaHostAlloc(&h->p2p_err_host, sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable));
@@ -411,16 +424,19 @@ int p2p_setup(pamg_handle* h) {
 
 int p2p_args(pamg_handle* h, LevelDev& L, double* ovl, P2PArgs& a) {
   const long long S3 = 3ll * L.S;
+  const int il = (int)(&L - h->lev.data());
   const int base = h->plan.peers[0].send_begin;
   a.send = ovl + ((size_t)h->plan.nstrips + base) * S3;
-  a.strips = ovl; a.stage = h->p2p_stage; a.stage_words = h->p2p_stage_words;
-  a.sync = h->p2p_sync; a.err = h->p2p_err_dev; a.npeers = (int)h->plan.peers.size(); a.timeout_ns = h->p2p_timeout_ns;
+  a.strips = ovl; a.stage = h->p2p_stage + stage_offset(h->p2p_strips, h->lev, il); a.stage_words = h->p2p_strips * S3;
+  a.sync = h->p2p_sync + (size_t)il * P2P_WORDS; a.err = h->p2p_err_dev; a.npeers = (int)h->plan.peers.size();
+  a.timeout_ns = h->p2p_timeout_ns;
   long long so = 0, ro = 0;
   for (int i = 0; i < a.npeers; ++i) {
     const auto& pr = h->plan.peers[i];
     if ((long long)(pr.send_begin - base) * S3 != so) return fail(h, PAMG_ERR_STATE, "send slots are not contiguous per peer");
-    a.remote[i] = h->p2p_peers[i].stage + (long long)h->p2p_peers[i].strip_begin_at_peer * S3;
-    a.rstride[i] = h->p2p_peers[i].recv_strips_at_peer * 3 * h->lev[0].S;   // the peer's own p2p_stage_words
+    a.remote[i] = h->p2p_peers[i].stage + stage_offset(h->p2p_peers[i].recv_strips_at_peer, h->lev, il) +
+                  (long long)h->p2p_peers[i].strip_begin_at_peer * S3;
+    a.rstride[i] = h->p2p_peers[i].recv_strips_at_peer * S3;   // the peer's own words per parity on this level
     a.soff[i] = so; a.roff[i] = ro; a.rbeg[i] = (long long)pr.strip_begin * S3;
     so += pr.nfaces * S3; ro += pr.nfaces * S3;
   }
@@ -1908,7 +1924,7 @@ int pamg_implicit_get_bsr(pamg_handle* h, double* val, int32_t* col) {
   if (rc) return fail(h, rc, e);
   const int grid = std::max(1, std::min((h->un.E + TPB - 1) / TPB, h->nsm * 8));
   if (val) {
-    k_from_planes<double><<<grid, TPB, 0, h->stream>>>(h->un.bsr_val, h->un.xfer, 36, h->un.E);
+    k_from_planes<double><<<grid, TPB, 0, h->stream>>>(h->un.bsr_val, h->un.xfer, 36, h->un.E, h->un.ld);
     h->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(val, h->un.xfer, E * 36 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1916,7 +1932,7 @@ int pamg_implicit_get_bsr(pamg_handle* h, double* val, int32_t* col) {
   if (col) {
     int32_t* tmp = reinterpret_cast<int32_t*>(h->un.xfer);
     CK(cudaStreamSynchronize(h->stream));
-    k_from_planes<int32_t><<<grid, TPB, 0, h->stream>>>(h->un.bsr_col, tmp, 4, h->un.E);
+    k_from_planes<int32_t><<<grid, TPB, 0, h->stream>>>(h->un.bsr_col, tmp, 4, h->un.E, h->un.ld);
     h->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(col, tmp, E * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -1933,8 +1949,8 @@ int pamg_implicit_apply(pamg_handle* h, const double* x, double* y) {
   const size_t nb = (size_t)h->un.E * 3 * sizeof(double);
   double* W = h->un.work;
   CK(cudaMemcpyAsync(W, x, nb, cudaMemcpyHostToDevice, h->stream));
-  const int grid = std::max(1, std::min((h->un.E + TPB - 1) / TPB, h->nsm * 8));
-  k_bsr_spmv<<<grid, TPB, 0, h->stream>>>(h->un.bsr_val, h->un.bsr_col, W, nullptr, W + (size_t)h->un.E * 3, h->un.E, 0);
+  const int grid = stream_grid(k_bsr_spmv, h->un.occ_spmv, h->un.E, h->nsm);
+  k_bsr_spmv<<<grid, TPB, 0, h->stream>>>(h->un.bsr_val, h->un.bsr_col, W, nullptr, W + (size_t)h->un.E * 3, h->un.E, h->un.ld, 0);
   h->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(y, W + (size_t)h->un.E * 3, nb, cudaMemcpyDeviceToHost, h->stream));
@@ -1964,7 +1980,7 @@ int pamg_unstr_stab(pamg_handle* h, const double* told, double dt, double u_x, d
   cudaMemcpyAsync(d_old, told, E * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
   StabArgs sa;
   sa.X = h->un.X; sa.tnew = h->un.T[h->un.cur]; sa.told = d_old; sa.diff_coe = d_out + E * 9; sa.stab = d_out; sa.diag0 = nullptr;
-  sa.val = nullptr; sa.dinv = nullptr; sa.dt = dt; sa.ux = u_x; sa.uy = u_y; sa.E = h->un.E; sa.mode = 0;
+  sa.val = nullptr; sa.dinv = nullptr; sa.dt = dt; sa.ux = u_x; sa.uy = u_y; sa.ld = h->un.ld; sa.E = h->un.E; sa.mode = 0;
   const int grid = std::max(1, std::min((h->un.E + TPB - 1) / TPB, h->nsm * 8));
   k_unstr_stab<<<grid, TPB, 0, h->stream>>>(sa);
   h->launches++;
@@ -1999,11 +2015,11 @@ int pamg_implicit_spmv_time(pamg_handle* h, int reps, float* ms) {
   CK(cudaSetDevice(h->device));
   double* W = h->un.work;
   const size_t n = (size_t)h->un.E * 3;
-  const int grid = std::max(1, std::min((h->un.E + TPB - 1) / TPB, h->nsm * 8));
+  const int grid = stream_grid(k_bsr_spmv, h->un.occ_spmv, h->un.E, h->nsm);
   CK(cudaMemcpyAsync(W, h->un.T[h->un.cur], n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  k_bsr_spmv<<<grid, TPB, 0, h->stream>>>(h->un.bsr_val, h->un.bsr_col, W, nullptr, W + n, h->un.E, 0);
+  k_bsr_spmv<<<grid, TPB, 0, h->stream>>>(h->un.bsr_val, h->un.bsr_col, W, nullptr, W + n, h->un.E, h->un.ld, 0);
   CK(cudaEventRecord(h->ev[14], h->stream));
-  for (int i = 0; i < reps; ++i) k_bsr_spmv<<<grid, TPB, 0, h->stream>>>(h->un.bsr_val, h->un.bsr_col, W, nullptr, W + n, h->un.E, 0);
+  for (int i = 0; i < reps; ++i) k_bsr_spmv<<<grid, TPB, 0, h->stream>>>(h->un.bsr_val, h->un.bsr_col, W, nullptr, W + n, h->un.E, h->un.ld, 0);
   CK(cudaEventRecord(h->ev[15], h->stream));
   h->launches += reps + 1;
   CK(cudaGetLastError());

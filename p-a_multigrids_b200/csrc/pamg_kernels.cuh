@@ -28,6 +28,69 @@ constexpr int TPB = 256;
 
 enum { MODE_JACOBI = 0, MODE_RESID = 1, MODE_GS = 2, MODE_RICH = 3 };
 
+// ------------------------------------------------------------------------------------------------
+// update_overlaps across GPUs without a library collective.  Every GPU STORES its cut-face strips straight into
+// a staging buffer of its peers over NVLink (peer pointers from CUDA IPC) in a flagged format: a double travels as
+// two 8-byte words {low 32 bits, exchange number} {high 32 bits, exchange number}; an aligned 8-byte store is
+// atomic, so the receiver simply polls every word of its own staging buffer until it carries the number of this
+// exchange and unpacks it into the strip buffer.  No fence, no separate flag, no credit: the latency is one
+// NVLink one-way trip.  The staging buffer is double-buffered by the parity of the exchange number (a sender can
+// only be one exchange ahead of a receiver because it needs the receiver's data to get any further), and the
+// exchange number lives in device memory so that a captured CUDA graph replays correctly.  Polling has a time-out
+// that raises the error word (host-mapped memory, checked at every host synchronisation point) instead of hanging the GPU.
+constexpr int P2P_MAXP = 16;
+enum { P2P_EPOCH = 0, P2P_COUNT = 1, P2P_WORDS = 8 };
+struct P2PArgs {
+  const double* send;                 // my send slots of this level (contiguous, grouped per peer)
+  int send_base;                      // first send slot (in strips) of peer 0, relative to the send-slot space
+  double* strips;                     // my strip buffer of this level (receive side)
+  uint4* remote[P2P_MAXP];            // each peer's staging buffer (parity 0), already offset to my range there
+  long long rstride[P2P_MAXP];        // words per parity of each peer's staging buffer
+  long long soff[P2P_MAXP + 1];       // prefix offsets (doubles) of the per-peer send ranges
+  long long rbeg[P2P_MAXP];           // first double of the strips I receive from each peer
+  long long roff[P2P_MAXP + 1];       // prefix offsets (doubles) of the per-peer receive ranges
+  uint4* stage;                       // my staging buffer (parity 0)
+  long long stage_words;              // words per parity
+  unsigned long long* sync;           // exchange number, block counter
+  unsigned long long* err;            // error word (mapped host memory): a poll that timed out raises it instead of hanging
+  int npeers;
+  unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ unsigned long long p2p_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// one double into the staging buffer of peer p (idx = offset in doubles inside my range there)
+__device__ __forceinline__ void p2p_put(const P2PArgs& a, unsigned e, int p, long long idx, double val) {
+  const unsigned long long v = (unsigned long long)__double_as_longlong(val);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(a.remote[p] + (long long)(e & 1u) * a.rstride[p] + idx), "r"((unsigned)v), "r"(e),
+               "r"((unsigned)(v >> 32)), "r"(e) : "memory");
+}
+
+
+// one value out of MY staging buffer for the exchange number e (polls until the flagged word has arrived)
+__device__ __forceinline__ double p2p_take(const P2PArgs& a, unsigned long long e64, long long j) {
+  const uint4* src = a.stage + (long long)(e64 & 1) * a.stage_words + j;
+  const unsigned e = (unsigned)e64;
+  volatile unsigned long long* err = a.err;
+  uint4 w;
+  unsigned long long t0 = 0;
+  for (unsigned spins = 0;; ++spins) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(src) : "memory");
+    if (w.y == e && w.w == e) break;
+    if ((spins & 1023u) == 1023u) {
+      if (*err) break;
+      const unsigned long long t = p2p_now();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > a.timeout_ns) { *err = 1; break; }
+    }
+  }
+  return __longlong_as_double((long long)(((unsigned long long)w.z << 32) | w.x));
+}
+
 struct ElemArgs {
   const double* Tin;      // field the sweep reads (may alias Tout for the in-place coloured pass)
   double* Tout;           // Jacobi/GS/Richardson: new iterate; residual: RES
@@ -41,6 +104,10 @@ struct ElemArgs {
   const int32_t* dst_strip; // [U*3] strip my boundary children of (u, side) are copied to; -1 = domain boundary
   const int32_t* rev;       // [U*3] slot reversal flag
   int nstrips;              // dst_strip >= nstrips: send slot of a face cut by the GPU partition
+  const P2PArgs* xchg;      // != nullptr: the sweep does the exchange of the cut faces itself - the producer warp stores their new
+                            // values straight into the peers' flagged staging buffers, consumers poll their own staging buffer
+                            // for the strips [0, ncut) instead of reading unpacked copies
+  int ncut;                 // cut strips are the first ncut strips of the strip space
   double* partial;        // residual: [nblocks][3] = sum r^2, max |r|, max r
   double omega;
   double rsign;
@@ -162,6 +229,17 @@ __device__ __forceinline__ void ext_pair(const ElemArgs& a, int d, int strip, in
   if (d >= 0) { nbr_pair(a.Tin, d, p, a.s, va, vb); return; }
   const double* e = a.ovl + ((size_t)strip * S + p) * 3;
   va = __ldg(e + (hm & 3)); vb = __ldg(e + (hm >> 2));
+}
+
+// the same for a kernel that takes part in the exchange: strips of cut faces come out of the flagged staging buffer
+__device__ __forceinline__ void ext_pair_x(const ElemArgs& a, unsigned long long e64, int d, int strip, int hm, int p, int S,
+                                           double& va, double& vb) {
+  if (a.xchg != nullptr && d < 0 && strip < a.ncut) {
+    const long long j = ((long long)strip * S + p) * 3;
+    va = p2p_take(*a.xchg, e64, j + (hm & 3)); vb = p2p_take(*a.xchg, e64, j + (hm >> 2));
+    return;
+  }
+  ext_pair(a, d, strip, hm, p, S, va, vb);
 }
 
 // same with the per-parent tables still in global memory: mf = gmsh side (0..2), slot0 = 0-based strip position
@@ -1413,47 +1491,6 @@ __global__ void __launch_bounds__(1024) k_reduce_partials(const double* partial,
 // ------------------------------------------------------------------------------------------------
 // update_overlaps (splitting.F90:1210-1397): one thread per (parent, side, position)
 // ------------------------------------------------------------------------------------------------
-// update_overlaps across GPUs without a library collective.  Every GPU STORES its cut-face strips straight into
-// a staging buffer of its peers over NVLink (peer pointers from CUDA IPC) in a flagged format: a double travels as
-// two 8-byte words {low 32 bits, exchange number} {high 32 bits, exchange number}; an aligned 8-byte store is
-// atomic, so the receiver simply polls every word of its own staging buffer until it carries the number of this
-// exchange and unpacks it into the strip buffer.  No fence, no separate flag, no credit: the latency is one
-// NVLink one-way trip.  The staging buffer is double-buffered by the parity of the exchange number (a sender can
-// only be one exchange ahead of a receiver because it needs the receiver's data to get any further), and the
-// exchange number lives in device memory so that a captured CUDA graph replays correctly.  Polling has a time-out
-// that raises the error word (host-mapped memory, checked at every host synchronisation point) instead of hanging the GPU.
-constexpr int P2P_MAXP = 16;
-enum { P2P_EPOCH = 0, P2P_COUNT = 1, P2P_WORDS = 8 };
-struct P2PArgs {
-  const double* send;                 // my send slots of this level (contiguous, grouped per peer)
-  int send_base;                      // first send slot (in strips) of peer 0, relative to the send-slot space
-  double* strips;                     // my strip buffer of this level (receive side)
-  uint4* remote[P2P_MAXP];            // each peer's staging buffer (parity 0), already offset to my range there
-  long long rstride[P2P_MAXP];        // words per parity of each peer's staging buffer
-  long long soff[P2P_MAXP + 1];       // prefix offsets (doubles) of the per-peer send ranges
-  long long rbeg[P2P_MAXP];           // first double of the strips I receive from each peer
-  long long roff[P2P_MAXP + 1];       // prefix offsets (doubles) of the per-peer receive ranges
-  uint4* stage;                       // my staging buffer (parity 0)
-  long long stage_words;              // words per parity
-  unsigned long long* sync;           // exchange number, block counter
-  unsigned long long* err;            // error word (mapped host memory): a poll that timed out raises it instead of hanging
-  int npeers;
-  unsigned long long timeout_ns;
-};
-
-__device__ __forceinline__ unsigned long long p2p_now() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
-// one double into the staging buffer of peer p (idx = offset in doubles inside my range there)
-__device__ __forceinline__ void p2p_put(const P2PArgs& a, unsigned e, int p, long long idx, double val) {
-  const unsigned long long v = (unsigned long long)__double_as_longlong(val);
-  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(a.remote[p] + (long long)(e & 1u) * a.rstride[p] + idx), "r"((unsigned)v), "r"(e),
-               "r"((unsigned)(v >> 32)), "r"(e) : "memory");
-}
-
 // poll my staging buffer, unpack into the strips, and let the last block advance the exchange number
 __device__ __forceinline__ void p2p_receive(const P2PArgs& a, unsigned long long e64) {
   __shared__ int s_last;

@@ -26,29 +26,42 @@ namespace pamg {
 
 struct UnstrDev {
   int E = 0;
-  double* X = nullptr;        // [6][E] planes x1, y1, x2, y2, x3, y3
-  int32_t* neig = nullptr;    // [3][E] 1-based, 0 = boundary
-  int32_t* nside = nullptr;   // [3][E] fNeig | swap<<2 (swap: geometric pairing differs from get_unstr_sn2)
-  double* dcen = nullptr;     // [3][E] penalty length of the diffusion face term: centroid distance to the neighbour, or
-                              //        centroid -> edge midpoint on the domain boundary (matrices.F90:84-110)
+  size_t ld = 0;              // plane stride in elements: 32 x odd >= E.  A power-of-two E (the synthetic meshes) would put the
+                              // same element of all 36 matrix planes into one L2 set: ncu showed 1.32 x the stored bytes going
+                              // to DRAM in k_assemble_bsr (lines evicted half written); with an odd number of lines between
+                              // planes the streams spread over the sets
+  double* X = nullptr;        // [6][ld] planes x1, y1, x2, y2, x3, y3
+  int32_t* neig = nullptr;    // [3][ld] 1-based, 0 = boundary
+  int32_t* nside = nullptr;   // [3][ld] fNeig | swap<<2 (swap: geometric pairing differs from get_unstr_sn2)
+  double* pen = nullptr;      // [3][ld] (L/2) / dx of the diffusion face term: half the face length over the centroid distance
+                              //         to the neighbour, or over centroid -> edge midpoint on the domain boundary
+                              //         (matrices.F90:84-110); times k it is the penalty coefficient of the face
   double* T[2] = {nullptr, nullptr};   // (3, E) like tnew
   double* told = nullptr;
   int cur = 0;
   // implicit operator in block-CSR: 4 blocks of 3x3 per element row (own, face 1, face 2, face 3)
-  double* bsr_val = nullptr;   // [36][E]: plane (block * 9 + row * 3 + col)
-  int32_t* bsr_col = nullptr;  // [4][E] 0-based element of the block column, -1 = no block
-  double* dinv = nullptr;      // [9][E] inverse of the diagonal block (block-Jacobi preconditioner)
+  double* bsr_val = nullptr;   // [36][ld]: plane (block * 9 + row * 3 + col)
+  int32_t* bsr_col = nullptr;  // [4][ld] 0-based element of the block column, -1 = no block
+  double* dinv = nullptr;      // [9][ld] inverse of the diagonal block (block-Jacobi preconditioner)
   double* mdt = nullptr;       // [E] A/(12 dt): M/dt = mdt (I + J) per element
   double* work = nullptr;      // 9 vectors of 3E doubles for BiCGStab
   double* dots = nullptr;      // device scalars and partial sums of the Krylov solve
   double* dots_host = nullptr; // pinned mirror
   bool assembled = false;
-  double* diag0 = nullptr;     // [9][E] diagonal blocks without stabilisation
+  double* diag0 = nullptr;     // [9][ld] diagonal blocks without stabilisation
   double* stab = nullptr;      // [E][9] Petrov-Galerkin element matrices ; [E][3] diff_coe behind them (ABI order)
   bool with_stab = false;
   double dt = 0.0, ux = 0.0, uy = 0.0, kdiff = 0.0;
   double* xfer = nullptr; size_t xfer_bytes = 0;   // staging for the [E][..] <-> [..][E] conversions at the ABI
+  int occ_explicit = 0, occ_assemble = 0, occ_spmv = 0, occ_apply = 0, occ_stab = 0, occ_kry[6] = {0, 0, 0, 0, 0, 0};   // resident CTAs
+                              // per SM of the streaming kernels (this device)
 };
+
+inline size_t plane_stride(int E) {
+  size_t q = ((size_t)E + 31) / 32;
+  if ((q & 1) == 0) ++q;
+  return q * 32;
+}
 
 // ---- a warp's 32 consecutive (3, E) records through shared memory: every global access is a full line ----------------
 // base = field + 3 * (first element of the warp), nvalid = elements of this warp inside the array, sm = 96 doubles
@@ -69,135 +82,170 @@ __device__ __forceinline__ void warp_store3(double* __restrict__ base, int nvali
   __syncwarp();
 }
 
-// geometry of one P1 triangle in registers (tri_det_nlx, ShapFun.F90:1414-1454)
-struct TriGeo { double area, gx[3], gy[3], px[3], py[3], cx, cy; };
-__device__ __forceinline__ void tri_geo(const double* __restrict__ X, size_t E, size_t e, TriGeo& g, double& detj) {
-  const double x1 = __ldg(X + e), y1 = __ldg(X + E + e), x2 = __ldg(X + 2 * E + e), y2 = __ldg(X + 3 * E + e),
-               x3 = __ldg(X + 4 * E + e), y3 = __ldg(X + 5 * E + e);
-  const double A = x1 - x3, B = y1 - y3, C = x2 - x3, D = y2 - y3;
-  detj = A * D - B * C;
-  g.area = 0.5 * fabs(detj);
-  // (fp64 division costs ~40 issue slots on sm_100a and this kernel family is issue-bound, not HBM-bound, with them: one
-  // reciprocal per element instead of six quotients - a last-bit difference to the reference's D/detj, far inside 1e-12)
-  const double idet = 1.0 / detj;
-  g.gx[0] = D * idet; g.gx[1] = -B * idet; g.gx[2] = -(g.gx[0] + g.gx[1]);
-  g.gy[0] = -C * idet; g.gy[1] = A * idet; g.gy[2] = -(g.gy[0] + g.gy[1]);
+// Geometry of one P1 triangle WITHOUT divisions or square roots.  Everything the explicit step and the implicit operator need
+// from tri_det_nlx (ShapFun.F90:1414-1454) and det_snlx_all / NORMGI (:1554-1590, 2012-2037) comes as a product in which the
+// normalisations cancel:
+//   area * grad(phi_i)          = sign(detj)/2 * (D, -C), (-B, A), -(sum)        [A = x1-x3, B = y1-y3, C = x2-x3, D = y2-y3]
+//   sdetwei * (n . u) on a face = 1/2 * s * (ey ux - ex uy),  (ex, ey) = the edge vector, s = +-1 makes (ey, -ex) point away
+//                                 from the opposite vertex (the reference's test against centroid -> edge midpoint)
+// so the kernels spend a few FMAs where the literal formulas need six quotients, three rsqrt and a handful of x/3 (fp64
+// division and rsqrt expand to 20-40 instructions each on sm_100a; with them these kernels were issue-bound at a third of the
+// HBM rate).  The results differ from the literal order of operations in the last bit only (tests: <= 1e-12 relative).
+struct TriEdges {
+  double px[3], py[3];
+  double A, B, C, D, detj, sgn;    // sgn = sign(detj)
+};
+__device__ __forceinline__ void tri_edges(const double* __restrict__ X, size_t ld, size_t e, TriEdges& g) {
+  const double x1 = __ldg(X + e), y1 = __ldg(X + ld + e), x2 = __ldg(X + 2 * ld + e), y2 = __ldg(X + 3 * ld + e),
+               x3 = __ldg(X + 4 * ld + e), y3 = __ldg(X + 5 * ld + e);
   g.px[0] = x1; g.px[1] = x2; g.px[2] = x3; g.py[0] = y1; g.py[1] = y2; g.py[2] = y3;
-  g.cx = (x1 + x2 + x3) / 3.0; g.cy = (y1 + y2 + y3) / 3.0;
+  g.A = x1 - x3; g.B = y1 - y3; g.C = x2 - x3; g.D = y2 - y3;
+  g.detj = g.A * g.D - g.B * g.C;
+  g.sgn = g.detj < 0.0 ? -1.0 : 1.0;
 }
-// face f (0..2) of the gmsh numbering: nodes (l1, l2) = (1,3), (2,1), (3,2) (ShapFun_unstruc.F90:160-188); outward unit
-// normal and half length (det_snlx_all / NORMGI, ShapFun.F90:1554-1590, 2012-2037)
-__device__ __forceinline__ void face_geo(const TriGeo& g, int l1, int l2, double& nx, double& ny, double& sdet) {
+// face f (0..2) of the gmsh numbering: nodes (l1, l2) = (1,3), (2,1), (3,2) (ShapFun_unstruc.F90:160-188), l3 = the opposite
+// vertex.  Returns c = sdetwei * (n . u) (n = outward unit normal, sdetwei = L/2).
+__device__ __forceinline__ double face_flux(const TriEdges& g, int l1, int l2, int l3, double ux, double uy) {
   const double ex = g.px[l2] - g.px[l1], ey = g.py[l2] - g.py[l1];
-  const double len2 = ex * ex + ey * ey;
-  const double ilen = rsqrt(len2);
-  nx = ey * ilen; ny = -ex * ilen;
-  const double mx = 0.5 * (g.px[l1] + g.px[l2]) - g.cx, my = 0.5 * (g.py[l1] + g.py[l2]) - g.cy;
-  if (nx * mx + ny * my < 0.0) { nx = -nx; ny = -ny; }
-  sdet = 0.5 * len2 * ilen;
+  // (ey, -ex) against (midpoint - centroid) = ((p_l1 - p_l3) + (p_l2 - p_l3)) / 6
+  const double mx = (g.px[l1] - g.px[l3]) + (g.px[l2] - g.px[l3]), my = (g.py[l1] - g.py[l3]) + (g.py[l2] - g.py[l3]);
+  const double c = 0.5 * (ey * ux - ex * uy);
+  return (ey * mx - ex * my < 0.0) ? -c : c;
 }
 
 struct UnstrArgs {
   const double* X; const int32_t* neig; const int32_t* nside;
   const double* Tin; const double* told; double* Tout;
   double dt, ux, uy, t_bc;
+  size_t ld;
   int E, njac, exact, use_dir;
 };
 
-__global__ void __launch_bounds__(TPB) k_unstr_explicit(UnstrArgs a) {
-  __shared__ double smw[TPB / 32][96];
+// unstr_explicit element loop (transport_tri_unstr.F90:600-791).  One warp = 32 consecutive elements per trip: all the
+// streaming loads of a trip (own and told records as 768 contiguous bytes each, six coordinate planes, neighbour ids and
+// sides) are issued before anything is used, the six neighbour values are gathered (L2: a locality-ordered mesh keeps
+// them a few lines away) and the new record leaves through shared memory as full lines again.
+#ifndef PAMG_OCC_EXPLICIT
+#define PAMG_OCC_EXPLICIT 4
+#endif
+#ifndef PAMG_OCC_ASSEMBLE
+#define PAMG_OCC_ASSEMBLE 4
+#endif
+__global__ void __launch_bounds__(TPB, PAMG_OCC_EXPLICIT) k_unstr_explicit(UnstrArgs a) {
+  __shared__ double smw[TPB / 32][2][96];
   const double al = 0.78867513459481288, be = 0.21132486540518712;  // sn_orig, ShapFun.F90:1100-1111
   // weights of int sn_c * trace over the face: (2/3, 1/3) -- exact products of the 2-point Gauss rule
   const double w2 = al * al + be * be, w1 = 2.0 * al * be;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  double* sm = smw[wib];
-  const size_t E = (size_t)a.E;
+  double* smT = smw[wib][0];
+  double* smO = smw[wib][1];
+  const size_t ld = a.ld;
+  const double sixth = 1.0 / 6.0;
   for (int e0 = (blockIdx.x * (TPB / 32) + wib) * 32; e0 < a.E; e0 += gridDim.x * TPB) {
     const int nvalid = min(32, a.E - e0);
-    const int e = e0 + lane;
-    const bool act = lane < nvalid;
-    double T[3] = {0, 0, 0}, To[3] = {0, 0, 0};
-    warp_load3(a.Tin + (size_t)e0 * 3, nvalid, sm, lane, T[0], T[1], T[2]);
-    warp_load3(a.told + (size_t)e0 * 3, nvalid, sm, lane, To[0], To[1], To[2]);
-    double out[3] = {0, 0, 0};
-    if (act) {
-      TriGeo g; double detj;
-      tri_geo(a.X, E, (size_t)e, g, detj);
-      const double area = g.area;
-      const double sumT = T[0] + T[1] + T[2];
-      double rhs[3];
+    const int e = min(e0 + lane, a.E - 1);          // lanes past the end redo the last element and store nothing
+    const int n3 = nvalid * 3;
+    // ---- every streaming load of the trip
+    const double* tin = a.Tin + (size_t)e0 * 3;
+    const double* tol = a.told + (size_t)e0 * 3;
+    double ra[3], rb[3];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) rhs[i] = (g.gx[i] * a.ux + g.gy[i] * a.uy) * (area / 3.0) * sumT;  // :668-672
-      const int L1[3] = {0, 1, 2}, L2[3] = {2, 0, 1};
-#pragma unroll
-      for (int f = 0; f < 3; ++f) {
-        const int l1 = L1[f], l2 = L2[f];
-        double nx, ny, sdet;
-        face_geo(g, l1, l2, nx, ny, sdet);
-        const int q = __ldg(a.neig + (size_t)f * E + e);
-        const int enc = __ldg(a.nside + (size_t)f * E + e);
-        const int ns = enc & 3;
-        double T2a = 0.0, T2b = 0.0, has2 = 0.0;   // neighbour values paired with sn_orig(:,1), sn_orig(:,2)
-        if (ns >= 1) {
-          // get_unstr_sn2 (ShapFun_unstruc.F90:205-222): Nside 1 -> nodes (3,1), 2 -> (1,2), 3 -> (2,3)
-          int m1 = (ns == 1) ? 2 : (ns == 2 ? 0 : 1), m2 = (ns == 1) ? 0 : (ns == 2 ? 1 : 2);
-          if (a.use_dir && (enc >> 2)) { const int t = m1; m1 = m2; m2 = t; }
-          has2 = 1.0;
-          if (q != 0) { T2a = __ldg(a.Tin + (size_t)(q - 1) * 3 + m1); T2b = __ldg(a.Tin + (size_t)(q - 1) * 3 + m2); }
-          else { T2a = a.t_bc; T2b = a.t_bc; }
-        }
-        const double unn = nx * a.ux + ny * a.uy;
-        const double un = 0.5 * (unn + has2 * unn);       // n . (u + u2)/2 ; u2 = 0 when sn2 = 0 (Nside = 0)
-        const bool in = signbit(-un) == 0;                // income = 0.5 + 0.5*sign(1, -un)  (:731)
-        double ca, cb;
-        if (in) { const double f2 = sdet * has2 * unn; ca = f2 * (w2 * T2a + w1 * T2b); cb = f2 * (w1 * T2a + w2 * T2b); }
-        else { const double f1 = sdet * unn; ca = f1 * (w2 * T[l1] + w1 * T[l2]); cb = f1 * (w1 * T[l1] + w2 * T[l2]); }
-        rhs[l1] -= ca; rhs[l2] -= cb;                     // :742-746
-      }
-      const double m12 = area / 12.0, ml = area / 3.0;
-      const double so = To[0] + To[1] + To[2];
-      if (a.exact) {
-        // T = M^-1 (M told + dt rhs), M^-1 = (12/A)(I - J/4)  (transport_rect.F90:277-291 semantics)
-        double v[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) v[i] = m12 * (To[i] + so) + a.dt * rhs[i];
-        const double sv = v[0] + v[1] + v[2];
-        const double i12 = 12.0 / area;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) out[i] = i12 * (v[i] - 0.25 * sv);
-      } else {
-        double rj[3], tl[3] = {T[0], T[1], T[2]};         // tnew_nonlin(:,ele) == tnew(:,ele) here (:598,783)
-#pragma unroll
-        for (int i = 0; i < 3; ++i) rj[i] = m12 * (To[i] + so) + a.dt * rhs[i];   // :774
-        const double iml = 1.0 / ml;
-        for (int it = 0; it < a.njac; ++it) {
-          const double st = tl[0] + tl[1] + tl[2];
-          double nt[3];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) nt[i] = (ml * tl[i] - m12 * (tl[i] + st) + rj[i]) * iml;  // :780-787
-          tl[0] = nt[0]; tl[1] = nt[1]; tl[2] = nt[2];
-        }
-        out[0] = tl[0]; out[1] = tl[1]; out[2] = tl[2];
-      }
+    for (int k = 0; k < 3; ++k) {
+      const int i = lane + 32 * k;
+      ra[k] = i < n3 ? __ldg(tin + i) : 0.0;
+      rb[k] = i < n3 ? __ldg(tol + i) : 0.0;
     }
-    warp_store3(a.Tout + (size_t)e0 * 3, nvalid, sm, lane, out[0], out[1], out[2]);
+    TriEdges g;
+    tri_edges(a.X, ld, (size_t)e, g);
+    int q[3], enc[3];
+#pragma unroll
+    for (int f = 0; f < 3; ++f) { q[f] = __ldg(a.neig + (size_t)f * ld + e); enc[f] = __ldg(a.nside + (size_t)f * ld + e); }
+    // ---- neighbour values paired with sn_orig(:,1), sn_orig(:,2): get_unstr_sn2 (ShapFun_unstruc.F90:205-222),
+    // Nside 1 -> nodes (3,1), 2 -> (1,2), 3 -> (2,3); use_dir: the geometric pairing
+    double T2a[3], T2b[3];
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      const int ns = enc[f] & 3;
+      int m1 = (ns == 1) ? 2 : (ns == 2 ? 0 : 1), m2 = (ns == 1) ? 0 : (ns == 2 ? 1 : 2);
+      if (a.use_dir && (enc[f] >> 2)) { const int t = m1; m1 = m2; m2 = t; }
+      T2a[f] = a.t_bc; T2b[f] = a.t_bc;
+      if (ns >= 1 && q[f] != 0) { const double* nb = a.Tin + (size_t)(q[f] - 1) * 3; T2a[f] = __ldg(nb + m1); T2b[f] = __ldg(nb + m2); }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { smT[lane + 32 * k] = ra[k]; smO[lane + 32 * k] = rb[k]; }
+    __syncwarp();
+    const double T[3] = {smT[lane * 3], smT[lane * 3 + 1], smT[lane * 3 + 2]};
+    const double To[3] = {smO[lane * 3], smO[lane * 3 + 1], smO[lane * 3 + 2]};
+    __syncwarp();
+    const double sumT = T[0] + T[1] + T[2];
+    double rhs[3];
+    // (grad(phi_i) . u) (A/3) sum(T)  (:668-672)
+    rhs[0] = g.sgn * (g.D * a.ux - g.C * a.uy) * sixth * sumT;
+    rhs[1] = g.sgn * (g.A * a.uy - g.B * a.ux) * sixth * sumT;
+    rhs[2] = -(rhs[0] + rhs[1]);
+    const int L1[3] = {0, 1, 2}, L2[3] = {2, 0, 1}, L3[3] = {1, 2, 0};
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      const int l1 = L1[f], l2 = L2[f];
+      const double c = face_flux(g, l1, l2, L3[f], a.ux, a.uy);   // sdetwei * n . u
+      const bool has2 = (enc[f] & 3) >= 1;
+      // income = 0.5 + 0.5 sign(1, -n.(u + u2)/2) (:731); u2 = 0 when sn2 = 0 (Nside = 0) does not change the sign
+      const bool in = signbit(-c) == 0;
+      double ca, cb;
+      if (in) { const double f2 = has2 ? c : 0.0; ca = f2 * (w2 * T2a[f] + w1 * T2b[f]); cb = f2 * (w1 * T2a[f] + w2 * T2b[f]); }
+      else { ca = c * (w2 * T[l1] + w1 * T[l2]); cb = c * (w1 * T[l1] + w2 * T[l2]); }
+      rhs[l1] -= ca; rhs[l2] -= cb;                     // :742-746
+    }
+    const double area = 0.5 * fabs(g.detj);
+    const double m12 = area * (1.0 / 12.0);
+    const double iarea = 1.0 / area;
+    const double so = To[0] + To[1] + To[2];
+    double out[3];
+    if (a.exact) {
+      // T = M^-1 (M told + dt rhs), M^-1 = (12/A)(I - J/4)  (transport_rect.F90:277-291 semantics)
+      double v[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) v[i] = m12 * (To[i] + so) + a.dt * rhs[i];
+      const double sv = v[0] + v[1] + v[2];
+      const double i12 = 12.0 * iarea;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) out[i] = i12 * (v[i] - 0.25 * sv);
+    } else {
+      // Jacobi on the lumped mass ml = A/3 (:774-787): t <- (ml t - M t + rj) / ml = t - (t + sum t)/4 + rj / ml
+      double rj[3], tl[3] = {T[0], T[1], T[2]};           // tnew_nonlin(:,ele) == tnew(:,ele) here (:598,783)
+      const double iml = 3.0 * iarea;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) rj[i] = (m12 * (To[i] + so) + a.dt * rhs[i]) * iml;
+      for (int it = 0; it < a.njac; ++it) {
+        const double st = tl[0] + tl[1] + tl[2];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) tl[i] = tl[i] - 0.25 * (tl[i] + st) + rj[i];
+      }
+      out[0] = tl[0]; out[1] = tl[1]; out[2] = tl[2];
+    }
+    smT[lane * 3] = out[0]; smT[lane * 3 + 1] = out[1]; smT[lane * 3 + 2] = out[2];
+    __syncwarp();
+    double* to = a.Tout + (size_t)e0 * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { const int i = lane + 32 * k; if (i < n3) to[i] = smT[i]; }
+    __syncwarp();
   }
 }
 
-// [E][K] (ABI order) <-> [K][E] planes; one thread per element (set-up and read-back only)
+// [E][K] (ABI order) <-> [K][ld] planes; one thread per element (set-up and read-back only)
 template <typename Tp>
-__global__ void __launch_bounds__(TPB) k_to_planes(const Tp* __restrict__ aos, Tp* __restrict__ soa, int K, int E) {
+__global__ void __launch_bounds__(TPB) k_to_planes(const Tp* __restrict__ aos, Tp* __restrict__ soa, int K, int E, size_t ld) {
   for (int e = blockIdx.x * TPB + threadIdx.x; e < E; e += gridDim.x * TPB)
-    for (int k = 0; k < K; ++k) soa[(size_t)k * E + e] = aos[(size_t)e * K + k];
+    for (int k = 0; k < K; ++k) soa[(size_t)k * ld + e] = aos[(size_t)e * K + k];
 }
 template <typename Tp>
-__global__ void __launch_bounds__(TPB) k_from_planes(const Tp* __restrict__ soa, Tp* __restrict__ aos, int K, int E) {
+__global__ void __launch_bounds__(TPB) k_from_planes(const Tp* __restrict__ soa, Tp* __restrict__ aos, int K, int E, size_t ld) {
   for (int e = blockIdx.x * TPB + threadIdx.x; e < E; e += gridDim.x * TPB)
-    for (int k = 0; k < K; ++k) aos[(size_t)e * K + k] = soa[(size_t)k * E + e];
+    for (int k = 0; k < K; ++k) aos[(size_t)e * K + k] = soa[(size_t)k * ld + e];
 }
 
 inline void unstr_free(UnstrDev& u) {
-  cudaFree(u.X); cudaFree(u.neig); cudaFree(u.nside); cudaFree(u.dcen); cudaFree(u.T[0]); cudaFree(u.T[1]); cudaFree(u.told);
+  cudaFree(u.X); cudaFree(u.neig); cudaFree(u.nside); cudaFree(u.pen); cudaFree(u.T[0]); cudaFree(u.T[1]); cudaFree(u.told);
   cudaFree(u.bsr_val); cudaFree(u.bsr_col); cudaFree(u.dinv); cudaFree(u.mdt); cudaFree(u.work); cudaFree(u.dots); cudaFree(u.diag0); cudaFree(u.stab);
   cudaFree(u.xfer);
   if (u.dots_host) cudaFreeHost(u.dots_host);
@@ -214,19 +262,32 @@ inline int unstr_xfer(UnstrDev& u, size_t bytes, std::string& err) {
   return PAMG_OK;
 }
 
+// grid of a streaming kernel: every resident CTA slot of the device exactly once (a partial last wave of a grid-stride loop
+// costs a whole trip), or fewer CTAs for a small mesh
+template <typename K>
+inline int stream_grid(K kernel, int& occ_cache, int E, int nsm) {
+  if (occ_cache <= 0) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, TPB, 0) != cudaSuccess || occ < 1) occ = 2;
+    occ_cache = occ;
+  }
+  return std::max(1, std::min((E + TPB - 1) / TPB, nsm * std::min(occ_cache, 8)));   // (8: the Krylov partial sums are sized for it)
+}
+
 inline int unstr_setup(UnstrDev& u, int E, const double* X, const int32_t* neig, const int32_t* fneig,
                        cudaStream_t st, std::string& err) {
   unstr_free(u);
   // geometric pairing flag per face: does the neighbour node that get_unstr_sn2 pairs with my first face
   // node actually coincide with it?  (SURVEY B-9: the reference ignores Dir here)
   // penalty length of the diffusion face term (get_d_center Msh2Tri.F90:349-385, add_diffusion_surf matrices.F90:84-110)
-  std::vector<int32_t> enc((size_t)E * 3), ng((size_t)E * 3);
-  std::vector<double> xs((size_t)E * 6), dc((size_t)E * 3);
+  const size_t ld = plane_stride(E);
+  std::vector<int32_t> enc(ld * 3, 0), ng(ld * 3, 0);
+  std::vector<double> xs(ld * 6, 0.0), pn(ld * 3, 0.0);
   const int L1[3] = {0, 1, 2}, L2[3] = {2, 0, 1};
   for (int e = 0; e < E; ++e) {
     const double* P = X + (size_t)e * 6;
     const double cx = (P[0] + P[2] + P[4]) / 3.0, cy = (P[1] + P[3] + P[5]) / 3.0;
-    for (int k = 0; k < 6; ++k) xs[(size_t)k * E + e] = P[k];
+    for (int k = 0; k < 6; ++k) xs[(size_t)k * ld + e] = P[k];
     for (int f = 0; f < 3; ++f) {
       const int q = neig[(size_t)e * 3 + f], ns = fneig[(size_t)e * 3 + f];
       int sw = 0;
@@ -244,22 +305,23 @@ inline int unstr_setup(UnstrDev& u, int E, const double* X, const int32_t* neig,
         const double mx = 0.5 * (P[2 * L1[f]] + P[2 * L2[f]]), my = 0.5 * (P[2 * L1[f] + 1] + P[2 * L2[f] + 1]);
         d = std::sqrt((cx - mx) * (cx - mx) + (cy - my) * (cy - my));
       }
-      enc[(size_t)f * E + e] = (ns & 3) | (sw << 2);
-      ng[(size_t)f * E + e] = q;
-      dc[(size_t)f * E + e] = d;
+      const double ex = P[2 * L2[f]] - P[2 * L1[f]], ey = P[2 * L2[f] + 1] - P[2 * L1[f] + 1];
+      enc[(size_t)f * ld + e] = (ns & 3) | (sw << 2);
+      ng[(size_t)f * ld + e] = q;
+      pn[(size_t)f * ld + e] = 0.5 * std::sqrt(ex * ex + ey * ey) / d;
     }
   }
-  u.E = E;
-  UCK(cudaMalloc(&u.X, (size_t)E * 6 * sizeof(double)));
-  UCK(cudaMalloc(&u.neig, (size_t)E * 3 * sizeof(int32_t)));
-  UCK(cudaMalloc(&u.nside, (size_t)E * 3 * sizeof(int32_t)));
-  UCK(cudaMalloc(&u.dcen, (size_t)E * 3 * sizeof(double)));
+  u.E = E; u.ld = ld;
+  UCK(cudaMalloc(&u.X, ld * 6 * sizeof(double)));
+  UCK(cudaMalloc(&u.neig, ld * 3 * sizeof(int32_t)));
+  UCK(cudaMalloc(&u.nside, ld * 3 * sizeof(int32_t)));
+  UCK(cudaMalloc(&u.pen, ld * 3 * sizeof(double)));
   for (int i = 0; i < 2; ++i) UCK(cudaMalloc(&u.T[i], (size_t)E * 3 * sizeof(double)));
   UCK(cudaMalloc(&u.told, (size_t)E * 3 * sizeof(double)));
-  UCK(cudaMemcpyAsync(u.X, xs.data(), (size_t)E * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
-  UCK(cudaMemcpyAsync(u.neig, ng.data(), (size_t)E * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  UCK(cudaMemcpyAsync(u.nside, enc.data(), (size_t)E * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  UCK(cudaMemcpyAsync(u.dcen, dc.data(), (size_t)E * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+  UCK(cudaMemcpyAsync(u.X, xs.data(), ld * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
+  UCK(cudaMemcpyAsync(u.neig, ng.data(), ld * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  UCK(cudaMemcpyAsync(u.nside, enc.data(), ld * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  UCK(cudaMemcpyAsync(u.pen, pn.data(), ld * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
   UCK(cudaMemsetAsync(u.T[0], 0, (size_t)E * 3 * sizeof(double), st));
   UCK(cudaMemsetAsync(u.T[1], 0, (size_t)E * 3 * sizeof(double), st));
   UCK(cudaStreamSynchronize(st));
@@ -270,13 +332,13 @@ inline int unstr_setup(UnstrDev& u, int E, const double* X, const int32_t* neig,
 // time loop of unstr_explicit (:588-795): told = tnew ; nits x { tnew = tnew_nonlin ; element loop }
 inline int unstr_step(UnstrDev& u, double dt, double ux, double uy, double t_bc, int ntime, int nits, int njac,
                       int exact, int use_dir, int nsm, cudaStream_t st, long long& nlaunch, std::string& err) {
-  const int grid = std::max(1, std::min((u.E + TPB - 1) / TPB, nsm * 8));
+  const int grid = stream_grid(k_unstr_explicit, u.occ_explicit, u.E, nsm);
   for (int it = 0; it < ntime; ++it) {
     UCK(cudaMemcpyAsync(u.told, u.T[u.cur], (size_t)u.E * 3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
     for (int k = 0; k < nits; ++k) {
       UnstrArgs a;
       a.X = u.X; a.neig = u.neig; a.nside = u.nside; a.Tin = u.T[u.cur]; a.told = u.told; a.Tout = u.T[u.cur ^ 1];
-      a.dt = dt; a.ux = ux; a.uy = uy; a.t_bc = t_bc; a.E = u.E; a.njac = njac; a.exact = exact; a.use_dir = use_dir;
+      a.dt = dt; a.ux = ux; a.uy = uy; a.t_bc = t_bc; a.ld = u.ld; a.E = u.E; a.njac = njac; a.exact = exact; a.use_dir = use_dir;
       k_unstr_explicit<<<grid, TPB, 0, st>>>(a);
       nlaunch++;
       UCK(cudaGetLastError());
@@ -296,93 +358,116 @@ inline int unstr_step(UnstrDev& u, double dt, double ux, double uy, double t_bc,
 // (k/dx) int sn_i (T - T2) (matrices.F90:113-115, get_diff_surf_stencl transport_tri_semi.F90:468-477) on the own and
 // the neighbour's columns.  The reference builds three scalar CSR matrices, converts them to dense and inverts
 // the dense (3E)^2 matrix with FINDInv (:366-378); here the operator never leaves its 4-blocks-per-row form, stored as
-// 36 + 4 planes so that every store of a warp is one full line.
+// 36 + 4 planes so that every store of a warp is one full line.  A face block has four non-zero entries (rows = my two face
+// nodes, columns = the neighbour's two); it leaves the registers as soon as its face is done, so only the diagonal block is
+// live across the face loop (48 registers instead of 74: 5 resident CTAs per SM keep enough stores in flight for HBM).
 struct BsrArgs {
-  const double* X; const int32_t* neig; const int32_t* nside; const double* dcen;
+  const double* X; const int32_t* neig; const int32_t* nside; const double* pen;
   double* val; int32_t* col; double* dinv; double* mdt; double* diag0;
-  double dt, ux, uy, kdiff;
+  double inv24dt, ux, uy, kdiff;
+  size_t ld;
   int E, use_dir;
 };
 
-__global__ void __launch_bounds__(TPB) k_assemble_bsr(BsrArgs a) {
+__global__ void __launch_bounds__(TPB, PAMG_OCC_ASSEMBLE) k_assemble_bsr(BsrArgs a) {
   const double al = 0.78867513459481288, be = 0.21132486540518712;
   const double w2 = al * al + be * be, w1 = 2.0 * al * be;
-  const size_t E = (size_t)a.E;
+  const size_t ld = a.ld;
+  const double sixth = 1.0 / 6.0;
   for (int e = blockIdx.x * TPB + threadIdx.x; e < a.E; e += gridDim.x * TPB) {
-    TriGeo g; double detj;
-    tri_geo(a.X, E, (size_t)e, g, detj);
-    const double area = g.area;
-    const double m12 = area / (12.0 * a.dt);
-    double blk[4][9];
+    TriEdges g;
+    tri_edges(a.X, ld, (size_t)e, g);
+    int q[3], enc[3];
 #pragma unroll
-    for (int bq = 0; bq < 4; ++bq)
+    for (int f = 0; f < 3; ++f) { q[f] = __ldg(a.neig + (size_t)f * ld + e); enc[f] = __ldg(a.nside + (size_t)f * ld + e); }
+    double pn[3] = {0.0, 0.0, 0.0};
+    if (a.kdiff != 0.0) {
 #pragma unroll
-      for (int q = 0; q < 9; ++q) blk[bq][q] = 0.0;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const double st = (g.gx[i] * a.ux + g.gy[i] * a.uy) * (area / 3.0);   // stiff(i,j): the same for every j (:281-283)
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-        blk[0][i * 3 + j] = m12 * (i == j ? 2.0 : 1.0) - st + a.kdiff * area * (g.gx[i] * g.gx[j] + g.gy[i] * g.gy[j]);
+      for (int f = 0; f < 3; ++f) pn[f] = a.kdiff * __ldg(a.pen + (size_t)f * ld + e);
     }
-    const int L1[3] = {0, 1, 2}, L2[3] = {2, 0, 1};
-    int cols[4] = {e, -1, -1, -1};
+    const double adet = fabs(g.detj);
+    const double m12 = adet * a.inv24dt;                    // A / (12 dt)
+    double d[9];
+    {
+      // stiff(i,j) = (grad(phi_i) . u) A/3: the same for every j (:281-283)
+      double st[3];
+      st[0] = g.sgn * (g.D * a.ux - g.C * a.uy) * sixth;
+      st[1] = g.sgn * (g.A * a.uy - g.B * a.ux) * sixth;
+      st[2] = -(st[0] + st[1]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) d[i * 3 + j] = m12 * (i == j ? 2.0 : 1.0) - st[i];
+      if (a.kdiff != 0.0) {
+        // k A grad(phi_i) . grad(phi_j) = k / (2 |detj|) G_i . G_j with the unnormalised gradients G = (D,-C), (-B,A), -(sum)
+        const double kk = a.kdiff * 0.5 / adet;
+        const double Gx[3] = {g.D, -g.B, g.B - g.D}, Gy[3] = {-g.C, g.A, g.C - g.A};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) d[i * 3 + j] += kk * (Gx[i] * Gx[j] + Gy[i] * Gy[j]);
+      }
+    }
+    const int L1[3] = {0, 1, 2}, L2[3] = {2, 0, 1}, L3[3] = {1, 2, 0};
+    a.col[e] = e;
 #pragma unroll
     for (int f = 0; f < 3; ++f) {
       const int l1 = L1[f], l2 = L2[f];
-      double nx, ny, sdet;
-      face_geo(g, l1, l2, nx, ny, sdet);
-      const int q = __ldg(a.neig + (size_t)f * E + e);
-      const int enc = __ldg(a.nside + (size_t)f * E + e);
-      const int ns = enc & 3;
-      const double has2 = ns >= 1 ? 1.0 : 0.0;
-      const double unn = nx * a.ux + ny * a.uy;
-      const double un = 0.5 * (unn + has2 * unn);
-      const bool in = signbit(-un) == 0;
-      const double c = sdet * unn;
+      const double c = face_flux(g, l1, l2, L3[f], a.ux, a.uy);   // sdetwei * n . u
+      const int ns = enc[f] & 3;
+      const bool in = signbit(-c) == 0;
       // neighbour nodes coincident with (l1, l2): as in get_unstr_sn2, or the geometric pairing with use_dir
       int m1 = (ns == 1) ? 2 : (ns == 2 ? 0 : 1), m2 = (ns == 1) ? 0 : (ns == 2 ? 1 : 2);
-      if (a.use_dir && (enc >> 2)) { const int t = m1; m1 = m2; m2 = t; }
+      if (a.use_dir && (enc[f] >> 2)) { const int t = m1; m1 = m2; m2 = t; }
+      double o11 = 0.0, o12 = 0.0;     // the face block: rows (l1, l2) x columns (m1, m2) = [[o11, o12], [o12, o11]]
+      int colf = -1;
       if (!in) {                       // outflow: own columns
-        blk[0][l1 * 3 + l1] += c * w2; blk[0][l1 * 3 + l2] += c * w1;
-        blk[0][l2 * 3 + l1] += c * w1; blk[0][l2 * 3 + l2] += c * w2;
+        d[l1 * 3 + l1] += c * w2; d[l1 * 3 + l2] += c * w1;
+        d[l2 * 3 + l1] += c * w1; d[l2 * 3 + l2] += c * w2;
       } else if (ns >= 1) {            // inflow: the neighbour's columns, its nodes paired as in get_unstr_sn2
-        const int b = (q != 0) ? 1 + f : 0;   // target_ele == 0 falls back to the element itself (:340-342)
-        blk[b][l1 * 3 + m1] += c * w2; blk[b][l1 * 3 + m2] += c * w1;
-        blk[b][l2 * 3 + m1] += c * w1; blk[b][l2 * 3 + m2] += c * w2;
-        if (q != 0) cols[1 + f] = q - 1;
+        if (q[f] != 0) { o11 = c * w2; o12 = c * w1; colf = q[f] - 1; }
+        else {                         // target_ele == 0 falls back to the element itself (:340-342)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            d[l1 * 3 + j] += (j == m1) ? c * w2 : ((j == m2) ? c * w1 : 0.0);
+            d[l2 * 3 + j] += (j == m1) ? c * w1 : ((j == m2) ? c * w2 : 0.0);
+          }
+        }
       }                                // inflow through the domain boundary (Nside = 0): sn2 = 0 -> no block
       if (a.kdiff != 0.0) {
         // penalty diffusion: own block += (k/dx) F, neighbour block -= (k/dx) F, F = (L/2) [[w2, w1], [w1, w2]]; on the
         // domain boundary the exterior trace is Dirichlet data (right-hand side), only the own part stays
-        const double kd = a.kdiff / __ldg(a.dcen + (size_t)f * E + e) * sdet;
-        blk[0][l1 * 3 + l1] += kd * w2; blk[0][l1 * 3 + l2] += kd * w1;
-        blk[0][l2 * 3 + l1] += kd * w1; blk[0][l2 * 3 + l2] += kd * w2;
-        if (q != 0 && ns >= 1) {
-          blk[1 + f][l1 * 3 + m1] -= kd * w2; blk[1 + f][l1 * 3 + m2] -= kd * w1;
-          blk[1 + f][l2 * 3 + m1] -= kd * w1; blk[1 + f][l2 * 3 + m2] -= kd * w2;
-          cols[1 + f] = q - 1;
-        }
+        const double kd = pn[f];
+        d[l1 * 3 + l1] += kd * w2; d[l1 * 3 + l2] += kd * w1;
+        d[l2 * 3 + l1] += kd * w1; d[l2 * 3 + l2] += kd * w2;
+        if (q[f] != 0 && ns >= 1) { o11 -= kd * w2; o12 -= kd * w1; colf = q[f] - 1; }
       }
+      a.col[(size_t)(1 + f) * ld + e] = colf;
+      double* v = a.val + (size_t)((1 + f) * 9) * ld + e;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          double x = 0.0;
+          if (i == l1) x = (j == m1) ? o11 : ((j == m2) ? o12 : 0.0);
+          if (i == l2) x = (j == m1) ? o12 : ((j == m2) ? o11 : 0.0);
+          v[(size_t)(i * 3 + j) * ld] = x;
+        }
     }
 #pragma unroll
-    for (int bq = 0; bq < 4; ++bq) {
-      a.col[(size_t)bq * E + e] = cols[bq];
-#pragma unroll
-      for (int q = 0; q < 9; ++q) a.val[(size_t)(bq * 9 + q) * E + e] = blk[bq][q];
-    }
-#pragma unroll
-    for (int q = 0; q < 9; ++q) a.diag0[(size_t)q * E + e] = blk[0][q];     // diagonal block without stabilisation
+    for (int k = 0; k < 9; ++k) { a.val[(size_t)k * ld + e] = d[k]; a.diag0[(size_t)k * ld + e] = d[k]; }   // diag0: without stabilisation
     // inverse of the diagonal block by its adjugate
-    const double* d = blk[0];
     const double c00 = d[4] * d[8] - d[5] * d[7], c01 = d[5] * d[6] - d[3] * d[8], c02 = d[3] * d[7] - d[4] * d[6];
     const double det = d[0] * c00 + d[1] * c01 + d[2] * c02, id = 1.0 / det;
-    double o[9];
-    o[0] = c00 * id; o[1] = (d[2] * d[7] - d[1] * d[8]) * id; o[2] = (d[1] * d[5] - d[2] * d[4]) * id;
-    o[3] = c01 * id; o[4] = (d[0] * d[8] - d[2] * d[6]) * id; o[5] = (d[2] * d[3] - d[0] * d[5]) * id;
-    o[6] = c02 * id; o[7] = (d[1] * d[6] - d[0] * d[7]) * id; o[8] = (d[0] * d[4] - d[1] * d[3]) * id;
-#pragma unroll
-    for (int q = 0; q < 9; ++q) a.dinv[(size_t)q * E + e] = o[q];
+    a.dinv[e] = c00 * id;
+    a.dinv[ld + e] = (d[2] * d[7] - d[1] * d[8]) * id;
+    a.dinv[2 * ld + e] = (d[1] * d[5] - d[2] * d[4]) * id;
+    a.dinv[3 * ld + e] = c01 * id;
+    a.dinv[4 * ld + e] = (d[0] * d[8] - d[2] * d[6]) * id;
+    a.dinv[5 * ld + e] = (d[2] * d[3] - d[0] * d[5]) * id;
+    a.dinv[6 * ld + e] = c02 * id;
+    a.dinv[7 * ld + e] = (d[1] * d[6] - d[0] * d[7]) * id;
+    a.dinv[8 * ld + e] = (d[0] * d[4] - d[1] * d[3]) * id;
     a.mdt[e] = m12;
   }
 }
@@ -390,11 +475,11 @@ __global__ void __launch_bounds__(TPB) k_assemble_bsr(BsrArgs a) {
 // y = A x (block-CSR planes) ; mode 1: y = b - A x.  x, b, y are (3, E) vectors.
 __global__ void __launch_bounds__(TPB) k_bsr_spmv(const double* __restrict__ val, const int32_t* __restrict__ col,
                                                   const double* __restrict__ x, const double* __restrict__ b,
-                                                  double* __restrict__ y, int En, int mode) {
+                                                  double* __restrict__ y, int En, size_t ld, int mode) {
   __shared__ double smw[TPB / 32][96];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* sm = smw[wib];
-  const size_t E = (size_t)En;
+  const size_t E = ld;   // plane stride
   for (int e0 = (blockIdx.x * (TPB / 32) + wib) * 32; e0 < En; e0 += gridDim.x * TPB) {
     const int nvalid = min(32, En - e0);
     const int e = e0 + lane;
@@ -420,11 +505,11 @@ __global__ void __launch_bounds__(TPB) k_bsr_spmv(const double* __restrict__ val
 
 // y = Dinv x (block-Jacobi preconditioner) ; mode 1: y = (M/dt) x with M/dt = mdt (I + J) per element (:366-369)
 __global__ void __launch_bounds__(TPB) k_block_apply(const double* __restrict__ dinv, const double* __restrict__ mdt,
-                                                     const double* __restrict__ x, double* __restrict__ y, int En, int mode) {
+                                                     const double* __restrict__ x, double* __restrict__ y, int En, size_t ld, int mode) {
   __shared__ double smw[TPB / 32][96];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* sm = smw[wib];
-  const size_t E = (size_t)En;
+  const size_t E = ld;   // plane stride
   for (int e0 = (blockIdx.x * (TPB / 32) + wib) * 32; e0 < En; e0 += gridDim.x * TPB) {
     const int nvalid = min(32, En - e0);
     const int e = e0 + lane;
@@ -498,6 +583,7 @@ struct KryArgs {
   const double* val; const int32_t* col; const double* dinv;
   double *x, *b, *r, *rh, *p, *v, *s, *t, *y, *z;
   double* ks;
+  size_t ld;
   int E;
 };
 
@@ -506,7 +592,7 @@ __global__ void __launch_bounds__(TPB) k_kry_init(KryArgs a, double tol) {
   __shared__ double smw[TPB / 32][96];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* sm = smw[wib];
-  const size_t E = (size_t)a.E;
+  const size_t E = a.ld;   // plane stride
   double sbb = 0, srr = 0;
   for (int e0 = (blockIdx.x * (TPB / 32) + wib) * 32; e0 < a.E; e0 += gridDim.x * TPB) {
     const int nvalid = min(32, a.E - e0);
@@ -547,7 +633,7 @@ __global__ void __launch_bounds__(TPB) k_kry_p(KryArgs a) {
   __shared__ double smw[TPB / 32][96];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* sm = smw[wib];
-  const size_t E = (size_t)a.E;
+  const size_t E = a.ld;   // plane stride
   const double rho_new = a.ks[KS_RHONEW], rho = a.ks[KS_RHO], alpha = a.ks[KS_ALPHA], omega = a.ks[KS_OMEGA];
   const double beta = (rho_new / rho) * (alpha / omega);
   for (int e0 = (blockIdx.x * (TPB / 32) + wib) * 32; e0 < a.E; e0 += gridDim.x * TPB) {
@@ -577,7 +663,7 @@ __global__ void __launch_bounds__(TPB) k_kry_spmv(KryArgs a) {
   __shared__ double smw[TPB / 32][96];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* sm = smw[wib];
-  const size_t E = (size_t)a.E;
+  const size_t E = a.ld;   // plane stride
   const double* in = WHICH == 0 ? a.y : a.z;
   double* out = WHICH == 0 ? a.v : a.t;
   const double* other = WHICH == 0 ? a.rh : a.s;
@@ -619,7 +705,7 @@ __global__ void __launch_bounds__(TPB) k_kry_s(KryArgs a) {
   __shared__ double smw[TPB / 32][96];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* sm = smw[wib];
-  const size_t E = (size_t)a.E;
+  const size_t E = a.ld;   // plane stride
   const double alpha = a.ks[KS_ALPHA];
   for (int e0 = (blockIdx.x * (TPB / 32) + wib) * 32; e0 < a.E; e0 += gridDim.x * TPB) {
     const int nvalid = min(32, a.E - e0);
@@ -669,12 +755,13 @@ struct StabArgs {
   const double* X; const double* tnew; const double* told;
   double* diff_coe; double* stab; const double* diag0; double* val; double* dinv;
   double dt, ux, uy;
+  size_t ld;
   int E, mode;
 };
 
 __global__ void __launch_bounds__(TPB) k_unstr_stab(StabArgs a) {
   const double toler = 0.00000000001;
-  const size_t E = (size_t)a.E;
+  const size_t E = a.ld;   // plane stride
   for (int e = blockIdx.x * TPB + threadIdx.x; e < a.E; e += gridDim.x * TPB) {
     const double x1 = __ldg(a.X + e), y1 = __ldg(a.X + E + e), x2 = __ldg(a.X + 2 * E + e), y2 = __ldg(a.X + 3 * E + e),
                  x3 = __ldg(a.X + 4 * E + e), y3 = __ldg(a.X + 5 * E + e);
@@ -737,24 +824,24 @@ __global__ void __launch_bounds__(TPB) k_unstr_stab(StabArgs a) {
 
 inline int implicit_assemble(UnstrDev& u, double dt, double ux, double uy, double kdiff, int use_dir, int nsm, cudaStream_t st,
                              long long& nlaunch, std::string& err) {
-  const size_t E = (size_t)u.E;
+  const size_t E = (size_t)u.E, ld = u.ld;
   if (!u.bsr_val) {
-    UCK(cudaMalloc(&u.bsr_val, E * 36 * sizeof(double)));
-    UCK(cudaMalloc(&u.bsr_col, E * 4 * sizeof(int32_t)));
-    UCK(cudaMalloc(&u.dinv, E * 9 * sizeof(double)));
+    UCK(cudaMalloc(&u.bsr_val, ld * 36 * sizeof(double)));
+    UCK(cudaMalloc(&u.bsr_col, ld * 4 * sizeof(int32_t)));
+    UCK(cudaMalloc(&u.dinv, ld * 9 * sizeof(double)));
     UCK(cudaMalloc(&u.mdt, E * sizeof(double)));
     UCK(cudaMalloc(&u.work, E * 3 * 9 * sizeof(double)));
     UCK(cudaMalloc(&u.dots, (size_t)(KS_PARTIAL + 2 * nsm * 8 + 2) * sizeof(double)));
     UCK(cudaMemsetAsync(u.dots, 0, (size_t)(KS_PARTIAL + 2 * nsm * 8 + 2) * sizeof(double), st));
     UCK(cudaMallocHost(&u.dots_host, KS_PARTIAL * sizeof(double)));
-    UCK(cudaMalloc(&u.diag0, E * 9 * sizeof(double)));
+    UCK(cudaMalloc(&u.diag0, ld * 9 * sizeof(double)));
     UCK(cudaMalloc(&u.stab, E * 12 * sizeof(double)));
   }
   BsrArgs a;
-  a.X = u.X; a.neig = u.neig; a.nside = u.nside; a.dcen = u.dcen; a.val = u.bsr_val; a.col = u.bsr_col; a.dinv = u.dinv;
+  a.X = u.X; a.neig = u.neig; a.nside = u.nside; a.pen = u.pen; a.val = u.bsr_val; a.col = u.bsr_col; a.dinv = u.dinv;
   a.mdt = u.mdt; a.diag0 = u.diag0;
-  a.dt = dt; a.ux = ux; a.uy = uy; a.kdiff = kdiff; a.E = u.E; a.use_dir = use_dir;
-  const int grid = std::max(1, std::min((u.E + TPB - 1) / TPB, nsm * 8));
+  a.inv24dt = 1.0 / (24.0 * dt); a.ux = ux; a.uy = uy; a.kdiff = kdiff; a.ld = ld; a.E = u.E; a.use_dir = use_dir;
+  const int grid = stream_grid(k_assemble_bsr, u.occ_assemble, u.E, nsm);
   k_assemble_bsr<<<grid, TPB, 0, st>>>(a);
   nlaunch++;
   UCK(cudaGetLastError());
@@ -770,10 +857,13 @@ inline int implicit_step(UnstrDev& u, int ntime, int nits, double tol, int max_i
                          int nsm, cudaStream_t st, long long& nlaunch, std::string& err, long long* host_syncs = nullptr) {
   const int E = u.E;
   const long long n = 3LL * E;
-  const int grid = std::max(1, std::min((E + TPB - 1) / TPB, nsm * 8));
+  const int g_apply = stream_grid(k_block_apply, u.occ_apply, E, nsm), g_stab = stream_grid(k_unstr_stab, u.occ_stab, E, nsm);
+  const int g_init = stream_grid(k_kry_init, u.occ_kry[0], E, nsm), g_p = stream_grid(k_kry_p, u.occ_kry[1], E, nsm);
+  const int g_v = stream_grid(k_kry_spmv<0>, u.occ_kry[2], E, nsm), g_s = stream_grid(k_kry_s, u.occ_kry[3], E, nsm);
+  const int g_t = stream_grid(k_kry_spmv<1>, u.occ_kry[4], E, nsm), g_x = stream_grid(k_kry_x, u.occ_kry[5], E, nsm);
   double* W = u.work;
   KryArgs a;
-  a.val = u.bsr_val; a.col = u.bsr_col; a.dinv = u.dinv; a.ks = u.dots; a.E = E;
+  a.val = u.bsr_val; a.col = u.bsr_col; a.dinv = u.dinv; a.ks = u.dots; a.E = E; a.ld = u.ld;
   a.b = W; a.r = W + n; a.rh = W + 2 * n; a.p = W + 3 * n; a.v = W + 4 * n; a.s = W + 5 * n; a.t = W + 6 * n; a.y = W + 7 * n;
   a.z = W + 8 * n;
   int total = 0;
@@ -786,23 +876,23 @@ inline int implicit_step(UnstrDev& u, int ntime, int nits, double tol, int max_i
       // the same system, which here starts converged and costs one residual evaluation
       if (k == 0) {
         UCK(cudaMemcpyAsync(u.told, a.x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        k_block_apply<<<grid, TPB, 0, st>>>(u.dinv, u.mdt, u.told, a.b, E, 1); nlaunch++;
+        k_block_apply<<<g_apply, TPB, 0, st>>>(u.dinv, u.mdt, u.told, a.b, E, u.ld, 1); nlaunch++;
       }
       if (u.with_stab) {   // INTENDED use (:367-368 commented at HEAD): diagonal blocks += stab(tnew_nonlin, told)
         StabArgs sa;
         sa.X = u.X; sa.tnew = a.x; sa.told = u.told; sa.diff_coe = u.stab + (size_t)E * 9; sa.stab = u.stab; sa.diag0 = u.diag0;
-        sa.val = u.bsr_val; sa.dinv = u.dinv; sa.dt = u.dt; sa.ux = u.ux; sa.uy = u.uy; sa.E = E; sa.mode = 1;
-        k_unstr_stab<<<grid, TPB, 0, st>>>(sa); nlaunch++;
+        sa.val = u.bsr_val; sa.dinv = u.dinv; sa.dt = u.dt; sa.ux = u.ux; sa.uy = u.uy; sa.ld = u.ld; sa.E = E; sa.mode = 1;
+        k_unstr_stab<<<g_stab, TPB, 0, st>>>(sa); nlaunch++;
       }
       UCK(cudaMemcpyAsync(u.dots + KS_MAXIT, &maxit, sizeof(double), cudaMemcpyHostToDevice, st));
-      k_kry_init<<<grid, TPB, 0, st>>>(a, tol); nlaunch++;
+      k_kry_init<<<g_init, TPB, 0, st>>>(a, tol); nlaunch++;
       for (;;) {
         for (int j = 0; j < KRY_BATCH; ++j) {
-          k_kry_p<<<grid, TPB, 0, st>>>(a);
-          k_kry_spmv<0><<<grid, TPB, 0, st>>>(a);
-          k_kry_s<<<grid, TPB, 0, st>>>(a);
-          k_kry_spmv<1><<<grid, TPB, 0, st>>>(a);
-          k_kry_x<<<grid, TPB, 0, st>>>(a);
+          k_kry_p<<<g_p, TPB, 0, st>>>(a);
+          k_kry_spmv<0><<<g_v, TPB, 0, st>>>(a);
+          k_kry_s<<<g_s, TPB, 0, st>>>(a);
+          k_kry_spmv<1><<<g_t, TPB, 0, st>>>(a);
+          k_kry_x<<<g_x, TPB, 0, st>>>(a);
           nlaunch += 5;
         }
         UCK(cudaMemcpyAsync(u.dots_host, u.dots, KS_PARTIAL * sizeof(double), cudaMemcpyDeviceToHost, st));
