@@ -1965,6 +1965,12 @@ int pamg_implicit_set_stab(pamg_handle* h, int with_stab) {
   CK(cudaSetDevice(h->device));
   if (h->un.with_stab && !with_stab)   // back to the plain operator: restore the diagonal blocks and their inverses
     return pamg_implicit_assemble_diffusion(h, h->un.dt, h->un.ux, h->un.uy, h->un.kdiff, -1);
+  if (with_stab && !h->un.with_stab) {
+    // keep the unstabilised diagonal blocks (the first 9 planes of the matrix): every nonlinear pass adds its own stab to them
+    const size_t bytes = h->un.ld * 9 * sizeof(double);
+    if (!h->un.diag0) CK(cudaMalloc(&h->un.diag0, bytes));
+    CK(cudaMemcpyAsync(h->un.diag0, h->un.bsr_val, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  }
   h->un.with_stab = with_stab != 0;
   return PAMG_OK;
 }

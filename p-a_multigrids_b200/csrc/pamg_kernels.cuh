@@ -1222,7 +1222,7 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
   constexpr uint32_t TILE_BYTES = 3 * TPB * sizeof(double);
   if (tid == 0) {
     for (int i = 0; i < WIN_NT + WIN_NB; ++i) mbar_init(&barT[i], 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&doneD[i], TPB / 32);
+    for (int i = 0; i < 4; ++i) mbar_init(&doneD[i], TPB / 64);   // the four down warps
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -1285,111 +1285,140 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
     }
     if (lane == 0) tma_store_wait_all();
   } else {
-    // ------------------------------------------------------------------ consumer warps
-    // (all per-tile index arithmetic in 32-bit: this branch is issue-bound and cannot use the uniform datapath)
+    // ------------------------------------------------------------------ consumer warps, split by colour
+    // Inside a row up and down children alternate, so a thread per child leaves every other lane idle in each colour phase
+    // (ncu: issue-bound at half the lanes).  Here a thread owns a PAIR of adjacent children (2j, 2j+1) of a tile: warps 0-3
+    // relax the down child of their pair in tile t+2, warps 4-7 the up child of theirs in tile t - every lane busy, and a warp
+    // runs one colour per iteration instead of two.  The one pair per row that straddles a row end holds two up children
+    // (last child of row r, first child of row r+1: both on parent faces) and no down child; the up warps relax its second
+    // child in an extra pass.  (all per-tile index arithmetic in 32-bit: this branch cannot use the uniform datapath)
     const int t0i = (int)t0, tbegi = (int)tbeg, tendi = (int)tend, dloi = (int)dlo, dhii = (int)dhi, tloi = (int)tlo, thii = (int)thi;
     const int pshift = twos - 8;                          // tiles per parent = 2^pshift (TPB = 2^8)
     const unsigned kmask = (unsigned)Cmask;
     auto waitT = [&](int tile) { mbar_wait(&barT[tile & (WIN_NT - 1)], (uint32_t)(((tile - tloi) >> 3) & 1)); };
     auto waitB = [&](int tile) { mbar_wait(&barB[(tile - dloi) & (WIN_NB - 1)], (uint32_t)(((tile - dloi) >> 2) & 1)); };
-    struct Prep { int r, ipos, len; double h1a, h1b, h2a, h2b; };
-    // numbering (r, ipos) of my child of `tile` comes from the down phase that relaxed the tile one iteration earlier;
-    // the parent of `tile` has been acquired through an rhs tile by then
-    auto prepare = [&](int tile, int r, int ipos, Prep& p) {
-      p.r = 2; p.ipos = 2; p.len = 3; p.h1a = 0.0; p.h1b = 0.0; p.h2a = 0.0; p.h2b = 0.0;
-      if (tile < tbegi || tile >= tendi) return;
-      p.r = r; p.ipos = ipos; p.len = b + 1 - 2 * r;
-      if (!(p.ipos & 1)) return;
-      const bool f1 = p.r == 1, side = p.ipos == 1 || p.ipos == p.len;
-      if (f1 | side) {
-        const int* ix = sIdx2[(tile >> pshift) & 1];
-        if (f1) {
-          ext_pair(a, ix[8], ix[0], ix[4], p.ipos >> 1, S, p.h1a, p.h1b);
+    const int j2 = (tid & (TPB / 2 - 1)) * 2;             // first child of my pair inside a tile
+    int r = 2, ipos = 2;                                  // numbering of child 2j of the tile this thread handled last
+    if (tid < TPB / 2) {
+      // ---- down warps: tile t+2 (reads the old up values of tiles t+1 .. t+4)
+      for (int tile = t0i; tile < tendi; ++tile) {
+        const int it = tile - t0i;
+        const int td = tile + 2;
+        if (tile == t0i) {
+          for (int tw = tloi; tw < min(thii, tile + 5); ++tw) waitT(tw);
+        } else if (tile + 4 < thii) {
+          waitT(tile + 4);
         }
-        if (side) {
-          const int mf = (p.ipos == 1) ? 2 : 1;
-          ext_pair(a, ix[8 + mf], ix[mf], ix[4 + mf], p.r - 1, S, p.h2a, p.h2b);
-        }
-      }
-    };
-    Prep cur, nxt;
-    prepare(t0i, 2, 2, cur);                             // t0 < tbeg: defaults
-    int rD = 2, iposD = 2;                               // numbering of my child of the tile relaxed by the last down phase
-    for (int tile = t0i; tile < tendi; ++tile) {
-      const int it = tile - t0i;
-      const int td = tile + 2;
-      const bool doD = td >= dloi && td <= dhii, doU = tile >= tbegi;
-      if (tile == t0i) {
-        for (int tw = tloi; tw < min(thii, tile + 5); ++tw) waitT(tw);
-      } else if (tile + 4 < thii) {
-        waitT(tile + 4);
-      }
-      const int rP = rD, iposP = iposD;                  // my child of tile+1 (down phase of the previous iteration)
-      if (doD) {
-        waitB(td);                                       // also acquires the coefficients of the parent of td
-        const int kD = (int)((((unsigned)td << 8) + (unsigned)tid) & kmask);
-        if (td == dloi) { int len; child_from_ele0(kD, s, rD, iposD, len); }
-        else child_advance(s, b, kD, rD, iposD);
-        const int r = rD, ipos = iposD;
-        if (!(ipos & 1)) {                               // down child: all three faces inside the parent
-          const int cw = ((td & (WIN_NT - 1)) << 8) + tid;
-          double* t = sT + cw * 3;
-          const double T1 = t[0], T2 = t[1], T3 = t[2];
-          FaceIn fi;
-          const double* tv = sT + ((cw + b - 2 * r) & (WIN_CH - 1)) * 3;
-          fi.n1a = tv[2]; fi.n1b = tv[0];
-          const double* tr = sT + ((cw + 1) & (WIN_CH - 1)) * 3;
-          const double* tl = sT + ((cw - 1) & (WIN_CH - 1)) * 3;
-          fi.n2a = tr[1]; fi.n2b = tr[2];
-          fi.n3a = tl[0]; fi.n3b = tl[1];
-          const double* bb = sB + ((td - dloi) & (WIN_NB - 1)) * (3 * TPB) + tid * 3;
-          const double* pd = sPC2[(td >> pshift) & 1] + PC_FOLD + 16;
-          const Folded& F = *reinterpret_cast<const Folded*>(pd);
-          double o1, o2, o3;
-          elem_apply_folded<MODE_GS>(F, pd, 0, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
-          t[0] = o1; t[1] = o2; t[2] = o3;
-        }
-      }
-      // down phase of this iteration done (also when there was nothing to do): tell the other warps
-      __syncwarp();
-      if ((tid & 31) == 0) mbar_arrive_cta(&doneD[it & 3]);
-      prepare(tile + 1, rP, iposP, nxt);
-      if (doU) {
-        // every warp has finished the down phase of the PREVIOUS iteration (first child of tile+1, last child of tile-1 ...)
-        if (it > 0) mbar_wait(&doneD[(it - 1) & 3], (uint32_t)(((it - 1) >> 2) & 1));
-        if (cur.ipos & 1) {
-          const int u_tile = tile >> pshift;
-          const int cw = ((tile & (WIN_NT - 1)) << 8) + tid;
-          double* t = sT + cw * 3;
-          const double T1 = t[0], T2 = t[1], T3 = t[2];
-          FaceIn fi;
-          int bmask = 0;
-          const double* tv = sT + ((cw + 2 * cur.r - b - 2) & (WIN_CH - 1)) * 3;
-          fi.n1a = tv[2]; fi.n1b = tv[0];
-          const double* tl = sT + ((cw - 1) & (WIN_CH - 1)) * 3;
-          const double* tr = sT + ((cw + 1) & (WIN_CH - 1)) * 3;
-          fi.n2a = tl[1]; fi.n2b = tl[2];
-          fi.n3a = tr[0]; fi.n3b = tr[1];
-          if (cur.r == 1 || cur.ipos == 1 || cur.ipos == cur.len) {
-            if (cur.r == 1) { fi.n1a = cur.h1a; fi.n1b = cur.h1b; bmask |= 1; }
-            if (cur.ipos == 1) { fi.n2a = cur.h2a; fi.n2b = cur.h2b; bmask |= 2; }
-            if (cur.ipos == cur.len) {
-              if (cur.len == 1) halo_pair(a, u_tile, 1, cur.r - 1, S, fi.n3a, fi.n3b);
-              else { fi.n3a = cur.h2a; fi.n3b = cur.h2b; }
-              bmask |= 4;
-            }
+        if (td >= dloi && td <= dhii) {
+          waitB(td);                                       // also acquires the coefficients of the parent of td
+          const int k = (int)((((unsigned)td << 8) + (unsigned)j2) & kmask);
+          if (td == dloi) { int len; child_from_ele0(k, s, r, ipos, len); }
+          else child_advance(s, b, k, r, ipos);
+          // the down child of the pair: child 2j when its position is even, else 2j+1 - unless 2j ends its row
+          const int off = ipos & 1;
+          if (!off || ipos < b + 1 - 2 * r) {
+            const int cw = ((td & (WIN_NT - 1)) << 8) + j2 + off;
+            double* t = sT + cw * 3;
+            const double T1 = t[0], T2 = t[1], T3 = t[2];
+            FaceIn fi;
+            const double* tv = sT + ((cw + b - 2 * r) & (WIN_CH - 1)) * 3;
+            fi.n1a = tv[2]; fi.n1b = tv[0];
+            const double* tr = sT + ((cw + 1) & (WIN_CH - 1)) * 3;
+            const double* tl = sT + ((cw - 1) & (WIN_CH - 1)) * 3;
+            fi.n2a = tr[1]; fi.n2b = tr[2];
+            fi.n3a = tl[0]; fi.n3b = tl[1];
+            const double* bb = sB + ((td - dloi) & (WIN_NB - 1)) * (3 * TPB) + (j2 + off) * 3;
+            const double* pd = sPC2[(td >> pshift) & 1] + PC_FOLD + 16;
+            const Folded& F = *reinterpret_cast<const Folded*>(pd);
+            double o1, o2, o3;
+            elem_apply_folded<MODE_GS>(F, pd, 0, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
+            t[0] = o1; t[1] = o2; t[2] = o3;
           }
-          const double* bb = sB + ((tile - dloi) & (WIN_NB - 1)) * (3 * TPB) + tid * 3;
-          const double* pu = sPC2[u_tile & 1];
-          const Folded& F = *reinterpret_cast<const Folded*>(pu + PC_FOLD);
-          double o1, o2, o3;
-          elem_apply_folded<MODE_GS>(F, pu + PC_DPEN, bmask, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
-          t[0] = o1; t[1] = o2; t[2] = o3;
         }
+        // down phase of this iteration done (also when there was nothing to do): tell the up warps
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive_cta(&doneD[it & 3]);
+        fence_async_smem();
+        named_arrive(1 + (it & 3), WIN2_THREADS);
       }
-      fence_async_smem();
-      named_arrive(1 + (it & 3), WIN2_THREADS);
-      cur = nxt;
+    } else {
+      // ---- up warps: tile t (reads the new down values of tiles t-2 .. t+1)
+      struct Prep { int r, ipos, len, off; double h1a, h1b, h2a, h2b; };   // my first up child of a tile, its halo values
+      auto prepare = [&](int tile, Prep& p) {
+        p.r = 2; p.ipos = 2; p.len = 3; p.off = 0; p.h1a = 0.0; p.h1b = 0.0; p.h2a = 0.0; p.h2b = 0.0;
+        if (tile < tbegi || tile >= tendi) return;
+        waitB(tile);                                       // landed long ago; acquires the tables of the tile's parent
+        const int k = (int)((((unsigned)tile << 8) + (unsigned)j2) & kmask);
+        if (tile == tbegi) { int len; child_from_ele0(k, s, r, ipos, len); }
+        else child_advance(s, b, k, r, ipos);
+        p.off = (ipos & 1) ^ 1;                            // child 2j when its position is odd, else 2j+1 (same row: rows are odd)
+        p.r = r; p.ipos = ipos + p.off; p.len = b + 1 - 2 * r;
+        const bool f1 = p.r == 1, side = p.ipos == 1 || p.ipos == p.len;
+        if (f1 | side) {
+          const int* ix = sIdx2[(tile >> pshift) & 1];
+          if (f1) ext_pair(a, ix[8], ix[0], ix[4], p.ipos >> 1, S, p.h1a, p.h1b);
+          if (side) {
+            const int mf = (p.ipos == 1) ? 2 : 1;
+            ext_pair(a, ix[8 + mf], ix[mf], ix[4 + mf], p.r - 1, S, p.h2a, p.h2b);
+          }
+        }
+      };
+      // one up child: row rr, position ip of a row of length ln, at ring index cw; h1 = values across parent face 1,
+      // h2 = across the side face the child lies on (side 3 for ip == 1, else side 2)
+      auto relax_up = [&](int tile, int cw, int rr, int ip, int ln, double h1a, double h1b, double h2a, double h2b) {
+        const int u_tile = tile >> pshift;
+        double* t = sT + cw * 3;
+        const double T1 = t[0], T2 = t[1], T3 = t[2];
+        FaceIn fi;
+        int bmask = 0;
+        const double* tv = sT + ((cw + 2 * rr - b - 2) & (WIN_CH - 1)) * 3;
+        fi.n1a = tv[2]; fi.n1b = tv[0];
+        const double* tl = sT + ((cw - 1) & (WIN_CH - 1)) * 3;
+        const double* tr = sT + ((cw + 1) & (WIN_CH - 1)) * 3;
+        fi.n2a = tl[1]; fi.n2b = tl[2];
+        fi.n3a = tr[0]; fi.n3b = tr[1];
+        if (rr == 1 || ip == 1 || ip == ln) {
+          if (rr == 1) { fi.n1a = h1a; fi.n1b = h1b; bmask |= 1; }
+          if (ip == 1) { fi.n2a = h2a; fi.n2b = h2b; bmask |= 2; }
+          if (ip == ln) {
+            if (ln == 1) halo_pair(a, u_tile, 1, rr - 1, S, fi.n3a, fi.n3b);
+            else { fi.n3a = h2a; fi.n3b = h2b; }
+            bmask |= 4;
+          }
+        }
+        const double* bb = sB + ((tile - dloi) & (WIN_NB - 1)) * (3 * TPB) + (cw & (TPB - 1)) * 3;
+        const double* pu = sPC2[u_tile & 1];
+        const Folded& F = *reinterpret_cast<const Folded*>(pu + PC_FOLD);
+        double o1, o2, o3;
+        elem_apply_folded<MODE_GS>(F, pu + PC_DPEN, bmask, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
+        t[0] = o1; t[1] = o2; t[2] = o3;
+      };
+      Prep cur, nxt;
+      prepare(t0i, cur);                                   // t0 < tbeg: defaults
+      for (int tile = t0i; tile < tendi; ++tile) {
+        const int it = tile - t0i;
+        if (tile == t0i) {
+          for (int tw = tloi; tw < min(thii, tile + 2); ++tw) waitT(tw);
+        } else if (tile + 1 < thii) {
+          waitT(tile + 1);
+        }
+        prepare(tile + 1, nxt);
+        if (tile >= tbegi) {
+          // every down warp has finished the PREVIOUS iteration (down children of tile+1; those of tile-2 .. tile are older)
+          if (it > 0) mbar_wait(&doneD[(it - 1) & 3], (uint32_t)(((it - 1) >> 2) & 1));
+          const int cw = ((tile & (WIN_NT - 1)) << 8) + j2 + cur.off;
+          relax_up(tile, cw, cur.r, cur.ipos, cur.len, cur.h1a, cur.h1b, cur.h2a, cur.h2b);
+          if (cur.off == 0 && cur.ipos == cur.len) {
+            // child 2j+1 opens row r+1: an up child on parent side 3 (and on side 2 as well at the apex)
+            double h2a, h2b;
+            halo_pair(a, tile >> pshift, 2, cur.r, S, h2a, h2b);
+            relax_up(tile, cw + 1, cur.r + 1, 1, cur.len - 2, 0.0, 0.0, h2a, h2b);
+          }
+        }
+        fence_async_smem();
+        named_arrive(1 + (it & 3), WIN2_THREADS);
+        cur = nxt;
+      }
     }
   }
 }

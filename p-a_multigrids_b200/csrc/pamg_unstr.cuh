@@ -48,7 +48,8 @@ struct UnstrDev {
   double* dots = nullptr;      // device scalars and partial sums of the Krylov solve
   double* dots_host = nullptr; // pinned mirror
   bool assembled = false;
-  double* diag0 = nullptr;     // [9][ld] diagonal blocks without stabilisation
+  double* diag0 = nullptr;     // [9][ld] diagonal blocks without stabilisation: copied out of bsr_val when the stabilisation is
+                               //         switched on (pamg_implicit_set_stab), not written by every assembly
   double* stab = nullptr;      // [E][9] Petrov-Galerkin element matrices ; [E][3] diff_coe behind them (ABI order)
   bool with_stab = false;
   double dt = 0.0, ux = 0.0, uy = 0.0, kdiff = 0.0;
@@ -129,7 +130,12 @@ struct UnstrArgs {
 #define PAMG_OCC_EXPLICIT 4
 #endif
 #ifndef PAMG_OCC_ASSEMBLE
-#define PAMG_OCC_ASSEMBLE 4
+#define PAMG_OCC_ASSEMBLE 3
+#endif
+#ifdef PAMG_ASM_STCS
+#define ASM_ST(p, v) __stcs((p), (v))
+#else
+#define ASM_ST(p, v) (*(p) = (v))
 #endif
 __global__ void __launch_bounds__(TPB, PAMG_OCC_EXPLICIT) k_unstr_explicit(UnstrArgs a) {
   __shared__ double smw[TPB / 32][2][96];
@@ -269,6 +275,7 @@ inline int stream_grid(K kernel, int& occ_cache, int E, int nsm) {
   if (occ_cache <= 0) {
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, TPB, 0) != cudaSuccess || occ < 1) occ = 2;
+    if (const char* ev = getenv("PAMG_UNSTR_CTAS_PER_SM")) occ = std::max(1, std::min(occ, atoi(ev)));   // experiments
     occ_cache = occ;
   }
   return std::max(1, std::min((E + TPB - 1) / TPB, nsm * std::min(occ_cache, 8)));   // (8: the Krylov partial sums are sized for it)
@@ -363,7 +370,7 @@ inline int unstr_step(UnstrDev& u, double dt, double ux, double uy, double t_bc,
 // live across the face loop (48 registers instead of 74: 5 resident CTAs per SM keep enough stores in flight for HBM).
 struct BsrArgs {
   const double* X; const int32_t* neig; const int32_t* nside; const double* pen;
-  double* val; int32_t* col; double* dinv; double* mdt; double* diag0;
+  double* val; int32_t* col; double* dinv; double* mdt;
   double inv24dt, ux, uy, kdiff;
   size_t ld;
   int E, use_dir;
@@ -409,7 +416,7 @@ __global__ void __launch_bounds__(TPB, PAMG_OCC_ASSEMBLE) k_assemble_bsr(BsrArgs
       }
     }
     const int L1[3] = {0, 1, 2}, L2[3] = {2, 0, 1}, L3[3] = {1, 2, 0};
-    a.col[e] = e;
+    ASM_ST(a.col + e, e);
 #pragma unroll
     for (int f = 0; f < 3; ++f) {
       const int l1 = L1[f], l2 = L2[f];
@@ -442,7 +449,7 @@ __global__ void __launch_bounds__(TPB, PAMG_OCC_ASSEMBLE) k_assemble_bsr(BsrArgs
         d[l2 * 3 + l1] += kd * w1; d[l2 * 3 + l2] += kd * w2;
         if (q[f] != 0 && ns >= 1) { o11 -= kd * w2; o12 -= kd * w1; colf = q[f] - 1; }
       }
-      a.col[(size_t)(1 + f) * ld + e] = colf;
+      ASM_ST(a.col + (size_t)(1 + f) * ld + e, colf);
       double* v = a.val + (size_t)((1 + f) * 9) * ld + e;
 #pragma unroll
       for (int i = 0; i < 3; ++i)
@@ -451,24 +458,24 @@ __global__ void __launch_bounds__(TPB, PAMG_OCC_ASSEMBLE) k_assemble_bsr(BsrArgs
           double x = 0.0;
           if (i == l1) x = (j == m1) ? o11 : ((j == m2) ? o12 : 0.0);
           if (i == l2) x = (j == m1) ? o12 : ((j == m2) ? o11 : 0.0);
-          v[(size_t)(i * 3 + j) * ld] = x;
+          ASM_ST(v + (size_t)(i * 3 + j) * ld, x);
         }
     }
 #pragma unroll
-    for (int k = 0; k < 9; ++k) { a.val[(size_t)k * ld + e] = d[k]; a.diag0[(size_t)k * ld + e] = d[k]; }   // diag0: without stabilisation
+    for (int k = 0; k < 9; ++k) ASM_ST(a.val + (size_t)k * ld + e, d[k]);
     // inverse of the diagonal block by its adjugate
     const double c00 = d[4] * d[8] - d[5] * d[7], c01 = d[5] * d[6] - d[3] * d[8], c02 = d[3] * d[7] - d[4] * d[6];
     const double det = d[0] * c00 + d[1] * c01 + d[2] * c02, id = 1.0 / det;
-    a.dinv[e] = c00 * id;
-    a.dinv[ld + e] = (d[2] * d[7] - d[1] * d[8]) * id;
-    a.dinv[2 * ld + e] = (d[1] * d[5] - d[2] * d[4]) * id;
-    a.dinv[3 * ld + e] = c01 * id;
-    a.dinv[4 * ld + e] = (d[0] * d[8] - d[2] * d[6]) * id;
-    a.dinv[5 * ld + e] = (d[2] * d[3] - d[0] * d[5]) * id;
-    a.dinv[6 * ld + e] = c02 * id;
-    a.dinv[7 * ld + e] = (d[1] * d[6] - d[0] * d[7]) * id;
-    a.dinv[8 * ld + e] = (d[0] * d[4] - d[1] * d[3]) * id;
-    a.mdt[e] = m12;
+    ASM_ST(a.dinv + e, c00 * id);
+    ASM_ST(a.dinv + ld + e, (d[2] * d[7] - d[1] * d[8]) * id);
+    ASM_ST(a.dinv + 2 * ld + e, (d[1] * d[5] - d[2] * d[4]) * id);
+    ASM_ST(a.dinv + 3 * ld + e, c01 * id);
+    ASM_ST(a.dinv + 4 * ld + e, (d[0] * d[8] - d[2] * d[6]) * id);
+    ASM_ST(a.dinv + 5 * ld + e, (d[2] * d[3] - d[0] * d[5]) * id);
+    ASM_ST(a.dinv + 6 * ld + e, c02 * id);
+    ASM_ST(a.dinv + 7 * ld + e, (d[1] * d[6] - d[0] * d[7]) * id);
+    ASM_ST(a.dinv + 8 * ld + e, (d[0] * d[4] - d[1] * d[3]) * id);
+    ASM_ST(a.mdt + e, m12);
   }
 }
 
@@ -834,12 +841,11 @@ inline int implicit_assemble(UnstrDev& u, double dt, double ux, double uy, doubl
     UCK(cudaMalloc(&u.dots, (size_t)(KS_PARTIAL + 2 * nsm * 8 + 2) * sizeof(double)));
     UCK(cudaMemsetAsync(u.dots, 0, (size_t)(KS_PARTIAL + 2 * nsm * 8 + 2) * sizeof(double), st));
     UCK(cudaMallocHost(&u.dots_host, KS_PARTIAL * sizeof(double)));
-    UCK(cudaMalloc(&u.diag0, ld * 9 * sizeof(double)));
     UCK(cudaMalloc(&u.stab, E * 12 * sizeof(double)));
   }
   BsrArgs a;
   a.X = u.X; a.neig = u.neig; a.nside = u.nside; a.pen = u.pen; a.val = u.bsr_val; a.col = u.bsr_col; a.dinv = u.dinv;
-  a.mdt = u.mdt; a.diag0 = u.diag0;
+  a.mdt = u.mdt;
   a.inv24dt = 1.0 / (24.0 * dt); a.ux = ux; a.uy = uy; a.kdiff = kdiff; a.ld = ld; a.E = u.E; a.use_dir = use_dir;
   const int grid = stream_grid(k_assemble_bsr, u.occ_assemble, u.E, nsm);
   k_assemble_bsr<<<grid, TPB, 0, st>>>(a);
