@@ -271,6 +271,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # watchdog: a run that makes no progress for this long dumps every thread's stack and exits instead of holding the box
+    wd = int(os.environ.get("PAMG_BENCH_WATCHDOG_S", "900"))
+    if wd > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, exit=True)
     if args.impl == "reference":
         run_reference(args, rank)
         return

@@ -77,6 +77,7 @@ struct LevelDev {
   bool strips_valid = false;                  // strips of the faces between local parents hold the current iterate
   bool cut_valid = false;                     // strips of the faces cut by the GPU partition hold the current iterate
   bool stage_valid = false;                   // ... and the level's flagged staging buffer holds it under the current exchange number
+  ulonglong2* xsend = nullptr;                // [U*3] where a sweep's producer warp sends the values of a cut side (ElemArgs::xsend)
   double* ovl_old = nullptr;                  // told strips (update_overlaps as written only)
   double* pc = nullptr;               // [U][NPC]
   bool rhs_valid = false;             // level 1: RHS matches TOLD
@@ -116,7 +117,7 @@ struct pamg_handle {
   int halo_mode = 2;
   long long debug_gap_ns = 0;   // PAMG_DEBUG_GAP_NS (measurement aid): a one-warp kernel that idles this long before every sweep
   // resident CTAs per SM of the shared-memory kernels on THIS device ([face_terms]); set once per handle in configure_kernels
-  struct KernelCfg { int win2[2] = {0, 0}, win[2] = {0, 0}, tma[2] = {0, 0}, gs2 = 0, gs = 0, halo = 0; bool done = false; } kc;
+  struct KernelCfg { int win2[2] = {0, 0}, win2x = 0, win[2] = {0, 0}, tma[2] = {0, 0}, gs2 = 0, gs2x = 0, gs = 0, halo = 0; bool done = false; } kc;
   bool capturing = false;   // stream capture in progress: no synchronisation, no per-launch error polling
   bool use_graph = true;    // replay the V-cycle as a CUDA graph from the second cycle on (PAMG_GRAPH=0 disables)
   struct VcGraph { long long key; std::vector<cudaGraphExec_t> exec; std::vector<long long> launches; };   // one graph per GPU of the group
@@ -157,11 +158,11 @@ struct pamg_handle {
   unsigned long long* p2p_sync = nullptr;   // exchange number, block counter (device)
   unsigned long long* p2p_err_host = nullptr;   // error word raised by a halo kernel that timed out: mapped pinned memory, so
   unsigned long long* p2p_err_dev = nullptr;    // every host synchronisation point can check it without a copy
-  uint4* p2p_stage = nullptr;               // flagged receive staging of ALL levels (IPC-exported): per level 2 parities x
+  uint4* p2p_stage = nullptr;               // flagged receive staging of ALL levels (IPC-exported): per level P2P_SLOTS slots x
   long long p2p_strips = 0;                 //   p2p_strips * 3 * S(level) words, levels one after the other
-  P2PArgs* d_xchg = nullptr;                // device copies of the per-level exchange descriptors for the sweep kernels
-  bool xchg_in_kernel = true;               // faces cut by the GPU partition are sent by the producer warps of the sweep and
-                                            // polled by the consumers that need them (PAMG_XCHG=kernel: separate k_halo launch)
+  bool xchg_in_kernel = true;               // the producer warps of a sweep send the new cut-face values to the peers themselves and a
+                                            // small unpack launch runs between two sweeps (PAMG_XCHG=halo: k_halo copies, sends and
+                                            // receives between the sweeps instead)
   struct P2PPeer { int slot_at_peer = -1, strip_begin_at_peer = 0; long long recv_strips_at_peer = 0; uint4* stage = nullptr; };
   std::vector<P2PPeer> p2p_peers;      // same order as plan.peers
   std::vector<void*> p2p_opened;       // IPC mappings to close
@@ -210,10 +211,10 @@ double* field_ptr(pamg_handle* h, int field, int level, bool for_write, int* rc)
   LevelDev& L = h->lev[level - 1];
   switch (field) {
     case PAMG_TNEW:
-      if (for_write) { *rc = materialise_tnew(h, L); L.strips_valid = false; L.cut_valid = false; return L.T[L.cur ^ 1]; }
+      if (for_write) { *rc = materialise_tnew(h, L); L.strips_valid = false; L.cut_valid = false; L.stage_valid = false; return L.T[L.cur ^ 1]; }
       return tnew_ptr(L);
     case PAMG_TNONLIN:
-      if (for_write) { *rc = materialise_tnew(h, L); L.strips_valid = false; L.cut_valid = false; }
+      if (for_write) { *rc = materialise_tnew(h, L); L.strips_valid = false; L.cut_valid = false; L.stage_valid = false; }
       return L.T[L.cur];
     case PAMG_TOLD: if (for_write) L.rhs_valid = false; return L.told;
     case PAMG_RHS: if (for_write) L.rhs_valid = true; return L.rhs;
@@ -325,13 +326,13 @@ bool parent_coefficients(const pamg_params& p, const double* Xall, const int32_t
 }
 
 int launch_halo(pamg_handle* h, int level, int what = 0);
+int p2p_upload_args(pamg_handle* h);
 
 void p2p_close(pamg_handle* h) {
   for (void* p : h->p2p_opened) cudaIpcCloseMemHandle(p);
   h->p2p_opened.clear();
   if (h->p2p_sync) { cudaFree(h->p2p_sync); h->p2p_sync = nullptr; }
   if (h->p2p_stage) { cudaFree(h->p2p_stage); h->p2p_stage = nullptr; }
-  if (h->d_xchg) { cudaFree(h->d_xchg); h->d_xchg = nullptr; }
   if (h->p2p_err_host) { cudaFreeHost(h->p2p_err_host); h->p2p_err_host = nullptr; h->p2p_err_dev = nullptr; }
   h->p2p_ready = false; h->p2p_failed = false;
   for (auto& pp : h->p2p_peers) pp.stage = nullptr;
@@ -345,14 +346,14 @@ int p2p_check(pamg_handle* h) {
   return PAMG_OK;
 }
 
-// first word of level il (0-based) inside a staging buffer that holds `strips` cut strips per level and parity
+// first word of level il (0-based) inside a staging buffer that holds `strips` cut strips per level and slot
 long long stage_offset(long long strips, const std::vector<LevelDev>& lev, int il) {
   long long off = 0;
-  for (int l = 0; l < il; ++l) off += 2 * strips * 3 * lev[l].S;
+  for (int l = 0; l < il; ++l) off += (long long)P2P_SLOTS * strips * 3 * lev[l].S;
   return off;
 }
 
-// local part of the set-up: exchange counters, the flagged receive staging buffers (per level, 2 parities) and the error word
+// local part of the set-up: exchange counters, the flagged receive staging buffers (per level, P2P_SLOTS slots) and the error word
 int p2p_alloc_local(pamg_handle* h) {
   long long strips = 0;
   for (const auto& pr : h->plan.peers) strips = std::max(strips, (long long)pr.strip_begin + pr.nfaces);
@@ -378,12 +379,20 @@ int p2p_setup(pamg_handle* h) {
   if ((int)h->plan.peers.size() > P2P_MAXP) ok = 0;
   for (const auto& pp : h->p2p_peers) if (pp.slot_at_peer < 0) ok = 0;
   if (p2p_alloc_local(h) != PAMG_OK) { ok = 0; (void)cudaGetLastError(); }
-  cudaIpcMemHandle_t mine;
+  // what travels: the IPC handle of my staging buffer and the identity of my GPU
+  struct Card { cudaIpcMemHandle_t handle; long long gpu; };
+  Card mine;
   std::memset(&mine, 0, sizeof(mine));
-  if (ok && cudaIpcGetMemHandle(&mine, h->p2p_stage) != cudaSuccess) { ok = 0; (void)cudaGetLastError(); }
-  // all-gather of the handles with grouped send / recv (R <= 8)
-  const size_t hb = sizeof(cudaIpcMemHandle_t);
-  std::vector<cudaIpcMemHandle_t> all(R);
+  {
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, h->device) == cudaSuccess)
+      mine.gpu = ((long long)pr.pciDomainID << 32) | ((long long)pr.pciBusID << 16) | (long long)pr.pciDeviceID;
+    else { ok = 0; (void)cudaGetLastError(); }
+  }
+  if (ok && cudaIpcGetMemHandle(&mine.handle, h->p2p_stage) != cudaSuccess) { ok = 0; (void)cudaGetLastError(); }
+  // all-gather of the cards with grouped send / recv (R <= 8)
+  const size_t hb = sizeof(Card);
+  std::vector<Card> all(R);
   unsigned char* d_buf = nullptr;      // [mine][all R][ok]
   const bool have_buf = cudaMalloc(&d_buf, hb * (R + 1) + sizeof(int)) == cudaSuccess;
   int rc = PAMG_OK;
@@ -404,7 +413,7 @@ int p2p_setup(pamg_handle* h) {
   if (!rc && ok) {
     for (size_t i = 0; i < h->plan.peers.size(); ++i) {
       void* ptr = nullptr;
-      if (cudaIpcOpenMemHandle(&ptr, all[h->plan.peers[i].part], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; (void)cudaGetLastError(); break; }
+      if (cudaIpcOpenMemHandle(&ptr, all[h->plan.peers[i].part].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; (void)cudaGetLastError(); break; }
       h->p2p_opened.push_back(ptr);
       h->p2p_peers[i].stage = (uint4*)ptr;
     }
@@ -418,7 +427,13 @@ int p2p_setup(pamg_handle* h) {
   }
   cudaFree(d_buf);
   if (rc) return rc;
-  if (ok) h->p2p_ready = true; else h->p2p_failed = true;
+  if (ok) {
+    // parts that share one GPU keep the exchange in k_halo (the same data on every rank: the same decision)
+    for (int r = 0; r < R && h->xchg_in_kernel; ++r)
+      for (int q = r + 1; q < R; ++q) if (all[r].gpu == all[q].gpu) { h->xchg_in_kernel = false; break; }
+    if ((rc = p2p_upload_args(h))) return rc;
+    h->p2p_ready = true;
+  } else h->p2p_failed = true;
   return PAMG_OK;
 }
 
@@ -436,12 +451,38 @@ int p2p_args(pamg_handle* h, LevelDev& L, double* ovl, P2PArgs& a) {
     if ((long long)(pr.send_begin - base) * S3 != so) return fail(h, PAMG_ERR_STATE, "send slots are not contiguous per peer");
     a.remote[i] = h->p2p_peers[i].stage + stage_offset(h->p2p_peers[i].recv_strips_at_peer, h->lev, il) +
                   (long long)h->p2p_peers[i].strip_begin_at_peer * S3;
-    a.rstride[i] = h->p2p_peers[i].recv_strips_at_peer * S3;   // the peer's own words per parity on this level
+    a.rstride[i] = h->p2p_peers[i].recv_strips_at_peer * S3;   // the peer's own words per slot on this level
     a.soff[i] = so; a.roff[i] = ro; a.rbeg[i] = (long long)pr.strip_begin * S3;
     so += pr.nfaces * S3; ro += pr.nfaces * S3;
   }
   a.soff[a.npeers] = so; a.roff[a.npeers] = ro;
   a.send_base = base;
+  return PAMG_OK;
+}
+
+// per level and (parent, side): where the producer warp of a sweep sends the boundary values of a side cut by the GPU
+// partition (ElemArgs::xsend) - a host-built table, so that the producer warp has no dependent look-ups to do
+int p2p_upload_args(pamg_handle* h) {
+  if (h->plan.peers.empty()) return PAMG_OK;
+  std::vector<ulonglong2> t((size_t)h->U * 3);
+  for (size_t l = 0; l < h->lev.size(); ++l) {
+    P2PArgs v;
+    std::memset(&v, 0, sizeof(v));
+    int rc = p2p_args(h, h->lev[l], h->lev[l].ovlb[0], v);
+    if (rc) return rc;
+    const long long S3 = 3ll * h->lev[l].S;
+    for (int lf = 0; lf < h->U * 3; ++lf) {
+      const int d = h->plan.dst_strip[lf];
+      t[lf] = make_ulonglong2(0ull, 0ull);
+      if (d < h->plan.nstrips) continue;
+      const long long q0 = (long long)(d - h->plan.nstrips - v.send_base) * S3;
+      int p = 0;
+      while (q0 >= v.soff[p + 1]) ++p;
+      t[lf] = make_ulonglong2((unsigned long long)(v.remote[p] + (q0 - v.soff[p])), (unsigned long long)v.rstride[p]);
+    }
+    if (!h->lev[l].xsend) CK(cudaMalloc(&h->lev[l].xsend, t.size() * sizeof(ulonglong2)));
+    CK(cudaMemcpy(h->lev[l].xsend, t.data(), t.size() * sizeof(ulonglong2), cudaMemcpyHostToDevice));
+  }
   return PAMG_OK;
 }
 
@@ -473,26 +514,19 @@ int launch_halo(pamg_handle* h, int level, int what) {
   a.cut_lf = h->cut_lf; a.ncut = (int)h->plan.cut_lf.size();
   a.bc_kind = h->bc_kind; a.bc_val = h->bc_val;
   const bool cut = what != 1 && !h->plan.peers.empty();
-  if (what == 2 && !cut) { L.cut_valid = true; return PAMG_OK; }
-  const long long n = (what == 2 ? (long long)a.ncut : (long long)h->U * 3) * L.S;
+  if ((what == 2 || what == 4) && !cut) { L.cut_valid = true; return PAMG_OK; }
+  if (what == 4 && !(h->p2p_ready && L.stage_valid)) return fail(h, PAMG_ERR_STATE, "nothing staged to unpack");
+  const long long n = (what == 2 ? (long long)a.ncut : what == 4 ? (long long)a.ncut * 3 : (long long)h->U * 3) * L.S;
   a.x.npeers = 0;
   if (cut && h->comm && h->p2p_enabled && !h->p2p_ready && !h->p2p_failed && !h->capturing && h->level_offset == 0) {
     int rc = p2p_setup(h);      // collective, first exchange only
     if (rc) return rc;
   }
   const bool fused_x = cut && h->p2p_ready;
-  if (fused_x) { int rc = p2p_args(h, L, L.ovlb[L.ovl_cur], a.x); if (rc) return rc; }
-  // with the exchange fused in, blocks poll for remote data after their own work: keep the grid within one wave
-  int hgrid = grid_for(h, n);
-  if (fused_x) hgrid = std::min(hgrid, h->nsm * std::min(std::max(h->kc.halo, 1), 4));
-  k_halo<<<hgrid, TPB, 0, h->stream>>>(a);
-  h->launches++;
-  CK(cudaGetLastError());
-  if (what == 1) return PAMG_OK;
-  if (cut && !fused_x) { int rc = exchange_halo_nccl(h, L, L.ovlb[L.ovl_cur]); if (rc) return rc; }
   if (what == 0 && cut) {
-    // update_overlaps as written also fills t_overlap_old (splitting.F90:1259-1262): a second exchange carries the told
-    // values of the cut faces into the neighbours' old strips (the sweeps never read them; the entry point returns them)
+    // update_overlaps as written also fills t_overlap_old (splitting.F90:1259-1262): an exchange of its own carries the told
+    // values of the cut faces into the neighbours' old strips (the sweeps never read them; the entry point returns them).
+    // It goes FIRST, so that the staging buffers end up holding the tnew values under the current exchange number.
     HaloArgs b = a;
     b.tnew = L.told; b.ovl = L.ovl_old; b.with_old = 0; b.what = 2;
     if (fused_x) { int rc = p2p_args(h, L, L.ovl_old, b.x); if (rc) return rc; }
@@ -504,7 +538,18 @@ int launch_halo(pamg_handle* h, int level, int what) {
     CK(cudaGetLastError());
     if (!fused_x) { int rc = exchange_halo_nccl(h, L, L.ovl_old); if (rc) return rc; }
   }
+  if (fused_x) { int rc = p2p_args(h, L, L.ovlb[L.ovl_cur], a.x); if (rc) return rc; }
+  // with the exchange fused in, blocks poll for remote data after their own work: keep the grid within one wave
+  int hgrid = grid_for(h, n);
+  if (fused_x) hgrid = std::min(hgrid, h->nsm * std::min(std::max(h->kc.halo, 1), 4));
+  k_halo<<<hgrid, TPB, 0, h->stream>>>(a);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (what == 1) return PAMG_OK;
+  if (what == 4) { L.cut_valid = true; return PAMG_OK; }
+  if (cut && !fused_x) { int rc = exchange_halo_nccl(h, L, L.ovlb[L.ovl_cur]); if (rc) return rc; }
   L.cut_valid = true;
+  if (fused_x) L.stage_valid = true;       // the same values sit in the staging buffers under the current exchange number
   if (what != 2) L.strips_valid = true;
   return PAMG_OK;
 }
@@ -516,7 +561,15 @@ int ensure_strips(pamg_handle* h, int level, bool all = true) {
   LevelDev& L = h->lev[level - 1];
   if (!h->p.face_terms) return PAMG_OK;
   if ((all || h->halo_mode == 0) && !L.strips_valid) return launch_halo(h, level, 3);
-  return L.cut_valid ? PAMG_OK : launch_halo(h, level, 2);
+  if (L.cut_valid) return PAMG_OK;
+  // the values a sweep's producer warps sent are waiting in the staging buffer: unpack them; else a full exchange
+  return launch_halo(h, level, (L.stage_valid && h->p2p_ready) ? 4 : 2);
+}
+
+// the producer warps of this level's sweep kernel can send the cut-face values themselves
+bool xchg_kernel(const pamg_handle* h, const LevelDev& L) {
+  return h->xchg_in_kernel && h->p2p_ready && L.xsend && !h->plan.peers.empty() && h->p.face_terms &&
+         h->kernel_mode == 4 && h->win_producer && L.s >= 6 && L.s <= 8;
 }
 
 int launch_build_rhs(pamg_handle* h) {
@@ -547,6 +600,10 @@ int configure_face(pamg_handle* h) {
   if ((rc = configure_one(h, k_element_win2<MODE_JACOBI, FACE>, WIN2_THREADS, WIN_SMEM_BYTES, h->kc.win2[f]))) return rc;
   if ((rc = configure_one(h, k_element_win2<MODE_RESID, FACE>, WIN2_THREADS, WIN_SMEM_BYTES, dummy))) return rc;
   if ((rc = configure_one(h, k_element_win2<MODE_RICH, FACE>, WIN2_THREADS, WIN_SMEM_BYTES, dummy))) return rc;
+  if (FACE) {
+    if ((rc = configure_one(h, k_element_win2<MODE_JACOBI, FACE, true>, WIN2_THREADS, WIN_SMEM_BYTES, h->kc.win2x))) return rc;
+    if ((rc = configure_one(h, k_element_win2<MODE_RICH, FACE, true>, WIN2_THREADS, WIN_SMEM_BYTES, dummy))) return rc;
+  }
   if ((rc = configure_one(h, k_element_win<MODE_JACOBI, FACE>, TPB, WIN_SMEM_BYTES, h->kc.win[f]))) return rc;
   if ((rc = configure_one(h, k_element_win<MODE_RESID, FACE>, TPB, WIN_SMEM_BYTES, dummy))) return rc;
   if ((rc = configure_one(h, k_element_win<MODE_RICH, FACE>, TPB, WIN_SMEM_BYTES, dummy))) return rc;
@@ -562,7 +619,8 @@ int configure_kernels(pamg_handle* h) {
   int rc;
   if ((rc = configure_face<true>(h))) return rc;
   if ((rc = configure_face<false>(h))) return rc;
-  if ((rc = configure_one(h, k_gs_win2, WIN2_THREADS, GSW_SMEM_BYTES, h->kc.gs2))) return rc;
+  if ((rc = configure_one(h, k_gs_win2<false>, WIN2_THREADS, GSW_SMEM_BYTES, h->kc.gs2))) return rc;
+  if ((rc = configure_one(h, k_gs_win2<true>, WIN2_THREADS, GSW_SMEM_BYTES, h->kc.gs2x))) return rc;
   if ((rc = configure_one(h, k_gs_win, TPB, GSW_SMEM_BYTES, h->kc.gs))) return rc;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->kc.halo, k_halo, TPB, 0));
   if (h->kc.halo < 1) h->kc.halo = 1;
@@ -603,8 +661,10 @@ bool producer_kernel(const pamg_handle* h, const LevelDev& L, bool gs) {
 // write_next: the kernel's producer warp writes the strips of the next sweep into the other strip buffer
 template <int MODE>
 int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout, int colour, int grid, bool use_strips,
-                   bool write_next = false) {
+                   bool write_next = false, bool xchg = false) {
   ElemArgs a;
+  a.xsend = L.xsend; a.xsync = h->p2p_sync ? h->p2p_sync + (size_t)(&L - h->lev.data()) * P2P_WORDS : nullptr;
+  if (MODE == MODE_RESID) xchg = false;     // a residual evaluation sends nothing
   a.Tin = Tin; a.Tout = Tout; a.rhs = L.rhs; a.ovl = L.ovlb[L.ovl_cur]; a.pc = L.pc; a.strip_of = h->strip_of; a.hmap = h->hmap;
   // (an in-place pass - the two-pass coloured GS - must see start-of-sweep values across parent faces: strips only)
   a.nsrc = (use_strips || Tin == Tout) ? nullptr : h->nsrc;
@@ -616,8 +676,9 @@ int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout,
   if (prof) CK(cudaEventRecord(h->pev[h->pev_used], h->stream));
   if (MODE != MODE_GS && h->kernel_mode == 4 && h->win_producer && L.s >= 6 && L.s <= 8) {
     // window kernel with a producer warp (no CTA-wide barrier between tiles)
-    auto kern = h->p.face_terms ? k_element_win2<MODE, true> : k_element_win2<MODE, false>;
-    const int tgrid = (int)std::max(1ll, std::min(L.nelem / TPB, (long long)h->nsm * h->kc.win2[f]));
+    auto kern = xchg ? k_element_win2<MODE == MODE_RESID ? MODE_JACOBI : MODE, true, true>
+                     : h->p.face_terms ? k_element_win2<MODE, true> : k_element_win2<MODE, false>;
+    const int tgrid = (int)std::max(1ll, std::min(L.nelem / TPB, (long long)h->nsm * (xchg ? h->kc.win2x : h->kc.win2[f])));
     kern<<<tgrid, WIN2_THREADS, WIN_SMEM_BYTES, h->stream>>>(a);
     if (MODE == MODE_RESID) h->last_partials = tgrid;
   } else if ((MODE != MODE_GS || h->gs_tma) && h->kernel_mode == 4 && L.C >= TPB && L.s <= 8) {
@@ -650,19 +711,21 @@ bool gs_fused_ok(const pamg_handle* h, const LevelDev& L) {
   return h->gs_fused && h->kernel_mode == 4 && h->p.face_terms && L.C >= TPB && L.s <= 8;
 }
 
-int launch_gs_fused(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout, bool use_strips, bool write_next) {
+int launch_gs_fused(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout, bool use_strips, bool write_next, bool xchg) {
   ElemArgs a;
+  a.xsend = L.xsend; a.xsync = h->p2p_sync ? h->p2p_sync + (size_t)(&L - h->lev.data()) * P2P_WORDS : nullptr;
   a.Tin = Tin; a.Tout = Tout; a.rhs = L.rhs; a.ovl = L.ovlb[L.ovl_cur]; a.pc = L.pc; a.strip_of = h->strip_of; a.hmap = h->hmap;
   a.nsrc = use_strips ? nullptr : h->nsrc;
   a.ovl_next = write_next ? L.ovlb[L.ovl_cur ^ 1] : nullptr; a.dst_strip = h->dst_strip; a.rev = h->rev; a.nstrips = h->plan.nstrips;
   a.partial = h->partial; a.omega = h->p.omega; a.rsign = (double)h->p.residual_sign; a.nelem = L.nelem; a.s = L.s;
   a.colour = 1; a.partial_off = 0;
   const bool producer = h->win_producer && L.s >= 6;
-  const int resident = producer ? h->kc.gs2 : h->kc.gs;
+  const int resident = producer ? (xchg ? h->kc.gs2x : h->kc.gs2) : h->kc.gs;
   const bool prof = h->profiling && h->pev_used + 2 <= (int)h->pev.size();
   if (prof) CK(cudaEventRecord(h->pev[h->pev_used], h->stream));
   const int tgrid = (int)std::max(1ll, std::min(L.nelem / TPB, (long long)h->nsm * resident));
-  if (producer) k_gs_win2<<<tgrid, WIN2_THREADS, GSW_SMEM_BYTES, h->stream>>>(a);
+  if (producer && xchg) k_gs_win2<true><<<tgrid, WIN2_THREADS, GSW_SMEM_BYTES, h->stream>>>(a);
+  else if (producer) k_gs_win2<false><<<tgrid, WIN2_THREADS, GSW_SMEM_BYTES, h->stream>>>(a);
   else k_gs_win<<<tgrid, TPB, GSW_SMEM_BYTES, h->stream>>>(a);
   if (prof) { CK(cudaEventRecord(h->pev[h->pev_used + 1], h->stream)); h->pev_used += 2; }
   h->launches++;
@@ -685,11 +748,14 @@ int do_smooth(pamg_handle* h, int level, int solver, int nsweeps) {
     const bool in_place = gs && !gs_fused_ok(h, L);
     const bool fusedk = h->halo_mode == 2 && h->p.face_terms && !in_place && producer_kernel(h, L, gs);
     const bool use_strips = in_place || fusedk || h->halo_mode == 0;
+    // the producer warps of the sweep send the new cut-face values to the peers themselves (the strips it reads were
+    // exchanged by k_halo or unpacked out of the staging buffer just before)
+    const bool xs = fusedk && xchg_kernel(h, L) && (!gs || (h->win_producer && L.s >= 6));
     int rc = ensure_strips(h, level, use_strips);
     if (rc) return rc;
     if (solver == 1 || solver == 2) {
-      rc = (solver == 1) ? launch_element<MODE_JACOBI>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid, use_strips, fusedk)
-                         : launch_element<MODE_RICH>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid, use_strips, fusedk);
+      rc = (solver == 1) ? launch_element<MODE_JACOBI>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid, use_strips, fusedk, xs)
+                         : launch_element<MODE_RICH>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid, use_strips, fusedk, xs);
       if (rc) return rc;
       L.cur ^= 1;
       L.tnew_alias = false;  // the old buffer now holds the start-of-sweep field = tracer%tnew
@@ -697,7 +763,7 @@ int do_smooth(pamg_handle* h, int level, int solver, int nsweeps) {
       // two-colour ordering of the reference's Gauss-Seidel sweep (all down children, then all up children; values across
       // parent faces stay lagged exactly as at :647-655), both colours in one pass over memory, written to the other
       // buffer (which then holds tracer%tnew, as for Jacobi)
-      rc = launch_gs_fused(h, L, L.T[L.cur], L.T[L.cur ^ 1], use_strips, fusedk);
+      rc = launch_gs_fused(h, L, L.T[L.cur], L.T[L.cur ^ 1], use_strips, fusedk, xs);
       if (rc) return rc;
       L.cur ^= 1;
       L.tnew_alias = false;
@@ -711,8 +777,9 @@ int do_smooth(pamg_handle* h, int level, int solver, int nsweeps) {
     if (fusedk) {
       L.ovl_cur ^= 1;                        // the producer warps wrote the strips of the new iterate
       L.strips_valid = true; L.cut_valid = h->plan.peers.empty();
+      L.stage_valid = xs;                    // ... and sent the cut-face values to the peers as the next exchange
     } else {
-      L.strips_valid = false; L.cut_valid = false;
+      L.strips_valid = false; L.cut_valid = false; L.stage_valid = false;
     }
   }
   return PAMG_OK;
@@ -785,7 +852,7 @@ int do_prolong(pamg_handle* h, int fine_level, bool keep_tnew = true) {
       F.tnew_alias = true;            // inside the V-cycle nothing reads the pre-correction field
     }
     a.src = Cc.T[Cc.cur]; a.dst = F.T[F.cur];
-    F.strips_valid = false; F.cut_valid = false;           // the iterate changes outside a sweep
+    F.strips_valid = false; F.cut_valid = false; F.stage_valid = false;           // the iterate changes outside a sweep
     k_prolong_p1<<<grid_for(h, F.nelem), TPB, 0, h->stream>>>(a);
   }
   h->launches++;
@@ -869,7 +936,7 @@ int agg_coarse_solve(const Group& G, pamg_handle* owner, int solver, int nu1, in
       LevelDev& A = g->lev[0];
       CK(cudaMemcpyAsync(A.rhs, Lc.rhs, per_parent * h->U * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
       CK(cudaMemsetAsync(A.T[A.cur], 0, A.ndof * sizeof(double), h->stream));
-      A.tnew_alias = true; A.strips_valid = false; A.cut_valid = false; A.rhs_valid = true;
+      A.tnew_alias = true; A.strips_valid = false; A.cut_valid = false; A.stage_valid = false; A.rhs_valid = true;
       const long long l0 = g->launches;
       int rc = vcycle_rec(Group{g}, g, 1, solver, nu1, nu2, ncoarse);
       h->launches += g->launches - l0;
@@ -886,7 +953,7 @@ int agg_coarse_solve(const Group& G, pamg_handle* owner, int solver, int nu1, in
       g_nccl.Recv(Lc.T[Lc.cur], per_parent * h->U, ncclFloat64, 0, h->comm, h->stream);
     }
     if (g_nccl.GroupEnd() != ncclSuccess) return fail(h, PAMG_ERR_CUDA, "ncclGroupEnd failed in coarse scatter");
-    Lc.tnew_alias = true; Lc.strips_valid = false; Lc.cut_valid = false;
+    Lc.tnew_alias = true; Lc.strips_valid = false; Lc.cut_valid = false; Lc.stage_valid = false;
     return PAMG_OK;
   }
   // single process, several GPUs: the parts push their slices into part 0's memory (k_push), part 0 waits for the
@@ -911,13 +978,13 @@ int agg_coarse_solve(const Group& G, pamg_handle* owner, int solver, int nu1, in
     CK(cudaMemsetAsync(A.T[A.cur], 0, A.ndof * sizeof(double), h->stream));
     int rc = launch_wait(h, all);
     if (rc) return gfail(owner, h, rc);
-    A.tnew_alias = true; A.strips_valid = false; A.cut_valid = false; A.rhs_valid = true;
+    A.tnew_alias = true; A.strips_valid = false; A.cut_valid = false; A.stage_valid = false; A.rhs_valid = true;
     const long long l0 = g->launches;
     rc = vcycle_rec(Group{g}, g, 1, solver, nu1, nu2, ncoarse);
     h->launches += g->launches - l0;
     if (rc) { h->err = g->err; return gfail(owner, h, rc); }
     CK(cudaMemcpyAsync(Lc.T[Lc.cur], A.T[A.cur], per_parent * h->U * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    Lc.tnew_alias = true; Lc.strips_valid = false; Lc.cut_valid = false;
+    Lc.tnew_alias = true; Lc.strips_valid = false; Lc.cut_valid = false; Lc.stage_valid = false;
     for (size_t p = 1; p < G.size(); ++p) {
       pamg_handle* q = G[p];
       LevelDev& Lq = q->lev[lvl - 1];
@@ -932,7 +999,7 @@ int agg_coarse_solve(const Group& G, pamg_handle* owner, int solver, int nu1, in
     int rc = launch_wait(q, 1u);
     if (rc) return gfail(owner, q, rc);
     LevelDev& Lq = q->lev[lvl - 1];
-    Lq.tnew_alias = true; Lq.strips_valid = false; Lq.cut_valid = false;
+    Lq.tnew_alias = true; Lq.strips_valid = false; Lq.cut_valid = false; Lq.stage_valid = false;
   }
   return PAMG_OK;
 }
@@ -973,7 +1040,7 @@ int vcycle_rec(const Group& G, pamg_handle* owner, int level, int solver, int nu
     int rc = do_fill(q, Cc.T[Cc.cur], Cc.ndof, 0.0);
     if (rc) return gfail(owner, q, rc);
     Cc.tnew_alias = true;
-    Cc.strips_valid = false; Cc.cut_valid = false;
+    Cc.strips_valid = false; Cc.cut_valid = false; Cc.stage_valid = false;
   }
   int rc;
   if (G[0]->agg_level && level + 1 == G[0]->agg_level) {
@@ -1019,7 +1086,7 @@ void free_levels(pamg_handle* h) {
   h->vc_graphs.clear();
   for (auto& L : h->lev) {
     cudaFree(L.T[0]); cudaFree(L.T[1]); cudaFree(L.spare); cudaFree(L.told); cudaFree(L.rhs); cudaFree(L.res);
-    cudaFree(L.ovl_old); cudaFree(L.pc);
+    cudaFree(L.ovl_old); cudaFree(L.pc); cudaFree(L.xsend);
   }
   h->lev.clear();
   cudaFree(h->strip_arena); h->strip_arena = nullptr; h->strip_arena_bytes = 0;
@@ -1096,6 +1163,8 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
     if (dg) h->debug_gap_ns = atoll(dg);
     const char* lp = getenv("PAMG_L2_PERSIST");
     if (lp && lp[0] == '0') h->l2_persist = false;
+    const char* xk = getenv("PAMG_XCHG");
+    if (xk && !strcmp(xk, "halo")) h->xchg_in_kernel = false;     // cut faces by a k_halo launch (copy, send, receive) between the sweeps
     const char* hl = getenv("PAMG_HALO");
     if (hl && !strcmp(hl, "strips")) h->halo_mode = 0;
     if (hl && !strcmp(hl, "direct")) h->halo_mode = 1;
@@ -1152,6 +1221,15 @@ int group_p2p_setup(pamg_handle* root) {
       if (q->p2p_peers[i].slot_at_peer < 0) return fail(root, PAMG_ERR_STATE, "inconsistent halo plans between parts");
       q->p2p_peers[i].stage = G[q->plan.peers[i].part]->p2p_stage;
     }
+  }
+  bool distinct = true;        // parts that share one GPU keep the exchange in k_halo
+  for (size_t i = 0; i < G.size(); ++i)
+    for (size_t j = i + 1; j < G.size(); ++j) if (G[i]->device == G[j]->device) distinct = false;
+  for (pamg_handle* q : G) {
+    CK_(root, cudaSetDevice(q->device));
+    if (!distinct) q->xchg_in_kernel = false;
+    int rc = p2p_upload_args(q);
+    if (rc) return gfail(root, q, rc);
     q->p2p_ready = true;
   }
   return PAMG_OK;
@@ -1314,7 +1392,7 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
     arena_off += 2 * obp;
     CK(cudaMalloc(&L.ovl_old, ob));
     CK(cudaMemsetAsync(L.ovl_old, 0, ob, h->stream));  // :207
-    L.ovl_cur = 0; L.strips_valid = false; L.cut_valid = false;
+    L.ovl_cur = 0; L.strips_valid = false; L.cut_valid = false; L.stage_valid = false;
     for (int u = 0; u < U; ++u)
       if (!parent_coefficients(h->p, X, neig, bc_glob, first + u, L.s, &pc[(size_t)u * NPC]))
         return fail(h, PAMG_ERR_UNSUPPORTED, "open boundary face (kind 2) with inflow: give it Dirichlet data instead");
@@ -1468,7 +1546,7 @@ int pamg_copy_field(pamg_handle* h, int level, int dst_field, int src_field) {
   if (dst_field == src_field) return PAMG_OK;
   if (dst_field == PAMG_TNEW && src_field == PAMG_TNONLIN) { L.tnew_alias = true; return PAMG_OK; }      // :550
   if (dst_field == PAMG_TNONLIN && src_field == PAMG_TNEW) {                                             // :327
-    if (!L.tnew_alias) { L.cur ^= 1; L.tnew_alias = true; L.strips_valid = false; L.cut_valid = false; }
+    if (!L.tnew_alias) { L.cur ^= 1; L.tnew_alias = true; L.strips_valid = false; L.cut_valid = false; L.stage_valid = false; }
     return PAMG_OK;
   }
   int rc;
@@ -1585,7 +1663,7 @@ int pamg_vcycle_solve(pamg_handle* h, int solver, int nu1, int nu2, int ncoarse,
   if (!valid_level(G[0], 1)) return PAMG_ERR_ARG;
   CK(cudaSetDevice(G[0]->device));
   int rc;
-  for (pamg_handle* q : G) { LevelDev& L = q->lev[0]; L.tnew_alias = true; L.strips_valid = false; L.cut_valid = false; }
+  for (pamg_handle* q : G) { LevelDev& L = q->lev[0]; L.tnew_alias = true; L.strips_valid = false; L.cut_valid = false; L.stage_valid = false; }
   double r0 = 0, r = 0, dummy;
   GALL(G, h, q, do_residual(q, 1, &dummy, nullptr, nullptr, true));
   if ((rc = group_norms(G, h, &r0, nullptr, nullptr))) return rc;
@@ -1711,7 +1789,7 @@ int pamg_timestep_host(pamg_handle* h, const double* tnew_in, double* tnew_out, 
     const size_t bytes = (size_t)L.ndof * sizeof(double);
     CK_(q, cudaMemcpyAsync(L.T[L.cur], tnew_in + off, bytes, cudaMemcpyHostToDevice, q->stream));
     L.tnew_alias = true;
-    L.strips_valid = false; L.cut_valid = false;
+    L.strips_valid = false; L.cut_valid = false; L.stage_valid = false;
     CK_(q, cudaMemcpyAsync(L.told, L.T[L.cur], bytes, cudaMemcpyDeviceToDevice, q->stream));
     L.rhs_valid = false;
     off += (size_t)L.ndof;
@@ -1787,7 +1865,7 @@ int pamg_smooth_host(pamg_handle* h, int solver, int nsweeps, const double* tnew
   if (!h->vc_graphs.empty()) { CK(cudaStreamSynchronize(h->stream)); for (auto& g : h->vc_graphs) for (auto e : g.exec) cudaGraphExecDestroy(e); h->vc_graphs.clear(); }
   std::swap(L.T[L.cur], L.spare);   // the uploaded field becomes the iterate; the previous result stays in `spare` for its download
   L.tnew_alias = true;              // tnew_nonlin = tnew = the uploaded field (transport_tri_semi.F90:317)
-  L.strips_valid = false; L.cut_valid = false;
+  L.strips_valid = false; L.cut_valid = false; L.stage_valid = false;
   int rc = do_smooth(h, 1, solver, nsweeps);
   if (rc) return rc;
   CK(cudaEventRecord(h->ev_comp, h->stream));

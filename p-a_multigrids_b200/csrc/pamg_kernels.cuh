@@ -38,19 +38,27 @@ enum { MODE_JACOBI = 0, MODE_RESID = 1, MODE_GS = 2, MODE_RICH = 3 };
 // only be one exchange ahead of a receiver because it needs the receiver's data to get any further), and the
 // exchange number lives in device memory so that a captured CUDA graph replays correctly.  Polling has a time-out
 // that raises the error word (host-mapped memory, checked at every host synchronisation point) instead of hanging the GPU.
+//
+// Two kinds of kernels take part.  k_halo sends AND receives exchange n in one launch (after something other than a sweep
+// changed the field).  The sweep kernels with a producer warp (XCHG) SEND: as a tile is finished the producer warp stores the
+// new values of its children on cut faces straight into the peers' staging buffers as exchange n+1 (the NVLink trip hides
+// under the rest of the sweep) and the last CTA advances the exchange number; a small unpack launch (k_halo, what = 4) before
+// the next sweep moves the values - long arrived - from the staging buffer into the strips.  A sender can then be up to three
+// exchanges ahead of what a receiver still reads, so the staging buffer has FOUR slots indexed by the exchange number mod 4.
+constexpr int P2P_SLOTS = 4;
 constexpr int P2P_MAXP = 16;
 enum { P2P_EPOCH = 0, P2P_COUNT = 1, P2P_WORDS = 8 };
 struct P2PArgs {
   const double* send;                 // my send slots of this level (contiguous, grouped per peer)
   int send_base;                      // first send slot (in strips) of peer 0, relative to the send-slot space
   double* strips;                     // my strip buffer of this level (receive side)
-  uint4* remote[P2P_MAXP];            // each peer's staging buffer (parity 0), already offset to my range there
-  long long rstride[P2P_MAXP];        // words per parity of each peer's staging buffer
+  uint4* remote[P2P_MAXP];            // each peer's staging buffer (slot 0), already offset to my range there
+  long long rstride[P2P_MAXP];        // words per slot of each peer's staging buffer
   long long soff[P2P_MAXP + 1];       // prefix offsets (doubles) of the per-peer send ranges
   long long rbeg[P2P_MAXP];           // first double of the strips I receive from each peer
   long long roff[P2P_MAXP + 1];       // prefix offsets (doubles) of the per-peer receive ranges
-  uint4* stage;                       // my staging buffer (parity 0)
-  long long stage_words;              // words per parity
+  uint4* stage;                       // my staging buffer (slot 0)
+  long long stage_words;              // words per slot
   unsigned long long* sync;           // exchange number, block counter
   unsigned long long* err;            // error word (mapped host memory): a poll that timed out raises it instead of hanging
   int npeers;
@@ -66,30 +74,10 @@ __device__ __forceinline__ unsigned long long p2p_now() {
 // one double into the staging buffer of peer p (idx = offset in doubles inside my range there)
 __device__ __forceinline__ void p2p_put(const P2PArgs& a, unsigned e, int p, long long idx, double val) {
   const unsigned long long v = (unsigned long long)__double_as_longlong(val);
-  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(a.remote[p] + (long long)(e & 1u) * a.rstride[p] + idx), "r"((unsigned)v), "r"(e),
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(a.remote[p] + (long long)(e & (P2P_SLOTS - 1)) * a.rstride[p] + idx), "r"((unsigned)v), "r"(e),
                "r"((unsigned)(v >> 32)), "r"(e) : "memory");
 }
 
-
-// one value out of MY staging buffer for the exchange number e (polls until the flagged word has arrived)
-__device__ __forceinline__ double p2p_take(const P2PArgs& a, unsigned long long e64, long long j) {
-  const uint4* src = a.stage + (long long)(e64 & 1) * a.stage_words + j;
-  const unsigned e = (unsigned)e64;
-  volatile unsigned long long* err = a.err;
-  uint4 w;
-  unsigned long long t0 = 0;
-  for (unsigned spins = 0;; ++spins) {
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(src) : "memory");
-    if (w.y == e && w.w == e) break;
-    if ((spins & 1023u) == 1023u) {
-      if (*err) break;
-      const unsigned long long t = p2p_now();
-      if (t0 == 0) t0 = t;
-      else if (t - t0 > a.timeout_ns) { *err = 1; break; }
-    }
-  }
-  return __longlong_as_double((long long)(((unsigned long long)w.z << 32) | w.x));
-}
 
 struct ElemArgs {
   const double* Tin;      // field the sweep reads (may alias Tout for the in-place coloured pass)
@@ -104,10 +92,9 @@ struct ElemArgs {
   const int32_t* dst_strip; // [U*3] strip my boundary children of (u, side) are copied to; -1 = domain boundary
   const int32_t* rev;       // [U*3] slot reversal flag
   int nstrips;              // dst_strip >= nstrips: send slot of a face cut by the GPU partition
-  const P2PArgs* xchg;      // != nullptr: the sweep does the exchange of the cut faces itself - the producer warp stores their new
-                            // values straight into the peers' flagged staging buffers, consumers poll their own staging buffer
-                            // for the strips [0, ncut) instead of reading unpacked copies
-  int ncut;                 // cut strips are the first ncut strips of the strip space
+  const ulonglong2* xsend;  // (XCHG kernels) [U*3] for a side cut by the GPU partition: .x = start of its range in the peer's staging buffer (slot 0),
+                            // .y = words per slot there; .x = 0 otherwise (host table: no dependent look-ups in the producer warp)
+  unsigned long long* xsync;  // the level's exchange number / block counter (P2PArgs::sync)
   double* partial;        // residual: [nblocks][3] = sum r^2, max |r|, max r
   double omega;
   double rsign;
@@ -231,21 +218,19 @@ __device__ __forceinline__ void ext_pair(const ElemArgs& a, int d, int strip, in
   va = __ldg(e + (hm & 3)); vb = __ldg(e + (hm >> 2));
 }
 
-// the same for a kernel that takes part in the exchange: strips of cut faces come out of the flagged staging buffer
-__device__ __forceinline__ void ext_pair_x(const ElemArgs& a, unsigned long long e64, int d, int strip, int hm, int p, int S,
-                                           double& va, double& vb) {
-  if (a.xchg != nullptr && d < 0 && strip < a.ncut) {
-    const long long j = ((long long)strip * S + p) * 3;
-    va = p2p_take(*a.xchg, e64, j + (hm & 3)); vb = p2p_take(*a.xchg, e64, j + (hm >> 2));
-    return;
-  }
-  ext_pair(a, d, strip, hm, p, S, va, vb);
-}
-
 // same with the per-parent tables still in global memory: mf = gmsh side (0..2), slot0 = 0-based strip position
 __device__ __forceinline__ void halo_pair(const ElemArgs& a, int u, int mf, int slot0, int S, double& va, double& vb) {
   const int d = a.nsrc ? __ldg(a.nsrc + u * 3 + mf) : -1;
   ext_pair(a, d, __ldg(a.strip_of + u * 3 + mf), __ldg(a.hmap + u * 3 + mf), slot0, S, va, vb);
+}
+
+// a sweep that sent exchange e64 + 1 from its producer warps: the last CTA to finish advances the level's exchange number
+__device__ __forceinline__ void p2p_advance(unsigned long long* sync, unsigned long long e64) {
+  // (no fence: whoever reads the number next is a later kernel on this stream)
+  if (atomicAdd(sync + P2P_COUNT, 1ull) == (unsigned long long)gridDim.x - 1) {
+    sync[P2P_COUNT] = 0;
+    *(volatile unsigned long long*)(sync + P2P_EPOCH) = e64 + 1;
+  }
 }
 
 // deterministic two-stage norm reduction: warp shuffle, then one partial per CTA
@@ -776,29 +761,54 @@ __global__ void __launch_bounds__(TPB, 3) k_element_win(ElemArgs a) {
 // work.  `tile`: 256 results in shared memory, first child k0 (0-based inside parent u); m0: row of k0 (kept across
 // tiles of a parent).  Children on parent side 1 are the odd-ipos children of row 1, on side 3 the first and on side 2 the
 // last child of every row (surf_ele, splitting.F90:434-449); the slot is the position or its mirror image (:1256-1391).
-struct StripDst { int d0, d1, d2, rv; };     // destination strips of the parent's three sides (-1: none) and reversal bits
-__device__ __forceinline__ StripDst strip_dst_load(const ElemArgs& a, int u, int lane) {
+struct StripDst { int d0, d1, d2, rv; uint4 *r0, *r1, *r2; };   // destination strips of the parent's three sides (-1: none), reversal
+                                                                // bits, and for a side cut by the GPU partition the start of its
+                                                                // range in the peer's staging buffer (slot of exchange xe)
+__device__ __forceinline__ StripDst strip_dst_load(const ElemArgs& a, int u, int lane, unsigned long long xe = 0) {
   int d = 0, rv = 0;
-  if (lane < 3) { d = __ldg(a.dst_strip + u * 3 + lane); rv = __ldg(a.rev + u * 3 + lane) << lane; }
+  unsigned long long r = 0;
+  if (lane < 3) {
+    d = __ldg(a.dst_strip + u * 3 + lane); rv = __ldg(a.rev + u * 3 + lane) << lane;
+    if (xe != 0) {
+      const ulonglong2 t = __ldg(a.xsend + u * 3 + lane);
+      if (t.x) r = t.x + (xe & (P2P_SLOTS - 1)) * t.y * sizeof(uint4);
+    }
+  }
   StripDst o;
   o.d0 = __shfl_sync(0xffffffffu, d, 0); o.d1 = __shfl_sync(0xffffffffu, d, 1); o.d2 = __shfl_sync(0xffffffffu, d, 2);
   o.rv = __shfl_sync(0xffffffffu, rv, 0) | __shfl_sync(0xffffffffu, rv, 1) | __shfl_sync(0xffffffffu, rv, 2);
+  o.r0 = (uint4*)__shfl_sync(0xffffffffu, r, 0); o.r1 = (uint4*)__shfl_sync(0xffffffffu, r, 1); o.r2 = (uint4*)__shfl_sync(0xffffffffu, r, 2);
   return o;
 }
 
+// values for a side cut by the GPU partition (remote base set) go straight into the peer's staging buffer, flagged with the
+// exchange number xe
 __device__ __forceinline__ void strips_from_tile(const ElemArgs& a, const double* __restrict__ tile, const StripDst& sd, int k0,
-                                                 int s, int& m0, int lane) {
+                                                 int s, int& m0, int lane, unsigned long long xe = 0) {
   const int S = 1 << s, b = 2 << s;
   const int kend = k0 + TPB;
-  auto put = [&](int dst, int rvf, int pos, int k) {
+  auto put = [&](int dst, uint4* rbase, int rvf, int pos, int k) {
     const int slot = rvf ? (S - 1 - pos) : pos;
     const double* t = tile + (k - k0) * 3;
+    if (rbase != nullptr) {
+      const unsigned e = (unsigned)xe;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const unsigned long long v = (unsigned long long)__double_as_longlong(t[i]);
+#ifdef PAMG_SEND_WEAK
+        asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(rbase + slot * 3 + i), "r"((unsigned)v), "r"(e), "r"((unsigned)(v >> 32)), "r"(e) : "memory");
+#else
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(rbase + slot * 3 + i), "r"((unsigned)v), "r"(e), "r"((unsigned)(v >> 32)), "r"(e) : "memory");
+#endif
+      }
+      return;
+    }
     double* e = a.ovl_next + ((size_t)dst * S + slot) * 3;
     e[0] = t[0]; e[1] = t[1]; e[2] = t[2];
   };
   if (sd.d0 >= 0 && k0 < b - 1) {                    // row 1: children k = 0, 2, 4, .. b-2 at positions k/2
     const int e1 = min(kend, b - 1);
-    for (int k = k0 + 2 * lane; k < e1; k += 64) put(sd.d0, sd.rv & 1, k >> 1, k);
+    for (int k = k0 + 2 * lane; k < e1; k += 64) put(sd.d0, sd.r0, sd.rv & 1, k >> 1, k);
   }
   while ((m0 + 1) * (b - m0 - 1) <= k0) ++m0;        // row (0-based) that holds child k0
   if (sd.d1 >= 0 || sd.d2 >= 0) {
@@ -806,8 +816,8 @@ __device__ __forceinline__ void strips_from_tile(const ElemArgs& a, const double
       const int first = m * (b - m);
       if (first >= kend) break;
       const int last = (m + 1) * (b - m - 1) - 1;
-      if (sd.d2 >= 0 && first >= k0) put(sd.d2, sd.rv & 4, m, first);
-      if (sd.d1 >= 0 && last < kend) put(sd.d1, sd.rv & 2, m, last);
+      if (sd.d2 >= 0 && first >= k0) put(sd.d2, sd.r2, sd.rv & 4, m, first);
+      if (sd.d1 >= 0 && last < kend) put(sd.d1, sd.r1, sd.rv & 2, m, last);
     }
   }
 }
@@ -824,7 +834,8 @@ constexpr int WIN2_THREADS = TPB + 32;
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-template <int MODE, bool FACE>
+// XCHG: the producer warp sends the new values of the children on cut faces to the peer GPUs (see P2PArgs)
+template <int MODE, bool FACE, bool XCHG = false>
 __global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
   extern __shared__ __align__(128) unsigned char dsm[];   // WIN_SMEM_BYTES
   double* sT = reinterpret_cast<double*>(dsm);
@@ -853,6 +864,9 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
     // ------------------------------------------------------------------ producer warp
     const int lane = tid - TPB;
     int u_loaded = -1;
+    // exchange number of the cut-face values this sweep READS (the sweep or k_halo before it sent them); it sends e64 + 1
+    unsigned long long e64 = 0;
+    if (XCHG) e64 = *(volatile unsigned long long*)(a.xsync + P2P_EPOCH);
     auto issueT = [&](long long tile) {   // lane 0
       const int sl = (int)(tile & (WIN_NT - 1));
       mbar_expect_tx(&barT[sl], TILE_BYTES);
@@ -880,7 +894,7 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
       for (long long t = tbeg; t < min(tend, tbeg + 3); ++t) issueB(t);
     }
     int m0 = 0, u_m0 = -1;
-    StripDst sd = {-1, -1, -1, 0};
+    StripDst sd = {-1, -1, -1, 0, nullptr, nullptr, nullptr};
     for (long long p = tbeg; p < tend; ++p) {
       const int it = (int)(p - tbeg);
       named_sync(1 + (it & 3), WIN2_THREADS);            // every consumer warp has written tile p
@@ -894,10 +908,11 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
       if (p + 3 < tend) issueB(p + 3);
       if (MODE != MODE_RESID && a.ovl_next) {            // halo strips of the next sweep from the finished tile
         const int u = (int)((p * TPB) >> twos);
-        if (u != u_m0) { m0 = 0; u_m0 = u; sd = strip_dst_load(a, u, lane); }      // once per parent
-        strips_from_tile(a, sB + (it & (WIN_NB - 1)) * 3 * TPB, sd, (int)((p * TPB) & Cmask), s, m0, lane);
+        if (u != u_m0) { m0 = 0; u_m0 = u; sd = strip_dst_load(a, u, lane, XCHG ? e64 + 1 : 0); }      // once per parent
+        strips_from_tile(a, sB + (it & (WIN_NB - 1)) * 3 * TPB, sd, (int)((p * TPB) & Cmask), s, m0, lane, XCHG ? e64 + 1 : 0);
       }
     }
+    if (XCHG && MODE != MODE_RESID && lane == 0) p2p_advance(a.xsync, e64);
     if (lane == 0) tma_store_wait_all();
   } else {
     // ------------------------------------------------------------------ consumer warps
@@ -1198,15 +1213,15 @@ __global__ void __launch_bounds__(TPB, 3) k_gs_win(ElemArgs a) {
 
 // ------------------------------------------------------------------------------------------------
 // One-pass coloured Gauss-Seidel with a producer warp (see k_gs_win for the algorithm, k_element_win2 for the roles).
-// The consumer warps of one CTA do depend on each other here - the up children of tile t read the down value that
-// the down phase of the previous iteration wrote at the first child of tile t+1, and the down phase reads an up value
-// that the next iteration's up phase overwrites - but only across one phase: a consumer arrives on an mbarrier when
-// its DOWN phase of an iteration is done, and waits before its UP phase for the down phases of the PREVIOUS iteration.
-// That leaves a whole phase of slack instead of a CTA-wide barrier per tile.
+// The two colours depend on each other - the up children of tile t read the down value at the first child of tile t+1, and
+// the down phase of tile t+1 reads up values of tile t that the up phase overwrites - so four consumer warps relax the down
+// children of tile t+1 and arrive on an mbarrier; the other four wait on it before they relax the up children of tile t.
+// The down warps never wait for the up warps (only for data), so they run ahead by up to the depth of the ring.
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
   asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+template <bool XCHG>
 __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
   extern __shared__ __align__(128) unsigned char dsm[];
   double* sT = reinterpret_cast<double*>(dsm);
@@ -1229,15 +1244,20 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
   const long long ntiles = a.nelem / TPB;
   const long long per = (ntiles + gridDim.x - 1) / gridDim.x;
   const long long tbeg = (long long)blockIdx.x * per, tend = min(ntiles, tbeg + per);
-  if (tbeg >= tend) return;
+  if (tbeg >= tend) {
+    if (XCHG && tid == TPB) p2p_advance(a.xsync, *(volatile unsigned long long*)(a.xsync + P2P_EPOCH));
+    return;
+  }
   const long long dlo = max(0ll, tbeg - 2), dhi = min(ntiles - 1, tend);       // tiles whose down children I relax
   const long long tlo = max(0ll, dlo - 1), thi = min(ntiles, dhi + 3);         // field tiles I load: [tlo, thi)
-  const long long t0 = dlo - 2;                                                // first iteration
+  const long long t0 = dlo - 1;                                                // first iteration (down phase one tile ahead)
 
   if (tid >= TPB) {
     // ------------------------------------------------------------------ producer warp
     const int lane = tid - TPB;
     int u_loaded = -1;
+    unsigned long long e64 = 0;                          // exchange number this sweep reads (see k_element_win2)
+    if (XCHG) e64 = *(volatile unsigned long long*)(a.xsync + P2P_EPOCH);
     auto issueT = [&](long long tile) {
       const int sl = (int)(tile & (WIN_NT - 1));
       mbar_expect_tx(&barT[sl], TILE_BYTES);
@@ -1263,7 +1283,7 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
     if (lane == 0) for (long long t = tlo; t < min(thi, t0 + 6); ++t) issueT(t);
     for (long long t = dlo; t <= min(dhi, dlo + 3); ++t) issueB(t);
     int m0 = 0, u_m0 = -1;
-    StripDst sd = {-1, -1, -1, 0};
+    StripDst sd = {-1, -1, -1, 0, nullptr, nullptr, nullptr};
     for (long long tile = t0; tile < tend; ++tile) {
       const int it = (int)(tile - t0);
       named_sync(1 + (it & 3), WIN2_THREADS);            // every consumer warp has finished iteration `tile`
@@ -1279,10 +1299,11 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
       if (tile + 4 >= dlo + 4 && tile + 4 <= dhi) issueB(tile + 4);   // rhs slot of tile: consumed by its up children
       if (a.ovl_next && tile >= tbeg) {                  // halo strips of the next sweep from the finished tile
         const int u = (int)((tile * TPB) >> twos);
-        if (u != u_m0) { m0 = 0; u_m0 = u; sd = strip_dst_load(a, u, lane); }      // once per parent
-        strips_from_tile(a, sT + (tile & (WIN_NT - 1)) * 3 * TPB, sd, (int)((tile * TPB) & Cmask), s, m0, lane);
+        if (u != u_m0) { m0 = 0; u_m0 = u; sd = strip_dst_load(a, u, lane, XCHG ? e64 + 1 : 0); }      // once per parent
+        strips_from_tile(a, sT + (tile & (WIN_NT - 1)) * 3 * TPB, sd, (int)((tile * TPB) & Cmask), s, m0, lane, XCHG ? e64 + 1 : 0);
       }
     }
+    if (XCHG && lane == 0) p2p_advance(a.xsync, e64);
     if (lane == 0) tma_store_wait_all();
   } else {
     // ------------------------------------------------------------------ consumer warps, split by colour
@@ -1300,14 +1321,14 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
     const int j2 = (tid & (TPB / 2 - 1)) * 2;             // first child of my pair inside a tile
     int r = 2, ipos = 2;                                  // numbering of child 2j of the tile this thread handled last
     if (tid < TPB / 2) {
-      // ---- down warps: tile t+2 (reads the old up values of tiles t+1 .. t+4)
+      // ---- down warps: tile t+1 (reads the old up values of tiles t .. t+3; the up warps touch tile t only after this phase)
       for (int tile = t0i; tile < tendi; ++tile) {
         const int it = tile - t0i;
-        const int td = tile + 2;
+        const int td = tile + 1;
         if (tile == t0i) {
-          for (int tw = tloi; tw < min(thii, tile + 5); ++tw) waitT(tw);
-        } else if (tile + 4 < thii) {
-          waitT(tile + 4);
+          for (int tw = tloi; tw < min(thii, tile + 4); ++tw) waitT(tw);
+        } else if (tile + 3 < thii) {
+          waitT(tile + 3);
         }
         if (td >= dloi && td <= dhii) {
           waitB(td);                                       // also acquires the coefficients of the parent of td
@@ -1356,7 +1377,7 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
         const bool f1 = p.r == 1, side = p.ipos == 1 || p.ipos == p.len;
         if (f1 | side) {
           const int* ix = sIdx2[(tile >> pshift) & 1];
-          if (f1) ext_pair(a, ix[8], ix[0], ix[4], p.ipos >> 1, S, p.h1a, p.h1b);
+          if (f1) { ext_pair(a, ix[8], ix[0], ix[4], p.ipos >> 1, S, p.h1a, p.h1b); }
           if (side) {
             const int mf = (p.ipos == 1) ? 2 : 1;
             ext_pair(a, ix[8 + mf], ix[mf], ix[4 + mf], p.r - 1, S, p.h2a, p.h2b);
@@ -1404,8 +1425,9 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
         }
         prepare(tile + 1, nxt);
         if (tile >= tbegi) {
-          // every down warp has finished the PREVIOUS iteration (down children of tile+1; those of tile-2 .. tile are older)
-          if (it > 0) mbar_wait(&doneD[(it - 1) & 3], (uint32_t)(((it - 1) >> 2) & 1));
+          // every down warp has finished THIS iteration: the down children of tile+1 are new (those of tile-2 .. tile are
+          // older) and nobody reads the old up values of this tile any more
+          mbar_wait(&doneD[it & 3], (uint32_t)((it >> 2) & 1));
           const int cw = ((tile & (WIN_NT - 1)) << 8) + j2 + cur.off;
           relax_up(tile, cw, cur.r, cur.ipos, cur.len, cur.h1a, cur.h1b, cur.h2a, cur.h2b);
           if (cur.off == 0 && cur.ipos == cur.len) {
@@ -1521,11 +1543,11 @@ __global__ void __launch_bounds__(1024) k_reduce_partials(const double* partial,
 // update_overlaps (splitting.F90:1210-1397): one thread per (parent, side, position)
 // ------------------------------------------------------------------------------------------------
 // poll my staging buffer, unpack into the strips, and let the last block advance the exchange number
-__device__ __forceinline__ void p2p_receive(const P2PArgs& a, unsigned long long e64) {
+__device__ __forceinline__ void p2p_receive(const P2PArgs& a, unsigned long long e64, bool advance) {
   __shared__ int s_last;
   const int tid = threadIdx.x;
   const unsigned e = (unsigned)e64;
-  const long long par = (long long)(e64 & 1) * a.stage_words;
+  const long long par = (long long)(e64 & (P2P_SLOTS - 1)) * a.stage_words;
   const long long nr = a.roff[a.npeers];
   volatile unsigned long long* err = a.err;
   for (long long i = (long long)blockIdx.x * TPB + tid; i < nr; i += (long long)gridDim.x * TPB) {
@@ -1548,6 +1570,7 @@ __device__ __forceinline__ void p2p_receive(const P2PArgs& a, unsigned long long
     }
     if (ok) a.strips[j] = __longlong_as_double((long long)(((unsigned long long)w.z << 32) | w.x));
   }
+  if (!advance) return;
   __syncthreads();
   if (tid == 0) { __threadfence(); s_last = (atomicAdd(a.sync + P2P_COUNT, 1ull) == (unsigned long long)gridDim.x - 1); }
   __syncthreads();
@@ -1619,7 +1642,8 @@ struct HaloArgs {
   double bc_scale;
   int U, s, with_old;
   int what;   // 0 everything (update_overlaps as written); 1 Dirichlet faces only; 2 faces cut by the GPU partition only
-              // (one thread per position of the faces listed in cut_lf); 3 all faces between parents (no Dirichlet data)
+              // (one thread per position of the faces listed in cut_lf); 3 all faces between parents (no Dirichlet data);
+              // 4 unpack the cut-face values a sweep's producer warps sent into my staging buffer
   int nstrips;
   const int32_t* cut_lf; int ncut;         // what == 2: (u*3+mf) of the cut faces
   // Dirichlet data of domain-boundary faces per (u, side): kind 0 = sin(x+y) (splitting.F90:1246-1252), 1 = the constant
@@ -1649,6 +1673,10 @@ __global__ void __launch_bounds__(TPB) k_halo(HaloArgs a) {
   const long long n = (a.what == 2 ? (long long)a.ncut : (long long)a.U * 3) * S;
   unsigned long long e64 = 0;
   if (a.x.npeers > 0) e64 = *(volatile unsigned long long*)(a.x.sync + P2P_EPOCH) + 1;
+  if (a.what == 4) {                       // the values of the current exchange sit in my staging buffer (a sweep's producer
+    p2p_receive(a.x, e64 - 1, false);      // warps sent them): unpack them into the strips, nothing to send
+    return;
+  }
   for (long long tid = (long long)blockIdx.x * TPB + threadIdx.x; tid < n; tid += (long long)gridDim.x * TPB) {
     const int i = (int)(tid & (S - 1));           // position - 1
     const int lf = (a.what == 2) ? __ldg(a.cut_lf + (tid >> a.s)) : (int)(tid >> a.s);   // u*3 + mf
@@ -1695,7 +1723,7 @@ __global__ void __launch_bounds__(TPB) k_halo(HaloArgs a) {
       }
     }
   }
-  if (a.x.npeers > 0) p2p_receive(a.x, e64);
+  if (a.x.npeers > 0) p2p_receive(a.x, e64, true);
 }
 
 // ------------------------------------------------------------------------------------------------
