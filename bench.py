@@ -53,6 +53,33 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def bind_to_gpu_numa(gpu):
+    """Pin this rank to the CPUs of the NUMA node its GPU hangs off BEFORE any pinned host buffer is allocated: the pages are
+    then local to that node and the PCIe copies of the end-to-end arm do not cross the socket interconnect (with N ranks on
+    one box the unpinned default made every rank's copies share one memory path).  Returns what was done, for the JSON line."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(gpu), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bus = bus[-12:]                                   # sysfs: 0000:xx:yy.z (nvidia-smi prints an 8-digit domain)
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "single NUMA node (sysfs reports -1)"}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if not use:
+            return {"numa_node": node, "note": "no CPU of that node is in this process's affinity mask"}
+        os.sched_setaffinity(0, use)
+        return {"numa_node": node, "cpus_bound": len(use)}
+    except Exception as e:     # noqa: BLE001 - best effort, the run goes on unbound
+        return {"numa_node": None, "note": f"not bound: {type(e).__name__}"}
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -284,6 +311,8 @@ def main():
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1 (or pass --single-process)")
     args.warmup = max(args.warmup, 3)
+    affinity0 = os.sched_getaffinity(0)
+    binding = bind_to_gpu_numa(local) if os.environ.get("PAMG_BENCH_BIND", "1") != "0" else {"numa_node": None, "note": "PAMG_BENCH_BIND=0"}
     nsplit = NSPLIT_OF[args.workload]
     pkg = importlib.import_module("p-a_multigrids_b200")
     if pkg.device_count() < 1:
@@ -522,6 +551,7 @@ def main():
         vc = gs
 
     # ---- numerical check of the run (cut-face strips + one sweep against the oracle) ----------------------------
+    os.sched_setaffinity(0, affinity0)          # the CPU arms (oracle threads are created from here on) may use every core again
     orc = oracle_api()
     pc = parity_check(pkg, orc, g, mesh, first, U_local, nsplit, gather, part_first, world)
 
@@ -537,7 +567,7 @@ def main():
             "parity_check": pc,
             "config": workload_config(ngpu, nsplit, args.scaling, single),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * ndof_job, "d2h_bytes_per_step": 8 * ndof_job,
-                    "steps": e2e_steps, "ms_per_step": e2e_ms,
+                    "steps": e2e_steps, "ms_per_step": e2e_ms, "host_binding": binding,
                     "what": "pamg_smooth_host: pinned host field up, 4 Jacobi sweeps, result down, every step (independent calls, pipelined)",
                     "dependent_loop": {"ms_per_step": dep_ms, "value": ndof_job * NSMOOTH / (dep_ms * 1e-3),
                                        "what": "pamg_smoother_host, blocking, output of a call = input of the next"}},
@@ -560,7 +590,7 @@ def main():
         except Exception:
             pass
         if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+            cores = len(affinity0) or 1
             v1, nd1, t1 = cpu_smoother_rate(orc, nsplit, 4, 1, 2)       # all 256 parents, 1 thread (serial like the reference)
             vall, nd2, t2 = cpu_smoother_rate(orc, nsplit, 4, cores, 2)  # all 256 parents, all cores
             line["cpu_baseline"] = {

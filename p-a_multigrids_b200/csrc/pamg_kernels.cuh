@@ -795,11 +795,8 @@ __device__ __forceinline__ void strips_from_tile(const ElemArgs& a, const double
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         const unsigned long long v = (unsigned long long)__double_as_longlong(t[i]);
-#ifdef PAMG_SEND_WEAK
-        asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(rbase + slot * 3 + i), "r"((unsigned)v), "r"(e), "r"((unsigned)(v >> 32)), "r"(e) : "memory");
-#else
+        // (volatile: a weak store may sit in the SM until the kernel ends - measured: the peer's unpack launch times out)
         asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(rbase + slot * 3 + i), "r"((unsigned)v), "r"(e), "r"((unsigned)(v >> 32)), "r"(e) : "memory");
-#endif
       }
       return;
     }
