@@ -1308,8 +1308,9 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
     // (ncu: issue-bound at half the lanes).  Here a thread owns a PAIR of adjacent children (2j, 2j+1) of a tile: warps 0-3
     // relax the down child of their pair in tile t+2, warps 4-7 the up child of theirs in tile t - every lane busy, and a warp
     // runs one colour per iteration instead of two.  The one pair per row that straddles a row end holds two up children
-    // (last child of row r, first child of row r+1: both on parent faces) and no down child; the up warps relax its second
-    // child in an extra pass.  (all per-tile index arithmetic in 32-bit: this branch cannot use the uniform datapath)
+    // (last child of row r, first child of row r+1: both on parent faces) and no down child; the down-warp lane that had
+    // nothing to do for it relaxes its second child.  (all per-tile index arithmetic in 32-bit: this branch cannot use the
+    // uniform datapath)
     const int t0i = (int)t0, tbegi = (int)tbeg, tendi = (int)tend, dloi = (int)dlo, dhii = (int)dhi, tloi = (int)tlo, thii = (int)thi;
     const int pshift = twos - 8;                          // tiles per parent = 2^pshift (TPB = 2^8)
     const unsigned kmask = (unsigned)Cmask;
@@ -1317,11 +1318,49 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
     auto waitB = [&](int tile) { mbar_wait(&barB[(tile - dloi) & (WIN_NB - 1)], (uint32_t)(((tile - dloi) >> 2) & 1)); };
     const int j2 = (tid & (TPB / 2 - 1)) * 2;             // first child of my pair inside a tile
     int r = 2, ipos = 2;                                  // numbering of child 2j of the tile this thread handled last
+    // one up child: row rr, position ip of a row of length ln, at ring index cw; h1 = values across parent face 1,
+    // h2 = across the side face the child lies on (side 3 for ip == 1, else side 2)
+    auto relax_up = [&](int tile, int cw, int rr, int ip, int ln, double h1a, double h1b, double h2a, double h2b) {
+      const int u_tile = tile >> pshift;
+      double* t = sT + cw * 3;
+      const double T1 = t[0], T2 = t[1], T3 = t[2];
+      FaceIn fi;
+      int bmask = 0;
+      const double* tv = sT + ((cw + 2 * rr - b - 2) & (WIN_CH - 1)) * 3;
+      fi.n1a = tv[2]; fi.n1b = tv[0];
+      const double* tl = sT + ((cw - 1) & (WIN_CH - 1)) * 3;
+      const double* tr = sT + ((cw + 1) & (WIN_CH - 1)) * 3;
+      fi.n2a = tl[1]; fi.n2b = tl[2];
+      fi.n3a = tr[0]; fi.n3b = tr[1];
+      if (rr == 1 || ip == 1 || ip == ln) {
+        if (rr == 1) { fi.n1a = h1a; fi.n1b = h1b; bmask |= 1; }
+        if (ip == 1) { fi.n2a = h2a; fi.n2b = h2b; bmask |= 2; }
+        if (ip == ln) {
+          if (ln == 1) halo_pair(a, u_tile, 1, rr - 1, S, fi.n3a, fi.n3b);
+          else { fi.n3a = h2a; fi.n3b = h2b; }
+          bmask |= 4;
+        }
+      }
+      const double* bb = sB + ((tile - dloi) & (WIN_NB - 1)) * (3 * TPB) + (cw & (TPB - 1)) * 3;
+      const double* pu = sPC2[u_tile & 1];
+      const Folded& F = *reinterpret_cast<const Folded*>(pu + PC_FOLD);
+      double o1, o2, o3;
+      elem_apply_folded<MODE_GS>(F, pu + PC_DPEN, bmask, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
+      t[0] = o1; t[1] = o2; t[2] = o3;
+    };
     if (tid < TPB / 2) {
-      // ---- down warps: tile t+1 (reads the old up values of tiles t .. t+3; the up warps touch tile t only after this phase)
+      // ---- down warps: tile t+1 (reads the old up values of tiles t .. t+3; the up warps touch tile t only after this phase).
+      // A pair whose first child ends its row has no down child: its second child opens the next row - an up child on parent
+      // side 3.  The lane that found it idle in the down phase relaxes it one iteration later, when the pair's tile is the up
+      // tile (exterior values fetched in between), so that no up warp makes a second trip through the up code.
+      bool sec = false;                                    // my pair of tile `tile` holds such a second up child, in row sec_r + 1
+      int sec_r = 0;
+      double sec_a = 0.0, sec_b = 0.0;
       for (int tile = t0i; tile < tendi; ++tile) {
         const int it = tile - t0i;
         const int td = tile + 1;
+        bool nsec = false;
+        double nsec_a = 0.0, nsec_b = 0.0;
         if (tile == t0i) {
           for (int tw = tloi; tw < min(thii, tile + 4); ++tw) waitT(tw);
         } else if (tile + 3 < thii) {
@@ -1351,11 +1390,21 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
             double o1, o2, o3;
             elem_apply_folded<MODE_GS>(F, pd, 0, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
             t[0] = o1; t[1] = o2; t[2] = o3;
+          } else if (td >= tbegi && td < tendi) {
+            const int* ix = sIdx2[(td >> pshift) & 1];
+            ext_pair(a, ix[10], ix[2], ix[6], r, S, nsec_a, nsec_b);   // side 3 at the position of row r+1
+            nsec = true;
           }
         }
         // down phase of this iteration done (also when there was nothing to do): tell the up warps
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive_cta(&doneD[it & 3]);
+        if (sec) {
+          // (its right neighbour may be the first down child of tile+1: every down warp must be through this iteration)
+          mbar_wait(&doneD[it & 3], (uint32_t)((it >> 2) & 1));
+          relax_up(tile, ((tile & (WIN_NT - 1)) << 8) + j2 + 1, sec_r + 1, 1, b - 1 - 2 * sec_r, 0.0, 0.0, sec_a, sec_b);
+        }
+        sec = nsec; sec_r = r; sec_a = nsec_a; sec_b = nsec_b;
         fence_async_smem();
         named_arrive(1 + (it & 3), WIN2_THREADS);
       }
@@ -1381,36 +1430,6 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
           }
         }
       };
-      // one up child: row rr, position ip of a row of length ln, at ring index cw; h1 = values across parent face 1,
-      // h2 = across the side face the child lies on (side 3 for ip == 1, else side 2)
-      auto relax_up = [&](int tile, int cw, int rr, int ip, int ln, double h1a, double h1b, double h2a, double h2b) {
-        const int u_tile = tile >> pshift;
-        double* t = sT + cw * 3;
-        const double T1 = t[0], T2 = t[1], T3 = t[2];
-        FaceIn fi;
-        int bmask = 0;
-        const double* tv = sT + ((cw + 2 * rr - b - 2) & (WIN_CH - 1)) * 3;
-        fi.n1a = tv[2]; fi.n1b = tv[0];
-        const double* tl = sT + ((cw - 1) & (WIN_CH - 1)) * 3;
-        const double* tr = sT + ((cw + 1) & (WIN_CH - 1)) * 3;
-        fi.n2a = tl[1]; fi.n2b = tl[2];
-        fi.n3a = tr[0]; fi.n3b = tr[1];
-        if (rr == 1 || ip == 1 || ip == ln) {
-          if (rr == 1) { fi.n1a = h1a; fi.n1b = h1b; bmask |= 1; }
-          if (ip == 1) { fi.n2a = h2a; fi.n2b = h2b; bmask |= 2; }
-          if (ip == ln) {
-            if (ln == 1) halo_pair(a, u_tile, 1, rr - 1, S, fi.n3a, fi.n3b);
-            else { fi.n3a = h2a; fi.n3b = h2b; }
-            bmask |= 4;
-          }
-        }
-        const double* bb = sB + ((tile - dloi) & (WIN_NB - 1)) * (3 * TPB) + (cw & (TPB - 1)) * 3;
-        const double* pu = sPC2[u_tile & 1];
-        const Folded& F = *reinterpret_cast<const Folded*>(pu + PC_FOLD);
-        double o1, o2, o3;
-        elem_apply_folded<MODE_GS>(F, pu + PC_DPEN, bmask, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
-        t[0] = o1; t[1] = o2; t[2] = o3;
-      };
       Prep cur, nxt;
       prepare(t0i, cur);                                   // t0 < tbeg: defaults
       for (int tile = t0i; tile < tendi; ++tile) {
@@ -1426,13 +1445,7 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_gs_win2(ElemArgs a) {
           // older) and nobody reads the old up values of this tile any more
           mbar_wait(&doneD[it & 3], (uint32_t)((it >> 2) & 1));
           const int cw = ((tile & (WIN_NT - 1)) << 8) + j2 + cur.off;
-          relax_up(tile, cw, cur.r, cur.ipos, cur.len, cur.h1a, cur.h1b, cur.h2a, cur.h2b);
-          if (cur.off == 0 && cur.ipos == cur.len) {
-            // child 2j+1 opens row r+1: an up child on parent side 3 (and on side 2 as well at the apex)
-            double h2a, h2b;
-            halo_pair(a, tile >> pshift, 2, cur.r, S, h2a, h2b);
-            relax_up(tile, cw + 1, cur.r + 1, 1, cur.len - 2, 0.0, 0.0, h2a, h2b);
-          }
+          relax_up(tile, cw, cur.r, cur.ipos, cur.len, cur.h1a, cur.h1b, cur.h2a, cur.h2b);   // (a second up child of the pair: the down warps)
         }
         fence_async_smem();
         named_arrive(1 + (it & 3), WIN2_THREADS);
