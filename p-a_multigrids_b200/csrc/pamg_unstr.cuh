@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(TPB) k_kry_s(KryArgs a) {
 }
 
 // x += alpha y + omega z ; r = s - omega t ; rr = (r, r) ; rho <- rho_new ; rho_new = (rh, r) ; convergence / breakdown
-__global__ void __launch_bounds__(TPB) k_kry_x(KryArgs a) {
+__global__ void __launch_bounds__(TPB, 6) k_kry_x(KryArgs a) {   // (unbounded the unroller took 110 registers: 2 CTAs per SM)
   if (a.ks[KS_DONE] != 0.0) return;
   const double alpha = a.ks[KS_ALPHA], omega = a.ks[KS_OMEGA];
   const long long n = 3LL * a.E;
