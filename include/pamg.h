@@ -101,7 +101,9 @@ int pamg_set_parents(pamg_handle* h, int U, const double* X, const int32_t* neig
                      const int32_t* dir);
 /* distributed run (one process per GPU): the mesh is cut into nparts contiguous blocks of parents,
  * part i owning [part_first[i], part_first[i+1]); this handle owns block my_part.  Faces cut by the
- * partition exchange their halo strips over NCCL inside pamg_update_overlaps / pamg_smooth. */
+ * partition exchange their halo strips inside pamg_update_overlaps / pamg_smooth: direct stores into the
+ * neighbour GPU's memory over NVLink (CUDA IPC, set up collectively at the first exchange), NCCL send/recv
+ * where peer memory is not available. */
 int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, const int32_t* neig,
                                const int32_t* fneig, const int32_t* dir, int nparts, const int32_t* part_first,
                                int my_part);
