@@ -629,6 +629,7 @@ int configure_kernels(pamg_handle* h) {
   // whose next kernel has never been launched in this process would then wait for ever (seen with two parts on one device).
   cudaFuncAttributes fa;
   CK(cudaFuncGetAttributes(&fa, k_halo));
+  CK(cudaFuncGetAttributes(&fa, k_gs_small));
   CK(cudaFuncGetAttributes(&fa, k_build_rhs));
   CK(cudaFuncGetAttributes(&fa, k_restrict));
   CK(cudaFuncGetAttributes(&fa, k_prolong_literal));
@@ -707,7 +708,12 @@ int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout,
 }
 
 // coloured Gauss-Seidel sweep in one pass (k_gs_win / k_gs_win2), out of place
+// small levels (a CTA holds whole parents): both colours in one launch of k_gs_small
+bool gs_small_ok(const pamg_handle* h, const LevelDev& L) {
+  return h->gs_fused && h->kernel_mode == 4 && h->p.face_terms && L.C <= TPB;
+}
 bool gs_fused_ok(const pamg_handle* h, const LevelDev& L) {
+  if (gs_small_ok(h, L)) return true;
   return h->gs_fused && h->kernel_mode == 4 && h->p.face_terms && L.C >= TPB && L.s <= 8;
 }
 
@@ -719,6 +725,14 @@ int launch_gs_fused(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout
   a.ovl_next = write_next ? L.ovlb[L.ovl_cur ^ 1] : nullptr; a.dst_strip = h->dst_strip; a.rev = h->rev; a.nstrips = h->plan.nstrips;
   a.partial = h->partial; a.omega = h->p.omega; a.rsign = (double)h->p.residual_sign; a.nelem = L.nelem; a.s = L.s;
   a.colour = 1; a.partial_off = 0;
+  if (gs_small_ok(h, L)) {
+    const long long ppc = TPB / L.C, nparents = L.nelem / L.C;
+    const int sgrid = (int)std::max(1ll, std::min((nparents + ppc - 1) / ppc, (long long)h->nsm * 8));
+    k_gs_small<<<sgrid, TPB, 0, h->stream>>>(a);
+    h->launches++;
+    CK(cudaGetLastError());
+    return PAMG_OK;
+  }
   const bool producer = h->win_producer && L.s >= 6;
   const int resident = producer ? (xchg ? h->kc.gs2x : h->kc.gs2) : h->kc.gs;
   const bool prof = h->profiling && h->pev_used + 2 <= (int)h->pev.size();

@@ -1527,6 +1527,73 @@ __global__ void __launch_bounds__(TPB) k_element_direct2(ElemArgs a) {
   if (MODE == MODE_RESID) block_partial(acc_sum, acc_abs, acc_max, a.partial + (size_t)3 * a.partial_off);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Coloured Gauss-Seidel sweep on a SMALL level (at most TPB children per parent, n_split <= 4) in one launch, out of place.
+// Inside a parent the two colours couple only children of that parent, and values across parent faces are lagged by one
+// sweep anyway (transport_tri_semi.F90:647-655): a CTA that owns whole parents keeps them in shared memory, relaxes the down
+// children, synchronises, relaxes the up children (exterior values straight from the neighbour parents' boundary children in
+// the start-of-sweep field, or from the strips of cut / Dirichlet faces) and writes the parents out.  Same arithmetic as the
+// two in-place passes over global memory it replaces (three launches per sweep with their halo kernel): these levels are
+// launch-bound.
+__global__ void __launch_bounds__(TPB) k_gs_small(ElemArgs a) {
+  __shared__ double sT[3 * TPB];
+  const int s = a.s, twos = 2 * s, C = 1 << twos, b = 2 << s, S = 1 << s;
+  const int tid = threadIdx.x;
+  const int ppc = TPB >> twos;                          // parents per CTA
+  const int nparents = (int)(a.nelem >> twos);
+  const int lu = tid >> twos, k = tid & (C - 1);        // my parent inside the CTA, my child (memory order)
+  int r, ipos, len;
+  child_from_ele0(k, s, r, ipos, len);
+  const bool up = ipos & 1;
+  double* t = sT + tid * 3;
+  for (int pbase = blockIdx.x * ppc; pbase < nparents; pbase += gridDim.x * ppc) {
+    const int u = pbase + lu;
+    const bool active = u < nparents;
+    double b1 = 0.0, b2 = 0.0, b3 = 0.0;
+    const size_t g3 = ((size_t)(active ? u : 0) * C + k) * 3;
+    if (active) {
+      t[0] = __ldg(a.Tin + g3); t[1] = __ldg(a.Tin + g3 + 1); t[2] = __ldg(a.Tin + g3 + 2);
+      b1 = __ldg(a.rhs + g3); b2 = __ldg(a.rhs + g3 + 1); b3 = __ldg(a.rhs + g3 + 2);
+    }
+    const double* pcu = a.pc + (size_t)(active ? u : 0) * NPC;
+    FaceIn fi;
+    int bmask = 0;
+    if (active && up && (r == 1 || ipos == 1 || ipos == len)) {   // exterior values first: their latency hides under the down phase
+      if (r == 1) { halo_pair(a, u, 0, ipos >> 1, S, fi.n1a, fi.n1b); bmask |= 1; }
+      if (ipos == 1) { halo_pair(a, u, 2, r - 1, S, fi.n2a, fi.n2b); bmask |= 2; }
+      if (ipos == len) { halo_pair(a, u, 1, r - 1, S, fi.n3a, fi.n3b); bmask |= 4; }
+    }
+    __syncthreads();
+    const double* P0 = sT + (lu << twos) * 3;           // my parent's children
+    if (active && !up) {
+      const double T1 = t[0], T2 = t[1], T3 = t[2];
+      const double* tv = P0 + (k + b - 2 * r) * 3;
+      const double* tr = P0 + (k + 1) * 3;
+      const double* tl = P0 + (k - 1) * 3;
+      fi.n1a = tv[2]; fi.n1b = tv[0];
+      fi.n2a = tr[1]; fi.n2b = tr[2];
+      fi.n3a = tl[0]; fi.n3b = tl[1];
+      const Folded& F = *reinterpret_cast<const Folded*>(pcu + PC_FOLD + 16);
+      double o1, o2, o3;
+      elem_apply_folded<MODE_GS>(F, pcu + PC_DPEN, 0, T1, T2, T3, fi, b1, b2, b3, a.rsign, o1, o2, o3);
+      t[0] = o1; t[1] = o2; t[2] = o3;
+    }
+    __syncthreads();
+    if (active && up) {
+      const double T1 = t[0], T2 = t[1], T3 = t[2];
+      if (!(bmask & 1)) { const double* tv = P0 + (k + 2 * r - b - 2) * 3; fi.n1a = tv[2]; fi.n1b = tv[0]; }
+      if (!(bmask & 2)) { const double* tl = P0 + (k - 1) * 3; fi.n2a = tl[1]; fi.n2b = tl[2]; }
+      if (!(bmask & 4)) { const double* tr = P0 + (k + 1) * 3; fi.n3a = tr[0]; fi.n3b = tr[1]; }
+      const Folded& F = *reinterpret_cast<const Folded*>(pcu + PC_FOLD);
+      double o1, o2, o3;
+      elem_apply_folded<MODE_GS>(F, pcu + PC_DPEN, bmask, T1, T2, T3, fi, b1, b2, b3, a.rsign, o1, o2, o3);
+      t[0] = o1; t[1] = o2; t[2] = o3;
+    }
+    if (active) { a.Tout[g3] = t[0]; a.Tout[g3 + 1] = t[1]; a.Tout[g3 + 2] = t[2]; }   // (my own child: no barrier needed)
+    __syncthreads();
+  }
+}
+
 // second stage of the norm reduction: one CTA
 __global__ void __launch_bounds__(1024) k_reduce_partials(const double* partial, int n, double* out3) {
   double s0 = 0, s1 = 0, s2 = 0;
