@@ -128,6 +128,8 @@ def test_jacobi_sweep_and_residual(meshes, name, n, intended, u):
 
 @pytest.mark.parametrize("name,n,u", [("test_sn2", 3, (0.9, 0.3)), ("split0", 5, (0.0, 0.0)), ("900_ele", 2, (0.1, 0.1)),
                                       ("syn", 4, (0.9, 0.3)),
+                                      # n_split <= 4: both colours in one launch, whole parents in shared memory (k_gs_small)
+                                      ("irregular", 1, (0.9, 0.3)), ("untitled8192", 1, (-0.4, 0.7)), ("test_sn2", 4, (0.0, -1.0)),
                                       # one-pass kernel with a producer warp (k_gs_win2): 6 <= n_split <= 8
                                       ("test_sn2", 6, (0.9, 0.3)), ("split0", 7, (-0.5, 0.8)), ("syn", 8, (0.9, 0.3)),
                                       ("irregular", 6, (0.3, -0.2)),
