@@ -181,8 +181,9 @@ def workload_config(n, nsplit, scaling, single_process=False):
             "elements_per_gpu": per if scaling == "weak" else per // n, "n_split": nsplit,
             "parents_per_gpu": 4 ** KP if scaling == "weak" else 4 ** KP // n,
             "n_smooth": NSMOOTH, "face_terms": 1, "velocity": [0.9, 0.3], "dt": 1e-3, "k": 1.0, "omega": 0.8,
-            "parallelism": f"parent-partition x{n}, {who}cut-face halo strips by NVLink peer stores polled inside the halo "
-                           "kernel, norms all-reduced, small coarse levels agglomerated on GPU 0",
+            "parallelism": f"parent-partition x{n}, {who}cut-face values stored straight into the peer GPU's memory over NVLink by "
+                           "the producer warps of the sweep kernels (flagged words, unpack launch between sweeps), norms "
+                           "all-reduced, small coarse levels agglomerated on GPU 0",
             "l2_policy": "inputs larger than L2 (403 MB per field at c5)"}
 
 

@@ -379,16 +379,10 @@ int p2p_setup(pamg_handle* h) {
   if ((int)h->plan.peers.size() > P2P_MAXP) ok = 0;
   for (const auto& pp : h->p2p_peers) if (pp.slot_at_peer < 0) ok = 0;
   if (p2p_alloc_local(h) != PAMG_OK) { ok = 0; (void)cudaGetLastError(); }
-  // what travels: the IPC handle of my staging buffer and the identity of my GPU
-  struct Card { cudaIpcMemHandle_t handle; long long gpu; };
+  // what travels: the IPC handle of my staging buffer
+  struct Card { cudaIpcMemHandle_t handle; };
   Card mine;
   std::memset(&mine, 0, sizeof(mine));
-  {
-    cudaDeviceProp pr;
-    if (cudaGetDeviceProperties(&pr, h->device) == cudaSuccess)
-      mine.gpu = ((long long)pr.pciDomainID << 32) | ((long long)pr.pciBusID << 16) | (long long)pr.pciDeviceID;
-    else { ok = 0; (void)cudaGetLastError(); }
-  }
   if (ok && cudaIpcGetMemHandle(&mine.handle, h->p2p_stage) != cudaSuccess) { ok = 0; (void)cudaGetLastError(); }
   // all-gather of the cards with grouped send / recv (R <= 8)
   const size_t hb = sizeof(Card);
@@ -428,9 +422,6 @@ int p2p_setup(pamg_handle* h) {
   cudaFree(d_buf);
   if (rc) return rc;
   if (ok) {
-    // parts that share one GPU keep the exchange in k_halo (the same data on every rank: the same decision)
-    for (int r = 0; r < R && h->xchg_in_kernel; ++r)
-      for (int q = r + 1; q < R; ++q) if (all[r].gpu == all[q].gpu) { h->xchg_in_kernel = false; break; }
     if ((rc = p2p_upload_args(h))) return rc;
     h->p2p_ready = true;
   } else h->p2p_failed = true;
@@ -1236,12 +1227,10 @@ int group_p2p_setup(pamg_handle* root) {
       q->p2p_peers[i].stage = G[q->plan.peers[i].part]->p2p_stage;
     }
   }
-  bool distinct = true;        // parts that share one GPU keep the exchange in k_halo
-  for (size_t i = 0; i < G.size(); ++i)
-    for (size_t j = i + 1; j < G.size(); ++j) if (G[i]->device == G[j]->device) distinct = false;
+  // (parts that share one GPU use the same protocol: only the small halo / unpack kernels ever poll, never a sweep that
+  // fills the device, so a kernel waiting for a peer cannot keep the peer's sweep from running)
   for (pamg_handle* q : G) {
     CK_(root, cudaSetDevice(q->device));
-    if (!distinct) q->xchg_in_kernel = false;
     int rc = p2p_upload_args(q);
     if (rc) return gfail(root, q, rc);
     q->p2p_ready = true;
