@@ -43,8 +43,10 @@ enum { MODE_JACOBI = 0, MODE_RESID = 1, MODE_GS = 2, MODE_RICH = 3 };
 // changed the field).  The sweep kernels with a producer warp (XCHG) SEND: as a tile is finished the producer warp stores the
 // new values of its children on cut faces straight into the peers' staging buffers as exchange n+1 (the NVLink trip hides
 // under the rest of the sweep) and the last CTA advances the exchange number; a small unpack launch (k_halo, what = 4) before
-// the next sweep moves the values - long arrived - from the staging buffer into the strips.  A sender can then be up to three
-// exchanges ahead of what a receiver still reads, so the staging buffer has FOUR slots indexed by the exchange number mod 4.
+// the next sweep moves the values - long arrived - from the staging buffer into the strips.  The staging buffer has FOUR
+// slots indexed by the exchange number mod 4: a sending sweep that nobody unpacks (a prolongation came next; the level's
+// next visit starts with a k_halo exchange) lets a rank run two exchanges ahead of a peer that still has to unpack - two
+// slots would be overwritten, four are safe for every launch sequence the host issues (tests/test_exchange_protocol_model.py).
 constexpr int P2P_SLOTS = 4;
 constexpr int P2P_MAXP = 16;
 enum { P2P_EPOCH = 0, P2P_COUNT = 1, P2P_WORDS = 8 };
