@@ -34,8 +34,7 @@ enum { MODE_JACOBI = 0, MODE_RESID = 1, MODE_GS = 2, MODE_RICH = 3 };
 // two 8-byte words {low 32 bits, exchange number} {high 32 bits, exchange number}; an aligned 8-byte store is
 // atomic, so the receiver simply polls every word of its own staging buffer until it carries the number of this
 // exchange and unpacks it into the strip buffer.  No fence, no separate flag, no credit: the latency is one
-// NVLink one-way trip.  The staging buffer is double-buffered by the parity of the exchange number (a sender can
-// only be one exchange ahead of a receiver because it needs the receiver's data to get any further), and the
+// NVLink one-way trip.  The staging buffer has several slots indexed by the exchange number (below), and the
 // exchange number lives in device memory so that a captured CUDA graph replays correctly.  Polling has a time-out
 // that raises the error word (host-mapped memory, checked at every host synchronisation point) instead of hanging the GPU.
 //
