@@ -479,7 +479,8 @@ def main():
         g._ck(g.L.pamg_explicit_step(g.h, 1e-6, 0.9, 0.3, 0.0, 1, 2, 10, 0, 0))     # warm-up
         g.sync()
         g.event_record(8)
-        g._ck(g.L.pamg_explicit_step(g.h, 1e-6, 0.9, 0.3, 0.0, 5, 2, 10, 0, 0))     # 10 element-loop passes
+        g._ck(g.L.pamg_explicit_step(g.h, 1e-6, 0.9, 0.3, 0.0, 1, 10, 10, 0, 0))    # one time step of 10 element-loop passes
+                                                                                     # (one told copy, 10 kernel launches)
         g.event_record(9)
         g.sync()
         t_ms = g.elapsed_ms(8, 9) / 10.0
