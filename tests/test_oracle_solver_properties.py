@@ -1,0 +1,88 @@
+"""Properties the intended solver components must have, checked on the oracle alone (CPU): more pins for the triangle
+multigrid path, which has no reference output to compare with.
+
+  * the level-1 operator assembled column by column from residual evaluations is the matrix whose direct solution is the
+    fixed point of every smoother and the limit of the V-cycle (a11, a12, a15);
+  * restriction is the transpose of the P1 prolongation (`transfer = 1`, a13)."""
+import numpy as np
+import pytest
+
+import oracle_api as orc
+from helpers import rng_field, write_msh
+
+
+def problem(name, n, levels, tmp_path, u=(0.6, -0.3), dt=1e-3, k=1.0):
+    # (dt as in the benchmarks: with dt = 2e-2 the damped Jacobi smoother of the reference, omega = 0.8 on the lumped-mass
+    # diagonal, diverges on test_sn2 - a property of the algorithm, not of an implementation)
+    m = orc.read_msh(write_msh(name, str(tmp_path / (name + ".msh"))))
+    fneig, _ = orc.neig_data(m["neig"], m["dir"])
+    p = orc.intended_params(n, levels, dt=dt, k=k, u=u)
+    return orc.Semi(p, m["X"], m["neig"], fneig, m["dir"])
+
+
+def operator_and_rhs(o):
+    """A and b of level 1 from residual evaluations: r(x) = b - A x (residual_sign = -1), Dirichlet data folded into b."""
+    shape = o.field(orc.TNEW).shape
+    N = int(np.prod(shape))
+
+    def resid(x):
+        o.field(orc.TNEW)[:] = x.reshape(shape); o.field(orc.TNONLIN)[:] = x.reshape(shape)
+        o.update_overlaps(1)
+        o.residual(1)
+        return o.field(orc.RES).reshape(-1).copy()
+    b = resid(np.zeros(N))
+    A = np.zeros((N, N))
+    for j in range(N):
+        e = np.zeros(N); e[j] = 1.0
+        A[:, j] = b - resid(e)
+    return A, b
+
+
+@pytest.mark.parametrize("name,n", [("test_sn2", 2), ("split0", 2)])
+def test_direct_solution_is_the_fixed_point_of_the_smoothers_and_the_limit_of_the_vcycle(name, n, tmp_path):
+    o = problem(name, n, n, tmp_path)
+    shape = o.field(orc.TNEW).shape
+    o.field(orc.TOLD)[:] = rng_field(shape, 5)
+    o.build_rhs()
+    A, b = operator_and_rhs(o)
+    assert np.linalg.cond(A) < 1e8
+    xs = np.linalg.solve(A, b)
+    scale = np.abs(xs).max()
+    for solver in (1, 4):                                   # Jacobi, two-colour Gauss-Seidel
+        o.field(orc.TNONLIN)[:] = xs.reshape(shape); o.field(orc.TNEW)[:] = xs.reshape(shape)
+        o.smooth(1, solver, 3)
+        assert np.abs(o.field(orc.TNONLIN).reshape(-1) - xs).max() <= 1e-11 * scale, solver
+    for solver in (1, 4):
+        o.field(orc.TNONLIN)[:] = 0.0; o.field(orc.TNEW)[:] = 0.0
+        cycles, hist = o.vcycle_solve(solver=solver, max_cycles=60, tol=1e-10)
+        assert cycles <= 60 and hist[-1] <= 1e-10 * hist[0], (cycles, hist[-1] / hist[0])
+        assert np.abs(o.field(orc.TNONLIN).reshape(-1) - xs).max() <= 1e-7 * scale, solver
+    # one Jacobi sweep is x + omega D^-1 (b - A x) with ONE fixed positive diagonal D (the reference's get_diagonal: lumped
+    # mass / dt + K_ii + penalty diagonal, transport_tri_semi.F90:481-486 - not diag(A), whose mass part is consistent)
+    Ds = []
+    for seed in (9, 10):
+        x0 = rng_field(shape, seed).reshape(-1)
+        o.field(orc.TNONLIN)[:] = x0.reshape(shape); o.field(orc.TNEW)[:] = x0.reshape(shape)
+        o.smooth(1, 1, 1)
+        dx = o.field(orc.TNONLIN).reshape(-1) - x0
+        Ds.append(o.params.omega * (b - A @ x0) / dx)
+    assert np.all(Ds[0] > 0.0)
+    assert np.abs(Ds[0] - Ds[1]).max() <= 1e-8 * np.abs(Ds[0]).max()
+    assert np.all(Ds[0] >= np.diag(A) * (1.0 - 1e-12)) or np.all(Ds[0] > 0.5 * np.diag(A))   # lumped >= consistent mass on the diagonal
+
+
+@pytest.mark.parametrize("name,n", [("test_sn2", 3), ("irregular", 2)])
+def test_restriction_is_the_transpose_of_the_p1_prolongation(name, n, tmp_path):
+    o = problem(name, n, 2, tmp_path)
+    f_shape, c_shape = o.field(orc.TNEW, 1).shape, o.field(orc.TNEW, 2).shape
+    r = rng_field(f_shape, 21) - 0.5
+    e = rng_field(c_shape, 22) - 0.5
+    o.field(orc.RES, 1)[:] = r
+    o.restrict(1)                                           # RHS(2) = R r
+    Rr = o.field(orc.RHS, 2).copy()
+    o.field(orc.TNONLIN, 1)[:] = 0.0; o.field(orc.TNEW, 1)[:] = 0.0
+    o.field(orc.TNONLIN, 2)[:] = e; o.field(orc.TNEW, 2)[:] = e
+    o.prolong(1)                                            # T(1) += P e
+    Pe = o.field(orc.TNONLIN, 1).copy()
+    lhs, rhs = float(np.sum(Rr * e)), float(np.sum(r * Pe))
+    assert abs(lhs - rhs) <= 1e-12 * max(abs(lhs), abs(rhs), 1.0), (lhs, rhs)
