@@ -86,3 +86,43 @@ def test_restriction_is_the_transpose_of_the_p1_prolongation(name, n, tmp_path):
     Pe = o.field(orc.TNONLIN, 1).copy()
     lhs, rhs = float(np.sum(Rr * e)), float(np.sum(r * Pe))
     assert abs(lhs - rhs) <= 1e-12 * max(abs(lhs), abs(rhs), 1.0), (lhs, rhs)
+
+
+@pytest.mark.parametrize("name,use_dir,u", [("split1", 1, (0.4, -0.7)), ("irregular", 1, (0.9, 0.3)), ("900_ele", 0, (1.0, 0.0)),
+                                            ("untitled8192", 1, (-0.6, 0.2))])
+def test_explicit_step_advects_a_linear_field_exactly(name, use_dir, u, tmp_path):
+    """unstr_explicit (transport_tri_unstr.F90:588-795) with the exact local mass inverse: for a continuous linear field the
+    upwind DG right-hand side is int phi_i u.grad(T) on every element without a boundary face, so one forward-Euler step gives
+    T - dt u.g at every node of those elements - whatever the mesh, neighbour numbering or node pairing."""
+    m = orc.read_msh(write_msh(name, str(tmp_path / (name + ".msh"))))
+    fneig, _ = orc.neig_data(m["neig"], m["dir"])
+    X = m["X"]
+    g = np.array([1.3, -0.8])
+    T0 = 0.2 + X @ g                                         # (E, 3)
+    dt = 1e-4
+    T = np.ascontiguousarray(T0.copy())
+    orc.lib().orc_unstr_explicit(X.shape[0], np.ascontiguousarray(X), np.ascontiguousarray(m["neig"]), fneig,
+                                 np.ascontiguousarray(m["dir"]), u[0], u[1], dt, 1, 1, 10, 1, use_dir, 0.0, T)
+    interior = np.all(m["neig"] != 0, axis=1)
+    assert interior.sum() >= 4
+    expect = T0 - dt * float(np.dot(g, u))
+    err = np.abs(T - expect)[interior]
+    assert err.max() <= 1e-12 * np.abs(expect).max(), err.max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,use_dir,u", [("irregular", 1, (0.9, 0.3)), ("untitled8192", 1, (-0.6, 0.2))])
+def test_device_explicit_step_advects_a_linear_field_exactly(name, use_dir, u, tmp_path):
+    """the same identity on k_unstr_explicit (division-free geometry) through the C ABI"""
+    from pamg_pkg import pamg
+    mesh = pamg.Mesh.read_msh(write_msh(name, str(tmp_path / (name + ".msh"))))
+    gs = pamg.SemiImplicitIterative(pamg.default_params(), pamg.Mesh.synthetic(0, 1))
+    gs.set_unstructured(mesh)
+    g = np.array([1.3, -0.8])
+    T0 = 0.2 + mesh.X @ g
+    dt = 1e-4
+    T = gs.unstr_explicit(T0, dt, u[0], u[1], ntime=1, nits=1, njac_its=10, exact_minv=True, use_dir=bool(use_dir))
+    interior = np.all(mesh.neig != 0, axis=1)
+    expect = T0 - dt * float(np.dot(g, u))
+    assert np.abs(T - expect)[interior].max() <= 1e-12 * np.abs(expect).max()
+    gs.close()
