@@ -126,3 +126,32 @@ def test_device_explicit_step_advects_a_linear_field_exactly(name, use_dir, u, t
     expect = T0 - dt * float(np.dot(g, u))
     assert np.abs(T - expect)[interior].max() <= 1e-12 * np.abs(expect).max()
     gs.close()
+
+
+@pytest.mark.parametrize("name,u,k", [("split1", (0.4, -0.7), 0.9), ("irregular", (0.9, 0.3), 0.0), ("900_ele", (1.0, 0.0), 0.5)])
+def test_implicit_operator_on_a_continuous_linear_field(name, u, k, tmp_path):
+    """unstr_implicit's matrix (transport_tri_unstr.F90:270-364, + the diffusion blocks of the iterative path): applied to a
+    continuous linear field it must give mass/dt T + int phi_i u.grad(T) + k A grad(phi_i).g on every element without a
+    boundary face (no jump: the penalty vanishes, the upwind flux telescopes)."""
+    m = orc.read_msh(write_msh(name, str(tmp_path / (name + ".msh"))))
+    fneig, _ = orc.neig_data(m["neig"], m["dir"])
+    X = m["X"]; E = X.shape[0]; N = 3 * E
+    dt = 1e-2
+    A = np.zeros((N, N)); M = np.zeros((N, N))
+    orc.lib().orc_unstr_implicit_assemble_diff(E, np.ascontiguousarray(X), np.ascontiguousarray(m["neig"]), fneig, u[0], u[1], k,
+                                               dt, 1, A, M)
+    g = np.array([1.3, -0.8])
+    T = 0.2 + X @ g                                          # (E, 3)
+    AT = (A @ T.reshape(-1)).reshape(E, 3)
+    e1, e2 = X[:, 0] - X[:, 2], X[:, 1] - X[:, 2]
+    det = e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0]
+    area = 0.5 * np.abs(det)
+    gphi = np.zeros((E, 3, 2))
+    gphi[:, 0, 0] = e2[:, 1] / det; gphi[:, 0, 1] = -e2[:, 0] / det
+    gphi[:, 1, 0] = -e1[:, 1] / det; gphi[:, 1, 1] = e1[:, 0] / det
+    gphi[:, 2] = -(gphi[:, 0] + gphi[:, 1])
+    expect = (area[:, None] / 12.0) * (T + T.sum(axis=1, keepdims=True)) / dt
+    expect += (np.dot(g, u) * area / 3.0)[:, None] + k * area[:, None] * (gphi @ g)
+    interior = np.all(m["neig"] != 0, axis=1)
+    assert interior.sum() >= 4
+    assert np.abs(AT - expect)[interior].max() <= 1e-11 * np.abs(expect[interior]).max()
