@@ -15,7 +15,12 @@
  * triangle path).  For the triangle multigrid path itself no reference output exists: PARITY UNPINNED
  * there; it is pinned instead against the known answers the reference formulas imply (SURVEY.md
  * appendix C), the reconstructible dump DG-rectangular_structured_analytical, the manufactured
- * solution sin(x+y) and geometric / algebraic invariants (tests/test_oracle_*.py).
+ * solution sin(x+y), the erfc boundary-layer gate of Check_thermal_analytical_validation.py
+ * (tests/test_erfc_boundary_layer.py), geometric / algebraic invariants (tests/test_oracle_*.py) and
+ * ANALYTIC identities that any correct implementation of the discretisation must satisfy: the operator,
+ * the implicit matrix and the explicit step applied to a continuous linear field have closed forms
+ * (tests/test_oracle_operator_consistency.py, tests/test_oracle_solver_properties.py), the direct
+ * solution of the assembled system is the fixed point of the smoothers and the limit of the V-cycles.
  *
  * Every function cites the reference file:line it follows.  Two behaviours exist
  * where the reference is work-in-progress:
