@@ -126,6 +126,7 @@ struct pamg_handle {
   bool gs_tma = true;   // coloured GS pass through the TMA tile kernel (PAMG_GS=direct selects the direct kernel)
   bool win_producer = true;  // window kernel with a producer warp (k_element_win2); PAMG_WIN=barrier: k_element_win
   bool gs_fused = true; // both colours in one pass (k_gs_win); PAMG_GS=twopass keeps the two in-place passes
+  bool vc_norm_fuse = true;   // Jacobi V-cycles take their convergence norm out of the first pre-sweep of the next cycle (PAMG_VC_NORM=0: a residual evaluation per cycle)
   // per-kernel timing (element kernels only)
   bool profiling = false;
   std::vector<cudaEvent_t> pev;  // pairs
@@ -593,6 +594,8 @@ int configure_face(pamg_handle* h) {
   if ((rc = configure_one(h, k_element_win2<MODE_RICH, FACE>, WIN2_THREADS, WIN_SMEM_BYTES, dummy))) return rc;
   if (FACE) {
     if ((rc = configure_one(h, k_element_win2<MODE_JACOBI, FACE, true>, WIN2_THREADS, WIN_SMEM_BYTES, h->kc.win2x))) return rc;
+    if ((rc = configure_one(h, k_element_win2<MODE_JACOBI, FACE, false, true>, WIN2_THREADS, WIN_SMEM_BYTES, dummy))) return rc;
+    if ((rc = configure_one(h, k_element_win2<MODE_JACOBI, FACE, true, true>, WIN2_THREADS, WIN_SMEM_BYTES, dummy))) return rc;
     if ((rc = configure_one(h, k_element_win2<MODE_RICH, FACE, true>, WIN2_THREADS, WIN_SMEM_BYTES, dummy))) return rc;
   }
   if ((rc = configure_one(h, k_element_win<MODE_JACOBI, FACE>, TPB, WIN_SMEM_BYTES, h->kc.win[f]))) return rc;
@@ -653,7 +656,7 @@ bool producer_kernel(const pamg_handle* h, const LevelDev& L, bool gs) {
 // write_next: the kernel's producer warp writes the strips of the next sweep into the other strip buffer
 template <int MODE>
 int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout, int colour, int grid, bool use_strips,
-                   bool write_next = false, bool xchg = false) {
+                   bool write_next = false, bool xchg = false, bool norm = false) {
   ElemArgs a;
   a.xsend = L.xsend; a.xsync = h->p2p_sync ? h->p2p_sync + (size_t)(&L - h->lev.data()) * P2P_WORDS : nullptr;
   if (MODE == MODE_RESID) xchg = false;     // a residual evaluation sends nothing
@@ -670,9 +673,12 @@ int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout,
     // window kernel with a producer warp (no CTA-wide barrier between tiles)
     auto kern = xchg ? k_element_win2<MODE == MODE_RESID ? MODE_JACOBI : MODE, true, true>
                      : h->p.face_terms ? k_element_win2<MODE, true> : k_element_win2<MODE, false>;
+    // a Jacobi sweep that also reduces the residual norms of the iterate it starts from (norm_fusable)
+    if (norm) kern = xchg ? k_element_win2<MODE == MODE_JACOBI ? MODE_JACOBI : MODE, true, true, MODE == MODE_JACOBI>
+                          : k_element_win2<MODE == MODE_JACOBI ? MODE_JACOBI : MODE, true, false, MODE == MODE_JACOBI>;
     const int tgrid = (int)std::max(1ll, std::min(L.nelem / TPB, (long long)h->nsm * (xchg ? h->kc.win2x : h->kc.win2[f])));
     kern<<<tgrid, WIN2_THREADS, WIN_SMEM_BYTES, h->stream>>>(a);
-    if (MODE == MODE_RESID) h->last_partials = tgrid;
+    if (MODE == MODE_RESID || norm) h->last_partials = tgrid;
   } else if ((MODE != MODE_GS || h->gs_tma) && h->kernel_mode == 4 && L.C >= TPB && L.s <= 8) {
     // (a vertical neighbour is up to 2^(s+1) children away: the 8-tile ring covers s <= 8)
     // window kernel: ring of 8 field tiles in shared memory, every neighbour value read from it
@@ -738,7 +744,13 @@ int launch_gs_fused(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout
   return PAMG_OK;
 }
 
-int do_smooth(pamg_handle* h, int level, int solver, int nsweeps) {
+// a Jacobi sweep of this level can hand out the residual norms of the iterate it starts from (k_element_win2<.., NORM>)
+bool norm_fusable(const pamg_handle* h, const LevelDev& L) {
+  return h->p.face_terms && h->kernel_mode == 4 && h->win_producer && L.s >= 6 && L.s <= 8;
+}
+
+// norm_first: the first sweep (Jacobi on a norm_fusable level) also leaves the partial sums of the residual norms
+int do_smooth(pamg_handle* h, int level, int solver, int nsweeps, bool norm_first = false) {
   LevelDev& L = h->lev[level - 1];
   if (level == 1 && !L.rhs_valid) { int rc = launch_build_rhs(h); if (rc) return rc; }
   const int grid = grid_for(h, L.nelem);
@@ -759,7 +771,8 @@ int do_smooth(pamg_handle* h, int level, int solver, int nsweeps) {
     int rc = ensure_strips(h, level, use_strips);
     if (rc) return rc;
     if (solver == 1 || solver == 2) {
-      rc = (solver == 1) ? launch_element<MODE_JACOBI>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid, use_strips, fusedk, xs)
+      rc = (solver == 1) ? launch_element<MODE_JACOBI>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid, use_strips, fusedk, xs,
+                                                       norm_first && sw == 0)
                          : launch_element<MODE_RICH>(h, L, L.T[L.cur], L.T[L.cur ^ 1], 0, grid, use_strips, fusedk, xs);
       if (rc) return rc;
       L.cur ^= 1;
@@ -790,6 +803,22 @@ int do_smooth(pamg_handle* h, int level, int solver, int nsweeps) {
   return PAMG_OK;
 }
 
+// second stage of the norm reduction, the all-reduce over the ranks and the copy to pinned host memory (queued, not awaited)
+int queue_norms(pamg_handle* h) {
+  k_reduce_partials<<<1, 1024, 0, h->stream>>>(h->partial, h->last_partials, h->out3);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (h->comm && h->nranks > 1) {
+    // global norms: sum of squares, max |r|, max r
+    g_nccl.GroupStart();
+    g_nccl.AllReduce(h->out3, h->out3, 1, ncclFloat64, ncclSum, h->comm, h->stream);
+    g_nccl.AllReduce(h->out3 + 1, h->out3 + 1, 2, ncclFloat64, ncclMax, h->comm, h->stream);
+    if (g_nccl.GroupEnd() != ncclSuccess) return fail(h, PAMG_ERR_CUDA, "ncclAllReduce failed");
+  }
+  CK(cudaMemcpyAsync(h->out3_host, h->out3, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  return PAMG_OK;
+}
+
 int do_residual(pamg_handle* h, int level, double* l2, double* linf, double* smax, bool queue_only = false) {
   LevelDev& L = h->lev[level - 1];
   if (level == 1 && !L.rhs_valid) { int rc = launch_build_rhs(h); if (rc) return rc; }
@@ -803,17 +832,7 @@ int do_residual(pamg_handle* h, int level, double* l2, double* linf, double* sma
   rc = launch_element<MODE_RESID>(h, L, tnew_ptr(L), L.res, 0, grid, use_strips);
   if (rc) return rc;
   if (l2 || linf || smax) {
-    k_reduce_partials<<<1, 1024, 0, h->stream>>>(h->partial, h->last_partials, h->out3);
-    h->launches++;
-    CK(cudaGetLastError());
-    if (h->comm && h->nranks > 1) {
-      // global norms: sum of squares, max |r|, max r
-      g_nccl.GroupStart();
-      g_nccl.AllReduce(h->out3, h->out3, 1, ncclFloat64, ncclSum, h->comm, h->stream);
-      g_nccl.AllReduce(h->out3 + 1, h->out3 + 1, 2, ncclFloat64, ncclMax, h->comm, h->stream);
-      if (g_nccl.GroupEnd() != ncclSuccess) return fail(h, PAMG_ERR_CUDA, "ncclAllReduce failed");
-    }
-    CK(cudaMemcpyAsync(h->out3_host, h->out3, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = queue_norms(h))) return rc;
     if (queue_only || h->capturing) return PAMG_OK;      // the caller synchronises (after the graph launch / for the whole group)
     CK(cudaStreamSynchronize(h->stream));
     if ((rc = p2p_check(h))) return rc;
@@ -891,7 +910,7 @@ int gfail(pamg_handle* owner, pamg_handle* q, int rc) { if (owner != q) owner->e
     }                                                                      \
   } while (0)
 
-int vcycle_rec(const Group& G, pamg_handle* owner, int level, int solver, int nu1, int nu2, int ncoarse);
+int vcycle_rec(const Group& G, pamg_handle* owner, int level, int solver, int nu1, int nu2, int ncoarse, int skip_pre = 0);
 
 int launch_push(pamg_handle* q, const double* src, double* dst, long long n, int channel, unsigned long long* peer_flag) {
   PushArgs a;
@@ -1019,7 +1038,9 @@ int normalise_parity(pamg_handle* h, LevelDev& L, int cur0) {
   return PAMG_OK;
 }
 
-int vcycle_rec(const Group& G, pamg_handle* owner, int level, int solver, int nu1, int nu2, int ncoarse) {
+// skip_pre (top level of a solve with the fused convergence norm): the first pre-smoothing sweep of this cycle has already
+// been run - it was the sweep that reduced the norm of the previous iterate - and the buffer parity is left to the caller
+int vcycle_rec(const Group& G, pamg_handle* owner, int level, int solver, int nu1, int nu2, int ncoarse, int skip_pre) {
   const int Lmax = (int)G[0]->lev.size();
   std::vector<int> cur0(G.size());
   for (size_t i = 0; i < G.size(); ++i) cur0[i] = G[i]->lev[level - 1].cur;
@@ -1035,7 +1056,7 @@ int vcycle_rec(const Group& G, pamg_handle* owner, int level, int solver, int nu
     GALL(G, owner, q, do_smooth(q, level, solver, ncoarse));
     return restore();
   }
-  GALL(G, owner, q, do_smooth(q, level, solver, nu1));
+  GALL(G, owner, q, do_smooth(q, level, solver, nu1 - skip_pre));
   for (pamg_handle* q : G) q->lev[level - 1].tnew_alias = true;   // tnew = tnew_nonlin
   GALL(G, owner, q, do_residual(q, level, nullptr, nullptr, nullptr));
   GALL(G, owner, q, do_restrict(q, level));
@@ -1055,16 +1076,37 @@ int vcycle_rec(const Group& G, pamg_handle* owner, int level, int solver, int nu
   }
   GALL(G, owner, q, do_prolong(q, level, false));
   GALL(G, owner, q, do_smooth(q, level, solver, nu2));
-  return restore();
+  return skip_pre ? PAMG_OK : restore();
 }
 
-// one V-cycle followed by the residual norms of level 1 (the copy to pinned memory is queued, not awaited)
-int vcycle_body(const Group& G, pamg_handle* owner, int solver, int nu1, int nu2, int ncoarse) {
+// one V-cycle followed by the residual norms of level 1 (the copy to pinned memory is queued, not awaited).
+// fuse (Jacobi): no residual evaluation of its own - the FIRST pre-smoothing sweep of the next cycle runs here and reduces
+// the norms of the iterate it starts from (k_element_win2<.., NORM>); `first` = this is cycle 1, whose own first
+// pre-sweep has not been run yet.  The sweep is undone (it wrote the other buffer) when the solve stops at this cycle.
+int vcycle_body(const Group& G, pamg_handle* owner, int solver, int nu1, int nu2, int ncoarse, bool fuse = false, bool first = true) {
   int rc;
-  if ((rc = vcycle_rec(G, owner, 1, solver, nu1, nu2, ncoarse))) return rc;
+  if ((rc = vcycle_rec(G, owner, 1, solver, nu1, nu2, ncoarse, (fuse && !first) ? 1 : 0))) return rc;
   for (pamg_handle* q : G) q->lev[0].tnew_alias = true;
+  if (fuse) {
+    GALL(G, owner, q, do_smooth(q, 1, solver, 1, /*norm_first=*/true));
+    GALL(G, owner, q, queue_norms(q));
+    return PAMG_OK;
+  }
   double dummy;
   GALL(G, owner, q, do_residual(q, 1, &dummy, nullptr, nullptr, /*queue_only=*/true));
+  return PAMG_OK;
+}
+
+// take back the norm sweep at the end of a fused body: the iterate it started from still sits in the other T buffer, and
+// the strips it read (local, unpacked cut faces) in the other strip buffer
+int undo_norm_sweep(pamg_handle* h) {
+  LevelDev& L = h->lev[0];
+  const bool fusedk = h->halo_mode == 2 && h->p.face_terms && producer_kernel(h, L, false);
+  L.cur ^= 1;
+  L.tnew_alias = true;
+  if (fusedk) { L.ovl_cur ^= 1; L.strips_valid = true; L.cut_valid = true; }
+  else { L.strips_valid = false; L.cut_valid = false; }
+  L.stage_valid = false;                    // (whatever the sweep sent to the peers belongs to the discarded iterate)
   return PAMG_OK;
 }
 
@@ -1168,6 +1210,8 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
     if (dg) h->debug_gap_ns = atoll(dg);
     const char* lp = getenv("PAMG_L2_PERSIST");
     if (lp && lp[0] == '0') h->l2_persist = false;
+    const char* vn = getenv("PAMG_VC_NORM");
+    if (vn && vn[0] == '0') h->vc_norm_fuse = false;
     const char* xk = getenv("PAMG_XCHG");
     if (xk && !strcmp(xk, "halo")) h->xchg_in_kernel = false;     // cut faces by a k_halo launch (copy, send, receive) between the sweeps
     const char* hl = getenv("PAMG_HALO");
@@ -1675,15 +1719,29 @@ int pamg_vcycle_solve(pamg_handle* h, int solver, int nu1, int nu2, int ncoarse,
   if (r0 == 0.0) return PAMG_OK;
   // cycle 1 runs eagerly; from cycle 2 on the identical launch sequence (most of it on launch-bound coarse levels) is
   // replayed as one CUDA graph per GPU
-  const long long key0 = ((((long long)solver * 64 + nu1) * 64 + nu2) * 64 + ncoarse);
+  // Jacobi: no residual evaluation per cycle - the first pre-smoothing sweep of the next cycle reduces the norms of the iterate
+  // it starts from (same numbers as get_residual's), and is taken back when the solve stops
+  bool fuse = solver == 1 && nu1 >= 1 && G[0]->vc_norm_fuse;
+  for (pamg_handle* q : G) fuse = fuse && norm_fusable(q, q->lev[0]) && q->halo_mode == 2;
+  bool swept = false;                       // a fused body has run: its trailing norm sweep is pending
+  auto finish = [&]() -> int {
+    if (!fuse || !swept) return PAMG_OK;
+    for (pamg_handle* q : G) { if (q->in_group) cudaSetDevice(q->device); int rc2 = undo_norm_sweep(q); if (rc2) return gfail(h, q, rc2); }
+    GALL(G, h, q, do_residual(q, 1, nullptr, nullptr, nullptr));      // leaves tracer%residuale of the final iterate, as before
+    return PAMG_OK;
+  };
+  const long long key0 = (((((long long)solver * 64 + nu1) * 64 + nu2) * 64 + ncoarse) * 2 + (fuse ? 1 : 0));
   // with NCCL in the cycle (halo exchange fallback, coarse gather/scatter) the capture is attempted once; if the library
   // refuses, the handle falls back to eager launches for good
   bool graph_ok = h->use_graph;
   for (pamg_handle* q : G) graph_ok = graph_ok && !q->profiling && (!q->comm || q->graph_nccl);
   for (int c = 1; c <= max_cycles; ++c) {
     if (c >= 2 && graph_ok) {
-      long long key = key0;                      // the graph bakes in which of the two T buffers holds the iterate
-      for (pamg_handle* q : G) for (auto& Lv : q->lev) key = key * 2 + Lv.cur;
+      // the graph bakes in which of the two T buffers holds the iterate and which strip buffer is current, on every level of
+      // every part (a hash: the product of the factors does not fit 64 bits for a group of GPUs)
+      unsigned long long hk = (unsigned long long)key0;
+      for (pamg_handle* q : G) for (auto& Lv : q->lev) hk = hk * 1000003ull + (unsigned long long)(Lv.cur * 2 + Lv.ovl_cur + 1);
+      const long long key = (long long)hk;
       pamg_handle::VcGraph* vg = nullptr;
       for (auto& g : h->vc_graphs) if (g.key == key) vg = &g;
       if (!vg) {
@@ -1699,7 +1757,7 @@ int pamg_vcycle_solve(pamg_handle* h, int solver, int nu1, int nu2, int ncoarse,
           if (ce != cudaSuccess) break;
           q->capturing = true;
         }
-        rc = (ce == cudaSuccess) ? vcycle_body(G, h, solver, nu1, nu2, ncoarse) : PAMG_ERR_CUDA;
+        rc = (ce == cudaSuccess) ? vcycle_body(G, h, solver, nu1, nu2, ncoarse, fuse, false) : PAMG_ERR_CUDA;
         pamg_handle::VcGraph ng;
         ng.key = key;
         for (size_t i = 0; i < begun; ++i) {
@@ -1728,7 +1786,7 @@ int pamg_vcycle_solve(pamg_handle* h, int solver, int nu1, int nu2, int ncoarse,
           // NCCL inside the capture was refused: run eagerly from now on (host-side state is periodic per cycle)
           for (pamg_handle* q : G) q->graph_nccl = false;
           graph_ok = false;
-          if ((rc = vcycle_body(G, h, solver, nu1, nu2, ncoarse))) return rc;
+          if ((rc = vcycle_body(G, h, solver, nu1, nu2, ncoarse, fuse, false))) return rc;
           goto cycle_done;
         }
         h->vc_graphs.push_back(ng);
@@ -1740,16 +1798,17 @@ int pamg_vcycle_solve(pamg_handle* h, int solver, int nu1, int nu2, int ncoarse,
         G[i]->launches += vg->launches[i];
       }
     } else {
-      if ((rc = vcycle_body(G, h, solver, nu1, nu2, ncoarse))) return rc;
+      if ((rc = vcycle_body(G, h, solver, nu1, nu2, ncoarse, fuse, c == 1))) return rc;
     }
   cycle_done:
+    swept = true;
     if ((rc = group_norms(G, h, &r, nullptr, nullptr))) return rc;
     if (hist) hist[c] = r;
     if (cycles) *cycles = c;
-    if (r / r0 <= tol) return PAMG_OK;
+    if (r / r0 <= tol) return finish();
   }
   if (cycles) *cycles = max_cycles + 1;
-  return PAMG_OK;
+  return finish();
 }
 
 int pamg_literal_timestep(pamg_handle* h, int solver, int n_multigrid, int n_smooth) {

@@ -347,10 +347,12 @@ static_assert(sizeof(Folded) == 16 * sizeof(double), "Folded layout");
 // at the PC_DPEN / PC_WB part of the parent's table.  The correction is the penalty formula with
 // dpen = penX - penI (the neighbour values already come from the halo strip), and omega / D is tabulated
 // per mask, so a boundary child costs a handful of extra FMAs instead of the generic path with 3 divisions.
-template <int MODE>
+// WITH_R: a sweep also hands out the residual rsign (A x - b) of the iterate it STARTS from (rr[0..2]) - the numbers
+// get_residual would compute on the same field, for free
+template <int MODE, bool WITH_R = false>
 __device__ __forceinline__ void elem_apply_folded(const Folded& F, const double* ext, int mask, double T1, double T2,
                                                   double T3, const FaceIn& fi, double b1, double b2, double b3,
-                                                  double rsign, double& o1, double& o2, double& o3) {
+                                                  double rsign, double& o1, double& o2, double& o3, double* rr = nullptr) {
   double ax1 = F.a11 * T1 + F.a12 * T2 + F.a13 * T3;
   double ax2 = F.a21 * T1 + F.a22 * T2 + F.a23 * T3;
   double ax3 = F.a31 * T1 + F.a32 * T2 + F.a33 * T3;
@@ -365,6 +367,7 @@ __device__ __forceinline__ void elem_apply_folded(const Folded& F, const double*
     const double* wb = ext + 4 + mask * 3;
     w1 = wb[0]; w2 = wb[1]; w3 = wb[2];
   }
+  if (WITH_R) { rr[0] = rsign * (ax1 - b1); rr[1] = rsign * (ax2 - b2); rr[2] = rsign * (ax3 - b3); }
   if (MODE == MODE_RESID) {
     o1 = rsign * (ax1 - b1); o2 = rsign * (ax2 - b2); o3 = rsign * (ax3 - b3);
   } else {
@@ -832,8 +835,11 @@ constexpr int WIN2_THREADS = TPB + 32;
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// XCHG: the producer warp sends the new values of the children on cut faces to the peer GPUs (see P2PArgs)
-template <int MODE, bool FACE, bool XCHG = false>
+// XCHG: the producer warp sends the new values of the children on cut faces to the peer GPUs (see P2PArgs).
+// NORM (Jacobi with face terms): the sweep also reduces the norms of the residual of the iterate it starts from, exactly as
+// the residual kernel would (same tiles per CTA, same order: the same partial sums) - the V-cycle takes its convergence
+// norm out of the first pre-smoothing sweep of the next cycle instead of a residual evaluation of its own.
+template <int MODE, bool FACE, bool XCHG = false, bool NORM = false>
 __global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
   extern __shared__ __align__(128) unsigned char dsm[];   // WIN_SMEM_BYTES
   double* sT = reinterpret_cast<double*>(dsm);
@@ -996,7 +1002,15 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
         }
         if (FACE && MODE != MODE_RICH) {
           const Folded& F = *reinterpret_cast<const Folded*>(sPC + PC_FOLD + (up ? 0 : 16));
-          elem_apply_folded<MODE>(F, sPC + PC_DPEN, bmask, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
+          if (NORM) {
+            double rr[3];
+            elem_apply_folded<MODE, true>(F, sPC + PC_DPEN, bmask, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3, rr);
+            acc_sum += rr[0] * rr[0] + rr[1] * rr[1] + rr[2] * rr[2];
+            acc_abs = fmax(acc_abs, fmax(fabs(rr[0]), fmax(fabs(rr[1]), fabs(rr[2]))));
+            acc_max = fmax(acc_max, fmax(rr[0], fmax(rr[1], rr[2])));
+          } else {
+            elem_apply_folded<MODE>(F, sPC + PC_DPEN, bmask, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.rsign, o1, o2, o3);
+          }
         } else {
           elem_apply_regs<MODE, FACE>(P, up, interior, T1, T2, T3, fi, bb[0], bb[1], bb[2], a.omega, a.rsign, o1, o2, o3);
         }
@@ -1012,7 +1026,7 @@ __global__ void __launch_bounds__(WIN2_THREADS, 3) k_element_win2(ElemArgs a) {
       cur = nxt;
     }
   }
-  if (MODE == MODE_RESID) {
+  if (MODE == MODE_RESID || NORM) {
     if (tid < TPB) {
       for (int o = 16; o > 0; o >>= 1) {
         acc_sum += __shfl_xor_sync(0xffffffffu, acc_sum, o);
