@@ -575,8 +575,10 @@ struct ElemOp {            // everything get_A_x / get_diagonal need for one chi
 // One child: volume terms (:575-609) and, if face_terms, the face block (:619-688 read with
 // transport_tri.F90:593-669 / transport_tri_unstr.F90:706-747).  Tcur: field the face traces and
 // neighbour values are taken from; Town: own nodal values used for traces.
+// ovl_field: the halo strips that go with Tnbr_field (nullptr = L.ovl, the strips of tracer%tnew; L.ovl_old for told).
 void element_terms(const orc_semi* h, const orc_semi::Level& L, int level, int u, int ele,
-                   const Stencil& st, const double* Town, const double* Tnbr_field, ElemOp& op) {
+                   const Stencil& st, const double* Town, const double* Tnbr_field, ElemOp& op,
+                   const std::vector<double>* ovl_field = nullptr) {
   int irow, ipos, ori;
   get_str_info(L.s, ele, irow, ipos, ori);
   int updown = ori == 0 ? -1 : 1;  // semi_get_nx_pos, ShapFun.F90:1801-1804
@@ -601,7 +603,7 @@ void element_terms(const orc_semi* h, const orc_semi::Level& L, int level, int u
   for (int i = 0; i < 3; ++i) { op.flux[i] = 0; op.dsurf[i] = 0; op.mydiag[i] = 0; }
   if (!h->p.face_terms) return;
 
-  const double* ovl = &L.ovl[(size_t)u * 3 * 3 * L.S];
+  const double* ovl = &(ovl_field ? *ovl_field : L.ovl)[(size_t)u * 3 * 3 * L.S];
   double lvl_scale = (double)ipow(2, level - 1);  // penalty length is level aware (INTENDED, SURVEY B-18)
   for (int f = 1; f <= 3; ++f) {
     int ele22 = L.str_neig[(size_t)(ele - 1) * 3 + f - 1];
@@ -663,6 +665,13 @@ void apply_A(const orc_semi* h, const Stencil& st, const ElemOp& op, const doubl
   }
 }
 
+// get_diagonal (:481-486).  For theta != 1 it is the diagonal of the operator get_A_x applies, ml/dt + theta (K_ii + sum_f my_ii);
+// the reference's mat_diag_approx leaves theta out (:483-484), which is the same thing at theta = 1, its only literal (:117).
+// solve_Richardson (:516) has no theta either and is weighted the same way here.
+inline double diag_of(const orc_semi* h, const Stencil& st, const ElemOp& op, int i) {
+  return st.ml[i] / h->p.dt + h->p.theta * op.dvol1[i][i] + h->p.theta * op.mydiag[i];   // (same rounding as before at theta = 1)
+}
+
 // source reset (:593) + get_RHS (:452-464) for one level-1 child
 void build_rhs_child(orc_semi* h, orc_semi::Level& L, int u, int ele, const Stencil& st) {
   const double (*X)[2] = Xof(h, u);
@@ -680,8 +689,20 @@ void build_rhs_child(orc_semi* h, orc_semi::Level& L, int u, int ele, const Sten
     double ms = 0;
     if (h->p.literal_source) { for (int j = 0; j < 3; ++j) ms += st.mass[i][j] * src[j]; src[i] = ms; }
     else { for (int j = 0; j < 3; ++j) ms += st.mass[i][j] * s0[j]; }
-    // theta = 1 form; the (1-theta) branch of :459-460 needs the old-time flux and is exercised only with theta=1 in the reference
-    L.rhs[o + i] = m_old + ms;
+    L.rhs[o + i] = m_old + ms;   // theta = 1 form of :458 (the reference's only literal, :117)
+  }
+  if (h->p.theta != 1.0) {
+    // (1-theta) branch of :459-460: + (1-theta)(stiff_old - flux_old - diff_vol - diff_surf), every spatial term evaluated
+    // on TOLD with the told strips (t_overlap_old, splitting.F90:1259-1262).  HEAD has no flux_ele_old (the face block is
+    // commented out) and takes diff_vol / diff_surf of the NEW iterate there; theta = 1 is its only literal, so this branch
+    // is the Crank-Nicolson reading, not a quirk that any run of the reference exercises.
+    ElemOp op;
+    element_terms(h, L, 1, u, ele, st, told, L.told.data(), op, &L.ovl_old);
+    for (int i = 0; i < 3; ++i) {
+      double stiff = 0, dvol = 0;
+      for (int j = 0; j < 3; ++j) { stiff += op.stiff1[i][j] * told[j]; dvol += op.dvol1[i][j] * told[j]; }
+      L.rhs[o + i] += (1.0 - h->p.theta) * (stiff - op.flux[i] - dvol - op.dsurf[i]);
+    }
   }
   if (!h->p.literal_source) for (int i = 0; i < 3; ++i) {
     double ms = 0; for (int j = 0; j < 3; ++j) ms += st.mass[i][j] * s0[j]; src[i] = ms; }
@@ -802,7 +823,7 @@ double* orc_semi_overlap(orc_semi* h, int level, int old) {
 }
 
 // update_overlaps, splitting.F90:1238-1394.  Reads tracer%tnew / told of the level.
-void orc_semi_update_overlaps(orc_semi* h, int level) {
+static void update_overlaps_impl(orc_semi* h, int level, bool do_new, bool do_old) {
   orc_semi::Level& L = h->lev[level - 1];
   int S = L.S;
   double bc_scale = (h->p.coarse_bc_zero && level > 1) ? 0.0 : 1.0;
@@ -826,23 +847,29 @@ void orc_semi_update_overlaps(orc_semi* h, int level) {
           double ta = bc_scale * boundary_fn(x[a][0], x[a][1]), tb = bc_scale * boundary_fn(x[b][0], x[b][1]);
           if (kind == 1) ta = tb = bc_scale * h->bc_val[u * 3 + mf - 1];      // t_bc as data (splitting.F90:1210)
           size_t o = ((size_t)u * 3 + (mf - 1)) * 3 * S + (size_t)(pos - 1) * 3;
-          L.ovl[o + a] = ta; L.ovl[o + b] = tb;
-          L.ovl_old[o + a] = ta; L.ovl_old[o + b] = tb;
+          if (do_new) { L.ovl[o + a] = ta; L.ovl[o + b] = tb; }
+          if (do_old) { L.ovl_old[o + a] = ta; L.ovl_old[o + b] = tb; }
         } else {
           int nside = h->fneig[u * 3 + mf - 1];
           int rev = h->halo_rev[u * 3 + mf - 1];
           int slot = rev ? (S - pos + 1) : pos;
           size_t o = ((size_t)(npos - 1) * 3 + (nside - 1)) * 3 * S + (size_t)(slot - 1) * 3;
           size_t src = ((size_t)u * L.C + (ele - 1)) * 3;
-          for (int q = 0; q < 3; ++q) { L.ovl[o + q] = L.tnew[src + q]; L.ovl_old[o + q] = L.told[src + q]; }
+          for (int q = 0; q < 3; ++q) {
+            if (do_new) L.ovl[o + q] = L.tnew[src + q];
+            if (do_old) L.ovl_old[o + q] = L.told[src + q];
+          }
         }
       }
     }
   }
 }
+void orc_semi_update_overlaps(orc_semi* h, int level) { update_overlaps_impl(h, level, true, true); }
 
 void orc_semi_build_rhs(orc_semi* h) {
   orc_semi::Level& L = h->lev[0];
+  // theta != 1: the old-time face terms read the told strips; refresh them from TOLD (the tnew strips stay as the caller left them)
+  if (h->p.theta != 1.0 && h->p.face_terms) update_overlaps_impl(h, 1, false, true);
 #pragma omp parallel for num_threads(g_threads) schedule(static)
   for (int u = 0; u < h->U; ++u) {
     Stencil st; stencil_for(h, L, u, st);
@@ -872,9 +899,9 @@ void orc_semi_smooth(orc_semi* h, int level, int solver, int nsweeps) {
           double m = 0, sfn = 0;
           for (int j = 0; j < 3; ++j) { m += st.mass[i][j] * Town[j]; sfn += op.stiff1[i][j] * Town[j]; }
           m /= h->p.dt;
-          L.tnonlin[o + i] = L.tnonlin[o + i] + h->p.omega * (L.rhs[o + i] - (m - sfn + op.flux[i]));
+          L.tnonlin[o + i] = L.tnonlin[o + i] + h->p.omega * (L.rhs[o + i] - (m - h->p.theta * sfn + h->p.theta * op.flux[i]));
         } else {
-          double D = st.ml[i] / h->p.dt + op.dvol1[i][i] + op.mydiag[i];  // get_diagonal :481-486
+          double D = diag_of(h, st, op, i);
           double base = latest ? L.tnonlin[o + i] : L.tnew[o + i];
           Ax[i] = Ax[i];
           // solve_Jacobi :491-497 / solve_Gauss_Seidel :501-507 (point-simultaneous inside the child)
@@ -901,7 +928,7 @@ void orc_semi_smooth(orc_semi* h, int level, int solver, int nsweeps) {
           double Ax[3];
           apply_A(h, st, op, own, Ax);
           for (int i = 0; i < 3; ++i) {
-            double D = st.ml[i] / h->p.dt + op.dvol1[i][i] + op.mydiag[i];
+            double D = diag_of(h, st, op, i);
             L.tnonlin[o + i] = own[i] + h->p.omega / D * (L.rhs[o + i] - Ax[i]);
           }
         }
@@ -923,7 +950,7 @@ void orc_semi_smooth(orc_semi* h, int level, int solver, int nsweeps) {
             double Ax[3];
             apply_A(h, st, op, own, Ax);
             for (int i = 0; i < 3; ++i) {
-              double D = st.ml[i] / h->p.dt + op.dvol1[i][i] + op.mydiag[i];
+              double D = diag_of(h, st, op, i);
               L.tnonlin[o + i] = own[i] + h->p.omega / D * (L.rhs[o + i] - Ax[i]);
             }
           }
