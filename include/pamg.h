@@ -51,7 +51,7 @@ typedef struct pamg_params {
   int32_t keep_tnew_gs;   /* 1: the in-place GS sweep keeps tracer%tnew = start-of-last-sweep field (:550) by a device copy;
                              0: TNEW aliases the iterate after a GS smoother call (saves 16 B/DOF per call) */
   int32_t reserved;       /* keeps the doubles 8-byte aligned */
-  double theta;           /* :117 (only theta = 1 is implemented, like the reference's literal) */
+  double theta;           /* :117 (the reference's literal is 1.; 0 <= theta <= 1: get_A_x :444-446 and the old-time branch of get_RHS :459-460) */
   double dt;              /* :133  dt = CFL*dx */
   double k;               /* :136 */
   double omega;           /* :140 */
@@ -125,7 +125,8 @@ int pamg_device_ptr(pamg_handle* h, int field, int level, void** dptr); /* for z
 /* ---- the hot path ------------------------------------------------------------------------------ */
 /* update_overlaps (splitting.F90:1210-1397): halo strips from TNEW/TOLD of the level */
 int pamg_update_overlaps(pamg_handle* h, int level);
-/* level-1 RHS = (1/dt) M told + M src (get_RHS, transport_tri_semi.F90:452-464, theta = 1) */
+/* level-1 RHS = (1/dt) M told + M src - (1 - theta)(-stiff + flux + diff_vol + diff_surf) told (get_RHS,
+ * transport_tri_semi.F90:452-464); with theta != 1 the RES field is the scratch of the old-time pass */
 int pamg_build_rhs(pamg_handle* h);
 /* smoother (:543-722): nsweeps sweeps on TNONLIN; each sweep does TNEW <- TNONLIN (:550), halo (:555),
  * then one Jacobi / Richardson / two-colour GS update of every child */

@@ -80,6 +80,7 @@ struct LevelDev {
   ulonglong2* xsend = nullptr;                // [U*3] where a sweep's producer warp sends the values of a cut side (ElemArgs::xsend)
   double* ovl_old = nullptr;                  // told strips (update_overlaps as written only)
   double* pc = nullptr;               // [U][NPC]
+  double* pc_old = nullptr;           // level 1, theta != 1: [U][NPC] of the old-time operator (1 - theta)(-stiff + flux + diff), no mass (get_RHS :459-460)
   bool rhs_valid = false;             // level 1: RHS matches TOLD
   double* spare = nullptr;            // third field buffer of pamg_smooth_host (level 1, allocated on first use)
 };
@@ -231,8 +232,12 @@ double* field_ptr(pamg_handle* h, int field, int level, bool for_write, int* rc)
 // bc_kind: [U_global][3] kinds of the domain-boundary faces (nullptr = Dirichlet everywhere); an open face (kind 2) has no
 // penalty term.  Returns false for an open face with inflow (n.u < 0): the exterior trace would have to follow the interior
 // one inside the kernels, which is not supported.
+// th weights every spatial term (get_A_x :444-446: theta (-stiff + flux + diff_vol + diff_surf) + mass; the diagonal follows
+// the operator, ml/dt + theta (K_ii + sum_f my_ii) - the reference's mat_diag_approx leaves theta out, :483, the same thing at
+// its only literal theta = 1); with_mass = false drops the mass term: th = 1 - theta without mass is the old-time operator of
+// get_RHS (:459-460).
 bool parent_coefficients(const pamg_params& p, const double* Xall, const int32_t* neig, const int32_t* bc_kind,
-                         int g /*global parent*/, int s, double* pc) {
+                         int g /*global parent*/, int s, double* pc, double th, bool with_mass = true) {
   bool supported = true;
   const double* X = Xall + (size_t)g * 6;
   const double x1 = X[0], y1 = X[1], x2 = X[2], y2 = X[3], x3 = X[4], y3 = X[5];
@@ -243,11 +248,12 @@ bool parent_coefficients(const pamg_params& p, const double* Xall, const int32_t
   const double g3[2] = {-(g1[0] + g2[0]), -(g1[1] + g2[1])};
   const double* G[3] = {g1, g2, g3};
   const double two_s = std::ldexp(1.0, s), four_s = std::ldexp(1.0, 2 * s);
-  pc[PC_CM] = area / (12.0 * four_s * p.dt);
+  pc[PC_CM] = with_mass ? area / (12.0 * four_s * p.dt) : 0.0;
   auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1]; };
-  pc[PC_K11] = p.k * area * dot(g1, g1); pc[PC_K12] = p.k * area * dot(g1, g2); pc[PC_K13] = p.k * area * dot(g1, g3);
-  pc[PC_K22] = p.k * area * dot(g2, g2); pc[PC_K23] = p.k * area * dot(g2, g3); pc[PC_K33] = p.k * area * dot(g3, g3);
-  const double uu[2] = {p.u_x, p.u_y};
+  const double kth = th * p.k;      // (th = 1: bit-identical to the unweighted tables)
+  pc[PC_K11] = kth * area * dot(g1, g1); pc[PC_K12] = kth * area * dot(g1, g2); pc[PC_K13] = kth * area * dot(g1, g3);
+  pc[PC_K22] = kth * area * dot(g2, g2); pc[PC_K23] = kth * area * dot(g2, g3); pc[PC_K33] = kth * area * dot(g3, g3);
+  const double uu[2] = {th * p.u_x, th * p.u_y};
   for (int i = 0; i < 3; ++i) pc[PC_ADV + i] = area * dot(G[i], uu) / (3.0 * two_s);
   const double cx = (x1 + x2 + x3) / 3.0, cy = (y1 + y2 + y3) / 3.0;
   // child faces: f1 = nodes (1,3) on side 1, f2 = (3,2) on side 3, f3 = (2,1) on side 2
@@ -264,7 +270,7 @@ bool parent_coefficients(const pamg_params& p, const double* Xall, const int32_t
     pc[PC_FL + f] = (uu[0] * nx + uu[1] * ny) * lhalf / (3.0 * two_s);
     const double dix = ci[f][0] * V1[0] + ci[f][1] * V2[0], diy = ci[f][0] * V1[1] + ci[f][1] * V2[1];
     const double dcI = std::sqrt(dix * dix + diy * diy);
-    pc[PC_PENI + f] = p.k * lhalf / (3.0 * dcI);
+    pc[PC_PENI + f] = kth * lhalf / (3.0 * dcI);
     const int q = neig[(size_t)g * 3 + mface[f]];
     double dcX;
     if (q != 0) {
@@ -274,7 +280,7 @@ bool parent_coefficients(const pamg_params& p, const double* Xall, const int32_t
     } else {
       dcX = std::sqrt((cx - mx) * (cx - mx) + (cy - my) * (cy - my));
     }
-    pc[PC_PENX + f] = p.k * lhalf / (3.0 * dcX);
+    pc[PC_PENX + f] = kth * lhalf / (3.0 * dcX);
     if (q == 0 && bc_kind && bc_kind[(size_t)g * 3 + mface[f]] == 2) {
       pc[PC_PENX + f] = 0.0;                                 // open face: no data, no penalty
       if (p.face_terms && pc[PC_FL + f] < 0.0) supported = false;
@@ -323,6 +329,11 @@ bool parent_coefficients(const pamg_params& p, const double* Xall, const int32_t
     pc[PC_WB + mask * 3 + 2] = p.omega / (4.0 * pc[PC_CM] + pc[PC_K33] + 2.0 * (pen[0] + pen[1]));
   }
   for (int i = PC_WB + 24; i < NPC; ++i) pc[i] = 0.0;
+  if (!with_mass) {
+    // operator-only table (residual mode reads no omega / D): the diagonal without the mass term may vanish
+    for (int i = 0; i < 3; ++i) { pc[PC_W + i] = 0.0; pc[PC_FOLD + 12 + i] = 0.0; pc[PC_FOLD + 16 + 12 + i] = 0.0; }
+    for (int i = 0; i < 24; ++i) pc[PC_WB + i] = 0.0;
+  }
   return supported;
 }
 
@@ -564,6 +575,8 @@ bool xchg_kernel(const pamg_handle* h, const LevelDev& L) {
          h->kernel_mode == 4 && h->win_producer && L.s >= 6 && L.s <= 8;
 }
 
+int add_old_time_terms(pamg_handle* h);
+
 int launch_build_rhs(pamg_handle* h) {
   LevelDev& L = h->lev[0];
   RhsArgs a;
@@ -572,6 +585,7 @@ int launch_build_rhs(pamg_handle* h) {
   k_build_rhs<<<grid_for(h, L.nelem), TPB, 0, h->stream>>>(a);
   h->launches++;
   CK(cudaGetLastError());
+  if (L.pc_old) { int rc = add_old_time_terms(h); if (rc) return rc; }
   L.rhs_valid = true;
   return PAMG_OK;
 }
@@ -654,9 +668,12 @@ bool producer_kernel(const pamg_handle* h, const LevelDev& L, bool gs) {
 
 // use_strips: every strip of the level holds the start-of-sweep values (else: neighbour-field reads where possible);
 // write_next: the kernel's producer warp writes the strips of the next sweep into the other strip buffer
+// what a launch takes from somewhere else than the level's current state (the old-time pass of get_RHS, theta != 1)
+struct ElemOverride { const double* ovl; const double* pc; double rsign; };
+
 template <int MODE>
 int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout, int colour, int grid, bool use_strips,
-                   bool write_next = false, bool xchg = false, bool norm = false) {
+                   bool write_next = false, bool xchg = false, bool norm = false, const ElemOverride* ov = nullptr) {
   ElemArgs a;
   a.xsend = L.xsend; a.xsync = h->p2p_sync ? h->p2p_sync + (size_t)(&L - h->lev.data()) * P2P_WORDS : nullptr;
   if (MODE == MODE_RESID) xchg = false;     // a residual evaluation sends nothing
@@ -666,8 +683,9 @@ int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout,
   a.ovl_next = write_next ? L.ovlb[L.ovl_cur ^ 1] : nullptr; a.dst_strip = h->dst_strip; a.rev = h->rev; a.nstrips = h->plan.nstrips;
   a.partial = h->partial; a.omega = h->p.omega; a.rsign = (double)h->p.residual_sign; a.nelem = L.nelem; a.s = L.s;
   a.colour = colour; a.partial_off = 0;
+  if (ov) { a.ovl = ov->ovl; a.pc = ov->pc; a.rsign = ov->rsign; }
   const int f = h->p.face_terms ? 1 : 0;
-  const bool prof = h->profiling && h->pev_used + 2 <= (int)h->pev.size();
+  const bool prof = !ov && h->profiling && h->pev_used + 2 <= (int)h->pev.size();
   if (prof) CK(cudaEventRecord(h->pev[h->pev_used], h->stream));
   if (MODE != MODE_GS && h->kernel_mode == 4 && h->win_producer && L.s >= 6 && L.s <= 8) {
     // window kernel with a producer warp (no CTA-wide barrier between tiles)
@@ -701,6 +719,49 @@ int launch_element(pamg_handle* h, LevelDev& L, const double* Tin, double* Tout,
   if (prof) { CK(cudaEventRecord(h->pev[h->pev_used + 1], h->stream)); h->pev_used += 2; }
   h->launches++;
   CK(cudaGetLastError());
+  return PAMG_OK;
+}
+
+// told values of the level-1 faces cut by the GPU partition into the neighbours' told strips (the exchange that
+// update_overlaps as written makes for t_overlap_old, splitting.F90:1259-1262; see launch_halo, what = 0)
+int exchange_told_cut(pamg_handle* h) {
+  LevelDev& L = h->lev[0];
+  if (h->plan.peers.empty()) return PAMG_OK;
+  HaloArgs b;
+  b.tnew = L.told; b.told = L.told; b.ovl = L.ovl_old; b.ovl_old = L.ovl_old; b.xg = h->xg;
+  b.dst_strip = h->dst_strip; b.rev = h->rev; b.strip_of = h->strip_of;
+  b.bc_scale = 1.0; b.U = h->U; b.s = L.s; b.with_old = 0; b.what = 2; b.nstrips = h->plan.nstrips;
+  b.cut_lf = h->cut_lf; b.ncut = (int)h->plan.cut_lf.size();
+  b.bc_kind = h->bc_kind; b.bc_val = h->bc_val;
+  b.x.npeers = 0;
+  if (h->comm && h->p2p_enabled && !h->p2p_ready && !h->p2p_failed && !h->capturing && h->level_offset == 0) {
+    int rc = p2p_setup(h);      // collective, first exchange only
+    if (rc) return rc;
+  }
+  const bool fused_x = h->p2p_ready;
+  if (fused_x) { int rc = p2p_args(h, L, L.ovl_old, b.x); if (rc) return rc; }
+  int g2 = grid_for(h, (long long)b.ncut * L.S);
+  if (fused_x) g2 = std::min(g2, h->nsm * std::min(std::max(h->kc.halo, 1), 4));
+  k_halo<<<g2, TPB, 0, h->stream>>>(b);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (!fused_x) { int rc = exchange_halo_nccl(h, L, L.ovl_old); if (rc) return rc; }
+  if (fused_x) L.stage_valid = false;     // the staging buffers now hold told values under the current exchange number
+  return PAMG_OK;
+}
+
+// theta != 1: RHS -= (1 - theta)(-stiff + flux + diff_vol + diff_surf) told  (get_RHS :459-460).  One residual-mode pass of the
+// level-1 sweep kernel over TOLD with the old-time coefficient table: exterior values of faces between local parents straight
+// from TOLD, Dirichlet data and cut-face values from the told strips.  RES is the scratch field of the pass.
+int add_old_time_terms(pamg_handle* h) {
+  LevelDev& L = h->lev[0];
+  int rc;
+  if (h->p.face_terms && (rc = exchange_told_cut(h))) return rc;
+  const int grid = grid_for(h, L.nelem);
+  if (2 * grid > h->npartial) return fail(h, PAMG_ERR_STATE, "partial buffer too small");
+  const ElemOverride ov = {L.ovl_old, L.pc_old, -1.0};     // r = b - A_old told with b = the theta = 1 right-hand side
+  if ((rc = launch_element<MODE_RESID>(h, L, L.told, L.res, 0, grid, false, false, false, false, &ov))) return rc;
+  CK(cudaMemcpyAsync(L.rhs, L.res, (size_t)L.ndof * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   return PAMG_OK;
 }
 
@@ -1133,7 +1194,7 @@ void free_levels(pamg_handle* h) {
   h->vc_graphs.clear();
   for (auto& L : h->lev) {
     cudaFree(L.T[0]); cudaFree(L.T[1]); cudaFree(L.spare); cudaFree(L.told); cudaFree(L.rhs); cudaFree(L.res);
-    cudaFree(L.ovl_old); cudaFree(L.pc); cudaFree(L.xsend);
+    cudaFree(L.ovl_old); cudaFree(L.pc); cudaFree(L.pc_old); cudaFree(L.xsend);
   }
   h->lev.clear();
   cudaFree(h->strip_arena); h->strip_arena = nullptr; h->strip_arena_bytes = 0;
@@ -1187,7 +1248,7 @@ int pamg_create(const pamg_params* p, int device, pamg_handle** out) {
   if (!p || !out) return PAMG_ERR_ARG;
   *out = nullptr;
   if (p->n_split < 1 || p->n_split > 13 || p->multi_levels < 1 || p->multi_levels > p->n_split) return PAMG_ERR_ARG;  // :120-123
-  if (p->theta != 1.0) return PAMG_ERR_UNSUPPORTED;
+  if (!(p->theta >= 0.0 && p->theta <= 1.0)) return PAMG_ERR_ARG;
   if (!(p->dt > 0.0)) return PAMG_ERR_ARG;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return PAMG_ERR_CUDA;  // no CPU fallback
@@ -1441,10 +1502,17 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
     CK(cudaMemsetAsync(L.ovl_old, 0, ob, h->stream));  // :207
     L.ovl_cur = 0; L.strips_valid = false; L.cut_valid = false; L.stage_valid = false;
     for (int u = 0; u < U; ++u)
-      if (!parent_coefficients(h->p, X, neig, bc_glob, first + u, L.s, &pc[(size_t)u * NPC]))
+      if (!parent_coefficients(h->p, X, neig, bc_glob, first + u, L.s, &pc[(size_t)u * NPC], h->p.theta))
         return fail(h, PAMG_ERR_UNSUPPORTED, "open boundary face (kind 2) with inflow: give it Dirichlet data instead");
     CK(cudaMalloc(&L.pc, pc.size() * sizeof(double)));
     CK(cudaMemcpy(L.pc, pc.data(), pc.size() * sizeof(double), cudaMemcpyHostToDevice));
+    if (il == 0 && h->p.theta != 1.0 && h->level_offset == 0) {
+      // old-time operator of get_RHS (:459-460), applied to TOLD when the level-1 right-hand side is built
+      for (int u = 0; u < U; ++u)
+        parent_coefficients(h->p, X, neig, bc_glob, first + u, L.s, &pc[(size_t)u * NPC], 1.0 - h->p.theta, false);
+      CK(cudaMalloc(&L.pc_old, pc.size() * sizeof(double)));
+      CK(cudaMemcpy(L.pc_old, pc.data(), pc.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     L.cur = 0; L.tnew_alias = true; L.rhs_valid = (il != 0);
   }
   // Dirichlet data sin(x+y) on domain-boundary faces never changes: fill those strips once per level
@@ -1455,6 +1523,15 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
       if (rc2) return rc2;
     }
   for (auto& Lv : h->lev) Lv.ovl_cur = 0;
+  if (h->lev[0].pc_old) {
+    // ... and in the told strips of level 1, which the old-time face terms read (theta != 1)
+    LevelDev& L1 = h->lev[0];
+    double* keep = L1.ovlb[0];
+    L1.ovlb[0] = L1.ovl_old;
+    int rc2 = launch_halo(h, 1, 1);
+    L1.ovlb[0] = keep;
+    if (rc2) return rc2;
+  }
   // coarse-level agglomeration on part 0: first level whose GLOBAL size is small enough to be launch-bound
   if (nparts > 1 && h->level_offset == 0) {
     const char* e = getenv("PAMG_AGG_ELEMS");

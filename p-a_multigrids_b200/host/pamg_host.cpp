@@ -24,7 +24,7 @@ struct Args {
   bool literal = true;             // HEAD behaviour (mode 9 default) or --intended
   int n_split = 1, multi_levels = 1, solver = 3, n_smooth = 4, n_multigrid = 2, ntime = 2;
   int region = -1;                 // IC T = 1 where region_id == region (4 for test_sn2, 12 in unstr_explicit)
-  double cfl = -1, dx = -1, ux = 0, uy = 0, k = 1.0, tol = 1e-8;
+  double cfl = -1, dx = -1, ux = 0, uy = 0, k = 1.0, tol = 1e-8, theta = 1.0;
   int nits = 2, njac = 10, exact_minv = 0, use_dir = 0, max_cycles = 50;
   int device = 0;
   std::vector<int> devices;        // --gpus N / --devices a,b,..: this ONE process drives several GPUs (pamg_create_multi)
@@ -67,6 +67,7 @@ int main(int argc, char** argv) {
     else if (flag(i, argc, argv, "--ux", v)) a.ux = std::atof(v.c_str());
     else if (flag(i, argc, argv, "--uy", v)) a.uy = std::atof(v.c_str());
     else if (flag(i, argc, argv, "--k", v)) a.k = std::atof(v.c_str());
+    else if (flag(i, argc, argv, "--theta", v)) a.theta = std::atof(v.c_str());   // transport_tri_semi.F90:117 (literal 1.)
     else if (flag(i, argc, argv, "--nits", v)) a.nits = std::atoi(v.c_str());
     else if (flag(i, argc, argv, "--njac_its", v)) a.njac = std::atoi(v.c_str());
     else if (flag(i, argc, argv, "--exact_minv", v)) a.exact_minv = std::atoi(v.c_str());
@@ -139,7 +140,7 @@ int main(int argc, char** argv) {
   pamg_params p;
   pamg_default_params(&p, a.literal ? 1 : 0);
   p.n_split = a.n_split; p.multi_levels = a.multi_levels; p.solver = a.solver; p.n_smooth = a.n_smooth;
-  p.n_multigrid = a.n_multigrid; p.dt = a.cfl * a.dx; p.k = a.k; p.u_x = a.ux; p.u_y = a.uy;
+  p.n_multigrid = a.n_multigrid; p.dt = a.cfl * a.dx; p.k = a.k; p.u_x = a.ux; p.u_y = a.uy; p.theta = a.theta;
   p.source_coef = (a.literal ? -2.0 : 2.0) * a.k;
   pamg_handle* h = nullptr;
   // the reference's driver is one serial process (main.F90:16-51): with --gpus N the same single host thread drives N
