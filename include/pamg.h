@@ -155,6 +155,18 @@ int pamg_smoother_host(pamg_handle* h, int solver, int nsweeps, const double* tn
  * entry that reads or writes level-1 fields must be preceded by pamg_sync. */
 int pamg_smooth_host(pamg_handle* h, int solver, int nsweeps, const double* tnew_in, double* tnew_out);
 
+/* host-only (no CUDA needed): the folded operator of ONE parent on the level with split s - the table the sweep kernels read.
+ * It replaces the per-sweep stencil set-up of get_un_ele_mass_stiff_diffvol / get_diff_surf_stencl / get_diagonal
+ * (ShapFun_unstruc.F90:304-335, transport_tri_semi.F90:468-486,575-609) with closed forms evaluated once per parent and level.
+ * table[88]: [0] A/(12 dt); [1..6] K11 K12 K13 K22 K23 K33; [7..9] advection; [10..12] upwind flux per child face;
+ * [13..15] / [19..21] penalty of faces inside / on the boundary of the parent; [16..18] omega/D of interior children;
+ * [24..39], [40..55] folded 3x3 operator + 3 neighbour couplings + omega/D of up / down children; [56..58] penalty change and
+ * [60..83] omega/D per face mask for children on parent faces.  parent is 0-based; bc_kind may be NULL (pamg_set_boundary_data);
+ * theta_weight multiplies every spatial term (p->theta for the operator of the sweeps, 1 - p->theta with with_mass = 0 for the
+ * old-time branch of get_RHS).  Returns PAMG_ERR_UNSUPPORTED for an open boundary face with inflow. */
+int pamg_parent_table(const pamg_params* p, int U, const double* X, const int32_t* neig, const int32_t* bc_kind, int parent,
+                      int s, double theta_weight, int with_mass, double* table);
+
 /* ---- distributed halo (update_overlaps across GPUs; Generic.F90:387-401 sketches the block partition) -- */
 /* host-only: where every halo strip lives and how cut faces are ordered per peer (no CUDA needed).
  * arrays are [U_local*3]; peers is [npeers][4] = part, nfaces, strip_begin, send_begin;

@@ -1567,6 +1567,13 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
   return PAMG_OK;
 }
 
+int pamg_parent_table(const pamg_params* p, int U, const double* X, const int32_t* neig, const int32_t* bc_kind, int parent,
+                      int s, double theta_weight, int with_mass, double* table) {
+  if (!p || !X || !neig || !table || U < 1 || parent < 0 || parent >= U || s < 0 || s > 13 || !(p->dt > 0.0)) return PAMG_ERR_ARG;
+  for (int f = 0; f < 3; ++f) { const int q = neig[(size_t)parent * 3 + f]; if (q < 0 || q > U) return PAMG_ERR_ARG; }
+  return parent_coefficients(*p, X, neig, bc_kind, parent, s, table, theta_weight, with_mass != 0) ? PAMG_OK : PAMG_ERR_UNSUPPORTED;
+}
+
 int pamg_set_boundary_data(pamg_handle* h, int U_global, const int32_t* kind, const double* value) {
   if (!h || U_global < 1 || !kind) return PAMG_ERR_ARG;
   for (size_t i = 0; i < (size_t)U_global * 3; ++i)

@@ -94,6 +94,7 @@ def lib():
         "pamg_timestep_host": (ci, [vp, vp, vp, ci, cd, pint, pdbl]),
         "pamg_smooth_host": (ci, [vp, ci, ci, vp, vp]),
         "pamg_smoother_host": (ci, [vp, ci, ci, vp, vp]),
+        "pamg_parent_table": (ci, [C.POINTER(Params), ci, _f64, _i32, vp, ci, ci, cd, ci, _f64]),
         "pamg_halo_plan": (ci, [ci, _f64, _i32, _i32, _i32, ci, ci, _i32, ci, _i32, _i32, _i32, _i32, _i32, _i32]),
         "pamg_comm_unique_id": (ci, [C.c_char_p]),
         "pamg_comm_init": (ci, [vp, C.c_char_p, ci, ci]),
@@ -230,6 +231,17 @@ def halo_plan(mesh, halo_rule=1, nparts=1, part_first=None, my_part=0):
         raise PamgError(rc, "pamg_halo_plan")
     out["peers"] = peers.reshape(-1, 4)[: counts[0]].copy()
     out["nstrips"], out["nsend"], out["U_local"], out["first"] = (int(c) for c in counts[1:5])
+    return out
+
+
+def parent_table(params, mesh, parent, s, theta_weight=None, with_mass=True, bc_kind=None):
+    """Host-only: the 88 folded coefficients of parent `parent` (0-based) on the level with split s (pamg_parent_table)."""
+    out = np.zeros(88)
+    bk = None if bc_kind is None else np.ascontiguousarray(bc_kind, np.int32)
+    rc = lib().pamg_parent_table(C.byref(params), mesh.U, mesh.X, mesh.neig, _ptr(bk), parent, s,
+                                 params.theta if theta_weight is None else theta_weight, 1 if with_mass else 0, out)
+    if rc != OK:
+        raise PamgError(rc, "pamg_parent_table")
     return out
 
 
