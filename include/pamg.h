@@ -167,6 +167,15 @@ int pamg_smooth_host(pamg_handle* h, int solver, int nsweeps, const double* tnew
 int pamg_parent_table(const pamg_params* p, int U, const double* X, const int32_t* neig, const int32_t* bc_kind, int parent,
                       int s, double theta_weight, int with_mass, double* table);
 
+/* host-only (no CUDA needed): the closed-form child numbering of the kernels, which replaces the tables of get_str_info,
+ * get_str_neig_multigrid and element_conversion (Msh2Tri.F90:32-60, splitting.F90:97-140,732-776).  The SAME functions are
+ * compiled for the device; this entry evaluates them on the host for indices first .. first+count-1, out is [count][4]:
+ *   what 0: child k (0-based, memory order = element id - 1) at split s -> row, position, row length, 0   (child_from_ele0)
+ *   what 1: paired-row index t (rows r and 2^s+1-r share 2^(s+1) slots) -> row, position, element id (1-based), row length
+ *   what 2: coarse child k (0-based) at split s -> element ids (1-based) of its four fine children fin(1..4) at split s+1
+ *   what 3: row, position of child k + 256 obtained by WALKING from those of child k (child_advance), row length, 0 */
+int pamg_numbering(int what, int s, int64_t first, int64_t count, int32_t* out);
+
 /* ---- distributed halo (update_overlaps across GPUs; Generic.F90:387-401 sketches the block partition) -- */
 /* host-only: where every halo strip lives and how cut faces are ordered per peer (no CUDA needed).
  * arrays are [U_local*3]; peers is [npeers][4] = part, nfaces, strip_begin, send_begin;

@@ -1567,6 +1567,28 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
   return PAMG_OK;
 }
 
+int pamg_numbering(int what, int s, int64_t first, int64_t count, int32_t* out) {
+  if (!out || s < 1 || s > 13 || what < 0 || what > 3 || first < 0 || count < 0) return PAMG_ERR_ARG;
+  const int64_t C = (int64_t)1 << (2 * s);
+  if (first + count > C) return PAMG_ERR_ARG;
+  const int b = 2 << s;
+  for (int64_t i = 0; i < count; ++i) {
+    const int k = (int)(first + i);
+    int32_t* o = out + 4 * i;
+    int r = 0, ipos = 0, ele = 0, len = 0;
+    if (what == 0) { child_from_ele0(k, s, r, ipos, len); o[0] = r; o[1] = ipos; o[2] = len; o[3] = 0; }
+    else if (what == 1) { child_from_flat(k, s, r, ipos, ele, len); o[0] = r; o[1] = ipos; o[2] = ele; o[3] = len; }
+    else if (what == 2) { int fin[4]; child_from_ele0(k, s, r, ipos, len); fine_children(s, r, ipos, fin); for (int q = 0; q < 4; ++q) o[q] = fin[q]; }
+    else {
+      if (k + TPB >= C) { o[0] = o[1] = o[2] = o[3] = 0; continue; }
+      child_from_ele0(k, s, r, ipos, len);
+      child_advance(s, b, k + TPB, r, ipos);
+      o[0] = r; o[1] = ipos; o[2] = b + 1 - 2 * r; o[3] = 0;
+    }
+  }
+  return PAMG_OK;
+}
+
 int pamg_parent_table(const pamg_params* p, int U, const double* X, const int32_t* neig, const int32_t* bc_kind, int parent,
                       int s, double theta_weight, int with_mass, double* table) {
   if (!p || !X || !neig || !table || U < 1 || parent < 0 || parent >= U || s < 0 || s > 13 || !(p->dt > 0.0)) return PAMG_ERR_ARG;

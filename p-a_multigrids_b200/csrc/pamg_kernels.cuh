@@ -106,7 +106,7 @@ struct ElemArgs {
 };
 
 // flat child index t in [0, 4^s) -> row r (1-based), position ipos (1-based), element id ele (1-based)
-__device__ __forceinline__ void child_from_flat(int t, int s, int& r, int& ipos, int& ele, int& len) {
+__host__ __device__ __forceinline__ void child_from_flat(int t, int s, int& r, int& ipos, int& ele, int& len) {
   const int b = 2 << s;            // 2^(s+1)
   const int S = 1 << s;
   const int p = t >> (s + 1);
@@ -295,7 +295,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // memory-order child index k (0-based) -> row, position.  Row r starts at m(b-m), m = r-1; the float sqrt
 // guess is off by at most one, fixed with two predicated corrections (no loops, no divergence).
-__device__ __forceinline__ void child_from_ele0(int k, int s, int& r, int& ipos, int& len) {
+__host__ __device__ __forceinline__ void child_from_ele0(int k, int s, int& r, int& ipos, int& len) {
   const int b = 2 << s, S = 1 << s;
   int m = (int)(((float)b - sqrtf((float)(b * b - 4 * k))) * 0.5f);
   m = max(0, min(m, S - 1));
@@ -310,7 +310,7 @@ __device__ __forceinline__ void child_from_ele0(int k, int s, int& r, int& ipos,
 // numbering of "my child of the next tile" from that of the current one: TPB positions further along the rows of the
 // parent.  Rows are at least TPB long except near the apex, so the loop usually runs zero or one time; the closed form
 // (with its square root) is only needed when the walk enters the next parent.
-__device__ __forceinline__ void child_advance(int s, int b, int k_next, int& r, int& ipos) {
+__host__ __device__ __forceinline__ void child_advance(int s, int b, int k_next, int& r, int& ipos) {
   if (k_next < TPB) { int len; child_from_ele0(k_next, s, r, ipos, len); return; }   // first tile of a parent (uniform)
   ipos += TPB;
   int len = b + 1 - 2 * r;
@@ -1862,7 +1862,7 @@ __global__ void __launch_bounds__(TPB) k_build_rhs(RhsArgs a) {
 // ------------------------------------------------------------------------------------------------
 // restrictor (splitting.F90:10-32) / its INTENDED form (transpose of P1 interpolation).
 // One thread per COARSE child; fine ids from the closed form of element_conversion (:105-139).
-__device__ __forceinline__ void fine_children(int sc, int r, int ipos, int fin[4]) {
+__host__ __device__ __forceinline__ void fine_children(int sc, int r, int ipos, int fin[4]) {
   const int bf = 4 << sc;  // 2^(sf+1), sf = sc+1
   auto start_f = [&](int rf) { return 1 + (rf - 1) * (bf + 1 - rf); };
   if (ipos & 1) {

@@ -94,6 +94,7 @@ def lib():
         "pamg_timestep_host": (ci, [vp, vp, vp, ci, cd, pint, pdbl]),
         "pamg_smooth_host": (ci, [vp, ci, ci, vp, vp]),
         "pamg_smoother_host": (ci, [vp, ci, ci, vp, vp]),
+        "pamg_numbering": (ci, [ci, ci, C.c_int64, C.c_int64, _i32]),
         "pamg_parent_table": (ci, [C.POINTER(Params), ci, _f64, _i32, vp, ci, ci, cd, ci, _f64]),
         "pamg_halo_plan": (ci, [ci, _f64, _i32, _i32, _i32, ci, ci, _i32, ci, _i32, _i32, _i32, _i32, _i32, _i32]),
         "pamg_comm_unique_id": (ci, [C.c_char_p]),
@@ -231,6 +232,17 @@ def halo_plan(mesh, halo_rule=1, nparts=1, part_first=None, my_part=0):
         raise PamgError(rc, "pamg_halo_plan")
     out["peers"] = peers.reshape(-1, 4)[: counts[0]].copy()
     out["nstrips"], out["nsend"], out["U_local"], out["first"] = (int(c) for c in counts[1:5])
+    return out
+
+
+def numbering(what, s, first=0, count=None):
+    """Host-only: the closed-form child numbering of the kernels (pamg_numbering), int32 array [count][4]."""
+    if count is None:
+        count = 4 ** s - first
+    out = np.zeros((count, 4), np.int32)
+    rc = lib().pamg_numbering(what, s, first, count, out)
+    if rc != OK:
+        raise PamgError(rc, "pamg_numbering")
     return out
 
 
