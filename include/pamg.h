@@ -183,6 +183,13 @@ int pamg_numbering(int what, int s, int64_t first, int64_t count, int32_t* out);
 int pamg_halo_plan(int U_global, const double* X, const int32_t* neig, const int32_t* fneig, const int32_t* dir,
                    int halo_rule, int nparts, const int32_t* part_first, int my_part, int32_t* strip_of,
                    int32_t* dst_strip, int32_t* rev, int32_t* hmap, int32_t* peers, int32_t* counts);
+/* host-only: where a sweep reads the exterior values of the parent faces of part my_part WITHOUT a halo strip, on the level with
+ * split s.  src is [U_local*3][2**s][2]: for (parent, gmsh side, strip position) the offsets (in doubles, inside the part's
+ * field T(3, C, U_local)) of the neighbour's values at the nodes coincident with my face nodes (a, b) - what update_overlaps
+ * (splitting.F90:1255-1391) would have copied into my strip and the face block would pick out of it - or -1, -1 where the values
+ * come from a strip (Dirichlet data, faces cut by the partition).  The decoding is the function the kernels use. */
+int pamg_halo_sources(int U_global, const double* X, const int32_t* neig, const int32_t* fneig, const int32_t* dir,
+                      int halo_rule, int nparts, const int32_t* part_first, int my_part, int s, int64_t* src);
 int pamg_comm_unique_id(char* id128);                        /* rank 0: ncclGetUniqueId */
 int pamg_comm_init(pamg_handle* h, const char* id128, int nranks, int rank);
 int pamg_halo_peer_count(const pamg_handle* h, int* npeers);

@@ -1567,6 +1567,25 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
   return PAMG_OK;
 }
 
+int pamg_halo_sources(int U_global, const double* X, const int32_t* neig, const int32_t* fneig, const int32_t* dir,
+                      int halo_rule, int nparts, const int32_t* part_first, int my_part, int s, int64_t* src) {
+  if (!src || s < 1 || s > 13) return PAMG_ERR_ARG;
+  HaloPlan plan;
+  int rc = build_halo_plan(U_global, X, neig, fneig, dir, halo_rule, nparts, part_first, my_part, plan);
+  if (rc != PAMG_OK) return rc;
+  const int S = 1 << s;
+  for (int lf = 0; lf < plan.U_local * 3; ++lf) {
+    const int d = plan.nsrc[lf];
+    for (int p = 0; p < S; ++p) {
+      int64_t* o = src + ((size_t)lf * S + p) * 2;
+      if (d < 0) { o[0] = o[1] = -1; continue; }
+      const size_t base = nbr_child_offset(d, p, s);
+      o[0] = (int64_t)(base + (d & 3)); o[1] = (int64_t)(base + ((d >> 2) & 3));
+    }
+  }
+  return PAMG_OK;
+}
+
 int pamg_numbering(int what, int s, int64_t first, int64_t count, int32_t* out) {
   if (!out || s < 1 || s > 13 || what < 0 || what > 3 || first < 0 || count < 0) return PAMG_ERR_ARG;
   const int64_t C = (int64_t)1 << (2 * s);

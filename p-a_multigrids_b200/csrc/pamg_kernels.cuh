@@ -200,14 +200,18 @@ __device__ __forceinline__ void elem_apply(const double* __restrict__ pc, bool u
 // of the neighbour parent's boundary children from the start-of-sweep field into my strip; a sweep that writes to another
 // buffer (Jacobi, Richardson, residual, the one-pass coloured GS) can read those same values straight from that field.
 // d = HaloPlan::nsrc (>= 0): nodes | reversal << 4 | (Nside-1) << 5 | neighbour parent << 7; p = my 0-based strip position.
-__device__ __forceinline__ void nbr_pair(const double* __restrict__ T, int d, int p, int s, double& va, double& vb) {
+// offset (in doubles, inside the level's field) of the neighbour parent's boundary child that faces my strip position p
+__host__ __device__ __forceinline__ size_t nbr_child_offset(int d, int p, int s) {
   const int S = 1 << s, b = 2 << s;
   const int m = (d & 16) ? (S - 1 - p) : p;              // the neighbour's own position along the shared edge
   const int ns = (d >> 5) & 3;
   // its boundary child there (surf_ele, splitting.F90:434-449), 0-based in memory order: side 1 = odd children of row 1,
   // side 3 = first child of row m+1, side 2 = last child of row m+1; row m+1 starts at m (b - m)
   const int e0 = (ns == 0) ? 2 * m : (m * (b - m) + (ns == 1 ? b - 2 - 2 * m : 0));
-  const size_t o = ((((size_t)(d >> 7)) << (2 * s)) + (size_t)e0) * 3;
+  return ((((size_t)(d >> 7)) << (2 * s)) + (size_t)e0) * 3;
+}
+__device__ __forceinline__ void nbr_pair(const double* __restrict__ T, int d, int p, int s, double& va, double& vb) {
+  const size_t o = nbr_child_offset(d, p, s);
   va = __ldg(T + o + (d & 3)); vb = __ldg(T + o + ((d >> 2) & 3));
 }
 

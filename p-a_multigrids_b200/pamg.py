@@ -94,6 +94,8 @@ def lib():
         "pamg_timestep_host": (ci, [vp, vp, vp, ci, cd, pint, pdbl]),
         "pamg_smooth_host": (ci, [vp, ci, ci, vp, vp]),
         "pamg_smoother_host": (ci, [vp, ci, ci, vp, vp]),
+        "pamg_halo_sources": (ci, [ci, _f64, _i32, _i32, _i32, ci, ci, _i32, ci, ci,
+                                   np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]),
         "pamg_numbering": (ci, [ci, ci, C.c_int64, C.c_int64, _i32]),
         "pamg_parent_table": (ci, [C.POINTER(Params), ci, _f64, _i32, vp, ci, ci, cd, ci, _f64]),
         "pamg_halo_plan": (ci, [ci, _f64, _i32, _i32, _i32, ci, ci, _i32, ci, _i32, _i32, _i32, _i32, _i32, _i32]),
@@ -232,6 +234,18 @@ def halo_plan(mesh, halo_rule=1, nparts=1, part_first=None, my_part=0):
         raise PamgError(rc, "pamg_halo_plan")
     out["peers"] = peers.reshape(-1, 4)[: counts[0]].copy()
     out["nstrips"], out["nsend"], out["U_local"], out["first"] = (int(c) for c in counts[1:5])
+    return out
+
+
+def halo_sources(mesh, s, halo_rule=1, nparts=1, part_first=None, my_part=0):
+    """Host-only: offsets of the strip-free exterior values, int64 [U_local, 3, 2**s, 2] (pamg_halo_sources)."""
+    U = mesh.U
+    pf = np.ascontiguousarray(part_first if part_first is not None else [0, U], np.int32)
+    ul = int(pf[my_part + 1] - pf[my_part])
+    out = np.zeros((ul, 3, 2 ** s, 2), np.int64)
+    rc = lib().pamg_halo_sources(U, mesh.X, mesh.neig, mesh.fneig, mesh.dir, halo_rule, nparts, pf, my_part, s, out)
+    if rc != OK:
+        raise PamgError(rc, "pamg_halo_sources")
     return out
 
 

@@ -23,6 +23,7 @@ NULLABLE = {"part_first", "region", "devices", "value", "val", "col", "diff_coe"
             "Minv", "status", "rhs", "x", "hist", "strip_of", "dst_strip", "rev", "hmap", "peers", "counts", "X_out", "bc_kind"}
 NULLABLE_IN = {"pamg_mesh_get": {"X", "neig", "fneig", "dir", "region"},
                "pamg_halo_plan": {"part_first", "strip_of", "dst_strip", "rev", "hmap", "peers", "counts"},
+               "pamg_halo_sources": {"part_first"},
                "pamg_apply_local_minv": {"rhs", "x", "Minv", "status"},
                "pamg_trans_rec": {"x_all"}, "pamg_create_multi": {"devices"},
                "pamg_set_parents_partition": {"part_first"}, "pamg_mesh_from_arrays": {"region"},
