@@ -26,6 +26,9 @@ struct Args {
   int region = -1;                 // IC T = 1 where region_id == region (4 for test_sn2, 12 in unstr_explicit)
   double cfl = -1, dx = -1, ux = 0, uy = 0, k = 1.0, tol = 1e-8, theta = 1.0;
   int nits = 2, njac = 10, exact_minv = 0, use_dir = 0, max_cycles = 50;
+  bool ntime_given = false, k_given = false, tol_given = false;
+  int ner = 20, nec = 2, max_iters = 500;   // str_explicit: no_ele_row, no_ele_col (main.F90:22); Krylov iterations per implicit solve
+  double dy = -1;
   int device = 0;
   std::vector<int> devices;        // --gpus N / --devices a,b,..: this ONE process drives several GPUs (pamg_create_multi)
 };
@@ -60,19 +63,23 @@ int main(int argc, char** argv) {
     else if (flag(i, argc, argv, "--solver", v)) a.solver = std::atoi(v.c_str());
     else if (flag(i, argc, argv, "--n_smooth", v)) a.n_smooth = std::atoi(v.c_str());
     else if (flag(i, argc, argv, "--n_multigrid", v)) a.n_multigrid = std::atoi(v.c_str());
-    else if (flag(i, argc, argv, "--ntime", v)) a.ntime = std::atoi(v.c_str());
+    else if (flag(i, argc, argv, "--ntime", v)) { a.ntime = std::atoi(v.c_str()); a.ntime_given = true; }
+    else if (flag(i, argc, argv, "--no_ele_row", v)) a.ner = std::atoi(v.c_str());
+    else if (flag(i, argc, argv, "--no_ele_col", v)) a.nec = std::atoi(v.c_str());
+    else if (flag(i, argc, argv, "--dy", v)) a.dy = std::atof(v.c_str());
+    else if (flag(i, argc, argv, "--max_iters", v)) a.max_iters = std::atoi(v.c_str());
     else if (flag(i, argc, argv, "--region", v)) a.region = std::atoi(v.c_str());
     else if (flag(i, argc, argv, "--cfl", v)) a.cfl = std::atof(v.c_str());
     else if (flag(i, argc, argv, "--dx", v)) a.dx = std::atof(v.c_str());
     else if (flag(i, argc, argv, "--ux", v)) a.ux = std::atof(v.c_str());
     else if (flag(i, argc, argv, "--uy", v)) a.uy = std::atof(v.c_str());
-    else if (flag(i, argc, argv, "--k", v)) a.k = std::atof(v.c_str());
+    else if (flag(i, argc, argv, "--k", v)) { a.k = std::atof(v.c_str()); a.k_given = true; }
     else if (flag(i, argc, argv, "--theta", v)) a.theta = std::atof(v.c_str());   // transport_tri_semi.F90:117 (literal 1.)
     else if (flag(i, argc, argv, "--nits", v)) a.nits = std::atoi(v.c_str());
     else if (flag(i, argc, argv, "--njac_its", v)) a.njac = std::atoi(v.c_str());
     else if (flag(i, argc, argv, "--exact_minv", v)) a.exact_minv = std::atoi(v.c_str());
     else if (flag(i, argc, argv, "--use_dir", v)) a.use_dir = std::atoi(v.c_str());
-    else if (flag(i, argc, argv, "--tol", v)) a.tol = std::atof(v.c_str());
+    else if (flag(i, argc, argv, "--tol", v)) { a.tol = std::atof(v.c_str()); a.tol_given = true; }
     else if (flag(i, argc, argv, "--max_cycles", v)) a.max_cycles = std::atoi(v.c_str());
     else if (flag(i, argc, argv, "--device", v)) a.device = std::atoi(v.c_str());
     else if (flag(i, argc, argv, "--gpus", v)) { a.devices.clear(); for (int d = 0; d < std::atoi(v.c_str()); ++d) a.devices.push_back(d); }
@@ -85,6 +92,10 @@ int main(int argc, char** argv) {
   // literal defaults of main.F90:28 (mode 4) and :46-47 (mode 9)
   if (a.mode == 4) { if (a.cfl < 0) a.cfl = 0.07; if (a.dx < 0) a.dx = 1e-3; if (a.region < 0) a.region = 12; if (a.ux == 0 && a.uy == 0) a.ux = 0.9; }
   else if (a.mode == 1) { if (a.cfl < 0) a.cfl = 0.7; }
+  // main.F90:22 str_explicit(0.7, ..., njac_its 10, nits 2, no_ele_row 20, no_ele_col 2, dx 0.1, dy 0.1, u 0.05 0.05); ntime = 100 (transport_tri.F90:469)
+  else if (a.mode == 2) { if (a.cfl < 0) a.cfl = 0.7; if (a.dx < 0) a.dx = 0.1; if (a.ux == 0 && a.uy == 0) { a.ux = 0.05; a.uy = 0.05; } if (!a.ntime_given) a.ntime = 100; }
+  // main.F90:31 unstr_implicit(.7, ..., time .7*.1*2, nits 2, dx 0.1, u -.1 .1) on Mesh_files/gmsh_100.msh: dt = CFL dx, ntime = time / dt = 2
+  else if (a.mode == 5) { if (a.cfl < 0) a.cfl = 0.7; if (a.dx < 0) a.dx = 0.1; if (a.ux == 0 && a.uy == 0) { a.ux = -0.1; a.uy = 0.1; } }
   else { if (a.cfl < 0) a.cfl = 1.0; if (a.dx < 0) a.dx = a.literal ? 1.25e-5 : 1e-3; if (a.region < 0) a.region = 4; }
 
   if (a.mode == 1) {
@@ -127,7 +138,9 @@ int main(int argc, char** argv) {
   std::printf("---------------------------------------------------------\n|       Reading the .msh file     |\n");
   const double t0 = now();
   pamg_mesh* mesh = nullptr;
-  int rc = a.kp >= 0 ? pamg_mesh_synthetic(a.kp, a.G, &mesh) : pamg_mesh_read_msh(a.mesh.c_str(), &mesh);
+  // str_explicit: totele = no_ele_row * no_ele_col * 2 (transport_tri.F90:400), no_ele_row triangles per row (str_tri_X_nodes)
+  int rc = a.mode == 2 ? pamg_mesh_structured_tri(a.ner, 2 * a.nec, a.dx, a.dy > 0 ? a.dy : a.dx, &mesh)
+           : a.kp >= 0 ? pamg_mesh_synthetic(a.kp, a.G, &mesh) : pamg_mesh_read_msh(a.mesh.c_str(), &mesh);
   if (rc != PAMG_OK) { std::fprintf(stderr, "cannot read mesh '%s' (%d)\n", a.mesh.c_str(), rc); return 1; }
   int U = 0;
   pamg_mesh_size(mesh, &U);
@@ -207,8 +220,52 @@ int main(int argc, char** argv) {
     double sum = 0, mx = -1e300, mn = 1e300;
     for (double v : T) { sum += v; mx = std::fmax(mx, v); mn = std::fmin(mn, v); }
     std::printf("cpu_time for time_loop = %g\ntnew: sum %.12e min %.6e max %.6e\n", t2 - t1, sum, mn, mx);
+  } else if (a.mode == 2) {
+    // str_explicit (transport_tri.F90:354): the structured triangles through the same explicit step; t_bc = 0, u_bc = u
+    // (:438-440,465); initial pulse as at :457-460 (the first no_ele_row/5 + 1 elements of row 1, the first fifth of every
+    // other row)
+    if ((rc = pamg_set_unstructured(h, U, X.data(), neig.data(), fneig.data()))) return die(h, "pamg_set_unstructured", rc);
+    std::vector<double> T((size_t)U * 3, 0.0);
+    auto one = [&](int e1) { if (e1 >= 1 && e1 <= U) T[3 * (e1 - 1)] = T[3 * (e1 - 1) + 1] = T[3 * (e1 - 1) + 2] = 1.0; };
+    for (int e = 1; e <= a.ner / 5 + 1; ++e) one(e);
+    for (int i = 2; i <= a.nec; ++i) for (int e = (i - 1) * a.ner + 1; e <= a.ner * i - (a.ner * 4 / 5); ++e) one(e);
+    std::printf("totele = %d\nntime = %d\n", U, a.ntime);
+    if ((rc = pamg_unstr_upload(h, T.data()))) return die(h, "upload", rc);
+    pamg_sync(h);
+    const double t1 = now();
+    if ((rc = pamg_explicit_step(h, a.cfl * a.dx, a.ux, a.uy, 0.0, a.ntime, a.nits, a.njac, a.exact_minv, 0)))
+      return die(h, "pamg_explicit_step", rc);
+    pamg_sync(h);
+    const double t2 = now();
+    pamg_unstr_download(h, T.data());
+    double sum = 0, mx = -1e300, mn = 1e300;
+    for (double v : T) { sum += v; mx = std::fmax(mx, v); mn = std::fmin(mn, v); }
+    std::printf("cpu_time for time_loop = %g\ntnew: sum %.12e min %.6e max %.6e\n", t2 - t1, sum, mn, mx);
+  } else if (a.mode == 5) {
+    // unstr_implicit (transport_tri_unstr.F90:7-408): block-CSR operator on the device instead of three CSR matrices -> dense
+    // -> FINDInv (:366-378), a Krylov solve per nonlinear pass; IC tnew(:,5) = 1 (:163) unless --region selects elements
+    if ((rc = pamg_set_unstructured(h, U, X.data(), neig.data(), fneig.data()))) return die(h, "pamg_set_unstructured", rc);
+    std::vector<double> T((size_t)U * 3, 0.0);
+    if (a.region >= 0) { for (int e = 0; e < U; ++e) if (region[e] == a.region) T[3 * e] = T[3 * e + 1] = T[3 * e + 2] = 1.0; }
+    else if (U >= 5) T[12] = T[13] = T[14] = 1.0;
+    std::printf("totele = %d\nntime = %d\n", U, a.ntime);
+    const double dt = a.cfl * a.dx;
+    if ((rc = a.k_given ? pamg_implicit_assemble_diffusion(h, dt, a.ux, a.uy, a.k, a.use_dir) : pamg_implicit_assemble(h, dt, a.ux, a.uy, a.use_dir)))
+      return die(h, "pamg_implicit_assemble", rc);
+    if ((rc = pamg_unstr_upload(h, T.data()))) return die(h, "upload", rc);
+    pamg_sync(h);
+    const double t1 = now();
+    int iters = 0; double relres = 0.0;
+    if ((rc = pamg_implicit_step(h, a.ntime, a.nits, a.tol_given ? a.tol : 1e-13, a.max_iters, &iters, &relres))) return die(h, "pamg_implicit_step", rc);
+    pamg_sync(h);
+    const double t2 = now();
+    pamg_unstr_download(h, T.data());
+    double sum = 0, mx = -1e300, mn = 1e300;
+    for (double v : T) { sum += v; mx = std::fmax(mx, v); mn = std::fmin(mn, v); }
+    std::printf("Krylov iterations %d  worst ||r||/||b|| %.3e\ncpu_time for time_loop = %g\ntnew: sum %.12e min %.6e max %.6e\n",
+                iters, relres, t2 - t1, sum, mn, mx);
   } else {
-    std::fprintf(stderr, "mode %d is outside the hot path (modes 1, 4 and 9 are implemented; see DESIGN.md)\n", a.mode);
+    std::fprintf(stderr, "mode %d is outside the hot path (modes 1, 2, 4, 5 and 9 are implemented; see DESIGN.md)\n", a.mode);
     pamg_destroy(h);
     return 2;
   }

@@ -1,4 +1,4 @@
-"""The C++ host driver (pamg_host, mirror of main.F90 modes 4 and 9) against the oracle."""
+"""The C++ host driver (pamg_host, mirror of main.F90 modes 1, 2, 4, 5 and 9) against the oracle."""
 import os
 import re
 import subprocess
@@ -62,6 +62,40 @@ def test_mode4_unstr_explicit(tmp_path):
     orc.lib().orc_unstr_explicit(mesh.U, mesh.X, mesh.neig, mesh.fneig, mesh.dir, 0.9, 0.0, 0.07e-3, 2, 2, 10, 0, 0, 0.0, T)
     assert abs(float(m.group(1)) - T.sum()) <= 1e-9 * abs(T.sum())
     assert "totele = 8192" in out
+
+
+def test_mode2_str_explicit_literal_arguments():
+    """pamg_host --mode 2 = case(2) of main.F90:22: str_explicit(0.7, ..., njac_its 10, nits 2, no_ele_row 20, no_ele_col 2,
+    dx = dy = 0.1, u = (0.05, 0.05)); totele = 20 * 2 * 2, ntime = 100, the pulse of transport_tri.F90:457-460."""
+    out = run_host("--mode", 2)
+    m = re.search(r"tnew: sum ([-+0-9.e]+) min ([-+0-9.e]+) max ([-+0-9.e]+)", out)
+    assert m and "totele = 80" in out and "ntime = 100" in out, out
+    ner, nec = 20, 2
+    mesh = pamg.Mesh.structured_tri(ner, 2 * nec, 0.1, 0.1)
+    T = np.zeros((mesh.U, 3))
+    T[0:ner // 5 + 1] = 1.0
+    for i in range(2, nec + 1):
+        T[(i - 1) * ner: ner * i - (ner * 4 // 5)] = 1.0
+    orc.lib().orc_unstr_explicit(mesh.U, mesh.X, mesh.neig, mesh.fneig, mesh.dir, 0.05, 0.05, 0.7 * 0.1, 100, 2, 10, 0, 0, 0.0, T)
+    assert abs(float(m.group(1)) - T.sum()) <= 1e-9 * abs(T.sum())
+    assert abs(float(m.group(2)) - T.min()) <= 1e-6 and abs(float(m.group(3)) - T.max()) <= 1e-6
+
+
+def test_mode5_unstr_implicit_literal_arguments(tmp_path):
+    """pamg_host --mode 5 = case(5) of main.F90:31 on Mesh_files/gmsh_100.msh: dt = 0.7 * 0.1, ntime = 2, nits = 2,
+    u = (-0.1, 0.1), tnew(:,5) = 1; the dense FINDInv solve of the reference (oracle) against the Krylov solve on the device."""
+    path = write_msh("gmsh_100", str(tmp_path / "gmsh_100.msh"))
+    out = run_host("--mode", 5, "--mesh", path)
+    m = re.search(r"tnew: sum ([-+0-9.e]+) min ([-+0-9.e]+) max ([-+0-9.e]+)", out)
+    assert m and "ntime = 2" in out, out
+    mesh = pamg.Mesh.read_msh(path)
+    T = np.zeros((mesh.U, 3))
+    T[4] = 1.0
+    assert orc.lib().orc_unstr_implicit(mesh.U, mesh.X, mesh.neig, mesh.fneig, -0.1, 0.1, 0.07, 2, 2, 0, T) == 0
+    assert abs(float(m.group(1)) - T.sum()) <= 1e-9 * abs(T.sum())
+    assert abs(float(m.group(2)) - T.min()) <= 1e-6 and abs(float(m.group(3)) - T.max()) <= 1e-6
+    it = re.search(r"Krylov iterations (\d+)  worst \|\|r\|\|/\|\|b\|\| ([0-9.e+-]+)", out)
+    assert it and float(it.group(2)) <= 1e-12, out
 
 
 def test_mode1_trans_rec_writes_the_reference_dumps(tmp_path):
