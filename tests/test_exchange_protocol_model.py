@@ -98,12 +98,17 @@ def shipped_programs(max_len):
     def grow(p, pending):
         if len(p) >= max_len:
             out.append(p); return
+        # "XHH": told changed (or update_overlaps as written was called): the told values of the cut faces are exchanged by a
+        # k_halo launch of their own, which leaves nothing to unpack, and a second one exchanges the tnew values
+        # (exchange_told_cut + ensure_strips, theta != 1; launch_halo what = 0)
         if pending:                       # a sweep has sent: unpack, or the field changes and k_halo exchanges afresh
             grow(p + "U", False)
             grow(p + "XH", False)
+            grow(p + "XHH", False)
         else:
             grow(p + "W", True)
             grow(p + "XH", False)
+            grow(p + "XHH", False)
     grow("H", False)
     return sorted(set(out))
 
