@@ -20,7 +20,10 @@
  * ANALYTIC identities that any correct implementation of the discretisation must satisfy: the operator,
  * the implicit matrix and the explicit step applied to a continuous linear field have closed forms
  * (tests/test_oracle_operator_consistency.py, tests/test_oracle_solver_properties.py), the direct
- * solution of the assembled system is the fixed point of the smoothers and the limit of the V-cycles.
+ * solution of the assembled system is the fixed point of the smoothers and the limit of the V-cycles; every entry
+ * of the level-1 matrix and right-hand side equals an independent exact-integration assembly in numpy that sees only
+ * the child coordinates (tests/test_oracle_independent_assembly.py); the theta != 1 branches converge to the exact
+ * semi-discrete solution with the order of theta (tests/test_oracle_theta.py).
  *
  * Every function cites the reference file:line it follows.  Two behaviours exist
  * where the reference is work-in-progress:

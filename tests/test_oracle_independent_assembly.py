@@ -1,0 +1,163 @@
+"""The oracle's level-1 operator and right-hand side against an INDEPENDENT assembly (CPU only).
+
+The oracle restates the reference's Gauss-point / stencil-array code (shape-function tables, per-parent scaling, closed-form
+neighbour tables, halo strips with reversal rules and node maps).  Here the same discretisation is assembled a second time in
+numpy from nothing but the coordinates of the child triangles, with exact integrals of P1 functions instead of quadrature and
+neighbours found geometrically by shared edges:
+
+    A = M/dt - S + F_up + K + P            b = M told/dt + M src + Dirichlet data
+    M_ij = |K|/12 (1 + delta_ij)           S_ij = (grad phi_i . u) |K|/3          K_ij = k |K| grad phi_i . grad phi_j
+    F_up : (n.u) int_f phi_i T_upwind      P : (k/d) int_f phi_i (T - T_neighbour)       int_f phi_a phi_b = L/6 (1 + delta_ab)
+
+with the reference's penalty length d (matrices.F90:101-109, get_d_center Msh2Tri.F90:349-385): distance of the child
+centroids inside a parent, distance of the PARENT centroids / 2^n across parent faces, parent centroid -> edge midpoint / 2^n
+on the domain boundary (for children of congruent splittings the first two coincide: the centroids of the two children that
+meet across a parent face differ by a sixth of the difference of the parents' apexes).  Every entry of the matrix the oracle
+yields through residual evaluations must agree: this pins the shape tables, the level scaling, the numbering and neighbour tables, the halo strips, both reversal rules and the node maps
+of the triangle multigrid path - for which the reference ships no output to compare with."""
+import numpy as np
+import pytest
+
+import oracle_api as orc
+from helpers import child_coordinates, write_msh
+
+
+def oracle_problem(name, n, rule, tmp_path, u, k, dt):
+    m = orc.read_msh(write_msh(name, str(tmp_path / (name + ".msh"))))
+    fneig, _ = orc.neig_data(m["neig"], m["dir"])
+    p = orc.intended_params(n, 1, dt=dt, k=k, u=u)
+    p.halo_rule = rule
+    return m, orc.Semi(p, m["X"], m["neig"], fneig, m["dir"])
+
+
+def oracle_matrix(o):
+    sh = o.field(orc.TNEW).shape
+    N = int(np.prod(sh))
+
+    def resid(x):
+        o.field(orc.TNEW)[:] = x.reshape(sh); o.field(orc.TNONLIN)[:] = x.reshape(sh); o.field(orc.TOLD)[:] = 0.0
+        o.update_overlaps(1)
+        o.residual(1)
+        return o.field(orc.RES).reshape(-1).copy()
+    b = resid(np.zeros(N))
+    A = np.zeros((N, N))
+    for j in range(N):
+        e = np.zeros(N); e[j] = 1.0
+        A[:, j] = b - resid(e)
+    return A, b
+
+
+def key(p):
+    return (round(float(p[0]) * 1e9), round(float(p[1]) * 1e9))
+
+
+def independent_assembly(Xparents, xy, n, u, k, dt, source_coef):
+    """xy: (U, C, 3, 2) child vertex coordinates.  Returns A (N x N), b (N) in the DOF order (parent, child, node)."""
+    U, C = xy.shape[0], xy.shape[1]
+    E = U * C
+    tri = xy.reshape(E, 3, 2)
+    parent_of = np.repeat(np.arange(U), C)
+    pc = Xparents.mean(axis=1)                                   # parent centroids
+    cc = tri.mean(axis=1)                                        # child centroids
+    u = np.asarray(u, float)
+    # edges -> the (element, local nodes) that share them
+    edges = {}
+    for e in range(E):
+        for a, b in ((0, 1), (1, 2), (2, 0)):
+            ka, kb = key(tri[e, a]), key(tri[e, b])
+            edges.setdefault((min(ka, kb), max(ka, kb)), []).append((e, a, b))
+    N = 3 * E
+    A = np.zeros((N, N)); rhs = np.zeros(N)
+    for e in range(E):
+        x = tri[e]
+        d = np.array([[x[1, 1] - x[2, 1], x[2, 0] - x[1, 0]], [x[2, 1] - x[0, 1], x[0, 0] - x[2, 0]], [x[0, 1] - x[1, 1], x[1, 0] - x[0, 0]]])
+        det = (x[1, 0] - x[0, 0]) * (x[2, 1] - x[0, 1]) - (x[2, 0] - x[0, 0]) * (x[1, 1] - x[0, 1])
+        grad = d / det                                           # grad phi_i (constant)
+        area = 0.5 * abs(det)
+        M = area / 12.0 * (np.ones((3, 3)) + np.eye(3))
+        rows = slice(3 * e, 3 * e + 3)
+        blk = M / dt + k * area * grad @ grad.T
+        blk -= np.outer(grad @ u, np.ones(3)) * area / 3.0       # - int (grad phi_i . u) phi_j
+        A[rows, rows] += blk
+        rhs[rows] += M @ (source_coef * np.sin(x[:, 0] + x[:, 1]))
+    for (ka, kb), owners in edges.items():
+        for (e, a, b) in owners:
+            x = tri[e]
+            L = np.linalg.norm(x[b] - x[a])
+            t = (x[b] - x[a]) / L
+            nrm = np.array([t[1], -t[0]])
+            mid = 0.5 * (x[a] + x[b])
+            if nrm @ (mid - cc[e]) < 0:
+                nrm = -nrm
+            un = float(nrm @ u)
+            inflow = un < 0.0
+            fm = L / 6.0 * np.array([[2.0, 1.0], [1.0, 2.0]])    # int_f phi_p phi_q over my face nodes (a, b)
+            mine = [3 * e + a, 3 * e + b]
+            others = [o for o in owners if o[0] != e]
+            P = parent_of[e]
+            if others:
+                e2, a2, b2 = others[0]
+                # the neighbour's local nodes coincident with my a and b
+                na, nb = (a2, b2) if key(tri[e2, a2]) == key(x[a]) else (b2, a2)
+                theirs = [3 * e2 + na, 3 * e2 + nb]
+                Q = parent_of[e2]
+                dist = np.linalg.norm(cc[e] - cc[e2]) if Q == P else np.linalg.norm(pc[P] - pc[Q]) / 2 ** n
+                pen = k / dist
+                for i in range(2):
+                    for j in range(2):
+                        A[mine[i], mine[j]] += pen * fm[i, j]
+                        A[mine[i], theirs[j]] -= pen * fm[i, j]
+                        if inflow:
+                            A[mine[i], theirs[j]] += un * fm[i, j]
+                        else:
+                            A[mine[i], mine[j]] += un * fm[i, j]
+            else:
+                # domain boundary: Dirichlet data sin(x+y) at the two face nodes; length = parent centroid -> midpoint of the
+                # parent edge that carries this face, / 2^n
+                Xp = Xparents[P]
+                best = None
+                for s0, s1 in ((0, 1), (1, 2), (2, 0)):
+                    w = Xp[s1] - Xp[s0]
+                    off = abs(w[0] * (mid[1] - Xp[s0, 1]) - w[1] * (mid[0] - Xp[s0, 0])) / np.linalg.norm(w)
+                    if best is None or off < best[0]:
+                        best = (off, 0.5 * (Xp[s0] + Xp[s1]))
+                assert best[0] < 1e-9
+                pen = k / (np.linalg.norm(pc[P] - best[1]) / 2 ** n)
+                g = np.sin(np.array([x[a, 0] + x[a, 1], x[b, 0] + x[b, 1]]))
+                for i in range(2):
+                    for j in range(2):
+                        A[mine[i], mine[j]] += pen * fm[i, j]
+                        rhs[mine[i]] += pen * fm[i, j] * g[j]
+                        if inflow:
+                            rhs[mine[i]] -= un * fm[i, j] * g[j]
+                        else:
+                            A[mine[i], mine[j]] += un * fm[i, j]
+    return A, rhs
+
+
+CASES = [("test_sn2", 1), ("test_sn2", 2), ("irregular", 2), ("split1", 1), ("2_unele_test", 3), ("split0", 3)]
+
+
+@pytest.mark.parametrize("name,n", CASES)
+@pytest.mark.parametrize("rule", [0, 1])
+def test_oracle_operator_equals_an_independent_exact_integration_assembly(name, n, rule, tmp_path):
+    u, k, dt = (0.6, -0.35), 0.7, 2e-2
+    m, o = oracle_problem(name, n, rule, tmp_path, u, k, dt)
+    Ao, bo = oracle_matrix(o)
+    xy = child_coordinates(orc, m["X"], n)
+    Ai, bi = independent_assembly(m["X"], xy, n, u, k, dt, o.params.source_coef)
+    scale = np.abs(Ao).max()
+    assert np.abs(Ao - Ai).max() <= 1e-10 * scale
+    assert np.abs(bo - bi).max() <= 1e-10 * max(np.abs(bo).max(), scale * 1e-3)
+    # the couplings are where the independent neighbour search says they are, nowhere else
+    assert np.array_equal(np.abs(Ao) > 1e-12 * scale, np.abs(Ai) > 1e-12 * scale)
+
+
+def test_pure_advection_and_pure_diffusion_limits(tmp_path):
+    for u, k in (((0.9, 0.3), 0.0), ((0.0, 0.0), 1.0), ((-0.2, -0.8), 1e-3)):
+        m, o = oracle_problem("test_sn2", 2, 1, tmp_path, u, k, 1e-2)
+        Ao, bo = oracle_matrix(o)
+        Ai, bi = independent_assembly(m["X"], child_coordinates(orc, m["X"], 2), 2, u, k, 1e-2, o.params.source_coef)
+        scale = np.abs(Ao).max()
+        assert np.abs(Ao - Ai).max() <= 1e-10 * scale, (u, k)
+        assert np.abs(bo - bi).max() <= 1e-10 * max(np.abs(bo).max(), scale * 1e-3), (u, k)
