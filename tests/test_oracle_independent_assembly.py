@@ -161,3 +161,53 @@ def test_pure_advection_and_pure_diffusion_limits(tmp_path):
         scale = np.abs(Ao).max()
         assert np.abs(Ao - Ai).max() <= 1e-10 * scale, (u, k)
         assert np.abs(bo - bi).max() <= 1e-10 * max(np.abs(bo).max(), scale * 1e-3), (u, k)
+
+
+@pytest.mark.parametrize("name,n,level", [("test_sn2", 3, 2), ("test_sn2", 3, 3), ("irregular", 3, 2), ("split0", 4, 3)])
+def test_coarse_level_operators_are_the_same_discretisation_on_the_coarser_children(name, n, level, tmp_path):
+    """level l of the hierarchy (split s = n - l + 1, semi_tri_det_nlx_multigrid / semi_det_snlx_multigrid scaling,
+    ShapFun.F90:1661-1684,1737-1783, level-aware penalty length) against the independent assembly on the children of split s;
+    homogeneous Dirichlet data on the error equation (coarse_bc_zero)."""
+    u, k, dt = (0.6, -0.35), 0.7, 2e-2
+    m = orc.read_msh(write_msh(name, str(tmp_path / (name + ".msh"))))
+    fneig, _ = orc.neig_data(m["neig"], m["dir"])
+    p = orc.intended_params(n, level, dt=dt, k=k, u=u)
+    o = orc.Semi(p, m["X"], m["neig"], fneig, m["dir"])
+    sh = o.field(orc.TNEW, level).shape
+    N = int(np.prod(sh))
+    o.field(orc.RHS, level)[:] = 0.0
+
+    def resid(x):
+        o.field(orc.TNEW, level)[:] = x.reshape(sh); o.field(orc.TNONLIN, level)[:] = x.reshape(sh)
+        o.update_overlaps(level)
+        o.residual(level)
+        return o.field(orc.RES, level).reshape(-1).copy()
+    b = resid(np.zeros(N))
+    assert np.abs(b).max() == 0.0                                  # no data on the error equation
+    Ao = np.zeros((N, N))
+    for j in range(N):
+        e = np.zeros(N); e[j] = 1.0
+        Ao[:, j] = -resid(e)
+    s = n - level + 1
+    Ai, _ = independent_assembly(m["X"], child_coordinates(orc, m["X"], s), s, u, k, dt, 0.0)
+    assert np.abs(Ao - Ai).max() <= 1e-10 * np.abs(Ao).max()
+
+
+@pytest.mark.parametrize("name", ["gmsh_100", "irregular", "test_sn2", "untitled8"])
+@pytest.mark.parametrize("k", [0.0, 0.4])
+def test_unstructured_implicit_matrix_equals_the_independent_assembly(name, k, tmp_path):
+    """unstr_implicit's Jacobian (transport_tri_unstr.F90:270-364, with the geometric node pairing `use_dir` and the diffusion
+    blocks of the iterative path): every element its own parent; homogeneous inflow data (t_bc = 0, :127)."""
+    u, dt = (-0.1, 0.1), 0.07
+    m = orc.read_msh(write_msh(name, str(tmp_path / (name + ".msh"))))
+    fneig, _ = orc.neig_data(m["neig"], m["dir"])
+    E = m["X"].shape[0]
+    N = 3 * E
+    A = np.zeros((N, N)); M = np.zeros((N, N))
+    orc.lib().orc_unstr_implicit_assemble_diff(E, np.ascontiguousarray(m["X"]), np.ascontiguousarray(m["neig"]), fneig,
+                                               u[0], u[1], k, dt, 1, A, M)
+    Ai, _ = independent_assembly(m["X"], m["X"][:, None, :, :], 0, u, k, dt, 0.0)
+    assert np.abs(A - Ai).max() <= 1e-10 * np.abs(A).max()
+    # and the mass matrix handed out beside it
+    Mi, _ = independent_assembly(m["X"], m["X"][:, None, :, :], 0, (0.0, 0.0), 0.0, dt, 0.0)
+    assert np.abs(M - Mi).max() <= 1e-12 * np.abs(M).max()
