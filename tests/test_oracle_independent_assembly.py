@@ -211,3 +211,96 @@ def test_unstructured_implicit_matrix_equals_the_independent_assembly(name, k, t
     # and the mass matrix handed out beside it
     Mi, _ = independent_assembly(m["X"], m["X"][:, None, :, :], 0, (0.0, 0.0), 0.0, dt, 0.0)
     assert np.abs(M - Mi).max() <= 1e-12 * np.abs(M).max()
+
+
+@pytest.mark.parametrize("name", ["gmsh_100", "irregular", "untitled8"])
+@pytest.mark.parametrize("exact", [1, 0])
+def test_unstructured_explicit_step_equals_independent_time_stepping(name, exact, tmp_path):
+    """unstr_explicit (transport_tri_unstr.F90:588-795, geometric node pairing): per nonlinear pass
+    T <- M^-1 (M told + dt rhs(T)) with rhs(T) = -(A_adv - M/dt) T from the independent assembly; the local solve is FINDInv
+    (exact) or njac_its Jacobi iterations on the lumped mass starting from the current iterate (:770-790)."""
+    u, dt, ntime, nits, njac = (0.9, -0.2), 0.004, 2, 2, 10
+    m = orc.read_msh(write_msh(name, str(tmp_path / (name + ".msh"))))
+    fneig, _ = orc.neig_data(m["neig"], m["dir"])
+    E = m["X"].shape[0]
+    rng = np.random.Generator(np.random.MT19937(12))
+    T0 = rng.random((E, 3))
+    got = T0.copy()
+    orc.lib().orc_unstr_explicit(E, np.ascontiguousarray(m["X"]), np.ascontiguousarray(m["neig"]), fneig,
+                                 np.ascontiguousarray(m["dir"]), u[0], u[1], dt, ntime, nits, njac, exact, 1, 0.0, got)
+    A, _ = independent_assembly(m["X"], m["X"][:, None, :, :], 0, u, 0.0, 1.0, 0.0)      # dt = 1: A = M + spatial operator
+    M, _ = independent_assembly(m["X"], m["X"][:, None, :, :], 0, (0.0, 0.0), 0.0, 1.0, 0.0)
+    Sp = A - M
+    ml = M.sum(axis=1)
+    T = T0.reshape(-1).copy()
+    for _ in range(ntime):
+        told = T.copy()
+        for _ in range(nits):
+            rj = M @ told - dt * (Sp @ T)
+            if exact:
+                T = np.linalg.solve(M, rj)
+            else:
+                x = T.copy()
+                for _ in range(njac):
+                    x = x + (rj - M @ x) / ml
+                T = x
+    assert np.abs(got.reshape(-1) - T).max() <= 1e-12 * np.abs(T).max()
+
+
+def smoother_ingredients(name, n, rule, tmp_path, u=(0.6, -0.35), k=0.7, dt=2e-2):
+    m, o = oracle_problem(name, n, rule, tmp_path, u, k, dt)
+    xy = child_coordinates(orc, m["X"], n)
+    A, b = independent_assembly(m["X"], xy, n, u, k, dt, o.params.source_coef)
+    A0, _ = independent_assembly(m["X"], xy, n, (0.0, 0.0), k, dt, 0.0)          # no advection: mass/dt + diffusion + penalty
+    Mdt, _ = independent_assembly(m["X"], xy, n, (0.0, 0.0), 0.0, dt, 0.0)
+    # get_diagonal (:481-486): LUMPED mass / dt + K_ii + sum_f my_diff_surf(i,i,f) - not diag(A)
+    D = Mdt.sum(axis=1) + (np.diag(A0) - np.diag(Mdt))
+    U, C = xy.shape[0], xy.shape[1]
+    # an "up" child is a scaled translate of its parent, a "down" child the point reflection of one
+    pcen = m["X"].mean(axis=1)
+    up = np.zeros((U, C), bool)
+    for p in range(U):
+        w = m["X"][p] - pcen[p]
+        for c in range(C):
+            v = (xy[p, c, 0] - xy[p, c].mean(axis=0)) * 2 ** n
+            up[p, c] = min(np.linalg.norm(v - w[j]) for j in range(3)) < 1e-9 * np.linalg.norm(w[0])
+    parent_of_dof = np.repeat(np.arange(U), 3 * C)
+    same = parent_of_dof[:, None] == parent_of_dof[None, :]
+    return o, A, b, D, np.repeat(up.reshape(-1), 3), same
+
+
+def set_iterate(o, x):
+    sh = o.field(orc.TNEW).shape
+    o.field(orc.TNONLIN)[:] = x.reshape(sh); o.field(orc.TNEW)[:] = x.reshape(sh); o.field(orc.TOLD)[:] = 0.0
+
+
+@pytest.mark.parametrize("name,n", [("test_sn2", 2), ("irregular", 2), ("split0", 3)])
+def test_sweeps_are_the_textbook_iterations_on_the_independent_matrix(name, n, tmp_path):
+    """solve_Jacobi / solve_Gauss_Seidel (transport_tri_semi.F90:491-507) with get_diagonal's D: one Jacobi sweep, the
+    reference's element-sequential Gauss-Seidel sweep (values across parents lagged through t_overlap, :647-655) and the
+    two-colour ordering of it that the GPU runs - each replayed with the independently assembled A, b, D."""
+    o, A, b, D, up_dof, same = smoother_ingredients(name, n, 1, tmp_path)
+    w = o.params.omega
+    N = A.shape[0]
+    x0 = np.random.Generator(np.random.MT19937(3)).random(N)
+    A_same, A_cross = np.where(same, A, 0.0), np.where(same, 0.0, A)
+    # Jacobi
+    set_iterate(o, x0); o.smooth(1, 1, 1)
+    want = x0 + w / D * (b - A @ x0)
+    assert np.abs(o.field(orc.TNONLIN).reshape(-1) - want).max() <= 1e-12 * np.abs(want).max()
+    # two-colour Gauss-Seidel: down children, then up children with the new down values of their own parent
+    set_iterate(o, x0); o.smooth(1, 4, 1)
+    x1 = x0.copy()
+    r = b - A @ x0
+    x1[~up_dof] += (w / D * r)[~up_dof]
+    r = b - A_same @ x1 - A_cross @ x0
+    x1[up_dof] += (w / D * r)[up_dof]
+    assert np.abs(o.field(orc.TNONLIN).reshape(-1) - x1).max() <= 1e-12 * np.abs(x1).max()
+    # the reference's order: parent-major, child-minor, the three nodes of a child simultaneously
+    set_iterate(o, x0); o.smooth(1, 3, 1)
+    x = x0.copy()
+    cross = A_cross @ x0
+    for e in range(N // 3):
+        rows = slice(3 * e, 3 * e + 3)
+        x[rows] = x[rows] + w / D[rows] * (b[rows] - A_same[rows] @ x - cross[rows])
+    assert np.abs(o.field(orc.TNONLIN).reshape(-1) - x).max() <= 1e-12 * np.abs(x).max()
