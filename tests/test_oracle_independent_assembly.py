@@ -378,3 +378,29 @@ def test_vcycle_is_the_textbook_cycle_on_independent_operators(name, n, levels, 
     assert np.allclose(hist[: cycles + 1], want, rtol=1e-9, atol=0.0)
     assert want[-1] < 0.5 * want[0]                                   # and it is a contraction
     assert np.abs(o.field(orc.TNONLIN).reshape(-1) - x).max() <= 1e-10 * np.abs(x).max()
+
+
+@pytest.mark.parametrize("theta", [0.5, 0.0])
+def test_theta_scheme_on_the_independent_matrix(theta, tmp_path):
+    """get_A_x / get_RHS with theta != 1 (:441-446,457-460): A_theta = M/dt + theta Abar and
+    b_theta = M told/dt + M src - (1 - theta) Abar told - (Dirichlet data, weight theta + (1 - theta) = 1)."""
+    name, n, u, k, dt = "irregular", 2, (0.6, -0.35), 0.7, 2e-2
+    m = orc.read_msh(write_msh(name, str(tmp_path / (name + ".msh"))))
+    fneig, _ = orc.neig_data(m["neig"], m["dir"])
+    p = orc.intended_params(n, 1, dt=dt, k=k, u=u)
+    p.theta = theta
+    o = orc.Semi(p, m["X"], m["neig"], fneig, m["dir"])
+    xy = child_coordinates(orc, m["X"], n)
+    A, b = independent_assembly(m["X"], xy, n, u, k, dt, p.source_coef)
+    Mdt, _ = independent_assembly(m["X"], xy, n, (0.0, 0.0), 0.0, dt, 0.0)
+    Abar = A - Mdt
+    sh = o.field(orc.TNEW).shape
+    N = A.shape[0]
+    rng = np.random.Generator(np.random.MT19937(4))
+    x, told = rng.random(N), rng.random(N)
+    o.field(orc.TNEW)[:] = x.reshape(sh); o.field(orc.TNONLIN)[:] = x.reshape(sh); o.field(orc.TOLD)[:] = told.reshape(sh)
+    o.update_overlaps(1)
+    o.residual(1)
+    got = o.field(orc.RES).reshape(-1)
+    want = (b + Mdt @ told - (1.0 - theta) * (Abar @ told)) - (Mdt + theta * Abar) @ x
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
