@@ -1509,7 +1509,8 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
     if (il == 0 && h->p.theta != 1.0 && h->level_offset == 0) {
       // old-time operator of get_RHS (:459-460), applied to TOLD when the level-1 right-hand side is built
       for (int u = 0; u < U; ++u)
-        parent_coefficients(h->p, X, neig, bc_glob, first + u, L.s, &pc[(size_t)u * NPC], 1.0 - h->p.theta, false);
+        if (!parent_coefficients(h->p, X, neig, bc_glob, first + u, L.s, &pc[(size_t)u * NPC], 1.0 - h->p.theta, false))
+          return fail(h, PAMG_ERR_UNSUPPORTED, "open boundary face (kind 2) with inflow: give it Dirichlet data instead");
       CK(cudaMalloc(&L.pc_old, pc.size() * sizeof(double)));
       CK(cudaMemcpy(L.pc_old, pc.data(), pc.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
