@@ -94,3 +94,109 @@ def test_literal_restrictor_and_prolongator_follow_the_geometry(name, n, tmp_pat
                 if source in ("interp", "corner3"):
                     total = new_total                             # corner@1 and corner@2 both read the centre child's totals
     assert np.abs(got - want).max() <= 1e-13
+
+
+def volume_blocks(tri, u, k, dt):
+    E = tri.shape[0]
+    A = np.zeros((E, 3, 3)); M = np.zeros((E, 3, 3)); K = np.zeros((E, 3))
+    for e in range(E):
+        x = tri[e]
+        d = np.array([[x[1, 1] - x[2, 1], x[2, 0] - x[1, 0]], [x[2, 1] - x[0, 1], x[0, 0] - x[2, 0]], [x[0, 1] - x[1, 1], x[1, 0] - x[0, 0]]])
+        det = (x[1, 0] - x[0, 0]) * (x[2, 1] - x[0, 1]) - (x[2, 0] - x[0, 0]) * (x[1, 1] - x[0, 1])
+        g = d / det
+        area = 0.5 * abs(det)
+        M[e] = area / 12.0 * (np.ones((3, 3)) + np.eye(3))
+        Kb = k * area * g @ g.T
+        K[e] = np.diag(Kb)
+        A[e] = M[e] / dt + Kb - np.outer(g @ np.asarray(u, float), np.ones(3)) * area / 3.0
+    return A, M, M.sum(axis=2) / dt + K
+
+
+@pytest.mark.parametrize("name,n,levels,u", [("test_sn2", 2, 2, (0.0, 0.0)), ("split1", 3, 3, (0.1, 0.1))])
+def test_literal_multilevel_time_step_replayed_from_the_fortran(name, n, levels, u, tmp_path):
+    """`do multigrid` as checked in (transport_tri_semi.F90:319-379) on several levels, face loop commented out: smoother,
+    restrictor (of the residual of the PREVIOUS pass: it runs before get_residual), get_residual with r = A x - b on
+    tracer%tnew, 15 smoother calls on the coarsest level, and on the way up tnew_nonlin <- tnew BEFORE the prolongator, so the
+    smoother's first `tnew = tnew_nonlin` (:550) overwrites the prolonged field - all of it replayed with per-child blocks and
+    the geometric transfers above."""
+    n_smooth, n_multigrid = 4, 2
+    m = orc.read_msh(write_msh(name, str(tmp_path / (name + ".msh"))))
+    fneig, _ = orc.neig_data(m["neig"], m["dir"])
+    p = orc.literal_params(n, levels, u=u)
+    o = orc.Semi(p, m["X"], m["neig"], fneig, m["dir"])
+    U = m["X"].shape[0]
+    xy = [child_coordinates(orc, m["X"], n - l) for l in range(levels)]
+    blk = [volume_blocks(x.reshape(-1, 3, 2), u, p.k, p.dt) for x in xy]
+    fam = [[families(xy[l + 1][q], xy[l][q]) for q in range(U)] for l in range(levels - 1)]
+    shape = [x.shape[:2] + (3,) for x in xy]
+    rng = np.random.Generator(np.random.MT19937(23))
+    T0 = rng.random(shape[0])
+    o.field(orc.TNEW, 1)[:] = T0
+    tri0 = xy[0].reshape(-1, 3, 2)
+    s = p.source_coef * np.sin(tri0[:, :, 0] + tri0[:, :, 1])
+    for i in range(3):
+        s[:, i] = np.einsum("ej,ej->e", blk[0][1][:, i, :], s)            # in-place M src (:455-456)
+    tnew = [np.zeros(sh) for sh in shape]; tnl = [np.zeros(sh) for sh in shape]
+    rhs = [np.zeros(sh) for sh in shape]; res = [np.zeros(sh) for sh in shape]
+    tnew[0] = T0.copy()
+
+    def smooth(l, count):
+        A, _, D = blk[l]
+        for _ in range(count):
+            tnew[l] = tnl[l].copy()
+            x = tnl[l].reshape(-1, 3)
+            tnl[l] = (x + p.omega / D * (rhs[l].reshape(-1, 3) - np.einsum("eij,ej->ei", A, x))).reshape(shape[l])
+
+    def restrict(l):
+        if l == levels - 1:
+            return
+        for q in range(U):
+            for c, (k1, k2, k3, _) in enumerate(fam[l][q]):
+                rhs[l + 1][q, c] = [res[l][q, k1].mean(), res[l][q, k2].mean(), res[l][q, k3].mean()]
+
+    def residual(l):
+        A = blk[l][0]
+        res[l] = (np.einsum("eij,ej->ei", A, tnew[l].reshape(-1, 3)) - rhs[l].reshape(-1, 3)).reshape(shape[l])   # :869
+
+    def prolong(l):
+        for q in range(U):
+            for c, (k1, k2, k3, kc) in enumerate(fam[l][q]):
+                X, cv = xy[l + 1][q, c], tnew[l + 1][q, c]
+                vertex = {key(X[j]): cv[j] for j in range(3)}
+                interp = {key(0.5 * (X[a] + X[b])): 0.5 * (cv[a] + cv[b]) for a, b in ((0, 1), (1, 2), (0, 2))}
+                mid12 = key(0.5 * (X[0] + X[1]))
+                total = {}
+                for kid, source in ((k3, "interp"), (kc, "corner3"), (k1, "centre"), (k2, "centre")):
+                    new_total = {}
+                    for i in range(3):
+                        kk = key(xy[l][q, kid, i])
+                        if kk in vertex:
+                            tnew[l][q, kid, i] += vertex[kk]
+                        elif source == "interp" or (source == "corner3" and kk == mid12):
+                            tnew[l][q, kid, i] += interp[kk]
+                        else:
+                            tnew[l][q, kid, i] += total[kk]
+                        new_total[kk] = tnew[l][q, kid, i]
+                    if source in ("interp", "corner3"):
+                        total = new_total
+
+    for step in range(2):
+        told = tnew[0].copy(); tnl[0] = tnew[0].copy()                      # :316-317
+        rhs[0] = (np.einsum("eij,ej->ei", blk[0][1], told.reshape(-1, 3)) / p.dt + s).reshape(shape[0])
+        for _ in range(n_multigrid):
+            for l in range(levels):
+                tnl[l] = tnew[l].copy()                                     # :327
+                smooth(l, n_smooth); restrict(l); residual(l)               # :331,336,338
+            tnl[levels - 1] = tnew[levels - 1].copy()                       # :348
+            for _ in range(15):
+                smooth(levels - 1, n_smooth)                                # :351-352
+            for l in range(levels - 2, -1, -1):
+                tnl[l] = tnew[l].copy()                                     # :367
+                prolong(l)                                                  # :370
+                smooth(l, n_smooth)                                         # :376
+        o.literal_timestep(solver=3, n_multigrid=n_multigrid, n_smooth=n_smooth)
+        for l in range(levels):
+            scale = max(1.0, np.abs(tnew[l]).max())
+            assert np.abs(o.field(orc.TNEW, l + 1) - tnew[l]).max() <= 1e-10 * scale, (step, l)
+            assert np.abs(o.field(orc.TNONLIN, l + 1) - tnl[l]).max() <= 1e-10 * scale, (step, l)
+            assert np.abs(o.field(orc.RES, l + 1) - res[l]).max() <= 1e-9 * max(1.0, np.abs(res[l]).max()), (step, l)
