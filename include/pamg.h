@@ -109,15 +109,15 @@ int pamg_set_parents_partition(pamg_handle* h, int U_global, const double* X, co
                                int my_part);
 /* Dirichlet data of the domain-boundary parent faces (Neig == 0), [U_global][3] in gmsh face order.  update_overlaps carries
  * a t_bc argument (splitting.F90:1210) that HEAD overwrites with boundary(x,y) = sin(x+y) (:1246-1252); this entry makes it
- * data: kind 0 = sin(x+y) (the default everywhere), 1 = the constant value[], 2 = open face (no data and no penalty term; only
- * for faces with n.u >= 0, else pamg_set_parents returns PAMG_ERR_UNSUPPORTED).  value may be NULL (zeros).  Must precede
+ * data: bc_kind 0 = sin(x+y) (the default everywhere), 1 = the constant bc_value[], 2 = open face (no data and no penalty term; only
+ * for faces with n.u >= 0, else pamg_set_parents returns PAMG_ERR_UNSUPPORTED).  bc_value may be NULL (zeros).  Must precede
  * pamg_set_parents / pamg_set_parents_partition. */
-int pamg_set_boundary_data(pamg_handle* h, int U_global, const int32_t* kind, const double* value);
+int pamg_set_boundary_data(pamg_handle* h, int U_global, const int32_t* bc_kind, const double* bc_value);
 int pamg_ndof(const pamg_handle* h, int level, int64_t* ndof);
 
 int pamg_upload_field(pamg_handle* h, int field, int level, const double* host);
 int pamg_download_field(pamg_handle* h, int field, int level, double* host);
-int pamg_fill_field(pamg_handle* h, int field, int level, double value);
+int pamg_fill_field(pamg_handle* h, int field, int level, double fill_value);
 int pamg_copy_field(pamg_handle* h, int level, int dst_field, int src_field);
 int pamg_download_overlap(pamg_handle* h, int level, int old, double* host /* [U][3][2**s][3] */);
 int pamg_device_ptr(pamg_handle* h, int field, int level, void** dptr); /* for zero-copy interop */

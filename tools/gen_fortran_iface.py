@@ -19,7 +19,7 @@ OUT = os.path.join(ROOT, "p-a_multigrids_b200", "host", "pamg_iface.F90")
 SCALAR_OUT = {"n", "U", "ndof", "l2", "linf", "conv", "cycles", "relres", "npeers", "peer_part", "nfaces", "iters_total",
               "ntime", "ms", "total_ms", "launches"}
 # array arguments the header documents as optional (NULL allowed): passed as type(c_ptr) so that c_null_ptr can be given
-NULLABLE = {"part_first", "region", "devices", "value", "val", "col", "diff_coe", "stab", "x_all", "analytical", "error",
+NULLABLE = {"part_first", "region", "devices", "bc_value", "val", "col", "diff_coe", "stab", "x_all", "analytical", "error",
             "Minv", "status", "rhs", "x", "hist", "strip_of", "dst_strip", "rev", "hmap", "peers", "counts", "X_out", "bc_kind"}
 NULLABLE_IN = {"pamg_mesh_get": {"X", "neig", "fneig", "dir", "region"},
                "pamg_halo_plan": {"part_first", "strip_of", "dst_strip", "rev", "hmap", "peers", "counts"},
@@ -27,7 +27,7 @@ NULLABLE_IN = {"pamg_mesh_get": {"X", "neig", "fneig", "dir", "region"},
                "pamg_apply_local_minv": {"rhs", "x", "Minv", "status"},
                "pamg_trans_rec": {"x_all"}, "pamg_create_multi": {"devices"},
                "pamg_set_parents_partition": {"part_first"}, "pamg_mesh_from_arrays": {"region"},
-               "pamg_set_boundary_data": {"value"}, "pamg_implicit_get_bsr": {"val", "col"},
+               "pamg_set_boundary_data": {"bc_value"}, "pamg_implicit_get_bsr": {"val", "col"},
                "pamg_unstr_stab": {"diff_coe", "stab"}, "pamg_output_fields": {"x_all", "analytical", "error"},
                "pamg_vcycle_solve": {"cycles", "hist"}, "pamg_residual": {"l2", "linf"},
                "pamg_timestep_host": {"cycles", "relres"}, "pamg_implicit_step": {"iters_total", "relres"},
