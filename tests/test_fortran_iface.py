@@ -64,3 +64,17 @@ def test_header_exports_match_the_library():
     for _, name, _ in funcs:
         assert hasattr(lib, name), name
     assert set(pamg.lib()._signatures) == {name for _, name, _ in funcs}
+
+
+def test_names_survive_fortran_case_insensitivity_and_attribute_keywords():
+    """Fortran folds case and shares one namespace per scope: no two dummies of an entry, and no two module-level names, may differ
+    by case only; a dummy called like the VALUE attribute would read `value :: value`."""
+    funcs, fields, defines, enums = gen.parse_header()
+    for ret, name, args in funcs:
+        low = [an.lower() for _, an in args]
+        assert len(set(low)) == len(low), name
+        assert name.lower() not in low and "value" not in low, name
+        assert all(len(an) <= 63 and not an.startswith("_") for an in low), name
+    scope = [k.lower() for k, _ in defines + enums] + [n.lower() for _, n, _ in funcs] + ["pamg_params"]
+    assert len(set(scope)) == len(scope)
+    assert not re.search(r"\bvalue\s*::\s*value\b", module_text())
