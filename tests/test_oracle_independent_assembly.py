@@ -404,3 +404,28 @@ def test_theta_scheme_on_the_independent_matrix(theta, tmp_path):
     got = o.field(orc.RES).reshape(-1)
     want = (b + Mdt @ told - (1.0 - theta) * (Abar @ told)) - (Mdt + theta * Abar) @ x
     assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("seed,npts", [(1, 8), (2, 14), (5, 20)])
+@pytest.mark.parametrize("rule", [0, 1])
+def test_operator_on_random_triangulations_with_mixed_orientation(seed, npts, rule, tmp_path):
+    """Delaunay triangulations of random points, half of the triangles flipped to clockwise: nothing like the regular shipped
+    meshes.  The literal Dir / Nside reversal table (splitting.F90:1256-1391) holds up as well as the geometric pairing."""
+    from scipy.spatial import Delaunay
+    from helpers import write_msh_triangles
+    rng = np.random.Generator(np.random.MT19937(seed))
+    pts = rng.random((npts, 2))
+    simplices = Delaunay(pts).simplices.copy()
+    flip = rng.random(len(simplices)) < 0.5
+    simplices[flip] = simplices[flip][:, [0, 2, 1]]
+    m = orc.read_msh(write_msh_triangles(pts[simplices], str(tmp_path / "rnd.msh")))
+    fneig, _ = orc.neig_data(m["neig"], m["dir"])
+    u, k, dt = (0.6, -0.35), 0.7, 2e-2
+    for n in (1, 2):
+        p = orc.intended_params(n, 1, dt=dt, k=k, u=u)
+        p.halo_rule = rule
+        o = orc.Semi(p, m["X"], m["neig"], fneig, m["dir"])
+        Ao, bo = oracle_matrix(o)
+        Ai, bi = independent_assembly(m["X"], child_coordinates(orc, m["X"], n), n, u, k, dt, p.source_coef)
+        assert np.abs(Ao - Ai).max() <= 1e-9 * np.abs(Ao).max()           # (sliver triangles: the penalty terms are large)
+        assert np.abs(bo - bi).max() <= 1e-9 * max(np.abs(bo).max(), 1e-3 * np.abs(Ao).max())
