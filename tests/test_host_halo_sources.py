@@ -76,3 +76,31 @@ def test_cut_faces_of_a_partition_keep_their_strips():
                 assert np.all(src[u - first, mf] >= 0) == local and (local or np.all(src[u - first, mf] == -1))
                 if local:                                                 # offsets are relative to the part's own field
                     assert src[u - first, mf].max() < (last - first) * 4 ** n * 3
+
+
+@pytest.mark.parametrize("seed,npts", [(2, 14), (7, 60)])
+@pytest.mark.parametrize("rule", [0, 1])
+def test_exterior_values_on_random_triangulations_with_mixed_orientation(seed, npts, rule):
+    from scipy.spatial import Delaunay
+    rng = np.random.Generator(np.random.MT19937(seed))
+    pts = rng.random((npts, 2))
+    simplices = Delaunay(pts).simplices.copy()
+    flip = rng.random(len(simplices)) < 0.5
+    simplices[flip] = simplices[flip][:, [0, 2, 1]]
+    m = pamg.Mesh.from_arrays(pts[simplices])
+    n = 2
+    S = 2 ** n
+    T = continuous_field(child_coordinates(orc, m.X, n))
+    flat = T.reshape(-1)
+    surf = np.zeros(3 * S, np.int32)
+    orc.lib().orc_surf_ele(n, surf)
+    surf = surf.reshape(3, S)
+    src = pamg.halo_sources(m, n, halo_rule=rule)
+    for u in range(m.U):
+        for mf in range(3):
+            if m.neig[u, mf] == 0:
+                continue
+            a, b = SIDE_FACE_NODES[mf]
+            own = T[u, surf[mf] - 1]
+            assert np.abs(flat[src[u, mf, :, 0]] - own[:, a]).max() <= 1e-12
+            assert np.abs(flat[src[u, mf, :, 1]] - own[:, b]).max() <= 1e-12

@@ -144,3 +144,25 @@ def test_parent_table_argument_errors(tmp_path):
     codes = {L.pamg_parent_table(C.byref(gp), mesh.U, mesh.X, mesh.neig, kind.ctypes.data_as(C.c_void_p), u, 1, 1.0, 1, out)
              for u in range(mesh.U)}
     assert codes == {pamg.OK, pamg.ERR_UNSUPPORTED}
+
+
+@pytest.mark.parametrize("seed,npts", [(1, 8), (5, 20)])
+@pytest.mark.parametrize("theta", [1.0, 0.5])
+def test_folded_table_on_random_triangulations_with_mixed_orientation(seed, npts, theta, tmp_path):
+    from scipy.spatial import Delaunay
+    rng = np.random.Generator(np.random.MT19937(seed))
+    pts = rng.random((npts, 2))
+    simplices = Delaunay(pts).simplices.copy()
+    flip = rng.random(len(simplices)) < 0.5
+    simplices[flip] = simplices[flip][:, [0, 2, 1]]
+    mesh = pamg.Mesh.from_arrays(pts[simplices])
+    n = 2
+    op = orc.intended_params(n, 1, dt=1e-2, k=0.05, u=(0.6, -0.3))
+    op.theta = theta
+    gp = pamg.default_params(n_split=n, multi_levels=1)
+    for f in ("face_terms", "literal_source", "transfer", "residual_sign", "halo_rule", "coarse_bc_zero",
+              "theta", "dt", "k", "omega", "u_x", "u_y", "source_coef"):
+        setattr(gp, f, getattr(op, f))
+    o = orc.Semi(op, mesh.X, mesh.neig, mesh.fneig, mesh.dir)
+    A, _ = matrix(o)
+    check_against_matrix(A, mesh, gp, n, theta, True)
